@@ -1,0 +1,52 @@
+"""Generate tests/golden/* from the REFERENCE's own code (container only: needs /root/reference
+and `make -C oracle ref`).  Committed outputs let the oracle be checked where the reference
+cannot travel.  Run:  python tests/golden/make_golden.py
+"""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import harness as H  # noqa: E402
+
+ROOT = H.ROOT
+
+
+def main():
+    subprocess.check_call(["make", "-C", H.ORACLE_DIR, "ref", "oracle"])
+    # 1. dSFMT-19937: compile the reference's rng/dsfmt_19937.c behind oracle/pin_dsfmt.c
+    exe = os.path.join(H.ORACLE_DIR, "_ref", "pin_dsfmt")
+    subprocess.check_call(["gcc", "-O2", "-msse2", "-w", "-I/root/reference/rng",
+                           os.path.join(H.ORACLE_DIR, "pin_dsfmt.c"), "-o", exe])
+    out = subprocess.check_output([exe, str(H.SEED), "1000"]).decode().split()
+    with open(os.path.join(HERE, "dsfmt19937_seed20121018.json"), "w") as f:
+        json.dump({"seed": H.SEED, "source": "reference rng/dsfmt_19937.c getCloseOpen",
+                   "close_open": [float(x) for x in out]}, f)
+    # 2. potrf factors of the seeded SPD inputs, from the reference's CPU {s,d,c,z}potrf
+    REF = H.CpuLib("ref")
+    for p in "sdcz":
+        d = {}
+        for uplo in "LU":
+            for n in (1, 5, 31, 32, 33, 100, 257):
+                A = H.spd_matrix(p, n, ld=n + 3)
+                assert REF.potrf(p, uplo, A) == 0
+                d["%s_%d" % (uplo, n)] = np.ascontiguousarray(H.tri(A, uplo))
+        np.savez_compressed(os.path.join(HERE, "potrf_%s.npz" % p), **d)
+    # 3. potri + logdet of the n=100 case (d only, both uplo)
+    d = {}
+    for uplo in "LU":
+        A = H.spd_matrix("d", 100)
+        REF.potrf("d", uplo, A)
+        d["logdet_" + uplo] = np.array(REF.logdet("d", A, A.strides[1] // 8 + 1, 100))
+        REF.potri("d", uplo, A)
+        d["potri_" + uplo] = np.ascontiguousarray(H.tri(A, uplo))
+    np.savez_compressed(os.path.join(HERE, "potri_logdet_d.npz"), **d)
+    print("golden written to", HERE)
+
+
+if __name__ == "__main__":
+    main()
