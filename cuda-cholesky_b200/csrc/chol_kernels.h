@@ -1,0 +1,80 @@
+/*
+ * chol_kernels.h — the thin C-ABI between the C host code (cuda-cholesky_b200/host/*.c) and the
+ * hand-written sm_100a kernels (cuda-cholesky_b200/csrc/*.cu).  Plain C: pointers, sizes and
+ * chars only.  Every launcher is asynchronous on `stream` (a CUstream / cudaStream_t) and
+ * returns a cudaError_t value as int (0 = success).
+ *
+ * Conventions (same as the reference's BLAS, include/blas.h:24-27): column-major, leading
+ * dimensions in elements, enum arguments are the reference's char values.
+ */
+#ifndef CHOL_KERNELS_H
+#define CHOL_KERNELS_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- the GEMM engine: D = alpha * op(A) * op(B) + beta * C  (+ triangle / Hermitian options) ----
+ * One descriptor serves GEMM, SYRK/HERK (cuplo), TRMM (triA/triB masks) and the inverse-based
+ * panel solves.  prec 'd'/'z' run on FP64 DMMA tensor-core tiles, 's'/'c' on FP32 FFMA tiles.  */
+typedef struct chol_gemm_desc {
+  int prec;             /* 's','d','c','z' */
+  int opA, opB;         /* 'N','T','C': how the stored operand enters the product */
+  int triA, triB;       /* 0, 'L' or 'U': stored operand is triangular; the other triangle is
+                           never read and counts as zero */
+  int unitA, unitB;     /* nonzero: triangular operand has an implicit unit diagonal */
+  int cuplo;            /* 0 = all of D; 'L'/'U' = only that triangle of C is read and of D written */
+  int herm;             /* nonzero: force Im(diag(D)) = 0 (HERK, blas/zherk.c:108) */
+  size_t m, n, k;       /* D is m x n, inner dimension k */
+  double alpha[2];      /* (re, im); real precisions use [0] */
+  double beta[2];
+  const void *A; size_t lda;
+  const void *B; size_t ldb;
+  const void *C; size_t ldc;   /* may equal D */
+  void *D; size_t ldd;
+  void *stream;
+  int force_generic;    /* test hook: never take the TMA-fed path */
+} chol_gemm_desc;
+
+int chol_gemm_launch(const chol_gemm_desc *d);
+/* 1 if the descriptor would take the TMA (cp.async.bulk) operand path, 0 for the generic loader */
+int chol_gemm_uses_tma(const chol_gemm_desc *d);
+
+/* ---- diagonal-block kernels: one CTA, block staged in shared memory (n <= CHOL_DIAG_MAX) ---- */
+#define CHOL_DIAG_MAX 128
+int chol_diag_max(int prec); /* largest n the one-CTA diagonal kernels accept: 128 (s,d,c), 64 (z) */
+/* Cholesky of an n x n diagonal block in place.  *dinfo (device long) is set to
+ * info_base + failing column (1-based) if it is still 0 and a pivot is <= 0 or NaN; when
+ * *dinfo != 0 on entry the kernel does nothing (lapack/dpotrf.c:70-73 semantics). */
+int chol_potf2_launch(int prec, int uplo, size_t n, void *A, size_t lda, long *dinfo, long info_base, void *stream);
+/* inverse of an n x n triangular block, out of place (B may equal A).  Only the uplo triangle of
+ * B is written; if zero_other != 0 the opposite triangle of B is set to zero as well.  Zero pivot
+ * -> *dinfo = info_base + column (1-based) when *dinfo == 0 (lapack/dtrtri.c:49-52). */
+int chol_trti2_launch(int prec, int uplo, int diag, size_t n, const void *A, size_t lda, void *B, size_t ldb,
+                      int zero_other, long *dinfo, long info_base, void *stream);
+/* A := U*U^H (upper) or L^H*L (lower) of an n x n triangular block in place (lapack/dlauum.c:43-69) */
+int chol_lauu2_launch(int prec, int uplo, size_t n, void *A, size_t lda, void *stream);
+
+/* ---- data movement helpers ---- */
+/* B(m x n) := A(m x n), or B(n x m) := A^T / A^H when trans is 'T' / 'C'.  uplo 0 = all;
+ * 'L'/'U' = only that triangle of the SOURCE is copied (to the corresponding destination slot),
+ * 'l'/'u' = the same without the diagonal. */
+int chol_copy_launch(int prec, int trans, int uplo, size_t m, size_t n, const void *A, size_t lda, void *B,
+                     size_t ldb, void *stream);
+/* A(m x n) := value on the chosen part: uplo 0 all, 'L' strictly-lower, 'U' strictly-upper */
+int chol_fill_launch(int prec, int uplo, size_t m, size_t n, double re, double im, void *A, size_t lda, void *stream);
+
+/* ---- logdet: *dresult (device REAL) = 2 * sum_i log(Re x[i*incx]); one kernel, no host sync ---- */
+int chol_logdet_launch(int prec, const void *x, size_t incx, size_t n, void *dresult, void *dscratch, void *stream);
+size_t chol_logdet_scratch_bytes(void);
+
+/* ---- measurement probes (used by bench.py / profiles, not by the library path) ---- */
+/* kind 0: DMMA m8n8k4 only; 1: DFMA only; 2: both interleaved.  Returns achieved TFLOP/s. */
+int chol_probe_fp64(int kind, int iters, double *tflops, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,191 @@
+// gemm_ffma.cu — the FP32 GEMM engine (s and c) for sm_100a: FFMA register tiles.
+//
+// Same descriptor, scheduler and operand semantics as the FP64 DMMA engine (gemm_dmma.cu); it is
+// what cuSgemm2/cuCgemm2, cuSsyrk/cuCherk, cuStrmm2/cuCtrmm2 and the s/c LAPACK drivers run on
+// (reference: blas/sgemm.c:148, cgemm.c:226, ssyrk.c:163, cherk.c:190).  north_star allows "FP32
+// FFMA or a 3xTF32 split" for s/c; this is the FFMA choice: exact FP32 products, FP32 accumulate,
+// so the s/c tolerance is the plain FP32 one.
+//   * CTA tile 128x128 (s) / 64x64 (c), BK = 8, 256 threads, 8x8 (s) / 4x4-complex (c) register
+//     tile per thread, operands in shared memory as [k][m] / [k][n], 128-bit shared loads;
+//   * global -> register -> shared double buffering, one __syncthreads per k-tile;
+//   * any transpose / conjugate / triangular mask handled by the loader, k-ranges that are
+//     structurally zero are skipped, triangular (cuplo) grids launch only the needed tiles.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "chol_kernels.h"
+#include "gemm_common.cuh"
+
+namespace chol {
+
+template <typename T>
+struct FCfg {
+  static constexpr bool CPLX = ScalarOf<T>::cplx;
+  static constexpr int VW = 16 / sizeof(T);  // elements per 128-bit access: 4 (float) / 2 (float2)
+  static constexpr int TM = 2 * VW, TN = 2 * VW;
+  static constexpr int BM = 16 * TM, BN = 16 * TN;  // 128 / 64
+  static constexpr int BK = 8;
+  static constexpr int LDS = BM + VW;  // padded pitch (elements); keeps 16-byte alignment
+  static constexpr int THREADS = 256;
+  static constexpr int LPT = BM * BK / THREADS;  // loads per thread per operand tile
+};
+
+template <typename T>
+struct FArgs {
+  const T *A, *B, *C;
+  T *D;
+  long long lda, ldb, ldc, ldd;
+  int M, N, K;
+  T alpha, beta;
+  int opA, opB, triA, triB, unitA, unitB, cuplo, herm, NI, NJ, vec_ok, beta_zero;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256, 2) gemm_ffma_kernel(const FArgs<T> p) {
+  using Cfg = FCfg<T>;
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, LDS = Cfg::LDS, VW = Cfg::VW, TM = Cfg::TM, TN = Cfg::TN, LPT = Cfg::LPT;
+  __shared__ __align__(16) T As[2][BK * LDS];
+  __shared__ __align__(16) T Bs[2][BK * LDS];
+
+  int bi, bj;
+  if (!tile_coords<1, 8>(p.cuplo, p.NI, p.NJ, (long long)blockIdx.x, bi, bj)) return;
+  const int m0 = bi * BM, n0 = bj * BN;
+  int kb = 0, ke = p.K;
+  if (p.triA) {
+    const bool lower = (p.triA == 1) == (p.opA == 0);
+    if (lower) ke = min(ke, m0 + BM); else kb = max(kb, m0);
+  }
+  if (p.triB) {
+    const bool kgen = (p.triB == 1) == (p.opB == 0);
+    if (kgen) kb = max(kb, n0); else ke = min(ke, n0 + BN);
+  }
+  kb = (kb / BK) * BK;
+  const int nk = ke > kb ? (ke - kb + BK - 1) / BK : 0;
+
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  T acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = zero_of<T>();
+
+  T ra[LPT], rb[LPT];
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int u = 0; u < LPT; ++u) {
+      const int idx = u * 256 + tid;
+      int mm, kk;
+      if (p.opA == 0) { mm = idx % BM; kk = idx / BM; } else { kk = idx % BK; mm = idx / BK; }
+      const long long m = m0 + mm, k = k0 + kk;
+      const bool in = (m < p.M) && (k < ke);
+      ra[u] = (p.opA == 0) ? fetch_stored<T>(p.A, p.lda, in, m, k, p.triA, p.unitA, false)
+                           : fetch_stored<T>(p.A, p.lda, in, k, m, p.triA, p.unitA, p.opA == 2);
+      int nn, kk2;
+      if (p.opB != 0) { nn = idx % BN; kk2 = idx / BN; } else { kk2 = idx % BK; nn = idx / BK; }
+      const long long n = n0 + nn, k2 = k0 + kk2;
+      const bool inb = (n < p.N) && (k2 < ke);
+      rb[u] = (p.opB == 0) ? fetch_stored<T>(p.B, p.ldb, inb, k2, n, p.triB, p.unitB, false)
+                           : fetch_stored<T>(p.B, p.ldb, inb, n, k2, p.triB, p.unitB, p.opB == 2);
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int u = 0; u < LPT; ++u) {
+      const int idx = u * 256 + tid;
+      int mm, kk;
+      if (p.opA == 0) { mm = idx % BM; kk = idx / BM; } else { kk = idx % BK; mm = idx / BK; }
+      As[buf][kk * LDS + mm] = ra[u];
+      int nn, kk2;
+      if (p.opB != 0) { nn = idx % BN; kk2 = idx / BN; } else { kk2 = idx % BK; nn = idx / BK; }
+      Bs[buf][kk2 * LDS + nn] = rb[u];
+    }
+  };
+
+  if (nk > 0) {
+    gload(kb);
+    sstore(0);
+  }
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int cur = kt & 1;
+    if (kt + 1 < nk) gload(kb + (kt + 1) * BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      T a[TM], b[TN];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float4 va = *reinterpret_cast<const float4 *>(&As[cur][kk * LDS + h * (BM / 2) + tx * VW]);
+        const float4 vb = *reinterpret_cast<const float4 *>(&Bs[cur][kk * LDS + h * (BN / 2) + ty * VW]);
+        if constexpr (Cfg::CPLX) {
+          a[h * 2] = make_float2(va.x, va.y); a[h * 2 + 1] = make_float2(va.z, va.w);
+          b[h * 2] = make_float2(vb.x, vb.y); b[h * 2 + 1] = make_float2(vb.z, vb.w);
+        } else {
+          a[h * 4] = va.x; a[h * 4 + 1] = va.y; a[h * 4 + 2] = va.z; a[h * 4 + 3] = va.w;
+          b[h * 4] = vb.x; b[h * 4 + 1] = vb.y; b[h * 4 + 2] = vb.z; b[h * 4 + 3] = vb.w;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) fma_acc(acc[i][j], a[i], b[j]);
+    }
+    if (kt + 1 < nk) sstore(cur ^ 1);
+    __syncthreads();
+  }
+
+  // epilogue: thread owns rows m0 + h*(BM/2) + tx*VW + v, columns n0 + h2*(BN/2) + ty*VW + w
+#pragma unroll
+  for (int j = 0; j < TN; ++j) {
+    const long long n = n0 + (j / VW) * (BN / 2) + ty * VW + (j % VW);
+    if (n >= p.N) continue;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      const long long m = m0 + (i / VW) * (BM / 2) + tx * VW + (i % VW);
+      if (m >= p.M) continue;
+      if (p.cuplo == 1 && m < n) continue;
+      if (p.cuplo == 2 && m > n) continue;
+      T o = mul(p.alpha, acc[i][j]);
+      if (!p.beta_zero) fma_acc(o, p.beta, p.C[n * p.ldc + m]);
+      if constexpr (Cfg::CPLX) { if (p.herm && m == n) o.y = 0.f; }
+      p.D[n * p.ldd + m] = o;
+    }
+  }
+}
+
+template <typename T>
+static int launch_f(const chol_gemm_desc *d) {
+  using Cfg = FCfg<T>;
+  using Real = typename ScalarOf<T>::Real;
+  if (d->m == 0 || d->n == 0) return 0;
+  FArgs<T> a;
+  a.A = (const T *)d->A; a.B = (const T *)d->B; a.C = (const T *)d->C; a.D = (T *)d->D;
+  a.lda = (long long)d->lda; a.ldb = (long long)d->ldb; a.ldc = (long long)d->ldc; a.ldd = (long long)d->ldd;
+  a.M = (int)d->m; a.N = (int)d->n; a.K = (int)d->k;
+  const bool alpha_zero = d->alpha[0] == 0.0 && (!Cfg::CPLX || d->alpha[1] == 0.0);
+  if (alpha_zero) a.K = 0;
+  a.alpha = mk(T(), (Real)d->alpha[0], (Real)d->alpha[1]);
+  a.beta = mk(T(), (Real)d->beta[0], (Real)d->beta[1]);
+  a.beta_zero = d->beta[0] == 0.0 && (!Cfg::CPLX || d->beta[1] == 0.0);
+  a.opA = op_code(d->opA); a.opB = op_code(d->opB);
+  if (!Cfg::CPLX) { if (a.opA == 2) a.opA = 1; if (a.opB == 2) a.opB = 1; }
+  a.triA = tri_code(d->triA); a.triB = tri_code(d->triB);
+  a.unitA = d->unitA; a.unitB = d->unitB;
+  a.cuplo = tri_code(d->cuplo);
+  a.herm = Cfg::CPLX ? d->herm : 0;
+  a.NI = (a.M + Cfg::BM - 1) / Cfg::BM;
+  a.NJ = (a.N + Cfg::BN - 1) / Cfg::BN;
+  a.vec_ok = 0;
+  const long long tiles = total_tiles<1, 8>(a.cuplo, a.NI, a.NJ);
+  if (tiles <= 0) return 0;
+  if (tiles > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
+  gemm_ffma_kernel<T><<<(unsigned)tiles, 256, 0, (cudaStream_t)d->stream>>>(a);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace chol
+
+int chol_gemm_fp32_launch(const chol_gemm_desc *d) {
+  if (d->prec == 's') return chol::launch_f<float>(d);
+  if (d->prec == 'c') return chol::launch_f<float2>(d);
+  return (int)cudaErrorInvalidValue;
+}

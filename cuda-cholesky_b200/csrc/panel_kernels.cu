@@ -1,0 +1,385 @@
+// panel_kernels.cu — the latency-bound pieces of the path, hand-written for sm_100a:
+//   potf2  : Cholesky of a diagonal block        (reference spec: lapack/dpotrf.c:34-81, kernel lapack/dpotrf.cu:23-148)
+//   trti2  : inverse of a triangular block       (lapack/dtrtri.c:43-96, lapack/dtrtri.cu:23)
+//   lauu2  : U*U^H / L^H*L of a triangular block (lapack/dlauum.c:43-69, lapack/dlauum.cu:23)
+//   copy / transpose / fill helpers, the single-pass logdet reduction (lapack/dlogdet.cu:53-118)
+//   and the FP64 peak probes used by bench.py.
+//
+// The reference runs these on the CPU (its device versions are dead code: 1 block x 32 threads,
+// SURVEY.md §2.3).  Here the whole block is staged once in shared memory (up to 128x128 doubles,
+// 129 KB of the 227 KB a B200 CTA can own), factored by one 512-thread CTA with one barrier per
+// column, and results stream straight back to HBM - nothing crosses PCIe, nothing runs on the host.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "chol_kernels.h"
+#include "ptx_sm100.cuh"
+#include "scalar_ops.cuh"
+
+namespace chol {
+
+constexpr int PANEL_THREADS = 512;
+
+template <typename T>
+__device__ __forceinline__ void load_lower_form(T *S, int LD, int upper, bool conj_upper, int n, const T *A, long long lda) {
+  // S[i + k*LD] (i >= k) = A(i,k) for lower storage, op(A(k,i)) for upper storage
+  for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+    const int r = idx % n, c = idx / n;  // coalesced along r
+    if (!upper) {
+      if (r >= c) S[r + c * LD] = A[(long long)c * lda + r];
+    } else if (r <= c) {
+      T v = A[(long long)c * lda + r];
+      S[c + r * LD] = conj_upper ? conj_of(v) : v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(PANEL_THREADS) potf2_kernel(int upper, int n, T *A, long long lda, long *dinfo, long info_base) {
+  using Real = typename ScalarOf<T>::Real;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T *S = reinterpret_cast<T *>(smem_raw);
+  const int LD = n | 1;
+  if (*dinfo != 0) return;
+  load_lower_form(S, LD, upper, true, n, A, lda);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int j = 0; j < n; ++j) {
+    const Real d = re_of(S[j + j * LD]);
+    if (!(d > Real(0))) {  // <= 0 or NaN: not positive definite (lapack/dpotrf.c:70-73)
+      if (threadIdx.x == 0) {
+        *dinfo = info_base + j + 1;
+        A[(long long)j * lda + j] = from_real<T>(d);
+      }
+      return;
+    }
+    const Real r = sqrt(d), rinv = Real(1) / r, dinv = Real(1) / d;
+    for (int i = j + threadIdx.x; i < n; i += blockDim.x) {
+      const T v = (i == j) ? from_real<T>(r) : rscale(S[i + j * LD], rinv);
+      if (!upper) A[(long long)j * lda + i] = v; else A[(long long)i * lda + j] = conj_of(v);
+    }
+    for (int k = j + 1 + warp; k < n; k += nwarps) {
+      const T f = neg(rscale(conj_of(S[k + j * LD]), dinv));
+      for (int i = k + lane; i < n; i += 32) fma_acc(S[i + k * LD], S[i + j * LD], f);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(PANEL_THREADS) trti2_kernel(int upper, int unit, int n, const T *A, long long lda, T *B,
+                                                              long long ldb, int zero_other, long *dinfo, long info_base) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T *L = reinterpret_cast<T *>(smem_raw);
+  const int LD = n | 1;
+  T *dinv = L + (size_t)n * LD;
+  __shared__ int fail_lo, fail_hi;
+  if (*dinfo != 0) return;
+  if (threadIdx.x == 0) { fail_lo = 0x7fffffff; fail_hi = -1; }
+  load_lower_form(L, LD, upper, false, n, A, lda);
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    if (unit) dinv[i] = one_of<T>();
+    else {
+      const T d = L[i + i * LD];
+      if (is_zero(d)) { atomicMin(&fail_lo, i); atomicMax(&fail_hi, i); dinv[i] = zero_of<T>(); }
+      else dinv[i] = recip(d);
+    }
+  }
+  __syncthreads();
+  if (fail_hi >= 0) {
+    // the reference sweeps columns upwards for Upper and downwards for Lower and reports the first
+    // zero pivot it meets (lapack/dtrtri.c:49-52, :73-77)
+    if (threadIdx.x == 0) *dinfo = info_base + (upper ? fail_lo : fail_hi) + 1;
+    return;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  // X = L^-1, one column per warp: forward substitution with the residual held in registers
+  for (int j = warp; j < n; j += nwarps) {
+    T r[4], x[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { r[q] = (lane + 32 * q == j) ? one_of<T>() : zero_of<T>(); x[q] = zero_of<T>(); }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (32 * q + 31 < j || 32 * q >= n) continue;
+      for (int kk = 0; kk < 32; ++kk) {
+        const int k = 32 * q + kk;
+        if (k < j || k >= n) continue;
+        T rk;
+        if constexpr (ScalarOf<T>::cplx) { rk.x = __shfl_sync(0xffffffffu, r[q].x, kk); rk.y = __shfl_sync(0xffffffffu, r[q].y, kk); }
+        else rk = __shfl_sync(0xffffffffu, r[q], kk);
+        const T xk = mul(rk, dinv[k]);
+        if (lane == kk) x[q] = xk;
+        const T nxk = neg(xk);
+#pragma unroll
+        for (int q2 = 0; q2 < 4; ++q2) {
+          const int i = lane + 32 * q2;
+          if (q2 >= q && i > k && i < n) fma_acc(r[q2], L[i + k * LD], nxk);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = lane + 32 * q;
+      if (i < n) {
+        if (i >= j) { if (!upper) B[(long long)j * ldb + i] = x[q]; else B[(long long)i * ldb + j] = x[q]; }
+        else if (zero_other) { if (!upper) B[(long long)j * ldb + i] = zero_of<T>(); else B[(long long)i * ldb + j] = zero_of<T>(); }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(PANEL_THREADS) lauu2_kernel(int upper, int n, T *A, long long lda) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T *L = reinterpret_cast<T *>(smem_raw);
+  const int LD = n | 1;
+  load_lower_form(L, LD, upper, true, n, A, lda);  // upper: L = U^H, so U*U^H = L^H*L
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  // R(a,b) = sum_{k>=a} conj(L(k,a)) * L(k,b),  a >= b
+  for (int b = warp; b < n; b += nwarps)
+    for (int a = b + lane; a < n; a += 32) {
+      T acc = zero_of<T>();
+      for (int k = a; k < n; ++k) fma_acc(acc, conj_of(L[k + a * LD]), L[k + b * LD]);
+      if (!upper) A[(long long)b * lda + a] = acc; else A[(long long)a * lda + b] = conj_of(acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// uplo filter on SOURCE coordinates: 0 all, 1 lower, 2 upper, 3 strictly lower, 4 strictly upper
+__device__ __forceinline__ bool tri_keep(int uplo, int r, int c) {
+  return uplo == 0 || (uplo == 1 && r >= c) || (uplo == 2 && r <= c) || (uplo == 3 && r > c) || (uplo == 4 && r < c);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) copy_kernel(int trans, int uplo, int m, int n, const T *A, long long lda, T *B, long long ldb) {
+  __shared__ T tile[32][33];
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  if (trans == 0) {
+    for (int cc = ty; cc < 32; cc += 8) {
+      const int r = r0 + tx, c = c0 + cc;
+      if (r < m && c < n && tri_keep(uplo, r, c))
+        B[(long long)c * ldb + r] = A[(long long)c * lda + r];
+    }
+    return;
+  }
+  for (int cc = ty; cc < 32; cc += 8) {
+    const int r = r0 + tx, c = c0 + cc;
+    if (r < m && c < n) tile[cc][tx] = A[(long long)c * lda + r];
+  }
+  __syncthreads();
+  for (int rr = ty; rr < 32; rr += 8) {
+    const int r = r0 + rr, c = c0 + tx;  // source coordinates; destination is B(c, r)
+    if (r < m && c < n && tri_keep(uplo, r, c)) {
+      T v = tile[tx][rr];
+      B[(long long)r * ldb + c] = (trans == 2) ? conj_of(v) : v;
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) fill_kernel(int uplo, int m, int n, T value, T *A, long long lda) {
+  const int r = blockIdx.x * 32 + (threadIdx.x & 31);
+  for (int cc = threadIdx.x >> 5; cc < 32; cc += 8) {
+    const int c = blockIdx.y * 32 + cc;
+    if (r < m && c < n && (uplo == 0 || (uplo == 1 && r > c) || (uplo == 2 && r < c))) A[(long long)c * lda + r] = value;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// logdet: 2*sum log(Re x[i*incx]).  Single launch; every block reduces a strided slice, the last
+// block to finish (atomic ticket, as in the reference's threadfence reduction) sums the partials in
+// a FIXED order, so the result is deterministic.  d/z use the double-precision log (the
+// reference's z path uses logf, lapack/zlogdet.c:18 - see DESIGN.md), s/c use logf.
+constexpr int LOGDET_BLOCKS = 296;
+constexpr int LOGDET_THREADS = 256;
+struct LogdetScratch { double partial[LOGDET_BLOCKS]; unsigned int ticket; };
+
+template <typename T>
+__global__ void __launch_bounds__(LOGDET_THREADS) logdet_kernel(const T *x, long long incx, long long n,
+                                                                typename ScalarOf<T>::Real *result, LogdetScratch *scr) {
+  using Real = typename ScalarOf<T>::Real;
+  __shared__ double wsum[LOGDET_THREADS / 32];
+  __shared__ bool last;
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const Real v = re_of(x[i * incx]);
+    if constexpr (sizeof(Real) == 4) acc += (double)logf(v); else acc += log(v);
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < LOGDET_THREADS / 32; ++w) s += wsum[w];
+    scr->partial[blockIdx.x] = s;
+    __threadfence();
+    const unsigned int t = atomicAdd(&scr->ticket, 1u);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double s = 0.0;
+    for (unsigned int b = 0; b < gridDim.x; ++b) s += ((volatile double *)scr->partial)[b];
+    *result = (Real)(2.0 * s);
+    scr->ticket = 0;  // ready for the next call
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 peak probes: kind 0 = DMMA only, 1 = DFMA only, 2 = both in the same warp
+template <int KIND>
+__global__ void __launch_bounds__(256) probe_fp64_kernel(double *out, int iters) {
+  double d[16][2], f[16];
+  const double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { d[i][0] = d[i][1] = 0.0; f[i] = i; }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (KIND == 0 || KIND == 2) dmma_884(d[i][0], d[i][1], a, b);
+      if (KIND == 1 || KIND == 2) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) f[i] = fma(f[i], a, b);
+      }
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += d[i][0] + d[i][1] + f[i];
+  if (s == 12345.678) out[0] = s;
+}
+
+template <typename T> static size_t panel_smem(size_t n, size_t extra) { return ((n | 1) * n + extra) * sizeof(T); }
+
+template <typename K> static int set_smem(K kern, size_t bytes) {
+  if (bytes > 48 * 1024) return (int)cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  return 0;
+}
+
+template <typename T>
+static int potf2_t(int uplo, size_t n, void *A, size_t lda, long *dinfo, long base, cudaStream_t st) {
+  const size_t sm = panel_smem<T>(n, 0);
+  int e = set_smem(potf2_kernel<T>, sm); if (e) return e;
+  potf2_kernel<T><<<1, PANEL_THREADS, sm, st>>>(uplo == 'U', (int)n, (T *)A, (long long)lda, dinfo, base);
+  return (int)cudaGetLastError();
+}
+template <typename T>
+static int trti2_t(int uplo, int diag, size_t n, const void *A, size_t lda, void *B, size_t ldb, int zo, long *dinfo, long base, cudaStream_t st) {
+  const size_t sm = panel_smem<T>(n, n);
+  int e = set_smem(trti2_kernel<T>, sm); if (e) return e;
+  trti2_kernel<T><<<1, PANEL_THREADS, sm, st>>>(uplo == 'U', diag == 'U', (int)n, (const T *)A, (long long)lda, (T *)B, (long long)ldb, zo, dinfo, base);
+  return (int)cudaGetLastError();
+}
+template <typename T>
+static int lauu2_t(int uplo, size_t n, void *A, size_t lda, cudaStream_t st) {
+  const size_t sm = panel_smem<T>(n, 0);
+  int e = set_smem(lauu2_kernel<T>, sm); if (e) return e;
+  lauu2_kernel<T><<<1, PANEL_THREADS, sm, st>>>(uplo == 'U', (int)n, (T *)A, (long long)lda);
+  return (int)cudaGetLastError();
+}
+template <typename T>
+static int copy_t(int trans, int uplo, size_t m, size_t n, const void *A, size_t lda, void *B, size_t ldb, cudaStream_t st) {
+  dim3 grid((unsigned)((m + 31) / 32), (unsigned)((n + 31) / 32));
+  const int tc = trans == 'N' ? 0 : (trans == 'T' ? 1 : 2);
+  const int uc = uplo == 'L' ? 1 : (uplo == 'U' ? 2 : (uplo == 'l' ? 3 : (uplo == 'u' ? 4 : 0)));
+  copy_kernel<T><<<grid, 256, 0, st>>>(tc, uc, (int)m, (int)n, (const T *)A, (long long)lda, (T *)B, (long long)ldb);
+  return (int)cudaGetLastError();
+}
+template <typename T>
+static int fill_t(int uplo, size_t m, size_t n, T v, void *A, size_t lda, cudaStream_t st) {
+  dim3 grid((unsigned)((m + 31) / 32), (unsigned)((n + 31) / 32));
+  const int uc = uplo == 'L' ? 1 : (uplo == 'U' ? 2 : 0);
+  fill_kernel<T><<<grid, 256, 0, st>>>(uc, (int)m, (int)n, v, (T *)A, (long long)lda);
+  return (int)cudaGetLastError();
+}
+template <typename T>
+static int logdet_t(const void *x, size_t incx, size_t n, void *res, void *scr, cudaStream_t st) {
+  long long want = ((long long)n + LOGDET_THREADS - 1) / LOGDET_THREADS;
+  int blocks = (int)(want < 1 ? 1 : (want > LOGDET_BLOCKS ? LOGDET_BLOCKS : want));
+  logdet_kernel<T><<<blocks, LOGDET_THREADS, 0, st>>>((const T *)x, (long long)incx, (long long)n,
+                                                    (typename ScalarOf<T>::Real *)res, (LogdetScratch *)scr);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace chol
+
+using namespace chol;
+
+#define DISPATCH(prec, CALL)                        \
+  switch (prec) {                                   \
+    case 's': { using T = float;   return CALL; }   \
+    case 'd': { using T = double;  return CALL; }   \
+    case 'c': { using T = float2;  return CALL; }   \
+    case 'z': { using T = double2; return CALL; }   \
+    default: return (int)cudaErrorInvalidValue;     \
+  }
+
+extern "C" int chol_diag_max(int prec) { return prec == 'z' ? 64 : 128; }
+
+extern "C" int chol_potf2_launch(int prec, int uplo, size_t n, void *A, size_t lda, long *dinfo, long info_base, void *stream) {
+  if (n == 0) return 0;
+  if (n > (size_t)chol_diag_max(prec)) return (int)cudaErrorInvalidValue;
+  DISPATCH(prec, potf2_t<T>(uplo, n, A, lda, dinfo, info_base, (cudaStream_t)stream));
+}
+extern "C" int chol_trti2_launch(int prec, int uplo, int diag, size_t n, const void *A, size_t lda, void *B, size_t ldb,
+                                 int zero_other, long *dinfo, long info_base, void *stream) {
+  if (n == 0) return 0;
+  if (n > (size_t)chol_diag_max(prec)) return (int)cudaErrorInvalidValue;
+  DISPATCH(prec, trti2_t<T>(uplo, diag, n, A, lda, B, ldb, zero_other, dinfo, info_base, (cudaStream_t)stream));
+}
+extern "C" int chol_lauu2_launch(int prec, int uplo, size_t n, void *A, size_t lda, void *stream) {
+  if (n == 0) return 0;
+  if (n > (size_t)chol_diag_max(prec)) return (int)cudaErrorInvalidValue;
+  DISPATCH(prec, lauu2_t<T>(uplo, n, A, lda, (cudaStream_t)stream));
+}
+extern "C" int chol_copy_launch(int prec, int trans, int uplo, size_t m, size_t n, const void *A, size_t lda, void *B,
+                                size_t ldb, void *stream) {
+  if (m == 0 || n == 0) return 0;
+  DISPATCH(prec, copy_t<T>(trans, uplo, m, n, A, lda, B, ldb, (cudaStream_t)stream));
+}
+extern "C" int chol_fill_launch(int prec, int uplo, size_t m, size_t n, double re, double im, void *A, size_t lda, void *stream) {
+  if (m == 0 || n == 0) return 0;
+  DISPATCH(prec, fill_t<T>(uplo, m, n, mk(T(), (typename ScalarOf<T>::Real)re, (typename ScalarOf<T>::Real)im), A, lda, (cudaStream_t)stream));
+}
+extern "C" size_t chol_logdet_scratch_bytes(void) { return sizeof(LogdetScratch); }
+extern "C" int chol_logdet_launch(int prec, const void *x, size_t incx, size_t n, void *dresult, void *dscratch, void *stream) {
+  DISPATCH(prec, logdet_t<T>(x, incx, n, dresult, dscratch, (cudaStream_t)stream));
+}
+
+extern "C" int chol_probe_fp64(int kind, int iters, double *tflops, float *ms_out) {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  double *out = nullptr;
+  cudaMalloc(&out, 8);
+  const int blocks = sms * 4, threads = 256;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int rep = 0; rep < 2; ++rep) {  // first pass warms up
+    cudaEventRecord(e0);
+    if (kind == 0) probe_fp64_kernel<0><<<blocks, threads>>>(out, iters);
+    else if (kind == 1) probe_fp64_kernel<1><<<blocks, threads>>>(out, iters);
+    else probe_fp64_kernel<2><<<blocks, threads>>>(out, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+  }
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  const double warps = (double)blocks * threads / 32.0;
+  double flops = 0.0;
+  if (kind == 0 || kind == 2) flops += warps * iters * 16.0 * (8 * 8 * 4 * 2.0);
+  if (kind == 1 || kind == 2) flops += warps * iters * 16.0 * 8.0 * 32 * 2.0;
+  *tflops = flops / (ms * 1e-3) / 1e12;
+  if (ms_out) *ms_out = ms;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(out);
+  return (int)cudaGetLastError();
+}

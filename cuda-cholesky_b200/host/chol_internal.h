@@ -1,0 +1,91 @@
+/*
+ * chol_internal.h — private declarations shared by the C host code (handles, workspaces, the
+ * precision-generic drivers).  Host code is C (north_star: "Host code stays in C and calls CUDA
+ * through a thin C-ABI layer"); the CUDA side is reached only through csrc/chol_kernels.h.
+ */
+#ifndef CHOL_INTERNAL_H
+#define CHOL_INTERNAL_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <cuda.h>
+
+#include "blas.h"
+#include "lapack.h"
+#include "error.h"
+#include "../csrc/chol_kernels.h"
+
+/* reference blas/handle.h:4-11 keeps a context and 16 lazily loaded CUmodules; kernels here are
+ * linked in, so the handle keeps the context and a growable device scratch instead. */
+struct __cublashandle_st {
+  CUcontext context;
+  CUdevice device;
+  bool primary_retained; /* cuBLASCreate had to retain a primary context (no current context) */
+  CUdeviceptr scratch;   /* TRSM/TRMM temporaries */
+  size_t scratch_bytes;
+  CUdeviceptr dinfo;     /* device long, sink for the diagonal-inverse kernels used by TRSM */
+};
+
+#define CHOL_EVENT_RING 4
+
+/* reference lapack/handle.h:4-11 */
+struct __culapackhandle_st {
+  CUBLAShandle blas_handle;
+  CUcontext context;
+  CUstream s_panel;  /* high priority: diagonal block, panel solve, look-ahead update */
+  CUstream s_update; /* trailing-matrix update */
+  CUevent ev_panel[CHOL_EVENT_RING];
+  CUevent ev_rest[CHOL_EVENT_RING];
+  CUdeviceptr ws; /* workspace, cached across calls (the reference allocates per call, dpotrf.c:200) */
+  size_t ws_bytes;
+  CUdeviceptr dinfo;      /* device long */
+  long *hinfo;            /* pinned host mirror */
+  CUdeviceptr logdet_scr; /* reduction scratch + result */
+  void *hlogdet;          /* pinned */
+  size_t nb;              /* outer block size (0 = default per precision) */
+};
+
+static inline size_t chol_esize(int prec) { return prec == 's' ? 4 : (prec == 'z' ? 16 : 8); }
+static inline bool chol_is_complex(int prec) { return prec == 'c' || prec == 'z'; }
+static inline size_t chol_min(size_t a, size_t b) { return a < b ? a : b; }
+static inline size_t chol_roundup(size_t a, size_t b) { return (a + b - 1) / b * b; }
+/* address of element (i, j) of a column-major device matrix */
+static inline CUdeviceptr chol_at(CUdeviceptr A, size_t lda, size_t i, size_t j, size_t es) {
+  return A + (CUdeviceptr)((j * lda + i) * es);
+}
+
+/* cudaError_t (as int, from the launchers) -> CUresult, through the error hook */
+CUresult chol_rt_error(int cuda_rt_error, const char *call, const char *func, const char *file, int line);
+#define RT_CHECK(call)                                                                  \
+  do {                                                                                  \
+    int __rt__ = (call);                                                                \
+    if (__rt__ != 0) return chol_rt_error(__rt__, STRING(call), __func__, __FILE__, __LINE__); \
+  } while (false)
+
+CUresult chol_blas_scratch(CUBLAShandle h, size_t bytes, CUdeviceptr *out);
+CUresult chol_lapack_workspace(CULAPACKhandle h, size_t bytes, CUdeviceptr *out);
+
+/* ---- precision-generic BLAS-3 cores (blas3.c).  alpha/beta as (re, im) ---- */
+CUresult chol_gemm(int prec, int opA, int opB, size_t m, size_t n, size_t k, const double alpha[2], CUdeviceptr A,
+                   size_t lda, CUdeviceptr B, size_t ldb, const double beta[2], CUdeviceptr C, size_t ldc,
+                   CUdeviceptr D, size_t ldd, CUstream stream);
+/* general descriptor form: triangular masks, triangle-only output, Hermitian diagonal */
+CUresult chol_gemm_ex(int prec, int opA, int opB, int triA, int unitA, int triB, int unitB, int cuplo, int herm,
+                      size_t m, size_t n, size_t k, const double alpha[2], CUdeviceptr A, size_t lda,
+                      CUdeviceptr B, size_t ldb, const double beta[2], CUdeviceptr C, size_t ldc, CUdeviceptr D,
+                      size_t ldd, CUstream stream);
+CUresult chol_rankk(int prec, int uplo, int trans, size_t n, size_t k, double alpha, CUdeviceptr A, size_t lda,
+                    double beta, CUdeviceptr C, size_t ldc, CUstream stream);
+CUresult chol_trmm2(int prec, int side, int uplo, int trans, int diag, size_t m, size_t n, const double alpha[2],
+                    CUdeviceptr A, size_t lda, CUdeviceptr B, size_t ldb, CUdeviceptr X, size_t ldx, CUstream stream);
+CUresult chol_trsm(CUBLAShandle h, int prec, int side, int uplo, int trans, int diag, size_t m, size_t n,
+                   const double alpha[2], CUdeviceptr A, size_t lda, CUdeviceptr B, size_t ldb, CUstream stream);
+
+/* ---- precision-generic LAPACK cores (lapack.c) ---- */
+CUresult chol_potrf(CULAPACKhandle h, int prec, int uplo, size_t n, CUdeviceptr A, size_t lda, long *info);
+CUresult chol_trtri(CULAPACKhandle h, int prec, int uplo, int diag, size_t n, CUdeviceptr A, size_t lda, long *info);
+CUresult chol_lauum(CULAPACKhandle h, int prec, int uplo, size_t n, CUdeviceptr A, size_t lda, long *info);
+CUresult chol_potri(CULAPACKhandle h, int prec, int uplo, size_t n, CUdeviceptr A, size_t lda, long *info);
+CUresult chol_logdet(CULAPACKhandle h, int prec, CUdeviceptr x, size_t incx, size_t n, void *result, CUstream stream);
+
+#endif

@@ -1,0 +1,343 @@
+/*
+ * lapack.c — POTRF / TRTRI / LAUUM / POTRI / logdet on device pointers, all four precisions.
+ *
+ * What the reference does (lapack/dpotrf.c:172-296, dtrtri.c:326-468, dlauum.c:154-292): a
+ * left-looking loop whose diagonal block makes a D2H -> CPU -> H2D round trip every step.
+ * What this file does instead (B200-first):
+ *   POTRF  right-looking, block size nb (256): per step
+ *            [panel stream, high priority]  potf2 of the diagonal block in shared memory ->
+ *            in-shared-memory inverse of it -> panel solve as ONE tensor-core GEMM into a
+ *            contiguous panel buffer W -> write-back -> look-ahead update of the next block column
+ *            [update stream]                trailing-matrix HERK/SYRK  A22 -= W*W^H  on DMMA tiles
+ *          The panel chain of step j+1 overlaps the trailing update of step j (depth-1
+ *          look-ahead); nothing runs on the CPU and nothing crosses PCIe.
+ *          Upper is the same algorithm on W = U12^H, so the trailing update is the identical
+ *          TMA-fed "NT" kernel for both triangles.
+ *   TRTRI  block columns (the reference's sweep order, dtrtri.c:119-163), each step =
+ *          small out-of-place inverse + two GEMMs (the "two-TRMM" form of lapack/strtri.c:408-424)
+ *   LAUUM  per block row one masked GEMM + one masked HERK over the trapezoid L[i:,i] / U[i,i:]
+ *   POTRI  = TRTRI(NonUnit) then LAUUM (lapack/dpotri.c:19-22); input is the Cholesky factor
+ *   logdet one single-pass reduction kernel (lapack/dlogdet.c:37-74)
+ * info is accumulated on the device (csrc/panel_kernels.cu) and read once at the end.
+ */
+#include <complex.h>
+
+#include "chol_internal.h"
+
+static const double ONE[2] = {1.0, 0.0};
+static const double ZERO[2] = {0.0, 0.0};
+static const double MONE[2] = {-1.0, 0.0};
+
+static size_t default_nb(int prec) { return prec == 'z' ? 128 : 256; }
+
+/* workspace layout of one LAPACK call */
+typedef struct {
+  size_t nb, db, ldw, es;
+  CUdeviceptr W[2]; /* panel buffers, ldw x nb */
+  CUdeviceptr Xd;   /* nb x nb : inverse of the diagonal block (other triangle zero) */
+  CUdeviceptr T1;   /* nb x nb : temporary of the blocked small inverse */
+  CUdeviceptr Tinv; /* db x db : inverse of a potf2 sub-block */
+  CUdeviceptr Wd;   /* nb x db : panel of the diagonal-block recursion */
+} ws_t;
+
+static CUresult carve(CULAPACKhandle h, int prec, size_t n, ws_t *w) {
+  w->es = chol_esize(prec);
+  w->nb = h->nb ? h->nb : default_nb(prec);
+  w->db = (size_t)chol_diag_max(prec);
+  if (w->nb < w->db) w->db = w->nb;
+  w->ldw = chol_roundup(n > w->nb ? n : w->nb, 16);
+  const size_t szW = chol_roundup(w->ldw * w->nb * w->es, 256), szX = chol_roundup(w->nb * w->nb * w->es, 256),
+               szT = chol_roundup(w->db * w->db * w->es, 256), szWd = chol_roundup(w->nb * w->db * w->es, 256);
+  CUdeviceptr base;
+  CU_ERROR_CHECK(chol_lapack_workspace(h, 2 * szW + 2 * szX + szT + szWd, &base));
+  w->W[0] = base;
+  w->W[1] = base + szW;
+  w->Xd = base + 2 * szW;
+  w->T1 = w->Xd + szX;
+  w->Tinv = w->T1 + szX;
+  w->Wd = w->Tinv + szT;
+  return CUDA_SUCCESS;
+}
+
+/* `producer` = the stream on which the info-writing kernels ran */
+static CUresult finish_info(CULAPACKhandle h, CUstream producer, long *info) {
+  CU_ERROR_CHECK(cuMemcpyDtoHAsync(h->hinfo, h->dinfo, sizeof(long), producer));
+  CU_ERROR_CHECK(cuStreamSynchronize(h->s_panel));
+  CU_ERROR_CHECK(cuStreamSynchronize(h->s_update));
+  *info = *h->hinfo;
+  return CUDA_SUCCESS;
+}
+
+/* Cholesky of a jb x jb (jb <= nb) diagonal block, blocked by db on one stream */
+static CUresult potrf_diag(int prec, int uplo, size_t jb, CUdeviceptr A, size_t lda, long *dinfo, long base,
+                           const ws_t *w, CUstream st) {
+  const size_t es = w->es, db = w->db;
+  const int herm = chol_is_complex(prec);
+  for (size_t i = 0; i < jb; i += db) {
+    const size_t ib = chol_min(db, jb - i), r = jb - i - ib;
+    const CUdeviceptr Aii = chol_at(A, lda, i, i, es);
+    RT_CHECK(chol_potf2_launch(prec, uplo, ib, (void *)Aii, lda, dinfo, base + (long)i, (void *)st));
+    if (r == 0) break;
+    RT_CHECK(chol_trti2_launch(prec, uplo, 'N', ib, (const void *)Aii, lda, (void *)w->Tinv, db, 1, dinfo,
+                               base + (long)i, (void *)st));
+    const CUdeviceptr A22 = chol_at(A, lda, i + ib, i + ib, es);
+    if (uplo == 'L') {
+      const CUdeviceptr A21 = chol_at(A, lda, i + ib, i, es);
+      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'C', r, ib, ib, ONE, A21, lda, w->Tinv, db, ZERO, 0, 0, w->Wd, w->nb, st));
+      RT_CHECK(chol_copy_launch(prec, 'N', 0, r, ib, (const void *)w->Wd, w->nb, (void *)A21, lda, (void *)st));
+    } else {
+      const CUdeviceptr A12 = chol_at(A, lda, i, i + ib, es);
+      CU_ERROR_CHECK(chol_gemm(prec, 'C', 'N', r, ib, ib, ONE, A12, lda, w->Tinv, db, ZERO, 0, 0, w->Wd, w->nb, st));
+      RT_CHECK(chol_copy_launch(prec, 'C', 0, r, ib, (const void *)w->Wd, w->nb, (void *)A12, lda, (void *)st));
+    }
+    CU_ERROR_CHECK(chol_gemm_ex(prec, 'N', 'C', 0, 0, 0, 0, uplo, herm, r, r, ib, MONE, w->Wd, w->nb, w->Wd, w->nb, ONE,
+                                A22, lda, A22, lda, st));
+  }
+  return CUDA_SUCCESS;
+}
+
+/* X (jb x jb, ldx, other triangle zero) = inverse of the triangular jb x jb block A, jb <= nb */
+static CUresult trtri_small(int prec, int uplo, int diag, size_t jb, CUdeviceptr A, size_t lda, CUdeviceptr X,
+                            size_t ldx, long *dinfo, long base, const ws_t *w, CUstream st) {
+  const size_t es = w->es, db = w->db, nblk = (jb + db - 1) / db;
+  if (nblk > 1) RT_CHECK(chol_fill_launch(prec, 0, jb, jb, 0.0, 0.0, (void *)X, ldx, (void *)st));
+  for (size_t b = 0; b < nblk; b++) {
+    const size_t c = (uplo == 'L') ? nblk - 1 - b : b; /* the reference's sweep direction */
+    const size_t i = c * db, ib = chol_min(db, jb - i);
+    const CUdeviceptr Xcc = chol_at(X, ldx, i, i, es);
+    RT_CHECK(chol_trti2_launch(prec, uplo, diag, ib, (const void *)chol_at(A, lda, i, i, es), lda, (void *)Xcc, ldx, 1,
+                               dinfo, base + (long)i, (void *)st));
+    if (uplo == 'L') {
+      const size_t r = jb - i - ib;
+      if (r == 0) continue;
+      /* X21 = -X22 * (L21 * X11) */
+      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'N', r, ib, ib, ONE, chol_at(A, lda, i + ib, i, es), lda, Xcc, ldx, ZERO, 0, 0,
+                               w->T1, w->nb, st));
+      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'N', r, ib, r, MONE, chol_at(X, ldx, i + ib, i + ib, es), ldx, w->T1, w->nb,
+                               ZERO, 0, 0, chol_at(X, ldx, i + ib, i, es), ldx, st));
+    } else {
+      if (i == 0) continue;
+      /* X12 = -X11 * (U12 * X22) for the block column above the diagonal block */
+      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'N', i, ib, ib, ONE, chol_at(A, lda, 0, i, es), lda, Xcc, ldx, ZERO, 0, 0,
+                               w->T1, w->nb, st));
+      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'N', i, ib, i, MONE, X, ldx, w->T1, w->nb, ZERO, 0, 0,
+                               chol_at(X, ldx, 0, i, es), ldx, st));
+    }
+  }
+  return CUDA_SUCCESS;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+CUresult chol_potrf(CULAPACKhandle h, int prec, int uplo, size_t n, CUdeviceptr A, size_t lda, long *info) {
+  ws_t w;
+  CU_ERROR_CHECK(cuCtxPushCurrent(h->context));
+  CU_ERROR_CHECK(carve(h, prec, n, &w));
+  const size_t es = w.es, nb = w.nb;
+  const int herm = chol_is_complex(prec);
+  long *dinfo = (long *)h->dinfo;
+  CUstream sp = h->s_panel, su = h->s_update;
+  CU_ERROR_CHECK(cuMemsetD8Async(h->dinfo, 0, sizeof(long), sp));
+
+  size_t step = 0;
+  for (size_t j = 0; j < n; j += nb, step++) {
+    const size_t jb = chol_min(nb, n - j), rest = n - j - jb;
+    const CUdeviceptr Ajj = chol_at(A, lda, j, j, es);
+    const CUdeviceptr W = w.W[step & 1];
+    /* --- panel stream: diagonal block, its inverse, panel solve into W, write-back --- */
+    CU_ERROR_CHECK(potrf_diag(prec, uplo, jb, Ajj, lda, dinfo, (long)j, &w, sp));
+    if (rest == 0) break;
+    CU_ERROR_CHECK(trtri_small(prec, uplo, 'N', jb, Ajj, lda, w.Xd, nb, dinfo, (long)j, &w, sp));
+    if (uplo == 'L') {
+      const CUdeviceptr P = chol_at(A, lda, j + jb, j, es); /* rest x jb */
+      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'C', rest, jb, jb, ONE, P, lda, w.Xd, nb, ZERO, 0, 0, W, w.ldw, sp));
+      RT_CHECK(chol_copy_launch(prec, 'N', 0, rest, jb, (const void *)W, w.ldw, (void *)P, lda, (void *)sp));
+    } else {
+      const CUdeviceptr P = chol_at(A, lda, j, j + jb, es); /* jb x rest; W = P^H * U11^-1 */
+      CU_ERROR_CHECK(chol_gemm(prec, 'C', 'N', rest, jb, jb, ONE, P, lda, w.Xd, nb, ZERO, 0, 0, W, w.ldw, sp));
+      RT_CHECK(chol_copy_launch(prec, 'C', 0, rest, jb, (const void *)W, w.ldw, (void *)P, lda, (void *)sp));
+    }
+    CU_ERROR_CHECK(cuEventRecord(h->ev_panel[step % CHOL_EVENT_RING], sp));
+
+    /* --- trailing update  A22 -= W W^H, split into the next block column/row (look-ahead, panel
+     *     stream) and the rest (update stream) --- */
+    const size_t jb2 = chol_min(nb, rest), rest2 = rest - jb2;
+    if (rest2) {
+      CU_ERROR_CHECK(cuStreamWaitEvent(su, h->ev_panel[step % CHOL_EVENT_RING], 0));
+      const CUdeviceptr W2 = chol_at(W, w.ldw, jb2, 0, es);
+      const CUdeviceptr A33 = chol_at(A, lda, j + jb + jb2, j + jb + jb2, es);
+      CU_ERROR_CHECK(chol_gemm_ex(prec, 'N', 'C', 0, 0, 0, 0, uplo, herm, rest2, rest2, jb, MONE, W2, w.ldw, W2, w.ldw, ONE,
+                                  A33, lda, A33, lda, su));
+      CU_ERROR_CHECK(cuEventRecord(h->ev_rest[step % CHOL_EVENT_RING], su));
+    }
+    /* the look-ahead block was last written by the previous step's trailing update */
+    if (step > 0) CU_ERROR_CHECK(cuStreamWaitEvent(sp, h->ev_rest[(step - 1) % CHOL_EVENT_RING], 0));
+    {
+      const CUdeviceptr A22 = chol_at(A, lda, j + jb, j + jb, es);
+      if (uplo == 'L') /* rest x jb2 block column, lower part */
+        CU_ERROR_CHECK(chol_gemm_ex(prec, 'N', 'C', 0, 0, 0, 0, 'L', herm, rest, jb2, jb, MONE, W, w.ldw, W, w.ldw, ONE, A22,
+                                    lda, A22, lda, sp));
+      else /* jb2 x rest block row, upper part */
+        CU_ERROR_CHECK(chol_gemm_ex(prec, 'N', 'C', 0, 0, 0, 0, 'U', herm, jb2, rest, jb, MONE, W, w.ldw, W, w.ldw, ONE, A22,
+                                    lda, A22, lda, sp));
+    }
+  }
+  CU_ERROR_CHECK(finish_info(h, sp, info));
+  CUcontext dummy;
+  CU_ERROR_CHECK(cuCtxPopCurrent(&dummy));
+  return CUDA_SUCCESS;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+CUresult chol_trtri(CULAPACKhandle h, int prec, int uplo, int diag, size_t n, CUdeviceptr A, size_t lda, long *info) {
+  ws_t w;
+  CU_ERROR_CHECK(cuCtxPushCurrent(h->context));
+  CU_ERROR_CHECK(carve(h, prec, n, &w));
+  const size_t es = w.es, nb = w.nb;
+  long *dinfo = (long *)h->dinfo;
+  CUstream st = h->s_update;
+  const int unit = (diag == 'U');
+  const int strict = (uplo == 'L') ? 'l' : 'u';
+  CU_ERROR_CHECK(cuMemsetD8Async(h->dinfo, 0, sizeof(long), st));
+  const size_t nblk = (n + nb - 1) / nb;
+  for (size_t b = 0; b < nblk; b++) {
+    const size_t blk = (uplo == 'L') ? nblk - 1 - b : b; /* reference sweep: lapack/dtrtri.c:119,:137 */
+    const size_t j = blk * nb, jb = chol_min(nb, n - j);
+    const CUdeviceptr Ajj = chol_at(A, lda, j, j, es);
+    CU_ERROR_CHECK(trtri_small(prec, uplo, diag, jb, Ajj, lda, w.Xd, nb, dinfo, (long)j, &w, st));
+    if (uplo == 'L') {
+      const size_t rest = n - j - jb;
+      if (rest) { /* A21 = -inv(A22) * (A21 * inv(A11)) ; inv(A22) is already in place */
+        const CUdeviceptr A21 = chol_at(A, lda, j + jb, j, es), A22 = chol_at(A, lda, j + jb, j + jb, es);
+        CU_ERROR_CHECK(chol_gemm(prec, 'N', 'N', rest, jb, jb, ONE, A21, lda, w.Xd, nb, ZERO, 0, 0, w.W[0], w.ldw, st));
+        CU_ERROR_CHECK(chol_gemm_ex(prec, 'N', 'N', 'L', unit, 0, 0, 0, 0, rest, jb, rest, MONE, A22, lda, w.W[0], w.ldw,
+                                    ZERO, 0, 0, A21, lda, st));
+      }
+    } else if (j) { /* A12 = -inv(A11) * (A12 * inv(A22)) */
+      const CUdeviceptr A12 = chol_at(A, lda, 0, j, es);
+      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'N', j, jb, jb, ONE, A12, lda, w.Xd, nb, ZERO, 0, 0, w.W[0], w.ldw, st));
+      CU_ERROR_CHECK(chol_gemm_ex(prec, 'N', 'N', 'U', unit, 0, 0, 0, 0, j, jb, j, MONE, A, lda, w.W[0], w.ldw, ZERO, 0, 0,
+                                  A12, lda, st));
+    }
+    /* a unit-diagonal inverse leaves the caller's diagonal untouched (lapack/dtrtri.c:56-57) */
+    RT_CHECK(chol_copy_launch(prec, 'N', unit ? strict : uplo, jb, jb, (const void *)w.Xd, nb, (void *)Ajj, lda, (void *)st));
+  }
+  CU_ERROR_CHECK(finish_info(h, st, info));
+  CUcontext dummy;
+  CU_ERROR_CHECK(cuCtxPopCurrent(&dummy));
+  return CUDA_SUCCESS;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+CUresult chol_lauum(CULAPACKhandle h, int prec, int uplo, size_t n, CUdeviceptr A, size_t lda, long *info) {
+  ws_t w;
+  CU_ERROR_CHECK(cuCtxPushCurrent(h->context));
+  CU_ERROR_CHECK(carve(h, prec, n, &w));
+  const size_t es = w.es, nb = w.nb;
+  const int herm = chol_is_complex(prec);
+  CUstream st = h->s_update;
+  *info = 0;
+  for (size_t i = 0; i < n; i += nb) {
+    const size_t ib = chol_min(nb, n - i), k = n - i;
+    const CUdeviceptr Aii = chol_at(A, lda, i, i, es);
+    if (uplo == 'L') {
+      /* row block i of L^H L = (L[i:, i-block])^H * L[i:, 0:i+ib]; the trapezoid's top block is
+       * lower triangular (mask), products go to scratch because the output aliases the operands */
+      if (i)
+        CU_ERROR_CHECK(chol_gemm_ex(prec, 'C', 'N', 'L', 0, 0, 0, 0, 0, ib, i, k, ONE, Aii, lda, chol_at(A, lda, i, 0, es), lda,
+                                    ZERO, 0, 0, w.W[0], nb, st));
+      CU_ERROR_CHECK(chol_gemm_ex(prec, 'C', 'N', 'L', 0, 'L', 0, 'L', herm, ib, ib, k, ONE, Aii, lda, Aii, lda, ZERO, 0, 0,
+                                  w.Xd, nb, st));
+      if (i) RT_CHECK(chol_copy_launch(prec, 'N', 0, ib, i, (const void *)w.W[0], nb, (void *)chol_at(A, lda, i, 0, es), lda, (void *)st));
+    } else {
+      /* column block i of U U^H = U[0:i+ib, i:] * (U[i-block, i:])^H */
+      if (i)
+        CU_ERROR_CHECK(chol_gemm_ex(prec, 'N', 'C', 0, 0, 'U', 0, 0, 0, i, ib, k, ONE, chol_at(A, lda, 0, i, es), lda, Aii, lda,
+                                    ZERO, 0, 0, w.W[0], w.ldw, st));
+      CU_ERROR_CHECK(chol_gemm_ex(prec, 'N', 'C', 'U', 0, 'U', 0, 'U', herm, ib, ib, k, ONE, Aii, lda, Aii, lda, ZERO, 0, 0,
+                                  w.Xd, nb, st));
+      if (i) RT_CHECK(chol_copy_launch(prec, 'N', 0, i, ib, (const void *)w.W[0], w.ldw, (void *)chol_at(A, lda, 0, i, es), lda, (void *)st));
+    }
+    RT_CHECK(chol_copy_launch(prec, 'N', uplo, ib, ib, (const void *)w.Xd, nb, (void *)Aii, lda, (void *)st));
+  }
+  CU_ERROR_CHECK(cuStreamSynchronize(st));
+  CUcontext dummy;
+  CU_ERROR_CHECK(cuCtxPopCurrent(&dummy));
+  return CUDA_SUCCESS;
+}
+
+CUresult chol_potri(CULAPACKhandle h, int prec, int uplo, size_t n, CUdeviceptr A, size_t lda, long *info) {
+  CU_ERROR_CHECK(chol_trtri(h, prec, uplo, 'N', n, A, lda, info));
+  if (*info != 0) return CUDA_SUCCESS;
+  return chol_lauum(h, prec, uplo, n, A, lda, info);
+}
+
+CUresult chol_logdet(CULAPACKhandle h, int prec, CUdeviceptr x, size_t incx, size_t n, void *result, CUstream stream) {
+  const size_t rs = (prec == 's' || prec == 'c') ? 4 : 8;
+  CU_ERROR_CHECK(cuCtxPushCurrent(h->context));
+  const CUdeviceptr dres = h->logdet_scr + (CUdeviceptr)chol_roundup(chol_logdet_scratch_bytes(), 16);
+  RT_CHECK(chol_logdet_launch(prec, (const void *)x, incx, n, (void *)dres, (void *)h->logdet_scr, (void *)stream));
+  CU_ERROR_CHECK(cuMemcpyDtoHAsync(result, dres, rs, stream));
+  CUcontext dummy;
+  CU_ERROR_CHECK(cuCtxPopCurrent(&dummy));
+  return CUDA_SUCCESS;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * typed entry points (include/lapack.h).  Argument checks follow the reference:
+ * potrf/lauum/potri lda -> info -4 (dpotrf.c:174-179), trtri lda -> -5 (dtrtri.c:330-335).
+ * ------------------------------------------------------------------------------------------- */
+#define LAPACK_ARG(cond, pos)               \
+  do {                                      \
+    if (cond) {                             \
+      *info = -(pos);                       \
+      XERBLA(pos);                          \
+      return CUDA_ERROR_INVALID_VALUE;      \
+    }                                       \
+  } while (false)
+
+#define GEN_LAPACK(U, p, REAL)                                                                                       \
+  CUresult cu##U##potrf(CULAPACKhandle h, CBlasUplo uplo, size_t n, CUdeviceptr A, size_t lda, long *info) {         \
+    *info = 0;                                                                                                       \
+    LAPACK_ARG(lda < n, 4);                                                                                          \
+    if (n == 0) return CUDA_SUCCESS;                                                                                 \
+    return chol_potrf(h, p, uplo, n, A, lda, info);                                                                  \
+  }                                                                                                                  \
+  CUresult cu##U##trtri(CULAPACKhandle h, CBlasUplo uplo, CBlasDiag diag, size_t n, CUdeviceptr A, size_t lda,       \
+                        long *info) {                                                                                \
+    *info = 0;                                                                                                       \
+    LAPACK_ARG(lda < n, 5);                                                                                          \
+    if (n == 0) return CUDA_SUCCESS;                                                                                 \
+    return chol_trtri(h, p, uplo, diag, n, A, lda, info);                                                            \
+  }                                                                                                                  \
+  CUresult cu##U##trti22(CULAPACKhandle h, CBlasUplo uplo, CBlasDiag diag, size_t n, CUdeviceptr A, size_t lda,      \
+                         CUdeviceptr B, size_t ldb, CUdeviceptr info, CUstream stream) {                             \
+    (void)h;                                                                                                         \
+    if (n > (size_t)chol_diag_max(p) || lda < n || ldb < n) return CUDA_ERROR_INVALID_VALUE;                         \
+    RT_CHECK(chol_trti2_launch(p, uplo, diag, n, (const void *)A, lda, (void *)B, ldb, 0, (long *)info, 0,           \
+                               (void *)stream));                                                                     \
+    return CUDA_SUCCESS;                                                                                             \
+  }                                                                                                                  \
+  CUresult cu##U##lauum(CULAPACKhandle h, CBlasUplo uplo, size_t n, CUdeviceptr A, size_t lda, long *info) {         \
+    *info = 0;                                                                                                       \
+    LAPACK_ARG(lda < n, 4);                                                                                          \
+    if (n == 0) return CUDA_SUCCESS;                                                                                 \
+    return chol_lauum(h, p, uplo, n, A, lda, info);                                                                  \
+  }                                                                                                                  \
+  CUresult cu##U##potri(CULAPACKhandle h, CBlasUplo uplo, size_t n, CUdeviceptr A, size_t lda, long *info) {         \
+    *info = 0;                                                                                                       \
+    LAPACK_ARG(lda < n, 4);                                                                                          \
+    if (n == 0) return CUDA_SUCCESS;                                                                                 \
+    return chol_potri(h, p, uplo, n, A, lda, info);                                                                  \
+  }                                                                                                                  \
+  CUresult cu##U##logdet(CULAPACKhandle h, CUdeviceptr x, size_t incx, size_t n, REAL *result, CUstream stream) {    \
+    if (n == 0) {                                                                                                    \
+      *result = 0;                                                                                                   \
+      return CUDA_SUCCESS;                                                                                           \
+    }                                                                                                                \
+    return chol_logdet(h, p, x, incx, n, result, stream);                                                            \
+  }
+
+GEN_LAPACK(S, 's', float)
+GEN_LAPACK(D, 'd', double)
+GEN_LAPACK(C, 'c', float)
+GEN_LAPACK(Z, 'z', double)

@@ -1,0 +1,205 @@
+"""GPU parity tests of cu{S,D,C,Z}{potrf,trtri,trti22,lauum,potri,logdet} through the C-ABI against
+the CPU oracle (which is pinned to the reference, tests/test_oracle_pins.py).
+
+Tolerances: elementwise max|X - X_ref| <= 64 n eps max|X_ref| and residual
+||A - L L^H||_F / ||A||_F <= 8 n eps; `info` must be EQUAL to the oracle's."""
+import os
+
+import numpy as np
+import pytest
+
+import harness as H
+from harness import PREC
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("no GPU", allow_module_level=True)
+
+import gpu_util as G  # noqa: E402
+
+ORA = H.CpuLib("oracle")
+
+
+@pytest.fixture(scope="module")
+def lapack():
+    h = G.chol.LapackHandle()
+    yield h
+    h.close()
+
+
+def elem_tol(p, n):
+    return 64 * n * H.eps(p)
+
+
+SIZES = [1, 2, 31, 64, 100, 128, 129, 256, 257, 300, 513, 777]
+
+
+@pytest.mark.parametrize("p", "dzsc")
+@pytest.mark.parametrize("uplo", "LU")
+@pytest.mark.parametrize("n", SIZES)
+def test_potrf_vs_oracle(lapack, p, uplo, n):
+    A = H.spd_matrix(p, n, ld=n + (n % 3), k=min(n, 64))
+    A0 = A.copy()
+    want = A.copy(order="F")
+    assert ORA.potrf(p, uplo, want) == 0
+    dA, lda = G.to_dev(A)
+    assert lapack.potrf(p, uplo, n, dA.data_ptr(), lda) == 0
+    got = G.to_host(dA, n)
+    err = np.abs(H.tri(got, uplo) - H.tri(want, uplo)).max() / np.abs(want).max()
+    assert err <= elem_tol(p, n), err
+    # the opposite (strict) triangle is untouched, bit for bit
+    other = np.triu(got, 1) if uplo == "L" else np.tril(got, -1)
+    other0 = np.triu(A0, 1) if uplo == "L" else np.tril(A0, -1)
+    assert np.array_equal(other, other0)
+    L = H.tri(got, uplo).astype(np.complex128 if PREC[p]["cplx"] else np.float64)
+    R = L @ L.conj().T if uplo == "L" else L.conj().T @ L
+    assert np.linalg.norm(R - A0) / np.linalg.norm(A0) <= 8 * n * H.eps(p)
+
+
+@pytest.mark.parametrize("p", "dz")
+@pytest.mark.parametrize("uplo", "LU")
+def test_potrf_golden_fixture(lapack, p, uplo):
+    """Directly against factors produced by the reference's own CPU code (tests/golden)."""
+    g = np.load(os.path.join(H.GOLDEN, "potrf_%s.npz" % p))
+    for n in (33, 100, 257):
+        A = H.spd_matrix(p, n, ld=n + 3)
+        dA, lda = G.to_dev(A)
+        assert lapack.potrf(p, uplo, n, dA.data_ptr(), lda) == 0
+        got, want = G.to_host(dA, n), g["%s_%d" % (uplo, n)]
+        assert np.abs(H.tri(got, uplo) - H.tri(want, uplo)).max() <= elem_tol(p, n) * np.abs(want).max()
+
+
+@pytest.mark.parametrize("p", "dzsc")
+@pytest.mark.parametrize("uplo", "LU")
+def test_potrf_not_positive_definite_info(lapack, p, uplo):
+    n = 700
+    for bad in (0, 5, 255, 256, 300, 699):
+        A = H.spd_matrix(p, n, k=32)
+        A[bad, bad] = -1.0
+        want = A.copy(order="F")
+        i_ref = ORA.potrf(p, uplo, want)
+        dA, lda = G.to_dev(A)
+        assert lapack.potrf(p, uplo, n, dA.data_ptr(), lda) == i_ref == bad + 1
+
+
+def test_lapack_argument_errors_and_empty(lapack):
+    G.chol.set_xerbla_silent()
+    d = torch.zeros(64, dtype=torch.float64, device="cuda").data_ptr()
+    assert lapack.potrf("d", "L", 8, d, 4, allow_invalid=True) == (-4, G.chol.CUDA_ERROR_INVALID_VALUE)
+    assert lapack.trtri("d", "L", "N", 8, d, 4, allow_invalid=True) == (-5, G.chol.CUDA_ERROR_INVALID_VALUE)
+    assert lapack.lauum("d", "U", 8, d, 4, allow_invalid=True) == (-4, G.chol.CUDA_ERROR_INVALID_VALUE)
+    assert lapack.potri("z", "U", 8, d, 4, allow_invalid=True) == (-4, G.chol.CUDA_ERROR_INVALID_VALUE)
+    assert lapack.potrf("d", "L", 0, d, 0) == 0
+    assert lapack.logdet("d", d, 1, 0) == 0.0
+
+
+@pytest.mark.parametrize("p", "dzsc")
+@pytest.mark.parametrize("uplo", "LU")
+@pytest.mark.parametrize("diag", "NU")
+@pytest.mark.parametrize("n", [3, 64, 129, 256, 300, 600])
+def test_trtri_vs_oracle(lapack, p, uplo, diag, n):
+    A = H.spd_matrix(p, n, k=min(n, 64))
+    ORA.potrf(p, uplo, A)
+    if diag == "U":
+        A /= np.abs(np.diag(A)).max() * 4
+    A0 = A.copy()
+    want = A.copy(order="F")
+    assert ORA.trtri(p, uplo, diag, want) == 0
+    dA, lda = G.to_dev(A)
+    assert lapack.trtri(p, uplo, diag, n, dA.data_ptr(), lda) == 0
+    got = G.to_host(dA, n)
+    assert np.abs(H.tri(got, uplo) - H.tri(want, uplo)).max() <= elem_tol(p, n) * np.abs(H.tri(want, uplo)).max()
+    other = np.triu(got, 1) if uplo == "L" else np.tril(got, -1)
+    other0 = np.triu(A0, 1) if uplo == "L" else np.tril(A0, -1)
+    assert np.array_equal(other, other0)
+    if diag == "U":
+        assert np.array_equal(np.diag(got), np.diag(A0))  # unit diagonal is never referenced or written
+
+
+@pytest.mark.parametrize("p", "dz")
+@pytest.mark.parametrize("uplo", "LU")
+def test_trtri_singular_info_and_trti22(lapack, p, uplo):
+    n = 600
+    A = H.spd_matrix(p, n, k=32)
+    ORA.potrf(p, uplo, A)
+    A[77, 77] = 0
+    A[400, 400] = 0
+    want = A.copy(order="F")
+    i_ref = ORA.trtri(p, uplo, "N", want)
+    dA, lda = G.to_dev(A)
+    assert lapack.trtri(p, uplo, "N", n, dA.data_ptr(), lda) == i_ref
+    # unblocked out-of-place block inverse
+    nb = 64
+    Bm = H.spd_matrix(p, nb, seed=3)
+    ORA.potrf(p, uplo, Bm)
+    wantb = Bm.copy(order="F")
+    ORA.trtri(p, uplo, "N", wantb)
+    dB, ldb = G.to_dev(Bm)
+    dX = torch.zeros_like(dB)
+    dinfo = torch.zeros(1, dtype=torch.int64, device="cuda")
+    lapack.trti22(p, uplo, "N", nb, dB.data_ptr(), ldb, dX.data_ptr(), ldb, dinfo.data_ptr())
+    G.sync()
+    assert int(dinfo.item()) == 0
+    assert np.abs(H.tri(G.to_host(dX, nb), uplo) - H.tri(wantb, uplo)).max() <= elem_tol(p, nb) * np.abs(wantb).max()
+
+
+@pytest.mark.parametrize("p", "dzsc")
+@pytest.mark.parametrize("uplo", "LU")
+@pytest.mark.parametrize("n", [2, 100, 256, 257, 640])
+def test_lauum_potri_logdet_vs_oracle(lapack, p, uplo, n):
+    A = H.spd_matrix(p, n, k=min(n, 64))
+    A0 = A.copy()
+    ORA.potrf(p, uplo, A)
+    F = A.copy(order="F")
+    # lauum
+    want = F.copy(order="F")
+    ORA.lauum(p, uplo, want)
+    dA, lda = G.to_dev(F)
+    assert lapack.lauum(p, uplo, n, dA.data_ptr(), lda) == 0
+    got = G.to_host(dA, n)
+    assert np.abs(H.tri(got, uplo) - H.tri(want, uplo)).max() <= elem_tol(p, n) * np.abs(want).max()
+    # logdet of the factor's diagonal
+    dF, ldf = G.to_dev(F)
+    ld = lapack.logdet(p, dF.data_ptr(), ldf + 1, n)
+    ld_ref = ORA.logdet(p, F, F.strides[1] // F.itemsize + 1, n)
+    e = H.eps("s") if p != "d" else H.eps("d")  # c/z oracle uses logf (lapack/zlogdet.c:18)
+    assert abs(ld - ld_ref) <= 4 * n * e * abs(ld_ref)
+    # potri
+    want = F.copy(order="F")
+    assert ORA.potri(p, uplo, want) == 0
+    assert lapack.potri(p, uplo, n, dF.data_ptr(), ldf) == 0
+    got = G.to_host(dF, n)
+    assert np.abs(H.tri(got, uplo) - H.tri(want, uplo)).max() <= elem_tol(p, n) * np.abs(H.tri(want, uplo)).max()
+    T = H.tri(got, uplo)
+    Ainv = T + T.conj().T - np.diag(np.diag(T))
+    assert np.abs(A0.astype(np.complex128) @ Ainv - np.eye(n)).max() <= 32 * n * H.eps(p)
+    other = np.triu(got, 1) if uplo == "L" else np.tril(got, -1)
+    other0 = np.triu(F, 1) if uplo == "L" else np.tril(F, -1)
+    assert np.array_equal(other, other0)
+
+
+@pytest.mark.parametrize("uplo", "LU")
+def test_dpotrf_large_properties(lapack, uplo):
+    """Full-size properties on the GPU (no oracle at this size): residual, leading-block parity
+    (the factor of a leading block is the leading block of the factor), logdet consistency."""
+    n, k = 8192, 512
+    g = torch.Generator(device="cuda").manual_seed(H.SEED)
+    B = torch.rand(n, k, dtype=torch.float64, device="cuda", generator=g) - 0.5
+    A = B @ B.T + n * torch.eye(n, dtype=torch.float64, device="cuda")
+    F = A.clone()
+    assert lapack.potrf("d", uplo, n, F.data_ptr(), n) == 0
+    # torch row-major (n,n) tensor == column-major transpose: lower(col-major) is torch's upper
+    Lt = torch.triu(F) if uplo == "L" else torch.tril(F)  # = L^T (row-major view) / U^T
+    R = Lt.T @ Lt if uplo == "L" else Lt @ Lt.T
+    resid = (torch.linalg.norm(R - A) / torch.linalg.norm(A)).item()
+    assert resid <= 1e-13, resid
+    m = 1024
+    lead = np.asfortranarray(A[:m, :m].cpu().numpy().T)
+    assert ORA.potrf("d", uplo, lead) == 0
+    got = F[:m, :m].cpu().numpy().T
+    assert np.abs(H.tri(got, uplo) - H.tri(lead, uplo)).max() <= elem_tol("d", m) * np.abs(lead).max()
+    ld = lapack.logdet("d", F.data_ptr(), n + 1, n)
+    want = 2 * torch.log(torch.diagonal(F)).sum().item()
+    assert abs(ld - want) <= 1e-12 * abs(want)
