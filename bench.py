@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py — DPOTRF GFLOP/s (N^3/3) at N = 65536 on 1/2/4/8 B200 (BASELINE.json `metric`).
+
+  python bench.py --gpus 1 --steps K --warmup W            # this library, one GPU
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+         --master-port P bench.py --gpus N --steps K --warmup W      # one rank per GPU, NCCL
+  python bench.py --impl reference --steps K --warmup W    # the reference's CPU dpotrf on host cores
+
+One "step" = one full Cholesky factorisation (lower, FP64) of the synthetic SPD matrix
+A = B*B^T + N*I (B: N x 1024, uniform(-0.5, 0.5), fixed seed), restored before each step inside the
+timed region.  `value` is whole-job GFLOP/s with the matrix already resident in HBM (for N > 1: in
+the 1-D block-cyclic layout across the ranks); `e2e` is the same metric through the host-pointer
+C-ABI call (cuMultiGPUDpotrf / host shard -> cholDistDpotrf -> host shard) with the H2D and D2H
+copies inside the timed region.  The JSON line also carries the roofline of the dominant kernel
+(the DMMA trailing update, timed per launch with CUDA events on its own stream, against the FP64
+tensor-core peak measured in the same process) and the reference's CPU dpotrf timed on this box.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "DPOTRF GFLOP/s (N^3/3) at N=65536, 1/2/4/8 B200, % of FP64 TC peak"
+SEED = 20121018
+KGEN = 1024  # inner dimension of the generator B (N x 1024 for large N)
+
+
+# ---------------------------------------------------------------------------------------------
+# host-side helpers of the multi-process path (covered by tests/test_host_logic.py with gloo)
+# ---------------------------------------------------------------------------------------------
+def _dist():
+    import torch.distributed as dist
+    return dist if dist.is_available() and dist.is_initialized() else None
+
+
+def exchange_unique_id(make_id, rank):
+    """rank 0 creates the 128-byte NCCL id, everyone gets it."""
+    dist = _dist()
+    box = [make_id() if rank == 0 else None]
+    if dist is not None:
+        dist.broadcast_object_list(box, src=0)
+    return box[0]
+
+
+def owned_columns(n, nb, rank, nranks):
+    """global column indices of the rank's packed local columns (block c = lc*nranks + rank)."""
+    import numpy as np
+    nblk = (n + nb - 1) // nb
+    parts = [np.arange(c * nb, min(n, c * nb + nb)) for c in range(rank, nblk, nranks)]
+    return np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)
+
+
+def combine_info(local_info):
+    """first failing column over all ranks (0 = success)."""
+    dist = _dist()
+    if dist is None:
+        return int(local_info)
+    allv = [None] * dist.get_world_size()
+    dist.all_gather_object(allv, int(local_info))
+    pos = [v for v in allv if v > 0]
+    return min(pos) if pos else 0
+
+
+def max_over_ranks(x):
+    dist = _dist()
+    if dist is None:
+        return float(x)
+    allv = [None] * dist.get_world_size()
+    dist.all_gather_object(allv, float(x))
+    return max(allv)
+
+
+def barrier():
+    dist = _dist()
+    if dist is not None:
+        dist.barrier()
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.path = device, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.path)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        return {}
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_lib():
+    """(ctypes lib, kind): the reference's own CPU code if it was compiled (oracle/_ref), else the port."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import harness as H
+    if H.ref() is not None:
+        return H.CpuLib("ref"), "reference", H
+    return H.CpuLib("oracle"), "port", H
+
+
+def cpu_spd(n, k=KGEN):
+    import numpy as np
+    rng = np.random.default_rng(SEED)
+    B = rng.random((n, min(k, n))) - 0.5
+    A = B @ B.T + n * np.eye(n)
+    return np.asfortranarray(A)
+
+
+def time_cpu_dpotrf(n, steps, warmup):
+    import numpy as np
+    lib, kind, _ = cpu_reference_lib()
+    A0 = cpu_spd(n)
+    times = []
+    for it in range(warmup + steps):
+        A = A0.copy(order="F")
+        t0 = time.perf_counter()
+        info = lib.potrf("d", "L", A)
+        dt = time.perf_counter() - t0
+        assert info == 0
+        if it >= warmup:
+            times.append(dt)
+    L = np.tril(A)
+    resid = float(np.linalg.norm(L @ L.T - A0) / np.linalg.norm(A0))
+    return sum(times) / len(times), kind, resid
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    n_s = args.ref_n
+    sec, kind, resid = time_cpu_dpotrf(n_s, args.steps, args.warmup)
+    gf = n_s ** 3 / 3.0 / sec / 1e9
+    sample = "reference CPU dpotrf (lower) of the leading %dx%d principal block of the N=%d workload, per step" % (n_s, n_s, args.n)
+    line = {"impl": "reference", "metric": METRIC, "value": gf, "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "dpotrf lower N=%d (configs[1]-[4] family; metric N)" % args.n, "N": args.n, "uplo": "L",
+                       "sample_N": n_s, "resid": resid},
+            "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    from cholesky_b200_loader import load
+    chol = load()
+    chol.lib()  # fails loudly if the CUDA library is missing: there is no fallback
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    P = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus != P:
+        raise SystemExit("bench.py: --gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)" % (args.gpus, P))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if P > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    N, K, Wm = args.n, args.steps, args.warmup
+
+    # FP64 tensor-core peak of THIS GPU, measured now (MEASURED_PEAKS.json has no FP64 entry)
+    peak_tf = max(chol.probe_fp64(0, 40000)[0] for _ in range(3)) if rank == 0 else 0.0
+
+    uid = exchange_unique_id(chol.dist_unique_id, rank) if P > 1 else None
+    d = chol.Dist(rank, P, uid, nb=args.nb)
+    nb = d.block_size("d")
+    cols = owned_columns(N, nb, rank, P)
+    nloc = len(cols)
+    cols_t = torch.from_numpy(cols).to(dev)
+
+    # synthetic SPD input, generated in place in the distributed layout (row-major (nloc, N) tensor ==
+    # column-major N x nloc with ld = N): A[:, cols] = B * B[cols, :]^T + N * I
+    g = torch.Generator(device=dev).manual_seed(SEED)
+    Bt = torch.rand(KGEN, N, dtype=torch.float64, device=dev, generator=g) - 0.5  # column-major N x KGEN
+    A0 = torch.empty(nloc, N, dtype=torch.float64, device=dev)
+    for s in range(0, nloc, 4096):
+        e = min(nloc, s + 4096)
+        A0[s:e] = Bt[:, cols_t[s:e]].T @ Bt
+    A0[torch.arange(nloc, device=dev), cols_t] += float(N)
+    A = torch.empty_like(A0)
+    torch.cuda.synchronize()
+
+    def step():
+        A.copy_(A0)
+        return d.potrf("d", N, A.data_ptr(), N)
+
+    for _ in range(Wm):
+        info = step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    chol.launch_count(reset=True)
+    d.lapack.profile(True)
+    barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        info = step()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = chol.launch_count()
+    upd_ms, upd_flops, upd_launches = d.lapack.profile_read()
+    d.lapack.profile(False)
+    info = combine_info(info)
+    ms_per_step = ms_total / K
+    gflops = N ** 3 / 3.0 / (ms_per_step * 1e-3) / 1e9
+
+    # ---- untimed correctness probe at full size: || A x - L (L^T x) || / || A x || ----
+    x = torch.rand(N, dtype=torch.float64, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
+    rows = torch.arange(N, device=dev)
+    y_loc = torch.empty(nloc, dtype=torch.float64, device=dev)
+    for s in range(0, nloc, 2048):
+        e = min(nloc, s + 2048)
+        Lc = torch.where(rows[None, :] >= cols_t[s:e, None], A[s:e], torch.zeros((), dtype=torch.float64, device=dev))
+        y_loc[s:e] = Lc @ x  # (L^T x)[cols]
+    z = torch.zeros(N, dtype=torch.float64, device=dev)
+    ax = torch.zeros(N, dtype=torch.float64, device=dev)
+    for s in range(0, nloc, 2048):
+        e = min(nloc, s + 2048)
+        Lc = torch.where(rows[None, :] >= cols_t[s:e, None], A[s:e], torch.zeros((), dtype=torch.float64, device=dev))
+        z += y_loc[s:e] @ Lc
+        ax += x[cols_t[s:e]] @ A0[s:e]
+    if P > 1:
+        dist.all_reduce(z)
+        dist.all_reduce(ax)
+    probe_resid = (torch.linalg.norm(z - ax) / torch.linalg.norm(ax)).item()
+
+    # ---- e2e: host buffers, copies inside the timed region ----
+    e2e_steps = max(1, min(K, args.e2e_steps))
+    h2d_bytes = d2h_bytes = nloc * N * 8
+    hostA = torch.empty(nloc, N, dtype=torch.float64, pin_memory=True)
+    e2e_times = []
+    if P == 1:
+        del A  # the host-pointer API owns its own device copy
+        torch.cuda.empty_cache()
+        mg = chol.MultiGPU([local_rank])
+        if args.nb:
+            mg.set_block_size(args.nb)
+        for it in range(1 + e2e_steps):
+            hostA.copy_(A0)  # restore the input on the host (untimed)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            info2 = mg.potrf("d", "L", N, hostA.data_ptr(), N)  # scatter (H2D) + factor + gather (D2H)
+            dt = time.perf_counter() - t0
+            if it >= 1:
+                e2e_times.append(dt)
+        mg.close()
+        e2e_api = "cuMultiGPUDpotrf(host pointer), 1 GPU"
+    else:
+        for it in range(1 + e2e_steps):
+            hostA.copy_(A0)
+            torch.cuda.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            A.copy_(hostA, non_blocking=True)
+            info2 = d.potrf("d", N, A.data_ptr(), N)
+            hostA.copy_(A, non_blocking=True)
+            torch.cuda.synchronize()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            if it >= 1:
+                e2e_times.append(dt)
+        e2e_api = "pinned host shard -> cholDistDpotrf -> pinned host shard, %d ranks" % P
+    info2 = combine_info(info2)
+    e2e_s = sum(e2e_times) / len(e2e_times)
+    e2e_gflops = N ** 3 / 3.0 / e2e_s / 1e9
+    d.close()
+
+    if rank != 0:
+        if P > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (trailing-update DMMA tiles) ----
+    achieved_tf = (upd_flops / (upd_ms * 1e-3) / 1e12) if upd_ms > 0 else None
+    roofline = {"bound": "tensor", "kernel": "chol::gemm_dmma_kernel<false,0> (trailing update A22 -= W*W^T)",
+                "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved_tf / peak_tf) if achieved_tf else None,
+                "traffic": None, "launches": upd_launches, "ms_total": upd_ms,
+                "share_of_step": upd_ms / ms_total if ms_total else None,
+                "peak_source": "FP64 DMMA (mma.sync.m8n8k4.f64) peak measured in this run by chol_probe_fp64; "
+                               "MEASURED_PEAKS.json has no FP64 entry (bf16 %.0f TF/s, HBM %.0f GB/s)"
+                               % (measured_peaks().get("bf16_tflops", 0), measured_peaks().get("hbm_gbs", 0)),
+                "whole_factorisation_frac_of_peak": gflops / 1e3 / peak_tf if peak_tf else None}
+
+    # ---- the reference's CPU path on this box's host cores (bounded sample) ----
+    cpu = None
+    if P == 1 and not args.no_cpu_baseline:
+        cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+        sec, kind, _ = time_cpu_dpotrf(args.cpu_n, 1, 0)
+        cpu = {"value": args.cpu_n ** 3 / 3.0 / sec / 1e9, "unit": "GFLOP/s", "cores": cores, "kind": kind,
+               "sample": "reference CPU dpotrf (lower) of a %dx%d SPD matrix of the same family, one run, %.1f s"
+                         % (args.cpu_n, args.cpu_n, sec)}
+
+    line = {"metric": METRIC, "value": gflops, "unit": "GFLOP/s", "n_gpus": P, "steps": K, "warmup": Wm,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "dpotrf lower N=%d, FP64 DMMA trailing update (BASELINE configs[1]/[4] family at the metric's N)" % N,
+                       "N": N, "uplo": "L", "nb": nb, "layout": "1-D block-cyclic block columns over %d rank(s)" % P,
+                       "parallelism": "bc%d" % P, "l2": "inputs (%.1f GB per rank) are larger than L2" % (nloc * N * 8 / 1e9),
+                       "restore_in_timed_region": True, "info": info, "probe_resid": probe_resid},
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": e2e_gflops, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "s_per_step": e2e_s, "steps": e2e_steps, "api": e2e_api, "info": info2},
+            "roofline": roofline}
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if P > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=65536, help="matrix order (the metric's N)")
+    ap.add_argument("--nb", type=int, default=0, help="outer block size (0 = library default)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-n", type=int, default=6144, help="order of the CPU-baseline sample")
+    ap.add_argument("--ref-n", type=int, default=4096, help="order of the per-step sample of --impl reference")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -33,7 +33,8 @@ class GemmDesc(C.Structure):  # csrc/chol_kernels.h chol_gemm_desc
                 ("m", C.c_size_t), ("n", C.c_size_t), ("k", C.c_size_t), ("alpha", C.c_double * 2),
                 ("beta", C.c_double * 2), ("A", C.c_void_p), ("lda", C.c_size_t), ("B", C.c_void_p),
                 ("ldb", C.c_size_t), ("C", C.c_void_p), ("ldc", C.c_size_t), ("D", C.c_void_p), ("ldd", C.c_size_t),
-                ("stream", C.c_void_p), ("force_generic", C.c_int)]
+                ("stream", C.c_void_p), ("force_generic", C.c_int),
+                ("cyc_nb", C.c_int), ("cyc_p", C.c_int), ("cyc_off", C.c_int)]
 
 
 _SCALAR = {"s": C.c_float, "d": C.c_double, "c": cfloat, "z": cdouble}
@@ -146,6 +147,15 @@ class LapackHandle:
     def set_block_size(self, nb):
         _check("cuLAPACKSetBlockSize", lib().cuLAPACKSetBlockSize(self.h, C.c_size_t(nb)))
 
+    def profile(self, enable=True):
+        """Time every trailing-update launch of subsequent calls with CUDA events (roofline)."""
+        _check("cuLAPACKProfile", lib().cuLAPACKProfile(self.h, C.c_int(1 if enable else 0)))
+
+    def profile_read(self):
+        ms, fl, n = C.c_double(0), C.c_double(0), C.c_int(0)
+        _check("cuLAPACKProfileRead", lib().cuLAPACKProfileRead(self.h, C.byref(ms), C.byref(fl), C.byref(n)))
+        return ms.value, fl.value, n.value
+
     def close(self):
         if self.h:
             lib().cuLAPACKDestroy(self.h)
@@ -218,6 +228,13 @@ def gemm_desc_launch(**kw):
     return uses_tma
 
 
+def launch_count(reset=False):
+    """Kernels launched by the library so far."""
+    f = lib().chol_launch_count
+    f.restype = C.c_ulonglong
+    return int(f(C.c_int(1 if reset else 0)))
+
+
 def probe_fp64(kind, iters=20000):
     """Measured FP64 peak of this GPU in TFLOP/s: kind 0 = DMMA (tensor core), 1 = DFMA, 2 = both."""
     tf, ms = C.c_double(0), C.c_float(0)
@@ -225,3 +242,141 @@ def probe_fp64(kind, iters=20000):
     if rc != 0:
         raise CholeskyError("chol_probe_fp64", rc)
     return tf.value, ms.value
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-GPU: the reference's host-pointer API (one process, one worker thread per GPU) ...
+# ---------------------------------------------------------------------------------------------
+class MultiGPU:
+    """CUmultiGPU + CUmultiGPULAPACKhandle + CUmultiGPUBLAShandle (include/cumultigpu.h, lapack.h, blas.h).
+    Matrices are HOST arrays (numpy, column-major); pass their ctypes address."""
+
+    def __init__(self, devices):
+        self.m = C.c_void_p()
+        arr = (C.c_int * len(devices))(*devices)
+        _check("cuMultiGPUCreate", lib().cuMultiGPUCreate(C.byref(self.m), arr, C.c_int(len(devices))))
+        self.lap = C.c_void_p()
+        _check("cuMultiGPULAPACKCreate", lib().cuMultiGPULAPACKCreate(C.byref(self.lap), self.m))
+        self.blas = C.c_void_p()
+        _check("cuMultiGPUBLASCreate", lib().cuMultiGPUBLASCreate(C.byref(self.blas), self.m))
+
+    def count(self):
+        return lib().cuMultiGPUGetContextCount(self.m)
+
+    def close(self):
+        if self.m:
+            lib().cuMultiGPUBLASDestroy(self.blas)
+            lib().cuMultiGPULAPACKDestroy(self.lap)
+            lib().cuMultiGPUDestroy(self.m)
+            self.m = C.c_void_p()
+
+    def set_block_size(self, nb):
+        lib().chol_mgpu_rank_lapack.restype = C.c_void_p
+        for i in range(self.count()):
+            h = lib().chol_mgpu_rank_lapack(self.m, C.c_int(i))
+            _check("cuLAPACKSetBlockSize", lib().cuLAPACKSetBlockSize(C.c_void_p(h), C.c_size_t(nb)))
+
+    def _lapack(self, name, p, uplo, n, A, lda, diag=None, allow_invalid=False):
+        f = getattr(lib(), "cuMultiGPU%s%s" % (_U[p], name))
+        info = C.c_long(0)
+        if diag is None:
+            rc = f(self.lap, C.c_int(ord(uplo)), C.c_size_t(n), C.c_void_p(A), C.c_size_t(lda), C.byref(info))
+        else:
+            rc = f(self.lap, C.c_int(ord(uplo)), C.c_int(ord(diag)), C.c_size_t(n), C.c_void_p(A), C.c_size_t(lda), C.byref(info))
+        _check(f.__name__, rc, allow_invalid)
+        return (info.value, rc) if allow_invalid else info.value
+
+    def potrf(self, p, uplo, n, A, lda, **kw):
+        return self._lapack("potrf", p, uplo, n, A, lda, **kw)
+
+    def lauum(self, p, uplo, n, A, lda, **kw):
+        return self._lapack("lauum", p, uplo, n, A, lda, **kw)
+
+    def potri(self, p, uplo, n, A, lda, **kw):
+        return self._lapack("potri", p, uplo, n, A, lda, **kw)
+
+    def trtri(self, p, uplo, diag, n, A, lda, **kw):
+        return self._lapack("trtri", p, uplo, n, A, lda, diag=diag, **kw)
+
+    def gemm(self, p, tA, tB, m, n, k, alpha, A, lda, B, ldb, beta, Cp, ldc):
+        f = getattr(lib(), "cuMultiGPU%sgemm" % _U[p])
+        return _check(f.__name__, f(self.blas, C.c_int(ord(tA)), C.c_int(ord(tB)), C.c_size_t(m), C.c_size_t(n), C.c_size_t(k),
+                                    _scalar(p, alpha), C.c_void_p(A), C.c_size_t(lda), C.c_void_p(B), C.c_size_t(ldb),
+                                    _scalar(p, beta), C.c_void_p(Cp), C.c_size_t(ldc)))
+
+    def rankk(self, p, uplo, trans, n, k, alpha, A, lda, beta, Cp, ldc):
+        f = getattr(lib(), "cuMultiGPU%s%s" % (_U[p], "herk" if p in "cz" else "syrk"))
+        return _check(f.__name__, f(self.blas, C.c_int(ord(uplo)), C.c_int(ord(trans)), C.c_size_t(n), C.c_size_t(k),
+                                    _REAL[p](alpha), C.c_void_p(A), C.c_size_t(lda), _REAL[p](beta), C.c_void_p(Cp), C.c_size_t(ldc)))
+
+    def _tr(self, name, p, side, uplo, trans, diag, m, n, alpha, A, lda, B, ldb):
+        f = getattr(lib(), "cuMultiGPU%s%s" % (_U[p], name))
+        return _check(f.__name__, f(self.blas, C.c_int(ord(side)), C.c_int(ord(uplo)), C.c_int(ord(trans)), C.c_int(ord(diag)),
+                                    C.c_size_t(m), C.c_size_t(n), _scalar(p, alpha), C.c_void_p(A), C.c_size_t(lda),
+                                    C.c_void_p(B), C.c_size_t(ldb)))
+
+    def trmm(self, *a):
+        return self._tr("trmm", *a)
+
+    def trsm(self, *a):
+        return self._tr("trsm", *a)
+
+
+# ---------------------------------------------------------------------------------------------
+# ... and one process per GPU (torchrun): the SPMD core behind cuMultiGPU*potrf, C-ABI cholDist*
+# ---------------------------------------------------------------------------------------------
+def dist_unique_id():
+    """128-byte NCCL unique id (rank 0 creates it, the launcher ships it to the other ranks)."""
+    buf = C.create_string_buffer(128)
+    _check("cholDistGetUniqueId", lib().cholDistGetUniqueId(buf))
+    return buf.raw
+
+
+def dist_local_cols(n, nb, rank, nranks):
+    f = lib().cholDistLocalCols
+    f.restype = C.c_size_t
+    return int(f(C.c_size_t(n), C.c_size_t(nb), C.c_int(rank), C.c_int(nranks)))
+
+
+class Dist:
+    """One rank of the distributed factorisation.  The rank's block columns (global block
+    c = lc*nranks + rank) are packed side by side in device memory, n rows, leading dimension ldl."""
+
+    def __init__(self, rank, nranks, unique_id=None, nb=0):
+        self.h = C.c_void_p()
+        idbuf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
+        _check("cholDistCreate", lib().cholDistCreate(C.byref(self.h), C.c_int(rank), C.c_int(nranks), idbuf))
+        self.rank, self.nranks = rank, nranks
+        if nb:
+            _check("cholDistSetBlockSize", lib().cholDistSetBlockSize(self.h, C.c_size_t(nb)))
+        lib().cholDistLapackHandle.restype = C.c_void_p
+        self.lapack = LapackHandle.__new__(LapackHandle)
+        self.lapack.h = C.c_void_p(lib().cholDistLapackHandle(self.h))
+
+    def block_size(self, p):
+        f = lib().cholDistBlockSize
+        f.restype = C.c_size_t
+        return int(f(self.h, C.c_int(ord(p))))
+
+    def potrf(self, p, n, Aloc, ldl):
+        f = getattr(lib(), "cholDist%spotrf" % _U[p])
+        info = C.c_long(0)
+        _check(f.__name__, f(self.h, C.c_size_t(n), C.c_void_p(Aloc), C.c_size_t(ldl), C.byref(info)))
+        return info.value
+
+    def close(self):
+        if self.h:
+            lib().cholDistDestroy(self.h)
+            self.h = C.c_void_p()
+
+
+def tile_schedule(cuplo, m, n, cyc_nb=0, cyc_p=0, cyc_off=0):
+    """Host-side decode of the d-engine's tile schedule (test hook).  Returns (grid, [(bi, bj), ...])."""
+    cap = ((m + 127) // 128 + 8) * ((n + 63) // 64 + 8)
+    out = (C.c_int * (2 * cap))()
+    nv = C.c_longlong(0)
+    f = lib().chol_test_tile_schedule
+    f.restype = C.c_longlong
+    grid = f(C.c_int(ord(cuplo) if cuplo else 0), C.c_int(m), C.c_int(n), C.c_int(cyc_nb), C.c_int(cyc_p), C.c_int(cyc_off),
+             out, C.c_longlong(cap), C.byref(nv))
+    return int(grid), [(out[2 * i], out[2 * i + 1]) for i in range(nv.value)]

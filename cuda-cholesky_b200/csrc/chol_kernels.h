@@ -36,6 +36,10 @@ typedef struct chol_gemm_desc {
   void *D; size_t ldd;
   void *stream;
   int force_generic;    /* test hook: never take the TMA-fed path */
+  /* block-cyclic column map (multi-GPU trailing update; 0,0,0 = off): D's packed local column n
+   * stands for global triangle column  g(n) = ((n / cyc_nb) * cyc_p + cyc_off) * cyc_nb + n % cyc_nb;
+   * the B operand row of column n is g(n) and cuplo 'L' keeps m >= g(n).  Requires op(B) != 'N'. */
+  int cyc_nb, cyc_p, cyc_off;
 } chol_gemm_desc;
 
 int chol_gemm_launch(const chol_gemm_desc *d);
@@ -69,6 +73,9 @@ int chol_fill_launch(int prec, int uplo, size_t m, size_t n, double re, double i
 /* ---- logdet: *dresult (device REAL) = 2 * sum_i log(Re x[i*incx]); one kernel, no host sync ---- */
 int chol_logdet_launch(int prec, const void *x, size_t incx, size_t n, void *dresult, void *dscratch, void *stream);
 size_t chol_logdet_scratch_bytes(void);
+
+/* number of kernels launched by the library so far (optionally resetting the counter) */
+unsigned long long chol_launch_count(int reset);
 
 /* ---- measurement probes (used by bench.py / profiles, not by the library path) ---- */
 /* kind 0: DMMA m8n8k4 only; 1: DFMA only; 2: both interleaved.  Returns achieved TFLOP/s. */

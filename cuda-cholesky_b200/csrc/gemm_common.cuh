@@ -7,48 +7,75 @@
 namespace chol {
 
 // ---- tile scheduler ---------------------------------------------------------------------------
-template <int R, int GROUP>
-__host__ __device__ inline int sr_ncols(int cuplo, int NJ, int s) {
+// Tiles are enumerated in super-rows of GROUP row-blocks; inside a super-row the column-tile index
+// runs slowest and the row-block fastest, so CTAs that are resident together share the same B rows
+// and a small, L2-resident set of A rows.  For triangle-only outputs (cuplo) the grid holds just
+// the column tiles that can touch the triangle.
+//
+// Block-cyclic column map (multi-GPU): a rank's packed local columns n map to global triangle
+// coordinates  gcol(n) = ((n / cnb) * cP + coff) * cnb + n % cnb  (cnb = 0: identity).  The
+// lower-triangle test is then  m >= gcol(n)  and the B operand row of column n is gcol(n).
+struct ColMap {
+  int cnb, cP, coff;
+};
+__host__ __device__ inline long long gcol(const ColMap &cm, long long n) {
+  return cm.cnb ? ((n / cm.cnb) * cm.cP + cm.coff) * cm.cnb + n % cm.cnb : n;
+}
+// number of column tiles (width BN, BN | cnb) whose first column has gcol <= m_max
+template <int BN>
+__host__ __device__ inline int cols_upto(const ColMap &cm, long long m_max) {
+  if (m_max < 0) return 0;
+  if (!cm.cnb) return (int)(m_max / BN) + 1;
+  const long long q = m_max / cm.cnb;  // global block column that holds m_max
+  if (q < cm.coff) return 0;
+  const long long lc = (q - cm.coff) / cm.cP;  // last local block whose global index is <= q
+  const int tpb = cm.cnb / BN;
+  int cnt = (int)lc * tpb;  // local blocks 0..lc-1 are entirely reachable
+  if (lc * cm.cP + cm.coff == q) cnt += (int)((m_max - q * cm.cnb) / BN) + 1;
+  else cnt += tpb;
+  return cnt;
+}
+template <int BM, int BN, int GROUP>
+__host__ __device__ inline int sr_ncols(int cuplo, int NJ, const ColMap &cm, int s) {
   if (cuplo == 1) {
-    int c = R * GROUP * (s + 1);
+    const int c = cols_upto<BN>(cm, (long long)GROUP * (s + 1) * BM - 1);
     return c < NJ ? c : NJ;
   }
   if (cuplo == 2) {
-    int b = R * GROUP * s;
+    const int b = (BM / BN) * GROUP * s;
     return b < NJ ? NJ - b : 0;
   }
   return NJ;
 }
-template <int R, int GROUP>
-__host__ inline long long total_tiles(int cuplo, int NI, int NJ) {
+template <int BM, int BN, int GROUP>
+__host__ inline long long total_tiles(int cuplo, int NI, int NJ, const ColMap &cm) {
   long long t = 0;
-  for (int s = 0; s * GROUP < NI; ++s) t += (long long)GROUP * sr_ncols<R, GROUP>(cuplo, NJ, s);
+  for (int s = 0; s * GROUP < NI; ++s) t += (long long)GROUP * sr_ncols<BM, BN, GROUP>(cuplo, NJ, cm, s);
   return t;
 }
-template <int R, int GROUP>
-__device__ inline bool tile_coords(int cuplo, int NI, int NJ, long long t, int &bi, int &bj) {
+template <int BM, int BN, int GROUP>
+__host__ __device__ inline bool tile_coords(int cuplo, int NI, int NJ, const ColMap &cm, long long t, int &bi, int &bj) {
   int s = 0;
   if (cuplo == 0) {
     s = (int)(t / ((long long)GROUP * NJ));
     t -= (long long)s * GROUP * NJ;
   } else {
     for (;;) {
-      long long c = (long long)GROUP * sr_ncols<R, GROUP>(cuplo, NJ, s);
+      long long c = (long long)GROUP * sr_ncols<BM, BN, GROUP>(cuplo, NJ, cm, s);
       if (t < c) break;
       t -= c;
       ++s;
     }
   }
-  const int jbase = (cuplo == 2) ? R * GROUP * s : 0;
+  const int jbase = (cuplo == 2) ? (BM / BN) * GROUP * s : 0;
   bj = jbase + (int)(t / GROUP);
   bi = GROUP * s + (int)(t % GROUP);
   if (bi >= NI || bj >= NJ) return false;
-  if (cuplo == 1 && bj > R * bi + R - 1) return false;  // tile entirely above the diagonal
-  if (cuplo == 2 && bj < R * bi) return false;          // tile entirely below the diagonal
+  if (cuplo == 1 && bj >= cols_upto<BN>(cm, (long long)(bi + 1) * BM - 1)) return false;  // above the diagonal
+  if (cuplo == 2 && bj < (BM / BN) * bi) return false;                                     // below the diagonal
   return true;
 }
 
-// ---- generic operand fetch (MODE 1) -----------------------------------------------------------
 // element (r, c) of a stored operand: bounds, triangular mask, implicit unit diagonal, conjugation
 template <typename T>
 __device__ __forceinline__ T fetch_stored(const T *__restrict__ P, long long ld, bool in, long long r, long long c,

@@ -31,6 +31,7 @@
 #include <type_traits>
 
 #include "chol_kernels.h"
+#include "launch_count.h"
 #include "gemm_common.cuh"
 #include "ptx_sm100.cuh"
 
@@ -70,6 +71,7 @@ struct GemmArgs {
   int vec_ok;        // C/D allow 16-byte accesses
   int beta_zero;
   int conjB_regs;    // MODE 0, z: conjugate B fragments in registers (raw TMA copy cannot)
+  ColMap cm;         // block-cyclic column map of D's columns (cnb = 0: identity)
 };
 
 template <bool CPLX, int MODE>
@@ -85,8 +87,9 @@ __global__ void __launch_bounds__(GemmCfg<CPLX>::THREADS, 2) gemm_dmma_kernel(co
   uint64_t *empty = full + ST;
 
   int bi, bj;
-  if (!tile_coords<Cfg::R, Cfg::GROUP>(p.cuplo, p.NI, p.NJ, (long long)blockIdx.x, bi, bj)) return;
+  if (!tile_coords<BM, BN, Cfg::GROUP>(p.cuplo, p.NI, p.NJ, p.cm, (long long)blockIdx.x, bi, bj)) return;
   const int m0 = bi * BM, n0 = bj * BN;
+  const int g0 = (int)gcol(p.cm, n0);  // triangle coordinate / B row of the tile's first column
 
   // structurally-zero k ranges of triangular operands
   int kb = 0, ke = p.K;
@@ -96,7 +99,7 @@ __global__ void __launch_bounds__(GemmCfg<CPLX>::THREADS, 2) gemm_dmma_kernel(co
   }
   if (p.triB) {
     const bool kgen = (p.triB == 1) == (p.opB == 0);  // op(B)[k][n] != 0 only for k >= n
-    if (kgen) kb = max(kb, n0); else ke = min(ke, n0 + BN);
+    if (kgen) kb = max(kb, g0); else ke = min(ke, g0 + BN);
   }
   kb = (kb / BK) * BK;
   const int nk = ke > kb ? (ke - kb + BK - 1) / BK : 0;
@@ -127,7 +130,7 @@ __global__ void __launch_bounds__(GemmCfg<CPLX>::THREADS, 2) gemm_dmma_kernel(co
         if (lane < BK)
           tma_bulk_g2s(as + lane * LDA, p.A + (long long)(k0 + lane) * p.lda + m0, rowsA * Cfg::ESZ, &full[s]);
         else if (lane < 2 * BK)
-          tma_bulk_g2s(bs + (lane - BK) * LDB, p.B + (long long)(k0 + lane - BK) * p.ldb + n0, rowsB * Cfg::ESZ, &full[s]);
+          tma_bulk_g2s(bs + (lane - BK) * LDB, p.B + (long long)(k0 + lane - BK) * p.ldb + g0, rowsB * Cfg::ESZ, &full[s]);
       } else {
         constexpr int U = 8;  // loads in flight per lane
         // A tile: logical op(A)[m0+mm][k0+kk] -> as[kk*LDA + mm]
@@ -159,8 +162,8 @@ __global__ void __launch_bounds__(GemmCfg<CPLX>::THREADS, 2) gemm_dmma_kernel(co
             const int idx = base + u * 64 + pw * 32 + lane;
             int nn, kk;
             if (p.opB != 0) { nn = idx % BN; kk = idx / BN; } else { kk = idx % BK; nn = idx / BK; }
-            const long long n = n0 + nn, k = k0 + kk;
-            const bool in = (n < p.N) && (k < ke);
+            const long long n = g0 + nn, k = k0 + kk;
+            const bool in = (n0 + nn < p.N) && (k < ke);
             if (p.opB == 0) v[u] = fetch_stored<T>(p.B, p.ldb, in, k, n, p.triB, p.unitB, false);
             else            v[u] = fetch_stored<T>(p.B, p.ldb, in, n, k, p.triB, p.unitB, p.opB == 2);
           }
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__(GemmCfg<CPLX>::THREADS, 2) gemm_dmma_kernel(co
     //      n = n0 + wn*32 + 16*(j>>1) + 2*(2t+c) + (j&1)
     const double alpha = p.alpha, beta = p.beta;
     const bool interior = (m0 + BM <= p.M) && (n0 + BN <= p.N) &&
-                          (p.cuplo == 0 || (p.cuplo == 1 && m0 >= n0 + BN - 1) || (p.cuplo == 2 && m0 + BM - 1 <= n0));
+                          (p.cuplo == 0 || (p.cuplo == 1 && m0 >= g0 + BN - 1) || (p.cuplo == 2 && m0 + BM - 1 <= g0));
     if (interior && p.vec_ok) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -258,8 +261,8 @@ __global__ void __launch_bounds__(GemmCfg<CPLX>::THREADS, 2) gemm_dmma_kernel(co
             const long long m = m0 + wm * 64 + 16 * (i >> 1) + 2 * g + (i & 1);
             const long long n = n0 + wn * 32 + 16 * (j >> 1) + 2 * (2 * t + c) + (j & 1);
             if (m >= p.M || n >= p.N) continue;
-            if (p.cuplo == 1 && m < n) continue;
-            if (p.cuplo == 2 && m > n) continue;
+            if (p.cuplo == 1 && m < n - n0 + g0) continue;
+            if (p.cuplo == 2 && m > n - n0 + g0) continue;
             double o = alpha * acc[i][j][c];
             if (!p.beta_zero) o += beta * p.C[n * p.ldc + m];
             p.D[n * p.ldd + m] = o;
@@ -312,8 +315,8 @@ __global__ void __launch_bounds__(GemmCfg<CPLX>::THREADS, 2) gemm_dmma_kernel(co
           const long long m = m0 + wm * 32 + 8 * i + g;
           const long long n = n0 + wn * 32 + 8 * j + 2 * t + c;
           if (m >= p.M || n >= p.N) continue;
-          if (p.cuplo == 1 && m < n) continue;
-          if (p.cuplo == 2 && m > n) continue;
+          if (p.cuplo == 1 && m < n - n0 + g0) continue;
+          if (p.cuplo == 2 && m > n - n0 + g0) continue;
           const double xr = accr[i][j][c], xi = acci[i][j][c];
           double2 o = make_double2(alpha.x * xr - alpha.y * xi, alpha.x * xi + alpha.y * xr);
           if (!p.beta_zero) {
@@ -321,7 +324,7 @@ __global__ void __launch_bounds__(GemmCfg<CPLX>::THREADS, 2) gemm_dmma_kernel(co
             o.x += beta.x * cv.x - beta.y * cv.y;
             o.y += beta.x * cv.y + beta.y * cv.x;
           }
-          if (p.herm && m == n) o.y = 0.0;
+          if (p.herm && m == n - n0 + g0) o.y = 0.0;
           p.D[n * p.ldd + m] = o;
         }
   }
@@ -374,8 +377,10 @@ static int launch_t(const chol_gemm_desc *d) {
   a.vec_ok = CPLX ? 1 : ((((uintptr_t)d->D & 15) == 0) && (d->ldd % 2 == 0) &&
                          (a.beta_zero || ((((uintptr_t)d->C & 15) == 0) && (d->ldc % 2 == 0))));
   a.conjB_regs = CPLX && d->opB == 'C';
+  a.cm.cnb = d->cyc_nb; a.cm.cP = d->cyc_p; a.cm.coff = d->cyc_off;
+  if (a.cm.cnb && (a.cm.cnb % Cfg::BN || a.cuplo == 2 || d->triA || d->triB || a.cm.cP < 1)) return (int)cudaErrorInvalidValue;
   const bool tma = !alpha_zero && tma_eligible<CPLX>(d);
-  const long long tiles = total_tiles<Cfg::R, Cfg::GROUP>(a.cuplo, a.NI, a.NJ);
+  const long long tiles = total_tiles<Cfg::BM, Cfg::BN, Cfg::GROUP>(a.cuplo, a.NI, a.NJ, a.cm);
   if (tiles <= 0) return 0;
   if (tiles > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
   cudaStream_t st = (cudaStream_t)d->stream;
@@ -389,6 +394,7 @@ static int launch_t(const chol_gemm_desc *d) {
     attr_set[dev & 63][CPLX][tma] = true;
   }
   kern<<<(unsigned)tiles, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a);
+  CHOL_COUNT_LAUNCH();
   return (int)cudaGetLastError();
 }
 
@@ -404,6 +410,28 @@ extern "C" int chol_gemm_launch(const chol_gemm_desc *d) {
     case 'c': return chol_gemm_fp32_launch(d);
     default: return (int)cudaErrorInvalidValue;
   }
+}
+
+// test hook (host only, no GPU needed): enumerate the tile schedule of the d-engine (128x64 tiles)
+// exactly as the kernel's CTAs decode it.  Writes (bi, bj) pairs of the VALID tiles, returns the
+// grid size; *nvalid receives the number of valid tiles.
+extern "C" long long chol_test_tile_schedule(int cuplo, int m, int n, int cyc_nb, int cyc_p, int cyc_off, int *out,
+                                             long long cap, long long *nvalid) {
+  using Cfg = chol::GemmCfg<false>;
+  chol::ColMap cm{cyc_nb, cyc_p, cyc_off};
+  const int cu = chol::tri_code(cuplo);
+  const int NI = (m + Cfg::BM - 1) / Cfg::BM, NJ = (n + Cfg::BN - 1) / Cfg::BN;
+  const long long tiles = chol::total_tiles<Cfg::BM, Cfg::BN, Cfg::GROUP>(cu, NI, NJ, cm);
+  long long v = 0;
+  for (long long t = 0; t < tiles; ++t) {
+    int bi, bj;
+    if (chol::tile_coords<Cfg::BM, Cfg::BN, Cfg::GROUP>(cu, NI, NJ, cm, t, bi, bj)) {
+      if (v < cap) { out[2 * v] = bi; out[2 * v + 1] = bj; }
+      ++v;
+    }
+  }
+  *nvalid = v;
+  return tiles;
 }
 
 extern "C" int chol_gemm_uses_tma(const chol_gemm_desc *d) {

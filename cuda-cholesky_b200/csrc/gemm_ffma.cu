@@ -14,6 +14,7 @@
 #include <stdint.h>
 
 #include "chol_kernels.h"
+#include "launch_count.h"
 #include "gemm_common.cuh"
 
 namespace chol {
@@ -38,6 +39,7 @@ struct FArgs {
   int M, N, K;
   T alpha, beta;
   int opA, opB, triA, triB, unitA, unitB, cuplo, herm, NI, NJ, vec_ok, beta_zero;
+  ColMap cm;
 };
 
 template <typename T>
@@ -48,8 +50,9 @@ __global__ void __launch_bounds__(256, 2) gemm_ffma_kernel(const FArgs<T> p) {
   __shared__ __align__(16) T Bs[2][BK * LDS];
 
   int bi, bj;
-  if (!tile_coords<1, 8>(p.cuplo, p.NI, p.NJ, (long long)blockIdx.x, bi, bj)) return;
+  if (!tile_coords<BM, BN, 8>(p.cuplo, p.NI, p.NJ, p.cm, (long long)blockIdx.x, bi, bj)) return;
   const int m0 = bi * BM, n0 = bj * BN;
+  const int g0 = (int)gcol(p.cm, n0);
   int kb = 0, ke = p.K;
   if (p.triA) {
     const bool lower = (p.triA == 1) == (p.opA == 0);
@@ -57,7 +60,7 @@ __global__ void __launch_bounds__(256, 2) gemm_ffma_kernel(const FArgs<T> p) {
   }
   if (p.triB) {
     const bool kgen = (p.triB == 1) == (p.opB == 0);
-    if (kgen) kb = max(kb, n0); else ke = min(ke, n0 + BN);
+    if (kgen) kb = max(kb, g0); else ke = min(ke, g0 + BN);
   }
   kb = (kb / BK) * BK;
   const int nk = ke > kb ? (ke - kb + BK - 1) / BK : 0;
@@ -82,8 +85,8 @@ __global__ void __launch_bounds__(256, 2) gemm_ffma_kernel(const FArgs<T> p) {
                            : fetch_stored<T>(p.A, p.lda, in, k, m, p.triA, p.unitA, p.opA == 2);
       int nn, kk2;
       if (p.opB != 0) { nn = idx % BN; kk2 = idx / BN; } else { kk2 = idx % BK; nn = idx / BK; }
-      const long long n = n0 + nn, k2 = k0 + kk2;
-      const bool inb = (n < p.N) && (k2 < ke);
+      const long long n = g0 + nn, k2 = k0 + kk2;
+      const bool inb = (n0 + nn < p.N) && (k2 < ke);
       rb[u] = (p.opB == 0) ? fetch_stored<T>(p.B, p.ldb, inb, k2, n, p.triB, p.unitB, false)
                            : fetch_stored<T>(p.B, p.ldb, inb, n, k2, p.triB, p.unitB, p.opB == 2);
     }
@@ -142,11 +145,11 @@ __global__ void __launch_bounds__(256, 2) gemm_ffma_kernel(const FArgs<T> p) {
     for (int i = 0; i < TM; ++i) {
       const long long m = m0 + (i / VW) * (BM / 2) + tx * VW + (i % VW);
       if (m >= p.M) continue;
-      if (p.cuplo == 1 && m < n) continue;
-      if (p.cuplo == 2 && m > n) continue;
+      if (p.cuplo == 1 && m < n - n0 + g0) continue;
+      if (p.cuplo == 2 && m > n - n0 + g0) continue;
       T o = mul(p.alpha, acc[i][j]);
       if (!p.beta_zero) fma_acc(o, p.beta, p.C[n * p.ldc + m]);
-      if constexpr (Cfg::CPLX) { if (p.herm && m == n) o.y = 0.f; }
+      if constexpr (Cfg::CPLX) { if (p.herm && m == n - n0 + g0) o.y = 0.f; }
       p.D[n * p.ldd + m] = o;
     }
   }
@@ -175,10 +178,13 @@ static int launch_f(const chol_gemm_desc *d) {
   a.NI = (a.M + Cfg::BM - 1) / Cfg::BM;
   a.NJ = (a.N + Cfg::BN - 1) / Cfg::BN;
   a.vec_ok = 0;
-  const long long tiles = total_tiles<1, 8>(a.cuplo, a.NI, a.NJ);
+  a.cm.cnb = d->cyc_nb; a.cm.cP = d->cyc_p; a.cm.coff = d->cyc_off;
+  if (a.cm.cnb && (a.cm.cnb % Cfg::BN || a.cuplo == 2 || d->triA || d->triB || a.cm.cP < 1)) return (int)cudaErrorInvalidValue;
+  const long long tiles = total_tiles<Cfg::BM, Cfg::BN, 8>(a.cuplo, a.NI, a.NJ, a.cm);
   if (tiles <= 0) return 0;
   if (tiles > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
   gemm_ffma_kernel<T><<<(unsigned)tiles, 256, 0, (cudaStream_t)d->stream>>>(a);
+  CHOL_COUNT_LAUNCH();
   return (int)cudaGetLastError();
 }
 

@@ -14,6 +14,7 @@
 #include <stdint.h>
 
 #include "chol_kernels.h"
+#include "launch_count.h"
 #include "ptx_sm100.cuh"
 #include "scalar_ops.cuh"
 
@@ -269,6 +270,7 @@ static int potf2_t(int uplo, size_t n, void *A, size_t lda, long *dinfo, long ba
   const size_t sm = panel_smem<T>(n, 0);
   int e = set_smem(potf2_kernel<T>, sm); if (e) return e;
   potf2_kernel<T><<<1, PANEL_THREADS, sm, st>>>(uplo == 'U', (int)n, (T *)A, (long long)lda, dinfo, base);
+  CHOL_COUNT_LAUNCH();
   return (int)cudaGetLastError();
 }
 template <typename T>
@@ -276,6 +278,7 @@ static int trti2_t(int uplo, int diag, size_t n, const void *A, size_t lda, void
   const size_t sm = panel_smem<T>(n, n);
   int e = set_smem(trti2_kernel<T>, sm); if (e) return e;
   trti2_kernel<T><<<1, PANEL_THREADS, sm, st>>>(uplo == 'U', diag == 'U', (int)n, (const T *)A, (long long)lda, (T *)B, (long long)ldb, zo, dinfo, base);
+  CHOL_COUNT_LAUNCH();
   return (int)cudaGetLastError();
 }
 template <typename T>
@@ -283,6 +286,7 @@ static int lauu2_t(int uplo, size_t n, void *A, size_t lda, cudaStream_t st) {
   const size_t sm = panel_smem<T>(n, 0);
   int e = set_smem(lauu2_kernel<T>, sm); if (e) return e;
   lauu2_kernel<T><<<1, PANEL_THREADS, sm, st>>>(uplo == 'U', (int)n, (T *)A, (long long)lda);
+  CHOL_COUNT_LAUNCH();
   return (int)cudaGetLastError();
 }
 template <typename T>
@@ -291,6 +295,7 @@ static int copy_t(int trans, int uplo, size_t m, size_t n, const void *A, size_t
   const int tc = trans == 'N' ? 0 : (trans == 'T' ? 1 : 2);
   const int uc = uplo == 'L' ? 1 : (uplo == 'U' ? 2 : (uplo == 'l' ? 3 : (uplo == 'u' ? 4 : 0)));
   copy_kernel<T><<<grid, 256, 0, st>>>(tc, uc, (int)m, (int)n, (const T *)A, (long long)lda, (T *)B, (long long)ldb);
+  CHOL_COUNT_LAUNCH();
   return (int)cudaGetLastError();
 }
 template <typename T>
@@ -298,6 +303,7 @@ static int fill_t(int uplo, size_t m, size_t n, T v, void *A, size_t lda, cudaSt
   dim3 grid((unsigned)((m + 31) / 32), (unsigned)((n + 31) / 32));
   const int uc = uplo == 'L' ? 1 : (uplo == 'U' ? 2 : 0);
   fill_kernel<T><<<grid, 256, 0, st>>>(uc, (int)m, (int)n, v, (T *)A, (long long)lda);
+  CHOL_COUNT_LAUNCH();
   return (int)cudaGetLastError();
 }
 template <typename T>
@@ -306,6 +312,7 @@ static int logdet_t(const void *x, size_t incx, size_t n, void *res, void *scr, 
   int blocks = (int)(want < 1 ? 1 : (want > LOGDET_BLOCKS ? LOGDET_BLOCKS : want));
   logdet_kernel<T><<<blocks, LOGDET_THREADS, 0, st>>>((const T *)x, (long long)incx, (long long)n,
                                                     (typename ScalarOf<T>::Real *)res, (LogdetScratch *)scr);
+  CHOL_COUNT_LAUNCH();
   return (int)cudaGetLastError();
 }
 
@@ -321,6 +328,13 @@ using namespace chol;
     case 'z': { using T = double2; return CALL; }   \
     default: return (int)cudaErrorInvalidValue;     \
   }
+
+extern "C" { unsigned long long chol_launch_counter = 0; }
+extern "C" unsigned long long chol_launch_count(int reset) {
+  const unsigned long long v = chol_launch_counter;
+  if (reset) chol_launch_counter = 0;
+  return v;
+}
 
 extern "C" int chol_diag_max(int prec) { return prec == 'z' ? 64 : 128; }
 

@@ -41,6 +41,7 @@ CUresult chol_gemm_ex(int prec, int opA, int opB, int triA, int unitA, int triB,
   d.D = (void *)D; d.ldd = ldd;
   d.stream = (void *)stream;
   d.force_generic = 0;
+  d.cyc_nb = d.cyc_p = d.cyc_off = 0;
   RT_CHECK(chol_gemm_launch(&d));
   return CUDA_SUCCESS;
 }

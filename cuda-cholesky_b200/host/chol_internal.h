@@ -43,6 +43,14 @@ struct __culapackhandle_st {
   CUdeviceptr logdet_scr; /* reduction scratch + result */
   void *hlogdet;          /* pinned */
   size_t nb;              /* outer block size (0 = default per precision) */
+  /* optional per-launch timing of the dominant kernel (the trailing-matrix update): CUDA events
+   * recorded on the stream the kernel is launched on; read back by bench.py for the roofline */
+  int profile;
+  int prof_n, prof_cap;
+  CUevent *prof_e0, *prof_e1;
+  double *prof_flops;
+  double prof_total_ms, prof_total_flops;
+  int prof_launches;
 };
 
 static inline size_t chol_esize(int prec) { return prec == 's' ? 4 : (prec == 'z' ? 16 : 8); }
@@ -80,6 +88,24 @@ CUresult chol_trmm2(int prec, int side, int uplo, int trans, int diag, size_t m,
                     CUdeviceptr A, size_t lda, CUdeviceptr B, size_t ldb, CUdeviceptr X, size_t ldx, CUstream stream);
 CUresult chol_trsm(CUBLAShandle h, int prec, int side, int uplo, int trans, int diag, size_t m, size_t n,
                    const double alpha[2], CUdeviceptr A, size_t lda, CUdeviceptr B, size_t ldb, CUstream stream);
+
+/* workspace layout of one LAPACK call */
+typedef struct chol_ws {
+  size_t nb, db, ldw, es;
+  CUdeviceptr W[2]; /* panel buffers, ldw x nb */
+  CUdeviceptr Xd;   /* nb x nb : inverse of the diagonal block (other triangle zero) */
+  CUdeviceptr T1;   /* nb x nb : temporary of the blocked small inverse */
+  CUdeviceptr Tinv; /* db x db : inverse of a potf2 sub-block */
+  CUdeviceptr Wd;   /* nb x db : panel of the diagonal-block recursion */
+} chol_ws;
+
+size_t chol_default_nb(int prec);
+CUresult chol_carve(CULAPACKhandle h, int prec, size_t n, chol_ws *w);
+/* Cholesky of a jb x jb (jb <= nb) diagonal block / out-of-place inverse of one (other triangle zero) */
+CUresult chol_potrf_diag(int prec, int uplo, size_t jb, CUdeviceptr A, size_t lda, long *dinfo, long base,
+                         const chol_ws *w, CUstream st);
+CUresult chol_trtri_small(int prec, int uplo, int diag, size_t jb, CUdeviceptr A, size_t lda, CUdeviceptr X,
+                          size_t ldx, long *dinfo, long base, const chol_ws *w, CUstream st);
 
 /* ---- precision-generic LAPACK cores (lapack.c) ---- */
 CUresult chol_potrf(CULAPACKhandle h, int prec, int uplo, size_t n, CUdeviceptr A, size_t lda, long *info);

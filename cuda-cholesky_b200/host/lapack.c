@@ -28,21 +28,11 @@ static const double ONE[2] = {1.0, 0.0};
 static const double ZERO[2] = {0.0, 0.0};
 static const double MONE[2] = {-1.0, 0.0};
 
-static size_t default_nb(int prec) { return prec == 'z' ? 128 : 256; }
+size_t chol_default_nb(int prec) { return prec == 'z' ? 128 : 256; }
 
-/* workspace layout of one LAPACK call */
-typedef struct {
-  size_t nb, db, ldw, es;
-  CUdeviceptr W[2]; /* panel buffers, ldw x nb */
-  CUdeviceptr Xd;   /* nb x nb : inverse of the diagonal block (other triangle zero) */
-  CUdeviceptr T1;   /* nb x nb : temporary of the blocked small inverse */
-  CUdeviceptr Tinv; /* db x db : inverse of a potf2 sub-block */
-  CUdeviceptr Wd;   /* nb x db : panel of the diagonal-block recursion */
-} ws_t;
-
-static CUresult carve(CULAPACKhandle h, int prec, size_t n, ws_t *w) {
+CUresult chol_carve(CULAPACKhandle h, int prec, size_t n, chol_ws *w) {
   w->es = chol_esize(prec);
-  w->nb = h->nb ? h->nb : default_nb(prec);
+  w->nb = h->nb ? h->nb : chol_default_nb(prec);
   w->db = (size_t)chol_diag_max(prec);
   if (w->nb < w->db) w->db = w->nb;
   w->ldw = chol_roundup(n > w->nb ? n : w->nb, 16);
@@ -69,8 +59,8 @@ static CUresult finish_info(CULAPACKhandle h, CUstream producer, long *info) {
 }
 
 /* Cholesky of a jb x jb (jb <= nb) diagonal block, blocked by db on one stream */
-static CUresult potrf_diag(int prec, int uplo, size_t jb, CUdeviceptr A, size_t lda, long *dinfo, long base,
-                           const ws_t *w, CUstream st) {
+CUresult chol_potrf_diag(int prec, int uplo, size_t jb, CUdeviceptr A, size_t lda, long *dinfo, long base,
+                         const chol_ws *w, CUstream st) {
   const size_t es = w->es, db = w->db;
   const int herm = chol_is_complex(prec);
   for (size_t i = 0; i < jb; i += db) {
@@ -97,8 +87,8 @@ static CUresult potrf_diag(int prec, int uplo, size_t jb, CUdeviceptr A, size_t 
 }
 
 /* X (jb x jb, ldx, other triangle zero) = inverse of the triangular jb x jb block A, jb <= nb */
-static CUresult trtri_small(int prec, int uplo, int diag, size_t jb, CUdeviceptr A, size_t lda, CUdeviceptr X,
-                            size_t ldx, long *dinfo, long base, const ws_t *w, CUstream st) {
+CUresult chol_trtri_small(int prec, int uplo, int diag, size_t jb, CUdeviceptr A, size_t lda, CUdeviceptr X,
+                          size_t ldx, long *dinfo, long base, const chol_ws *w, CUstream st) {
   const size_t es = w->es, db = w->db, nblk = (jb + db - 1) / db;
   if (nblk > 1) RT_CHECK(chol_fill_launch(prec, 0, jb, jb, 0.0, 0.0, (void *)X, ldx, (void *)st));
   for (size_t b = 0; b < nblk; b++) {
@@ -129,14 +119,15 @@ static CUresult trtri_small(int prec, int uplo, int diag, size_t jb, CUdeviceptr
 
 /* ------------------------------------------------------------------------------------------ */
 CUresult chol_potrf(CULAPACKhandle h, int prec, int uplo, size_t n, CUdeviceptr A, size_t lda, long *info) {
-  ws_t w;
+  chol_ws w;
   CU_ERROR_CHECK(cuCtxPushCurrent(h->context));
-  CU_ERROR_CHECK(carve(h, prec, n, &w));
+  CU_ERROR_CHECK(chol_carve(h, prec, n, &w));
   const size_t es = w.es, nb = w.nb;
   const int herm = chol_is_complex(prec);
   long *dinfo = (long *)h->dinfo;
   CUstream sp = h->s_panel, su = h->s_update;
   CU_ERROR_CHECK(cuMemsetD8Async(h->dinfo, 0, sizeof(long), sp));
+  h->prof_n = 0;
 
   size_t step = 0;
   for (size_t j = 0; j < n; j += nb, step++) {
@@ -144,9 +135,9 @@ CUresult chol_potrf(CULAPACKhandle h, int prec, int uplo, size_t n, CUdeviceptr 
     const CUdeviceptr Ajj = chol_at(A, lda, j, j, es);
     const CUdeviceptr W = w.W[step & 1];
     /* --- panel stream: diagonal block, its inverse, panel solve into W, write-back --- */
-    CU_ERROR_CHECK(potrf_diag(prec, uplo, jb, Ajj, lda, dinfo, (long)j, &w, sp));
+    CU_ERROR_CHECK(chol_potrf_diag(prec, uplo, jb, Ajj, lda, dinfo, (long)j, &w, sp));
     if (rest == 0) break;
-    CU_ERROR_CHECK(trtri_small(prec, uplo, 'N', jb, Ajj, lda, w.Xd, nb, dinfo, (long)j, &w, sp));
+    CU_ERROR_CHECK(chol_trtri_small(prec, uplo, 'N', jb, Ajj, lda, w.Xd, nb, dinfo, (long)j, &w, sp));
     if (uplo == 'L') {
       const CUdeviceptr P = chol_at(A, lda, j + jb, j, es); /* rest x jb */
       CU_ERROR_CHECK(chol_gemm(prec, 'N', 'C', rest, jb, jb, ONE, P, lda, w.Xd, nb, ZERO, 0, 0, W, w.ldw, sp));
@@ -165,8 +156,14 @@ CUresult chol_potrf(CULAPACKhandle h, int prec, int uplo, size_t n, CUdeviceptr 
       CU_ERROR_CHECK(cuStreamWaitEvent(su, h->ev_panel[step % CHOL_EVENT_RING], 0));
       const CUdeviceptr W2 = chol_at(W, w.ldw, jb2, 0, es);
       const CUdeviceptr A33 = chol_at(A, lda, j + jb + jb2, j + jb + jb2, es);
+      const bool prof = h->profile && h->prof_n < h->prof_cap;
+      if (prof) CU_ERROR_CHECK(cuEventRecord(h->prof_e0[h->prof_n], su));
       CU_ERROR_CHECK(chol_gemm_ex(prec, 'N', 'C', 0, 0, 0, 0, uplo, herm, rest2, rest2, jb, MONE, W2, w.ldw, W2, w.ldw, ONE,
                                   A33, lda, A33, lda, su));
+      if (prof) {
+        CU_ERROR_CHECK(cuEventRecord(h->prof_e1[h->prof_n], su));
+        h->prof_flops[h->prof_n++] = (double)rest2 * (double)(rest2 + 1) * (double)jb * (herm ? 4.0 : 1.0);
+      }
       CU_ERROR_CHECK(cuEventRecord(h->ev_rest[step % CHOL_EVENT_RING], su));
     }
     /* the look-ahead block was last written by the previous step's trailing update */
@@ -182,6 +179,14 @@ CUresult chol_potrf(CULAPACKhandle h, int prec, int uplo, size_t n, CUdeviceptr 
     }
   }
   CU_ERROR_CHECK(finish_info(h, sp, info));
+  for (int i = 0; i < h->prof_n; i++) { /* the streams are idle: all events have completed */
+    float ms = 0.f;
+    CU_ERROR_CHECK(cuEventElapsedTime(&ms, h->prof_e0[i], h->prof_e1[i]));
+    h->prof_total_ms += ms;
+    h->prof_total_flops += h->prof_flops[i];
+    h->prof_launches++;
+  }
+  h->prof_n = 0;
   CUcontext dummy;
   CU_ERROR_CHECK(cuCtxPopCurrent(&dummy));
   return CUDA_SUCCESS;
@@ -189,9 +194,9 @@ CUresult chol_potrf(CULAPACKhandle h, int prec, int uplo, size_t n, CUdeviceptr 
 
 /* ------------------------------------------------------------------------------------------ */
 CUresult chol_trtri(CULAPACKhandle h, int prec, int uplo, int diag, size_t n, CUdeviceptr A, size_t lda, long *info) {
-  ws_t w;
+  chol_ws w;
   CU_ERROR_CHECK(cuCtxPushCurrent(h->context));
-  CU_ERROR_CHECK(carve(h, prec, n, &w));
+  CU_ERROR_CHECK(chol_carve(h, prec, n, &w));
   const size_t es = w.es, nb = w.nb;
   long *dinfo = (long *)h->dinfo;
   CUstream st = h->s_update;
@@ -203,7 +208,7 @@ CUresult chol_trtri(CULAPACKhandle h, int prec, int uplo, int diag, size_t n, CU
     const size_t blk = (uplo == 'L') ? nblk - 1 - b : b; /* reference sweep: lapack/dtrtri.c:119,:137 */
     const size_t j = blk * nb, jb = chol_min(nb, n - j);
     const CUdeviceptr Ajj = chol_at(A, lda, j, j, es);
-    CU_ERROR_CHECK(trtri_small(prec, uplo, diag, jb, Ajj, lda, w.Xd, nb, dinfo, (long)j, &w, st));
+    CU_ERROR_CHECK(chol_trtri_small(prec, uplo, diag, jb, Ajj, lda, w.Xd, nb, dinfo, (long)j, &w, st));
     if (uplo == 'L') {
       const size_t rest = n - j - jb;
       if (rest) { /* A21 = -inv(A22) * (A21 * inv(A11)) ; inv(A22) is already in place */
@@ -229,9 +234,9 @@ CUresult chol_trtri(CULAPACKhandle h, int prec, int uplo, int diag, size_t n, CU
 
 /* ------------------------------------------------------------------------------------------ */
 CUresult chol_lauum(CULAPACKhandle h, int prec, int uplo, size_t n, CUdeviceptr A, size_t lda, long *info) {
-  ws_t w;
+  chol_ws w;
   CU_ERROR_CHECK(cuCtxPushCurrent(h->context));
-  CU_ERROR_CHECK(carve(h, prec, n, &w));
+  CU_ERROR_CHECK(chol_carve(h, prec, n, &w));
   const size_t es = w.es, nb = w.nb;
   const int herm = chol_is_complex(prec);
   CUstream st = h->s_update;

@@ -1,0 +1,731 @@
+/*
+ * multigpu.c — the multi-GPU runtime and the distributed Cholesky.
+ *
+ * Replaces reference multigpu/multigpu.c (pthread-per-GPU ring-buffer scheduler, :13-538) and the
+ * cuMultiGPU* drivers built on it (lapack/dpotrf.c:298-366, blas/dgemm.c:211-566), which deal C
+ * tiles round-robin to the GPUs and stage EVERY tile over PCIe in both directions each step.
+ *
+ * Here:
+ *   - the API keeps the reference's signatures: CUtask, CUmultiGPU (include/cumultigpu.h) and
+ *     cuMultiGPU{S,D,C,Z}potrf (include/lapack.h) with the matrix in HOST memory;
+ *   - the matrix is scattered ONCE into a 1-D block-cyclic layout (block column c lives on GPU
+ *     c mod P, packed side by side, resident in HBM), factored there, and gathered once;
+ *   - per step the owner factors the diagonal block and solves the panel into a contiguous buffer
+ *     W; W is broadcast GPU-to-GPU over NVLink with ncclBroadcast on the high-priority panel
+ *     stream; every GPU then updates all the block columns it owns with ONE block-cyclic-aware
+ *     launch of the DMMA tile engine (csrc/gemm_common.cuh ColMap);
+ *   - depth-1 look-ahead: the owner of the next block column updates that column first, factors
+ *     it and starts its broadcast while all GPUs are still busy with the current trailing update;
+ *   - the same SPMD core serves (a) one worker thread per GPU inside one process (cuMultiGPU*, the
+ *     reference's model) and (b) one process per GPU (cholDist*, used under torchrun: the NCCL
+ *     unique id is exchanged by the launcher).
+ * Upper-triangular inputs are transposed on the way in and out (U^H is a lower factor), so the
+ * distributed core only ever sees the lower form.
+ */
+#define _GNU_SOURCE
+#include <complex.h>
+#include <dlfcn.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "chol_internal.h"
+
+static const double ONE[2] = {1.0, 0.0};
+static const double ZERO[2] = {0.0, 0.0};
+static const double MONE[2] = {-1.0, 0.0};
+
+/* =============================================================================================
+ * NCCL, bound at run time (dlopen by soname: inside a PyTorch process this resolves to the copy
+ * torch already loaded).  Only what the panel broadcast needs.
+ * ===========================================================================================*/
+typedef struct { char internal[128]; } chol_nccl_id;
+typedef void *chol_nccl_comm;
+static struct {
+  int loaded;
+  int (*GetUniqueId)(chol_nccl_id *);
+  int (*CommInitRank)(chol_nccl_comm *, int, chol_nccl_id, int);
+  int (*CommInitAll)(chol_nccl_comm *, int, const int *);
+  int (*CommDestroy)(chol_nccl_comm);
+  int (*Broadcast)(const void *, void *, size_t, int, int, chol_nccl_comm, CUstream);
+  int (*GroupStart)(void);
+  int (*GroupEnd)(void);
+  const char *(*GetErrorString)(int);
+} nccl;
+static pthread_mutex_t nccl_lock = PTHREAD_MUTEX_INITIALIZER;
+#define CHOL_NCCL_UINT8 1
+
+static const char *nccl_strerror(int e) { return nccl.GetErrorString ? nccl.GetErrorString(e) : "NCCL error"; }
+
+static CUresult nccl_load(void) {
+  pthread_mutex_lock(&nccl_lock);
+  if (!nccl.loaded) {
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (h == NULL) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (h != NULL) {
+      nccl.GetUniqueId = (int (*)(chol_nccl_id *))dlsym(h, "ncclGetUniqueId");
+      nccl.CommInitRank = (int (*)(chol_nccl_comm *, int, chol_nccl_id, int))dlsym(h, "ncclCommInitRank");
+      nccl.CommInitAll = (int (*)(chol_nccl_comm *, int, const int *))dlsym(h, "ncclCommInitAll");
+      nccl.CommDestroy = (int (*)(chol_nccl_comm))dlsym(h, "ncclCommDestroy");
+      nccl.Broadcast = (int (*)(const void *, void *, size_t, int, int, chol_nccl_comm, CUstream))dlsym(h, "ncclBroadcast");
+      nccl.GroupStart = (int (*)(void))dlsym(h, "ncclGroupStart");
+      nccl.GroupEnd = (int (*)(void))dlsym(h, "ncclGroupEnd");
+      nccl.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+      nccl.loaded = nccl.GetUniqueId && nccl.CommInitRank && nccl.CommInitAll && nccl.CommDestroy && nccl.Broadcast &&
+                    nccl.GroupStart && nccl.GroupEnd;
+    }
+  }
+  pthread_mutex_unlock(&nccl_lock);
+  if (!nccl.loaded) {
+    if (errorHandler != NULL)
+      errorHandler("dlopen(libnccl.so.2)", __func__, __FILE__, __LINE__, -1, (const char *(*)(int))nccl_strerror);
+    return CUDA_ERROR_NOT_SUPPORTED;
+  }
+  return CUDA_SUCCESS;
+}
+#define NCCL_CHECK(call)                                                                                       \
+  do {                                                                                                         \
+    int __n__ = (call);                                                                                        \
+    if (__n__ != 0) {                                                                                          \
+      if (errorHandler != NULL) errorHandler(STRING(call), __func__, __FILE__, __LINE__, __n__, nccl_strerror); \
+      return CUDA_ERROR_UNKNOWN;                                                                               \
+    }                                                                                                          \
+  } while (false)
+
+/* =============================================================================================
+ * CUtask  (reference multigpu/multigpu.c:297-400)
+ * ===========================================================================================*/
+struct __cutask_st {
+  CUresult (*function)(const void *);
+  void *args;
+  CUresult result;
+  bool complete;
+  pthread_mutex_t mutex;
+  pthread_cond_t cond;
+  struct __cutask_st *next; /* queue link */
+};
+
+CUresult cuTaskCreate(CUtask *task, CUresult (*function)(const void *), const void *args, size_t size) {
+  if (task == NULL || function == NULL || (args == NULL && size > 0)) return CUDA_ERROR_INVALID_VALUE;
+  struct __cutask_st *t = malloc(sizeof *t);
+  if (t == NULL) return CUDA_ERROR_OUT_OF_MEMORY;
+  t->function = function;
+  t->args = NULL;
+  if (size > 0) {
+    if ((t->args = malloc(size)) == NULL) {
+      free(t);
+      return CUDA_ERROR_OUT_OF_MEMORY;
+    }
+    memcpy(t->args, args, size);
+  }
+  t->result = CUDA_SUCCESS;
+  t->complete = false;
+  t->next = NULL;
+  pthread_mutex_init(&t->mutex, NULL);
+  pthread_cond_init(&t->cond, NULL);
+  *task = t;
+  return CUDA_SUCCESS;
+}
+
+CUresult cuTaskExecute(CUtask t) {
+  if (t == NULL) return CUDA_ERROR_INVALID_VALUE;
+  const CUresult r = t->function(t->args);
+  ERROR_CHECK(pthread_mutex_lock(&t->mutex));
+  t->result = r;
+  t->complete = true;
+  pthread_cond_broadcast(&t->cond);
+  ERROR_CHECK(pthread_mutex_unlock(&t->mutex));
+  return CUDA_SUCCESS;
+}
+
+CUresult cuTaskDestroy(CUtask t, CUresult *result) {
+  if (t == NULL) return CUDA_ERROR_INVALID_VALUE;
+  ERROR_CHECK(pthread_mutex_lock(&t->mutex));
+  while (!t->complete) pthread_cond_wait(&t->cond, &t->mutex);
+  ERROR_CHECK(pthread_mutex_unlock(&t->mutex));
+  if (result != NULL) *result = t->result;
+  pthread_mutex_destroy(&t->mutex);
+  pthread_cond_destroy(&t->cond);
+  free(t->args);
+  free(t);
+  return CUDA_SUCCESS;
+}
+
+/* =============================================================================================
+ * CUmultiGPU: one worker thread per device, FIFO of tasks  (reference multigpu.c:128-292, :405-538)
+ * ===========================================================================================*/
+struct chol_rank; /* per-GPU state of the distributed solver, below */
+
+struct worker {
+  pthread_t thread;
+  pthread_mutex_t mutex;
+  pthread_cond_t cond;
+  struct __cutask_st *head, *tail;
+  bool stop;
+  CUdevice device;
+  CUcontext context;
+  CUresult error; /* first failing task result is latched (reference multigpu.c:139-147) */
+};
+
+struct __cumultigpu_st {
+  int n;
+  struct worker *w;
+  struct chol_rank *ranks; /* created on first multi-GPU LAPACK call */
+  chol_nccl_comm *comms;
+};
+
+static void *worker_main(void *arg) {
+  struct worker *w = arg;
+  cuCtxSetCurrent(w->context);
+  for (;;) {
+    pthread_mutex_lock(&w->mutex);
+    while (w->head == NULL && !w->stop) pthread_cond_wait(&w->cond, &w->mutex);
+    struct __cutask_st *t = w->head;
+    if (t != NULL) {
+      w->head = t->next;
+      if (w->head == NULL) w->tail = NULL;
+    }
+    const bool stop = (t == NULL) && w->stop;
+    pthread_mutex_unlock(&w->mutex);
+    if (stop) break;
+    cuTaskExecute(t);
+    if (t->result != CUDA_SUCCESS && w->error == CUDA_SUCCESS) w->error = t->result;
+  }
+  return NULL;
+}
+
+int cuMultiGPUGetContextCount(CUmultiGPU m) { return m == NULL ? 0 : m->n; }
+
+CUresult cuMultiGPUCreate(CUmultiGPU *mGPU, CUdevice *devices, int n) {
+  if (mGPU == NULL || devices == NULL || n <= 0) return CUDA_ERROR_INVALID_VALUE;
+  CU_ERROR_CHECK(cuInit(0));
+  struct __cumultigpu_st *m = calloc(1, sizeof *m);
+  if (m == NULL) return CUDA_ERROR_OUT_OF_MEMORY;
+  m->w = calloc((size_t)n, sizeof *m->w);
+  if (m->w == NULL) {
+    free(m);
+    return CUDA_ERROR_OUT_OF_MEMORY;
+  }
+  for (int i = 0; i < n; i++) {
+    struct worker *w = &m->w[i];
+    w->device = devices[i];
+    CUresult e = cuDevicePrimaryCtxRetain(&w->context, w->device);
+    if (e == CUDA_SUCCESS) {
+      pthread_mutex_init(&w->mutex, NULL);
+      pthread_cond_init(&w->cond, NULL);
+      if (pthread_create(&w->thread, NULL, worker_main, w) != 0) e = CUDA_ERROR_OPERATING_SYSTEM;
+    }
+    if (e != CUDA_SUCCESS) {
+      m->n = i;
+      cuMultiGPUDestroy(m);
+      CU_ERROR_CHECK(e);
+    }
+  }
+  m->n = n;
+  *mGPU = m;
+  return CUDA_SUCCESS;
+}
+
+CUresult cuMultiGPURunTask(CUmultiGPU m, int i, CUtask task) {
+  if (m == NULL || task == NULL || i < 0 || i >= m->n) return CUDA_ERROR_INVALID_VALUE;
+  struct worker *w = &m->w[i];
+  ERROR_CHECK(pthread_mutex_lock(&w->mutex));
+  task->next = NULL;
+  if (w->tail) w->tail->next = task; else w->head = task;
+  w->tail = task;
+  pthread_cond_signal(&w->cond);
+  ERROR_CHECK(pthread_mutex_unlock(&w->mutex));
+  return CUDA_SUCCESS;
+}
+
+static CUresult sync_task(const void *args) {
+  (void)args;
+  return cuCtxSynchronize();
+}
+
+/* run `fn(args_i)` on every worker and wait; returns the first failure */
+static CUresult run_on_all(CUmultiGPU m, CUresult (*fn)(const void *), const void *args, size_t stride, size_t size) {
+  CUtask *tasks = calloc((size_t)m->n, sizeof *tasks);
+  if (tasks == NULL) return CUDA_ERROR_OUT_OF_MEMORY;
+  CUresult first = CUDA_SUCCESS;
+  int launched = 0;
+  for (int i = 0; i < m->n && first == CUDA_SUCCESS; i++) {
+    first = cuTaskCreate(&tasks[i], fn, args ? (const char *)args + (size_t)i * stride : NULL, size);
+    if (first == CUDA_SUCCESS) first = cuMultiGPURunTask(m, i, tasks[i]);
+    if (first == CUDA_SUCCESS) launched++;
+  }
+  for (int i = 0; i < launched; i++) {
+    CUresult r = CUDA_SUCCESS;
+    cuTaskDestroy(tasks[i], &r);
+    if (first == CUDA_SUCCESS && r != CUDA_SUCCESS) first = r;
+  }
+  free(tasks);
+  return first;
+}
+
+CUresult cuMultiGPUSynchronize(CUmultiGPU m) {
+  if (m == NULL) return CUDA_ERROR_INVALID_VALUE;
+  CUresult r = run_on_all(m, sync_task, NULL, 0, 0);
+  for (int i = 0; i < m->n && r == CUDA_SUCCESS; i++) {
+    r = m->w[i].error;
+    m->w[i].error = CUDA_SUCCESS;
+  }
+  return r;
+}
+
+/* =============================================================================================
+ * The SPMD distributed POTRF (lower form, 1-D block-cyclic block columns)
+ * ===========================================================================================*/
+typedef struct chol_rank {
+  int rank, nranks;
+  CUcontext context;
+  chol_nccl_comm comm; /* NULL when nranks == 1 */
+  CULAPACKhandle lap;
+  CUdeviceptr local;   /* single-process mode: the rank's packed block columns */
+  size_t local_bytes;
+} chol_rank;
+
+/* number of columns rank r owns of an n-column matrix with block size nb over P ranks */
+static size_t local_cols(size_t n, size_t nb, int r, int P) {
+  const size_t nblk = (n + nb - 1) / nb;
+  size_t cols = 0;
+  for (size_t c = (size_t)r; c < nblk; c += (size_t)P) cols += chol_min(nb, n - c * nb);
+  return cols;
+}
+
+static CUresult gemm_cyc(int prec, int herm, size_t m, size_t n, size_t k, CUdeviceptr W, size_t ldw, CUdeviceptr D,
+                         size_t ldd, int cnb, int cP, CUstream st) {
+  chol_gemm_desc d;
+  memset(&d, 0, sizeof d);
+  d.prec = prec;
+  d.opA = 'N';
+  d.opB = 'C';
+  d.cuplo = 'L';
+  d.herm = herm;
+  d.m = m; d.n = n; d.k = k;
+  d.alpha[0] = -1.0;
+  d.beta[0] = 1.0;
+  d.A = (const void *)W; d.lda = ldw;
+  d.B = (const void *)W; d.ldb = ldw;
+  d.C = (const void *)D; d.ldc = ldd;
+  d.D = (void *)D; d.ldd = ldd;
+  d.stream = (void *)st;
+  d.cyc_nb = cnb; d.cyc_p = cP; d.cyc_off = 0;
+  RT_CHECK(chol_gemm_launch(&d));
+  return CUDA_SUCCESS;
+}
+
+/* A_loc: this rank's block columns (global block c = lc*P + rank at local columns lc*nb...),
+ * n rows, leading dimension ldl.  Factor in place (lower).  *info = local failure (global column,
+ * 1-based) or 0. */
+static CUresult dist_potrf(chol_rank *R, int prec, size_t n, CUdeviceptr Aloc, size_t ldl, long *info) {
+  CULAPACKhandle h = R->lap;
+  const int P = R->nranks, me = R->rank;
+  chol_ws w;
+  CU_ERROR_CHECK(chol_carve(h, prec, n, &w));
+  const size_t es = w.es, nb = w.nb, nblk = (n + nb - 1) / nb;
+  const int herm = chol_is_complex(prec);
+  long *dinfo = (long *)h->dinfo;
+  CUstream sp = h->s_panel, su = h->s_update;
+  const size_t my_cols = local_cols(n, nb, me, P);
+  CU_ERROR_CHECK(cuMemsetD8Async(h->dinfo, 0, sizeof(long), sp));
+  h->prof_n = 0;
+
+  for (size_t c = 0; c < nblk; c++) {
+    const size_t j = c * nb, jb = chol_min(nb, n - j), rest = n - j - jb;
+    const int owner = (int)(c % (size_t)P);
+    const CUdeviceptr W = w.W[c & 1];
+    const size_t ldw = chol_roundup(rest ? rest : 1, 16);
+    /* W's buffer was last read by the trailing update of step c-2 */
+    if (c >= 2) CU_ERROR_CHECK(cuStreamWaitEvent(sp, h->ev_rest[(c - 2) % CHOL_EVENT_RING], 0));
+    if (me == owner) {
+      const size_t lc = c / (size_t)P;
+      const CUdeviceptr Ajj = chol_at(Aloc, ldl, j, lc * nb, es);
+      CU_ERROR_CHECK(chol_potrf_diag(prec, 'L', jb, Ajj, ldl, dinfo, (long)j, &w, sp));
+      if (rest) {
+        const CUdeviceptr Pn = chol_at(Aloc, ldl, j + jb, lc * nb, es);
+        CU_ERROR_CHECK(chol_trtri_small(prec, 'L', 'N', jb, Ajj, ldl, w.Xd, nb, dinfo, (long)j, &w, sp));
+        CU_ERROR_CHECK(chol_gemm(prec, 'N', 'C', rest, jb, jb, ONE, Pn, ldl, w.Xd, nb, ZERO, 0, 0, W, ldw, sp));
+        RT_CHECK(chol_copy_launch(prec, 'N', 0, rest, jb, (const void *)W, ldw, (void *)Pn, ldl, (void *)sp));
+      }
+    }
+    if (rest == 0) break;
+    if (P > 1) /* the factored panel travels GPU-to-GPU over NVLink */
+      NCCL_CHECK(nccl.Broadcast((const void *)W, (void *)W, ldw * jb * es, CHOL_NCCL_UINT8, owner, R->comm, sp));
+    CU_ERROR_CHECK(cuEventRecord(h->ev_panel[c % CHOL_EVENT_RING], sp));
+
+    /* trailing update of every owned block column with global index >= c+2, one launch */
+    const size_t lc2 = (c + 2 > (size_t)me) ? (c + 2 - (size_t)me + (size_t)P - 1) / (size_t)P : 0;
+    const size_t col2 = lc2 * nb;
+    if (col2 < my_cols) {
+      const size_t g_first = (lc2 * (size_t)P + (size_t)me) * nb; /* global column of local column col2 */
+      const size_t m2 = n - g_first, n2 = my_cols - col2;
+      const CUdeviceptr W2 = chol_at(W, ldw, g_first - (j + jb), 0, es);
+      const CUdeviceptr D = chol_at(Aloc, ldl, g_first, col2, es);
+      CU_ERROR_CHECK(cuStreamWaitEvent(su, h->ev_panel[c % CHOL_EVENT_RING], 0));
+      const bool prof = h->profile && h->prof_n < h->prof_cap;
+      if (prof) CU_ERROR_CHECK(cuEventRecord(h->prof_e0[h->prof_n], su));
+      CU_ERROR_CHECK(gemm_cyc(prec, herm, m2, n2, jb, W2, ldw, D, ldl, P > 1 ? (int)nb : 0, P, su));
+      if (prof) {
+        CU_ERROR_CHECK(cuEventRecord(h->prof_e1[h->prof_n], su));
+        /* algorithmic flops of this rank's share: sum over owned block columns of rows*width*k */
+        double fl = 0.0;
+        for (size_t lc = lc2; lc * nb < my_cols; lc++) {
+          const size_t g = (lc * (size_t)P + (size_t)me) * nb, wd = chol_min(nb, n - g);
+          fl += ((double)(n - g) * (double)wd - 0.5 * (double)wd * (double)(wd - 1)) * 2.0 * (double)jb;
+        }
+        h->prof_flops[h->prof_n++] = fl * (herm ? 4.0 : 1.0);
+      }
+    }
+    CU_ERROR_CHECK(cuEventRecord(h->ev_rest[c % CHOL_EVENT_RING], su));
+
+    /* look-ahead: the owner of block column c+1 brings it up to date on the panel stream */
+    if ((int)((c + 1) % (size_t)P) == me) {
+      const size_t lc1 = (c + 1) / (size_t)P, jb2 = chol_min(nb, rest);
+      const CUdeviceptr A22 = chol_at(Aloc, ldl, j + jb, lc1 * nb, es);
+      if (c >= 1) CU_ERROR_CHECK(cuStreamWaitEvent(sp, h->ev_rest[(c - 1) % CHOL_EVENT_RING], 0));
+      CU_ERROR_CHECK(chol_gemm_ex(prec, 'N', 'C', 0, 0, 0, 0, 'L', herm, rest, jb2, jb, MONE, W, ldw, W, ldw, ONE, A22, ldl,
+                                  A22, ldl, sp));
+    }
+  }
+  CU_ERROR_CHECK(cuMemcpyDtoHAsync(h->hinfo, h->dinfo, sizeof(long), sp));
+  CU_ERROR_CHECK(cuStreamSynchronize(sp));
+  CU_ERROR_CHECK(cuStreamSynchronize(su));
+  *info = *h->hinfo;
+  for (int i = 0; i < h->prof_n; i++) {
+    float ms = 0.f;
+    CU_ERROR_CHECK(cuEventElapsedTime(&ms, h->prof_e0[i], h->prof_e1[i]));
+    h->prof_total_ms += ms;
+    h->prof_total_flops += h->prof_flops[i];
+    h->prof_launches++;
+  }
+  h->prof_n = 0;
+  return CUDA_SUCCESS;
+}
+
+/* =============================================================================================
+ * one-process-per-GPU entry points (C-ABI extension used under torchrun)
+ * ===========================================================================================*/
+typedef struct chol_rank *cholDist;
+
+/* 128-byte NCCL unique id, to be created on rank 0 and sent to the other ranks by the launcher */
+CUresult cholDistGetUniqueId(void *id128) {
+  CU_ERROR_CHECK(nccl_load());
+  chol_nccl_id id;
+  NCCL_CHECK(nccl.GetUniqueId(&id));
+  memcpy(id128, &id, sizeof id);
+  return CUDA_SUCCESS;
+}
+
+/* binds the calling thread's current context; nranks == 1 needs neither an id nor NCCL */
+CUresult cholDistCreate(cholDist *out, int rank, int nranks, const void *id128) {
+  if (out == NULL || nranks < 1 || rank < 0 || rank >= nranks) return CUDA_ERROR_INVALID_VALUE;
+  chol_rank *R = calloc(1, sizeof *R);
+  if (R == NULL) return CUDA_ERROR_OUT_OF_MEMORY;
+  R->rank = rank;
+  R->nranks = nranks;
+  CUresult e = cuLAPACKCreate(&R->lap);
+  if (e != CUDA_SUCCESS) {
+    free(R);
+    return e;
+  }
+  R->context = R->lap->context;
+  if (nranks > 1) {
+    if (id128 == NULL) return CUDA_ERROR_INVALID_VALUE;
+    CU_ERROR_CHECK(nccl_load());
+    chol_nccl_id id;
+    memcpy(&id, id128, sizeof id);
+    NCCL_CHECK(nccl.CommInitRank(&R->comm, nranks, id, rank));
+  }
+  *out = R;
+  return CUDA_SUCCESS;
+}
+
+CUresult cholDistDestroy(cholDist R) {
+  if (R == NULL) return CUDA_ERROR_INVALID_VALUE;
+  if (R->comm) nccl.CommDestroy(R->comm);
+  if (R->lap) cuLAPACKDestroy(R->lap);
+  free(R);
+  return CUDA_SUCCESS;
+}
+
+CUresult cholDistSetBlockSize(cholDist R, size_t nb) { return R ? cuLAPACKSetBlockSize(R->lap, nb) : CUDA_ERROR_INVALID_VALUE; }
+CULAPACKhandle cholDistLapackHandle(cholDist R) { return R ? R->lap : NULL; }
+size_t cholDistBlockSize(cholDist R, int prec) { return (R && R->lap->nb) ? R->lap->nb : chol_default_nb(prec); }
+/* columns of an n x n matrix held by `rank` (they are packed side by side, block c = lc*P + rank) */
+size_t cholDistLocalCols(size_t n, size_t nb, int rank, int nranks) { return local_cols(n, nb, rank, nranks); }
+
+#define GEN_DIST(U, p)                                                                                      \
+  /* local part of A = L*L^H in the block-cyclic lower layout; info = first failure seen by THIS rank */    \
+  CUresult cholDist##U##potrf(cholDist R, size_t n, CUdeviceptr Aloc, size_t ldl, long *info) {             \
+    *info = 0;                                                                                              \
+    if (R == NULL) return CUDA_ERROR_INVALID_VALUE;                                                         \
+    if (ldl < n) {                                                                                          \
+      *info = -4;                                                                                           \
+      XERBLA(4);                                                                                            \
+      return CUDA_ERROR_INVALID_VALUE;                                                                      \
+    }                                                                                                       \
+    if (n == 0) return CUDA_SUCCESS;                                                                        \
+    CU_ERROR_CHECK(cuCtxPushCurrent(R->context));                                                           \
+    const CUresult e = dist_potrf(R, p, n, Aloc, ldl, info);                                                \
+    CUcontext dummy;                                                                                        \
+    cuCtxPopCurrent(&dummy);                                                                                \
+    return e;                                                                                               \
+  }
+GEN_DIST(S, 's')
+GEN_DIST(D, 'd')
+GEN_DIST(C, 'c')
+GEN_DIST(Z, 'z')
+
+/* =============================================================================================
+ * cuMultiGPU LAPACK handle and the host-pointer POTRF (reference lapack/handle.c:90-108,
+ * lapack/dpotrf.c:298-366)
+ * ===========================================================================================*/
+struct __cumultigpulapackhandle_st {
+  CUmultiGPU mgpu;
+};
+struct __cumultigpublashandle_st {
+  CUmultiGPU mgpu;
+};
+
+static CUresult rank_init_task(const void *args) {
+  chol_rank *R = *(chol_rank *const *)args;
+  CUresult e = cuLAPACKCreate(&R->lap); /* adopts the worker's context */
+  if (e == CUDA_SUCCESS) R->context = R->lap->context;
+  return e;
+}
+
+static CUresult ensure_ranks(CUmultiGPU m) {
+  if (m->ranks != NULL) return CUDA_SUCCESS;
+  const int P = m->n;
+  m->ranks = calloc((size_t)P, sizeof *m->ranks);
+  m->comms = calloc((size_t)P, sizeof *m->comms);
+  if (m->ranks == NULL || m->comms == NULL) return CUDA_ERROR_OUT_OF_MEMORY;
+  if (P > 1) {
+    CU_ERROR_CHECK(nccl_load());
+    int *devs = malloc(sizeof(int) * (size_t)P);
+    for (int i = 0; i < P; i++) devs[i] = (int)m->w[i].device;
+    const int rc = nccl.CommInitAll(m->comms, P, devs);
+    free(devs);
+    NCCL_CHECK(rc);
+  }
+  chol_rank **ptrs = malloc(sizeof(*ptrs) * (size_t)P);
+  for (int i = 0; i < P; i++) {
+    m->ranks[i].rank = i;
+    m->ranks[i].nranks = P;
+    m->ranks[i].comm = m->comms[i];
+    ptrs[i] = &m->ranks[i];
+  }
+  const CUresult e = run_on_all(m, rank_init_task, ptrs, sizeof(*ptrs), sizeof(*ptrs));
+  free(ptrs);
+  return e;
+}
+
+static CUresult rank_free_task(const void *args) {
+  chol_rank *R = *(chol_rank *const *)args;
+  if (R->local) cuMemFree(R->local);
+  if (R->lap) cuLAPACKDestroy(R->lap);
+  R->local = 0;
+  R->lap = NULL;
+  return CUDA_SUCCESS;
+}
+
+CUresult cuMultiGPUDestroy(CUmultiGPU m) {
+  if (m == NULL) return CUDA_ERROR_INVALID_VALUE;
+  if (m->ranks != NULL) {
+    chol_rank **ptrs = malloc(sizeof(*ptrs) * (size_t)m->n);
+    for (int i = 0; i < m->n; i++) ptrs[i] = &m->ranks[i];
+    run_on_all(m, rank_free_task, ptrs, sizeof(*ptrs), sizeof(*ptrs));
+    free(ptrs);
+    for (int i = 0; i < m->n; i++)
+      if (m->comms[i]) nccl.CommDestroy(m->comms[i]);
+    free(m->ranks);
+    free(m->comms);
+  }
+  for (int i = 0; i < m->n; i++) {
+    struct worker *w = &m->w[i];
+    pthread_mutex_lock(&w->mutex);
+    w->stop = true;
+    pthread_cond_signal(&w->cond);
+    pthread_mutex_unlock(&w->mutex);
+    pthread_join(w->thread, NULL);
+    pthread_mutex_destroy(&w->mutex);
+    pthread_cond_destroy(&w->cond);
+    cuDevicePrimaryCtxRelease(w->device);
+  }
+  free(m->w);
+  free(m);
+  return CUDA_SUCCESS;
+}
+
+CUresult cuMultiGPULAPACKCreate(CUmultiGPULAPACKhandle *handle, CUmultiGPU mGPU) {
+  if (handle == NULL || mGPU == NULL) return CUDA_ERROR_INVALID_VALUE;
+  struct __cumultigpulapackhandle_st *h = calloc(1, sizeof *h);
+  if (h == NULL) return CUDA_ERROR_OUT_OF_MEMORY;
+  h->mgpu = mGPU;
+  const CUresult e = ensure_ranks(mGPU);
+  if (e != CUDA_SUCCESS) {
+    free(h);
+    return e;
+  }
+  *handle = h;
+  return CUDA_SUCCESS;
+}
+CUresult cuMultiGPULAPACKDestroy(CUmultiGPULAPACKhandle h) {
+  if (h == NULL) return CUDA_ERROR_INVALID_VALUE;
+  free(h);
+  return CUDA_SUCCESS;
+}
+CUresult cuMultiGPULAPACKSynchronize(CUmultiGPULAPACKhandle h) {
+  return h == NULL ? CUDA_ERROR_INVALID_VALUE : cuMultiGPUSynchronize(h->mgpu);
+}
+CUresult cuMultiGPUBLASCreate(CUmultiGPUBLAShandle *handle, CUmultiGPU mGPU) {
+  if (handle == NULL || mGPU == NULL) return CUDA_ERROR_INVALID_VALUE;
+  struct __cumultigpublashandle_st *h = calloc(1, sizeof *h);
+  if (h == NULL) return CUDA_ERROR_OUT_OF_MEMORY;
+  h->mgpu = mGPU;
+  const CUresult e = ensure_ranks(mGPU);
+  if (e != CUDA_SUCCESS) {
+    free(h);
+    return e;
+  }
+  *handle = h;
+  return CUDA_SUCCESS;
+}
+CUresult cuMultiGPUBLASDestroy(CUmultiGPUBLAShandle h) {
+  if (h == NULL) return CUDA_ERROR_INVALID_VALUE;
+  free(h);
+  return CUDA_SUCCESS;
+}
+CUresult cuMultiGPUBLASSynchronize(CUmultiGPUBLAShandle h) {
+  return h == NULL ? CUDA_ERROR_INVALID_VALUE : cuMultiGPUSynchronize(h->mgpu);
+}
+CUmultiGPU chol_mgpu_of_lapack(CUmultiGPULAPACKhandle h) { return h->mgpu; }
+CUmultiGPU chol_mgpu_of_blas(CUmultiGPUBLAShandle h) { return h->mgpu; }
+int chol_mgpu_device(CUmultiGPU m, int i) { return (int)m->w[i].device; }
+CULAPACKhandle chol_mgpu_rank_lapack(CUmultiGPU m, int i) { return m->ranks ? m->ranks[i].lap : NULL; }
+CUresult chol_mgpu_run_on_all(CUmultiGPU m, CUresult (*fn)(const void *), const void *args, size_t stride, size_t size) {
+  return run_on_all(m, fn, args, stride, size);
+}
+
+/* ---- scatter / factor / gather, executed by every worker ---- */
+typedef struct {
+  chol_rank *R;
+  int prec, uplo;
+  size_t n, lda;
+  void *hostA;
+  long info;
+} potrf_args;
+
+static CUresult copy2d(int h2d, void *host, size_t ldh, CUdeviceptr dev, size_t ldd, size_t rows, size_t cols, size_t es,
+                       CUstream st) {
+  CUDA_MEMCPY2D c;
+  memset(&c, 0, sizeof c);
+  if (h2d) {
+    c.srcMemoryType = CU_MEMORYTYPE_HOST; c.srcHost = host; c.srcPitch = ldh * es;
+    c.dstMemoryType = CU_MEMORYTYPE_DEVICE; c.dstDevice = dev; c.dstPitch = ldd * es;
+  } else {
+    c.srcMemoryType = CU_MEMORYTYPE_DEVICE; c.srcDevice = dev; c.srcPitch = ldd * es;
+    c.dstMemoryType = CU_MEMORYTYPE_HOST; c.dstHost = host; c.dstPitch = ldh * es;
+  }
+  c.WidthInBytes = rows * es;
+  c.Height = cols;
+  return cuMemcpy2DAsync(&c, st);
+}
+
+static CUresult rank_potrf_task(const void *argp) {
+  potrf_args *a = *(potrf_args *const *)argp;
+  chol_rank *R = a->R;
+  const int P = R->nranks, me = R->rank, prec = a->prec;
+  const size_t n = a->n, es = chol_esize(prec), lda = a->lda;
+  CULAPACKhandle h = R->lap;
+  chol_ws w;
+  CU_ERROR_CHECK(chol_carve(h, prec, n, &w));
+  const size_t nb = w.nb, nblk = (n + nb - 1) / nb, my_cols = local_cols(n, nb, me, P);
+  const size_t ldl = chol_roundup(n, 16);
+  const size_t need = ldl * (my_cols ? my_cols : 1) * es;
+  if (need > R->local_bytes) {
+    if (R->local) CU_ERROR_CHECK(cuMemFree(R->local));
+    R->local = 0;
+    R->local_bytes = 0;
+    CU_ERROR_CHECK(cuMemAlloc(&R->local, need));
+    R->local_bytes = need;
+  }
+  CUstream st = h->s_update;
+  char *hostA = a->hostA;
+  /* ---- scatter: block column c (lower) or block row c (upper, transposed on the device) ---- */
+  for (size_t c = (size_t)me, lc = 0; c < nblk; c += (size_t)P, lc++) {
+    const size_t j = c * nb, jb = chol_min(nb, n - j), rows = n - j;
+    const CUdeviceptr dst = chol_at(R->local, ldl, j, lc * nb, es);
+    if (a->uplo == 'L') {
+      CU_ERROR_CHECK(copy2d(1, hostA + (j * lda + j) * es, lda, dst, ldl, rows, jb, es, st));
+    } else { /* U[j:j+jb, j:n] -> staging (jb x rows) -> conj-transpose into the local column */
+      const size_t lds = chol_roundup(jb, 2);
+      CU_ERROR_CHECK(copy2d(1, hostA + (j * lda + j) * es, lda, w.W[lc & 1], lds, jb, rows, es, st));
+      RT_CHECK(chol_copy_launch(prec, 'C', 0, jb, rows, (const void *)w.W[lc & 1], lds, (void *)dst, ldl, (void *)st));
+    }
+  }
+  CU_ERROR_CHECK(cuStreamSynchronize(st));
+  /* ---- factor ---- */
+  CU_ERROR_CHECK(dist_potrf(R, prec, n, R->local, ldl, &a->info));
+  /* ---- gather ----
+   * Whole block columns / rows travel back.  The part of each diagonal block that lies in the
+   * caller's OTHER triangle was uploaded with the block, is never written by the factorisation and
+   * therefore returns bit-identical (for Upper it is conjugated twice, which is exact). */
+  for (size_t c = (size_t)me, lc = 0; c < nblk; c += (size_t)P, lc++) {
+    const size_t j = c * nb, jb = chol_min(nb, n - j), rows = n - j;
+    const CUdeviceptr src = chol_at(R->local, ldl, j, lc * nb, es);
+    if (a->uplo == 'L') {
+      CU_ERROR_CHECK(copy2d(0, hostA + (j * lda + j) * es, lda, src, ldl, rows, jb, es, st));
+    } else {
+      const size_t lds = chol_roundup(jb, 2);
+      RT_CHECK(chol_copy_launch(prec, 'C', 0, rows, jb, (const void *)src, ldl, (void *)w.W[lc & 1], lds, (void *)st));
+      CU_ERROR_CHECK(copy2d(0, hostA + (j * lda + j) * es, lda, w.W[lc & 1], lds, jb, rows, es, st));
+    }
+  }
+  CU_ERROR_CHECK(cuStreamSynchronize(st));
+  return CUDA_SUCCESS;
+}
+
+static CUresult mgpu_potrf(CUmultiGPULAPACKhandle handle, int prec, int uplo, size_t n, void *A, size_t lda, long *info) {
+  CUmultiGPU m = handle->mgpu;
+  const int P = m->n;
+  potrf_args *args = calloc((size_t)P, sizeof *args);
+  potrf_args **ptrs = calloc((size_t)P, sizeof *ptrs);
+  if (args == NULL || ptrs == NULL) return CUDA_ERROR_OUT_OF_MEMORY;
+  for (int i = 0; i < P; i++) {
+    args[i].R = &m->ranks[i];
+    args[i].prec = prec;
+    args[i].uplo = uplo;
+    args[i].n = n;
+    args[i].lda = lda;
+    args[i].hostA = A;
+    ptrs[i] = &args[i];
+  }
+  const CUresult e = run_on_all(m, rank_potrf_task, ptrs, sizeof(*ptrs), sizeof(*ptrs));
+  long first = 0;
+  for (int i = 0; i < P; i++)
+    if (args[i].info > 0 && (first == 0 || args[i].info < first)) first = args[i].info;
+  *info = first;
+  free(args);
+  free(ptrs);
+  return e;
+}
+
+#define GEN_MGPU_POTRF(U, p, SCALAR)                                                                              \
+  CUresult cuMultiGPU##U##potrf(CUmultiGPULAPACKhandle handle, CBlasUplo uplo, size_t n, SCALAR *A, size_t lda,   \
+                                long *info) {                                                                     \
+    *info = 0;                                                                                                    \
+    if (lda < n) {                                                                                                \
+      *info = -4;                                                                                                 \
+      XERBLA(4);                                                                                                  \
+      return CUDA_ERROR_INVALID_VALUE;                                                                            \
+    }                                                                                                             \
+    if (n == 0) return CUDA_SUCCESS;                                                                              \
+    return mgpu_potrf(handle, p, uplo, n, A, lda, info);                                                          \
+  }
+GEN_MGPU_POTRF(S, 's', float)
+GEN_MGPU_POTRF(D, 'd', double)
+GEN_MGPU_POTRF(C, 'c', float complex)
+GEN_MGPU_POTRF(Z, 'z', double complex)

@@ -138,6 +138,13 @@ CUresult cuLAPACKDestroy(CULAPACKhandle h) {
     if (h->hinfo) cuMemFreeHost(h->hinfo);
     if (h->logdet_scr) cuMemFree(h->logdet_scr);
     if (h->hlogdet) cuMemFreeHost(h->hlogdet);
+    for (int i = 0; i < h->prof_cap; i++) {
+      cuEventDestroy(h->prof_e0[i]);
+      cuEventDestroy(h->prof_e1[i]);
+    }
+    free(h->prof_e0);
+    free(h->prof_e1);
+    free(h->prof_flops);
     CUcontext dummy;
     CU_ERROR_CHECK(cuCtxPopCurrent(&dummy));
   }
@@ -159,6 +166,39 @@ CUresult chol_lapack_workspace(CULAPACKhandle h, size_t bytes, CUdeviceptr *out)
     h->ws_bytes = bytes;
   }
   *out = h->ws;
+  return CUDA_SUCCESS;
+}
+
+/* measurement hook: time every trailing-update launch of the next LAPACK calls with CUDA events */
+CUresult cuLAPACKProfile(CULAPACKhandle h, int enable) {
+  if (h == NULL) return CUDA_ERROR_INVALID_VALUE;
+  if (enable && h->prof_cap == 0) {
+    const int cap = 2048;
+    h->prof_e0 = calloc((size_t)cap, sizeof(CUevent));
+    h->prof_e1 = calloc((size_t)cap, sizeof(CUevent));
+    h->prof_flops = calloc((size_t)cap, sizeof(double));
+    if (!h->prof_e0 || !h->prof_e1 || !h->prof_flops) return CUDA_ERROR_OUT_OF_MEMORY;
+    CU_ERROR_CHECK(cuCtxPushCurrent(h->context));
+    for (int i = 0; i < cap; i++) {
+      CU_ERROR_CHECK(cuEventCreate(&h->prof_e0[i], CU_EVENT_DEFAULT));
+      CU_ERROR_CHECK(cuEventCreate(&h->prof_e1[i], CU_EVENT_DEFAULT));
+    }
+    CUcontext dummy;
+    CU_ERROR_CHECK(cuCtxPopCurrent(&dummy));
+    h->prof_cap = cap;
+  }
+  h->profile = enable;
+  h->prof_total_ms = h->prof_total_flops = 0.0;
+  h->prof_launches = 0;
+  return CUDA_SUCCESS;
+}
+
+/* totals since cuLAPACKProfile(h, 1): device milliseconds, algorithmic flops, launches */
+CUresult cuLAPACKProfileRead(CULAPACKhandle h, double *ms, double *flops, int *launches) {
+  if (h == NULL) return CUDA_ERROR_INVALID_VALUE;
+  if (ms) *ms = h->prof_total_ms;
+  if (flops) *flops = h->prof_total_flops;
+  if (launches) *launches = h->prof_launches;
   return CUDA_SUCCESS;
 }
 

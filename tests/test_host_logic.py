@@ -1,0 +1,176 @@
+"""CPU-only tests (no GPU): the C-ABI library loads and exports every symbol include/*.h declares,
+the task objects follow the reference's unit tests (test/multigpu/cutask.c), the tile scheduler
+covers exactly the needed tiles, and the multi-process layout logic works at world_size 2 (gloo)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import harness as H
+from cholesky_b200_loader import load
+
+chol = load()
+ROOT = H.ROOT
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = chol.lib()
+    decl = set()
+    for f in ("blas.h", "lapack.h", "cumultigpu.h", "error.h"):
+        s = open(os.path.join(ROOT, "include", f)).read()
+        s = re.sub(r"/\*.*?\*/", "", s, flags=re.S)
+        s = re.sub(r"#define[^\n]*(\\\n[^\n]*)*", "", s)
+        decl |= set(re.findall(r"\b(cu[A-Z]\w+)\s*\(", s))
+    decl = {d for d in decl if not d.startswith(("cuMem", "cuCtx", "cuStream", "cuEvent", "cuDevice", "cuInit", "cuGetError"))}
+    assert len(decl) >= 90
+    for name in sorted(decl):
+        assert hasattr(lib, name), name
+    for var in ("xerbla", "errorHandler"):
+        C.c_void_p.in_dll(lib, var)
+    # the product library has no CPU path: none of the reference's un-prefixed CPU names
+    out = subprocess.check_output(["nm", "-D", "--defined-only", chol.LIB_PATH]).decode()
+    syms = {l.split()[-1] for l in out.splitlines() if l.strip()}
+    for cpu_name in ("dpotrf", "dgemm", "dtrsm", "dsyrk", "dpotri", "dlogdet", "zpotrf", "spotrf"):
+        assert cpu_name not in syms
+    # ... and it does not link the oracle
+    ldd = subprocess.check_output(["readelf", "-d", chol.LIB_PATH]).decode()
+    assert "oracle" not in ldd
+
+
+TASKFN = C.CFUNCTYPE(C.c_int, C.c_void_p)
+
+
+def test_cutask_semantics():
+    """reference test/multigpu/cutask.c: NULL function -> INVALID_VALUE, huge args -> OUT_OF_MEMORY,
+    the task's result is plumbed back through cuTaskDestroy."""
+    lib = chol.lib()
+    task = C.c_void_p()
+    seen = []
+
+    @TASKFN
+    def fn(args):
+        seen.append(C.cast(args, C.POINTER(C.c_int))[0])
+        return 7
+
+    val = C.c_int(42)
+    assert lib.cuTaskCreate(C.byref(task), None, C.byref(val), C.c_size_t(4)) == 1  # CUDA_ERROR_INVALID_VALUE
+    assert lib.cuTaskCreate(C.byref(task), fn, None, C.c_size_t(4)) == 1
+    assert lib.cuTaskCreate(C.byref(task), fn, C.byref(val), C.c_size_t(1 << 50)) == 2  # CUDA_ERROR_OUT_OF_MEMORY
+    assert lib.cuTaskCreate(C.byref(task), fn, C.byref(val), C.c_size_t(4)) == 0
+    val.value = 0  # the task owns a COPY of its arguments (multigpu.c:336-342)
+    assert lib.cuTaskExecute(task) == 0
+    res = C.c_int(-1)
+    assert lib.cuTaskDestroy(task, C.byref(res)) == 0
+    assert res.value == 7 and seen == [42]
+
+
+def test_multigpu_argument_errors_without_gpu():
+    lib = chol.lib()
+    m = C.c_void_p()
+    assert lib.cuMultiGPUCreate(C.byref(m), None, C.c_int(1)) == 1
+    dev = (C.c_int * 1)(0)
+    assert lib.cuMultiGPUCreate(C.byref(m), dev, C.c_int(0)) == 1
+    assert lib.cuMultiGPUGetContextCount(None) == 0
+
+
+@pytest.mark.parametrize("cuplo", ["", "L", "U"])
+@pytest.mark.parametrize("m,n", [(1, 1), (128, 64), (129, 65), (1000, 1000), (3000, 700), (700, 3000), (4096, 4096)])
+def test_tile_schedule_covers_needed_tiles_once(cuplo, m, n):
+    BM, BN = 128, 64
+    grid, tiles = chol.tile_schedule(cuplo, m, n)
+    assert len(tiles) == len(set(tiles))
+    want = set()
+    for bi in range((m + BM - 1) // BM):
+        for bj in range((n + BN - 1) // BN):
+            r0, r1, c0, c1 = bi * BM, min(m, bi * BM + BM) - 1, bj * BN, min(n, bj * BN + BN) - 1
+            if cuplo == "L" and bi * BM + BM - 1 < c0:
+                continue  # (the kernel tests against the full tile height)
+            if cuplo == "U" and r0 > bj * BN + BN - 1:
+                continue
+            want.add((bi, bj))
+    assert set(tiles) == want
+    assert grid >= len(tiles)
+    if m >= 4096 and cuplo:
+        assert grid <= 1.25 * len(tiles)  # the triangular grid wastes little (-> 0 as n grows)
+
+
+@pytest.mark.parametrize("P", [2, 4, 8])
+def test_block_cyclic_schedule_matches_global_triangle(P):
+    """A rank's packed local columns with the ColMap must select exactly the tiles whose global
+    coordinates touch the lower triangle."""
+    nb, n = 256, 4096
+    for rank in range(P):
+        for c in (0, 3, 9):  # current step: rows start at global block c+1; this rank's first column >= c+2
+            lc2 = max(0, -(-(c + 2 - rank) // P))
+            ncols = chol.dist_local_cols(n, nb, rank, P) - lc2 * nb
+            if ncols <= 0:
+                continue
+            g_first = (lc2 * P + rank) * nb
+            mrows = n - g_first
+            grid, tiles = chol.tile_schedule("L", mrows, ncols, nb, P, 0)
+            want = set()
+            for bi in range((mrows + 127) // 128):
+                for bj in range((ncols + 63) // 64):
+                    nloc = bj * 64
+                    gcol = ((nloc // nb) * P) * nb + nloc % nb  # relative to g_first
+                    if bi * 128 + 127 >= gcol:
+                        want.add((bi, bj))
+            assert set(tiles) == want and len(tiles) == len(set(tiles))
+
+
+def test_local_cols_partition():
+    for n, nb in ((1000, 256), (4096, 256), (65536, 256), (777, 128)):
+        for P in (1, 2, 3, 8):
+            assert sum(chol.dist_local_cols(n, nb, r, P) for r in range(P)) == n
+
+
+GLOO_WORKER = r"""
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, %(root)r)
+sys.path.insert(0, os.path.join(%(root)r, "tests"))
+import bench
+from cholesky_b200_loader import load
+chol = load()
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, P = dist.get_rank(), dist.get_world_size()
+# 1. the NCCL-id exchange path of bench.py, with a stand-in id
+uid = bench.exchange_unique_id(lambda: bytes(range(128)), rank)
+assert uid == bytes(range(128))
+# 2. block-cyclic ownership: every global column is owned exactly once, in the packed order
+n, nb = 2000, 256
+cols = bench.owned_columns(n, nb, rank, P)
+assert len(cols) == chol.dist_local_cols(n, nb, rank, P)
+allc = [None] * P
+dist.all_gather_object(allc, cols.tolist())
+flat = sorted(c for l in allc for c in l)
+assert flat == list(range(n))
+# 3. info reduction: smallest positive failure wins
+info = bench.combine_info(0 if rank == 0 else 513)
+assert info == 513
+info = bench.combine_info(700 if rank == 0 else 513)
+assert info == 513
+assert bench.combine_info(0) == 0
+# 4. max-over-ranks timing reduction
+t = bench.max_over_ranks(1.0 + rank)
+assert t == float(P)
+dist.barrier()
+dist.destroy_process_group()
+print("OK", rank)
+"""
+
+
+def test_multiprocess_host_logic_gloo_world2(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(GLOO_WORKER % {"root": ROOT})
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0 and "OK" in o, o
