@@ -213,7 +213,7 @@ def run_ours(args):
     N, K, Wm = args.n, args.steps, args.warmup
 
     # FP64 tensor-core peak of THIS GPU, measured now (MEASURED_PEAKS.json has no FP64 entry)
-    peak_tf = max(chol.probe_fp64(0, 40000)[0] for _ in range(3)) if rank == 0 else 0.0
+    peak_tf = max(chol.probe_fp64(0, 20000)[0] for _ in range(3)) if rank == 0 else 0.0
 
     uid = exchange_unique_id(chol.dist_unique_id, rank) if P > 1 else None
     d = chol.Dist(rank, P, uid, nb=args.nb)
@@ -373,13 +373,13 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=65536, help="matrix order (the metric's N)")
-    ap.add_argument("--nb", type=int, default=0, help="outer block size (0 = library default)")
+    ap.add_argument("--order", dest="n", type=int, default=65536, help="matrix order N (the metric's N = 65536)")
+    ap.add_argument("--block", dest="nb", type=int, default=0, help="outer block size (0 = library default)")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-n", type=int, default=6144, help="order of the CPU-baseline sample")
-    ap.add_argument("--ref-n", type=int, default=4096, help="order of the per-step sample of --impl reference")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
+    ap.add_argument("--cpu-order", dest="cpu_n", type=int, default=6144, help="order of the CPU-baseline sample")
+    ap.add_argument("--ref-order", dest="ref_n", type=int, default=4096, help="order of the per-step sample of --impl reference")
+    ap.add_argument("--skip-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    args = ap.parse_args()  # option names avoid every prefix of torch.distributed.run's own options
     if args.impl == "reference":
         return run_reference(args)
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:

@@ -235,26 +235,45 @@ __global__ void __launch_bounds__(LOGDET_THREADS) logdet_kernel(const T *x, long
 }
 
 // ------------------------------------------------------------------------------------------------
-// FP64 peak probes: kind 0 = DMMA only, 1 = DFMA only, 2 = both in the same warp
+// FP64 peak probes (registers only, no memory traffic):
+//   kind 0 = DMMA, the GEMM engine's own instruction mix: 8 A-fragments x 4 B-fragments -> 32
+//            independent m8n8k4 accumulators per warp
+//   kind 1 = DFMA only (the FP64 vector pipe), kind 2 = both interleaved in the same warps,
+//   kind 3 = DMMA with a single shared operand pair (an upper bound on operand-port effects)
 template <int KIND>
-__global__ void __launch_bounds__(256) probe_fp64_kernel(double *out, int iters) {
-  double d[16][2], f[16];
-  const double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+__global__ void __launch_bounds__(128, 2) probe_fp64_kernel(double *out, int iters) {
+  double acc[8][4][2], a[8], b[4], f[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) { d[i][0] = d[i][1] = 0.0; f[i] = i; }
+  for (int i = 0; i < 8; ++i) a[i] = 1.0 + (threadIdx.x + i) * 1e-9;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) b[j] = 1.0 - (threadIdx.x + j) * 1e-9;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) f[i] = i;
   for (int it = 0; it < iters; ++it) {
+    if (KIND == 0 || KIND == 2 || KIND == 3) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      if (KIND == 0 || KIND == 2) dmma_884(d[i][0], d[i][1], a, b);
-      if (KIND == 1 || KIND == 2) {
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int r = 0; r < 8; ++r) f[i] = fma(f[i], a, b);
-      }
+        for (int j = 0; j < 4; ++j) dmma_884(acc[i][j][0], acc[i][j][1], KIND == 3 ? a[0] : a[i], KIND == 3 ? b[0] : b[j]);
+    }
+    if (KIND == 1 || KIND == 2) {
+#pragma unroll
+      for (int r = 0; r < 16; ++r)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = fma(f[i], a[i & 7], b[i & 3]);
     }
   }
   double s = 0.0;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) s += d[i][0] + d[i][1] + f[i];
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s += acc[i][j][0] + acc[i][j][1];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += f[i];
   if (s == 12345.678) out[0] = s;
 }
 
@@ -374,14 +393,15 @@ extern "C" int chol_probe_fp64(int kind, int iters, double *tflops, float *ms_ou
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   double *out = nullptr;
   cudaMalloc(&out, 8);
-  const int blocks = sms * 4, threads = 256;
+  const int blocks = sms * 2, threads = 128;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int rep = 0; rep < 2; ++rep) {  // first pass warms up
     cudaEventRecord(e0);
     if (kind == 0) probe_fp64_kernel<0><<<blocks, threads>>>(out, iters);
     else if (kind == 1) probe_fp64_kernel<1><<<blocks, threads>>>(out, iters);
-    else probe_fp64_kernel<2><<<blocks, threads>>>(out, iters);
+    else if (kind == 2) probe_fp64_kernel<2><<<blocks, threads>>>(out, iters);
+    else probe_fp64_kernel<3><<<blocks, threads>>>(out, iters);
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
   }
@@ -389,8 +409,8 @@ extern "C" int chol_probe_fp64(int kind, int iters, double *tflops, float *ms_ou
   cudaEventElapsedTime(&ms, e0, e1);
   const double warps = (double)blocks * threads / 32.0;
   double flops = 0.0;
-  if (kind == 0 || kind == 2) flops += warps * iters * 16.0 * (8 * 8 * 4 * 2.0);
-  if (kind == 1 || kind == 2) flops += warps * iters * 16.0 * 8.0 * 32 * 2.0;
+  if (kind == 0 || kind == 2 || kind == 3) flops += warps * iters * 32.0 * (8 * 8 * 4 * 2.0);
+  if (kind == 1 || kind == 2) flops += warps * iters * 256.0 * 32 * 2.0;
   *tflops = flops / (ms * 1e-3) / 1e12;
   if (ms_out) *ms_out = ms;
   cudaEventDestroy(e0); cudaEventDestroy(e1);

@@ -14,8 +14,8 @@ chol = load()
 out = {}
 torch.cuda.init()
 torch.zeros(1, device="cuda")
-for kind, name in ((0, "dmma"), (1, "dfma"), (2, "dmma+dfma")):
-    tf, ms = chol.probe_fp64(kind, 20000)
+for kind, name in ((0, "dmma"), (1, "dfma"), (2, "dmma+dfma"), (3, "dmma_same_operands")):
+    tf, ms = chol.probe_fp64(kind, 10000)
     out["probe_" + name] = {"tflops": tf, "ms": ms}
     print("probe", name, "%.2f TFLOP/s (%.2f ms)" % (tf, ms), flush=True)
 
