@@ -25,7 +25,7 @@ __host__ __device__ inline long long gcol(const ColMap &cm, long long n) {
 template <int BN>
 __host__ __device__ inline int cols_upto(const ColMap &cm, long long m_max) {
   if (m_max < 0) return 0;
-  if (!cm.cnb) return (int)(m_max / BN) + 1;
+  if (!cm.cnb) return (int)((unsigned)m_max / (unsigned)BN) + 1;  // rows fit 32 bits
   const long long q = m_max / cm.cnb;  // global block column that holds m_max
   if (q < cm.coff) return 0;
   const long long lc = (q - cm.coff) / cm.cP;  // last local block whose global index is <= q
@@ -73,6 +73,46 @@ __host__ __device__ inline bool tile_coords(int cuplo, int NI, int NJ, const Col
   if (bi >= NI || bj >= NJ) return false;
   if (cuplo == 1 && bj >= cols_upto<BN>(cm, (long long)(bi + 1) * BM - 1)) return false;  // above the diagonal
   if (cuplo == 2 && bj < (BM / BN) * bi) return false;                                     // below the diagonal
+  return true;
+}
+
+// Host-built prefix table of the super-row tile counts (passed in the kernel arguments): the CTA's
+// tile decode becomes a short scan over warp-uniform constants instead of a chain of divisions.
+constexpr int SCHED_MAX_SR = 160;
+struct SchedTable {
+  int nsr;                      // number of super-rows; 0 = table not usable, decode arithmetically
+  int start[SCHED_MAX_SR + 1];  // first tile id of super-row s; start[nsr] = grid size
+};
+template <int BM, int BN, int GROUP>
+__host__ inline void build_sched_table(SchedTable &tb, int cuplo, int NI, int NJ, const ColMap &cm) {
+  const int nsr = (NI + GROUP - 1) / GROUP;
+  tb.nsr = 0;
+  if (nsr > SCHED_MAX_SR) return;
+  long long t = 0;
+  for (int s = 0; s < nsr; ++s) {
+    tb.start[s] = (int)t;
+    t += (long long)GROUP * sr_ncols<BM, BN, GROUP>(cuplo, NJ, cm, s);
+    if (t > 0x7fffffffLL) return;
+  }
+  tb.start[nsr] = (int)t;
+  tb.nsr = nsr;
+}
+template <int BM, int BN, int GROUP>
+__device__ __forceinline__ bool tile_coords_tb(const SchedTable &tb, int cuplo, int NI, int NJ, const ColMap &cm,
+                                               long long t, int &bi, int &bj) {
+  if (tb.nsr == 0) return tile_coords<BM, BN, GROUP>(cuplo, NI, NJ, cm, t, bi, bj);
+  const int ti = (int)t;
+  int s = 0;
+  // start[] is increasing: scan in strides of 8, then by 1 (at most ~28 uniform constant loads)
+  while (s + 8 <= tb.nsr && tb.start[s + 8] <= ti) s += 8;
+  while (s + 1 < tb.nsr && tb.start[s + 1] <= ti) ++s;
+  const int local = ti - tb.start[s];
+  const int jbase = (cuplo == 2) ? (BM / BN) * GROUP * s : 0;
+  bj = jbase + local / GROUP;
+  bi = GROUP * s + local % GROUP;
+  if (bi >= NI || bj >= NJ) return false;
+  if (cuplo == 1 && bj >= cols_upto<BN>(cm, (long long)(bi + 1) * BM - 1)) return false;
+  if (cuplo == 2 && bj < (BM / BN) * bi) return false;
   return true;
 }
 

@@ -27,6 +27,7 @@
 //   * triangular operands skip the k-range that is structurally zero.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <type_traits>
 
@@ -70,12 +71,88 @@ struct GemmArgs {
   int NI, NJ;        // tile counts
   int vec_ok;        // C/D allow 16-byte accesses
   int beta_zero;
-  int conjB_regs;    // MODE 0, z: conjugate B fragments in registers (raw TMA copy cannot)
+  int conjA_regs;    // z: conjugate A / B fragments in registers (raw TMA / cp.async copies cannot)
+  int conjB_regs;
+  long long total_tiles;  // size of the tile sequence the persistent CTAs walk
+  int prefetch_c;         // pull the C tile towards L2 when the producer starts a tile
+  SchedTable tb;          // super-row prefix table for the tile decode
+  int vecA, vecB;         // generic loader may use 16-byte copies along the stored rows of A / B
   ColMap cm;         // block-cyclic column map of D's columns (cnb = 0: identity)
 };
 
+// structurally-zero k ranges of triangular operands: [kb, ke) is what a tile really has to visit
+template <int BM, int BN, int BK, typename P>
+__device__ __forceinline__ void k_range(const P &p, int m0, int g0, int &kb, int &ke) {
+  kb = 0;
+  ke = p.K;
+  if (p.triA) {
+    const bool lower = (p.triA == 1) == (p.opA == 0);  // op(A)[m][k] != 0 only for k <= m
+    if (lower) ke = min(ke, m0 + BM); else kb = max(kb, m0);
+  }
+  if (p.triB) {
+    const bool kgen = (p.triB == 1) == (p.opB == 0);  // op(B)[k][n] != 0 only for k >= n
+    if (kgen) kb = max(kb, g0); else ke = min(ke, g0 + BN);
+  }
+  kb = (kb / BK) * BK;
+}
+
+// ---- generic loader, fast path: an interior, unmasked ROWS x BK operand tile --------------------
+// stored column-major; `along_rows` = the tile's ROWS index is the stored (contiguous) row index
+// (op = N for A, op = T/C for B).  dst is the [k][row] shared tile with pitch LD.
+template <int ROWS, int BK, int LD, int ESZ, typename T>
+__device__ __forceinline__ void fill_tile_fast(T *dst, const T *src, long long ld, bool along_rows, bool vec16,
+                                               long long r0, long long k0, int pw, int lane) {
+  if (along_rows) {
+    if (ESZ == 8 && vec16) {  // 16-byte copies of row pairs
+      const int mv = pw * 32 + lane;  // 0..63 -> rows 2mv, 2mv+1 (+128 per pass)
+#pragma unroll
+      for (int pass = 0; pass < ROWS / 128 + (ROWS % 128 ? 1 : 0); ++pass) {
+        const int mm = 2 * mv + 128 * pass;
+        if (mm < ROWS) {
+          const T *s = src + k0 * ld + r0 + mm;
+          T *d = dst + mm;
+#pragma unroll
+          for (int kk = 0; kk < BK; ++kk) cp_async_elem<16>(d + kk * LD, s + kk * ld);
+        }
+      }
+    } else {
+      const int m1 = pw * 32 + lane;  // 0..63
+#pragma unroll
+      for (int pass = 0; pass < (ROWS + 63) / 64; ++pass) {
+        const int mm = m1 + 64 * pass;
+        if (mm < ROWS) {
+          const T *s = src + k0 * ld + r0 + mm;
+          T *d = dst + mm;
+#pragma unroll
+          for (int kk = 0; kk < BK; ++kk) cp_async_elem<ESZ>(d + kk * LD, s + kk * ld);
+        }
+      }
+    }
+  } else {
+    // stored k-contiguous: a warp copies 4 k x 8 rows per pass (full 32-byte sectors on the global
+    // side, conflict-free on the shared side thanks to the +4 / +2 pitch pad)
+    const int kq = lane & 3, mq = lane >> 2;
+#pragma unroll
+    for (int mb = 0; mb < ROWS / 16; ++mb) {
+      const int mm = 16 * mb + 8 * pw + mq;
+      const T *s = src + (r0 + mm) * ld + k0 + kq;
+      T *d = dst + kq * LD + mm;
+#pragma unroll
+      for (int kb4 = 0; kb4 < BK / 4; ++kb4) cp_async_elem<ESZ>(d + 4 * kb4 * LD, s + 4 * kb4);
+    }
+  }
+}
+// true if the stored-triangle mask cannot touch the tile rows [r0, r0+ROWS) x k [k0, k0+BK)
+__device__ __forceinline__ bool tri_clear(int tri, bool along_rows, int r0, int rows, int k0, int bk) {
+  if (!tri) return true;
+  // stored coordinates: along_rows -> (row, col) = (r, k) else (k, r); lower keeps row >= col
+  const int row_min = along_rows ? r0 : k0, row_max = along_rows ? r0 + rows - 1 : k0 + bk - 1;
+  const int col_min = along_rows ? k0 : r0, col_max = along_rows ? k0 + bk - 1 : r0 + rows - 1;
+  return tri == 1 ? (row_min > col_max) : (row_max < col_min);  // strictly off the diagonal: no unit-diagonal either
+}
+
 template <bool CPLX, int MODE>
-__global__ void __launch_bounds__(GemmCfg<CPLX>::THREADS, 2) gemm_dmma_kernel(const GemmArgs<CPLX> p) {
+__global__ void __launch_bounds__(GemmCfg<CPLX>::THREADS, 2) gemm_dmma_kernel(const __grid_constant__ GemmArgs<CPLX> p) {
   using Cfg = GemmCfg<CPLX>;
   using T = typename GemmArgs<CPLX>::T;
   constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, LDA = Cfg::LDA, LDB = Cfg::LDB, ST = Cfg::STAGES;
@@ -86,247 +163,256 @@ __global__ void __launch_bounds__(GemmCfg<CPLX>::THREADS, 2) gemm_dmma_kernel(co
   uint64_t *full = reinterpret_cast<uint64_t *>(Bs + ST * Cfg::B_STAGE);
   uint64_t *empty = full + ST;
 
-  int bi, bj;
-  if (!tile_coords<BM, BN, Cfg::GROUP>(p.cuplo, p.NI, p.NJ, p.cm, (long long)blockIdx.x, bi, bj)) return;
-  const int m0 = bi * BM, n0 = bj * BN;
-  const int g0 = (int)gcol(p.cm, n0);  // triangle coordinate / B row of the tile's first column
-
-  // structurally-zero k ranges of triangular operands
-  int kb = 0, ke = p.K;
-  if (p.triA) {
-    const bool lower = (p.triA == 1) == (p.opA == 0);  // op(A)[m][k] != 0 only for k <= m
-    if (lower) ke = min(ke, m0 + BM); else kb = max(kb, m0);
-  }
-  if (p.triB) {
-    const bool kgen = (p.triB == 1) == (p.opB == 0);  // op(B)[k][n] != 0 only for k >= n
-    if (kgen) kb = max(kb, g0); else ke = min(ke, g0 + BN);
-  }
-  kb = (kb / BK) * BK;
-  const int nk = ke > kb ? (ke - kb + BK - 1) / BK : 0;
-
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < ST; ++s) {
-      mbar_init(&full[s], MODE == 0 ? 1 : 2);
+      // MODE 0: one arrive.expect_tx; MODE 1: per producer lane one cp.async-tracked arrive (noinc)
+      // plus one plain arrive that releases its zero-fill stores
+      mbar_init(&full[s], MODE == 0 ? 1 : 128);
       mbar_init(&empty[s], 4);
     }
     mbar_fence_init();
   }
   __syncthreads();
 
+  // PERSISTENT: CTA b walks tiles b, b+grid, ...; producer and consumers decode the same sequence.
+  // `it` counts k-stages across tiles so the mbarrier ring never drains between tiles: while the
+  // consumers run a tile's epilogue the producer is already filling the next tile's stages.
+  uint32_t it = 0;
+
   if (warp >= 4) {
     // ======================= producer warps =======================
     if (MODE == 0 && warp == 5) return;
     const int pw = warp - 4;
-    const int rowsA = min(BM, p.M - m0), rowsB = min(BN, p.N - n0);
-    for (int kt = 0; kt < nk; ++kt) {
-      const int s = kt % ST;
-      mbar_wait(&empty[s], ((kt / ST) & 1) ^ 1);
-      T *as = As + s * Cfg::A_STAGE, *bs = Bs + s * Cfg::B_STAGE;
-      const int k0 = kb + kt * BK;
-      if constexpr (MODE == 0) {
-        if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)(BK * (rowsA + rowsB) * Cfg::ESZ));
-        __syncwarp();
-        if (lane < BK)
-          tma_bulk_g2s(as + lane * LDA, p.A + (long long)(k0 + lane) * p.lda + m0, rowsA * Cfg::ESZ, &full[s]);
-        else if (lane < 2 * BK)
-          tma_bulk_g2s(bs + (lane - BK) * LDB, p.B + (long long)(k0 + lane - BK) * p.ldb + g0, rowsB * Cfg::ESZ, &full[s]);
-      } else {
-        constexpr int U = 8;  // loads in flight per lane
-        // A tile: logical op(A)[m0+mm][k0+kk] -> as[kk*LDA + mm]
-        for (int base = 0; base < BM * BK; base += 64 * U) {
-          T v[U];
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int idx = base + u * 64 + pw * 32 + lane;
+    for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      int bi, bj;
+      if (!tile_coords_tb<BM, BN, Cfg::GROUP>(p.tb, p.cuplo, p.NI, p.NJ, p.cm, t, bi, bj)) continue;
+      const int m0 = bi * BM, n0 = bj * BN;
+      const int g0 = (int)gcol(p.cm, n0);
+      int kb, ke;
+      k_range<BM, BN, BK>(p, m0, g0, kb, ke);
+      const int nk = ke > kb ? (ke - kb + BK - 1) / BK : 0;
+      const int rowsA = min(BM, p.M - m0), rowsB = min(BN, p.N - n0);
+      if (MODE == 0 || pw == 0) {
+        // pull this tile's C block towards L2 now; the epilogue reads it a whole main loop later
+        if (p.prefetch_c && !p.beta_zero && p.vec_ok && rowsA == BM) {
+          for (int c = lane; c < rowsB; c += 32)
+            l2_prefetch_bulk(p.C + (long long)(n0 + c) * p.ldc + m0, BM * Cfg::ESZ);
+        }
+      }
+      for (int kt = 0; kt < nk; ++kt, ++it) {
+        const int s = it % ST;
+        mbar_wait(&empty[s], ((it / ST) & 1) ^ 1);
+        T *as = As + s * Cfg::A_STAGE, *bs = Bs + s * Cfg::B_STAGE;
+        const int k0 = kb + kt * BK;
+        if constexpr (MODE == 0) {
+          if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)(BK * (rowsA + rowsB) * Cfg::ESZ));
+          __syncwarp();
+          if (lane < BK)
+            tma_bulk_g2s(as + lane * LDA, p.A + (long long)(k0 + lane) * p.lda + m0, rowsA * Cfg::ESZ, &full[s]);
+          else if (lane < 2 * BK)
+            tma_bulk_g2s(bs + (lane - BK) * LDB, p.B + (long long)(k0 + lane - BK) * p.ldb + g0, rowsB * Cfg::ESZ, &full[s]);
+        } else {
+          // generic loader: every element is either an asynchronous 8/16-byte cp.async (LDGSTS)
+          // straight into its transposed slot, or a zero / one written for masked, out-of-range and
+          // implicit-unit-diagonal positions.  Conjugation is applied by the consumers.
+          const bool kfull = (k0 + BK <= ke);
+          if (kfull && rowsA == BM && tri_clear(p.triA, p.opA == 0, m0, BM, k0, BK)) {
+            fill_tile_fast<BM, BK, LDA, Cfg::ESZ, T>(as, p.A, p.lda, p.opA == 0, p.vecA, m0, k0, pw, lane);
+          } else
+          for (int idx = pw * 32 + lane; idx < BM * BK; idx += 64) {
             int mm, kk;
             if (p.opA == 0) { mm = idx % BM; kk = idx / BM; } else { kk = idx % BK; mm = idx / BK; }
             const long long m = m0 + mm, k = k0 + kk;
+            const long long r = p.opA == 0 ? m : k, c = p.opA == 0 ? k : m;
+            T *dst = as + kk * LDA + mm;
             const bool in = (m < p.M) && (k < ke);
-            if (p.opA == 0) v[u] = fetch_stored<T>(p.A, p.lda, in, m, k, p.triA, p.unitA, false);
-            else            v[u] = fetch_stored<T>(p.A, p.lda, in, k, m, p.triA, p.unitA, p.opA == 2);
+            const bool masked = !in || (p.triA == 1 && r < c) || (p.triA == 2 && r > c);
+            if (masked) *dst = zero_of<T>();
+            else if (p.unitA && p.triA && r == c) *dst = one_of<T>();
+            else cp_async_elem<Cfg::ESZ>(dst, p.A + c * p.lda + r);
           }
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int idx = base + u * 64 + pw * 32 + lane;
-            int mm, kk;
-            if (p.opA == 0) { mm = idx % BM; kk = idx / BM; } else { kk = idx % BK; mm = idx / BK; }
-            as[kk * LDA + mm] = v[u];
-          }
-        }
-        // B tile: logical op(B)[k0+kk][n0+nn] -> bs[kk*LDB + nn]
-        for (int base = 0; base < BN * BK; base += 64 * U) {
-          T v[U];
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int idx = base + u * 64 + pw * 32 + lane;
+          if (kfull && rowsB == BN && tri_clear(p.triB, p.opB != 0, g0, BN, k0, BK)) {
+            fill_tile_fast<BN, BK, LDB, Cfg::ESZ, T>(bs, p.B, p.ldb, p.opB != 0, p.vecB, g0, k0, pw, lane);
+          } else
+          for (int idx = pw * 32 + lane; idx < BN * BK; idx += 64) {
             int nn, kk;
             if (p.opB != 0) { nn = idx % BN; kk = idx / BN; } else { kk = idx % BK; nn = idx / BK; }
             const long long n = g0 + nn, k = k0 + kk;
+            const long long r = p.opB == 0 ? k : n, c = p.opB == 0 ? n : k;
+            T *dst = bs + kk * LDB + nn;
             const bool in = (n0 + nn < p.N) && (k < ke);
-            if (p.opB == 0) v[u] = fetch_stored<T>(p.B, p.ldb, in, k, n, p.triB, p.unitB, false);
-            else            v[u] = fetch_stored<T>(p.B, p.ldb, in, n, k, p.triB, p.unitB, p.opB == 2);
+            const bool masked = !in || (p.triB == 1 && r < c) || (p.triB == 2 && r > c);
+            if (masked) *dst = zero_of<T>();
+            else if (p.unitB && p.triB && r == c) *dst = one_of<T>();
+            else cp_async_elem<Cfg::ESZ>(dst, p.B + c * p.ldb + r);
           }
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int idx = base + u * 64 + pw * 32 + lane;
-            int nn, kk;
-            if (p.opB != 0) { nn = idx % BN; kk = idx / BN; } else { kk = idx % BK; nn = idx / BK; }
-            bs[kk * LDB + nn] = v[u];
-          }
+          cp_async_mbar_arrive_noinc(&full[s]);
+          mbar_arrive(&full[s]);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full[s]);
       }
     }
     return;
   }
 
   // ======================= consumer warps =======================
-  const int g = lane >> 2, t = lane & 3;
+  const int g = lane >> 2, t4 = lane & 3;
   const int wm = warp & 1, wn = warp >> 1;
+  const bool conja = CPLX && p.conjA_regs, conjb = CPLX && p.conjB_regs;
 
-  if constexpr (!CPLX) {
-    double acc[8][4][2];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    int bi, bj;
+    if (!tile_coords_tb<BM, BN, Cfg::GROUP>(p.tb, p.cuplo, p.NI, p.NJ, p.cm, t, bi, bj)) continue;
+    const int m0 = bi * BM, n0 = bj * BN;
+    const int g0 = (int)gcol(p.cm, n0);
+    int kb, ke;
+    k_range<BM, BN, BK>(p, m0, g0, kb, ke);
+    const int nk = ke > kb ? (ke - kb + BK - 1) / BK : 0;
 
-    for (int kt = 0; kt < nk; ++kt) {
-      const int s = kt % ST;
-      mbar_wait(&full[s], (kt / ST) & 1);
-      const double *as = As + s * Cfg::A_STAGE + wm * 64 + 2 * g;
-      const double *bs = Bs + s * Cfg::B_STAGE + wn * 32 + 2 * g;
+    if constexpr (!CPLX) {
+      double acc[8][4][2];
 #pragma unroll
-      for (int ks = 0; ks < BK / 4; ++ks) {
-        const int k = ks * 4 + t;
-        double2 a[4], b[2];
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) a[q] = *reinterpret_cast<const double2 *>(as + k * LDA + 16 * q);
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+      for (int kt = 0; kt < nk; ++kt, ++it) {
+        const int s = it % ST;
+        mbar_wait(&full[s], (it / ST) & 1);
+        const double *as = As + s * Cfg::A_STAGE + wm * 64 + 2 * g;
+        const double *bs = Bs + s * Cfg::B_STAGE + wn * 32 + 2 * g;
 #pragma unroll
-        for (int q = 0; q < 2; ++q) b[q] = *reinterpret_cast<const double2 *>(bs + k * LDB + 16 * q);
+        for (int ks = 0; ks < BK / 4; ++ks) {
+          const int k = ks * 4 + t4;
+          double2 a[4], b[2];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) a[q] = *reinterpret_cast<const double2 *>(as + k * LDA + 16 * q);
+#pragma unroll
+          for (int q = 0; q < 2; ++q) b[q] = *reinterpret_cast<const double2 *>(bs + k * LDB + 16 * q);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              dmma_884(acc[i][j][0], acc[i][j][1], (i & 1) ? a[i >> 1].y : a[i >> 1].x, (j & 1) ? b[j >> 1].y : b[j >> 1].x);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+      }
+
+      // ---- epilogue: D = alpha*acc + beta*C.  Thread owns rows m, m+1 (m = ..+16q+2g) of columns
+      //      n = n0 + wn*32 + 16*(j>>1) + 2*(2t+c) + (j&1)
+      const double alpha = p.alpha, beta = p.beta;
+      const bool interior = (m0 + BM <= p.M) && (n0 + BN <= p.N) &&
+                            (p.cuplo == 0 || (p.cuplo == 1 && m0 >= g0 + BN - 1) || (p.cuplo == 2 && m0 + BM - 1 <= g0));
+      if (interior && p.vec_ok) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const long long m = m0 + wm * 64 + 16 * q + 2 * g;
+#pragma unroll
+          for (int jh = 0; jh < 2; ++jh) {  // 4 columns (16-byte row pairs) per batch
+            double2 cv[4];
+            if (!p.beta_zero) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int j = jh * 2 + (e >> 1), c = e & 1;
+                const long long n = n0 + wn * 32 + 16 * (j >> 1) + 2 * (2 * t4 + c) + (j & 1);
+                cv[e] = *reinterpret_cast<const double2 *>(p.C + n * p.ldc + m);
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = jh * 2 + (e >> 1), c = e & 1;
+              const long long n = n0 + wn * 32 + 16 * (j >> 1) + 2 * (2 * t4 + c) + (j & 1);
+              double2 o;
+              o.x = alpha * acc[2 * q][j][c];
+              o.y = alpha * acc[2 * q + 1][j][c];
+              if (!p.beta_zero) {
+                o.x += beta * cv[e].x;
+                o.y += beta * cv[e].y;
+              }
+              *reinterpret_cast<double2 *>(p.D + n * p.ldd + m) = o;
+            }
+          }
+        }
+      } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            dmma_884(acc[i][j][0], acc[i][j][1], (i & 1) ? a[i >> 1].y : a[i >> 1].x, (j & 1) ? b[j >> 1].y : b[j >> 1].x);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);
-    }
-
-    // ---- epilogue: D = alpha*acc + beta*C.  Thread owns rows m, m+1 (m = ..+16q+2g) of columns
-    //      n = n0 + wn*32 + 16*(j>>1) + 2*(2t+c) + (j&1)
-    const double alpha = p.alpha, beta = p.beta;
-    const bool interior = (m0 + BM <= p.M) && (n0 + BN <= p.N) &&
-                          (p.cuplo == 0 || (p.cuplo == 1 && m0 >= g0 + BN - 1) || (p.cuplo == 2 && m0 + BM - 1 <= g0));
-    if (interior && p.vec_ok) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const long long m = m0 + wm * 64 + 16 * q + 2 * g;
-#pragma unroll
-        for (int jh = 0; jh < 2; ++jh) {  // 4 columns (16-byte row pairs) per batch
-          double2 cv[4];
-          if (!p.beta_zero) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = jh * 2 + (e >> 1), c = e & 1;
-              const long long n = n0 + wn * 32 + 16 * (j >> 1) + 2 * (2 * t + c) + (j & 1);
-              cv[e] = *reinterpret_cast<const double2 *>(p.C + n * p.ldc + m);
+            for (int c = 0; c < 2; ++c) {
+              const long long m = m0 + wm * 64 + 16 * (i >> 1) + 2 * g + (i & 1);
+              const long long n = n0 + wn * 32 + 16 * (j >> 1) + 2 * (2 * t4 + c) + (j & 1);
+              if (m >= p.M || n >= p.N) continue;
+              if (p.cuplo == 1 && m < n - n0 + g0) continue;
+              if (p.cuplo == 2 && m > n - n0 + g0) continue;
+              double o = alpha * acc[i][j][c];
+              if (!p.beta_zero) o += beta * p.C[n * p.ldc + m];
+              p.D[n * p.ldd + m] = o;
             }
-          }
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int j = jh * 2 + (e >> 1), c = e & 1;
-            const long long n = n0 + wn * 32 + 16 * (j >> 1) + 2 * (2 * t + c) + (j & 1);
-            double2 o;
-            o.x = alpha * acc[2 * q][j][c];
-            o.y = alpha * acc[2 * q + 1][j][c];
-            if (!p.beta_zero) {
-              o.x += beta * cv[e].x;
-              o.y += beta * cv[e].y;
-            }
-            *reinterpret_cast<double2 *>(p.D + n * p.ldd + m) = o;
-          }
-        }
       }
     } else {
+      // ---------------- complex: split accumulators, 4 DMMAs per complex MAC ----------------
+      double accr[4][4][2], acci[4][4][2];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) accr[i][j][0] = accr[i][j][1] = acci[i][j][0] = acci[i][j][1] = 0.0;
+
+      for (int kt = 0; kt < nk; ++kt, ++it) {
+        const int s = it % ST;
+        mbar_wait(&full[s], (it / ST) & 1);
+        const double2 *as = As + s * Cfg::A_STAGE + wm * 32 + g;
+        const double2 *bs = Bs + s * Cfg::B_STAGE + wn * 32 + g;
+#pragma unroll
+        for (int ks = 0; ks < BK / 4; ++ks) {
+          const int k = ks * 4 + t4;
+          double2 a[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            a[q] = as[k * LDA + 8 * q];
+            if (conja) a[q].y = -a[q].y;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            double2 b = bs[k * LDB + 8 * j];
+            if (conjb) b.y = -b.y;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              dmma_884(accr[i][j][0], accr[i][j][1], a[i].x, b.x);
+              dmma_884(acci[i][j][0], acci[i][j][1], a[i].x, b.y);
+              dmma_884(acci[i][j][0], acci[i][j][1], a[i].y, b.x);
+              dmma_884(accr[i][j][0], accr[i][j][1], -a[i].y, b.y);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+      }
+
+      const double2 alpha = p.alpha, beta = p.beta;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j)
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
-            const long long m = m0 + wm * 64 + 16 * (i >> 1) + 2 * g + (i & 1);
-            const long long n = n0 + wn * 32 + 16 * (j >> 1) + 2 * (2 * t + c) + (j & 1);
+            const long long m = m0 + wm * 32 + 8 * i + g;
+            const long long n = n0 + wn * 32 + 8 * j + 2 * t4 + c;
             if (m >= p.M || n >= p.N) continue;
             if (p.cuplo == 1 && m < n - n0 + g0) continue;
             if (p.cuplo == 2 && m > n - n0 + g0) continue;
-            double o = alpha * acc[i][j][c];
-            if (!p.beta_zero) o += beta * p.C[n * p.ldc + m];
+            const double xr = accr[i][j][c], xi = acci[i][j][c];
+            double2 o = make_double2(alpha.x * xr - alpha.y * xi, alpha.x * xi + alpha.y * xr);
+            if (!p.beta_zero) {
+              const double2 cv = p.C[n * p.ldc + m];
+              o.x += beta.x * cv.x - beta.y * cv.y;
+              o.y += beta.x * cv.y + beta.y * cv.x;
+            }
+            if (p.herm && m == n - n0 + g0) o.y = 0.0;
             p.D[n * p.ldd + m] = o;
           }
     }
-  } else {
-    // ---------------- complex: split accumulators, 4 DMMAs per complex MAC ----------------
-    double accr[4][4][2], acci[4][4][2];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) accr[i][j][0] = accr[i][j][1] = acci[i][j][0] = acci[i][j][1] = 0.0;
-
-    const bool conjb = (MODE == 0) && p.conjB_regs;
-    for (int kt = 0; kt < nk; ++kt) {
-      const int s = kt % ST;
-      mbar_wait(&full[s], (kt / ST) & 1);
-      const double2 *as = As + s * Cfg::A_STAGE + wm * 32 + g;
-      const double2 *bs = Bs + s * Cfg::B_STAGE + wn * 32 + g;
-#pragma unroll
-      for (int ks = 0; ks < BK / 4; ++ks) {
-        const int k = ks * 4 + t;
-        double2 a[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) a[q] = as[k * LDA + 8 * q];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          double2 b = bs[k * LDB + 8 * j];
-          if (conjb) b.y = -b.y;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            dmma_884(accr[i][j][0], accr[i][j][1], a[i].x, b.x);
-            dmma_884(acci[i][j][0], acci[i][j][1], a[i].x, b.y);
-            dmma_884(acci[i][j][0], acci[i][j][1], a[i].y, b.x);
-            dmma_884(accr[i][j][0], accr[i][j][1], -a[i].y, b.y);
-          }
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);
-    }
-
-    const double2 alpha = p.alpha, beta = p.beta;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const long long m = m0 + wm * 32 + 8 * i + g;
-          const long long n = n0 + wn * 32 + 8 * j + 2 * t + c;
-          if (m >= p.M || n >= p.N) continue;
-          if (p.cuplo == 1 && m < n - n0 + g0) continue;
-          if (p.cuplo == 2 && m > n - n0 + g0) continue;
-          const double xr = accr[i][j][c], xi = acci[i][j][c];
-          double2 o = make_double2(alpha.x * xr - alpha.y * xi, alpha.x * xi + alpha.y * xr);
-          if (!p.beta_zero) {
-            const double2 cv = p.C[n * p.ldc + m];
-            o.x += beta.x * cv.x - beta.y * cv.y;
-            o.y += beta.x * cv.y + beta.y * cv.x;
-          }
-          if (p.herm && m == n - n0 + g0) o.y = 0.0;
-          p.D[n * p.ldd + m] = o;
-        }
   }
 }
 
@@ -376,24 +462,42 @@ static int launch_t(const chol_gemm_desc *d) {
   a.NJ = (a.N + Cfg::BN - 1) / Cfg::BN;
   a.vec_ok = CPLX ? 1 : ((((uintptr_t)d->D & 15) == 0) && (d->ldd % 2 == 0) &&
                          (a.beta_zero || ((((uintptr_t)d->C & 15) == 0) && (d->ldc % 2 == 0))));
+  a.vecA = !CPLX && (((uintptr_t)d->A & 15) == 0) && (d->lda % 2 == 0);
+  a.vecB = !CPLX && (((uintptr_t)d->B & 15) == 0) && (d->ldb % 2 == 0);
+  a.conjA_regs = CPLX && d->opA == 'C';
   a.conjB_regs = CPLX && d->opB == 'C';
   a.cm.cnb = d->cyc_nb; a.cm.cP = d->cyc_p; a.cm.coff = d->cyc_off;
   if (a.cm.cnb && (a.cm.cnb % Cfg::BN || a.cuplo == 2 || d->triA || d->triB || a.cm.cP < 1)) return (int)cudaErrorInvalidValue;
   const bool tma = !alpha_zero && tma_eligible<CPLX>(d);
   const long long tiles = total_tiles<Cfg::BM, Cfg::BN, Cfg::GROUP>(a.cuplo, a.NI, a.NJ, a.cm);
   if (tiles <= 0) return 0;
-  if (tiles > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
+  a.total_tiles = tiles;
+  build_sched_table<Cfg::BM, Cfg::BN, Cfg::GROUP>(a.tb, a.cuplo, a.NI, a.NJ, a.cm);
   cudaStream_t st = (cudaStream_t)d->stream;
   static bool attr_set[64][2][2];  // per device
+  static int sm_count[64];
   int dev = 0;
   cudaGetDevice(&dev);
   auto kern = tma ? gemm_dmma_kernel<CPLX, 0> : gemm_dmma_kernel<CPLX, 1>;
   if (!attr_set[dev & 63][CPLX][tma]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
+    cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev);
     attr_set[dev & 63][CPLX][tma] = true;
   }
-  kern<<<(unsigned)tiles, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a);
+  // tuning switches (environment, read once): CHOL_GEMM_PERSIST=0 launches one CTA per tile,
+  // CHOL_GEMM_PREFETCH=0 disables the L2 prefetch of C
+  static int persist = -1, prefetch = -1;
+  if (persist < 0) {
+    const char *e1 = getenv("CHOL_GEMM_PERSIST"), *e2 = getenv("CHOL_GEMM_PREFETCH");
+    persist = e1 ? atoi(e1) : 0;  // measured: the hardware's dynamic CTA placement beats a static persistent walk
+    prefetch = e2 ? atoi(e2) : 1;
+  }
+  a.prefetch_c = prefetch;
+  if (tiles > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
+  const long long resident = (long long)(persist > 0 ? persist : 2) * sm_count[dev & 63];  // persistent CTAs
+  const unsigned grid = (unsigned)((persist == 0 || tiles < resident) ? tiles : resident);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a);
   CHOL_COUNT_LAUNCH();
   return (int)cudaGetLastError();
 }

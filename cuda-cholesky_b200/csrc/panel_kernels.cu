@@ -37,40 +37,87 @@ __device__ __forceinline__ void load_lower_form(T *S, int LD, int upper, bool co
 }
 
 // ------------------------------------------------------------------------------------------------
-template <typename T>
+// potf2: the block lives in REGISTERS, distributed 2-D cyclically over the CTA's 16 warps x 32 lanes
+// (thread (lane, w) owns rows lane+32a, columns w+16b): the active window stays load-balanced as it
+// shrinks.  Right-looking, one __syncthreads per column: the warp that owns column c takes the
+// pivot by shuffle, scales its column, publishes it through a double-buffered shared-memory vector
+// and streams it to HBM; every thread then applies the rank-1 update to its own registers.
+template <typename T, int NA, int NB>
 __global__ void __launch_bounds__(PANEL_THREADS) potf2_kernel(int upper, int n, T *A, long long lda, long *dinfo, long info_base) {
   using Real = typename ScalarOf<T>::Real;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  T *S = reinterpret_cast<T *>(smem_raw);
-  const int LD = n | 1;
+  __shared__ T col[2][32 * NA];
+  __shared__ int sfail;
   if (*dinfo != 0) return;
-  load_lower_form(S, LD, upper, true, n, A, lda);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) sfail = 0;
+  T reg[NA][NB];
+#pragma unroll
+  for (int a = 0; a < NA; ++a)
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const int i = lane + 32 * a, k = warp + 16 * b;
+      T v = zero_of<T>();
+      if (i < n && k < n && i >= k) v = upper ? conj_of(A[(long long)i * lda + k]) : A[(long long)k * lda + i];
+      reg[a][b] = v;
+    }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int j = 0; j < n; ++j) {
-    const Real d = re_of(S[j + j * LD]);
-    if (!(d > Real(0))) {  // <= 0 or NaN: not positive definite (lapack/dpotrf.c:70-73)
-      if (threadIdx.x == 0) {
-        *dinfo = info_base + j + 1;
-        A[(long long)j * lda + j] = from_real<T>(d);
+#pragma unroll
+  for (int bo = 0; bo < NB; ++bo) {
+    constexpr int dummy = 0; (void)dummy;
+    const int ao = bo >> 1;  // rows 16bo..16bo+15 live in register slice a = (16bo + cw) / 32 = bo / 2
+    for (int cw = 0; cw < 16; ++cw) {
+      const int c = 16 * bo + cw;
+      if (c >= n) break;
+      T *cb = col[c & 1];
+      if (warp == cw) {  // this warp owns column c (register slice b = bo)
+        const int lo = c & 31;
+        Real d;
+        d = __shfl_sync(0xffffffffu, re_of(reg[ao][bo]), lo);
+        if (!(d > Real(0))) {  // <= 0 or NaN: not positive definite (lapack/dpotrf.c:70-73)
+          if (lane == 0) {
+            sfail = 1;
+            *dinfo = info_base + c + 1;
+            A[(long long)c * lda + c] = from_real<T>(d);
+          }
+        } else {
+          const Real r = sqrt(d), rinv = Real(1) / r;
+#pragma unroll
+          for (int a = 0; a < NA; ++a) {
+            const int i = lane + 32 * a;
+            if (i >= c && i < n) {
+              const T x = (i == c) ? from_real<T>(r) : rscale(reg[a][bo], rinv);
+              cb[i] = x;
+              if (!upper) A[(long long)c * lda + i] = x; else A[(long long)i * lda + c] = conj_of(x);
+            }
+          }
+        }
       }
-      return;
+      __syncthreads();
+      if (sfail) return;
+      // rank-1 update of the trailing window: columns k > c, rows i >= k
+      T li[NA];
+#pragma unroll
+      for (int a = 0; a < NA; ++a) li[a] = cb[lane + 32 * a];
+#pragma unroll
+      for (int b = bo; b < NB; ++b) {
+        const int k = warp + 16 * b;
+        if (k > c && k < n) {
+          const T f = neg(conj_of(cb[k]));
+#pragma unroll
+          for (int a = 0; a < NA; ++a)
+            if (lane + 32 * a >= k) fma_acc(reg[a][b], li[a], f);
+        }
+      }
     }
-    const Real r = sqrt(d), rinv = Real(1) / r, dinv = Real(1) / d;
-    for (int i = j + threadIdx.x; i < n; i += blockDim.x) {
-      const T v = (i == j) ? from_real<T>(r) : rscale(S[i + j * LD], rinv);
-      if (!upper) A[(long long)j * lda + i] = v; else A[(long long)i * lda + j] = conj_of(v);
-    }
-    for (int k = j + 1 + warp; k < n; k += nwarps) {
-      const T f = neg(rscale(conj_of(S[k + j * LD]), dinv));
-      for (int i = k + lane; i < n; i += 32) fma_acc(S[i + k * LD], S[i + j * LD], f);
-    }
-    __syncthreads();
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-template <typename T>
+// trti2: X = L^-1 by forward substitution, the triangle staged in shared memory.  Every warp carries
+// EIGHT columns at once (columns warp+16c): the residuals live in registers (lane = row mod 32), the
+// current unknown is broadcast by shuffle, and the eight independent chains hide each other's latency
+// while sharing the loads of L's column k.
+template <typename T, int NQ, int NC>
 __global__ void __launch_bounds__(PANEL_THREADS) trti2_kernel(int upper, int unit, int n, const T *A, long long lda, T *B,
                                                               long long ldb, int zero_other, long *dinfo, long info_base) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -97,36 +144,51 @@ __global__ void __launch_bounds__(PANEL_THREADS) trti2_kernel(int upper, int uni
     if (threadIdx.x == 0) *dinfo = info_base + (upper ? fail_lo : fail_hi) + 1;
     return;
   }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  // X = L^-1, one column per warp: forward substitution with the residual held in registers
-  for (int j = warp; j < n; j += nwarps) {
-    T r[4], x[4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // NC columns per warp (16 warps x NC = nmax), NQ = nmax / 32 row slices
+  T r[NC][NQ];           // residual; entry (lane, q) turns into x_row once row 32q+lane is solved
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { r[q] = (lane + 32 * q == j) ? one_of<T>() : zero_of<T>(); x[q] = zero_of<T>(); }
+  for (int c = 0; c < NC; ++c)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (32 * q + 31 < j || 32 * q >= n) continue;
-      for (int kk = 0; kk < 32; ++kk) {
-        const int k = 32 * q + kk;
-        if (k < j || k >= n) continue;
+    for (int q = 0; q < NQ; ++q) r[c][q] = (lane + 32 * q == warp + 16 * c) ? one_of<T>() : zero_of<T>();
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    if (32 * q >= n) continue;
+    for (int kk = 0; kk < 32; ++kk) {
+      const int k = 32 * q + kk;
+      if (k >= n) break;
+      if (k < warp) continue;  // none of this warp's columns has started yet
+      const T dk = dinv[k];
+      T lk[NQ];
+#pragma unroll
+      for (int q2 = 0; q2 < NQ; ++q2) {
+        const int i = lane + 32 * q2;
+        lk[q2] = (q2 >= q && i > k && i < n) ? L[i + k * LD] : zero_of<T>();
+      }
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        if (k < warp + 16 * c) continue;  // warp-uniform
         T rk;
-        if constexpr (ScalarOf<T>::cplx) { rk.x = __shfl_sync(0xffffffffu, r[q].x, kk); rk.y = __shfl_sync(0xffffffffu, r[q].y, kk); }
-        else rk = __shfl_sync(0xffffffffu, r[q], kk);
-        const T xk = mul(rk, dinv[k]);
-        if (lane == kk) x[q] = xk;
+        if constexpr (ScalarOf<T>::cplx) { rk.x = __shfl_sync(0xffffffffu, r[c][q].x, kk); rk.y = __shfl_sync(0xffffffffu, r[c][q].y, kk); }
+        else rk = __shfl_sync(0xffffffffu, r[c][q], kk);
+        const T xk = mul(rk, dk);
+        if (lane == kk) r[c][q] = xk;
         const T nxk = neg(xk);
 #pragma unroll
-        for (int q2 = 0; q2 < 4; ++q2) {
-          const int i = lane + 32 * q2;
-          if (q2 >= q && i > k && i < n) fma_acc(r[q2], L[i + k * LD], nxk);
-        }
+        for (int q2 = 0; q2 < NQ; ++q2)
+          if (q2 >= q) fma_acc(r[c][q2], lk[q2], nxk);  // rows <= k have lk = 0
       }
     }
+  }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+  for (int c = 0; c < NC; ++c) {
+    const int j = warp + 16 * c;
+    if (j >= n) continue;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
       const int i = lane + 32 * q;
       if (i < n) {
-        if (i >= j) { if (!upper) B[(long long)j * ldb + i] = x[q]; else B[(long long)i * ldb + j] = x[q]; }
+        if (i >= j) { if (!upper) B[(long long)j * ldb + i] = r[c][q]; else B[(long long)i * ldb + j] = r[c][q]; }
         else if (zero_other) { if (!upper) B[(long long)j * ldb + i] = zero_of<T>(); else B[(long long)i * ldb + j] = zero_of<T>(); }
       }
     }
@@ -286,17 +348,17 @@ template <typename K> static int set_smem(K kern, size_t bytes) {
 
 template <typename T>
 static int potf2_t(int uplo, size_t n, void *A, size_t lda, long *dinfo, long base, cudaStream_t st) {
-  const size_t sm = panel_smem<T>(n, 0);
-  int e = set_smem(potf2_kernel<T>, sm); if (e) return e;
-  potf2_kernel<T><<<1, PANEL_THREADS, sm, st>>>(uplo == 'U', (int)n, (T *)A, (long long)lda, dinfo, base);
+  constexpr int NMAX = sizeof(T) == 16 ? 64 : 128;  // chol_diag_max
+  potf2_kernel<T, NMAX / 32, NMAX / 16><<<1, PANEL_THREADS, 0, st>>>(uplo == 'U', (int)n, (T *)A, (long long)lda, dinfo, base);
   CHOL_COUNT_LAUNCH();
   return (int)cudaGetLastError();
 }
 template <typename T>
 static int trti2_t(int uplo, int diag, size_t n, const void *A, size_t lda, void *B, size_t ldb, int zo, long *dinfo, long base, cudaStream_t st) {
   const size_t sm = panel_smem<T>(n, n);
-  int e = set_smem(trti2_kernel<T>, sm); if (e) return e;
-  trti2_kernel<T><<<1, PANEL_THREADS, sm, st>>>(uplo == 'U', diag == 'U', (int)n, (const T *)A, (long long)lda, (T *)B, (long long)ldb, zo, dinfo, base);
+  int e = set_smem(trti2_kernel<T, (sizeof(T) == 16 ? 64 : 128) / 32, (sizeof(T) == 16 ? 64 : 128) / 16>, sm); if (e) return e;
+  constexpr int NMAX = sizeof(T) == 16 ? 64 : 128;
+  trti2_kernel<T, NMAX / 32, NMAX / 16><<<1, PANEL_THREADS, sm, st>>>(uplo == 'U', diag == 'U', (int)n, (const T *)A, (long long)lda, (T *)B, (long long)ldb, zo, dinfo, base);
   CHOL_COUNT_LAUNCH();
   return (int)cudaGetLastError();
 }
@@ -393,7 +455,9 @@ extern "C" int chol_probe_fp64(int kind, int iters, double *tflops, float *ms_ou
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   double *out = nullptr;
   cudaMalloc(&out, 8);
-  const int blocks = sms * 2, threads = 128;
+  const int per_sm = kind >= 10 ? kind / 10 : 2;  // kind 10/20/..: DMMA with 1/2/.. CTAs (4 warps each) per SM
+  if (kind >= 10) kind = 0;
+  const int blocks = sms * per_sm, threads = 128;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int rep = 0; rep < 2; ++rep) {  // first pass warms up

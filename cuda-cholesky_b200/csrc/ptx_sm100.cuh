@@ -48,6 +48,21 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
                : "memory");
 }
 
+// L2 prefetch of `bytes` (multiple of 16) through the TMA engine - no register or smem destination
+__device__ __forceinline__ void l2_prefetch_bulk(const void *src_gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
+
+// one element (8 or 16 bytes) global -> shared, asynchronously (SASS LDGSTS)
+template <int BYTES>
+__device__ __forceinline__ void cp_async_elem(void *dst_smem, const void *src_gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "n"(BYTES) : "memory");
+}
+// arrive on `bar` once all cp.async issued so far by this thread have landed (count it in the init)
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // D(8x8) += A(8x4) * B(4x8).  lane = 4*g + t:  a = A[g][t], b = B[t][g], d0/d1 = D[g][2t], D[g][2t+1]
 __device__ __forceinline__ void dmma_884(double &d0, double &d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"

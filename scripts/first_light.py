@@ -14,7 +14,7 @@ chol = load()
 out = {}
 torch.cuda.init()
 torch.zeros(1, device="cuda")
-for kind, name in ((0, "dmma"), (1, "dfma"), (2, "dmma+dfma"), (3, "dmma_same_operands")):
+for kind, name in ((0, "dmma"), (1, "dfma"), (2, "dmma+dfma"), (3, "dmma_same_operands"), (10, "dmma_1cta_per_sm(1 warp/SMSP)")):
     tf, ms = chol.probe_fp64(kind, 10000)
     out["probe_" + name] = {"tflops": tf, "ms": ms}
     print("probe", name, "%.2f TFLOP/s (%.2f ms)" % (tf, ms), flush=True)
