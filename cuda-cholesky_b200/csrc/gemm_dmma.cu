@@ -52,6 +52,8 @@ struct GemmCfg {
   static constexpr int R = BM / BN;  // tile aspect, used by the triangular scheduler
   static constexpr int GROUP = 8;    // row-blocks per super-row
   static constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * ESZ + 2 * STAGES * 8;
+  static constexpr int PP_THREADS = 384;  // staggered kernel: 2 consumer groups x 4 warps + 2 x 2 producer warps
+  static constexpr int PP_SMEM_BYTES = 2 * STAGES * (A_STAGE + B_STAGE) * ESZ + (4 * STAGES + 2) * 8;
   static constexpr int THREADS = 192;  // 4 consumer warps + 2 producer warps (register file is allocated in warp pairs)
 };
 
@@ -99,15 +101,15 @@ __device__ __forceinline__ void k_range(const P &p, int m0, int g0, int &kb, int
 // ---- generic loader, fast path: an interior, unmasked ROWS x BK operand tile --------------------
 // stored column-major; `along_rows` = the tile's ROWS index is the stored (contiguous) row index
 // (op = N for A, op = T/C for B).  dst is the [k][row] shared tile with pitch LD.
-template <int ROWS, int BK, int LD, int ESZ, typename T>
+template <int ROWS, int BK, int LD, int ESZ, int NPW, typename T>
 __device__ __forceinline__ void fill_tile_fast(T *dst, const T *src, long long ld, bool along_rows, bool vec16,
                                                long long r0, long long k0, int pw, int lane) {
+  constexpr int LANES = 32 * NPW;
   if (along_rows) {
     if (ESZ == 8 && vec16) {  // 16-byte copies of row pairs
-      const int mv = pw * 32 + lane;  // 0..63 -> rows 2mv, 2mv+1 (+128 per pass)
 #pragma unroll
-      for (int pass = 0; pass < ROWS / 128 + (ROWS % 128 ? 1 : 0); ++pass) {
-        const int mm = 2 * mv + 128 * pass;
+      for (int pass = 0; pass < (ROWS / 2 + LANES - 1) / LANES; ++pass) {
+        const int mm = 2 * (pw * 32 + lane + LANES * pass);
         if (mm < ROWS) {
           const T *s = src + k0 * ld + r0 + mm;
           T *d = dst + mm;
@@ -116,10 +118,9 @@ __device__ __forceinline__ void fill_tile_fast(T *dst, const T *src, long long l
         }
       }
     } else {
-      const int m1 = pw * 32 + lane;  // 0..63
 #pragma unroll
-      for (int pass = 0; pass < (ROWS + 63) / 64; ++pass) {
-        const int mm = m1 + 64 * pass;
+      for (int pass = 0; pass < (ROWS + LANES - 1) / LANES; ++pass) {
+        const int mm = pw * 32 + lane + LANES * pass;
         if (mm < ROWS) {
           const T *s = src + k0 * ld + r0 + mm;
           T *d = dst + mm;
@@ -133,8 +134,8 @@ __device__ __forceinline__ void fill_tile_fast(T *dst, const T *src, long long l
     // side, conflict-free on the shared side thanks to the +4 / +2 pitch pad)
     const int kq = lane & 3, mq = lane >> 2;
 #pragma unroll
-    for (int mb = 0; mb < ROWS / 16; ++mb) {
-      const int mm = 16 * mb + 8 * pw + mq;
+    for (int mb = 0; mb < ROWS / (8 * NPW); ++mb) {
+      const int mm = 8 * NPW * mb + 8 * pw + mq;
       const T *s = src + (r0 + mm) * ld + k0 + kq;
       T *d = dst + kq * LD + mm;
 #pragma unroll
@@ -151,267 +152,350 @@ __device__ __forceinline__ bool tri_clear(int tri, bool along_rows, int r0, int 
   return tri == 1 ? (row_min > col_max) : (row_max < col_min);  // strictly off the diagonal: no unit-diagonal either
 }
 
+// One tile's worth of producer work: fill the group's stage ring (TMA bulk rows or cp.async gather).
+template <bool CPLX, int MODE, int NPW>
+__device__ __forceinline__ void produce_tile(const GemmArgs<CPLX> &p, int bi, int bj, typename GemmArgs<CPLX>::T *As,
+                                             typename GemmArgs<CPLX>::T *Bs, uint64_t *full, uint64_t *empty, uint32_t &it,
+                                             int pw, int lane) {
+  using Cfg = GemmCfg<CPLX>;
+  using T = typename GemmArgs<CPLX>::T;
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, LDA = Cfg::LDA, LDB = Cfg::LDB, ST = Cfg::STAGES;
+  const int m0 = bi * BM, n0 = bj * BN;
+  const int g0 = (int)gcol(p.cm, n0);
+  int kb, ke;
+  k_range<BM, BN, BK>(p, m0, g0, kb, ke);
+  const int nk = ke > kb ? (ke - kb + BK - 1) / BK : 0;
+  const int rowsA = min(BM, p.M - m0), rowsB = min(BN, p.N - n0);
+  if (MODE == 0 || pw == 0) {
+    // pull this tile's C block towards L2 now; the epilogue reads it a whole main loop later
+    if (p.prefetch_c && !p.beta_zero && p.vec_ok && rowsA == BM) {
+      for (int c = lane; c < rowsB; c += 32)
+        l2_prefetch_bulk(p.C + (long long)(n0 + c) * p.ldc + m0, BM * Cfg::ESZ);
+    }
+  }
+  for (int kt = 0; kt < nk; ++kt, ++it) {
+    const int s = it % ST;
+    mbar_wait(&empty[s], ((it / ST) & 1) ^ 1);
+    T *as = As + s * Cfg::A_STAGE, *bs = Bs + s * Cfg::B_STAGE;
+    const int k0 = kb + kt * BK;
+    if constexpr (MODE == 0) {
+      if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)(BK * (rowsA + rowsB) * Cfg::ESZ));
+      __syncwarp();
+      if (lane < BK)
+        tma_bulk_g2s(as + lane * LDA, p.A + (long long)(k0 + lane) * p.lda + m0, rowsA * Cfg::ESZ, &full[s]);
+      else if (lane < 2 * BK)
+        tma_bulk_g2s(bs + (lane - BK) * LDB, p.B + (long long)(k0 + lane - BK) * p.ldb + g0, rowsB * Cfg::ESZ, &full[s]);
+    } else {
+      // generic loader: every element is either an asynchronous 8/16-byte cp.async (LDGSTS)
+      // straight into its transposed slot, or a zero / one written for masked, out-of-range and
+      // implicit-unit-diagonal positions.  Conjugation is applied by the consumers.
+      const bool kfull = (k0 + BK <= ke);
+      if (kfull && rowsA == BM && tri_clear(p.triA, p.opA == 0, m0, BM, k0, BK)) {
+        fill_tile_fast<BM, BK, LDA, Cfg::ESZ, NPW, T>(as, p.A, p.lda, p.opA == 0, p.vecA, m0, k0, pw, lane);
+      } else
+      for (int idx = pw * 32 + lane; idx < BM * BK; idx += 32 * NPW) {
+        int mm, kk;
+        if (p.opA == 0) { mm = idx % BM; kk = idx / BM; } else { kk = idx % BK; mm = idx / BK; }
+        const long long m = m0 + mm, k = k0 + kk;
+        const long long r = p.opA == 0 ? m : k, c = p.opA == 0 ? k : m;
+        T *dst = as + kk * LDA + mm;
+        const bool in = (m < p.M) && (k < ke);
+        const bool masked = !in || (p.triA == 1 && r < c) || (p.triA == 2 && r > c);
+        if (masked) *dst = zero_of<T>();
+        else if (p.unitA && p.triA && r == c) *dst = one_of<T>();
+        else cp_async_elem<Cfg::ESZ>(dst, p.A + c * p.lda + r);
+      }
+      if (kfull && rowsB == BN && tri_clear(p.triB, p.opB != 0, g0, BN, k0, BK)) {
+        fill_tile_fast<BN, BK, LDB, Cfg::ESZ, NPW, T>(bs, p.B, p.ldb, p.opB != 0, p.vecB, g0, k0, pw, lane);
+      } else
+      for (int idx = pw * 32 + lane; idx < BN * BK; idx += 32 * NPW) {
+        int nn, kk;
+        if (p.opB != 0) { nn = idx % BN; kk = idx / BN; } else { kk = idx % BK; nn = idx / BK; }
+        const long long n = g0 + nn, k = k0 + kk;
+        const long long r = p.opB == 0 ? k : n, c = p.opB == 0 ? n : k;
+        T *dst = bs + kk * LDB + nn;
+        const bool in = (n0 + nn < p.N) && (k < ke);
+        const bool masked = !in || (p.triB == 1 && r < c) || (p.triB == 2 && r > c);
+        if (masked) *dst = zero_of<T>();
+        else if (p.unitB && p.triB && r == c) *dst = one_of<T>();
+        else cp_async_elem<Cfg::ESZ>(dst, p.B + c * p.ldb + r);
+      }
+      cp_async_mbar_arrive_noinc(&full[s]);
+      mbar_arrive(&full[s]);
+    }
+  }
+}
+
+// One tile's worth of consumer work for a group of 4 warps: DMMA main loop + epilogue.
+template <bool CPLX, int MODE>
+__device__ __forceinline__ void consume_tile(const GemmArgs<CPLX> &p, int bi, int bj, const typename GemmArgs<CPLX>::T *As,
+                                             const typename GemmArgs<CPLX>::T *Bs, uint64_t *full, uint64_t *empty, uint32_t &it,
+                                             uint64_t *mid, int warp, int lane) {
+  using Cfg = GemmCfg<CPLX>;
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, LDA = Cfg::LDA, LDB = Cfg::LDB, ST = Cfg::STAGES;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int wm = warp & 1, wn = warp >> 1;
+  const bool conja = CPLX && p.conjA_regs, conjb = CPLX && p.conjB_regs;
+  (void)conja; (void)conjb;
+  const int m0 = bi * BM, n0 = bj * BN;
+  const int g0 = (int)gcol(p.cm, n0);
+  int kb, ke;
+  k_range<BM, BN, BK>(p, m0, g0, kb, ke);
+  const int nk = ke > kb ? (ke - kb + BK - 1) / BK : 0;
+  if (nk == 0 && mid != nullptr && lane == 0) mbar_arrive(mid);
+
+  if constexpr (!CPLX) {
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int kt = 0; kt < nk; ++kt, ++it) {
+      const int s = it % ST;
+      mbar_wait(&full[s], (it / ST) & 1);
+      const double *as = As + s * Cfg::A_STAGE + wm * 64 + 2 * g;
+      const double *bs = Bs + s * Cfg::B_STAGE + wn * 32 + 2 * g;
+#pragma unroll
+      for (int ks = 0; ks < BK / 4; ++ks) {
+        const int k = ks * 4 + t4;
+        double2 a[4], b[2];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a[q] = *reinterpret_cast<const double2 *>(as + k * LDA + 16 * q);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) b[q] = *reinterpret_cast<const double2 *>(bs + k * LDB + 16 * q);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            dmma_884(acc[i][j][0], acc[i][j][1], (i & 1) ? a[i >> 1].y : a[i >> 1].x, (j & 1) ? b[j >> 1].y : b[j >> 1].x);
+      }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&empty[s]);
+        if (mid != nullptr && kt == (nk - 1) / 2) mbar_arrive(mid);  // half-way mark (ping-pong stagger)
+      }
+    }
+
+    // ---- epilogue: D = alpha*acc + beta*C.  Thread owns rows m, m+1 (m = ..+16q+2g) of columns
+    //      n = n0 + wn*32 + 16*(j>>1) + 2*(2t+c) + (j&1)
+    const double alpha = p.alpha, beta = p.beta;
+    const bool interior = (m0 + BM <= p.M) && (n0 + BN <= p.N) &&
+                          (p.cuplo == 0 || (p.cuplo == 1 && m0 >= g0 + BN - 1) || (p.cuplo == 2 && m0 + BM - 1 <= g0));
+    if (interior && p.vec_ok) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const long long m = m0 + wm * 64 + 16 * q + 2 * g;
+#pragma unroll
+        for (int jh = 0; jh < 2; ++jh) {  // 4 columns (16-byte row pairs) per batch
+          double2 cv[4];
+          if (!p.beta_zero) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = jh * 2 + (e >> 1), c = e & 1;
+              const long long n = n0 + wn * 32 + 16 * (j >> 1) + 2 * (2 * t4 + c) + (j & 1);
+              cv[e] = *reinterpret_cast<const double2 *>(p.C + n * p.ldc + m);
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = jh * 2 + (e >> 1), c = e & 1;
+            const long long n = n0 + wn * 32 + 16 * (j >> 1) + 2 * (2 * t4 + c) + (j & 1);
+            double2 o;
+            o.x = alpha * acc[2 * q][j][c];
+            o.y = alpha * acc[2 * q + 1][j][c];
+            if (!p.beta_zero) {
+              o.x += beta * cv[e].x;
+              o.y += beta * cv[e].y;
+            }
+            *reinterpret_cast<double2 *>(p.D + n * p.ldd + m) = o;
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const long long m = m0 + wm * 64 + 16 * (i >> 1) + 2 * g + (i & 1);
+            const long long n = n0 + wn * 32 + 16 * (j >> 1) + 2 * (2 * t4 + c) + (j & 1);
+            if (m >= p.M || n >= p.N) continue;
+            if (p.cuplo == 1 && m < n - n0 + g0) continue;
+            if (p.cuplo == 2 && m > n - n0 + g0) continue;
+            double o = alpha * acc[i][j][c];
+            if (!p.beta_zero) o += beta * p.C[n * p.ldc + m];
+            p.D[n * p.ldd + m] = o;
+          }
+    }
+  } else {
+    // ---------------- complex: split accumulators, 4 DMMAs per complex MAC ----------------
+    double accr[4][4][2], acci[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) accr[i][j][0] = accr[i][j][1] = acci[i][j][0] = acci[i][j][1] = 0.0;
+
+    for (int kt = 0; kt < nk; ++kt, ++it) {
+      const int s = it % ST;
+      mbar_wait(&full[s], (it / ST) & 1);
+      const double2 *as = As + s * Cfg::A_STAGE + wm * 32 + g;
+      const double2 *bs = Bs + s * Cfg::B_STAGE + wn * 32 + g;
+#pragma unroll
+      for (int ks = 0; ks < BK / 4; ++ks) {
+        const int k = ks * 4 + t4;
+        double2 a[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          a[q] = as[k * LDA + 8 * q];
+          if (conja) a[q].y = -a[q].y;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          double2 b = bs[k * LDB + 8 * j];
+          if (conjb) b.y = -b.y;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            dmma_884(accr[i][j][0], accr[i][j][1], a[i].x, b.x);
+            dmma_884(acci[i][j][0], acci[i][j][1], a[i].x, b.y);
+            dmma_884(acci[i][j][0], acci[i][j][1], a[i].y, b.x);
+            dmma_884(accr[i][j][0], accr[i][j][1], -a[i].y, b.y);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&empty[s]);
+        if (mid != nullptr && kt == (nk - 1) / 2) mbar_arrive(mid);  // half-way mark (ping-pong stagger)
+      }
+    }
+
+    const double2 alpha = p.alpha, beta = p.beta;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const long long m = m0 + wm * 32 + 8 * i + g;
+          const long long n = n0 + wn * 32 + 8 * j + 2 * t4 + c;
+          if (m >= p.M || n >= p.N) continue;
+          if (p.cuplo == 1 && m < n - n0 + g0) continue;
+          if (p.cuplo == 2 && m > n - n0 + g0) continue;
+          const double xr = accr[i][j][c], xi = acci[i][j][c];
+          double2 o = make_double2(alpha.x * xr - alpha.y * xi, alpha.x * xi + alpha.y * xr);
+          if (!p.beta_zero) {
+            const double2 cv = p.C[n * p.ldc + m];
+            o.x += beta.x * cv.x - beta.y * cv.y;
+            o.y += beta.x * cv.y + beta.y * cv.x;
+          }
+          if (p.herm && m == n - n0 + g0) o.y = 0.0;
+          p.D[n * p.ldd + m] = o;
+        }
+  }
+}
+
+template <bool CPLX, int MODE, int NPW>
+__device__ __forceinline__ void init_ring(uint64_t *full, uint64_t *empty) {
+  for (int s = 0; s < GemmCfg<CPLX>::STAGES; ++s) {
+    // MODE 0: one arrive.expect_tx; MODE 1: per producer lane one cp.async-tracked arrive (noinc)
+    // plus one plain arrive that releases its zero-fill stores
+    mbar_init(&full[s], MODE == 0 ? 1 : 64 * NPW);
+    mbar_init(&empty[s], 4);
+  }
+}
+
+// ---- classic schedule: 2 CTAs per SM, one consumer group each (CHOL_GEMM_PP=0) -------------------
 template <bool CPLX, int MODE>
 __global__ void __launch_bounds__(GemmCfg<CPLX>::THREADS, 2) gemm_dmma_kernel(const __grid_constant__ GemmArgs<CPLX> p) {
   using Cfg = GemmCfg<CPLX>;
   using T = typename GemmArgs<CPLX>::T;
-  constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, LDA = Cfg::LDA, LDB = Cfg::LDB, ST = Cfg::STAGES;
-
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, ST = Cfg::STAGES;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T *As = reinterpret_cast<T *>(smem_raw);
   T *Bs = As + ST * Cfg::A_STAGE;
   uint64_t *full = reinterpret_cast<uint64_t *>(Bs + ST * Cfg::B_STAGE);
   uint64_t *empty = full + ST;
-
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < ST; ++s) {
-      // MODE 0: one arrive.expect_tx; MODE 1: per producer lane one cp.async-tracked arrive (noinc)
-      // plus one plain arrive that releases its zero-fill stores
-      mbar_init(&full[s], MODE == 0 ? 1 : 128);
-      mbar_init(&empty[s], 4);
-    }
+    init_ring<CPLX, MODE, 2>(full, empty);
     mbar_fence_init();
   }
   __syncthreads();
-
-  // PERSISTENT: CTA b walks tiles b, b+grid, ...; producer and consumers decode the same sequence.
-  // `it` counts k-stages across tiles so the mbarrier ring never drains between tiles: while the
-  // consumers run a tile's epilogue the producer is already filling the next tile's stages.
-  uint32_t it = 0;
-
-  if (warp >= 4) {
-    // ======================= producer warps =======================
-    if (MODE == 0 && warp == 5) return;
-    const int pw = warp - 4;
-    for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      int bi, bj;
-      if (!tile_coords_tb<BM, BN, Cfg::GROUP>(p.tb, p.cuplo, p.NI, p.NJ, p.cm, t, bi, bj)) continue;
-      const int m0 = bi * BM, n0 = bj * BN;
-      const int g0 = (int)gcol(p.cm, n0);
-      int kb, ke;
-      k_range<BM, BN, BK>(p, m0, g0, kb, ke);
-      const int nk = ke > kb ? (ke - kb + BK - 1) / BK : 0;
-      const int rowsA = min(BM, p.M - m0), rowsB = min(BN, p.N - n0);
-      if (MODE == 0 || pw == 0) {
-        // pull this tile's C block towards L2 now; the epilogue reads it a whole main loop later
-        if (p.prefetch_c && !p.beta_zero && p.vec_ok && rowsA == BM) {
-          for (int c = lane; c < rowsB; c += 32)
-            l2_prefetch_bulk(p.C + (long long)(n0 + c) * p.ldc + m0, BM * Cfg::ESZ);
-        }
-      }
-      for (int kt = 0; kt < nk; ++kt, ++it) {
-        const int s = it % ST;
-        mbar_wait(&empty[s], ((it / ST) & 1) ^ 1);
-        T *as = As + s * Cfg::A_STAGE, *bs = Bs + s * Cfg::B_STAGE;
-        const int k0 = kb + kt * BK;
-        if constexpr (MODE == 0) {
-          if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)(BK * (rowsA + rowsB) * Cfg::ESZ));
-          __syncwarp();
-          if (lane < BK)
-            tma_bulk_g2s(as + lane * LDA, p.A + (long long)(k0 + lane) * p.lda + m0, rowsA * Cfg::ESZ, &full[s]);
-          else if (lane < 2 * BK)
-            tma_bulk_g2s(bs + (lane - BK) * LDB, p.B + (long long)(k0 + lane - BK) * p.ldb + g0, rowsB * Cfg::ESZ, &full[s]);
-        } else {
-          // generic loader: every element is either an asynchronous 8/16-byte cp.async (LDGSTS)
-          // straight into its transposed slot, or a zero / one written for masked, out-of-range and
-          // implicit-unit-diagonal positions.  Conjugation is applied by the consumers.
-          const bool kfull = (k0 + BK <= ke);
-          if (kfull && rowsA == BM && tri_clear(p.triA, p.opA == 0, m0, BM, k0, BK)) {
-            fill_tile_fast<BM, BK, LDA, Cfg::ESZ, T>(as, p.A, p.lda, p.opA == 0, p.vecA, m0, k0, pw, lane);
-          } else
-          for (int idx = pw * 32 + lane; idx < BM * BK; idx += 64) {
-            int mm, kk;
-            if (p.opA == 0) { mm = idx % BM; kk = idx / BM; } else { kk = idx % BK; mm = idx / BK; }
-            const long long m = m0 + mm, k = k0 + kk;
-            const long long r = p.opA == 0 ? m : k, c = p.opA == 0 ? k : m;
-            T *dst = as + kk * LDA + mm;
-            const bool in = (m < p.M) && (k < ke);
-            const bool masked = !in || (p.triA == 1 && r < c) || (p.triA == 2 && r > c);
-            if (masked) *dst = zero_of<T>();
-            else if (p.unitA && p.triA && r == c) *dst = one_of<T>();
-            else cp_async_elem<Cfg::ESZ>(dst, p.A + c * p.lda + r);
-          }
-          if (kfull && rowsB == BN && tri_clear(p.triB, p.opB != 0, g0, BN, k0, BK)) {
-            fill_tile_fast<BN, BK, LDB, Cfg::ESZ, T>(bs, p.B, p.ldb, p.opB != 0, p.vecB, g0, k0, pw, lane);
-          } else
-          for (int idx = pw * 32 + lane; idx < BN * BK; idx += 64) {
-            int nn, kk;
-            if (p.opB != 0) { nn = idx % BN; kk = idx / BN; } else { kk = idx % BK; nn = idx / BK; }
-            const long long n = g0 + nn, k = k0 + kk;
-            const long long r = p.opB == 0 ? k : n, c = p.opB == 0 ? n : k;
-            T *dst = bs + kk * LDB + nn;
-            const bool in = (n0 + nn < p.N) && (k < ke);
-            const bool masked = !in || (p.triB == 1 && r < c) || (p.triB == 2 && r > c);
-            if (masked) *dst = zero_of<T>();
-            else if (p.unitB && p.triB && r == c) *dst = one_of<T>();
-            else cp_async_elem<Cfg::ESZ>(dst, p.B + c * p.ldb + r);
-          }
-          cp_async_mbar_arrive_noinc(&full[s]);
-          mbar_arrive(&full[s]);
-        }
-      }
-    }
-    return;
-  }
-
-  // ======================= consumer warps =======================
-  const int g = lane >> 2, t4 = lane & 3;
-  const int wm = warp & 1, wn = warp >> 1;
-  const bool conja = CPLX && p.conjA_regs, conjb = CPLX && p.conjB_regs;
-
+  uint32_t it = 0;  // k-stages consumed so far: the ring keeps rolling across tiles
+  if (MODE == 0 && warp == 5) return;
   for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
     int bi, bj;
     if (!tile_coords_tb<BM, BN, Cfg::GROUP>(p.tb, p.cuplo, p.NI, p.NJ, p.cm, t, bi, bj)) continue;
-    const int m0 = bi * BM, n0 = bj * BN;
-    const int g0 = (int)gcol(p.cm, n0);
-    int kb, ke;
-    k_range<BM, BN, BK>(p, m0, g0, kb, ke);
-    const int nk = ke > kb ? (ke - kb + BK - 1) / BK : 0;
+    if (warp >= 4) produce_tile<CPLX, MODE, 2>(p, bi, bj, As, Bs, full, empty, it, warp - 4, lane);
+    else consume_tile<CPLX, MODE>(p, bi, bj, As, Bs, full, empty, it, nullptr, warp, lane);
+  }
+}
 
-    if constexpr (!CPLX) {
-      double acc[8][4][2];
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-      for (int kt = 0; kt < nk; ++kt, ++it) {
-        const int s = it % ST;
-        mbar_wait(&full[s], (it / ST) & 1);
-        const double *as = As + s * Cfg::A_STAGE + wm * 64 + 2 * g;
-        const double *bs = Bs + s * Cfg::B_STAGE + wn * 32 + 2 * g;
-#pragma unroll
-        for (int ks = 0; ks < BK / 4; ++ks) {
-          const int k = ks * 4 + t4;
-          double2 a[4], b[2];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) a[q] = *reinterpret_cast<const double2 *>(as + k * LDA + 16 * q);
-#pragma unroll
-          for (int q = 0; q < 2; ++q) b[q] = *reinterpret_cast<const double2 *>(bs + k * LDB + 16 * q);
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              dmma_884(acc[i][j][0], acc[i][j][1], (i & 1) ? a[i >> 1].y : a[i >> 1].x, (j & 1) ? b[j >> 1].y : b[j >> 1].x);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
-      }
-
-      // ---- epilogue: D = alpha*acc + beta*C.  Thread owns rows m, m+1 (m = ..+16q+2g) of columns
-      //      n = n0 + wn*32 + 16*(j>>1) + 2*(2t+c) + (j&1)
-      const double alpha = p.alpha, beta = p.beta;
-      const bool interior = (m0 + BM <= p.M) && (n0 + BN <= p.N) &&
-                            (p.cuplo == 0 || (p.cuplo == 1 && m0 >= g0 + BN - 1) || (p.cuplo == 2 && m0 + BM - 1 <= g0));
-      if (interior && p.vec_ok) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const long long m = m0 + wm * 64 + 16 * q + 2 * g;
-#pragma unroll
-          for (int jh = 0; jh < 2; ++jh) {  // 4 columns (16-byte row pairs) per batch
-            double2 cv[4];
-            if (!p.beta_zero) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int j = jh * 2 + (e >> 1), c = e & 1;
-                const long long n = n0 + wn * 32 + 16 * (j >> 1) + 2 * (2 * t4 + c) + (j & 1);
-                cv[e] = *reinterpret_cast<const double2 *>(p.C + n * p.ldc + m);
-              }
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = jh * 2 + (e >> 1), c = e & 1;
-              const long long n = n0 + wn * 32 + 16 * (j >> 1) + 2 * (2 * t4 + c) + (j & 1);
-              double2 o;
-              o.x = alpha * acc[2 * q][j][c];
-              o.y = alpha * acc[2 * q + 1][j][c];
-              if (!p.beta_zero) {
-                o.x += beta * cv[e].x;
-                o.y += beta * cv[e].y;
-              }
-              *reinterpret_cast<double2 *>(p.D + n * p.ldd + m) = o;
-            }
-          }
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              const long long m = m0 + wm * 64 + 16 * (i >> 1) + 2 * g + (i & 1);
-              const long long n = n0 + wn * 32 + 16 * (j >> 1) + 2 * (2 * t4 + c) + (j & 1);
-              if (m >= p.M || n >= p.N) continue;
-              if (p.cuplo == 1 && m < n - n0 + g0) continue;
-              if (p.cuplo == 2 && m > n - n0 + g0) continue;
-              double o = alpha * acc[i][j][c];
-              if (!p.beta_zero) o += beta * p.C[n * p.ldc + m];
-              p.D[n * p.ldd + m] = o;
-            }
-      }
-    } else {
-      // ---------------- complex: split accumulators, 4 DMMAs per complex MAC ----------------
-      double accr[4][4][2], acci[4][4][2];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) accr[i][j][0] = accr[i][j][1] = acci[i][j][0] = acci[i][j][1] = 0.0;
-
-      for (int kt = 0; kt < nk; ++kt, ++it) {
-        const int s = it % ST;
-        mbar_wait(&full[s], (it / ST) & 1);
-        const double2 *as = As + s * Cfg::A_STAGE + wm * 32 + g;
-        const double2 *bs = Bs + s * Cfg::B_STAGE + wn * 32 + g;
-#pragma unroll
-        for (int ks = 0; ks < BK / 4; ++ks) {
-          const int k = ks * 4 + t4;
-          double2 a[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            a[q] = as[k * LDA + 8 * q];
-            if (conja) a[q].y = -a[q].y;
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            double2 b = bs[k * LDB + 8 * j];
-            if (conjb) b.y = -b.y;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              dmma_884(accr[i][j][0], accr[i][j][1], a[i].x, b.x);
-              dmma_884(acci[i][j][0], acci[i][j][1], a[i].x, b.y);
-              dmma_884(acci[i][j][0], acci[i][j][1], a[i].y, b.x);
-              dmma_884(accr[i][j][0], accr[i][j][1], -a[i].y, b.y);
-            }
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
-      }
-
-      const double2 alpha = p.alpha, beta = p.beta;
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const long long m = m0 + wm * 32 + 8 * i + g;
-            const long long n = n0 + wn * 32 + 8 * j + 2 * t4 + c;
-            if (m >= p.M || n >= p.N) continue;
-            if (p.cuplo == 1 && m < n - n0 + g0) continue;
-            if (p.cuplo == 2 && m > n - n0 + g0) continue;
-            const double xr = accr[i][j][c], xi = acci[i][j][c];
-            double2 o = make_double2(alpha.x * xr - alpha.y * xi, alpha.x * xi + alpha.y * xr);
-            if (!p.beta_zero) {
-              const double2 cv = p.C[n * p.ldc + m];
-              o.x += beta.x * cv.x - beta.y * cv.y;
-              o.y += beta.x * cv.y + beta.y * cv.x;
-            }
-            if (p.herm && m == n - n0 + g0) o.y = 0.0;
-            p.D[n * p.ldd + m] = o;
-          }
+// ---- staggered schedule: 1 persistent CTA per SM, TWO consumer groups (4 warps each) with their own
+//      stage rings and their own producer warp.  Two free-running tile streams that share an SM's
+//      DMMA pipe fairly drift into lock-step (equal tiles): both reach their HBM-latency-bound
+//      epilogue together and the pipe idles (the classic kernel: 84 % at k = 256, 90 % at k = 512).
+//      Here the groups are held half a tile apart with two mbarriers: a group's producer may
+//      start tile i only after the other group has passed the half-way mark of its tile i (i-1).
+//      In steady state both groups feed the pipe (two warps per SM sub-partition) and each one's
+//      epilogue falls into the middle of the other's main loop.
+template <bool CPLX, int MODE>
+__global__ void __launch_bounds__(GemmCfg<CPLX>::PP_THREADS, 1) gemm_dmma_pp_kernel(const __grid_constant__ GemmArgs<CPLX> p) {
+  using Cfg = GemmCfg<CPLX>;
+  using T = typename GemmArgs<CPLX>::T;
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, ST = Cfg::STAGES;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int RING = ST * (Cfg::A_STAGE + Cfg::B_STAGE);  // elements per group
+  T *base = reinterpret_cast<T *>(smem_raw);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(base + 2 * RING);  // [group][full ST | empty ST], then mid[2]
+  uint64_t *mid = bars + 4 * ST;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    init_ring<CPLX, MODE, 2>(bars, bars + ST);
+    init_ring<CPLX, MODE, 2>(bars + 2 * ST, bars + 3 * ST);
+    mbar_init(&mid[0], 4);
+    mbar_init(&mid[1], 4);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const long long nstreams = 2LL * gridDim.x;
+  const int imax = (int)((p.total_tiles + nstreams - 1) / nstreams);  // same trip count for both groups
+  // register re-balancing between the warp groups (separate code paths so ptxas can budget them):
+  // the 4 producer warps give registers back, the 8 consumer warps (64 accumulator doubles +
+  // double-buffered fragments each) take them
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    const int gq = (warp - 8) >> 1;
+    T *As = base + gq * RING, *Bs = As + ST * Cfg::A_STAGE;
+    uint64_t *full = bars + gq * 2 * ST, *empty = full + ST;
+    uint32_t it = 0;
+    if (MODE == 0 && (warp & 1)) return;  // TMA path: one producer warp per group is enough
+    for (int i = 0; i < imax; ++i) {
+      const long long t = 2LL * blockIdx.x + gq + (long long)i * nstreams;
+      int bi, bj;
+      const bool valid = t < p.total_tiles && tile_coords_tb<BM, BN, Cfg::GROUP>(p.tb, p.cuplo, p.NI, p.NJ, p.cm, t, bi, bj);
+      // stagger: group 0 waits for group 1's half-way mark of tile i-1, group 1 for group 0's of tile i
+      if (gq == 0) { if (i >= 1) mbar_wait(&mid[1], (i - 1) & 1); }
+      else mbar_wait(&mid[0], i & 1);
+      if (valid) produce_tile<CPLX, MODE, 2>(p, bi, bj, As, Bs, full, empty, it, warp & 1, lane);
+      else if (lane == 0) mbar_arrive_n(&mid[gq], MODE == 0 ? 4 : 2);
+      // (an empty slot passes its mark on behalf of the 4 consumer warps, but only after the gate
+      //  above and - generic path - only once BOTH producer warps are through it: nobody can ever
+      //  fall two marks behind, which is what the 1-bit mbarrier phase can tell apart)
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int gq = warp >> 2;
+    const T *As = base + gq * RING, *Bs = As + ST * Cfg::A_STAGE;
+    uint64_t *full = bars + gq * 2 * ST, *empty = full + ST;
+    uint32_t it = 0;
+    for (int i = 0; i < imax; ++i) {
+      const long long t = 2LL * blockIdx.x + gq + (long long)i * nstreams;
+      int bi, bj;
+      const bool valid = t < p.total_tiles && tile_coords_tb<BM, BN, Cfg::GROUP>(p.tb, p.cuplo, p.NI, p.NJ, p.cm, t, bi, bj);
+      if (valid) consume_tile<CPLX, MODE>(p, bi, bj, As, Bs, full, empty, it, &mid[gq], warp & 3, lane);
     }
   }
 }
@@ -479,25 +563,36 @@ static int launch_t(const chol_gemm_desc *d) {
   int dev = 0;
   cudaGetDevice(&dev);
   auto kern = tma ? gemm_dmma_kernel<CPLX, 0> : gemm_dmma_kernel<CPLX, 1>;
+  auto kern_pp = tma ? gemm_dmma_pp_kernel<CPLX, 0> : gemm_dmma_pp_kernel<CPLX, 1>;
   if (!attr_set[dev & 63][CPLX][tma]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_pp, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::PP_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev);
     attr_set[dev & 63][CPLX][tma] = true;
   }
-  // tuning switches (environment, read once): CHOL_GEMM_PERSIST=0 launches one CTA per tile,
-  // CHOL_GEMM_PREFETCH=0 disables the L2 prefetch of C
-  static int persist = -1, prefetch = -1;
+  // tuning switches (environment, read once):
+  //   CHOL_GEMM_PP=0        never use the ping-pong kernel (default: used when the grid has >= 4 tiles per SM)
+  //   CHOL_GEMM_PERSIST=n   classic kernel as n persistent CTAs per SM (default 0: one CTA per tile - the
+  //                         hardware's dynamic CTA placement beats a static persistent walk)
+  //   CHOL_GEMM_PREFETCH=0  disable the L2 prefetch of C
+  static int persist = -1, prefetch = -1, pingpong = -1;
   if (persist < 0) {
-    const char *e1 = getenv("CHOL_GEMM_PERSIST"), *e2 = getenv("CHOL_GEMM_PREFETCH");
-    persist = e1 ? atoi(e1) : 0;  // measured: the hardware's dynamic CTA placement beats a static persistent walk
+    const char *e1 = getenv("CHOL_GEMM_PERSIST"), *e2 = getenv("CHOL_GEMM_PREFETCH"), *e3 = getenv("CHOL_GEMM_PP");
+    persist = e1 ? atoi(e1) : 0;
     prefetch = e2 ? atoi(e2) : 1;
+    pingpong = e3 ? atoi(e3) : 1;
   }
   a.prefetch_c = prefetch;
   if (tiles > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
-  const long long resident = (long long)(persist > 0 ? persist : 2) * sm_count[dev & 63];  // persistent CTAs
-  const unsigned grid = (unsigned)((persist == 0 || tiles < resident) ? tiles : resident);
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a);
+  const int sms = sm_count[dev & 63];
+  if (pingpong && tiles >= 4LL * sms && a.K > 0) {  // (K = 0: no stages to pace the groups with)
+    kern_pp<<<(unsigned)sms, Cfg::PP_THREADS, Cfg::PP_SMEM_BYTES, st>>>(a);
+  } else {
+    const long long resident = (long long)(persist > 0 ? persist : 2) * sms;
+    const unsigned grid = (unsigned)((persist == 0 || tiles < resident) ? tiles : resident);
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a);
+  }
   CHOL_COUNT_LAUNCH();
   return (int)cudaGetLastError();
 }

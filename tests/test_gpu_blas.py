@@ -82,6 +82,28 @@ def test_gemm_tma_path_taken_and_matches_generic(p):
     assert np.abs(outs[0] - want).max() <= bound(p, k)
 
 
+@pytest.mark.parametrize("p", "dz")
+@pytest.mark.parametrize("ops", [("N", "T"), ("T", "N"), ("N", "N")])
+def test_gemm_large_grid_pingpong_kernel(blas, p, ops):
+    """Grids with >= 4 tiles per SM run on the ping-pong (two consumer groups, one producer) kernel:
+    check it, TMA-fed and generic, against the oracle at a size with ragged edges."""
+    tA, tB = ops
+    if PREC[p]["cplx"]:
+        tA, tB = tA.replace("T", "C"), tB.replace("T", "C")
+    m, n, k = (4226, 2114, 80) if p == "d" else (2114, 2114, 40)
+    A = H.rand_matrix(p, *((m, k) if tA == "N" else (k, m)), seed=31)
+    B = H.rand_matrix(p, *((k, n) if tB == "N" else (n, k)), seed=32)
+    Cm = H.rand_matrix(p, m, n, seed=33)
+    want = Cm.copy(order="F")
+    ORA.gemm(p, tA, tB, m, n, k, -1.0, A, B, 1.0, want)
+    dA, lda = G.to_dev(A)
+    dB, ldb = G.to_dev(B)
+    dC, ldc = G.to_dev(Cm)
+    blas.gemm2(p, tA, tB, m, n, k, -1.0, dA.data_ptr(), lda, dB.data_ptr(), ldb, 1.0, dC.data_ptr(), ldc, dC.data_ptr(), ldc)
+    G.sync()
+    assert np.abs(G.to_host(dC, m) - want).max() <= bound(p, k)
+
+
 @pytest.mark.parametrize("p", "dzsc")
 @pytest.mark.parametrize("n,k", [(200, 64), (129, 33), (64, 256), (513, 48)])
 def test_rankk(blas, p, n, k):
