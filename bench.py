@@ -217,7 +217,7 @@ def run_ours(args):
 
     uid = exchange_unique_id(chol.dist_unique_id, rank) if P > 1 else None
     d = chol.Dist(rank, P, uid, nb=args.nb)
-    nb = d.block_size("d")
+    nb = d.block_size("d", N)
     cols = owned_columns(N, nb, rank, P)
     nloc = len(cols)
     cols_t = torch.from_numpy(cols).to(dev)

@@ -353,10 +353,10 @@ class Dist:
         self.lapack = LapackHandle.__new__(LapackHandle)
         self.lapack.h = C.c_void_p(lib().cholDistLapackHandle(self.h))
 
-    def block_size(self, p):
+    def block_size(self, p, n):
         f = lib().cholDistBlockSize
         f.restype = C.c_size_t
-        return int(f(self.h, C.c_int(ord(p))))
+        return int(f(self.h, C.c_int(ord(p)), C.c_size_t(n)))
 
     def potrf(self, p, n, Aloc, ldl):
         f = getattr(lib(), "cholDist%spotrf" % _U[p])

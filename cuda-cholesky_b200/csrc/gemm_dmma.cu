@@ -77,6 +77,7 @@ struct GemmArgs {
   int conjB_regs;
   long long total_tiles;  // size of the tile sequence the persistent CTAs walk
   int prefetch_c;         // pull the C tile towards L2 when the producer starts a tile
+  int tps;                // staggered kernel: tiles per consumer group and CTA
   SchedTable tb;          // super-row prefix table for the tile decode
   int vecA, vecB;         // generic loader may use 16-byte copies along the stored rows of A / B
   ColMap cm;         // block-cyclic column map of D's columns (cnb = 0: identity)
@@ -460,8 +461,12 @@ __global__ void __launch_bounds__(GemmCfg<CPLX>::PP_THREADS, 1) gemm_dmma_pp_ker
     mbar_fence_init();
   }
   __syncthreads();
-  const long long nstreams = 2LL * gridDim.x;
-  const int imax = (int)((p.total_tiles + nstreams - 1) / nstreams);  // same trip count for both groups
+  // CTA b owns the 2*tps consecutive tiles [b*2*tps, (b+1)*2*tps): group g takes every other one.
+  // CTAs are deliberately NOT resident for the whole launch: they retire every few tiles so that
+  // kernels of the high-priority panel stream (and NCCL's broadcast CTAs) find an SM within
+  // microseconds - a fully persistent grid would serialise the look-ahead behind the update.
+  const int imax = p.tps;
+  const long long tbase = (long long)blockIdx.x * 2 * p.tps;
   // register re-balancing between the warp groups (separate code paths so ptxas can budget them):
   // the 4 producer warps give registers back, the 8 consumer warps (64 accumulator doubles +
   // double-buffered fragments each) take them
@@ -473,7 +478,7 @@ __global__ void __launch_bounds__(GemmCfg<CPLX>::PP_THREADS, 1) gemm_dmma_pp_ker
     uint32_t it = 0;
     if (MODE == 0 && (warp & 1)) return;  // TMA path: one producer warp per group is enough
     for (int i = 0; i < imax; ++i) {
-      const long long t = 2LL * blockIdx.x + gq + (long long)i * nstreams;
+      const long long t = tbase + gq + 2 * i;
       int bi, bj;
       const bool valid = t < p.total_tiles && tile_coords_tb<BM, BN, Cfg::GROUP>(p.tb, p.cuplo, p.NI, p.NJ, p.cm, t, bi, bj);
       // stagger: group 0 waits for group 1's half-way mark of tile i-1, group 1 for group 0's of tile i
@@ -492,7 +497,7 @@ __global__ void __launch_bounds__(GemmCfg<CPLX>::PP_THREADS, 1) gemm_dmma_pp_ker
     uint64_t *full = bars + gq * 2 * ST, *empty = full + ST;
     uint32_t it = 0;
     for (int i = 0; i < imax; ++i) {
-      const long long t = 2LL * blockIdx.x + gq + (long long)i * nstreams;
+      const long long t = tbase + gq + 2 * i;
       int bi, bj;
       const bool valid = t < p.total_tiles && tile_coords_tb<BM, BN, Cfg::GROUP>(p.tb, p.cuplo, p.NI, p.NJ, p.cm, t, bi, bj);
       if (valid) consume_tile<CPLX, MODE>(p, bi, bj, As, Bs, full, empty, it, &mid[gq], warp & 3, lane);
@@ -576,18 +581,22 @@ static int launch_t(const chol_gemm_desc *d) {
   //   CHOL_GEMM_PERSIST=n   classic kernel as n persistent CTAs per SM (default 0: one CTA per tile - the
   //                         hardware's dynamic CTA placement beats a static persistent walk)
   //   CHOL_GEMM_PREFETCH=0  disable the L2 prefetch of C
-  static int persist = -1, prefetch = -1, pingpong = -1;
+  //   CHOL_GEMM_TPS=n       staggered kernel: tiles per group and CTA (default 8)
+  static int persist = -1, prefetch = -1, pingpong = -1, tps = 8;
   if (persist < 0) {
     const char *e1 = getenv("CHOL_GEMM_PERSIST"), *e2 = getenv("CHOL_GEMM_PREFETCH"), *e3 = getenv("CHOL_GEMM_PP");
     persist = e1 ? atoi(e1) : 0;
     prefetch = e2 ? atoi(e2) : 1;
     pingpong = e3 ? atoi(e3) : 1;
+    const char *e4 = getenv("CHOL_GEMM_TPS");
+    if (e4 && atoi(e4) > 0) tps = atoi(e4);
   }
   a.prefetch_c = prefetch;
   if (tiles > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
   const int sms = sm_count[dev & 63];
   if (pingpong && tiles >= 4LL * sms && a.K > 0) {  // (K = 0: no stages to pace the groups with)
-    kern_pp<<<(unsigned)sms, Cfg::PP_THREADS, Cfg::PP_SMEM_BYTES, st>>>(a);
+    a.tps = tps;
+    kern_pp<<<(unsigned)((tiles + 2 * tps - 1) / (2 * tps)), Cfg::PP_THREADS, Cfg::PP_SMEM_BYTES, st>>>(a);
   } else {
     const long long resident = (long long)(persist > 0 ? persist : 2) * sms;
     const unsigned grid = (unsigned)((persist == 0 || tiles < resident) ? tiles : resident);

@@ -99,7 +99,7 @@ typedef struct chol_ws {
   CUdeviceptr Wd;   /* nb x db : panel of the diagonal-block recursion */
 } chol_ws;
 
-size_t chol_default_nb(int prec);
+size_t chol_default_nb(int prec, size_t n);
 CUresult chol_carve(CULAPACKhandle h, int prec, size_t n, chol_ws *w);
 /* Cholesky of a jb x jb (jb <= nb) diagonal block / out-of-place inverse of one (other triangle zero) */
 CUresult chol_potrf_diag(int prec, int uplo, size_t jb, CUdeviceptr A, size_t lda, long *dinfo, long base,

@@ -28,11 +28,17 @@ static const double ONE[2] = {1.0, 0.0};
 static const double ZERO[2] = {0.0, 0.0};
 static const double MONE[2] = {-1.0, 0.0};
 
-size_t chol_default_nb(int prec) { return prec == 'z' ? 128 : 256; }
+/* outer block size: k of the trailing update.  Larger k amortises the C-tile epilogue (measured on
+ * B200, d: 512 beats 256 from N ~ 32768 up), smaller k shortens the serial panel chain. */
+size_t chol_default_nb(int prec, size_t n) {
+  if (prec == 'z') return 128;
+  if (prec == 'd') return n >= 24576 ? 512 : 256;
+  return 256;
+}
 
 CUresult chol_carve(CULAPACKhandle h, int prec, size_t n, chol_ws *w) {
   w->es = chol_esize(prec);
-  w->nb = h->nb ? h->nb : chol_default_nb(prec);
+  w->nb = h->nb ? h->nb : chol_default_nb(prec, n);
   w->db = (size_t)chol_diag_max(prec);
   if (w->nb < w->db) w->db = w->nb;
   w->ldw = chol_roundup(n > w->nb ? n : w->nb, 16);

@@ -452,7 +452,7 @@ CUresult cholDistDestroy(cholDist R) {
 
 CUresult cholDistSetBlockSize(cholDist R, size_t nb) { return R ? cuLAPACKSetBlockSize(R->lap, nb) : CUDA_ERROR_INVALID_VALUE; }
 CULAPACKhandle cholDistLapackHandle(cholDist R) { return R ? R->lap : NULL; }
-size_t cholDistBlockSize(cholDist R, int prec) { return (R && R->lap->nb) ? R->lap->nb : chol_default_nb(prec); }
+size_t cholDistBlockSize(cholDist R, int prec, size_t n) { return (R && R->lap->nb) ? R->lap->nb : chol_default_nb(prec, n); }
 /* columns of an n x n matrix held by `rank` (they are packed side by side, block c = lc*P + rank) */
 size_t cholDistLocalCols(size_t n, size_t nb, int rank, int nranks) { return local_cols(n, nb, rank, nranks); }
 
