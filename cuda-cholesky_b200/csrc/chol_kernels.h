@@ -53,6 +53,10 @@ int chol_diag_max(int prec); /* largest n the one-CTA diagonal kernels accept: 1
  * info_base + failing column (1-based) if it is still 0 and a pivot is <= 0 or NaN; when
  * *dinfo != 0 on entry the kernel does nothing (lapack/dpotrf.c:70-73 semantics). */
 int chol_potf2_launch(int prec, int uplo, size_t n, void *A, size_t lda, long *dinfo, long info_base, void *stream);
+/* fused: Cholesky of the block in place AND X := inverse of the factor (uplo triangle; the other
+ * triangle of X is set to zero).  Same info semantics as chol_potf2_launch. */
+int chol_potf2_inv_launch(int prec, int uplo, size_t n, void *A, size_t lda, void *X, size_t ldx, long *dinfo,
+                          long info_base, void *stream);
 /* inverse of an n x n triangular block, out of place (B may equal A).  Only the uplo triangle of
  * B is written; if zero_other != 0 the opposite triangle of B is set to zero as well.  Zero pivot
  * -> *dinfo = info_base + column (1-based) when *dinfo == 0 (lapack/dtrtri.c:49-52). */

@@ -166,13 +166,13 @@ __global__ void __launch_bounds__(PANEL_THREADS) trti2_kernel(int upper, int uni
         lk[q2] = (q2 >= q && i > k && i < n) ? L[i + k * LD] : zero_of<T>();
       }
 #pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        if (k < warp + 16 * c) continue;  // warp-uniform
+      for (int c = 0; c < NC; ++c) {  // branch-free: the NC chains interleave
+        const bool active = (k >= warp + 16 * c);
         T rk;
         if constexpr (ScalarOf<T>::cplx) { rk.x = __shfl_sync(0xffffffffu, r[c][q].x, kk); rk.y = __shfl_sync(0xffffffffu, r[c][q].y, kk); }
         else rk = __shfl_sync(0xffffffffu, r[c][q], kk);
-        const T xk = mul(rk, dk);
-        if (lane == kk) r[c][q] = xk;
+        const T xk = active ? mul(rk, dk) : zero_of<T>();
+        if (lane == kk && active) r[c][q] = xk;
         const T nxk = neg(xk);
 #pragma unroll
         for (int q2 = 0; q2 < NQ; ++q2)
@@ -190,6 +190,133 @@ __global__ void __launch_bounds__(PANEL_THREADS) trti2_kernel(int upper, int uni
       if (i < n) {
         if (i >= j) { if (!upper) B[(long long)j * ldb + i] = r[c][q]; else B[(long long)i * ldb + j] = r[c][q]; }
         else if (zero_other) { if (!upper) B[(long long)j * ldb + i] = zero_of<T>(); else B[(long long)i * ldb + j] = zero_of<T>(); }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// potf2 + inverse, fused (the POTRF panel chain needs both the factor L of a diagonal block and
+// L^-1, lapack/spotrf.c:253): phase 1 is the register-resident right-looking factorisation above,
+// except that every finished column is published into a persistent shared-memory copy of L (and
+// 1/L_cc is kept); phase 2 inverts that copy by forward substitution, eight columns per warp as
+// independent, branch-free chains.  One launch, one pass over HBM, no division after the rsqrt.
+template <typename T, int NA, int NB, int NQ, int NC>
+__global__ void __launch_bounds__(PANEL_THREADS) potf2_inv_kernel(int upper, int n, T *A, long long lda, T *X, long long ldx,
+                                                                  long *dinfo, long info_base) {
+  using Real = typename ScalarOf<T>::Real;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NMAX = 32 * NA, LD = NMAX + 1;
+  T *Ls = reinterpret_cast<T *>(smem_raw);          // L(i,c) at Ls[i + c*LD]
+  Real *dinv = reinterpret_cast<Real *>(Ls + (size_t)NMAX * LD);
+  __shared__ int sfail;
+  if (*dinfo != 0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) sfail = 0;
+  T reg[NA][NB];
+#pragma unroll
+  for (int a = 0; a < NA; ++a)
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const int i = lane + 32 * a, k = warp + 16 * b;
+      T v = zero_of<T>();
+      if (i < n && k < n && i >= k) v = upper ? conj_of(A[(long long)i * lda + k]) : A[(long long)k * lda + i];
+      reg[a][b] = v;
+    }
+  __syncthreads();
+  // ---------------- phase 1: factor ----------------
+#pragma unroll
+  for (int bo = 0; bo < NB; ++bo) {
+    const int ao = bo >> 1;
+    for (int cw = 0; cw < 16; ++cw) {
+      const int c = 16 * bo + cw;
+      if (c >= n) break;
+      T *cb = Ls + c * LD;
+      if (warp == cw) {
+        const Real d = __shfl_sync(0xffffffffu, re_of(reg[ao][bo]), c & 31);
+        if (!(d > Real(0))) {  // <= 0 or NaN: not positive definite (lapack/dpotrf.c:70-73)
+          if (lane == 0) {
+            sfail = 1;
+            *dinfo = info_base + c + 1;
+            A[(long long)c * lda + c] = from_real<T>(d);
+          }
+        } else {
+          const Real rinv = rsqrt(d), r = d * rinv;
+          if (lane == 0) dinv[c] = rinv;
+#pragma unroll
+          for (int a = 0; a < NA; ++a) {
+            const int i = lane + 32 * a;
+            if (i < n) {
+              const T x = (i > c) ? rscale(reg[a][bo], rinv) : ((i == c) ? from_real<T>(r) : zero_of<T>());
+              cb[i] = x;  // rows above the diagonal are stored as zeros: phase 2 reads a full column
+              if (i >= c) { if (!upper) A[(long long)c * lda + i] = x; else A[(long long)i * lda + c] = conj_of(x); }
+            }
+          }
+        }
+      }
+      __syncthreads();
+      if (sfail) return;
+      T li[NA], f[NB];
+#pragma unroll
+      for (int a = 0; a < NA; ++a) li[a] = cb[lane + 32 * a];
+#pragma unroll
+      for (int b = bo; b < NB; ++b) {
+        const int k = warp + 16 * b;
+        f[b] = (k > c && k < n) ? neg(conj_of(cb[k])) : zero_of<T>();
+      }
+#pragma unroll
+      for (int b = bo; b < NB; ++b)
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+          if (32 * a + 31 >= 16 * b) fma_acc(reg[a][b], li[a], (lane + 32 * a >= warp + 16 * b) ? f[b] : zero_of<T>());
+    }
+  }
+  __syncthreads();
+  // ---------------- phase 2: X = L^-1 ----------------
+  T r[NC][NQ];
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) r[c][q] = (lane + 32 * q == warp + 16 * c) ? one_of<T>() : zero_of<T>();
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    if (32 * q >= n) continue;
+    for (int kk = 0; kk < 32; ++kk) {
+      const int k = 32 * q + kk;
+      if (k >= n) break;
+      if (k < warp) continue;  // none of this warp's columns has started yet (warp-uniform)
+      const Real dk = dinv[k];
+      T lk[NQ];
+#pragma unroll
+      for (int q2 = 0; q2 < NQ; ++q2) {
+        const int i = lane + 32 * q2;
+        lk[q2] = (q2 >= q && i > k && i < n) ? Ls[i + k * LD] : zero_of<T>();
+      }
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {  // branch-free: the NC chains interleave
+        const bool active = (k >= warp + 16 * c);
+        T rk;
+        if constexpr (ScalarOf<T>::cplx) { rk.x = __shfl_sync(0xffffffffu, r[c][q].x, kk); rk.y = __shfl_sync(0xffffffffu, r[c][q].y, kk); }
+        else rk = __shfl_sync(0xffffffffu, r[c][q], kk);
+        const T xk = active ? rscale(rk, dk) : zero_of<T>();
+        if (lane == kk && active) r[c][q] = xk;
+        const T nxk = neg(xk);
+#pragma unroll
+        for (int q2 = 0; q2 < NQ; ++q2)
+          if (q2 >= q) fma_acc(r[c][q2], lk[q2], nxk);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int j = warp + 16 * c;
+    if (j >= n) continue;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int i = lane + 32 * q;
+      if (i < n) {  // the other triangle of X is zeroed: the panel solve uses X as a dense operand
+        const T v = (i >= j) ? r[c][q] : zero_of<T>();
+        if (!upper) X[(long long)j * ldx + i] = v; else X[(long long)i * ldx + j] = conj_of(v);
       }
     }
   }
@@ -354,6 +481,17 @@ static int potf2_t(int uplo, size_t n, void *A, size_t lda, long *dinfo, long ba
   return (int)cudaGetLastError();
 }
 template <typename T>
+static int potf2_inv_t(int uplo, size_t n, void *A, size_t lda, void *X, size_t ldx, long *dinfo, long base, cudaStream_t st) {
+  constexpr int NMAX = sizeof(T) == 16 ? 64 : 128;
+  using Real = typename ScalarOf<T>::Real;
+  const size_t sm = (size_t)NMAX * (NMAX + 1) * sizeof(T) + NMAX * sizeof(Real);
+  auto kern = potf2_inv_kernel<T, NMAX / 32, NMAX / 16, NMAX / 32, NMAX / 16>;
+  int e = set_smem(kern, sm); if (e) return e;
+  kern<<<1, PANEL_THREADS, sm, st>>>(uplo == 'U', (int)n, (T *)A, (long long)lda, (T *)X, (long long)ldx, dinfo, base);
+  CHOL_COUNT_LAUNCH();
+  return (int)cudaGetLastError();
+}
+template <typename T>
 static int trti2_t(int uplo, int diag, size_t n, const void *A, size_t lda, void *B, size_t ldb, int zo, long *dinfo, long base, cudaStream_t st) {
   const size_t sm = panel_smem<T>(n, n);
   int e = set_smem(trti2_kernel<T, (sizeof(T) == 16 ? 64 : 128) / 32, (sizeof(T) == 16 ? 64 : 128) / 16>, sm); if (e) return e;
@@ -423,6 +561,12 @@ extern "C" int chol_potf2_launch(int prec, int uplo, size_t n, void *A, size_t l
   if (n == 0) return 0;
   if (n > (size_t)chol_diag_max(prec)) return (int)cudaErrorInvalidValue;
   DISPATCH(prec, potf2_t<T>(uplo, n, A, lda, dinfo, info_base, (cudaStream_t)stream));
+}
+extern "C" int chol_potf2_inv_launch(int prec, int uplo, size_t n, void *A, size_t lda, void *X, size_t ldx, long *dinfo,
+                                     long info_base, void *stream) {
+  if (n == 0) return 0;
+  if (n > (size_t)chol_diag_max(prec)) return (int)cudaErrorInvalidValue;
+  DISPATCH(prec, potf2_inv_t<T>(uplo, n, A, lda, X, ldx, dinfo, info_base, (cudaStream_t)stream));
 }
 extern "C" int chol_trti2_launch(int prec, int uplo, int diag, size_t n, const void *A, size_t lda, void *B, size_t ldb,
                                  int zero_other, long *dinfo, long info_base, void *stream) {

@@ -104,6 +104,8 @@ CUresult chol_carve(CULAPACKhandle h, int prec, size_t n, chol_ws *w);
 /* Cholesky of a jb x jb (jb <= nb) diagonal block / out-of-place inverse of one (other triangle zero) */
 CUresult chol_potrf_diag(int prec, int uplo, size_t jb, CUdeviceptr A, size_t lda, long *dinfo, long base,
                          const chol_ws *w, CUstream st);
+CUresult chol_diag_factor_inverse(int prec, int uplo, size_t jb, CUdeviceptr A, size_t lda, CUdeviceptr X, size_t ldx,
+                                  long *dinfo, long base, const chol_ws *w, CUstream st);
 CUresult chol_trtri_small(int prec, int uplo, int diag, size_t jb, CUdeviceptr A, size_t lda, CUdeviceptr X,
                           size_t ldx, long *dinfo, long base, const chol_ws *w, CUstream st);
 

@@ -123,6 +123,53 @@ CUresult chol_trtri_small(int prec, int uplo, int diag, size_t jb, CUdeviceptr A
   return CUDA_SUCCESS;
 }
 
+/* Factor the jb x jb (jb <= nb) diagonal block A in place AND produce X = inverse of its factor
+ * (ldx, other triangle zero) - what every POTRF step needs for the panel solve.  Each db-block
+ * is one fused potf2+inverse launch; the blocks are tied together with small GEMMs. */
+CUresult chol_diag_factor_inverse(int prec, int uplo, size_t jb, CUdeviceptr A, size_t lda, CUdeviceptr X, size_t ldx,
+                                  long *dinfo, long base, const chol_ws *w, CUstream st) {
+  const size_t es = w->es, db = w->db, nblk = (jb + db - 1) / db;
+  const int herm = chol_is_complex(prec);
+  if (nblk > 1) RT_CHECK(chol_fill_launch(prec, 0, jb, jb, 0.0, 0.0, (void *)X, ldx, (void *)st));
+  for (size_t c = 0; c < nblk; c++) {
+    const size_t i = c * db, ib = chol_min(db, jb - i), r = jb - i - ib;
+    const CUdeviceptr Aii = chol_at(A, lda, i, i, es), Xii = chol_at(X, ldx, i, i, es);
+    RT_CHECK(chol_potf2_inv_launch(prec, uplo, ib, (void *)Aii, lda, (void *)Xii, ldx, dinfo, base + (long)i, (void *)st));
+    if (r == 0) break;
+    const CUdeviceptr A22 = chol_at(A, lda, i + ib, i + ib, es);
+    if (uplo == 'L') {
+      const CUdeviceptr A21 = chol_at(A, lda, i + ib, i, es);
+      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'C', r, ib, ib, ONE, A21, lda, Xii, ldx, ZERO, 0, 0, w->Wd, w->nb, st));
+      RT_CHECK(chol_copy_launch(prec, 'N', 0, r, ib, (const void *)w->Wd, w->nb, (void *)A21, lda, (void *)st));
+    } else {
+      const CUdeviceptr A12 = chol_at(A, lda, i, i + ib, es);
+      CU_ERROR_CHECK(chol_gemm(prec, 'C', 'N', r, ib, ib, ONE, A12, lda, Xii, ldx, ZERO, 0, 0, w->Wd, w->nb, st));
+      RT_CHECK(chol_copy_launch(prec, 'C', 0, r, ib, (const void *)w->Wd, w->nb, (void *)A12, lda, (void *)st));
+    }
+    CU_ERROR_CHECK(chol_gemm_ex(prec, 'N', 'C', 0, 0, 0, 0, uplo, herm, r, r, ib, MONE, w->Wd, w->nb, w->Wd, w->nb, ONE, A22,
+                                lda, A22, lda, st));
+  }
+  /* off-diagonal blocks of the inverse (same recurrences as chol_trtri_small) */
+  for (size_t b = 1; b < nblk; b++) {
+    const size_t c = (uplo == 'L') ? nblk - 1 - b : b;
+    const size_t i = c * db, ib = chol_min(db, jb - i);
+    const CUdeviceptr Xcc = chol_at(X, ldx, i, i, es);
+    if (uplo == 'L') {
+      const size_t r = jb - i - ib;
+      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'N', r, ib, ib, ONE, chol_at(A, lda, i + ib, i, es), lda, Xcc, ldx, ZERO, 0, 0,
+                               w->T1, w->nb, st));
+      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'N', r, ib, r, MONE, chol_at(X, ldx, i + ib, i + ib, es), ldx, w->T1, w->nb, ZERO,
+                               0, 0, chol_at(X, ldx, i + ib, i, es), ldx, st));
+    } else {
+      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'N', i, ib, ib, ONE, chol_at(A, lda, 0, i, es), lda, Xcc, ldx, ZERO, 0, 0, w->T1,
+                               w->nb, st));
+      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'N', i, ib, i, MONE, X, ldx, w->T1, w->nb, ZERO, 0, 0, chol_at(X, ldx, 0, i, es),
+                               ldx, st));
+    }
+  }
+  return CUDA_SUCCESS;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 CUresult chol_potrf(CULAPACKhandle h, int prec, int uplo, size_t n, CUdeviceptr A, size_t lda, long *info) {
   chol_ws w;
@@ -141,9 +188,11 @@ CUresult chol_potrf(CULAPACKhandle h, int prec, int uplo, size_t n, CUdeviceptr 
     const CUdeviceptr Ajj = chol_at(A, lda, j, j, es);
     const CUdeviceptr W = w.W[step & 1];
     /* --- panel stream: diagonal block, its inverse, panel solve into W, write-back --- */
-    CU_ERROR_CHECK(chol_potrf_diag(prec, uplo, jb, Ajj, lda, dinfo, (long)j, &w, sp));
-    if (rest == 0) break;
-    CU_ERROR_CHECK(chol_trtri_small(prec, uplo, 'N', jb, Ajj, lda, w.Xd, nb, dinfo, (long)j, &w, sp));
+    if (rest == 0) {
+      CU_ERROR_CHECK(chol_potrf_diag(prec, uplo, jb, Ajj, lda, dinfo, (long)j, &w, sp));
+      break;
+    }
+    CU_ERROR_CHECK(chol_diag_factor_inverse(prec, uplo, jb, Ajj, lda, w.Xd, nb, dinfo, (long)j, &w, sp));
     if (uplo == 'L') {
       const CUdeviceptr P = chol_at(A, lda, j + jb, j, es); /* rest x jb */
       CU_ERROR_CHECK(chol_gemm(prec, 'N', 'C', rest, jb, jb, ONE, P, lda, w.Xd, nb, ZERO, 0, 0, W, w.ldw, sp));

@@ -342,10 +342,10 @@ static CUresult dist_potrf(chol_rank *R, int prec, size_t n, CUdeviceptr Aloc, s
     if (me == owner) {
       const size_t lc = c / (size_t)P;
       const CUdeviceptr Ajj = chol_at(Aloc, ldl, j, lc * nb, es);
-      CU_ERROR_CHECK(chol_potrf_diag(prec, 'L', jb, Ajj, ldl, dinfo, (long)j, &w, sp));
+      if (!rest) CU_ERROR_CHECK(chol_potrf_diag(prec, 'L', jb, Ajj, ldl, dinfo, (long)j, &w, sp));
       if (rest) {
         const CUdeviceptr Pn = chol_at(Aloc, ldl, j + jb, lc * nb, es);
-        CU_ERROR_CHECK(chol_trtri_small(prec, 'L', 'N', jb, Ajj, ldl, w.Xd, nb, dinfo, (long)j, &w, sp));
+        CU_ERROR_CHECK(chol_diag_factor_inverse(prec, 'L', jb, Ajj, ldl, w.Xd, nb, dinfo, (long)j, &w, sp));
         CU_ERROR_CHECK(chol_gemm(prec, 'N', 'C', rest, jb, jb, ONE, Pn, ldl, w.Xd, nb, ZERO, 0, 0, W, ldw, sp));
         RT_CHECK(chol_copy_launch(prec, 'N', 0, rest, jb, (const void *)W, ldw, (void *)Pn, ldl, (void *)sp));
       }
