@@ -258,6 +258,7 @@ def run_ours(args):
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = chol.launch_count()
     upd_ms, upd_flops, upd_launches = d.lapack.profile_read()
+    hist = d.lapack.profile_history() if os.environ.get("CHOL_BENCH_HIST") else None
     d.lapack.profile(False)
     info = combine_info(info)
     ms_per_step = ms_total / K
@@ -361,6 +362,8 @@ def run_ours(args):
             "roofline": roofline}
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if hist:
+        sys.stderr.write("update-kernel launches (ms, TFLOP/s): " + " ".join("%.3f/%.1f" % (m, f / m / 1e9) for m, f in hist[:len(hist) // K]) + "\n")
     print(json.dumps(line), flush=True)
     if P > 1:
         dist.destroy_process_group()

@@ -156,6 +156,12 @@ class LapackHandle:
         _check("cuLAPACKProfileRead", lib().cuLAPACKProfileRead(self.h, C.byref(ms), C.byref(fl), C.byref(n)))
         return ms.value, fl.value, n.value
 
+    def profile_history(self, cap=4096):
+        ms, fl = (C.c_float * cap)(), (C.c_double * cap)()
+        n = lib().cuLAPACKProfileHistory(self.h, ms, fl, C.c_int(cap))
+        n = min(n, cap)
+        return [(ms[i], fl[i]) for i in range(n)]
+
     def close(self):
         if self.h:
             lib().cuLAPACKDestroy(self.h)

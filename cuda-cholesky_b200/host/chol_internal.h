@@ -51,6 +51,9 @@ struct __culapackhandle_st {
   double *prof_flops;
   double prof_total_ms, prof_total_flops;
   int prof_launches;
+  float *prof_hist_ms;    /* per-launch history since cuLAPACKProfile(h, 1) (capacity prof_cap) */
+  double *prof_hist_flops;
+  int prof_hist_n;
 };
 
 static inline size_t chol_esize(int prec) { return prec == 's' ? 4 : (prec == 'z' ? 16 : 8); }

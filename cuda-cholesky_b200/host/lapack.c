@@ -240,6 +240,10 @@ CUresult chol_potrf(CULAPACKhandle h, int prec, int uplo, size_t n, CUdeviceptr 
     h->prof_total_ms += ms;
     h->prof_total_flops += h->prof_flops[i];
     h->prof_launches++;
+    if (h->prof_hist_n < h->prof_cap) {
+      h->prof_hist_ms[h->prof_hist_n] = ms;
+      h->prof_hist_flops[h->prof_hist_n++] = h->prof_flops[i];
+    }
   }
   h->prof_n = 0;
   CUcontext dummy;

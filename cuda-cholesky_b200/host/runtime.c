@@ -145,6 +145,8 @@ CUresult cuLAPACKDestroy(CULAPACKhandle h) {
     free(h->prof_e0);
     free(h->prof_e1);
     free(h->prof_flops);
+    free(h->prof_hist_ms);
+    free(h->prof_hist_flops);
     CUcontext dummy;
     CU_ERROR_CHECK(cuCtxPopCurrent(&dummy));
   }
@@ -177,7 +179,9 @@ CUresult cuLAPACKProfile(CULAPACKhandle h, int enable) {
     h->prof_e0 = calloc((size_t)cap, sizeof(CUevent));
     h->prof_e1 = calloc((size_t)cap, sizeof(CUevent));
     h->prof_flops = calloc((size_t)cap, sizeof(double));
-    if (!h->prof_e0 || !h->prof_e1 || !h->prof_flops) return CUDA_ERROR_OUT_OF_MEMORY;
+    h->prof_hist_ms = calloc((size_t)cap, sizeof(float));
+    h->prof_hist_flops = calloc((size_t)cap, sizeof(double));
+    if (!h->prof_e0 || !h->prof_e1 || !h->prof_flops || !h->prof_hist_ms || !h->prof_hist_flops) return CUDA_ERROR_OUT_OF_MEMORY;
     CU_ERROR_CHECK(cuCtxPushCurrent(h->context));
     for (int i = 0; i < cap; i++) {
       CU_ERROR_CHECK(cuEventCreate(&h->prof_e0[i], CU_EVENT_DEFAULT));
@@ -190,7 +194,18 @@ CUresult cuLAPACKProfile(CULAPACKhandle h, int enable) {
   h->profile = enable;
   h->prof_total_ms = h->prof_total_flops = 0.0;
   h->prof_launches = 0;
+  h->prof_hist_n = 0;
   return CUDA_SUCCESS;
+}
+
+/* per-launch history (ms, algorithmic flops) of the first min(cap, n) timed launches; returns n */
+int cuLAPACKProfileHistory(CULAPACKhandle h, float *ms, double *flops, int cap) {
+  if (h == NULL) return 0;
+  for (int i = 0; i < h->prof_hist_n && i < cap; i++) {
+    ms[i] = h->prof_hist_ms[i];
+    flops[i] = h->prof_hist_flops[i];
+  }
+  return h->prof_hist_n;
 }
 
 /* totals since cuLAPACKProfile(h, 1): device milliseconds, algorithmic flops, launches */
