@@ -357,7 +357,19 @@ static CUresult dist_carve(chol_rank *R, int prec, size_t n, chol_ws *w) {
   return e;
 }
 
-static CUresult dist_potrf(chol_rank *R, int prec, size_t n, CUdeviceptr Aloc, size_t ldl, long *info) {
+/* optional: stream every finished block column of a rank straight back to the caller's host matrix
+ * while the factorisation continues (lower form only) */
+typedef struct {
+  char *hostA;
+  size_t lda;
+  CUstream s_copy;
+  CUevent ev[8];
+} dist_gather;
+
+static CUresult copy2d(int h2d, void *host, size_t ldh, CUdeviceptr dev, size_t ldd, size_t rows, size_t cols, size_t es,
+                       CUstream st);
+
+static CUresult dist_potrf(chol_rank *R, int prec, size_t n, CUdeviceptr Aloc, size_t ldl, long *info, dist_gather *ga) {
   CULAPACKhandle h = R->lap;
   const int P = R->nranks, me = R->rank;
   chol_ws w;
@@ -380,7 +392,15 @@ static CUresult dist_potrf(chol_rank *R, int prec, size_t n, CUdeviceptr Aloc, s
     if (me == owner) {
       const size_t lc = c / (size_t)P;
       const CUdeviceptr Ajj = chol_at(Aloc, ldl, j, lc * nb, es);
-      if (!rest) CU_ERROR_CHECK(chol_potrf_diag(prec, 'L', jb, Ajj, ldl, dinfo, (long)j, &w, sp));
+      if (!rest) {
+        CU_ERROR_CHECK(chol_potrf_diag(prec, 'L', jb, Ajj, ldl, dinfo, (long)j, &w, sp));
+        if (ga != NULL) {
+          CUevent e = ga->ev[lc & 7];
+          CU_ERROR_CHECK(cuEventRecord(e, sp));
+          CU_ERROR_CHECK(cuStreamWaitEvent(ga->s_copy, e, 0));
+          CU_ERROR_CHECK(copy2d(0, ga->hostA + (j * ga->lda + j) * es, ga->lda, Ajj, ldl, jb, jb, es, ga->s_copy));
+        }
+      }
       if (rest) {
         const CUdeviceptr Pn = chol_at(Aloc, ldl, j + jb, lc * nb, es);
         CU_ERROR_CHECK(chol_diag_factor_inverse(prec, 'L', jb, Ajj, ldl, w.Xd, nb, dinfo, (long)j, &w, sp));
@@ -393,6 +413,13 @@ static CUresult dist_potrf(chol_rank *R, int prec, size_t n, CUdeviceptr Aloc, s
     if (me == owner) { /* write-back into the matrix is off the critical path: after the broadcast has been queued */
       const CUdeviceptr Pn = chol_at(Aloc, ldl, j + jb, (c / (size_t)P) * nb, es);
       RT_CHECK(chol_copy_launch(prec, 'N', 0, rest, jb, (const void *)W, ldw, (void *)Pn, ldl, (void *)sp));
+      if (ga != NULL) { /* block column c is final: D2H on the copy stream, overlapped with the remaining steps */
+        CUevent e = ga->ev[(c / (size_t)P) & 7];
+        CU_ERROR_CHECK(cuEventRecord(e, sp));
+        CU_ERROR_CHECK(cuStreamWaitEvent(ga->s_copy, e, 0));
+        CU_ERROR_CHECK(copy2d(0, ga->hostA + (j * ga->lda + j) * es, ga->lda, chol_at(Aloc, ldl, j, (c / (size_t)P) * nb, es), ldl,
+                              n - j, jb, es, ga->s_copy));
+      }
     }
     CU_ERROR_CHECK(cuEventRecord(h->ev_panel[c % CHOL_EVENT_RING], sp));
 
@@ -433,6 +460,7 @@ static CUresult dist_potrf(chol_rank *R, int prec, size_t n, CUdeviceptr Aloc, s
   CU_ERROR_CHECK(cuMemcpyDtoHAsync(h->hinfo, h->dinfo, sizeof(long), sp));
   CU_ERROR_CHECK(cuStreamSynchronize(sp));
   CU_ERROR_CHECK(cuStreamSynchronize(su));
+  if (ga != NULL) CU_ERROR_CHECK(cuStreamSynchronize(ga->s_copy));
   *info = *h->hinfo;
   for (int i = 0; i < h->prof_n; i++) {
     float ms = 0.f;
@@ -519,7 +547,7 @@ size_t cholDistLocalCols(size_t n, size_t nb, int rank, int nranks) { return loc
     }                                                                                                       \
     if (n == 0) return CUDA_SUCCESS;                                                                        \
     CU_ERROR_CHECK(cuCtxPushCurrent(R->context));                                                           \
-    const CUresult e = dist_potrf(R, p, n, Aloc, ldl, info);                                                \
+    const CUresult e = dist_potrf(R, p, n, Aloc, ldl, info, NULL);                                                \
     CUcontext dummy;                                                                                        \
     cuCtxPopCurrent(&dummy);                                                                                \
     return e;                                                                                               \
@@ -721,12 +749,25 @@ static CUresult rank_potrf_task(const void *argp) {
     }
   }
   CU_ERROR_CHECK(cuStreamSynchronize(st));
-  /* ---- factor ---- */
-  CU_ERROR_CHECK(dist_potrf(R, prec, n, R->local, ldl, &a->info));
-  /* ---- gather ----
-   * Whole block columns / rows travel back.  The part of each diagonal block that lies in the
-   * caller's OTHER triangle was uploaded with the block, is never written by the factorisation and
-   * therefore returns bit-identical (for Upper it is conjugated twice, which is exact). */
+  /* ---- factor (lower: finished block columns stream back to the host while later steps run) ---- */
+  unsigned int memtype = 0; /* overlap only with page-locked host memory: a pageable D2H would block this thread */
+  const bool pinned = cuPointerGetAttribute(&memtype, CU_POINTER_ATTRIBUTE_MEMORY_TYPE, (CUdeviceptr)(size_t)hostA) == CUDA_SUCCESS &&
+                      memtype == CU_MEMORYTYPE_HOST;
+  if (a->uplo == 'L' && pinned) {
+    dist_gather ga;
+    ga.hostA = hostA;
+    ga.lda = lda;
+    CU_ERROR_CHECK(cuStreamCreate(&ga.s_copy, CU_STREAM_NON_BLOCKING));
+    for (int i = 0; i < 8; i++) CU_ERROR_CHECK(cuEventCreate(&ga.ev[i], CU_EVENT_DISABLE_TIMING));
+    const CUresult fe = dist_potrf(R, prec, n, R->local, ldl, &a->info, &ga);
+    for (int i = 0; i < 8; i++) cuEventDestroy(ga.ev[i]);
+    cuStreamDestroy(ga.s_copy);
+    return fe;
+  }
+  CU_ERROR_CHECK(dist_potrf(R, prec, n, R->local, ldl, &a->info, NULL));
+  /* ---- gather: whole block columns / rows travel back (upper: through a transposing staging
+   * buffer).  The part of each diagonal block that lies in the caller's OTHER triangle was uploaded
+   * with the block, is never written by the factorisation and returns bit-identical. */
   for (size_t c = (size_t)me, lc = 0; c < nblk; c += (size_t)P, lc++) {
     const size_t j = c * nb, jb = chol_min(nb, n - j), rows = n - j;
     const CUdeviceptr src = chol_at(R->local, ldl, j, lc * nb, es);

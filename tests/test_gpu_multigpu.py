@@ -41,6 +41,24 @@ def test_multigpu_potrf_host_pointers(mgpu, p, uplo, n):
     assert np.array_equal(other, other0)
 
 
+@pytest.mark.parametrize("uplo", "LU")
+def test_multigpu_potrf_pinned_host_overlapped_gather(mgpu, uplo):
+    """Page-locked host matrices take the path that streams finished block columns back while the
+    factorisation is still running (lower); the result must be the same."""
+    n = 1500
+    A = H.spd_matrix("d", n, k=64)
+    want = A.copy(order="F")
+    assert ORA.potrf("d", uplo, want) == 0
+    hp = torch.empty(n, n, dtype=torch.float64, pin_memory=True)  # (n, lda) row-major == column-major A
+    hp.copy_(torch.from_numpy(np.ascontiguousarray(A.T)))
+    assert mgpu.potrf("d", uplo, n, hp.data_ptr(), n) == 0
+    got = hp.numpy().T
+    assert np.abs(H.tri(got, uplo) - H.tri(want, uplo)).max() <= 64 * n * H.eps("d") * np.abs(want).max()
+    other = np.triu(got, 1) if uplo == "L" else np.tril(got, -1)
+    other0 = np.triu(A, 1) if uplo == "L" else np.tril(A, -1)
+    assert np.array_equal(other, other0)
+
+
 def test_multigpu_potrf_info_and_args(mgpu):
     G.chol.set_xerbla_silent()
     n = 900
