@@ -577,7 +577,7 @@ static int launch_t(const chol_gemm_desc *d) {
     attr_set[dev & 63][CPLX][tma] = true;
   }
   // tuning switches (environment, read once):
-  //   CHOL_GEMM_PP=1        use the staggered two-group kernel when the grid has >= 4 tiles per SM (default 0)
+  //   CHOL_GEMM_PP=0/1      staggered two-group kernel for grids with >= 4 tiles per SM (default: z only)
   //   CHOL_GEMM_PERSIST=n   classic kernel as n persistent CTAs per SM (default 0: one CTA per tile - the
   //                         hardware's dynamic CTA placement beats a static persistent walk)
   //   CHOL_GEMM_PREFETCH=0  disable the L2 prefetch of C
@@ -587,14 +587,14 @@ static int launch_t(const chol_gemm_desc *d) {
     const char *e1 = getenv("CHOL_GEMM_PERSIST"), *e2 = getenv("CHOL_GEMM_PREFETCH"), *e3 = getenv("CHOL_GEMM_PP");
     persist = e1 ? atoi(e1) : 0;
     prefetch = e2 ? atoi(e2) : 1;
-    pingpong = e3 ? atoi(e3) : 0;  // measured: within +-2 % of the classic schedule on big grids, worse on small ones
+    pingpong = e3 ? atoi(e3) : -1;  // auto: z yes (+9 % on zpotrf: short main loops), d no (within +-2 %, worse on small grids)
     const char *e4 = getenv("CHOL_GEMM_TPS");
     if (e4 && atoi(e4) > 0) tps = atoi(e4);
   }
   a.prefetch_c = prefetch;
   if (tiles > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
   const int sms = sm_count[dev & 63];
-  if (pingpong && tiles >= 4LL * sms && a.K > 0) {  // (K = 0: no stages to pace the groups with)
+  if ((pingpong < 0 ? CPLX : pingpong != 0) && tiles >= 4LL * sms && a.K > 0) {  // (K = 0: no stages to pace the groups with)
     a.tps = tps;
     kern_pp<<<(unsigned)((tiles + 2 * tps - 1) / (2 * tps)), Cfg::PP_THREADS, Cfg::PP_SMEM_BYTES, st>>>(a);
   } else {

@@ -7,7 +7,7 @@
 // so the s/c tolerance is the plain FP32 one.
 //   * CTA tile 128x128 (s) / 64x64 (c), BK = 8, 256 threads, 8x8 (s) / 4x4-complex (c) register
 //     tile per thread, operands in shared memory as [k][m] / [k][n], 128-bit shared loads;
-//   * global -> register -> shared double buffering, one __syncthreads per k-tile;
+//   * 4-stage cp.async (LDGSTS) pipeline straight into shared memory, one __syncthreads per k-tile;
 //   * any transpose / conjugate / triangular mask handled by the loader, k-ranges that are
 //     structurally zero are skipped, triangular (cuplo) grids launch only the needed tiles.
 #include <cuda_runtime.h>
@@ -28,7 +28,6 @@ struct FCfg {
   static constexpr int BK = 8;
   static constexpr int LDS = BM + VW;  // padded pitch (elements); keeps 16-byte alignment
   static constexpr int THREADS = 256;
-  static constexpr int LPT = BM * BK / THREADS;  // loads per thread per operand tile
 };
 
 template <typename T>
@@ -39,15 +38,75 @@ struct FArgs {
   int M, N, K;
   T alpha, beta;
   int opA, opB, triA, triB, unitA, unitB, cuplo, herm, NI, NJ, vec_ok, beta_zero;
+  int vecA, vecB;            // 16-byte cp.async along the stored rows is legal
+  int conjA_regs, conjB_regs;  // complex: conjugate fragments in registers (fast path copies raw data)
   ColMap cm;
 };
 
+// true if the stored-triangle mask cannot touch the tile rows [r0, r0+rows) x k [k0, k0+bk)
+__device__ __forceinline__ bool f_tri_clear(int tri, bool along_rows, int r0, int rows, int k0, int bk) {
+  if (!tri) return true;
+  const int row_min = along_rows ? r0 : k0, row_max = along_rows ? r0 + rows - 1 : k0 + bk - 1;
+  const int col_min = along_rows ? k0 : r0, col_max = along_rows ? k0 + bk - 1 : r0 + rows - 1;
+  return tri == 1 ? (row_min > col_max) : (row_max < col_min);
+}
+template <int BYTES>
+__device__ __forceinline__ void f_cp_async(void *dst, const void *src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  if constexpr (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(src), "n"(BYTES) : "memory");
+}
+
+// One ROWS x BK operand tile -> shared [k][row] (pitch LDS).  Interior, unmasked tiles go through
+// cp.async (16-byte vectors along the stored rows when aligned, element-wise otherwise); edge and
+// diagonal-crossing tiles take the per-element path with masks.  256 threads cooperate.
+template <typename T, int ROWS, int BK, int LDS>
+__device__ __forceinline__ void f_fill(T *dst, const T *__restrict__ src, long long ld, int op, int tri, int unit, bool is_b,
+                                       int r0, int rlimit, int rows_valid, int k0, int ke, bool vec16, int tid) {
+  // logical element (row r0+rr, k0+kk); stored coordinates: A: op==0 -> (row, k) else (k, row); B: op!=0 -> (row, k) else (k, row)
+  const bool along_rows = is_b ? (op != 0) : (op == 0);
+  const bool conj = false;  // conjugation is applied to the register fragments (conjA_regs / conjB_regs)
+  const bool fast = (rows_valid == ROWS) && (k0 + BK <= ke) && f_tri_clear(tri, along_rows, r0, ROWS, k0, BK);
+  constexpr int VW = 16 / sizeof(T);
+  if (fast) {
+    if (along_rows) {
+      if (vec16) {
+        for (int v = tid; v < ROWS / VW * BK; v += 256) {
+          const int rv = v % (ROWS / VW), kk = v / (ROWS / VW);
+          f_cp_async<16>(dst + kk * LDS + rv * VW, src + (long long)(k0 + kk) * ld + r0 + rv * VW);
+        }
+      } else {
+        for (int e = tid; e < ROWS * BK; e += 256) {
+          const int rr = e % ROWS, kk = e / ROWS;
+          f_cp_async<sizeof(T)>(dst + kk * LDS + rr, src + (long long)(k0 + kk) * ld + r0 + rr);
+        }
+      }
+    } else {
+      for (int e = tid; e < ROWS * BK; e += 256) {
+        const int kk = e % BK, rr = e / BK;
+        f_cp_async<sizeof(T)>(dst + kk * LDS + rr, src + (long long)(r0 + rr) * ld + k0 + kk);
+      }
+    }
+    return;
+  }
+  for (int e = tid; e < ROWS * BK; e += 256) {
+    int rr, kk;
+    if (along_rows) { rr = e % ROWS; kk = e / ROWS; } else { kk = e % BK; rr = e / BK; }
+    const long long r = r0 + rr, k = k0 + kk;
+    const bool in = (rr < rows_valid) && (k < ke);
+    (void)rlimit;
+    dst[kk * LDS + rr] = along_rows ? fetch_stored<T>(src, ld, in, r, k, tri, unit, conj)
+                                    : fetch_stored<T>(src, ld, in, k, r, tri, unit, conj);
+  }
+}
+
 template <typename T>
-__global__ void __launch_bounds__(256, 2) gemm_ffma_kernel(const FArgs<T> p) {
+__global__ void __launch_bounds__(256, 2) gemm_ffma_kernel(const __grid_constant__ FArgs<T> p) {
   using Cfg = FCfg<T>;
-  constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, LDS = Cfg::LDS, VW = Cfg::VW, TM = Cfg::TM, TN = Cfg::TN, LPT = Cfg::LPT;
-  __shared__ __align__(16) T As[2][BK * LDS];
-  __shared__ __align__(16) T Bs[2][BK * LDS];
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, LDS = Cfg::LDS, VW = Cfg::VW, TM = Cfg::TM, TN = Cfg::TN;
+  constexpr int ST = 4;  // cp.async stages
+  __shared__ __align__(16) T As[ST][BK * LDS];
+  __shared__ __align__(16) T Bs[ST][BK * LDS];
 
   int bi, bj;
   if (!tile_coords<BM, BN, 8>(p.cuplo, p.NI, p.NJ, p.cm, (long long)blockIdx.x, bi, bj)) return;
@@ -66,52 +125,29 @@ __global__ void __launch_bounds__(256, 2) gemm_ffma_kernel(const FArgs<T> p) {
   const int nk = ke > kb ? (ke - kb + BK - 1) / BK : 0;
 
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int rowsA = min(BM, p.M - m0), rowsB = min(BN, p.N - n0);
   T acc[TM][TN];
 #pragma unroll
   for (int i = 0; i < TM; ++i)
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = zero_of<T>();
 
-  T ra[LPT], rb[LPT];
-  auto gload = [&](int k0) {
-#pragma unroll
-    for (int u = 0; u < LPT; ++u) {
-      const int idx = u * 256 + tid;
-      int mm, kk;
-      if (p.opA == 0) { mm = idx % BM; kk = idx / BM; } else { kk = idx % BK; mm = idx / BK; }
-      const long long m = m0 + mm, k = k0 + kk;
-      const bool in = (m < p.M) && (k < ke);
-      ra[u] = (p.opA == 0) ? fetch_stored<T>(p.A, p.lda, in, m, k, p.triA, p.unitA, false)
-                           : fetch_stored<T>(p.A, p.lda, in, k, m, p.triA, p.unitA, p.opA == 2);
-      int nn, kk2;
-      if (p.opB != 0) { nn = idx % BN; kk2 = idx / BN; } else { kk2 = idx % BK; nn = idx / BK; }
-      const long long n = g0 + nn, k2 = k0 + kk2;
-      const bool inb = (n0 + nn < p.N) && (k2 < ke);
-      rb[u] = (p.opB == 0) ? fetch_stored<T>(p.B, p.ldb, inb, k2, n, p.triB, p.unitB, false)
-                           : fetch_stored<T>(p.B, p.ldb, inb, n, k2, p.triB, p.unitB, p.opB == 2);
+  auto issue = [&](int kt) {
+    if (kt < nk) {
+      const int s = kt % ST, k0 = kb + kt * BK;
+      f_fill<T, BM, BK, LDS>(As[s], p.A, p.lda, p.opA, p.triA, p.unitA, false, m0, p.M, rowsA, k0, ke, p.vecA, tid);
+      f_fill<T, BN, BK, LDS>(Bs[s], p.B, p.ldb, p.opB, p.triB, p.unitB, true, g0, p.N, rowsB, k0, ke, p.vecB, tid);
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  auto sstore = [&](int buf) {
 #pragma unroll
-    for (int u = 0; u < LPT; ++u) {
-      const int idx = u * 256 + tid;
-      int mm, kk;
-      if (p.opA == 0) { mm = idx % BM; kk = idx / BM; } else { kk = idx % BK; mm = idx / BK; }
-      As[buf][kk * LDS + mm] = ra[u];
-      int nn, kk2;
-      if (p.opB != 0) { nn = idx % BN; kk2 = idx / BN; } else { kk2 = idx % BK; nn = idx / BK; }
-      Bs[buf][kk2 * LDS + nn] = rb[u];
-    }
-  };
+  for (int kt = 0; kt < ST - 1; ++kt) issue(kt);
 
-  if (nk > 0) {
-    gload(kb);
-    sstore(0);
-  }
-  __syncthreads();
   for (int kt = 0; kt < nk; ++kt) {
-    const int cur = kt & 1;
-    if (kt + 1 < nk) gload(kb + (kt + 1) * BK);
+    asm volatile("cp.async.wait_group %0;" ::"n"(ST - 2) : "memory");
+    __syncthreads();          // stage kt has landed for everyone; stage kt-1 is no longer being read
+    issue(kt + ST - 1);       // refill the slot that stage kt-1 used
+    const int cur = kt % ST;
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       T a[TM], b[TN];
@@ -127,13 +163,21 @@ __global__ void __launch_bounds__(256, 2) gemm_ffma_kernel(const FArgs<T> p) {
           b[h * 4] = vb.x; b[h * 4 + 1] = vb.y; b[h * 4 + 2] = vb.z; b[h * 4 + 3] = vb.w;
         }
       }
+      if constexpr (Cfg::CPLX) {  // conjugation of raw cp.async copies happens here
+        if (p.conjA_regs) {
+#pragma unroll
+          for (int i = 0; i < TM; ++i) a[i].y = -a[i].y;
+        }
+        if (p.conjB_regs) {
+#pragma unroll
+          for (int j = 0; j < TN; ++j) b[j].y = -b[j].y;
+        }
+      }
 #pragma unroll
       for (int i = 0; i < TM; ++i)
 #pragma unroll
         for (int j = 0; j < TN; ++j) fma_acc(acc[i][j], a[i], b[j]);
     }
-    if (kt + 1 < nk) sstore(cur ^ 1);
-    __syncthreads();
   }
 
   // epilogue: thread owns rows m0 + h*(BM/2) + tx*VW + v, columns n0 + h2*(BN/2) + ty*VW + w
@@ -178,6 +222,10 @@ static int launch_f(const chol_gemm_desc *d) {
   a.NI = (a.M + Cfg::BM - 1) / Cfg::BM;
   a.NJ = (a.N + Cfg::BN - 1) / Cfg::BN;
   a.vec_ok = 0;
+  a.vecA = (((uintptr_t)d->A & 15) == 0) && (d->lda % Cfg::VW == 0);
+  a.vecB = (((uintptr_t)d->B & 15) == 0) && (d->ldb % Cfg::VW == 0);
+  a.conjA_regs = Cfg::CPLX && d->opA == 'C';
+  a.conjB_regs = Cfg::CPLX && d->opB == 'C';
   a.cm.cnb = d->cyc_nb; a.cm.cP = d->cyc_p; a.cm.coff = d->cyc_off;
   if (a.cm.cnb && (a.cm.cnb % Cfg::BN || a.cuplo == 2 || d->triA || d->triB || a.cm.cP < 1)) return (int)cudaErrorInvalidValue;
   const long long tiles = total_tiles<Cfg::BM, Cfg::BN, 8>(a.cuplo, a.NI, a.NJ, a.cm);

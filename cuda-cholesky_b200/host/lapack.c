@@ -31,9 +31,10 @@ static const double MONE[2] = {-1.0, 0.0};
 /* outer block size: k of the trailing update.  Larger k amortises the C-tile epilogue (measured on
  * B200, d: 512 beats 256 from N ~ 32768 up), smaller k shortens the serial panel chain. */
 size_t chol_default_nb(int prec, size_t n) {
-  if (prec == 'z') return 128;
-  if (prec == 'd') return n >= 24576 ? 512 : 256;
-  return 256;
+  /* measured on B200 (scripts/nb_sweep.py, profiles/r01_first_light.md) */
+  if (prec == 'z') return n >= 8192 ? 256 : 128;
+  if (prec == 'd') return n >= 49152 ? 1024 : (n >= 12288 ? 512 : 256);
+  return n >= 16384 ? 512 : 256;
 }
 
 CUresult chol_carve(CULAPACKhandle h, int prec, size_t n, chol_ws *w) {
