@@ -146,6 +146,21 @@ def cpu_reference_lib():
     return H.CpuLib("oracle"), "port", H
 
 
+def use_all_host_cores():
+    """The CPU reference is OpenMP code; torchrun exports OMP_NUM_THREADS=1, so set the thread count
+    explicitly to every core this process may run on.  Returns the count used."""
+    import ctypes
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    try:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(ctypes.c_int(cores))
+    except OSError:
+        cores = int(os.environ.get("OMP_NUM_THREADS", "1"))
+    return cores
+
+
 def cpu_spd(n, k=KGEN):
     import numpy as np
     rng = np.random.default_rng(SEED)
@@ -176,7 +191,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    cores = use_all_host_cores()
     n_s = args.ref_n
     sec, kind, resid = time_cpu_dpotrf(n_s, args.steps, args.warmup)
     gf = n_s ** 3 / 3.0 / sec / 1e9
@@ -343,7 +358,7 @@ def run_ours(args):
     # ---- the reference's CPU path on this box's host cores (bounded sample) ----
     cpu = None
     if P == 1 and not args.no_cpu_baseline:
-        cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+        cores = use_all_host_cores()
         sec, kind, _ = time_cpu_dpotrf(args.cpu_n, 1, 0)
         cpu = {"value": args.cpu_n ** 3 / 3.0 / sec / 1e9, "unit": "GFLOP/s", "cores": cores, "kind": kind,
                "sample": "reference CPU dpotrf (lower) of a %dx%d SPD matrix of the same family, one run, %.1f s"

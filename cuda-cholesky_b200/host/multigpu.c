@@ -342,11 +342,14 @@ static CUresult gemm_cyc(int prec, int herm, size_t m, size_t n, size_t k, CUdev
  * n rows, leading dimension ldl.  Factor in place (lower).  *info = local failure (global column,
  * 1-based) or 0. */
 /* block size of the distributed layout: with P ranks the per-rank update shrinks by P while the
- * serial panel chain does not, so the smaller block wins (measured on 8 B200: 256 beats 512) */
+ * serial panel chain does not, so fewer columns per rank want a smaller block (measured at
+ * N = 65536 on B200: P = 2, 4 -> 512 beats 256 by 5-7 %; P = 8 -> 256 beats 512 by 5 %) */
 static size_t dist_nb(const chol_rank *R, int prec, size_t n) {
   if (R->lap->nb) return R->lap->nb;
   const size_t nb = chol_default_nb(prec, n);
-  return (R->nranks > 1 && nb > 256) ? 256 : nb;
+  if (R->nranks <= 1) return nb;
+  const size_t cap = (n / (size_t)R->nranks >= 16384) ? 512 : 256;
+  return nb > cap ? cap : nb;
 }
 
 static CUresult dist_carve(chol_rank *R, int prec, size_t n, chol_ws *w) {
