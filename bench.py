@@ -348,7 +348,12 @@ def run_ours(args):
     achieved_tf = (upd_flops / (upd_ms * 1e-3) / 1e12) if upd_ms > 0 else None
     roofline = {"bound": "tensor", "kernel": "chol::gemm_dmma_kernel<false,0> (trailing update A22 -= W*W^T)",
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved_tf / peak_tf) if achieved_tf else None,
-                "traffic": None, "launches": upd_launches, "ms_total": upd_ms,
+                # DRAM bytes of ONE launch of this kernel from the committed ncu --set full capture
+                # (profiles/r01_ncu_dmma_trailing_update.md: SYRK lower 32768^2 x 1024): 6.58 GB read + 4.33 GB written for
+                # 4.29 + 4.29 GB of C (one triangle in, one out) + 0.27 GB of panel = 8.86 GB algorithmic
+                "traffic": 1.0906e10, "traffic_launch": "lower SYRK n=32768 k=1024 (ncu capture, not this run)",
+                "algorithmic_bytes_of_that_launch": 8.858e9, "ncu_tensor_pipe_active_pct": 93.5,
+                "launches": upd_launches, "ms_total": upd_ms,
                 "share_of_step": upd_ms / ms_total if ms_total else None,
                 "peak_source": "FP64 DMMA (mma.sync.m8n8k4.f64) peak measured in this run by chol_probe_fp64; "
                                "MEASURED_PEAKS.json has no FP64 entry (bf16 %.0f TF/s, HBM %.0f GB/s)"

@@ -50,7 +50,7 @@ struct GemmCfg {
   static constexpr int B_STAGE = BK * LDB;
   static constexpr int ESZ = CPLX ? 16 : 8;
   static constexpr int R = BM / BN;  // tile aspect, used by the triangular scheduler
-  static constexpr int GROUP = 8;    // row-blocks per super-row
+  static constexpr int GROUP = 16;   // row-blocks per super-row: 2048 rows of A stay L2-resident while B streams by once
   static constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * ESZ + 2 * STAGES * 8;
   static constexpr int PP_THREADS = 384;  // staggered kernel: 2 consumer groups x 4 warps + 2 x 2 producer warps
   static constexpr int PP_SMEM_BYTES = 2 * STAGES * (A_STAGE + B_STAGE) * ESZ + (4 * STAGES + 2) * 8;
@@ -580,13 +580,13 @@ static int launch_t(const chol_gemm_desc *d) {
   //   CHOL_GEMM_PP=0/1      staggered two-group kernel for grids with >= 4 tiles per SM (default: z only)
   //   CHOL_GEMM_PERSIST=n   classic kernel as n persistent CTAs per SM (default 0: one CTA per tile - the
   //                         hardware's dynamic CTA placement beats a static persistent walk)
-  //   CHOL_GEMM_PREFETCH=0  disable the L2 prefetch of C
+  //   CHOL_GEMM_PREFETCH=1  enable the L2 prefetch of C tiles (default off)
   //   CHOL_GEMM_TPS=n       staggered kernel: tiles per group and CTA (default 8)
   static int persist = -1, prefetch = -1, pingpong = -1, tps = 8;
   if (persist < 0) {
     const char *e1 = getenv("CHOL_GEMM_PERSIST"), *e2 = getenv("CHOL_GEMM_PREFETCH"), *e3 = getenv("CHOL_GEMM_PP");
     persist = e1 ? atoi(e1) : 0;
-    prefetch = e2 ? atoi(e2) : 1;
+    prefetch = e2 ? atoi(e2) : 0;  // ncu: the prefetch costs +50 % DRAM reads (lines evicted before use) for +0.4 % speed
     pingpong = e3 ? atoi(e3) : -1;  // auto: z yes (+9 % on zpotrf: short main loops), d no (within +-2 %, worse on small grids)
     const char *e4 = getenv("CHOL_GEMM_TPS");
     if (e4 && atoi(e4) > 0) tps = atoi(e4);

@@ -78,7 +78,7 @@ def test_multigpu_argument_errors_without_gpu():
 
 
 @pytest.mark.parametrize("cuplo", ["", "L", "U"])
-@pytest.mark.parametrize("m,n", [(1, 1), (128, 64), (129, 65), (1000, 1000), (3000, 700), (700, 3000), (4096, 4096)])
+@pytest.mark.parametrize("m,n", [(1, 1), (128, 64), (129, 65), (1000, 1000), (3000, 700), (700, 3000), (4096, 4096), (16384, 16384)])
 def test_tile_schedule_covers_needed_tiles_once(cuplo, m, n):
     BM, BN = 128, 64
     grid, tiles = chol.tile_schedule(cuplo, m, n)
@@ -94,8 +94,8 @@ def test_tile_schedule_covers_needed_tiles_once(cuplo, m, n):
             want.add((bi, bj))
     assert set(tiles) == want
     assert grid >= len(tiles)
-    if m >= 4096 and cuplo:
-        assert grid <= 1.25 * len(tiles)  # the triangular grid wastes little (-> 0 as n grows)
+    if m >= 16384 and cuplo:
+        assert grid <= 1.15 * len(tiles)  # the triangular grid wastes little (-> 0 as n grows)
 
 
 @pytest.mark.parametrize("P", [2, 4, 8])
