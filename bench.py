@@ -199,8 +199,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": gf, "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "dpotrf lower N=%d (configs[1]-[4] family; metric N)" % args.n, "N": args.n, "uplo": "L",
-                       "sample_N": n_s, "resid": resid},
+            "config": {"workload": "dpotrf lower N=%d, FP64 DMMA trailing update (BASELINE configs[1]/[4] family at the metric's N)" % args.n,
+                       "N": args.n, "uplo": "L", "sample_N": n_s, "sample_resid": resid,
+                       "note": "CPU reference (lapack/dpotrf.c + blas/*.c, compiled unmodified) timed on a bounded sample per step"},
             "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
