@@ -51,7 +51,7 @@ struct GemmCfg {
   static constexpr int ESZ = CPLX ? 16 : 8;
   static constexpr int R = BM / BN;  // tile aspect, used by the triangular scheduler
   static constexpr int GROUP = 16;   // row-blocks per super-row: 2048 rows of A stay L2-resident while B streams by once
-  static constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * ESZ + 2 * STAGES * 8;
+  static constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * ESZ + 3 * STAGES * 8;  // + full, empty, cbar
   static constexpr int PP_THREADS = 384;  // staggered kernel: 2 consumer groups x 4 warps + 2 x 2 producer warps
   static constexpr int PP_SMEM_BYTES = 2 * STAGES * (A_STAGE + B_STAGE) * ESZ + (4 * STAGES + 2) * 8;
   static constexpr int THREADS = 192;  // 4 consumer warps + 2 producer warps (register file is allocated in warp pairs)
@@ -78,6 +78,7 @@ struct GemmArgs {
   long long total_tiles;  // size of the tile sequence the persistent CTAs walk
   int prefetch_c;         // pull the C tile towards L2 when the producer starts a tile
   int tps;                // staggered kernel: tiles per consumer group and CTA
+  int stage_c;            // classic kernel, d: TMA the C tile into the drained stage ring for the epilogue
   SchedTable tb;          // super-row prefix table for the tile decode
   int vecA, vecB;         // generic loader may use 16-byte copies along the stored rows of A / B
   ColMap cm;         // block-cyclic column map of D's columns (cnb = 0: identity)
@@ -153,11 +154,23 @@ __device__ __forceinline__ bool tri_clear(int tri, bool along_rows, int r0, int 
   return tri == 1 ? (row_min > col_max) : (row_max < col_min);  // strictly off the diagonal: no unit-diagonal either
 }
 
+// The epilogue of an interior d tile can read C from shared memory: when the main loop drains, the
+// producer TMA-copies the 128 x 64 C tile in four 16-column chunks into the A regions of the four
+// stages (a chunk has exactly the shape of an A stage: 16 rows of 128 doubles, pitch 132), so the
+// HBM latency of C overlaps the last k-iterations instead of stalling both co-resident CTAs.
+template <bool CPLX>
+__device__ __forceinline__ bool c_staged(const GemmArgs<CPLX> &p, int m0, int n0, int g0) {
+  using Cfg = GemmCfg<CPLX>;
+  if (CPLX || !p.stage_c || p.beta_zero || !p.vec_ok) return false;
+  if (m0 + Cfg::BM > p.M || n0 + Cfg::BN > p.N) return false;
+  return p.cuplo == 0 || (p.cuplo == 1 && m0 >= g0 + Cfg::BN - 1) || (p.cuplo == 2 && m0 + Cfg::BM - 1 <= g0);
+}
+
 // One tile's worth of producer work: fill the group's stage ring (TMA bulk rows or cp.async gather).
 template <bool CPLX, int MODE, int NPW>
 __device__ __forceinline__ void produce_tile(const GemmArgs<CPLX> &p, int bi, int bj, typename GemmArgs<CPLX>::T *As,
                                              typename GemmArgs<CPLX>::T *Bs, uint64_t *full, uint64_t *empty, uint32_t &it,
-                                             int pw, int lane) {
+                                             uint64_t *cbar, int pw, int lane) {
   using Cfg = GemmCfg<CPLX>;
   using T = typename GemmArgs<CPLX>::T;
   constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, LDA = Cfg::LDA, LDB = Cfg::LDB, ST = Cfg::STAGES;
@@ -225,13 +238,26 @@ __device__ __forceinline__ void produce_tile(const GemmArgs<CPLX> &p, int bi, in
       mbar_arrive(&full[s]);
     }
   }
+  if constexpr (!CPLX) {
+    if (cbar != nullptr && pw == 0 && c_staged<CPLX>(p, m0, n0, g0)) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {  // chunk j = tile columns 16j .. 16j+15 -> A region of stage (it + j) % ST
+        const int s = (it + j) % ST;
+        mbar_wait(&empty[s], (((it + j) / ST) & 1) ^ 1);  // the consumers are done with that stage
+        if (lane == 0) mbar_arrive_expect_tx(&cbar[j], 16u * BM * 8u);
+        __syncwarp();
+        if (lane < 16)
+          tma_bulk_g2s(As + s * Cfg::A_STAGE + lane * LDA, p.C + (long long)(n0 + 16 * j + lane) * p.ldc + m0, BM * 8, &cbar[j]);
+      }
+    }
+  }
 }
 
 // One tile's worth of consumer work for a group of 4 warps: DMMA main loop + epilogue.
 template <bool CPLX, int MODE>
 __device__ __forceinline__ void consume_tile(const GemmArgs<CPLX> &p, int bi, int bj, const typename GemmArgs<CPLX>::T *As,
                                              const typename GemmArgs<CPLX>::T *Bs, uint64_t *full, uint64_t *empty, uint32_t &it,
-                                             uint64_t *mid, int warp, int lane) {
+                                             uint64_t *mid, uint64_t *cbar, int warp, int lane) {
   using Cfg = GemmCfg<CPLX>;
   constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, LDA = Cfg::LDA, LDB = Cfg::LDB, ST = Cfg::STAGES;
   const int g = lane >> 2, t4 = lane & 3;
@@ -283,7 +309,30 @@ __device__ __forceinline__ void consume_tile(const GemmArgs<CPLX> &p, int bi, in
     const double alpha = p.alpha, beta = p.beta;
     const bool interior = (m0 + BM <= p.M) && (n0 + BN <= p.N) &&
                           (p.cuplo == 0 || (p.cuplo == 1 && m0 >= g0 + BN - 1) || (p.cuplo == 2 && m0 + BM - 1 <= g0));
-    if (interior && p.vec_ok) {
+    if (cbar != nullptr && c_staged<CPLX>(p, m0, n0, g0)) {
+      // C comes from shared memory: chunk (wn*2 + (j>>1)) sits in the A region of stage (it + chunk) % ST
+#pragma unroll
+      for (int jh = 0; jh < 2; ++jh) {
+        const int chunk = wn * 2 + jh;
+        mbar_wait(&cbar[chunk], 0);
+        const double *cs = As + ((it + chunk) % ST) * Cfg::A_STAGE;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int ml = wm * 64 + 16 * q + 2 * g;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = jh * 2 + (e >> 1), c = e & 1;
+            const int nl16 = 2 * (2 * t4 + c) + (j & 1);  // column inside the 16-column chunk
+            const double2 cv = *reinterpret_cast<const double2 *>(cs + nl16 * LDA + ml);
+            const long long n = n0 + wn * 32 + 16 * jh + nl16;
+            double2 o;
+            o.x = alpha * acc[2 * q][j][c] + beta * cv.x;
+            o.y = alpha * acc[2 * q + 1][j][c] + beta * cv.y;
+            *reinterpret_cast<double2 *>(p.D + n * p.ldd + (m0 + ml)) = o;
+          }
+        }
+      }
+    } else if (interior && p.vec_ok) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const long long m = m0 + wm * 64 + 16 * q + 2 * g;
@@ -418,19 +467,23 @@ __global__ void __launch_bounds__(GemmCfg<CPLX>::THREADS, 2) gemm_dmma_kernel(co
   T *Bs = As + ST * Cfg::A_STAGE;
   uint64_t *full = reinterpret_cast<uint64_t *>(Bs + ST * Cfg::B_STAGE);
   uint64_t *empty = full + ST;
+  uint64_t *cbar = empty + ST;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     init_ring<CPLX, MODE, 2>(full, empty);
+    for (int j = 0; j < ST; ++j) mbar_init(&cbar[j], 1);
     mbar_fence_init();
   }
+  // C staging reuses the stage ring after the main loop: only when this CTA owns exactly one tile
+  uint64_t *cb = (gridDim.x >= p.total_tiles) ? cbar : nullptr;
   __syncthreads();
   uint32_t it = 0;  // k-stages consumed so far: the ring keeps rolling across tiles
   if (MODE == 0 && warp == 5) return;
   for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
     int bi, bj;
     if (!tile_coords_tb<BM, BN, Cfg::GROUP>(p.tb, p.cuplo, p.NI, p.NJ, p.cm, t, bi, bj)) continue;
-    if (warp >= 4) produce_tile<CPLX, MODE, 2>(p, bi, bj, As, Bs, full, empty, it, warp - 4, lane);
-    else consume_tile<CPLX, MODE>(p, bi, bj, As, Bs, full, empty, it, nullptr, warp, lane);
+    if (warp >= 4) produce_tile<CPLX, MODE, 2>(p, bi, bj, As, Bs, full, empty, it, cb, warp - 4, lane);
+    else consume_tile<CPLX, MODE>(p, bi, bj, As, Bs, full, empty, it, nullptr, cb, warp, lane);
   }
 }
 
@@ -484,7 +537,7 @@ __global__ void __launch_bounds__(GemmCfg<CPLX>::PP_THREADS, 1) gemm_dmma_pp_ker
       // stagger: group 0 waits for group 1's half-way mark of tile i-1, group 1 for group 0's of tile i
       if (gq == 0) { if (i >= 1) mbar_wait(&mid[1], (i - 1) & 1); }
       else mbar_wait(&mid[0], i & 1);
-      if (valid) produce_tile<CPLX, MODE, 2>(p, bi, bj, As, Bs, full, empty, it, warp & 1, lane);
+      if (valid) produce_tile<CPLX, MODE, 2>(p, bi, bj, As, Bs, full, empty, it, nullptr, warp & 1, lane);
       else if (lane == 0) mbar_arrive_n(&mid[gq], MODE == 0 ? 4 : 2);
       // (an empty slot passes its mark on behalf of the 4 consumer warps, but only after the gate
       //  above and - generic path - only once BOTH producer warps are through it: nobody can ever
@@ -500,7 +553,7 @@ __global__ void __launch_bounds__(GemmCfg<CPLX>::PP_THREADS, 1) gemm_dmma_pp_ker
       const long long t = tbase + gq + 2 * i;
       int bi, bj;
       const bool valid = t < p.total_tiles && tile_coords_tb<BM, BN, Cfg::GROUP>(p.tb, p.cuplo, p.NI, p.NJ, p.cm, t, bi, bj);
-      if (valid) consume_tile<CPLX, MODE>(p, bi, bj, As, Bs, full, empty, it, &mid[gq], warp & 3, lane);
+      if (valid) consume_tile<CPLX, MODE>(p, bi, bj, As, Bs, full, empty, it, &mid[gq], nullptr, warp & 3, lane);
     }
   }
 }
@@ -582,16 +635,20 @@ static int launch_t(const chol_gemm_desc *d) {
   //                         hardware's dynamic CTA placement beats a static persistent walk)
   //   CHOL_GEMM_PREFETCH=1  enable the L2 prefetch of C tiles (default off)
   //   CHOL_GEMM_TPS=n       staggered kernel: tiles per group and CTA (default 8)
-  static int persist = -1, prefetch = -1, pingpong = -1, tps = 8;
+  //   CHOL_GEMM_STAGEC=0    classic kernel: read C from global memory in the epilogue instead of TMA-staging it
+  static int persist = -1, prefetch = -1, pingpong = -1, tps = 8, stagec = 1;
   if (persist < 0) {
     const char *e1 = getenv("CHOL_GEMM_PERSIST"), *e2 = getenv("CHOL_GEMM_PREFETCH"), *e3 = getenv("CHOL_GEMM_PP");
     persist = e1 ? atoi(e1) : 0;
     prefetch = e2 ? atoi(e2) : 0;  // ncu: the prefetch costs +50 % DRAM reads (lines evicted before use) for +0.4 % speed
     pingpong = e3 ? atoi(e3) : -1;  // auto: z yes (+9 % on zpotrf: short main loops), d no (within +-2 %, worse on small grids)
+    const char *e5 = getenv("CHOL_GEMM_STAGEC");
+    if (e5) stagec = atoi(e5);
     const char *e4 = getenv("CHOL_GEMM_TPS");
     if (e4 && atoi(e4) > 0) tps = atoi(e4);
   }
   a.prefetch_c = prefetch;
+  a.stage_c = stagec;
   if (tiles > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
   const int sms = sm_count[dev & 63];
   if ((pingpong < 0 ? CPLX : pingpong != 0) && tiles >= 4LL * sms && a.K > 0) {  // (K = 0: no stages to pace the groups with)

@@ -12,7 +12,7 @@ chol = load()
 torch.zeros(1, device="cuda")
 g = torch.Generator(device="cuda").manual_seed(1)
 blas = chol.BlasHandle()
-tag = "pp=%s tps=%s" % (os.environ.get("CHOL_GEMM_PP", "1"), os.environ.get("CHOL_GEMM_TPS", "4"))
+tag = "pp=%s stagec=%s" % (os.environ.get("CHOL_GEMM_PP", "auto"), os.environ.get("CHOL_GEMM_STAGEC", "1"))
 for (n, k) in ((16384, 256), (32768, 256), (49152, 256), (32768, 512)):
     A = torch.rand(k, n, dtype=torch.float64, device="cuda", generator=g) - 0.5
     Cm = torch.zeros(n, n, dtype=torch.float64, device="cuda")
