@@ -35,8 +35,8 @@ __host__ __device__ inline int cols_upto(const ColMap &cm, long long m_max) {
   else cnt += tpb;
   return cnt;
 }
-template <int BM, int BN, int GROUP>
-__host__ __device__ inline int sr_ncols(int cuplo, int NJ, const ColMap &cm, int s) {
+template <int BM, int BN>
+__host__ __device__ inline int sr_ncols(int GROUP, int cuplo, int NJ, const ColMap &cm, int s) {
   if (cuplo == 1) {
     const int c = cols_upto<BN>(cm, (long long)GROUP * (s + 1) * BM - 1);
     return c < NJ ? c : NJ;
@@ -47,21 +47,21 @@ __host__ __device__ inline int sr_ncols(int cuplo, int NJ, const ColMap &cm, int
   }
   return NJ;
 }
-template <int BM, int BN, int GROUP>
-__host__ inline long long total_tiles(int cuplo, int NI, int NJ, const ColMap &cm) {
+template <int BM, int BN>
+__host__ inline long long total_tiles(int GROUP, int cuplo, int NI, int NJ, const ColMap &cm) {
   long long t = 0;
-  for (int s = 0; s * GROUP < NI; ++s) t += (long long)GROUP * sr_ncols<BM, BN, GROUP>(cuplo, NJ, cm, s);
+  for (int s = 0; s * GROUP < NI; ++s) t += (long long)GROUP * sr_ncols<BM, BN>(GROUP, cuplo, NJ, cm, s);
   return t;
 }
-template <int BM, int BN, int GROUP>
-__host__ __device__ inline bool tile_coords(int cuplo, int NI, int NJ, const ColMap &cm, long long t, int &bi, int &bj) {
+template <int BM, int BN>
+__host__ __device__ inline bool tile_coords(int GROUP, int cuplo, int NI, int NJ, const ColMap &cm, long long t, int &bi, int &bj) {
   int s = 0;
   if (cuplo == 0) {
     s = (int)(t / ((long long)GROUP * NJ));
     t -= (long long)s * GROUP * NJ;
   } else {
     for (;;) {
-      long long c = (long long)GROUP * sr_ncols<BM, BN, GROUP>(cuplo, NJ, cm, s);
+      long long c = (long long)GROUP * sr_ncols<BM, BN>(GROUP, cuplo, NJ, cm, s);
       if (t < c) break;
       t -= c;
       ++s;
@@ -76,6 +76,9 @@ __host__ __device__ inline bool tile_coords(int cuplo, int NI, int NJ, const Col
   return true;
 }
 
+// (GROUP = row-blocks per super-row is a run-time choice of the launcher: 16 keeps 2048 rows of A in L2
+// while B streams by once - fewer DRAM re-reads on big grids; short, wide problems use 8 so that a
+// super-row is not mostly empty.)
 // Host-built prefix table of the super-row tile counts (passed in the kernel arguments): the CTA's
 // tile decode becomes a short scan over warp-uniform constants instead of a chain of divisions.
 constexpr int SCHED_MAX_SR = 160;
@@ -83,24 +86,24 @@ struct SchedTable {
   int nsr;                      // number of super-rows; 0 = table not usable, decode arithmetically
   int start[SCHED_MAX_SR + 1];  // first tile id of super-row s; start[nsr] = grid size
 };
-template <int BM, int BN, int GROUP>
-__host__ inline void build_sched_table(SchedTable &tb, int cuplo, int NI, int NJ, const ColMap &cm) {
+template <int BM, int BN>
+__host__ inline void build_sched_table(SchedTable &tb, int GROUP, int cuplo, int NI, int NJ, const ColMap &cm) {
   const int nsr = (NI + GROUP - 1) / GROUP;
   tb.nsr = 0;
   if (nsr > SCHED_MAX_SR) return;
   long long t = 0;
   for (int s = 0; s < nsr; ++s) {
     tb.start[s] = (int)t;
-    t += (long long)GROUP * sr_ncols<BM, BN, GROUP>(cuplo, NJ, cm, s);
+    t += (long long)GROUP * sr_ncols<BM, BN>(GROUP, cuplo, NJ, cm, s);
     if (t > 0x7fffffffLL) return;
   }
   tb.start[nsr] = (int)t;
   tb.nsr = nsr;
 }
-template <int BM, int BN, int GROUP>
-__device__ __forceinline__ bool tile_coords_tb(const SchedTable &tb, int cuplo, int NI, int NJ, const ColMap &cm,
+template <int BM, int BN>
+__device__ __forceinline__ bool tile_coords_tb(const SchedTable &tb, int GROUP, int cuplo, int NI, int NJ, const ColMap &cm,
                                                long long t, int &bi, int &bj) {
-  if (tb.nsr == 0) return tile_coords<BM, BN, GROUP>(cuplo, NI, NJ, cm, t, bi, bj);
+  if (tb.nsr == 0) return tile_coords<BM, BN>(GROUP, cuplo, NI, NJ, cm, t, bi, bj);
   const int ti = (int)t;
   int s = 0;
   // start[] is increasing: scan in strides of 8, then by 1 (at most ~28 uniform constant loads)

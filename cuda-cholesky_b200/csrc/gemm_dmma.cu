@@ -80,6 +80,7 @@ struct GemmArgs {
   int tps;                // staggered kernel: tiles per consumer group and CTA
   int stage_c;            // classic kernel, d: TMA the C tile into the drained stage ring for the epilogue
   SchedTable tb;          // super-row prefix table for the tile decode
+  int group;              // row-blocks per super-row (8 or 16)
   int vecA, vecB;         // generic loader may use 16-byte copies along the stored rows of A / B
   ColMap cm;         // block-cyclic column map of D's columns (cnb = 0: identity)
 };
@@ -481,7 +482,7 @@ __global__ void __launch_bounds__(GemmCfg<CPLX>::THREADS, 2) gemm_dmma_kernel(co
   if (MODE == 0 && warp == 5) return;
   for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
     int bi, bj;
-    if (!tile_coords_tb<BM, BN, Cfg::GROUP>(p.tb, p.cuplo, p.NI, p.NJ, p.cm, t, bi, bj)) continue;
+    if (!tile_coords_tb<BM, BN>(p.tb, p.group, p.cuplo, p.NI, p.NJ, p.cm, t, bi, bj)) continue;
     if (warp >= 4) produce_tile<CPLX, MODE, 2>(p, bi, bj, As, Bs, full, empty, it, cb, warp - 4, lane);
     else consume_tile<CPLX, MODE>(p, bi, bj, As, Bs, full, empty, it, nullptr, cb, warp, lane);
   }
@@ -533,7 +534,7 @@ __global__ void __launch_bounds__(GemmCfg<CPLX>::PP_THREADS, 1) gemm_dmma_pp_ker
     for (int i = 0; i < imax; ++i) {
       const long long t = tbase + gq + 2 * i;
       int bi, bj;
-      const bool valid = t < p.total_tiles && tile_coords_tb<BM, BN, Cfg::GROUP>(p.tb, p.cuplo, p.NI, p.NJ, p.cm, t, bi, bj);
+      const bool valid = t < p.total_tiles && tile_coords_tb<BM, BN>(p.tb, p.group, p.cuplo, p.NI, p.NJ, p.cm, t, bi, bj);
       // stagger: group 0 waits for group 1's half-way mark of tile i-1, group 1 for group 0's of tile i
       if (gq == 0) { if (i >= 1) mbar_wait(&mid[1], (i - 1) & 1); }
       else mbar_wait(&mid[0], i & 1);
@@ -552,7 +553,7 @@ __global__ void __launch_bounds__(GemmCfg<CPLX>::PP_THREADS, 1) gemm_dmma_pp_ker
     for (int i = 0; i < imax; ++i) {
       const long long t = tbase + gq + 2 * i;
       int bi, bj;
-      const bool valid = t < p.total_tiles && tile_coords_tb<BM, BN, Cfg::GROUP>(p.tb, p.cuplo, p.NI, p.NJ, p.cm, t, bi, bj);
+      const bool valid = t < p.total_tiles && tile_coords_tb<BM, BN>(p.tb, p.group, p.cuplo, p.NI, p.NJ, p.cm, t, bi, bj);
       if (valid) consume_tile<CPLX, MODE>(p, bi, bj, As, Bs, full, empty, it, &mid[gq], nullptr, warp & 3, lane);
     }
   }
@@ -611,10 +612,11 @@ static int launch_t(const chol_gemm_desc *d) {
   a.cm.cnb = d->cyc_nb; a.cm.cP = d->cyc_p; a.cm.coff = d->cyc_off;
   if (a.cm.cnb && (a.cm.cnb % Cfg::BN || a.cuplo == 2 || d->triA || d->triB || a.cm.cP < 1)) return (int)cudaErrorInvalidValue;
   const bool tma = !alpha_zero && tma_eligible<CPLX>(d);
-  const long long tiles = total_tiles<Cfg::BM, Cfg::BN, Cfg::GROUP>(a.cuplo, a.NI, a.NJ, a.cm);
+  a.group = (a.NI >= 2 * Cfg::GROUP && a.NJ >= 2 * Cfg::GROUP) ? Cfg::GROUP : 8;  // big in both dimensions
+  const long long tiles = total_tiles<Cfg::BM, Cfg::BN>(a.group, a.cuplo, a.NI, a.NJ, a.cm);
   if (tiles <= 0) return 0;
   a.total_tiles = tiles;
-  build_sched_table<Cfg::BM, Cfg::BN, Cfg::GROUP>(a.tb, a.cuplo, a.NI, a.NJ, a.cm);
+  build_sched_table<Cfg::BM, Cfg::BN>(a.tb, a.group, a.cuplo, a.NI, a.NJ, a.cm);
   cudaStream_t st = (cudaStream_t)d->stream;
   static bool attr_set[64][2][2];  // per device
   static int sm_count[64];
@@ -686,11 +688,12 @@ extern "C" long long chol_test_tile_schedule(int cuplo, int m, int n, int cyc_nb
   chol::ColMap cm{cyc_nb, cyc_p, cyc_off};
   const int cu = chol::tri_code(cuplo);
   const int NI = (m + Cfg::BM - 1) / Cfg::BM, NJ = (n + Cfg::BN - 1) / Cfg::BN;
-  const long long tiles = chol::total_tiles<Cfg::BM, Cfg::BN, Cfg::GROUP>(cu, NI, NJ, cm);
+  const int grp = (NI >= 2 * Cfg::GROUP && NJ >= 2 * Cfg::GROUP) ? Cfg::GROUP : 8;
+  const long long tiles = chol::total_tiles<Cfg::BM, Cfg::BN>(grp, cu, NI, NJ, cm);
   long long v = 0;
   for (long long t = 0; t < tiles; ++t) {
     int bi, bj;
-    if (chol::tile_coords<Cfg::BM, Cfg::BN, Cfg::GROUP>(cu, NI, NJ, cm, t, bi, bj)) {
+    if (chol::tile_coords<Cfg::BM, Cfg::BN>(grp, cu, NI, NJ, cm, t, bi, bj)) {
       if (v < cap) { out[2 * v] = bi; out[2 * v + 1] = bj; }
       ++v;
     }

@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(256, 2) gemm_ffma_kernel(const __grid_constant
   __shared__ __align__(16) T Bs[ST][BK * LDS];
 
   int bi, bj;
-  if (!tile_coords<BM, BN, 8>(p.cuplo, p.NI, p.NJ, p.cm, (long long)blockIdx.x, bi, bj)) return;
+  if (!tile_coords<BM, BN>(8, p.cuplo, p.NI, p.NJ, p.cm, (long long)blockIdx.x, bi, bj)) return;
   const int m0 = bi * BM, n0 = bj * BN;
   const int g0 = (int)gcol(p.cm, n0);
   int kb = 0, ke = p.K;
@@ -228,7 +228,7 @@ static int launch_f(const chol_gemm_desc *d) {
   a.conjB_regs = Cfg::CPLX && d->opB == 'C';
   a.cm.cnb = d->cyc_nb; a.cm.cP = d->cyc_p; a.cm.coff = d->cyc_off;
   if (a.cm.cnb && (a.cm.cnb % Cfg::BN || a.cuplo == 2 || d->triA || d->triB || a.cm.cP < 1)) return (int)cudaErrorInvalidValue;
-  const long long tiles = total_tiles<Cfg::BM, Cfg::BN, 8>(a.cuplo, a.NI, a.NJ, a.cm);
+  const long long tiles = total_tiles<Cfg::BM, Cfg::BN>(8, a.cuplo, a.NI, a.NJ, a.cm);
   if (tiles <= 0) return 0;
   if (tiles > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
   gemm_ffma_kernel<T><<<(unsigned)tiles, 256, 0, (cudaStream_t)d->stream>>>(a);
