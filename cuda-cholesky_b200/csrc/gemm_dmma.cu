@@ -10,21 +10,29 @@
 //   * math: mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4, the native FP64 tensor-core op on sm_100a);
 //     z uses 4 real DMMAs per complex MAC on split (re, im) accumulators.
 //   * CTA tile 128x64 (d) / 64x64 (z), 4 consumer warps (2x2), warp tile 64x32 (d) / 32x32 (z),
-//     accumulators in registers (64 doubles/thread); 2 CTAs per SM so that one CTA's C-tile
-//     epilogue (HBM latency bound) overlaps the other's DMMA main loop.
+//     accumulators in registers (64 doubles/thread); 2 CTAs per SM.
 //   * operands staged in shared memory as [k][m] / [k][n] rows with a +4 (d) / +2 (z) element pad:
 //     conflict-free for the 128-bit fragment loads of the DMMA lane layout.
 //   * 4-stage mbarrier ring, warp-specialised: warps 4-5 are producers (MODE 0 needs only warp 4).
 //       MODE 0 (hot path: op(A)=N, op(B)=T/C, aligned): every k-row of the A/B tile is one TMA
 //              bulk copy (cp.async.bulk, SASS UBLKCP) issued by one lane, completion counted as
 //              transaction bytes on the stage's mbarrier;
-//       MODE 1 (any transpose / conjugate / triangular mask / odd alignment): the producer warp
-//              gathers elements through registers into the same shared layout.
+//       MODE 1 (any transpose / conjugate / triangular mask / odd alignment): the producer warps
+//              gather with cp.async (LDGSTS) straight into the same shared layout; only tiles
+//              that cross a triangular operand's diagonal or the matrix edge take a per-element
+//              path with masks; conjugation is applied to the register fragments.
+//   * epilogue (d, interior tiles): when the main loop drains, the producer TMA-copies the CTA's C
+//     tile into the freed stages, so C is read from shared memory instead of stalling on HBM.
 //   * triangular tile scheduler: for cuplo the grid holds only tiles that touch the triangle
 //     (the reference launches the full square and lets half the blocks return, blas/dsyrk.cu:68-75);
-//     tiles are enumerated in 8-row-block super-rows so that concurrently resident CTAs share the
-//     same B rows and an L2-resident set of A rows.
+//     tiles are enumerated in super-rows of 8 or 16 row-blocks so that concurrently resident CTAs
+//     share the same B rows and an L2-resident set of A rows; the decode is a scan of a host-built
+//     prefix table carried in the kernel arguments.
 //   * triangular operands skip the k-range that is structurally zero.
+//   * a block-cyclic column map (ColMap) lets one launch update all the block columns a rank owns
+//     in the multi-GPU factorisation.
+//   * two schedules: the classic one (one tile per CTA, the hardware places CTAs) and a staggered
+//     one (gemm_dmma_pp_kernel below); which is used when is measured, see the launcher.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
