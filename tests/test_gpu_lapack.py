@@ -203,3 +203,19 @@ def test_dpotrf_large_properties(lapack, uplo):
     ld = lapack.logdet("d", F.data_ptr(), n + 1, n)
     want = 2 * torch.log(torch.diagonal(F)).sum().item()
     assert abs(ld - want) <= 1e-12 * abs(want)
+
+
+@pytest.mark.parametrize("p,n", [("d", 4096), ("z", 2048), ("s", 4096)])
+@pytest.mark.parametrize("uplo", "LU")
+def test_potrf_full_elementwise_vs_oracle_mid_size(lapack, p, uplo, n):
+    """SURVEY.md section 8d, config 2 style: the WHOLE factor against the CPU oracle (which is pinned to the
+    reference's dpotrf), elementwise max|L - L_ref| <= 64 n eps max|L_ref|, at a size where several
+    outer blocks, the look-ahead and the triangular-grid update kernel are all in play."""
+    A = H.spd_matrix(p, n, k=256)
+    want = A.copy(order="F")
+    assert ORA.potrf(p, uplo, want) == 0
+    dA, lda = G.to_dev(A)
+    assert lapack.potrf(p, uplo, n, dA.data_ptr(), lda) == 0
+    got = G.to_host(dA, n)
+    err = np.abs(H.tri(got, uplo) - H.tri(want, uplo)).max() / np.abs(want).max()
+    assert err <= elem_tol(p, n), err
