@@ -1,6 +1,6 @@
 /*
- * chol_kernels.h — the thin C-ABI between the C host code (cuda-cholesky_b200/host/*.c) and the
- * hand-written sm_100a kernels (cuda-cholesky_b200/csrc/*.cu).  Plain C: pointers, sizes and
+ * chol_kernels.h — the thin C-ABI between the C host code (the .c files under ../host) and the
+ * hand-written sm_100a kernels (the .cu files in this directory).  Plain C: pointers, sizes and
  * chars only.  Every launcher is asynchronous on `stream` (a CUstream / cudaStream_t) and
  * returns a cudaError_t value as int (0 = success).
  *

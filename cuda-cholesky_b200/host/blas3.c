@@ -73,14 +73,9 @@ CUresult chol_trmm2(int prec, int side, int uplo, int trans, int diag, size_t m,
                       ldx, stream);
 }
 
-CUresult chol_trsm(CUBLAShandle h, int prec, int side, int uplo, int trans, int diag, size_t m, size_t n,
-                   const double alpha[2], CUdeviceptr A, size_t lda, CUdeviceptr B, size_t ldb, CUstream stream) {
-  if (m == 0 || n == 0) return CUDA_SUCCESS;
+static CUresult trsm_body(CUBLAShandle h, int prec, int side, int uplo, int trans, int diag, size_t m, size_t n,
+                          const double alpha[2], CUdeviceptr A, size_t lda, CUdeviceptr B, size_t ldb, CUstream stream) {
   const size_t es = chol_esize(prec);
-  if (alpha[0] == 0.0 && alpha[1] == 0.0) {
-    RT_CHECK(chol_fill_launch(prec, 0, m, n, 0.0, 0.0, (void *)B, ldb, (void *)stream));
-    return CUDA_SUCCESS;
-  }
   const size_t tb = (size_t)chol_diag_max(prec);
   const size_t na = (side == 'L') ? m : n;
   const bool eff_lower = (uplo == 'L') == (trans == 'N'); /* shape of T = op(A) */
@@ -126,6 +121,19 @@ CUresult chol_trsm(CUBLAShandle h, int prec, int side, int uplo, int trans, int 
   return CUDA_SUCCESS;
 }
 
+CUresult chol_trsm(CUBLAShandle h, int prec, int side, int uplo, int trans, int diag, size_t m, size_t n,
+                   const double alpha[2], CUdeviceptr A, size_t lda, CUdeviceptr B, size_t ldb, CUstream stream) {
+  if (m == 0 || n == 0) return CUDA_SUCCESS;
+  if (alpha[0] == 0.0 && alpha[1] == 0.0) {
+    RT_CHECK(chol_fill_launch(prec, 0, m, n, 0.0, 0.0, (void *)B, ldb, (void *)stream));
+    return CUDA_SUCCESS;
+  }
+  CU_ERROR_CHECK(chol_blas_scratch_acquire(h, stream));
+  const CUresult e = trsm_body(h, prec, side, uplo, trans, diag, m, n, alpha, A, lda, B, ldb, stream);
+  CU_ERROR_CHECK(chol_blas_scratch_release(h, stream)); /* also after a failure: whatever was queued may use the scratch */
+  return e;
+}
+
 static CUresult chol_trmm_inplace(CUBLAShandle h, int prec, int side, int uplo, int trans, int diag, size_t m, size_t n,
                                   const double alpha[2], CUdeviceptr A, size_t lda, CUdeviceptr B, size_t ldb,
                                   CUstream stream) {
@@ -133,9 +141,11 @@ static CUresult chol_trmm_inplace(CUBLAShandle h, int prec, int side, int uplo, 
   if (m == 0 || n == 0) return CUDA_SUCCESS;
   const size_t es = chol_esize(prec), ldx = chol_roundup(m, 2);
   CUdeviceptr X;
+  CU_ERROR_CHECK(chol_blas_scratch_acquire(h, stream));
   CU_ERROR_CHECK(chol_blas_scratch(h, ldx * n * es, &X));
   CU_ERROR_CHECK(chol_trmm2(prec, side, uplo, trans, diag, m, n, alpha, A, lda, B, ldb, X, ldx, stream));
   RT_CHECK(chol_copy_launch(prec, 'N', 0, m, n, (const void *)X, ldx, (void *)B, ldb, (void *)stream));
+  CU_ERROR_CHECK(chol_blas_scratch_release(h, stream));
   return CUDA_SUCCESS;
 }
 
@@ -150,11 +160,24 @@ static CUresult chol_trmm_inplace(CUBLAShandle h, int prec, int side, int uplo, 
     }                                       \
   } while (false)
 
+/* run `call` inside the handle's context, as the reference launchers do (blas/dgemm.c:173-197);
+ * gemm2 / syrk|herk / trmm2 keep no per-handle state and also accept a NULL handle (caller's context) */
+#define IN_BLAS_CONTEXT(handle, call)                          \
+  do {                                                         \
+    if ((handle) == NULL) return (call);                       \
+    CU_ERROR_CHECK(cuCtxPushCurrent((handle)->context));       \
+    const CUresult body__ = (call);                            \
+    CUcontext popped__;                                        \
+    const CUresult pop__ = cuCtxPopCurrent(&popped__);         \
+    if (body__ != CUDA_SUCCESS) return body__;                 \
+    CU_ERROR_CHECK(pop__);                                     \
+    return CUDA_SUCCESS;                                       \
+  } while (false)
+
 #define GEN_BLAS3(U, p, SCALAR, REAL, RE, IM, RANKK, ISCPLX)                                                          \
   CUresult cu##U##gemm2(CUBLAShandle handle, CBlasTranspose transA, CBlasTranspose transB, size_t m, size_t n,         \
                         size_t k, SCALAR alpha, CUdeviceptr A, size_t lda, CUdeviceptr B, size_t ldb, SCALAR beta,     \
                         CUdeviceptr C, size_t ldc, CUdeviceptr D, size_t ldd, CUstream stream) {                       \
-    (void)handle;                                                                                                      \
     const size_t nRowA = (transA == CBlasNoTrans) ? m : k, nRowB = (transB == CBlasNoTrans) ? k : n;                   \
     CHECK_ARG(lda < nRowA, 8);                                                                                         \
     CHECK_ARG(ldb < nRowB, 10);                                                                                        \
@@ -163,29 +186,27 @@ static CUresult chol_trmm_inplace(CUBLAShandle h, int prec, int side, int uplo, 
     const double a[2] = {RE(alpha), IM(alpha)}, b[2] = {RE(beta), IM(beta)};                                           \
     if (m == 0 || n == 0 || (C == D && ((a[0] == 0.0 && a[1] == 0.0) || k == 0) && b[0] == 1.0 && b[1] == 0.0))        \
       return CUDA_SUCCESS;                                                                                             \
-    return chol_gemm(p, transA, transB, m, n, k, a, A, lda, B, ldb, b, C, ldc, D, ldd, stream);                        \
+    IN_BLAS_CONTEXT(handle, chol_gemm(p, transA, transB, m, n, k, a, A, lda, B, ldb, b, C, ldc, D, ldd, stream));      \
   }                                                                                                                    \
   CUresult cu##U##RANKK(CUBLAShandle handle, CBlasUplo uplo, CBlasTranspose trans, size_t n, size_t k, REAL alpha,     \
                         CUdeviceptr A, size_t lda, REAL beta, CUdeviceptr C, size_t ldc, CUstream stream) {            \
-    (void)handle;                                                                                                      \
     const size_t nRowA = (trans == CBlasNoTrans) ? n : k;                                                              \
     CHECK_ARG(ISCPLX && trans == CBlasTrans, 2);                                                                       \
     CHECK_ARG(lda < nRowA, 7);                                                                                         \
     CHECK_ARG(ldc < n, 10);                                                                                            \
     if (n == 0 || ((alpha == 0 || k == 0) && beta == 1)) return CUDA_SUCCESS;                                          \
-    return chol_rankk(p, uplo, trans, n, k, (double)alpha, A, lda, (double)beta, C, ldc, stream);                      \
+    IN_BLAS_CONTEXT(handle, chol_rankk(p, uplo, trans, n, k, (double)alpha, A, lda, (double)beta, C, ldc, stream));    \
   }                                                                                                                    \
   CUresult cu##U##trmm2(CUBLAShandle handle, CBlasSide side, CBlasUplo uplo, CBlasTranspose trans, CBlasDiag diag,     \
                         size_t m, size_t n, SCALAR alpha, CUdeviceptr A, size_t lda, CUdeviceptr B, size_t ldb,        \
                         CUdeviceptr X, size_t ldx, CUstream stream) {                                                  \
-    (void)handle;                                                                                                      \
     const size_t nRowA = (side == CBlasLeft) ? m : n;                                                                  \
     CHECK_ARG(lda < nRowA, 9);                                                                                         \
     CHECK_ARG(ldb < m, 11);                                                                                            \
     CHECK_ARG(ldx < m, 13);                                                                                            \
     if (m == 0 || n == 0) return CUDA_SUCCESS;                                                                         \
     const double a[2] = {RE(alpha), IM(alpha)};                                                                        \
-    return chol_trmm2(p, side, uplo, trans, diag, m, n, a, A, lda, B, ldb, X, ldx, stream);                            \
+    IN_BLAS_CONTEXT(handle, chol_trmm2(p, side, uplo, trans, diag, m, n, a, A, lda, B, ldb, X, ldx, stream));          \
   }                                                                                                                    \
   CUresult cu##U##trmm(CUBLAShandle handle, CBlasSide side, CBlasUplo uplo, CBlasTranspose trans, CBlasDiag diag,      \
                        size_t m, size_t n, SCALAR alpha, CUdeviceptr A, size_t lda, CUdeviceptr B, size_t ldb,         \
@@ -193,8 +214,9 @@ static CUresult chol_trmm_inplace(CUBLAShandle h, int prec, int side, int uplo, 
     const size_t nRowA = (side == CBlasLeft) ? m : n;                                                                  \
     CHECK_ARG(lda < nRowA, 9);                                                                                         \
     CHECK_ARG(ldb < m, 11);                                                                                            \
+    if (handle == NULL) return CUDA_ERROR_INVALID_VALUE; /* needs the handle's scratch */                              \
     const double a[2] = {RE(alpha), IM(alpha)};                                                                        \
-    return chol_trmm_inplace(handle, p, side, uplo, trans, diag, m, n, a, A, lda, B, ldb, stream);                     \
+    IN_BLAS_CONTEXT(handle, chol_trmm_inplace(handle, p, side, uplo, trans, diag, m, n, a, A, lda, B, ldb, stream));   \
   }                                                                                                                    \
   CUresult cu##U##trsm(CUBLAShandle handle, CBlasSide side, CBlasUplo uplo, CBlasTranspose trans, CBlasDiag diag,      \
                        size_t m, size_t n, SCALAR alpha, CUdeviceptr A, size_t lda, CUdeviceptr B, size_t ldb,         \
@@ -202,8 +224,9 @@ static CUresult chol_trmm_inplace(CUBLAShandle h, int prec, int side, int uplo, 
     const size_t nRowA = (side == CBlasLeft) ? m : n;                                                                  \
     CHECK_ARG(lda < nRowA, 9);                                                                                         \
     CHECK_ARG(ldb < m, 11);                                                                                            \
+    if (handle == NULL) return CUDA_ERROR_INVALID_VALUE; /* needs the handle's scratch */                              \
     const double a[2] = {RE(alpha), IM(alpha)};                                                                        \
-    return chol_trsm(handle, p, side, uplo, trans, diag, m, n, a, A, lda, B, ldb, stream);                             \
+    IN_BLAS_CONTEXT(handle, chol_trsm(handle, p, side, uplo, trans, diag, m, n, a, A, lda, B, ldb, stream));           \
   }
 
 #define RE_R(x) ((double)(x))

@@ -13,6 +13,7 @@
 #include "blas.h"
 #include "lapack.h"
 #include "error.h"
+#include "cholesky_b200.h"
 #include "../csrc/chol_kernels.h"
 
 /* reference blas/handle.h:4-11 keeps a context and 16 lazily loaded CUmodules; kernels here are
@@ -24,6 +25,11 @@ struct __cublashandle_st {
   CUdeviceptr scratch;   /* TRSM/TRMM temporaries */
   size_t scratch_bytes;
   CUdeviceptr dinfo;     /* device long, sink for the diagonal-inverse kernels used by TRSM */
+  /* scratch and dinfo are shared by every TRSM/TRMM call on this handle: calls on different
+   * streams are ordered against each other through this event (same stream: stream order) */
+  CUevent scratch_done;
+  CUstream scratch_stream;
+  bool scratch_in_use;
 };
 
 #define CHOL_EVENT_RING 4
@@ -74,6 +80,9 @@ CUresult chol_rt_error(int cuda_rt_error, const char *call, const char *func, co
   } while (false)
 
 CUresult chol_blas_scratch(CUBLAShandle h, size_t bytes, CUdeviceptr *out);
+/* bracket a call that uses the handle's scratch on `stream` */
+CUresult chol_blas_scratch_acquire(CUBLAShandle h, CUstream stream);
+CUresult chol_blas_scratch_release(CUBLAShandle h, CUstream stream);
 CUresult chol_lapack_workspace(CULAPACKhandle h, size_t bytes, CUdeviceptr *out);
 
 /* ---- precision-generic BLAS-3 cores (blas3.c).  alpha/beta as (re, im) ---- */
@@ -104,6 +113,7 @@ typedef struct chol_ws {
 
 size_t chol_default_nb(int prec, size_t n);
 CUresult chol_carve(CULAPACKhandle h, int prec, size_t n, chol_ws *w);
+CUresult chol_carve_nb(CULAPACKhandle h, int prec, size_t n, size_t nb, chol_ws *w);
 /* Cholesky of a jb x jb (jb <= nb) diagonal block / out-of-place inverse of one (other triangle zero) */
 CUresult chol_potrf_diag(int prec, int uplo, size_t jb, CUdeviceptr A, size_t lda, long *dinfo, long base,
                          const chol_ws *w, CUstream st);

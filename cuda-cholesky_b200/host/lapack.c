@@ -38,8 +38,13 @@ size_t chol_default_nb(int prec, size_t n) {
 }
 
 CUresult chol_carve(CULAPACKhandle h, int prec, size_t n, chol_ws *w) {
+  return chol_carve_nb(h, prec, n, h->nb ? h->nb : chol_default_nb(prec, n), w);
+}
+
+/* carve the handle's cached workspace for an n x n problem blocked by nb */
+CUresult chol_carve_nb(CULAPACKhandle h, int prec, size_t n, size_t nb, chol_ws *w) {
   w->es = chol_esize(prec);
-  w->nb = h->nb ? h->nb : chol_default_nb(prec, n);
+  w->nb = nb;
   w->db = (size_t)chol_diag_max(prec);
   if (w->nb < w->db) w->db = w->nb;
   w->ldw = chol_roundup(n > w->nb ? n : w->nb, 16);
@@ -172,9 +177,8 @@ CUresult chol_diag_factor_inverse(int prec, int uplo, size_t jb, CUdeviceptr A, 
 }
 
 /* ------------------------------------------------------------------------------------------ */
-CUresult chol_potrf(CULAPACKhandle h, int prec, int uplo, size_t n, CUdeviceptr A, size_t lda, long *info) {
+static CUresult potrf_body(CULAPACKhandle h, int prec, int uplo, size_t n, CUdeviceptr A, size_t lda, long *info) {
   chol_ws w;
-  CU_ERROR_CHECK(cuCtxPushCurrent(h->context));
   CU_ERROR_CHECK(chol_carve(h, prec, n, &w));
   const size_t es = w.es, nb = w.nb;
   const int herm = chol_is_complex(prec);
@@ -247,15 +251,12 @@ CUresult chol_potrf(CULAPACKhandle h, int prec, int uplo, size_t n, CUdeviceptr 
     }
   }
   h->prof_n = 0;
-  CUcontext dummy;
-  CU_ERROR_CHECK(cuCtxPopCurrent(&dummy));
   return CUDA_SUCCESS;
 }
 
 /* ------------------------------------------------------------------------------------------ */
-CUresult chol_trtri(CULAPACKhandle h, int prec, int uplo, int diag, size_t n, CUdeviceptr A, size_t lda, long *info) {
+static CUresult trtri_body(CULAPACKhandle h, int prec, int uplo, int diag, size_t n, CUdeviceptr A, size_t lda, long *info) {
   chol_ws w;
-  CU_ERROR_CHECK(cuCtxPushCurrent(h->context));
   CU_ERROR_CHECK(chol_carve(h, prec, n, &w));
   const size_t es = w.es, nb = w.nb;
   long *dinfo = (long *)h->dinfo;
@@ -287,22 +288,17 @@ CUresult chol_trtri(CULAPACKhandle h, int prec, int uplo, int diag, size_t n, CU
     RT_CHECK(chol_copy_launch(prec, 'N', unit ? strict : uplo, jb, jb, (const void *)w.Xd, nb, (void *)Ajj, lda, (void *)st));
   }
   CU_ERROR_CHECK(finish_info(h, st, info));
-  CUcontext dummy;
-  CU_ERROR_CHECK(cuCtxPopCurrent(&dummy));
   return CUDA_SUCCESS;
 }
 
 /* ------------------------------------------------------------------------------------------ */
-CUresult chol_lauum(CULAPACKhandle h, int prec, int uplo, size_t n, CUdeviceptr A, size_t lda, long *info) {
+static CUresult lauum_body(CULAPACKhandle h, int prec, int uplo, size_t n, CUdeviceptr A, size_t lda, long *info) {
   chol_ws w;
-  CU_ERROR_CHECK(cuCtxPushCurrent(h->context));
   /* LAUUM's GEMMs are ib x i with k = n-i: few, fat tiles; a taller block row keeps all SMs busy
    * (measured d, N = 32768: nb 256 / 512 / 1024 -> 15.6 / 22.2 / 28.8 TFLOP/s) */
-  const size_t saved_nb = h->nb;
-  if (!saved_nb && (prec == 'd' || prec == 's') && n >= 16384) h->nb = 1024;
-  const CUresult ce = chol_carve(h, prec, n, &w);
-  h->nb = saved_nb;
-  CU_ERROR_CHECK(ce);
+  size_t lnb = h->nb ? h->nb : chol_default_nb(prec, n);
+  if (!h->nb && (prec == 'd' || prec == 's') && n >= 16384) lnb = 1024;
+  CU_ERROR_CHECK(chol_carve_nb(h, prec, n, lnb, &w));
   const size_t es = w.es, nb = w.nb;
   const int herm = chol_is_complex(prec);
   CUstream st = h->s_update;
@@ -331,9 +327,30 @@ CUresult chol_lauum(CULAPACKhandle h, int prec, int uplo, size_t n, CUdeviceptr 
     RT_CHECK(chol_copy_launch(prec, 'N', uplo, ib, ib, (const void *)w.Xd, nb, (void *)Aii, lda, (void *)st));
   }
   CU_ERROR_CHECK(cuStreamSynchronize(st));
-  CUcontext dummy;
-  CU_ERROR_CHECK(cuCtxPopCurrent(&dummy));
   return CUDA_SUCCESS;
+}
+
+/* The drivers run inside the handle's context (the reference pushes it per call, lapack/dpotrf.c:181);
+ * the pop happens on every path, so a failing call leaves the caller's context stack as it found it. */
+#define IN_HANDLE_CONTEXT(h, call)                   \
+  do {                                               \
+    CU_ERROR_CHECK(cuCtxPushCurrent((h)->context));  \
+    const CUresult body__ = (call);                  \
+    CUcontext popped__;                              \
+    const CUresult pop__ = cuCtxPopCurrent(&popped__); \
+    if (body__ != CUDA_SUCCESS) return body__; /* already reported where it happened */ \
+    CU_ERROR_CHECK(pop__);                           \
+    return CUDA_SUCCESS;                             \
+  } while (false)
+
+CUresult chol_potrf(CULAPACKhandle h, int prec, int uplo, size_t n, CUdeviceptr A, size_t lda, long *info) {
+  IN_HANDLE_CONTEXT(h, potrf_body(h, prec, uplo, n, A, lda, info));
+}
+CUresult chol_trtri(CULAPACKhandle h, int prec, int uplo, int diag, size_t n, CUdeviceptr A, size_t lda, long *info) {
+  IN_HANDLE_CONTEXT(h, trtri_body(h, prec, uplo, diag, n, A, lda, info));
+}
+CUresult chol_lauum(CULAPACKhandle h, int prec, int uplo, size_t n, CUdeviceptr A, size_t lda, long *info) {
+  IN_HANDLE_CONTEXT(h, lauum_body(h, prec, uplo, n, A, lda, info));
 }
 
 CUresult chol_potri(CULAPACKhandle h, int prec, int uplo, size_t n, CUdeviceptr A, size_t lda, long *info) {
@@ -342,15 +359,15 @@ CUresult chol_potri(CULAPACKhandle h, int prec, int uplo, size_t n, CUdeviceptr 
   return chol_lauum(h, prec, uplo, n, A, lda, info);
 }
 
-CUresult chol_logdet(CULAPACKhandle h, int prec, CUdeviceptr x, size_t incx, size_t n, void *result, CUstream stream) {
+static CUresult logdet_body(CULAPACKhandle h, int prec, CUdeviceptr x, size_t incx, size_t n, void *result, CUstream stream) {
   const size_t rs = (prec == 's' || prec == 'c') ? 4 : 8;
-  CU_ERROR_CHECK(cuCtxPushCurrent(h->context));
   const CUdeviceptr dres = h->logdet_scr + (CUdeviceptr)chol_roundup(chol_logdet_scratch_bytes(), 16);
   RT_CHECK(chol_logdet_launch(prec, (const void *)x, incx, n, (void *)dres, (void *)h->logdet_scr, (void *)stream));
   CU_ERROR_CHECK(cuMemcpyDtoHAsync(result, dres, rs, stream));
-  CUcontext dummy;
-  CU_ERROR_CHECK(cuCtxPopCurrent(&dummy));
   return CUDA_SUCCESS;
+}
+CUresult chol_logdet(CULAPACKhandle h, int prec, CUdeviceptr x, size_t incx, size_t n, void *result, CUstream stream) {
+  IN_HANDLE_CONTEXT(h, logdet_body(h, prec, x, incx, n, result, stream));
 }
 
 /* ---------------------------------------------------------------------------------------------

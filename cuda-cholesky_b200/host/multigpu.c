@@ -150,6 +150,8 @@ CUresult cuTaskCreate(CUtask *task, CUresult (*function)(const void *), const vo
   return CUDA_SUCCESS;
 }
 
+/* Once `complete` is visible the owner may already be inside cuTaskDestroy: the task is not
+ * touched after the unlock. */
 CUresult cuTaskExecute(CUtask t) {
   if (t == NULL) return CUDA_ERROR_INVALID_VALUE;
   const CUresult r = t->function(t->args);
@@ -211,8 +213,16 @@ static void *worker_main(void *arg) {
     const bool stop = (t == NULL) && w->stop;
     pthread_mutex_unlock(&w->mutex);
     if (stop) break;
-    cuTaskExecute(t);
-    if (t->result != CUDA_SUCCESS && w->error == CUDA_SUCCESS) w->error = t->result;
+    /* latch the first failure BEFORE completion is published: whoever waits for a later task on
+     * this worker (cuMultiGPUSynchronize) then reads it through that task's mutex */
+    struct __cutask_st *const task = t;
+    const CUresult r = task->function(task->args);
+    if (r != CUDA_SUCCESS && w->error == CUDA_SUCCESS) w->error = r;
+    pthread_mutex_lock(&task->mutex);
+    task->result = r;
+    task->complete = true;
+    pthread_cond_broadcast(&task->cond);
+    pthread_mutex_unlock(&task->mutex); /* `task` may be freed by its owner from here on */
   }
   return NULL;
 }
@@ -236,10 +246,15 @@ CUresult cuMultiGPUCreate(CUmultiGPU *mGPU, CUdevice *devices, int n) {
     if (e == CUDA_SUCCESS) {
       pthread_mutex_init(&w->mutex, NULL);
       pthread_cond_init(&w->cond, NULL);
-      if (pthread_create(&w->thread, NULL, worker_main, w) != 0) e = CUDA_ERROR_OPERATING_SYSTEM;
+      if (pthread_create(&w->thread, NULL, worker_main, w) != 0) {
+        e = CUDA_ERROR_OPERATING_SYSTEM;
+        pthread_mutex_destroy(&w->mutex);
+        pthread_cond_destroy(&w->cond);
+        cuDevicePrimaryCtxRelease(w->device);
+      }
     }
     if (e != CUDA_SUCCESS) {
-      m->n = i;
+      m->n = i; /* workers 0..i-1 are running: tear those down */
       cuMultiGPUDestroy(m);
       CU_ERROR_CHECK(e);
     }
@@ -353,11 +368,7 @@ static size_t dist_nb(const chol_rank *R, int prec, size_t n) {
 }
 
 static CUresult dist_carve(chol_rank *R, int prec, size_t n, chol_ws *w) {
-  const size_t saved = R->lap->nb;
-  R->lap->nb = dist_nb(R, prec, n);
-  const CUresult e = chol_carve(R->lap, prec, n, w);
-  R->lap->nb = saved;
-  return e;
+  return chol_carve_nb(R->lap, prec, n, dist_nb(R, prec, n), w);
 }
 
 /* optional: stream every finished block column of a rank straight back to the caller's host matrix
@@ -369,10 +380,20 @@ typedef struct {
   CUevent ev[8];
 } dist_gather;
 
+/* optional: the rank's block columns are still arriving from the host while the first steps run
+ * (upload stream, in local block-column order; one event per group of gblk local block columns).
+ * The first split_steps trailing updates are launched group by group, each behind its group's
+ * event; from step split_steps on everything has arrived and the update is one launch again. */
+typedef struct {
+  CUevent *ev;
+  size_t ngroups, gblk, split_steps;
+} dist_stage;
+
 static CUresult copy2d(int h2d, void *host, size_t ldh, CUdeviceptr dev, size_t ldd, size_t rows, size_t cols, size_t es,
                        CUstream st);
 
-static CUresult dist_potrf(chol_rank *R, int prec, size_t n, CUdeviceptr Aloc, size_t ldl, long *info, dist_gather *ga) {
+static CUresult dist_potrf(chol_rank *R, int prec, size_t n, CUdeviceptr Aloc, size_t ldl, long *info, dist_gather *ga,
+                           const dist_stage *sg) {
   CULAPACKhandle h = R->lap;
   const int P = R->nranks, me = R->rank;
   chol_ws w;
@@ -392,9 +413,15 @@ static CUresult dist_potrf(chol_rank *R, int prec, size_t n, CUdeviceptr Aloc, s
     const size_t ldw = chol_roundup(rest ? rest : 1, 16);
     /* W's buffer was last read by the trailing update of step c-2 */
     if (c >= 2) CU_ERROR_CHECK(cuStreamWaitEvent(sp, h->ev_rest[(c - 2) % CHOL_EVENT_RING], 0));
+    const bool staged = sg != NULL && c < sg->split_steps;
+    if (sg != NULL && c == sg->split_steps) { /* one upload stream: its last event implies the others */
+      CU_ERROR_CHECK(cuStreamWaitEvent(sp, sg->ev[sg->ngroups - 1], 0));
+      CU_ERROR_CHECK(cuStreamWaitEvent(su, sg->ev[sg->ngroups - 1], 0));
+    }
     if (me == owner) {
       const size_t lc = c / (size_t)P;
       const CUdeviceptr Ajj = chol_at(Aloc, ldl, j, lc * nb, es);
+      if (staged) CU_ERROR_CHECK(cuStreamWaitEvent(sp, sg->ev[lc / sg->gblk], 0));
       if (!rest) {
         CU_ERROR_CHECK(chol_potrf_diag(prec, 'L', jb, Ajj, ldl, dinfo, (long)j, &w, sp));
         if (ga != NULL) {
@@ -435,9 +462,22 @@ static CUresult dist_potrf(chol_rank *R, int prec, size_t n, CUdeviceptr Aloc, s
       const CUdeviceptr W2 = chol_at(W, ldw, g_first - (j + jb), 0, es);
       const CUdeviceptr D = chol_at(Aloc, ldl, g_first, col2, es);
       CU_ERROR_CHECK(cuStreamWaitEvent(su, h->ev_panel[c % CHOL_EVENT_RING], 0));
-      const bool prof = h->profile && h->prof_n < h->prof_cap;
+      const bool prof = !staged && h->profile && h->prof_n < h->prof_cap;
       if (prof) CU_ERROR_CHECK(cuEventRecord(h->prof_e0[h->prof_n], su));
-      CU_ERROR_CHECK(gemm_cyc(prec, herm, m2, n2, jb, W2, ldw, D, ldl, P > 1 ? (int)nb : 0, P, su));
+      if (!staged) {
+        CU_ERROR_CHECK(gemm_cyc(prec, herm, m2, n2, jb, W2, ldw, D, ldl, P > 1 ? (int)nb : 0, P, su));
+      } else { /* one launch per upload group, each as soon as its columns are on the device */
+        const size_t nlocb = (my_cols + nb - 1) / nb;
+        for (size_t lcs = lc2; lcs < nlocb;) {
+          const size_t g = lcs / sg->gblk, lce = chol_min((g + 1) * sg->gblk, nlocb);
+          const size_t c0 = lcs * nb, c1 = chol_min(lce * nb, my_cols);
+          const size_t gf = (lcs * (size_t)P + (size_t)me) * nb;
+          CU_ERROR_CHECK(cuStreamWaitEvent(su, sg->ev[g], 0));
+          CU_ERROR_CHECK(gemm_cyc(prec, herm, n - gf, c1 - c0, jb, chol_at(W, ldw, gf - (j + jb), 0, es), ldw,
+                                  chol_at(Aloc, ldl, gf, c0, es), ldl, P > 1 ? (int)nb : 0, P, su));
+          lcs = lce;
+        }
+      }
       if (prof) {
         CU_ERROR_CHECK(cuEventRecord(h->prof_e1[h->prof_n], su));
         /* algorithmic flops of this rank's share: sum over owned block columns of rows*width*k */
@@ -456,6 +496,7 @@ static CUresult dist_potrf(chol_rank *R, int prec, size_t n, CUdeviceptr Aloc, s
       const size_t lc1 = (c + 1) / (size_t)P, jb2 = chol_min(nb, rest);
       const CUdeviceptr A22 = chol_at(Aloc, ldl, j + jb, lc1 * nb, es);
       if (c >= 1) CU_ERROR_CHECK(cuStreamWaitEvent(sp, h->ev_rest[(c - 1) % CHOL_EVENT_RING], 0));
+      if (staged) CU_ERROR_CHECK(cuStreamWaitEvent(sp, sg->ev[lc1 / sg->gblk], 0));
       CU_ERROR_CHECK(chol_gemm_ex(prec, 'N', 'C', 0, 0, 0, 0, 'L', herm, rest, jb2, jb, MONE, W, ldw, W, ldw, ONE, A22, ldl,
                                   A22, ldl, sp));
     }
@@ -483,7 +524,6 @@ static CUresult dist_potrf(chol_rank *R, int prec, size_t n, CUdeviceptr Aloc, s
 /* =============================================================================================
  * one-process-per-GPU entry points (C-ABI extension used under torchrun)
  * ===========================================================================================*/
-typedef struct chol_rank *cholDist;
 
 /* 128-byte NCCL unique id, to be created on rank 0 and sent to the other ranks by the launcher */
 CUresult cholDistGetUniqueId(void *id128) {
@@ -491,6 +531,20 @@ CUresult cholDistGetUniqueId(void *id128) {
   chol_nccl_id id;
   NCCL_CHECK(nccl.GetUniqueId(&id));
   memcpy(id128, &id, sizeof id);
+  return CUDA_SUCCESS;
+}
+
+static CUresult dist_comm_init(chol_rank *R, const void *id128) {
+  CU_ERROR_CHECK(nccl_load());
+  chol_nccl_id id;
+  memcpy(&id, id128, sizeof id);
+  if (nccl.CommInitRankConfig != NULL) {
+    chol_nccl_config cfg = {sizeof(chol_nccl_config), 0xcafebeef, 22703, CHOL_NCCL_UNDEF_INT, CHOL_NCCL_UNDEF_INT,
+                            CHOL_NCCL_UNDEF_INT, nccl_max_ctas(), NULL, CHOL_NCCL_UNDEF_INT, CHOL_NCCL_UNDEF_INT, NULL,
+                            CHOL_NCCL_UNDEF_INT, CHOL_NCCL_UNDEF_INT, CHOL_NCCL_UNDEF_INT, CHOL_NCCL_UNDEF_INT};
+    NCCL_CHECK(nccl.CommInitRankConfig(&R->comm, R->nranks, id, R->rank, &cfg));
+  } else
+    NCCL_CHECK(nccl.CommInitRank(&R->comm, R->nranks, id, R->rank));
   return CUDA_SUCCESS;
 }
 
@@ -508,17 +562,12 @@ CUresult cholDistCreate(cholDist *out, int rank, int nranks, const void *id128) 
   }
   R->context = R->lap->context;
   if (nranks > 1) {
-    if (id128 == NULL) return CUDA_ERROR_INVALID_VALUE;
-    CU_ERROR_CHECK(nccl_load());
-    chol_nccl_id id;
-    memcpy(&id, id128, sizeof id);
-    if (nccl.CommInitRankConfig != NULL) {
-      chol_nccl_config cfg = {sizeof(chol_nccl_config), 0xcafebeef, 22703, CHOL_NCCL_UNDEF_INT, CHOL_NCCL_UNDEF_INT,
-                              CHOL_NCCL_UNDEF_INT, nccl_max_ctas(), NULL, CHOL_NCCL_UNDEF_INT, CHOL_NCCL_UNDEF_INT, NULL,
-                              CHOL_NCCL_UNDEF_INT, CHOL_NCCL_UNDEF_INT, CHOL_NCCL_UNDEF_INT, CHOL_NCCL_UNDEF_INT};
-      NCCL_CHECK(nccl.CommInitRankConfig(&R->comm, nranks, id, rank, &cfg));
-    } else
-      NCCL_CHECK(nccl.CommInitRank(&R->comm, nranks, id, rank));
+    e = (id128 == NULL) ? CUDA_ERROR_INVALID_VALUE : dist_comm_init(R, id128);
+    if (e != CUDA_SUCCESS) {
+      cuLAPACKDestroy(R->lap);
+      free(R);
+      return e;
+    }
   }
   *out = R;
   return CUDA_SUCCESS;
@@ -550,7 +599,7 @@ size_t cholDistLocalCols(size_t n, size_t nb, int rank, int nranks) { return loc
     }                                                                                                       \
     if (n == 0) return CUDA_SUCCESS;                                                                        \
     CU_ERROR_CHECK(cuCtxPushCurrent(R->context));                                                           \
-    const CUresult e = dist_potrf(R, p, n, Aloc, ldl, info, NULL);                                                \
+    const CUresult e = dist_potrf(R, p, n, Aloc, ldl, info, NULL, NULL);                                    \
     CUcontext dummy;                                                                                        \
     cuCtxPopCurrent(&dummy);                                                                                \
     return e;                                                                                               \
@@ -578,32 +627,58 @@ static CUresult rank_init_task(const void *args) {
   return e;
 }
 
+/* NCCL reads NCCL_MAX_CTAS when a communicator is created; set it for the duration of
+ * ncclCommInitAll only (an explicit setting by the user wins) and put the environment back */
+static int nccl_comm_init_all_capped(chol_nccl_comm *comms, int P, const int *devs) {
+  const bool user_set = getenv("NCCL_MAX_CTAS") != NULL;
+  if (!user_set) {
+    char buf[16];
+    snprintf(buf, sizeof buf, "%d", nccl_max_ctas());
+    setenv("NCCL_MAX_CTAS", buf, 0);
+  }
+  const int rc = nccl.CommInitAll(comms, P, devs);
+  if (!user_set) unsetenv("NCCL_MAX_CTAS");
+  return rc;
+}
+
+static void release_ranks(CUmultiGPU m);
+
 static CUresult ensure_ranks(CUmultiGPU m) {
   if (m->ranks != NULL) return CUDA_SUCCESS;
   const int P = m->n;
-  m->ranks = calloc((size_t)P, sizeof *m->ranks);
-  m->comms = calloc((size_t)P, sizeof *m->comms);
-  if (m->ranks == NULL || m->comms == NULL) return CUDA_ERROR_OUT_OF_MEMORY;
-  if (P > 1) {
-    CU_ERROR_CHECK(nccl_load());
-    int *devs = malloc(sizeof(int) * (size_t)P);
-    for (int i = 0; i < P; i++) devs[i] = (int)m->w[i].device;
-    char buf[16];
-    snprintf(buf, sizeof buf, "%d", nccl_max_ctas());
-    setenv("NCCL_MAX_CTAS", buf, 0); /* single-process mode: NCCL is ours alone; an explicit setting wins */
-    const int rc = nccl.CommInitAll(m->comms, P, devs);
-    free(devs);
-    NCCL_CHECK(rc);
-  }
+  chol_rank *ranks = calloc((size_t)P, sizeof *ranks);
+  chol_nccl_comm *comms = calloc((size_t)P, sizeof *comms);
   chol_rank **ptrs = malloc(sizeof(*ptrs) * (size_t)P);
-  for (int i = 0; i < P; i++) {
-    m->ranks[i].rank = i;
-    m->ranks[i].nranks = P;
-    m->ranks[i].comm = m->comms[i];
-    ptrs[i] = &m->ranks[i];
+  int *devs = malloc(sizeof(int) * (size_t)P);
+  CUresult e = (ranks && comms && ptrs && devs) ? CUDA_SUCCESS : CUDA_ERROR_OUT_OF_MEMORY;
+  if (e == CUDA_SUCCESS && P > 1) {
+    e = nccl_load();
+    if (e == CUDA_SUCCESS) {
+      for (int i = 0; i < P; i++) devs[i] = (int)m->w[i].device;
+      const int rc = nccl_comm_init_all_capped(comms, P, devs);
+      if (rc != 0) {
+        if (errorHandler != NULL) errorHandler("ncclCommInitAll", __func__, __FILE__, __LINE__, rc, nccl_strerror);
+        e = CUDA_ERROR_UNKNOWN;
+      }
+    }
   }
-  const CUresult e = run_on_all(m, rank_init_task, ptrs, sizeof(*ptrs), sizeof(*ptrs));
+  if (e == CUDA_SUCCESS) {
+    for (int i = 0; i < P; i++) {
+      ranks[i].rank = i;
+      ranks[i].nranks = P;
+      ranks[i].comm = comms[i];
+      ptrs[i] = &ranks[i];
+    }
+    m->ranks = ranks;
+    m->comms = comms;
+    e = run_on_all(m, rank_init_task, ptrs, sizeof(*ptrs), sizeof(*ptrs));
+    if (e != CUDA_SUCCESS) release_ranks(m); /* a half-initialised set must not look ready */
+  } else {
+    free(ranks);
+    free(comms);
+  }
   free(ptrs);
+  free(devs);
   return e;
 }
 
@@ -616,18 +691,26 @@ static CUresult rank_free_task(const void *args) {
   return CUDA_SUCCESS;
 }
 
-CUresult cuMultiGPUDestroy(CUmultiGPU m) {
-  if (m == NULL) return CUDA_ERROR_INVALID_VALUE;
-  if (m->ranks != NULL) {
-    chol_rank **ptrs = malloc(sizeof(*ptrs) * (size_t)m->n);
+/* per-GPU solver state: device buffers and LAPACK handles go on their own workers, then the comms */
+static void release_ranks(CUmultiGPU m) {
+  if (m->ranks == NULL) return;
+  chol_rank **ptrs = malloc(sizeof(*ptrs) * (size_t)m->n);
+  if (ptrs != NULL) {
     for (int i = 0; i < m->n; i++) ptrs[i] = &m->ranks[i];
     run_on_all(m, rank_free_task, ptrs, sizeof(*ptrs), sizeof(*ptrs));
     free(ptrs);
-    for (int i = 0; i < m->n; i++)
-      if (m->comms[i]) nccl.CommDestroy(m->comms[i]);
-    free(m->ranks);
-    free(m->comms);
   }
+  for (int i = 0; i < m->n; i++)
+    if (m->comms[i]) nccl.CommDestroy(m->comms[i]);
+  free(m->ranks);
+  free(m->comms);
+  m->ranks = NULL;
+  m->comms = NULL;
+}
+
+CUresult cuMultiGPUDestroy(CUmultiGPU m) {
+  if (m == NULL) return CUDA_ERROR_INVALID_VALUE;
+  release_ranks(m);
   for (int i = 0; i < m->n; i++) {
     struct worker *w = &m->w[i];
     pthread_mutex_lock(&w->mutex);
@@ -719,6 +802,53 @@ static CUresult copy2d(int h2d, void *host, size_t ldh, CUdeviceptr dev, size_t 
   return cuMemcpy2DAsync(&c, st);
 }
 
+/* phase 1 (every rank, before anyone starts the collective factorisation): workspace and the
+ * rank's resident block columns.  An allocation failure on one GPU then fails the call on all of
+ * them instead of leaving the other ranks waiting in a broadcast. */
+static CUresult rank_potrf_prepare_task(const void *argp) {
+  potrf_args *a = *(potrf_args *const *)argp;
+  chol_rank *R = a->R;
+  const size_t n = a->n, es = chol_esize(a->prec);
+  chol_ws w;
+  CU_ERROR_CHECK(dist_carve(R, a->prec, n, &w));
+  const size_t my_cols = local_cols(n, w.nb, R->rank, R->nranks);
+  const size_t need = chol_roundup(n, 16) * (my_cols ? my_cols : 1) * es;
+  if (need > R->local_bytes) {
+    if (R->local) CU_ERROR_CHECK(cuMemFree(R->local));
+    R->local = 0;
+    R->local_bytes = 0;
+    CU_ERROR_CHECK(cuMemAlloc(&R->local, need));
+    R->local_bytes = need;
+  }
+  return CUDA_SUCCESS;
+}
+
+/* CHOL_MGPU_H2D_OVERLAP=1: start factoring while the block columns are still being uploaded
+ * (lower, page-locked host memory).  Off by default until it has been measured on hardware. */
+static bool h2d_overlap_enabled(void) {
+  const char *e = getenv("CHOL_MGPU_H2D_OVERLAP");
+  return e != NULL && atoi(e) != 0;
+}
+
+/* number of leading steps whose update must be split by upload group: those that can start before
+ * the upload (bytes at ~50 GB/s of PCIe, CHOL_H2D_GBPS overrides) has finished, at the update rate
+ * the engine sustains (~30 real TFLOP/s FP64, ~35 FP32), with a 1.5x safety margin. */
+static size_t staged_split_steps(int prec, size_t n, size_t nb, int P, double upload_bytes) {
+  const char *e = getenv("CHOL_H2D_GBPS");
+  const double gbps = (e != NULL && atof(e) > 0.0) ? atof(e) : 50.0;
+  const double t_up = 1.5 * upload_bytes / (gbps * 1e9);
+  const double rate = (prec == 'd' || prec == 'z') ? 30e12 : 35e12, cplx = chol_is_complex(prec) ? 4.0 : 1.0;
+  const size_t nblk = (n + nb - 1) / nb;
+  double t = 0.0;
+  size_t c = 0;
+  for (; c < nblk && t < t_up; c++) {
+    const double rest = (double)(n - chol_min(n, (c + 1) * nb));
+    t += cplx * rest * rest * (double)nb / (double)P / rate;
+  }
+  return c;
+}
+
+/* phase 2: scatter / factor / gather */
 static CUresult rank_potrf_task(const void *argp) {
   potrf_args *a = *(potrf_args *const *)argp;
   chol_rank *R = a->R;
@@ -729,16 +859,53 @@ static CUresult rank_potrf_task(const void *argp) {
   CU_ERROR_CHECK(dist_carve(R, prec, n, &w));
   const size_t nb = w.nb, nblk = (n + nb - 1) / nb, my_cols = local_cols(n, nb, me, P);
   const size_t ldl = chol_roundup(n, 16);
-  const size_t need = ldl * (my_cols ? my_cols : 1) * es;
-  if (need > R->local_bytes) {
-    if (R->local) CU_ERROR_CHECK(cuMemFree(R->local));
-    R->local = 0;
-    R->local_bytes = 0;
-    CU_ERROR_CHECK(cuMemAlloc(&R->local, need));
-    R->local_bytes = need;
-  }
   CUstream st = h->s_update;
   char *hostA = a->hostA;
+  unsigned int memtype = 0; /* overlap only with page-locked host memory: pageable copies would block this thread */
+  const bool pinned = cuPointerGetAttribute(&memtype, CU_POINTER_ATTRIBUTE_MEMORY_TYPE, (CUdeviceptr)(size_t)hostA) == CUDA_SUCCESS &&
+                      memtype == CU_MEMORYTYPE_HOST;
+  const size_t nlocb = (my_cols + nb - 1) / nb;
+
+  if (a->uplo == 'L' && pinned && h2d_overlap_enabled() && nlocb >= 2) {
+    /* ---- upload, factorisation and download all overlap ---- */
+    enum { MAXG = 8 };
+    CUevent up_ev[MAXG] = {0};
+    dist_stage sg;
+    dist_gather ga;
+    memset(&ga, 0, sizeof ga);
+    sg.ev = up_ev;
+    sg.gblk = (nlocb + MAXG - 1) / MAXG;
+    sg.ngroups = (nlocb + sg.gblk - 1) / sg.gblk;
+    ga.hostA = hostA;
+    ga.lda = lda;
+    CUstream s_up = NULL;
+    CUresult e = cuStreamCreate(&s_up, CU_STREAM_NON_BLOCKING);
+    if (e == CUDA_SUCCESS) e = cuStreamCreate(&ga.s_copy, CU_STREAM_NON_BLOCKING);
+    for (size_t g = 0; g < sg.ngroups && e == CUDA_SUCCESS; g++) e = cuEventCreate(&up_ev[g], CU_EVENT_DISABLE_TIMING);
+    for (int i = 0; i < 8 && e == CUDA_SUCCESS; i++) e = cuEventCreate(&ga.ev[i], CU_EVENT_DISABLE_TIMING);
+    double bytes = 0.0;
+    for (size_t c = (size_t)me, lc = 0; c < nblk && e == CUDA_SUCCESS; c += (size_t)P, lc++) {
+      const size_t j = c * nb, jb = chol_min(nb, n - j), rows = n - j;
+      e = copy2d(1, hostA + (j * lda + j) * es, lda, chol_at(R->local, ldl, j, lc * nb, es), ldl, rows, jb, es, s_up);
+      bytes += (double)rows * (double)jb * (double)es;
+      if (e == CUDA_SUCCESS && ((lc + 1) % sg.gblk == 0 || lc + 1 == nlocb)) e = cuEventRecord(up_ev[lc / sg.gblk], s_up);
+    }
+    if (e == CUDA_SUCCESS) {
+      sg.split_steps = staged_split_steps(prec, n, nb, P, bytes);
+      e = dist_potrf(R, prec, n, R->local, ldl, &a->info, &ga, &sg);
+    }
+    if (s_up) cuStreamSynchronize(s_up);
+    if (ga.s_copy) cuStreamSynchronize(ga.s_copy);
+    for (size_t g = 0; g < sg.ngroups; g++)
+      if (up_ev[g]) cuEventDestroy(up_ev[g]);
+    for (int i = 0; i < 8; i++)
+      if (ga.ev[i]) cuEventDestroy(ga.ev[i]);
+    if (s_up) cuStreamDestroy(s_up);
+    if (ga.s_copy) cuStreamDestroy(ga.s_copy);
+    CU_ERROR_CHECK(e);
+    return CUDA_SUCCESS;
+  }
+
   /* ---- scatter: block column c (lower) or block row c (upper, transposed on the device) ---- */
   for (size_t c = (size_t)me, lc = 0; c < nblk; c += (size_t)P, lc++) {
     const size_t j = c * nb, jb = chol_min(nb, n - j), rows = n - j;
@@ -753,21 +920,21 @@ static CUresult rank_potrf_task(const void *argp) {
   }
   CU_ERROR_CHECK(cuStreamSynchronize(st));
   /* ---- factor (lower: finished block columns stream back to the host while later steps run) ---- */
-  unsigned int memtype = 0; /* overlap only with page-locked host memory: a pageable D2H would block this thread */
-  const bool pinned = cuPointerGetAttribute(&memtype, CU_POINTER_ATTRIBUTE_MEMORY_TYPE, (CUdeviceptr)(size_t)hostA) == CUDA_SUCCESS &&
-                      memtype == CU_MEMORYTYPE_HOST;
   if (a->uplo == 'L' && pinned) {
     dist_gather ga;
+    memset(&ga, 0, sizeof ga);
     ga.hostA = hostA;
     ga.lda = lda;
-    CU_ERROR_CHECK(cuStreamCreate(&ga.s_copy, CU_STREAM_NON_BLOCKING));
-    for (int i = 0; i < 8; i++) CU_ERROR_CHECK(cuEventCreate(&ga.ev[i], CU_EVENT_DISABLE_TIMING));
-    const CUresult fe = dist_potrf(R, prec, n, R->local, ldl, &a->info, &ga);
-    for (int i = 0; i < 8; i++) cuEventDestroy(ga.ev[i]);
-    cuStreamDestroy(ga.s_copy);
-    return fe;
+    CUresult e = cuStreamCreate(&ga.s_copy, CU_STREAM_NON_BLOCKING);
+    for (int i = 0; i < 8 && e == CUDA_SUCCESS; i++) e = cuEventCreate(&ga.ev[i], CU_EVENT_DISABLE_TIMING);
+    if (e == CUDA_SUCCESS) e = dist_potrf(R, prec, n, R->local, ldl, &a->info, &ga, NULL);
+    for (int i = 0; i < 8; i++)
+      if (ga.ev[i]) cuEventDestroy(ga.ev[i]);
+    if (ga.s_copy) cuStreamDestroy(ga.s_copy);
+    CU_ERROR_CHECK(e);
+    return CUDA_SUCCESS;
   }
-  CU_ERROR_CHECK(dist_potrf(R, prec, n, R->local, ldl, &a->info, NULL));
+  CU_ERROR_CHECK(dist_potrf(R, prec, n, R->local, ldl, &a->info, NULL, NULL));
   /* ---- gather: whole block columns / rows travel back (upper: through a transposing staging
    * buffer).  The part of each diagonal block that lies in the caller's OTHER triangle was uploaded
    * with the block, is never written by the factorisation and returns bit-identical. */
@@ -801,7 +968,8 @@ static CUresult mgpu_potrf(CUmultiGPULAPACKhandle handle, int prec, int uplo, si
     args[i].hostA = A;
     ptrs[i] = &args[i];
   }
-  const CUresult e = run_on_all(m, rank_potrf_task, ptrs, sizeof(*ptrs), sizeof(*ptrs));
+  CUresult e = run_on_all(m, rank_potrf_prepare_task, ptrs, sizeof(*ptrs), sizeof(*ptrs));
+  if (e == CUDA_SUCCESS) e = run_on_all(m, rank_potrf_task, ptrs, sizeof(*ptrs), sizeof(*ptrs));
   long first = 0;
   for (int i = 0; i < P; i++)
     if (args[i].info > 0 && (first == 0 || args[i].info < first)) first = args[i].info;

@@ -55,7 +55,10 @@ CUresult cuBLASCreate(CUBLAShandle *handle) {
     e = cuCtxGetDevice(&h->device);
   }
   if (e == CUDA_SUCCESS) e = cuMemAlloc(&h->dinfo, sizeof(long));
+  if (e == CUDA_SUCCESS) e = cuEventCreate(&h->scratch_done, CU_EVENT_DISABLE_TIMING);
   if (e != CUDA_SUCCESS) {
+    if (h->dinfo) cuMemFree(h->dinfo);
+    if (h->primary_retained) cuDevicePrimaryCtxRelease(h->device);
     free(h);
     CU_ERROR_CHECK(e);
   }
@@ -68,6 +71,7 @@ CUresult cuBLASDestroy(CUBLAShandle h) {
   CU_ERROR_CHECK(cuCtxPushCurrent(h->context));
   if (h->scratch) cuMemFree(h->scratch);
   if (h->dinfo) cuMemFree(h->dinfo);
+  if (h->scratch_done) cuEventDestroy(h->scratch_done);
   CUcontext dummy;
   CU_ERROR_CHECK(cuCtxPopCurrent(&dummy));
   if (h->primary_retained) cuDevicePrimaryCtxRelease(h->device);
@@ -88,6 +92,18 @@ CUresult chol_blas_scratch(CUBLAShandle h, size_t bytes, CUdeviceptr *out) {
     h->scratch_bytes = bytes;
   }
   *out = h->scratch;
+  return CUDA_SUCCESS;
+}
+
+CUresult chol_blas_scratch_acquire(CUBLAShandle h, CUstream stream) {
+  if (h->scratch_in_use && h->scratch_stream != stream) CU_ERROR_CHECK(cuStreamWaitEvent(stream, h->scratch_done, 0));
+  return CUDA_SUCCESS;
+}
+
+CUresult chol_blas_scratch_release(CUBLAShandle h, CUstream stream) {
+  CU_ERROR_CHECK(cuEventRecord(h->scratch_done, stream));
+  h->scratch_stream = stream;
+  h->scratch_in_use = true;
   return CUDA_SUCCESS;
 }
 
@@ -176,19 +192,31 @@ CUresult cuLAPACKProfile(CULAPACKhandle h, int enable) {
   if (h == NULL) return CUDA_ERROR_INVALID_VALUE;
   if (enable && h->prof_cap == 0) {
     const int cap = 2048;
-    h->prof_e0 = calloc((size_t)cap, sizeof(CUevent));
-    h->prof_e1 = calloc((size_t)cap, sizeof(CUevent));
-    h->prof_flops = calloc((size_t)cap, sizeof(double));
-    h->prof_hist_ms = calloc((size_t)cap, sizeof(float));
-    h->prof_hist_flops = calloc((size_t)cap, sizeof(double));
-    if (!h->prof_e0 || !h->prof_e1 || !h->prof_flops || !h->prof_hist_ms || !h->prof_hist_flops) return CUDA_ERROR_OUT_OF_MEMORY;
+    if (h->prof_e0 == NULL) h->prof_e0 = calloc((size_t)cap, sizeof(CUevent));
+    if (h->prof_e1 == NULL) h->prof_e1 = calloc((size_t)cap, sizeof(CUevent));
+    if (h->prof_flops == NULL) h->prof_flops = calloc((size_t)cap, sizeof(double));
+    if (h->prof_hist_ms == NULL) h->prof_hist_ms = calloc((size_t)cap, sizeof(float));
+    if (h->prof_hist_flops == NULL) h->prof_hist_flops = calloc((size_t)cap, sizeof(double));
+    if (!h->prof_e0 || !h->prof_e1 || !h->prof_flops || !h->prof_hist_ms || !h->prof_hist_flops)
+      return CUDA_ERROR_OUT_OF_MEMORY; /* whatever was allocated is released by cuLAPACKDestroy */
     CU_ERROR_CHECK(cuCtxPushCurrent(h->context));
-    for (int i = 0; i < cap; i++) {
-      CU_ERROR_CHECK(cuEventCreate(&h->prof_e0[i], CU_EVENT_DEFAULT));
-      CU_ERROR_CHECK(cuEventCreate(&h->prof_e1[i], CU_EVENT_DEFAULT));
+    CUresult e = CUDA_SUCCESS;
+    int made = 0;
+    for (; made < cap && e == CUDA_SUCCESS; made++) {
+      e = cuEventCreate(&h->prof_e0[made], CU_EVENT_DEFAULT);
+      if (e == CUDA_SUCCESS) e = cuEventCreate(&h->prof_e1[made], CU_EVENT_DEFAULT);
+      if (e != CUDA_SUCCESS && h->prof_e0[made]) cuEventDestroy(h->prof_e0[made]);
+      if (e != CUDA_SUCCESS) break;
+    }
+    if (e != CUDA_SUCCESS) { /* roll back: profiling stays off, nothing leaks */
+      for (int i = 0; i < made; i++) {
+        cuEventDestroy(h->prof_e0[i]);
+        cuEventDestroy(h->prof_e1[i]);
+      }
     }
     CUcontext dummy;
     CU_ERROR_CHECK(cuCtxPopCurrent(&dummy));
+    CU_ERROR_CHECK(e);
     h->prof_cap = cap;
   }
   h->profile = enable;

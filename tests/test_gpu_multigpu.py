@@ -1,6 +1,8 @@
 """GPU tests of the multi-GPU surface: the host-pointer cuMultiGPU* API on however many GPUs are
 visible (1 is enough), the cholDist* SPMD core, and the block-cyclic trailing-update kernel
 (emulating every rank of P = 2, 4 on ONE GPU, as separate launches on that rank's packed columns)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -57,6 +59,31 @@ def test_multigpu_potrf_pinned_host_overlapped_gather(mgpu, uplo):
     other = np.triu(got, 1) if uplo == "L" else np.tril(got, -1)
     other0 = np.triu(A, 1) if uplo == "L" else np.tril(A, -1)
     assert np.array_equal(other, other0)
+
+
+# Code paths written after the round's GPU budget was spent: they are off by default in the library
+# (environment switches) and their tests run only on request, so that the first GPU session can
+# verify them in one go:  CHOL_TEST_STAGED=1 python -m pytest tests -m gpu -k staged
+staged = pytest.mark.skipif(os.environ.get("CHOL_TEST_STAGED") != "1", reason="not yet verified on hardware; CHOL_TEST_STAGED=1 runs it")
+
+
+@staged
+@pytest.mark.parametrize("gbps", ["50", "0.0001"])
+@pytest.mark.parametrize("n", [700, 1500, 3000])
+def test_staged_multigpu_potrf_upload_overlap(mgpu, n, gbps, monkeypatch):
+    """CHOL_MGPU_H2D_OVERLAP=1: the factorisation starts while block columns are still being
+    uploaded; a tiny assumed PCIe rate forces EVERY step through the group-by-group update."""
+    monkeypatch.setenv("CHOL_MGPU_H2D_OVERLAP", "1")
+    monkeypatch.setenv("CHOL_H2D_GBPS", gbps)
+    A = H.spd_matrix("d", n, k=64)
+    want = A.copy(order="F")
+    assert ORA.potrf("d", "L", want) == 0
+    hp = torch.empty(n, n, dtype=torch.float64, pin_memory=True)
+    hp.copy_(torch.from_numpy(np.ascontiguousarray(A.T)))
+    assert mgpu.potrf("d", "L", n, hp.data_ptr(), n) == 0
+    got = hp.numpy().T
+    assert np.abs(np.tril(got) - np.tril(want)).max() <= 64 * n * H.eps("d") * np.abs(want).max()
+    assert np.array_equal(np.triu(got, 1), np.triu(A, 1))
 
 
 def test_multigpu_potrf_info_and_args(mgpu):

@@ -20,11 +20,11 @@ ROOT = H.ROOT
 def test_library_loads_and_exports_every_declared_symbol():
     lib = chol.lib()
     decl = set()
-    for f in ("blas.h", "lapack.h", "cumultigpu.h", "error.h"):
+    for f in ("blas.h", "lapack.h", "cumultigpu.h", "error.h", "cholesky_b200.h"):
         s = open(os.path.join(ROOT, "include", f)).read()
         s = re.sub(r"/\*.*?\*/", "", s, flags=re.S)
         s = re.sub(r"#define[^\n]*(\\\n[^\n]*)*", "", s)
-        decl |= set(re.findall(r"\b(cu[A-Z]\w+)\s*\(", s))
+        decl |= set(re.findall(r"\b((?:cu[A-Z]|cholDist|chol_)\w+)\s*\(", s))
     decl = {d for d in decl if not d.startswith(("cuMem", "cuCtx", "cuStream", "cuEvent", "cuDevice", "cuInit", "cuGetError"))}
     assert len(decl) >= 90
     for name in sorted(decl):
