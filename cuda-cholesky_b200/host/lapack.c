@@ -386,6 +386,7 @@ CUresult chol_logdet(CULAPACKhandle h, int prec, CUdeviceptr x, size_t incx, siz
 #define GEN_LAPACK(U, p, REAL)                                                                                       \
   CUresult cu##U##potrf(CULAPACKhandle h, CBlasUplo uplo, size_t n, CUdeviceptr A, size_t lda, long *info) {         \
     *info = 0;                                                                                                       \
+    if (h == NULL) return CUDA_ERROR_INVALID_VALUE;                                                                  \
     LAPACK_ARG(lda < n, 4);                                                                                          \
     if (n == 0) return CUDA_SUCCESS;                                                                                 \
     return chol_potrf(h, p, uplo, n, A, lda, info);                                                                  \
@@ -393,6 +394,7 @@ CUresult chol_logdet(CULAPACKhandle h, int prec, CUdeviceptr x, size_t incx, siz
   CUresult cu##U##trtri(CULAPACKhandle h, CBlasUplo uplo, CBlasDiag diag, size_t n, CUdeviceptr A, size_t lda,       \
                         long *info) {                                                                                \
     *info = 0;                                                                                                       \
+    if (h == NULL) return CUDA_ERROR_INVALID_VALUE;                                                                  \
     LAPACK_ARG(lda < n, 5);                                                                                          \
     if (n == 0) return CUDA_SUCCESS;                                                                                 \
     return chol_trtri(h, p, uplo, diag, n, A, lda, info);                                                            \
@@ -407,17 +409,20 @@ CUresult chol_logdet(CULAPACKhandle h, int prec, CUdeviceptr x, size_t incx, siz
   }                                                                                                                  \
   CUresult cu##U##lauum(CULAPACKhandle h, CBlasUplo uplo, size_t n, CUdeviceptr A, size_t lda, long *info) {         \
     *info = 0;                                                                                                       \
+    if (h == NULL) return CUDA_ERROR_INVALID_VALUE;                                                                  \
     LAPACK_ARG(lda < n, 4);                                                                                          \
     if (n == 0) return CUDA_SUCCESS;                                                                                 \
     return chol_lauum(h, p, uplo, n, A, lda, info);                                                                  \
   }                                                                                                                  \
   CUresult cu##U##potri(CULAPACKhandle h, CBlasUplo uplo, size_t n, CUdeviceptr A, size_t lda, long *info) {         \
     *info = 0;                                                                                                       \
+    if (h == NULL) return CUDA_ERROR_INVALID_VALUE;                                                                  \
     LAPACK_ARG(lda < n, 4);                                                                                          \
     if (n == 0) return CUDA_SUCCESS;                                                                                 \
     return chol_potri(h, p, uplo, n, A, lda, info);                                                                  \
   }                                                                                                                  \
   CUresult cu##U##logdet(CULAPACKhandle h, CUdeviceptr x, size_t incx, size_t n, REAL *result, CUstream stream) {    \
+    if (h == NULL || result == NULL) return CUDA_ERROR_INVALID_VALUE;                                                \
     if (n == 0) {                                                                                                    \
       *result = 0;                                                                                                   \
       return CUDA_SUCCESS;                                                                                           \

@@ -769,8 +769,8 @@ CUresult cuMultiGPUBLASDestroy(CUmultiGPUBLAShandle h) {
 CUresult cuMultiGPUBLASSynchronize(CUmultiGPUBLAShandle h) {
   return h == NULL ? CUDA_ERROR_INVALID_VALUE : cuMultiGPUSynchronize(h->mgpu);
 }
-CUmultiGPU chol_mgpu_of_lapack(CUmultiGPULAPACKhandle h) { return h->mgpu; }
-CUmultiGPU chol_mgpu_of_blas(CUmultiGPUBLAShandle h) { return h->mgpu; }
+CUmultiGPU chol_mgpu_of_lapack(CUmultiGPULAPACKhandle h) { return h ? h->mgpu : NULL; }
+CUmultiGPU chol_mgpu_of_blas(CUmultiGPUBLAShandle h) { return h ? h->mgpu : NULL; }
 int chol_mgpu_device(CUmultiGPU m, int i) { return (int)m->w[i].device; }
 CULAPACKhandle chol_mgpu_rank_lapack(CUmultiGPU m, int i) { return m->ranks ? m->ranks[i].lap : NULL; }
 CUresult chol_mgpu_run_on_all(CUmultiGPU m, CUresult (*fn)(const void *), const void *args, size_t stride, size_t size) {
@@ -954,6 +954,7 @@ static CUresult rank_potrf_task(const void *argp) {
 }
 
 static CUresult mgpu_potrf(CUmultiGPULAPACKhandle handle, int prec, int uplo, size_t n, void *A, size_t lda, long *info) {
+  if (handle == NULL || A == NULL) return CUDA_ERROR_INVALID_VALUE;
   CUmultiGPU m = handle->mgpu;
   const int P = m->n;
   potrf_args *args = calloc((size_t)P, sizeof *args);

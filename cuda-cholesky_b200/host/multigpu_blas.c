@@ -181,6 +181,7 @@ static CUresult mb_task(const void *argp) {
 }
 
 static CUresult mb_run(CUmultiGPU m, mb_args *proto) {
+  if (m == NULL) return CUDA_ERROR_INVALID_VALUE;
   const int P = cuMultiGPUGetContextCount(m);
   mb_args *args = calloc((size_t)P, sizeof *args);
   mb_args **ptrs = calloc((size_t)P, sizeof *ptrs);
@@ -197,6 +198,222 @@ static CUresult mb_run(CUmultiGPU m, mb_args *proto) {
   free(args);
   free(ptrs);
   return e;
+}
+
+/* =============================================================================================
+ * Slab-distributed TRTRI / LAUUM / POTRI on host pointers (CHOL_MGPU_INVERSE=slab; the default
+ * still stages the whole matrix on the first GPU until this path has been verified on hardware).
+ *
+ * Both operations split by output slab with no GPU-to-GPU exchange:
+ *   TRTRI lower: columns J = [lo,hi) of inv(L) depend on T = L[lo:n, lo:n] only:
+ *                  X11 = inv(T11)            (blocked TRTRI of the w x w diagonal block)
+ *                  X21 = -inv(T22) (T21 X11) (TRMM2 then TRSM)
+ *         upper: columns J of inv(U) depend on T = U[0:hi, 0:hi]:  X22 = inv(T22), X12 = -inv(T11) (T12 X22)
+ *   LAUUM lower: rows I = [lo,hi) of L^H L are (L[lo:n, I])^H L[lo:n, 0:hi)   (the block-row step of
+ *                chol_lauum with ib = hi-lo), upper: columns I of U U^H are U[0:hi, lo:n] (U[I, lo:n])^H.
+ * Every slab READS parts of the matrix that other slabs WRITE, so all uploads finish (phase 1)
+ * before any result is downloaded (phase 2).  Slab boundaries equalise the work (cubic / quadratic
+ * cost profiles), in multiples of 64.  POTRI runs the two operations back to back through the
+ * host matrix.  CHOL_MGPU_INVERSE_SLABS=k gives every GPU k slabs (tests: several slabs on one GPU).
+ * ===========================================================================================*/
+typedef struct {
+  int op, prec, uplo, diag;
+  CULAPACKhandle lap;
+  size_t n, lda, lo, hi;
+  char *A;
+  CUdeviceptr dT, dY, dD;
+  long info;
+} inv_slab;
+
+typedef struct {
+  inv_slab *slabs;
+  int nslabs, rank, nranks, phase;
+} inv_job;
+
+static const double ONE[2] = {1.0, 0.0};
+static const double ZERO[2] = {0.0, 0.0};
+static const double MONE[2] = {-1.0, 0.0};
+
+int chol_inverse_slabs_enabled(void) {
+  const char *e = getenv("CHOL_MGPU_INVERSE");
+  return e != NULL && strcmp(e, "slab") == 0;
+}
+
+/* cost profile over the split dimension: 0 -> (n-x)^2, 1 -> x^2, 2 -> x (n-x) */
+void chol_inverse_slab_bounds(int profile, size_t n, int nslabs, size_t *bounds /* nslabs + 1 */) {
+  const size_t g = 64, nblk = (n + g - 1) / g;
+  double total = 0.0;
+  for (size_t b = 0; b < nblk; b++) {
+    const double x = (double)chol_min(n, b * g + g / 2), len = (double)(chol_min(n, (b + 1) * g) - b * g);
+    const double d = profile == 0 ? ((double)n - x) * ((double)n - x) : (profile == 1 ? x * x : x * ((double)n - x));
+    total += (d + 1.0) * len;
+  }
+  bounds[0] = 0;
+  int r = 1;
+  double acc = 0.0;
+  for (size_t b = 0; b < nblk && r < nslabs; b++) {
+    const double x = (double)chol_min(n, b * g + g / 2), len = (double)(chol_min(n, (b + 1) * g) - b * g);
+    const double d = profile == 0 ? ((double)n - x) * ((double)n - x) : (profile == 1 ? x * x : x * ((double)n - x));
+    acc += (d + 1.0) * len;
+    while (r < nslabs && acc >= total * (double)r / (double)nslabs) bounds[r++] = chol_min(n, (b + 1) * g);
+  }
+  while (r <= nslabs) bounds[r++] = n;
+}
+
+static CUresult inv_upload(inv_slab *a, CUstream st) {
+  const size_t es = chol_esize(a->prec), n = a->n, lo = a->lo, hi = a->hi, w = hi - lo;
+  if (w == 0) return CUDA_SUCCESS;
+  if (a->op == OP_TRTRI) {
+    /* T = the uplo triangle of A[o:o+s, o:o+s], uploaded as block-column trapezoids */
+    const size_t o = a->uplo == 'L' ? lo : 0, s = a->uplo == 'L' ? n - lo : hi, ldt = chol_roundup(s, 16), bw = 2048;
+    CU_ERROR_CHECK(cuMemAlloc(&a->dT, ldt * s * es));
+    for (size_t c0 = 0; c0 < s; c0 += bw) {
+      const size_t cb = chol_min(bw, s - c0);
+      const size_t r0 = a->uplo == 'L' ? c0 : 0, rows = a->uplo == 'L' ? s - c0 : c0 + cb;
+      CU_ERROR_CHECK(h2d(a->A + ((o + c0) * a->lda + o + r0) * es, a->lda, chol_at(a->dT, ldt, r0, c0, es), ldt, rows, cb, es, st));
+    }
+    const size_t r = s - w;
+    if (r) CU_ERROR_CHECK(cuMemAlloc(&a->dY, chol_roundup(r, 16) * w * es));
+  } else { /* LAUUM: lower R = A[lo:n, 0:hi) (k x hi), upper R = A[0:hi, lo:n) (hi x k) */
+    const size_t k = n - lo;
+    const size_t rows = a->uplo == 'L' ? k : hi, cols = a->uplo == 'L' ? hi : k, ldr = chol_roundup(rows, 16);
+    CU_ERROR_CHECK(cuMemAlloc(&a->dT, ldr * cols * es));
+    CU_ERROR_CHECK(h2d(a->uplo == 'L' ? a->A + lo * es : a->A + lo * a->lda * es, a->lda, a->dT, ldr, rows, cols, es, st));
+    if (lo) CU_ERROR_CHECK(cuMemAlloc(&a->dY, chol_roundup(a->uplo == 'L' ? w : lo, 16) * (a->uplo == 'L' ? lo : w) * es));
+    CU_ERROR_CHECK(cuMemAlloc(&a->dD, chol_roundup(w, 16) * w * es));
+  }
+  return CUDA_SUCCESS;
+}
+
+/* the uplo triangle (diagonal included) of a w x w device block -> the caller's matrix */
+static CUresult inv_download_triangle(const inv_slab *a, CUdeviceptr D, size_t ldd, CUstream st) {
+  const size_t es = chol_esize(a->prec), lo = a->lo, w = a->hi - a->lo;
+  for (size_t c = 0; c < w; c++) {
+    const size_t r0 = a->uplo == 'L' ? c : 0, cnt = a->uplo == 'L' ? w - c : c + 1;
+    CU_ERROR_CHECK(cuMemcpyDtoHAsync(a->A + ((lo + c) * a->lda + lo + r0) * es, chol_at(D, ldd, r0, c, es), cnt * es, st));
+  }
+  return CUDA_SUCCESS;
+}
+
+static CUresult inv_compute(inv_slab *a, CUstream st) {
+  const int prec = a->prec, uplo = a->uplo;
+  const size_t es = chol_esize(prec), n = a->n, lo = a->lo, hi = a->hi, w = hi - lo;
+  if (w == 0) return CUDA_SUCCESS;
+  if (a->op == OP_TRTRI) {
+    const size_t s = uplo == 'L' ? n - lo : hi, ldt = chol_roundup(s, 16), r = s - w, ldy = chol_roundup(r ? r : 1, 16);
+    const size_t d0 = uplo == 'L' ? 0 : lo;  /* position of the w x w diagonal block inside T */
+    const size_t t0 = uplo == 'L' ? w : 0;   /* position of the other (r x r) triangle */
+    const CUdeviceptr Tww = chol_at(a->dT, ldt, d0, d0, es), Trr = chol_at(a->dT, ldt, t0, t0, es);
+    const CUdeviceptr Trw = uplo == 'L' ? chol_at(a->dT, ldt, w, 0, es) : chol_at(a->dT, ldt, 0, lo, es); /* r x w */
+    long info = 0;
+    CU_ERROR_CHECK(chol_trtri(a->lap, prec, uplo, a->diag, w, Tww, ldt, &info));
+    if (info > 0) {
+      a->info = (long)lo + info;
+      return CUDA_SUCCESS; /* this slab is left untouched, like the block the reference stops in */
+    }
+    if (r) {
+      CU_ERROR_CHECK(chol_trmm2(prec, 'R', uplo, 'N', a->diag, r, w, ONE, Tww, ldt, Trw, ldt, a->dY, ldy, st));
+      CU_ERROR_CHECK(chol_trsm(a->lap->blas_handle, prec, 'L', uplo, 'N', a->diag, r, w, MONE, Trr, ldt, a->dY, ldy, st));
+      CU_ERROR_CHECK(d2h(a->A + (lo * a->lda + (uplo == 'L' ? hi : 0)) * es, a->lda, a->dY, ldy, r, w, es, st));
+    }
+    CU_ERROR_CHECK(inv_download_triangle(a, Tww, ldt, st));
+  } else {
+    const int herm = chol_is_complex(prec);
+    const size_t k = n - lo, ldd = chol_roundup(w, 16);
+    if (uplo == 'L') {
+      const size_t ldr = chol_roundup(k, 16), ldy = chol_roundup(w, 16);
+      const CUdeviceptr Aii = chol_at(a->dT, ldr, 0, lo, es);
+      if (lo) {
+        CU_ERROR_CHECK(chol_gemm_ex(prec, 'C', 'N', 'L', 0, 0, 0, 0, 0, w, lo, k, ONE, Aii, ldr, a->dT, ldr, ZERO, 0, 0, a->dY, ldy, st));
+        CU_ERROR_CHECK(d2h(a->A + lo * es, a->lda, a->dY, ldy, w, lo, es, st));
+      }
+      CU_ERROR_CHECK(chol_gemm_ex(prec, 'C', 'N', 'L', 0, 'L', 0, 'L', herm, w, w, k, ONE, Aii, ldr, Aii, ldr, ZERO, 0, 0, a->dD, ldd, st));
+    } else {
+      const size_t ldr = chol_roundup(hi, 16), ldy = chol_roundup(lo ? lo : 1, 16);
+      const CUdeviceptr Aii = chol_at(a->dT, ldr, lo, 0, es);
+      if (lo) {
+        CU_ERROR_CHECK(chol_gemm_ex(prec, 'N', 'C', 0, 0, 'U', 0, 0, 0, lo, w, k, ONE, a->dT, ldr, Aii, ldr, ZERO, 0, 0, a->dY, ldy, st));
+        CU_ERROR_CHECK(d2h(a->A + lo * a->lda * es, a->lda, a->dY, ldy, lo, w, es, st));
+      }
+      CU_ERROR_CHECK(chol_gemm_ex(prec, 'N', 'C', 'U', 0, 'U', 0, 'U', herm, w, w, k, ONE, Aii, ldr, Aii, ldr, ZERO, 0, 0, a->dD, ldd, st));
+    }
+    CU_ERROR_CHECK(inv_download_triangle(a, a->dD, ldd, st));
+  }
+  return CUDA_SUCCESS;
+}
+
+/* phase 0: upload, 1: compute + download, 2: release; a rank handles slabs rank, rank+P, ... */
+static CUresult inv_task(const void *argp) {
+  const inv_job *job = *(inv_job *const *)argp;
+  CUresult first = CUDA_SUCCESS;
+  for (int v = job->rank; v < job->nslabs; v += job->nranks) {
+    inv_slab *a = &job->slabs[v];
+    CUstream st = a->lap->s_update;
+    CUresult e = CUDA_SUCCESS;
+    if (job->phase == 0) e = inv_upload(a, st);
+    else if (job->phase == 1) e = inv_compute(a, st);
+    else {
+      if (a->dT) cuMemFree(a->dT);
+      if (a->dY) cuMemFree(a->dY);
+      if (a->dD) cuMemFree(a->dD);
+      a->dT = a->dY = a->dD = 0;
+    }
+    if (job->phase != 2) {
+      const CUresult es2 = cuStreamSynchronize(st);
+      if (e == CUDA_SUCCESS) e = es2;
+    }
+    if (first == CUDA_SUCCESS) first = e;
+  }
+  return first;
+}
+
+static CUresult inv_run_op(CUmultiGPU m, int op, int prec, int uplo, int diag, size_t n, char *A, size_t lda, long *info) {
+  const int P = cuMultiGPUGetContextCount(m);
+  const char *ev = getenv("CHOL_MGPU_INVERSE_SLABS");
+  const int per = (ev != NULL && atoi(ev) > 0) ? atoi(ev) : 1, V = P * per;
+  inv_slab *slabs = calloc((size_t)V, sizeof *slabs);
+  inv_job *jobs = calloc((size_t)P, sizeof *jobs);
+  inv_job **ptrs = calloc((size_t)P, sizeof *ptrs);
+  size_t *bounds = calloc((size_t)V + 1, sizeof *bounds);
+  if (!slabs || !jobs || !ptrs || !bounds) {
+    free(slabs); free(jobs); free(ptrs); free(bounds);
+    return CUDA_ERROR_OUT_OF_MEMORY;
+  }
+  chol_inverse_slab_bounds(op == OP_LAUUM ? 2 : (uplo == 'L' ? 0 : 1), n, V, bounds);
+  for (int v = 0; v < V; v++) {
+    slabs[v].op = op; slabs[v].prec = prec; slabs[v].uplo = uplo; slabs[v].diag = diag;
+    slabs[v].lap = chol_mgpu_rank_lapack(m, v % P);
+    slabs[v].n = n; slabs[v].lda = lda; slabs[v].A = A;
+    slabs[v].lo = bounds[v]; slabs[v].hi = bounds[v + 1];
+  }
+  CUresult e = CUDA_SUCCESS;
+  for (int phase = 0; phase < 3; phase++) {
+    if (phase == 1 && e != CUDA_SUCCESS) continue; /* a failed upload: skip the compute, still release */
+    for (int i = 0; i < P; i++) {
+      jobs[i].slabs = slabs; jobs[i].nslabs = V; jobs[i].rank = i; jobs[i].nranks = P; jobs[i].phase = phase;
+      ptrs[i] = &jobs[i];
+    }
+    const CUresult pe = chol_mgpu_run_on_all(m, inv_task, ptrs, sizeof(*ptrs), sizeof(*ptrs));
+    if (e == CUDA_SUCCESS) e = pe;
+  }
+  /* the reference reports the first zero pivot its sweep meets: bottom-up for lower, top-down for upper */
+  long found = 0;
+  for (int v = 0; v < V; v++)
+    if (slabs[v].info > 0 && (found == 0 || (uplo == 'L' ? slabs[v].info > found : slabs[v].info < found))) found = slabs[v].info;
+  *info = found;
+  free(slabs); free(jobs); free(ptrs); free(bounds);
+  return e;
+}
+
+CUresult chol_mgpu_inverse_slabs(CUmultiGPU m, int op, int prec, int uplo, int diag, size_t n, void *A, size_t lda, long *info) {
+  if (m == NULL) return CUDA_ERROR_INVALID_VALUE;
+  *info = 0;
+  if (op == OP_POTRI) {
+    CU_ERROR_CHECK(inv_run_op(m, OP_TRTRI, prec, uplo, 'N', n, (char *)A, lda, info));
+    if (*info != 0) return CUDA_SUCCESS;
+    return inv_run_op(m, OP_LAUUM, prec, uplo, 'N', n, (char *)A, lda, info);
+  }
+  return inv_run_op(m, op, prec, uplo, diag, n, (char *)A, lda, info);
 }
 
 #define CHECK_ARG(cond, pos)                \
@@ -286,6 +503,8 @@ static CUresult mb_run(CUmultiGPU m, mb_args *proto) {
     if (n == 0) return CUDA_SUCCESS;                                                                                   \
     mb_args a;                                                                                                         \
     memset(&a, 0, sizeof a);                                                                                           \
+    if (chol_inverse_slabs_enabled())                                                                                  \
+      return chol_mgpu_inverse_slabs(chol_mgpu_of_lapack(h), OP_TRTRI, p, uplo, diag, n, A, lda, info);                \
     a.op = OP_TRTRI; a.prec = p; a.uplo = uplo; a.diag = diag; a.n = n;                                                \
     a.A = (const char *)A; a.lda = lda; a.C = (char *)A; a.ldc = lda;                                                  \
     const CUresult e = mb_run(chol_mgpu_of_lapack(h), &a);                                                             \
@@ -299,6 +518,8 @@ static CUresult mb_run(CUmultiGPU m, mb_args *proto) {
     if (n == 0) return CUDA_SUCCESS;                                                                                   \
     mb_args a;                                                                                                         \
     memset(&a, 0, sizeof a);                                                                                           \
+    if (chol_inverse_slabs_enabled())                                                                                  \
+      return chol_mgpu_inverse_slabs(chol_mgpu_of_lapack(h), OP_LAUUM, p, uplo, 'N', n, A, lda, info);                 \
     a.op = OP_LAUUM; a.prec = p; a.uplo = uplo; a.n = n;                                                               \
     a.A = (const char *)A; a.lda = lda; a.C = (char *)A; a.ldc = lda;                                                  \
     const CUresult e = mb_run(chol_mgpu_of_lapack(h), &a);                                                             \
@@ -312,6 +533,8 @@ static CUresult mb_run(CUmultiGPU m, mb_args *proto) {
     if (n == 0) return CUDA_SUCCESS;                                                                                   \
     mb_args a;                                                                                                         \
     memset(&a, 0, sizeof a);                                                                                           \
+    if (chol_inverse_slabs_enabled())                                                                                  \
+      return chol_mgpu_inverse_slabs(chol_mgpu_of_lapack(h), OP_POTRI, p, uplo, 'N', n, A, lda, info);                 \
     a.op = OP_POTRI; a.prec = p; a.uplo = uplo; a.n = n;                                                               \
     a.A = (const char *)A; a.lda = lda; a.C = (char *)A; a.ldc = lda;                                                  \
     const CUresult e = mb_run(chol_mgpu_of_lapack(h), &a);                                                             \

@@ -86,6 +86,50 @@ def test_staged_multigpu_potrf_upload_overlap(mgpu, n, gbps, monkeypatch):
     assert np.array_equal(np.triu(got, 1), np.triu(A, 1))
 
 
+@staged
+@pytest.mark.parametrize("p", "dzs")
+@pytest.mark.parametrize("uplo", "LU")
+@pytest.mark.parametrize("n,slabs", [(400, 1), (400, 3), (1500, 4)])
+def test_staged_multigpu_inverse_slabs(mgpu, p, uplo, n, slabs, monkeypatch):
+    """CHOL_MGPU_INVERSE=slab: TRTRI / LAUUM / POTRI split into independent slabs (several per GPU
+    here, so one GPU exercises the slab algebra) against the oracle, other triangle untouched."""
+    monkeypatch.setenv("CHOL_MGPU_INVERSE", "slab")
+    monkeypatch.setenv("CHOL_MGPU_INVERSE_SLABS", str(slabs))
+    A = H.spd_matrix(p, n, k=64)
+    ORA.potrf(p, uplo, A)
+    cases = [("trtri", "N"), ("trtri", "U"), ("lauum", None), ("potri", None)]
+    for name, diag in cases:
+        want = A.copy(order="F")
+        got = A.copy(order="F")
+        if name == "trtri":
+            ORA.trtri(p, uplo, diag, want)
+            assert mgpu.trtri(p, uplo, diag, n, got.ctypes.data, n) == 0
+        else:
+            getattr(ORA, name)(p, uplo, want)
+            assert getattr(mgpu, name)(p, uplo, n, got.ctypes.data, n) == 0
+        assert np.abs(H.tri(got, uplo) - H.tri(want, uplo)).max() <= 64 * n * H.eps(p) * np.abs(H.tri(want, uplo)).max(), (name, diag)
+        other = np.triu(got, 1) if uplo == "L" else np.tril(got, -1)
+        other0 = np.triu(A, 1) if uplo == "L" else np.tril(A, -1)
+        assert np.array_equal(other, other0), (name, diag)
+
+
+@staged
+@pytest.mark.parametrize("uplo", "LU")
+def test_staged_multigpu_inverse_slabs_zero_pivot(mgpu, uplo, monkeypatch):
+    monkeypatch.setenv("CHOL_MGPU_INVERSE", "slab")
+    monkeypatch.setenv("CHOL_MGPU_INVERSE_SLABS", "3")
+    n = 600
+    A = H.spd_matrix("d", n, k=64)
+    ORA.potrf("d", uplo, A)
+    A[100, 100] = 0.0
+    A[450, 450] = 0.0
+    want = A.copy(order="F")
+    winfo = ORA.trtri("d", uplo, "N", want)
+    got = A.copy(order="F")
+    assert mgpu.trtri("d", uplo, "N", n, got.ctypes.data, n) == winfo
+    assert winfo == (451 if uplo == "L" else 101)
+
+
 def test_multigpu_potrf_info_and_args(mgpu):
     G.chol.set_xerbla_silent()
     n = 900

@@ -174,3 +174,22 @@ def test_multiprocess_host_logic_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=240)[0].decode() for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0 and "OK" in o, o
+
+
+@pytest.mark.parametrize("profile", [0, 1, 2])
+@pytest.mark.parametrize("n,nslabs", [(1, 1), (63, 3), (400, 3), (1500, 4), (32768, 8), (65536, 5)])
+def test_inverse_slab_bounds_cover_and_balance(profile, n, nslabs):
+    """Slab boundaries of the distributed TRTRI / LAUUM: monotone, multiples of 64 (except n itself),
+    cover [0, n) exactly, and equalise the cost profile when the matrix is large enough."""
+    lib = chol.lib()
+    b = (C.c_size_t * (nslabs + 1))()
+    lib.chol_inverse_slab_bounds(C.c_int(profile), C.c_size_t(n), C.c_int(nslabs), b)
+    b = list(b)
+    assert b[0] == 0 and b[-1] == n
+    assert all(b[i] <= b[i + 1] for i in range(nslabs))
+    assert all(x % 64 == 0 or x == n for x in b)
+    if n >= 32768:
+        x = np.arange(n) + 0.5
+        dens = [(n - x) ** 2, x ** 2, x * (n - x)][profile]
+        work = np.array([dens[b[i]:b[i + 1]].sum() for i in range(nslabs)])
+        assert work.max() <= 1.06 * work.mean()
