@@ -190,6 +190,14 @@ class LapackHandle:
                                   C.c_size_t(lda), C.byref(info)), allow_invalid)
         return (info.value, rc) if allow_invalid else info.value
 
+    def potrs(self, p, uplo, n, nrhs, A, lda, B, ldb, allow_invalid=False):
+        """Solve A X = B in place from the factor left by potrf (extension, include/cholesky_b200.h)."""
+        f = getattr(lib(), "cu%spotrs" % _U[p])
+        info = C.c_long(0)
+        rc = _check(f.__name__, f(self.h, C.c_int(ord(uplo)), C.c_size_t(n), C.c_size_t(nrhs), C.c_void_p(A), C.c_size_t(lda),
+                                  C.c_void_p(B), C.c_size_t(ldb), C.byref(info)), allow_invalid)
+        return (info.value, rc) if allow_invalid else info.value
+
     def trti22(self, p, uplo, diag, n, A, lda, B, ldb, dinfo, stream=0):
         f = getattr(lib(), "cu%strti22" % _U[p])
         return _check(f.__name__, f(self.h, C.c_int(ord(uplo)), C.c_int(ord(diag)), C.c_size_t(n), C.c_void_p(A),

@@ -127,6 +127,8 @@ CUresult chol_potrf(CULAPACKhandle h, int prec, int uplo, size_t n, CUdeviceptr 
 CUresult chol_trtri(CULAPACKhandle h, int prec, int uplo, int diag, size_t n, CUdeviceptr A, size_t lda, long *info);
 CUresult chol_lauum(CULAPACKhandle h, int prec, int uplo, size_t n, CUdeviceptr A, size_t lda, long *info);
 CUresult chol_potri(CULAPACKhandle h, int prec, int uplo, size_t n, CUdeviceptr A, size_t lda, long *info);
+CUresult chol_potrs(CULAPACKhandle h, int prec, int uplo, size_t n, size_t nrhs, CUdeviceptr A, size_t lda, CUdeviceptr B,
+                    size_t ldb);
 CUresult chol_logdet(CULAPACKhandle h, int prec, CUdeviceptr x, size_t incx, size_t n, void *result, CUstream stream);
 
 #endif

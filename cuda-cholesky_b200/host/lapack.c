@@ -359,6 +359,22 @@ CUresult chol_potri(CULAPACKhandle h, int prec, int uplo, size_t n, CUdeviceptr 
   return chol_lauum(h, prec, uplo, n, A, lda, info);
 }
 
+/* Solve A X = B from the Cholesky factor (the reference stops at POTRI):
+ * lower  L Y = B then L^H X = Y,  upper  U^H Y = B then U X = Y - two blocked TRSMs on the update stream. */
+static CUresult potrs_body(CULAPACKhandle h, int prec, int uplo, size_t n, size_t nrhs, CUdeviceptr A, size_t lda,
+                           CUdeviceptr B, size_t ldb) {
+  CUstream st = h->s_update;
+  const int first = (uplo == 'L') ? 'N' : 'C', second = (uplo == 'L') ? 'C' : 'N';
+  CU_ERROR_CHECK(chol_trsm(h->blas_handle, prec, 'L', uplo, first, 'N', n, nrhs, ONE, A, lda, B, ldb, st));
+  CU_ERROR_CHECK(chol_trsm(h->blas_handle, prec, 'L', uplo, second, 'N', n, nrhs, ONE, A, lda, B, ldb, st));
+  CU_ERROR_CHECK(cuStreamSynchronize(st));
+  return CUDA_SUCCESS;
+}
+CUresult chol_potrs(CULAPACKhandle h, int prec, int uplo, size_t n, size_t nrhs, CUdeviceptr A, size_t lda, CUdeviceptr B,
+                    size_t ldb) {
+  IN_HANDLE_CONTEXT(h, potrs_body(h, prec, uplo, n, nrhs, A, lda, B, ldb));
+}
+
 static CUresult logdet_body(CULAPACKhandle h, int prec, CUdeviceptr x, size_t incx, size_t n, void *result, CUstream stream) {
   const size_t rs = (prec == 's' || prec == 'c') ? 4 : 8;
   const CUdeviceptr dres = h->logdet_scr + (CUdeviceptr)chol_roundup(chol_logdet_scratch_bytes(), 16);
@@ -420,6 +436,15 @@ CUresult chol_logdet(CULAPACKhandle h, int prec, CUdeviceptr x, size_t incx, siz
     LAPACK_ARG(lda < n, 4);                                                                                          \
     if (n == 0) return CUDA_SUCCESS;                                                                                 \
     return chol_potri(h, p, uplo, n, A, lda, info);                                                                  \
+  }                                                                                                                  \
+  CUresult cu##U##potrs(CULAPACKhandle h, CBlasUplo uplo, size_t n, size_t nrhs, CUdeviceptr A, size_t lda,          \
+                        CUdeviceptr B, size_t ldb, long *info) {                                                     \
+    *info = 0;                                                                                                       \
+    if (h == NULL) return CUDA_ERROR_INVALID_VALUE;                                                                  \
+    LAPACK_ARG(lda < n, 5);                                                                                          \
+    LAPACK_ARG(ldb < n, 7);                                                                                          \
+    if (n == 0 || nrhs == 0) return CUDA_SUCCESS;                                                                    \
+    return chol_potrs(h, p, uplo, n, nrhs, A, lda, B, ldb);                                                          \
   }                                                                                                                  \
   CUresult cu##U##logdet(CULAPACKhandle h, CUdeviceptr x, size_t incx, size_t n, REAL *result, CUstream stream) {    \
     if (h == NULL || result == NULL) return CUDA_ERROR_INVALID_VALUE;                                                \

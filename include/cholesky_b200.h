@@ -59,6 +59,17 @@ CUresult cholDistCpotrf(cholDist, size_t n, CUdeviceptr Aloc, size_t ldl, long *
 CUresult cholDistZpotrf(cholDist, size_t n, CUdeviceptr Aloc, size_t ldl, long *info);
 
 /* ---------------------------------------------------------------------------------------------
+ * POTRS: solve A X = B for n x nrhs right-hand sides from the Cholesky factor cu*potrf left in A
+ * (the natural consumer of the factor; the reference stops at POTRI).  B is overwritten by X.
+ * Device pointers, column-major.  *info = -5 (lda < n) or -7 (ldb < n), else 0.  Returns after the
+ * device work has completed.
+ * ------------------------------------------------------------------------------------------- */
+CUresult cuSpotrs(CULAPACKhandle, CBlasUplo, size_t n, size_t nrhs, CUdeviceptr A, size_t lda, CUdeviceptr B, size_t ldb, long *info);
+CUresult cuDpotrs(CULAPACKhandle, CBlasUplo, size_t n, size_t nrhs, CUdeviceptr A, size_t lda, CUdeviceptr B, size_t ldb, long *info);
+CUresult cuCpotrs(CULAPACKhandle, CBlasUplo, size_t n, size_t nrhs, CUdeviceptr A, size_t lda, CUdeviceptr B, size_t ldb, long *info);
+CUresult cuZpotrs(CULAPACKhandle, CBlasUplo, size_t n, size_t nrhs, CUdeviceptr A, size_t lda, CUdeviceptr B, size_t ldb, long *info);
+
+/* ---------------------------------------------------------------------------------------------
  * Tuning / measurement hooks
  * ------------------------------------------------------------------------------------------- */
 /* outer block size of the LAPACK drivers (k of the trailing update); 0 = built-in default

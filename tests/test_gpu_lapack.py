@@ -219,3 +219,39 @@ def test_potrf_full_elementwise_vs_oracle_mid_size(lapack, p, uplo, n):
     got = G.to_host(dA, n)
     err = np.abs(H.tri(got, uplo) - H.tri(want, uplo)).max() / np.abs(want).max()
     assert err <= elem_tol(p, n), err
+
+
+@H.staged
+@pytest.mark.parametrize("p", "dzsc")
+@pytest.mark.parametrize("uplo", "LU")
+@pytest.mark.parametrize("n,nrhs", [(1, 1), (100, 7), (300, 64), (700, 130)])
+def test_staged_potrs_solves_the_system(lapack, p, uplo, n, nrhs):
+    """cu*potrs (extension): X from the GPU factor against the oracle's two triangular solves on the
+    oracle's factor, and the residual ||A X - B|| / (||A|| ||X||)."""
+    A0 = H.spd_matrix(p, n, k=min(n, 64))
+    B0 = H.rand_matrix(p, n, nrhs, seed=11, ld=n + 2)
+    F = A0.copy(order="F")
+    assert ORA.potrf(p, uplo, F) == 0
+    want = B0.copy(order="F")
+    hT = "C" if PREC[p]["cplx"] else "T"
+    for trans in (("N", hT) if uplo == "L" else (hT, "N")):
+        ORA.trsm(p, "L", uplo, trans, "N", n, nrhs, 1.0, F, want)
+    dA, lda = G.to_dev(A0)
+    dB, ldb = G.to_dev(B0)
+    assert lapack.potrf(p, uplo, n, dA.data_ptr(), lda) == 0
+    assert lapack.potrs(p, uplo, n, nrhs, dA.data_ptr(), lda, dB.data_ptr(), ldb) == 0
+    got = G.to_host(dB, n)[:, :nrhs]
+    assert np.abs(got - want[:, :nrhs]).max() <= 64 * n * H.eps(p) * np.abs(want).max()
+    wide = np.complex128 if PREC[p]["cplx"] else np.float64
+    R = A0.astype(wide) @ got.astype(wide) - B0[:, :nrhs].astype(wide)
+    assert np.linalg.norm(R) <= 16 * n * H.eps(p) * np.linalg.norm(A0) * np.linalg.norm(got)
+
+
+@H.staged
+def test_staged_potrs_argument_errors(lapack):
+    G.chol.set_xerbla_silent()
+    A = H.spd_matrix("d", 8)
+    dA, lda = G.to_dev(A)
+    assert lapack.potrs("d", "L", 16, 1, dA.data_ptr(), 8, dA.data_ptr(), 16, allow_invalid=True) == (-5, 1)
+    assert lapack.potrs("d", "L", 8, 1, dA.data_ptr(), lda, dA.data_ptr(), 4, allow_invalid=True) == (-7, 1)
+    assert lapack.potrs("d", "L", 0, 3, dA.data_ptr(), lda, dA.data_ptr(), lda) == 0

@@ -61,10 +61,7 @@ def test_multigpu_potrf_pinned_host_overlapped_gather(mgpu, uplo):
     assert np.array_equal(other, other0)
 
 
-# Code paths written after the round's GPU budget was spent: they are off by default in the library
-# (environment switches) and their tests run only on request, so that the first GPU session can
-# verify them in one go:  CHOL_TEST_STAGED=1 python -m pytest tests -m gpu -k staged
-staged = pytest.mark.skipif(os.environ.get("CHOL_TEST_STAGED") != "1", reason="not yet verified on hardware; CHOL_TEST_STAGED=1 runs it")
+staged = H.staged
 
 
 @staged
