@@ -1,0 +1,38 @@
+#!/bin/bash
+# First GPU call after a CPU-only stretch: verify everything that was written without hardware
+# (tests marked `staged`, library paths behind environment switches) and A/B it, in ONE gpurun call.
+#   gpurun --timeout 1500 -- 'bash scripts/verify_staged.sh'
+# Every step runs under its own `timeout`; results land in gpurun_out/staged_*.
+set -u
+cd "$(dirname "$0")/.."
+OUT=gpurun_out
+mkdir -p $OUT
+
+echo "== staged tests ==" | tee $OUT/staged_summary.txt
+CHOL_TEST_STAGED=1 timeout 600 python -m pytest tests -m gpu -k staged -q -x > $OUT/staged_tests.log 2>&1
+echo "staged tests rc=$?" | tee -a $OUT/staged_summary.txt
+tail -5 $OUT/staged_tests.log | tee -a $OUT/staged_summary.txt
+
+echo "== regular gpu tests (default paths were refactored on the host side) ==" | tee -a $OUT/staged_summary.txt
+timeout 900 python -m pytest tests -m gpu -q -x > $OUT/staged_gpu_tests.log 2>&1
+echo "gpu tests rc=$?" | tee -a $OUT/staged_summary.txt
+tail -3 $OUT/staged_gpu_tests.log | tee -a $OUT/staged_summary.txt
+
+echo "== e2e A/B: upload overlapped with the factorisation ==" | tee -a $OUT/staged_summary.txt
+for N in 32768 65536; do
+  for OV in 0 1; do
+    CHOL_MGPU_H2D_OVERLAP=$OV timeout 400 python bench.py --order $N --steps 1 --warmup 3 --e2e-steps 2 --skip-cpu-baseline \
+      > $OUT/staged_e2e_n${N}_ov${OV}.json 2> $OUT/staged_e2e_n${N}_ov${OV}.err
+    python - "$OUT/staged_e2e_n${N}_ov${OV}.json" $N $OV <<'PY' | tee -a $OUT/staged_summary.txt
+import json, sys
+try:
+    d = json.loads([l for l in open(sys.argv[1]) if l.startswith("{")][-1])
+    print("N=%s overlap=%s value=%.0f e2e=%.0f GFLOP/s info=%s" % (sys.argv[2], sys.argv[3], d["value"], d["e2e"]["value"], d["e2e"]["info"]))
+except Exception as e:
+    print("N=%s overlap=%s FAILED %r" % (sys.argv[2], sys.argv[3], e))
+PY
+  done
+done
+
+echo "== host-pointer POTRI: staged on one GPU vs slab-distributed ==" | tee -a $OUT/staged_summary.txt
+timeout 600 python scripts/mgpu_inverse_ab.py 2>&1 | tee -a $OUT/staged_summary.txt
