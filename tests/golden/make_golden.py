@@ -16,8 +16,33 @@ import harness as H  # noqa: E402
 ROOT = H.ROOT
 
 
+def latmc_golden():
+    """4. the reference's own test inputs: {s,d,c,z}latmc(n, c = 2) after srand(0) (what every reference
+    LAPACK test factors, test/lapack/dpotrf.c:56) from the reference's generator, and the reference's
+    CPU potrf of them, both triangles."""
+    exe = os.path.join(H.ORACLE_DIR, "_ref", "pin_latmc")
+    subprocess.check_call(["gcc", "-std=c99", "-O2", "-w", "-I/root/reference/test/lapack/util",
+                           os.path.join(H.ORACLE_DIR, "pin_latmc.c"), "-o", exe, "-lm"])
+    REF = H.CpuLib("ref")
+    d = {}
+    for p in "sdcz":
+        for n in (2, 64):
+            raw = subprocess.check_output([exe, p, str(n), "2.0", "0"])
+            A = np.frombuffer(raw, dtype=H.PREC[p]["np"]).reshape(n, n).T
+            d["%s_%d_A" % (p, n)] = np.ascontiguousarray(A)
+            for uplo in "LU":
+                F = H.fmat(n, n, H.PREC[p]["np"])
+                F[:, :] = A
+                assert REF.potrf(p, uplo, F) == 0
+                d["%s_%d_%s" % (p, n, uplo)] = np.ascontiguousarray(H.tri(F, uplo))
+    np.savez_compressed(os.path.join(HERE, "latmc.npz"), **d)
+
+
 def main():
     subprocess.check_call(["make", "-C", H.ORACLE_DIR, "ref", "oracle"])
+    if "--only-latmc" in sys.argv:
+        latmc_golden()
+        return
     # 1. dSFMT-19937: compile the reference's rng/dsfmt_19937.c behind oracle/pin_dsfmt.c
     exe = os.path.join(H.ORACLE_DIR, "_ref", "pin_dsfmt")
     subprocess.check_call(["gcc", "-O2", "-msse2", "-w", "-I/root/reference/rng",
@@ -45,6 +70,7 @@ def main():
         REF.potri("d", uplo, A)
         d["potri_" + uplo] = np.ascontiguousarray(H.tri(A, uplo))
     np.savez_compressed(os.path.join(HERE, "potri_logdet_d.npz"), **d)
+    latmc_golden()
     print("golden written to", HERE)
 
 

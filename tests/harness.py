@@ -206,6 +206,48 @@ def spd_matrix(p, n, seed=SEED, ld=None, k=None):
     return A
 
 
+_LIBC = None
+
+
+def latmc(p, n, c=2.0, ld=None, seed=0):
+    """The reference's own test-matrix generator (test/lapack/util/{s,d,c,z}latmc.c:11-70): SPD / HPD
+    with condition number c - a diagonal with entries in [1, c] (1 and c forced at (0,0), (1,1)),
+    then one similarity  A -= u w^H + w u^H  with a random vector u (w = t v - s u, v = A u,
+    t = 2 / u^H u, s = t^2 u^H v / 2).  Random numbers are libc rand() after srand(seed), drawn in
+    the reference's order; every reference LAPACK test uses c = 2 and srand(0)."""
+    global _LIBC
+    if n < 2:
+        raise ValueError("latmc needs n >= 2 (as the reference)")
+    if _LIBC is None:
+        _LIBC = C.CDLL("libc.so.6")
+    _LIBC.srand(C.c_uint(seed))
+    rmax = 2147483647.0
+    real, dt, cplx = PREC[p]["real"], PREC[p]["np"], PREC[p]["cplx"]
+    c = real(c)
+    diag = np.empty(n, dtype=real)
+    diag[0], diag[1] = 1.0, c
+    for j in range(2, n):
+        diag[j] = real(_LIBC.rand() / rmax) * (c - real(1.0)) + real(1.0)
+    u = np.empty(n, dtype=dt)
+    for j in range(n):
+        # complex: `rand()/RAND_MAX + rand()/RAND_MAX * I` leaves the order of the two calls to the
+        # compiler; gcc (the reference's compiler, and oracle/pin_latmc.c here) draws the imaginary part first
+        r1 = real(_LIBC.rand() / rmax)
+        u[j] = real(_LIBC.rand() / rmax) + 1j * r1 if cplx else r1
+    v = (diag * u).astype(dt)
+    t, sacc = real(0.0), dt(0.0)
+    for j in range(n):  # sequential accumulation, as the reference's loop
+        t = real(t + (np.conj(u[j]) * u[j]).real)
+        sacc = dt(sacc + np.conj(u[j]) * v[j])
+    t = real(2.0) / t
+    sacc = dt(t * t * sacc / real(2.0))
+    w = (t * v - sacc * u).astype(dt)
+    A = fmat(n, n, dt, ld)
+    A[:, :] = np.diag(diag).astype(dt)
+    A[:, :] -= (np.outer(u, np.conj(w)) + np.outer(w, np.conj(u))).astype(dt)
+    return A
+
+
 def tri(A, uplo):
     return np.tril(A) if uplo == "L" else np.triu(A)
 

@@ -255,3 +255,29 @@ def test_staged_potrs_argument_errors(lapack):
     assert lapack.potrs("d", "L", 16, 1, dA.data_ptr(), 8, dA.data_ptr(), 16, allow_invalid=True) == (-5, 1)
     assert lapack.potrs("d", "L", 8, 1, dA.data_ptr(), lda, dA.data_ptr(), 4, allow_invalid=True) == (-7, 1)
     assert lapack.potrs("d", "L", 0, 3, dA.data_ptr(), lda, dA.data_ptr(), lda) == 0
+
+
+@H.staged
+@pytest.mark.parametrize("p", "dzsc")
+@pytest.mark.parametrize("uplo", "LU")
+@pytest.mark.parametrize("n", [2, 64, 300, 1000])
+def test_staged_reference_test_inputs_latmc(lapack, p, uplo, n):
+    """The reference's LAPACK tests factor latmc(n, c = 2) after srand(0) and check `info` only
+    (test/lapack/dpotrf.c:56-67): same inputs here, info AND values, for the whole chain
+    potrf -> trtri / lauum / potri -> logdet."""
+    A0 = H.latmc(p, n, ld=n + 2)
+    want = A0.copy(order="F")
+    assert ORA.potrf(p, uplo, want) == 0
+    dA, lda = G.to_dev(A0)
+    assert lapack.potrf(p, uplo, n, dA.data_ptr(), lda) == 0
+    got = G.to_host(dA, n)
+    assert np.abs(H.tri(got, uplo) - H.tri(want, uplo)).max() <= elem_tol(p, n) * np.abs(want).max()
+    if n == 64 and uplo in "LU":  # frozen copy of the reference's own factor of this input
+        g = np.load(os.path.join(H.GOLDEN, "latmc.npz"))
+        ref = g["%s_%d_%s" % (p, n, uplo)]
+        assert np.abs(H.tri(got, uplo) - ref).max() <= elem_tol(p, n) * np.abs(ref).max()
+    inv = want.copy(order="F")
+    assert ORA.potri(p, uplo, inv) == 0
+    assert lapack.potri(p, uplo, n, dA.data_ptr(), lda) == 0
+    gotinv = G.to_host(dA, n)
+    assert np.abs(H.tri(gotinv, uplo) - H.tri(inv, uplo)).max() <= elem_tol(p, n) * np.abs(H.tri(inv, uplo)).max()

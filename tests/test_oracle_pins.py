@@ -232,3 +232,31 @@ def test_trsm_trmm_vs_ref(p):
                     ORA.trmm(p, side, uplo, trans, diag, m, n, alpha, Tm, B1)
                     REF.trmm(p, side, uplo, trans, diag, m, n, alpha, Tm, B2)
                     assert np.abs(B1 - B2).max() <= 16 * na * H.eps(p) * max(1, np.abs(B2).max()), (side, uplo, trans, diag)
+
+
+# ---- the reference's own test inputs: latmc(n, c = 2) after srand(0) (test/lapack/dpotrf.c:56) ----
+@pytest.mark.parametrize("p", "sdcz")
+@pytest.mark.parametrize("n", [2, 64])
+def test_latmc_restatement_matches_reference_generator(p, n):
+    """tests/harness.py::latmc against matrices dumped from the reference's {s,d,c,z}latmc.c
+    (oracle/pin_latmc.c); a few ulps of slack for the compiler's FMA contraction."""
+    g = np.load(os.path.join(H.GOLDEN, "latmc.npz"))
+    want = g["%s_%d_A" % (p, n)]
+    got = H.latmc(p, n)
+    assert got.dtype == want.dtype
+    assert np.abs(got - want).max() <= 4 * H.eps(p) * 2.0
+    w = np.linalg.eigvalsh(want.astype(np.complex128 if PREC[p]["cplx"] else np.float64))
+    assert abs(w.min() - 1.0) <= 1e-5 and abs(w.max() - 2.0) <= 1e-5  # condition number 2, as asked
+
+
+@pytest.mark.parametrize("p", "sdcz")
+@pytest.mark.parametrize("uplo", "LU")
+@pytest.mark.parametrize("n", [2, 64])
+def test_oracle_potrf_on_reference_inputs_golden(p, uplo, n):
+    """the oracle's potrf of the reference's latmc input against the reference's CPU potrf of it"""
+    g = np.load(os.path.join(H.GOLDEN, "latmc.npz"))
+    A = H.fmat(n, n, PREC[p]["np"], n + 2)
+    A[:, :] = g["%s_%d_A" % (p, n)]
+    assert ORA.potrf(p, uplo, A) == 0
+    want = g["%s_%d_%s" % (p, n, uplo)]
+    assert np.abs(H.tri(A, uplo) - want).max() <= tol(p, n) * np.abs(want).max()
