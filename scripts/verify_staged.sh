@@ -36,3 +36,13 @@ done
 
 echo "== host-pointer POTRI: staged on one GPU vs slab-distributed ==" | tee -a $OUT/staged_summary.txt
 timeout 600 python scripts/mgpu_inverse_ab.py 2>&1 | tee -a $OUT/staged_summary.txt
+
+echo "== memcheck of a small slice (after the same command has passed plain) ==" | tee -a $OUT/staged_summary.txt
+SLICE='tests/test_gpu_lapack.py -q -x -k "test_potrf_vs_oracle and (257 or 300) or test_trtri_vs_oracle and 300 or test_lauum_potri_logdet_vs_oracle and 257"'
+if eval timeout 300 python -m pytest $SLICE > $OUT/staged_slice_plain.log 2>&1; then
+  eval timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest $SLICE > $OUT/staged_memcheck.log 2>&1
+  echo "memcheck rc=$?" | tee -a $OUT/staged_summary.txt
+  grep -E "ERROR SUMMARY|passed|failed" $OUT/staged_memcheck.log | tail -3 | tee -a $OUT/staged_summary.txt
+else
+  echo "slice failed without the sanitizer; memcheck skipped" | tee -a $OUT/staged_summary.txt
+fi
