@@ -37,6 +37,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <atomic>
 #include <type_traits>
 
 #include "chol_kernels.h"
@@ -626,41 +627,46 @@ static int launch_t(const chol_gemm_desc *d) {
   a.total_tiles = tiles;
   build_sched_table<Cfg::BM, Cfg::BN>(a.tb, a.group, a.cuplo, a.NI, a.NJ, a.cm);
   cudaStream_t st = (cudaStream_t)d->stream;
-  static bool attr_set[64][2][2];  // per device
-  static int sm_count[64];
+  // per-device one-time setup; launch_t runs concurrently on the worker threads of the multi-GPU
+  // runtime (one device each), so the flags are atomics and the attribute calls are idempotent
+  static std::atomic<int> attr_set[64][2][2];
+  static std::atomic<int> sm_count[64];
   int dev = 0;
   cudaGetDevice(&dev);
   auto kern = tma ? gemm_dmma_kernel<CPLX, 0> : gemm_dmma_kernel<CPLX, 1>;
   auto kern_pp = tma ? gemm_dmma_pp_kernel<CPLX, 0> : gemm_dmma_pp_kernel<CPLX, 1>;
-  if (!attr_set[dev & 63][CPLX][tma]) {
+  if (!attr_set[dev & 63][CPLX][tma].load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_pp, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::PP_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev);
-    attr_set[dev & 63][CPLX][tma] = true;
+    int n_sm = 0;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    sm_count[dev & 63].store(n_sm, std::memory_order_relaxed);
+    attr_set[dev & 63][CPLX][tma].store(1, std::memory_order_release);
   }
-  // tuning switches (environment, read once):
+  // tuning switches (environment, read once - thread-safe static initialisation):
   //   CHOL_GEMM_PP=0/1      staggered two-group kernel for grids with >= 4 tiles per SM (default: z only)
   //   CHOL_GEMM_PERSIST=n   classic kernel as n persistent CTAs per SM (default 0: one CTA per tile - the
   //                         hardware's dynamic CTA placement beats a static persistent walk)
-  //   CHOL_GEMM_PREFETCH=1  enable the L2 prefetch of C tiles (default off)
+  //   CHOL_GEMM_PREFETCH=1  enable the L2 prefetch of C tiles (default off: ncu showed +50 % DRAM reads,
+  //                         lines evicted before use, for +0.4 % speed)
   //   CHOL_GEMM_TPS=n       staggered kernel: tiles per group and CTA (default 8)
   //   CHOL_GEMM_STAGEC=0    classic kernel: read C from global memory in the epilogue instead of TMA-staging it
-  static int persist = -1, prefetch = -1, pingpong = -1, tps = 8, stagec = 1;
-  if (persist < 0) {
-    const char *e1 = getenv("CHOL_GEMM_PERSIST"), *e2 = getenv("CHOL_GEMM_PREFETCH"), *e3 = getenv("CHOL_GEMM_PP");
-    persist = e1 ? atoi(e1) : 0;
-    prefetch = e2 ? atoi(e2) : 0;  // ncu: the prefetch costs +50 % DRAM reads (lines evicted before use) for +0.4 % speed
-    pingpong = e3 ? atoi(e3) : -1;  // auto: z yes (+9 % on zpotrf: short main loops), d no (within +-2 %, worse on small grids)
-    const char *e5 = getenv("CHOL_GEMM_STAGEC");
-    if (e5) stagec = atoi(e5);
-    const char *e4 = getenv("CHOL_GEMM_TPS");
-    if (e4 && atoi(e4) > 0) tps = atoi(e4);
-  }
+  struct Tuning { int persist, prefetch, pingpong, tps, stagec; };
+  static const Tuning tun = [] {
+    Tuning t{0, 0, -1, 8, 1};  // pingpong -1 = auto: z yes (+9 % on zpotrf: short main loops), d no (within +-2 %)
+    if (const char *e = getenv("CHOL_GEMM_PERSIST")) t.persist = atoi(e);
+    if (const char *e = getenv("CHOL_GEMM_PREFETCH")) t.prefetch = atoi(e);
+    if (const char *e = getenv("CHOL_GEMM_PP")) t.pingpong = atoi(e);
+    if (const char *e = getenv("CHOL_GEMM_STAGEC")) t.stagec = atoi(e);
+    if (const char *e = getenv("CHOL_GEMM_TPS")) { if (atoi(e) > 0) t.tps = atoi(e); }
+    return t;
+  }();
+  const int persist = tun.persist, prefetch = tun.prefetch, pingpong = tun.pingpong, tps = tun.tps, stagec = tun.stagec;
   a.prefetch_c = prefetch;
   a.stage_c = stagec;
   if (tiles > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
-  const int sms = sm_count[dev & 63];
+  const int sms = sm_count[dev & 63].load(std::memory_order_relaxed);
   if ((pingpong < 0 ? CPLX : pingpong != 0) && tiles >= 4LL * sms && a.K > 0) {  // (K = 0: no stages to pace the groups with)
     a.tps = tps;
     kern_pp<<<(unsigned)((tiles + 2 * tps - 1) / (2 * tps)), Cfg::PP_THREADS, Cfg::PP_SMEM_BYTES, st>>>(a);
