@@ -12,6 +12,9 @@
 //     structurally zero are skipped, triangular (cuplo) grids launch only the needed tiles.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+
+#include <atomic>
 
 #include "chol_kernels.h"
 #include "launch_count.h"
@@ -25,9 +28,11 @@ struct FCfg {
   static constexpr int VW = 16 / sizeof(T);  // elements per 128-bit access: 4 (float) / 2 (float2)
   static constexpr int TM = 2 * VW, TN = 2 * VW;
   static constexpr int BM = 16 * TM, BN = 16 * TN;  // 128 / 64
-  static constexpr int BK = 8;
   static constexpr int LDS = BM + VW;  // padded pitch (elements); keeps 16-byte alignment
   static constexpr int THREADS = 256;
+  static constexpr int STAGES = 4;     // cp.async stages
+  // bytes of the two operand rings for a k-tile depth of BK
+  static constexpr int smem_bytes(int BK) { return 2 * STAGES * BK * LDS * (int)sizeof(T); }
 };
 
 template <typename T>
@@ -100,13 +105,26 @@ __device__ __forceinline__ void f_fill(T *dst, const T *__restrict__ src, long l
   }
 }
 
-template <typename T>
+// BK = 8: the measured default (static shared memory, 33 KB).  BK = 16 (CHOL_FFMA_BK=16, dynamic
+// shared memory, 66 KB): the per-k-tile loader bookkeeping (about 100 integer instructions per
+// thread, SASS) and the barrier are amortised over twice as many FFMAs - 512 -> 1024 per thread.
+template <typename T, int BK>
 __global__ void __launch_bounds__(256, 2) gemm_ffma_kernel(const __grid_constant__ FArgs<T> p) {
   using Cfg = FCfg<T>;
-  constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, LDS = Cfg::LDS, VW = Cfg::VW, TM = Cfg::TM, TN = Cfg::TN;
-  constexpr int ST = 4;  // cp.async stages
-  __shared__ __align__(16) T As[ST][BK * LDS];
-  __shared__ __align__(16) T Bs[ST][BK * LDS];
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, LDS = Cfg::LDS, VW = Cfg::VW, TM = Cfg::TM, TN = Cfg::TN;
+  constexpr int ST = Cfg::STAGES;
+  typedef T Stage[BK * LDS];
+  Stage *As, *Bs;
+  if constexpr (BK == 8) {
+    __shared__ __align__(16) T sA[ST][BK * LDS];
+    __shared__ __align__(16) T sB[ST][BK * LDS];
+    As = sA;
+    Bs = sB;
+  } else {
+    extern __shared__ __align__(16) unsigned char f_dyn_smem[];
+    As = reinterpret_cast<Stage *>(f_dyn_smem);
+    Bs = As + ST;
+  }
 
   int bi, bj;
   if (!tile_coords<BM, BN>(8, p.cuplo, p.NI, p.NJ, p.cm, (long long)blockIdx.x, bi, bj)) return;
@@ -231,7 +249,23 @@ static int launch_f(const chol_gemm_desc *d) {
   const long long tiles = total_tiles<Cfg::BM, Cfg::BN>(8, a.cuplo, a.NI, a.NJ, a.cm);
   if (tiles <= 0) return 0;
   if (tiles > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
-  gemm_ffma_kernel<T><<<(unsigned)tiles, 256, 0, (cudaStream_t)d->stream>>>(a);
+  // CHOL_FFMA_BK=16 selects the deeper k-tile (written after the round-1 GPU budget was spent: off
+  // until it has been verified and measured on hardware)
+  static const int bk = [] { const char *e = getenv("CHOL_FFMA_BK"); return (e && atoi(e) == 16) ? 16 : 8; }();
+  if (bk == 16) {
+    constexpr int bytes = Cfg::smem_bytes(16);
+    static std::atomic<int> attr_set[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63].load(std::memory_order_acquire)) {
+      const cudaError_t e = cudaFuncSetAttribute(gemm_ffma_kernel<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      if (e != cudaSuccess) return (int)e;
+      attr_set[dev & 63].store(1, std::memory_order_release);
+    }
+    gemm_ffma_kernel<T, 16><<<(unsigned)tiles, 256, bytes, (cudaStream_t)d->stream>>>(a);
+  } else {
+    gemm_ffma_kernel<T, 8><<<(unsigned)tiles, 256, 0, (cudaStream_t)d->stream>>>(a);
+  }
   CHOL_COUNT_LAUNCH();
   return (int)cudaGetLastError();
 }

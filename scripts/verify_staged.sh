@@ -46,3 +46,12 @@ if eval timeout 300 python -m pytest $SLICE > $OUT/staged_slice_plain.log 2>&1; 
 else
   echo "slice failed without the sanitizer; memcheck skipped" | tee -a $OUT/staged_summary.txt
 fi
+
+echo "== FP32 engine with the deeper k-tile (CHOL_FFMA_BK=16): parity, then s/c/z potrf N=32768 A/B ==" | tee -a $OUT/staged_summary.txt
+CHOL_FFMA_BK=16 timeout 900 python -m pytest tests/test_gpu_blas.py tests/test_gpu_lapack.py -m gpu -q -x > $OUT/staged_ffma_bk16_tests.log 2>&1
+echo "BK=16 parity rc=$?" | tee -a $OUT/staged_summary.txt
+tail -2 $OUT/staged_ffma_bk16_tests.log | tee -a $OUT/staged_summary.txt
+for BK in 8 16; do
+  echo "CHOL_FFMA_BK=$BK" | tee -a $OUT/staged_summary.txt
+  CHOL_FFMA_BK=$BK timeout 400 python scripts/configs_bench.py cfg2 2>&1 | grep -E "^[sc]potrf" | tee -a $OUT/staged_summary.txt
+done
