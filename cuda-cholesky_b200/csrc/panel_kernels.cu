@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "chol_kernels.h"
 #include "launch_count.h"
@@ -195,13 +196,45 @@ __global__ void __launch_bounds__(PANEL_THREADS) trti2_kernel(int upper, int uni
   }
 }
 
+// L(:, 0:ncols) from its shared-memory copy (Ls[i + c*LD], zeros above the diagonal) to the caller's
+// triangle, coalesced for both storages: lower A(i,c) = L(i,c) - a warp per column, lanes along rows;
+// upper A(c,i) = conj(L(i,c)) - a warp per ROW i, lanes along the columns c <= i (LD is odd: the
+// shared reads are conflict-free either way).
+template <typename T, int NA, int LD>
+__device__ __forceinline__ void store_factor_columns(int upper, int n, int ncols, const T *Ls, T *A, long long lda, int warp,
+                                                     int lane) {
+  if (!upper) {
+    for (int c = warp; c < ncols; c += PANEL_THREADS / 32)
+#pragma unroll
+      for (int a = 0; a < NA; ++a) {
+        const int i = lane + 32 * a;
+        if (i >= c && i < n) A[(long long)c * lda + i] = Ls[i + c * LD];
+      }
+  } else {
+    for (int i = warp; i < n; i += PANEL_THREADS / 32)
+#pragma unroll
+      for (int a = 0; a < NA; ++a) {
+        const int c = lane + 32 * a;
+        if (c <= i && c < ncols) A[(long long)i * lda + c] = conj_of(Ls[i + c * LD]);
+      }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // potf2 + inverse, fused (the POTRF panel chain needs both the factor L of a diagonal block and
 // L^-1, lapack/spotrf.c:253): phase 1 is the register-resident right-looking factorisation above,
 // except that every finished column is published into a persistent shared-memory copy of L (and
 // 1/L_cc is kept); phase 2 inverts that copy by forward substitution, eight columns per warp as
 // independent, branch-free chains.  One launch, one pass over HBM, no division after the rsqrt.
-template <typename T, int NA, int NB, int NQ, int NC>
+//
+// V2 (CHOL_POTF2_V2=1; written after the round-1 GPU budget was spent, off until verified and measured):
+// the SASS of the owner warp's per-column section - the serial critical path, executed 128 times -
+// is dominated by the global stores of the finished column and their address arithmetic, and by
+// per-row branches.  V2 keeps only pivot -> rsqrt -> scale -> shared store before the barrier
+// (branch-free; rows beyond n hold zeros), writes L to HBM once after phase 1 from the shared copy
+// (coalesced for both triangles, overlapping phase 2), and prunes at compile time the phase-2 chains
+// that cannot have started in the current 32-row slice (column warp+16c >= 16c > 32q+31).
+template <typename T, int NA, int NB, int NQ, int NC, bool V2>
 __global__ void __launch_bounds__(PANEL_THREADS) potf2_inv_kernel(int upper, int n, T *A, long long lda, T *X, long long ldx,
                                                                   long *dinfo, long info_base) {
   using Real = typename ScalarOf<T>::Real;
@@ -242,11 +275,14 @@ __global__ void __launch_bounds__(PANEL_THREADS) potf2_inv_kernel(int upper, int
           }
         } else {
           const Real rinv = rsqrt(d), r = d * rinv;
-          if (lane == 0) dinv[c] = rinv;
+          if (V2 || lane == 0) dinv[c] = rinv;  // V2: every lane stores the same value - no divergent block (ptxas duplicated the rsqrt for it)
 #pragma unroll
           for (int a = 0; a < NA; ++a) {
             const int i = lane + 32 * a;
-            if (i < n) {
+            if constexpr (V2) {  // branch-free; registers of rows >= n are zero, the shared column has NMAX rows
+              const T x = (i > c) ? rscale(reg[a][bo], rinv) : ((i == c) ? from_real<T>(r) : zero_of<T>());
+              cb[i] = x;
+            } else if (i < n) {
               const T x = (i > c) ? rscale(reg[a][bo], rinv) : ((i == c) ? from_real<T>(r) : zero_of<T>());
               cb[i] = x;  // rows above the diagonal are stored as zeros: phase 2 reads a full column
               if (i >= c) { if (!upper) A[(long long)c * lda + i] = x; else A[(long long)i * lda + c] = conj_of(x); }
@@ -255,7 +291,10 @@ __global__ void __launch_bounds__(PANEL_THREADS) potf2_inv_kernel(int upper, int
         }
       }
       __syncthreads();
-      if (sfail) return;
+      if (sfail) {
+        if constexpr (V2) store_factor_columns<T, NA, LD>(upper, n, c, Ls, A, lda, warp, lane);  // columns finished so far
+        return;
+      }
       T li[NA], f[NB];
 #pragma unroll
       for (int a = 0; a < NA; ++a) li[a] = cb[lane + 32 * a];
@@ -272,6 +311,7 @@ __global__ void __launch_bounds__(PANEL_THREADS) potf2_inv_kernel(int upper, int
     }
   }
   __syncthreads();
+  if constexpr (V2) store_factor_columns<T, NA, LD>(upper, n, n, Ls, A, lda, warp, lane);  // fire and forget: overlaps phase 2
   // ---------------- phase 2: X = L^-1 ----------------
   T r[NC][NQ];
 #pragma unroll
@@ -294,6 +334,7 @@ __global__ void __launch_bounds__(PANEL_THREADS) potf2_inv_kernel(int upper, int
       }
 #pragma unroll
       for (int c = 0; c < NC; ++c) {  // branch-free: the NC chains interleave
+        if (V2 && 16 * c > 32 * q + 31) continue;  // compile-time: column warp+16c lies below this whole row slice
         const bool active = (k >= warp + 16 * c);
         T rk;
         if constexpr (ScalarOf<T>::cplx) { rk.x = __shfl_sync(0xffffffffu, r[c][q].x, kk); rk.y = __shfl_sync(0xffffffffu, r[c][q].y, kk); }
@@ -485,7 +526,9 @@ static int potf2_inv_t(int uplo, size_t n, void *A, size_t lda, void *X, size_t 
   constexpr int NMAX = sizeof(T) == 16 ? 64 : 128;
   using Real = typename ScalarOf<T>::Real;
   const size_t sm = (size_t)NMAX * (NMAX + 1) * sizeof(T) + NMAX * sizeof(Real);
-  auto kern = potf2_inv_kernel<T, NMAX / 32, NMAX / 16, NMAX / 32, NMAX / 16>;
+  static const bool v2 = [] { const char *e = getenv("CHOL_POTF2_V2"); return e != nullptr && atoi(e) != 0; }();
+  auto kern = v2 ? potf2_inv_kernel<T, NMAX / 32, NMAX / 16, NMAX / 32, NMAX / 16, true>
+                 : potf2_inv_kernel<T, NMAX / 32, NMAX / 16, NMAX / 32, NMAX / 16, false>;
   int e = set_smem(kern, sm); if (e) return e;
   kern<<<1, PANEL_THREADS, sm, st>>>(uplo == 'U', (int)n, (T *)A, (long long)lda, (T *)X, (long long)ldx, dinfo, base);
   CHOL_COUNT_LAUNCH();

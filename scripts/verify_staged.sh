@@ -55,3 +55,12 @@ for BK in 8 16; do
   echo "CHOL_FFMA_BK=$BK" | tee -a $OUT/staged_summary.txt
   CHOL_FFMA_BK=$BK timeout 400 python scripts/configs_bench.py cfg2 2>&1 | grep -E "^[sc]potrf" | tee -a $OUT/staged_summary.txt
 done
+
+echo "== diagonal-block kernel V2 (CHOL_POTF2_V2=1): parity, kernel time alone, dpotrf N=16384 ==" | tee -a $OUT/staged_summary.txt
+CHOL_POTF2_V2=1 timeout 900 python -m pytest tests/test_gpu_lapack.py tests/test_gpu_multigpu.py -m gpu -q -x > $OUT/staged_potf2_v2_tests.log 2>&1
+echo "V2 parity rc=$?" | tee -a $OUT/staged_summary.txt
+tail -2 $OUT/staged_potf2_v2_tests.log | tee -a $OUT/staged_summary.txt
+for V in 0 1; do
+  CHOL_POTF2_V2=$V timeout 200 python scripts/potf2_ab.py 2>&1 | grep potf2_inv | tee -a $OUT/staged_summary.txt
+  CHOL_POTF2_V2=$V timeout 300 python scripts/configs_bench.py cfg1 2>&1 | grep -E "^dpotrf" | sed "s/^/V2=$V /" | tee -a $OUT/staged_summary.txt
+done
