@@ -10,121 +10,23 @@
 //   * 4-stage cp.async (LDGSTS) pipeline straight into shared memory, one __syncthreads per k-tile;
 //   * any transpose / conjugate / triangular mask handled by the loader, k-ranges that are
 //     structurally zero are skipped, triangular (cuplo) grids launch only the needed tiles.
-#include <cuda_runtime.h>
-#include <stdint.h>
 #include <stdlib.h>
 
-#include <atomic>
-
-#include "chol_kernels.h"
-#include "launch_count.h"
-#include "gemm_common.cuh"
+#include "gemm_ffma.cuh"
 
 namespace chol {
 
-template <typename T>
-struct FCfg {
-  static constexpr bool CPLX = ScalarOf<T>::cplx;
-  static constexpr int VW = 16 / sizeof(T);  // elements per 128-bit access: 4 (float) / 2 (float2)
-  static constexpr int TM = 2 * VW, TN = 2 * VW;
-  static constexpr int BM = 16 * TM, BN = 16 * TN;  // 128 / 64
-  static constexpr int LDS = BM + VW;  // padded pitch (elements); keeps 16-byte alignment
-  static constexpr int THREADS = 256;
-  static constexpr int STAGES = 4;     // cp.async stages
-  // bytes of the two operand rings for a k-tile depth of BK
-  static constexpr int smem_bytes(int BK) { return 2 * STAGES * BK * LDS * (int)sizeof(T); }
-};
+// gemm_ffma_deep.cu
+int chol_gemm_fp32_deep_launch(const FArgs<float> &a, unsigned tiles, cudaStream_t st);
+int chol_gemm_fp32_deep_launch(const FArgs<float2> &a, unsigned tiles, cudaStream_t st);
 
 template <typename T>
-struct FArgs {
-  const T *A, *B, *C;
-  T *D;
-  long long lda, ldb, ldc, ldd;
-  int M, N, K;
-  T alpha, beta;
-  int opA, opB, triA, triB, unitA, unitB, cuplo, herm, NI, NJ, vec_ok, beta_zero;
-  int vecA, vecB;            // 16-byte cp.async along the stored rows is legal
-  int conjA_regs, conjB_regs;  // complex: conjugate fragments in registers (fast path copies raw data)
-  ColMap cm;
-};
-
-// true if the stored-triangle mask cannot touch the tile rows [r0, r0+rows) x k [k0, k0+bk)
-__device__ __forceinline__ bool f_tri_clear(int tri, bool along_rows, int r0, int rows, int k0, int bk) {
-  if (!tri) return true;
-  const int row_min = along_rows ? r0 : k0, row_max = along_rows ? r0 + rows - 1 : k0 + bk - 1;
-  const int col_min = along_rows ? k0 : r0, col_max = along_rows ? k0 + bk - 1 : r0 + rows - 1;
-  return tri == 1 ? (row_min > col_max) : (row_max < col_min);
-}
-template <int BYTES>
-__device__ __forceinline__ void f_cp_async(void *dst, const void *src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-  if constexpr (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
-  else asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(src), "n"(BYTES) : "memory");
-}
-
-// One ROWS x BK operand tile -> shared [k][row] (pitch LDS).  Interior, unmasked tiles go through
-// cp.async (16-byte vectors along the stored rows when aligned, element-wise otherwise); edge and
-// diagonal-crossing tiles take the per-element path with masks.  256 threads cooperate.
-template <typename T, int ROWS, int BK, int LDS>
-__device__ __forceinline__ void f_fill(T *dst, const T *__restrict__ src, long long ld, int op, int tri, int unit, bool is_b,
-                                       int r0, int rlimit, int rows_valid, int k0, int ke, bool vec16, int tid) {
-  // logical element (row r0+rr, k0+kk); stored coordinates: A: op==0 -> (row, k) else (k, row); B: op!=0 -> (row, k) else (k, row)
-  const bool along_rows = is_b ? (op != 0) : (op == 0);
-  const bool conj = false;  // conjugation is applied to the register fragments (conjA_regs / conjB_regs)
-  const bool fast = (rows_valid == ROWS) && (k0 + BK <= ke) && f_tri_clear(tri, along_rows, r0, ROWS, k0, BK);
-  constexpr int VW = 16 / sizeof(T);
-  if (fast) {
-    if (along_rows) {
-      if (vec16) {
-        for (int v = tid; v < ROWS / VW * BK; v += 256) {
-          const int rv = v % (ROWS / VW), kk = v / (ROWS / VW);
-          f_cp_async<16>(dst + kk * LDS + rv * VW, src + (long long)(k0 + kk) * ld + r0 + rv * VW);
-        }
-      } else {
-        for (int e = tid; e < ROWS * BK; e += 256) {
-          const int rr = e % ROWS, kk = e / ROWS;
-          f_cp_async<sizeof(T)>(dst + kk * LDS + rr, src + (long long)(k0 + kk) * ld + r0 + rr);
-        }
-      }
-    } else {
-      for (int e = tid; e < ROWS * BK; e += 256) {
-        const int kk = e % BK, rr = e / BK;
-        f_cp_async<sizeof(T)>(dst + kk * LDS + rr, src + (long long)(r0 + rr) * ld + k0 + kk);
-      }
-    }
-    return;
-  }
-  for (int e = tid; e < ROWS * BK; e += 256) {
-    int rr, kk;
-    if (along_rows) { rr = e % ROWS; kk = e / ROWS; } else { kk = e % BK; rr = e / BK; }
-    const long long r = r0 + rr, k = k0 + kk;
-    const bool in = (rr < rows_valid) && (k < ke);
-    (void)rlimit;
-    dst[kk * LDS + rr] = along_rows ? fetch_stored<T>(src, ld, in, r, k, tri, unit, conj)
-                                    : fetch_stored<T>(src, ld, in, k, r, tri, unit, conj);
-  }
-}
-
-// BK = 8: the measured default (static shared memory, 33 KB).  BK = 16 (CHOL_FFMA_BK=16, dynamic
-// shared memory, 66 KB): the per-k-tile loader bookkeeping (about 100 integer instructions per
-// thread, SASS) and the barrier are amortised over twice as many FFMAs - 512 -> 1024 per thread.
-template <typename T, int BK>
 __global__ void __launch_bounds__(256, 2) gemm_ffma_kernel(const __grid_constant__ FArgs<T> p) {
   using Cfg = FCfg<T>;
-  constexpr int BM = Cfg::BM, BN = Cfg::BN, LDS = Cfg::LDS, VW = Cfg::VW, TM = Cfg::TM, TN = Cfg::TN;
-  constexpr int ST = Cfg::STAGES;
-  typedef T Stage[BK * LDS];
-  Stage *As, *Bs;
-  if constexpr (BK == 8) {
-    __shared__ __align__(16) T sA[ST][BK * LDS];
-    __shared__ __align__(16) T sB[ST][BK * LDS];
-    As = sA;
-    Bs = sB;
-  } else {
-    extern __shared__ __align__(16) unsigned char f_dyn_smem[];
-    As = reinterpret_cast<Stage *>(f_dyn_smem);
-    Bs = As + ST;
-  }
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, LDS = Cfg::LDS, VW = Cfg::VW, TM = Cfg::TM, TN = Cfg::TN;
+  constexpr int ST = 4;  // cp.async stages
+  __shared__ __align__(16) T As[ST][BK * LDS];
+  __shared__ __align__(16) T Bs[ST][BK * LDS];
 
   int bi, bj;
   if (!tile_coords<BM, BN>(8, p.cuplo, p.NI, p.NJ, p.cm, (long long)blockIdx.x, bi, bj)) return;
@@ -249,23 +151,10 @@ static int launch_f(const chol_gemm_desc *d) {
   const long long tiles = total_tiles<Cfg::BM, Cfg::BN>(8, a.cuplo, a.NI, a.NJ, a.cm);
   if (tiles <= 0) return 0;
   if (tiles > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
-  // CHOL_FFMA_BK=16 selects the deeper k-tile (written after the round-1 GPU budget was spent: off
-  // until it has been verified and measured on hardware)
-  static const int bk = [] { const char *e = getenv("CHOL_FFMA_BK"); return (e && atoi(e) == 16) ? 16 : 8; }();
-  if (bk == 16) {
-    constexpr int bytes = Cfg::smem_bytes(16);
-    static std::atomic<int> attr_set[64];
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!attr_set[dev & 63].load(std::memory_order_acquire)) {
-      const cudaError_t e = cudaFuncSetAttribute(gemm_ffma_kernel<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-      if (e != cudaSuccess) return (int)e;
-      attr_set[dev & 63].store(1, std::memory_order_release);
-    }
-    gemm_ffma_kernel<T, 16><<<(unsigned)tiles, 256, bytes, (cudaStream_t)d->stream>>>(a);
-  } else {
-    gemm_ffma_kernel<T, 8><<<(unsigned)tiles, 256, 0, (cudaStream_t)d->stream>>>(a);
-  }
+  // CHOL_FFMA_BK=16: the deeper-k-tile variant (gemm_ffma_deep.cu), off until verified and measured on hardware
+  static const bool deep = [] { const char *e = getenv("CHOL_FFMA_BK"); return e != nullptr && atoi(e) == 16; }();
+  if (deep) return chol_gemm_fp32_deep_launch(a, (unsigned)tiles, (cudaStream_t)d->stream);
+  gemm_ffma_kernel<T><<<(unsigned)tiles, 256, 0, (cudaStream_t)d->stream>>>(a);
   CHOL_COUNT_LAUNCH();
   return (int)cudaGetLastError();
 }

@@ -1,0 +1,136 @@
+// gemm_ffma_deep.cu — the FP32 engine of gemm_ffma.cu with a k-tile of 16 instead of 8
+// (CHOL_FFMA_BK=16; dynamic shared memory, 66 KB, still 2 CTAs per SM).
+//
+// SASS of the BK = 8 kernel: per k-tile and thread 512 FFMA + 32 LDS.128 + about 100 integer /
+// control instructions of loader bookkeeping (fast-path predicates, 64-bit addresses) + one barrier,
+// so FFMA holds ~73 % of the issue slots; BK = 16 amortises the bookkeeping and the barrier over
+// 1024 FFMA.  Written after the round-1 GPU budget was spent.  It lives in its own translation unit
+// (the kernel body is a copy) because merely adding it next to the measured kernel changed that
+// kernel's code layout; this way the default stays bit-identical until the variant has been
+// verified and measured, after which the two are to be merged into one template.
+#include <atomic>
+
+#include "gemm_ffma.cuh"
+
+namespace chol {
+
+template <typename T>
+__global__ void __launch_bounds__(256, 2) gemm_ffma_deep_kernel(const __grid_constant__ FArgs<T> p) {
+  using Cfg = FCfg<T>;
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = 16, LDS = Cfg::LDS, VW = Cfg::VW, TM = Cfg::TM, TN = Cfg::TN;
+  constexpr int ST = 4;  // cp.async stages
+  extern __shared__ __align__(16) unsigned char f_dyn_smem[];
+  typedef T Stage[BK * LDS];
+  Stage *As = reinterpret_cast<Stage *>(f_dyn_smem), *Bs = As + ST;
+
+  int bi, bj;
+  if (!tile_coords<BM, BN>(8, p.cuplo, p.NI, p.NJ, p.cm, (long long)blockIdx.x, bi, bj)) return;
+  const int m0 = bi * BM, n0 = bj * BN;
+  const int g0 = (int)gcol(p.cm, n0);
+  int kb = 0, ke = p.K;
+  if (p.triA) {
+    const bool lower = (p.triA == 1) == (p.opA == 0);
+    if (lower) ke = min(ke, m0 + BM); else kb = max(kb, m0);
+  }
+  if (p.triB) {
+    const bool kgen = (p.triB == 1) == (p.opB == 0);
+    if (kgen) kb = max(kb, g0); else ke = min(ke, g0 + BN);
+  }
+  kb = (kb / BK) * BK;
+  const int nk = ke > kb ? (ke - kb + BK - 1) / BK : 0;
+
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int rowsA = min(BM, p.M - m0), rowsB = min(BN, p.N - n0);
+  T acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = zero_of<T>();
+
+  auto issue = [&](int kt) {
+    if (kt < nk) {
+      const int s = kt % ST, k0 = kb + kt * BK;
+      f_fill<T, BM, BK, LDS>(As[s], p.A, p.lda, p.opA, p.triA, p.unitA, false, m0, p.M, rowsA, k0, ke, p.vecA, tid);
+      f_fill<T, BN, BK, LDS>(Bs[s], p.B, p.ldb, p.opB, p.triB, p.unitB, true, g0, p.N, rowsB, k0, ke, p.vecB, tid);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+#pragma unroll
+  for (int kt = 0; kt < ST - 1; ++kt) issue(kt);
+
+  for (int kt = 0; kt < nk; ++kt) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(ST - 2) : "memory");
+    __syncthreads();          // stage kt has landed for everyone; stage kt-1 is no longer being read
+    issue(kt + ST - 1);       // refill the slot that stage kt-1 used
+    const int cur = kt % ST;
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      T a[TM], b[TN];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float4 va = *reinterpret_cast<const float4 *>(&As[cur][kk * LDS + h * (BM / 2) + tx * VW]);
+        const float4 vb = *reinterpret_cast<const float4 *>(&Bs[cur][kk * LDS + h * (BN / 2) + ty * VW]);
+        if constexpr (Cfg::CPLX) {
+          a[h * 2] = make_float2(va.x, va.y); a[h * 2 + 1] = make_float2(va.z, va.w);
+          b[h * 2] = make_float2(vb.x, vb.y); b[h * 2 + 1] = make_float2(vb.z, vb.w);
+        } else {
+          a[h * 4] = va.x; a[h * 4 + 1] = va.y; a[h * 4 + 2] = va.z; a[h * 4 + 3] = va.w;
+          b[h * 4] = vb.x; b[h * 4 + 1] = vb.y; b[h * 4 + 2] = vb.z; b[h * 4 + 3] = vb.w;
+        }
+      }
+      if constexpr (Cfg::CPLX) {  // conjugation of raw cp.async copies happens here
+        if (p.conjA_regs) {
+#pragma unroll
+          for (int i = 0; i < TM; ++i) a[i].y = -a[i].y;
+        }
+        if (p.conjB_regs) {
+#pragma unroll
+          for (int j = 0; j < TN; ++j) b[j].y = -b[j].y;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) fma_acc(acc[i][j], a[i], b[j]);
+    }
+  }
+
+  // epilogue: thread owns rows m0 + h*(BM/2) + tx*VW + v, columns n0 + h2*(BN/2) + ty*VW + w
+#pragma unroll
+  for (int j = 0; j < TN; ++j) {
+    const long long n = n0 + (j / VW) * (BN / 2) + ty * VW + (j % VW);
+    if (n >= p.N) continue;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      const long long m = m0 + (i / VW) * (BM / 2) + tx * VW + (i % VW);
+      if (m >= p.M) continue;
+      if (p.cuplo == 1 && m < n - n0 + g0) continue;
+      if (p.cuplo == 2 && m > n - n0 + g0) continue;
+      T o = mul(p.alpha, acc[i][j]);
+      if (!p.beta_zero) fma_acc(o, p.beta, p.C[n * p.ldc + m]);
+      if constexpr (Cfg::CPLX) { if (p.herm && m == n - n0 + g0) o.y = 0.f; }
+      p.D[n * p.ldd + m] = o;
+    }
+  }
+}
+
+template <typename T>
+static int deep_launch_t(const FArgs<T> &a, unsigned tiles, cudaStream_t st) {
+  constexpr int bytes = 2 * 4 * 16 * FCfg<T>::LDS * (int)sizeof(T);
+  static std::atomic<int> attr_set[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63].load(std::memory_order_acquire)) {
+    const cudaError_t e = cudaFuncSetAttribute(gemm_ffma_deep_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return (int)e;
+    attr_set[dev & 63].store(1, std::memory_order_release);
+  }
+  gemm_ffma_deep_kernel<T><<<tiles, 256, bytes, st>>>(a);
+  CHOL_COUNT_LAUNCH();
+  return (int)cudaGetLastError();
+}
+
+int chol_gemm_fp32_deep_launch(const FArgs<float> &a, unsigned tiles, cudaStream_t st) { return deep_launch_t<float>(a, tiles, st); }
+int chol_gemm_fp32_deep_launch(const FArgs<float2> &a, unsigned tiles, cudaStream_t st) { return deep_launch_t<float2>(a, tiles, st); }
+
+}  // namespace chol
