@@ -682,10 +682,12 @@ static int launch_t(const chol_gemm_desc *d) {
 }  // namespace chol
 
 int chol_gemm_fp32_launch(const chol_gemm_desc *d);  // gemm_ffma.cu
+extern "C" int chol_gemm_small_eligible(const chol_gemm_desc *d);  // gemm_small.cu (CHOL_SMALL_GEMM=1, off by default)
+extern "C" int chol_gemm_small_launch(const chol_gemm_desc *d);
 
 extern "C" int chol_gemm_launch(const chol_gemm_desc *d) {
   switch (d->prec) {
-    case 'd': return chol::launch_t<false>(d);
+    case 'd': return chol_gemm_small_eligible(d) ? chol_gemm_small_launch(d) : chol::launch_t<false>(d);
     case 'z': return chol::launch_t<true>(d);
     case 's':
     case 'c': return chol_gemm_fp32_launch(d);

@@ -64,3 +64,10 @@ for V in 0 1; do
   CHOL_POTF2_V2=$V timeout 200 python scripts/potf2_ab.py 2>&1 | grep potf2_inv | tee -a $OUT/staged_summary.txt
   CHOL_POTF2_V2=$V timeout 300 python scripts/configs_bench.py cfg1 2>&1 | grep -E "^dpotrf" | sed "s/^/V2=$V /" | tee -a $OUT/staged_summary.txt
 done
+
+echo "== small-tile FP64 GEMM for the panel chain (CHOL_SMALL_GEMM=1): parity, then dpotrf N=16384 alone and with POTF2 V2 ==" | tee -a $OUT/staged_summary.txt
+CHOL_SMALL_GEMM=1 timeout 900 python -m pytest tests/test_gpu_blas.py tests/test_gpu_lapack.py -m gpu -q -x > $OUT/staged_small_gemm_tests.log 2>&1
+echo "small GEMM parity rc=$?" | tee -a $OUT/staged_summary.txt
+tail -2 $OUT/staged_small_gemm_tests.log | tee -a $OUT/staged_summary.txt
+CHOL_SMALL_GEMM=1 timeout 300 python scripts/configs_bench.py cfg1 2>&1 | grep -E "^dpotrf" | sed "s/^/SMALL_GEMM=1 /" | tee -a $OUT/staged_summary.txt
+CHOL_SMALL_GEMM=1 CHOL_POTF2_V2=1 timeout 300 python scripts/configs_bench.py cfg1 2>&1 | grep -E "^dpotrf" | sed "s/^/SMALL_GEMM=1 POTF2_V2=1 /" | tee -a $OUT/staged_summary.txt
