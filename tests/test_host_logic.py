@@ -193,3 +193,81 @@ def test_inverse_slab_bounds_cover_and_balance(profile, n, nslabs):
         dens = [(n - x) ** 2, x ** 2, x * (n - x)][profile]
         work = np.array([dens[b[i]:b[i + 1]].sum() for i in range(nslabs)])
         assert work.max() <= 1.06 * work.mean()
+
+
+def _slab_bounds(profile, n, nslabs):
+    b = (C.c_size_t * (nslabs + 1))()
+    chol.lib().chol_inverse_slab_bounds(C.c_int(profile), C.c_size_t(n), C.c_int(nslabs), b)
+    return list(b)
+
+
+def _tri(A, uplo, unit=False):
+    T = np.tril(A) if uplo == "L" else np.triu(A)
+    return T - np.diag(np.diag(T)) + np.eye(len(T)) if unit else T
+
+
+@pytest.mark.parametrize("uplo", "LU")
+@pytest.mark.parametrize("n,nslabs", [(200, 1), (200, 3), (700, 4), (130, 8)])
+def test_slab_inverse_decomposition_model(uplo, n, nslabs):
+    """The algebra host/multigpu_blas.c distributes (CHOL_MGPU_INVERSE=slab), replayed in numpy with
+    the library's own slab boundaries: every slab reads only the ORIGINAL matrix, writes only its own
+    output slab, and together they give inv(T) / T^H T with the other triangle untouched."""
+    rng = np.random.default_rng(3)
+    M = rng.standard_normal((n, n))
+    F = np.linalg.cholesky(M @ M.T + n * np.eye(n))
+    junk = rng.standard_normal((n, n))
+    St = np.tril(F) + np.triu(junk, 1) if uplo == "L" else np.triu(F.T) + np.tril(junk, -1)
+
+    def put_triangle(out, lo, X):
+        for c in range(len(X)):
+            if uplo == "L":
+                out[lo + c:lo + len(X), lo + c] = X[c:, c]
+            else:
+                out[lo:lo + c + 1, lo + c] = X[:c + 1, c]
+
+    # TRTRI: lower columns J need T = L[lo:, lo:]; upper columns J need T = U[:hi, :hi]
+    b = _slab_bounds(0 if uplo == "L" else 1, n, nslabs)
+    out = St.copy()
+    for lo, hi in zip(b[:-1], b[1:]):
+        w = hi - lo
+        if w == 0:
+            continue
+        if uplo == "L":
+            T = St[lo:, lo:]
+            Tww, Trr, Trw = T[:w, :w], T[w:, w:], T[w:, :w]
+        else:
+            T = St[:hi, :hi]
+            Tww, Trr, Trw = T[lo:, lo:], T[:lo, :lo], T[:lo, lo:]
+        X = np.linalg.inv(_tri(Tww, uplo))
+        if len(Trr):
+            Y = -np.linalg.inv(_tri(Trr, uplo)) @ (Trw @ _tri(X, uplo))
+            if uplo == "L":
+                out[hi:, lo:hi] = Y
+            else:
+                out[:lo, lo:hi] = Y
+        put_triangle(out, lo, X)
+    want = np.linalg.inv(_tri(St, uplo))
+    assert np.abs(_tri(out, uplo) - _tri(want, uplo)).max() <= 1e-10 * np.abs(want).max()
+    strict = (lambda A: np.triu(A, 1)) if uplo == "L" else (lambda A: np.tril(A, -1))
+    assert np.array_equal(strict(out), strict(St))
+
+    # LAUUM: lower rows I need R = L[lo:, :hi]; upper columns I need R = U[:hi, lo:]
+    b = _slab_bounds(2, n, nslabs)
+    out = St.copy()
+    for lo, hi in zip(b[:-1], b[1:]):
+        if hi == lo:
+            continue
+        if uplo == "L":
+            R = St[lo:, :hi]
+            Aii = np.tril(R[:, lo:hi])
+            out[lo:hi, :lo] = Aii.T @ R[:, :lo]
+            put_triangle(out, lo, Aii.T @ Aii)
+        else:
+            R = St[:hi, lo:]
+            Aii = np.triu(R[lo:hi, :])
+            out[:lo, lo:hi] = R[:lo, :] @ Aii.T
+            put_triangle(out, lo, Aii @ Aii.T)
+    T = _tri(St, uplo)
+    want = T.T @ T if uplo == "L" else T @ T.T
+    assert np.abs(_tri(out, uplo) - _tri(want, uplo)).max() <= 1e-10 * np.abs(want).max()
+    assert np.array_equal(strict(out), strict(St))
