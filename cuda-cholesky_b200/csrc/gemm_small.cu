@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(S_THREADS) dgemm_small_kernel(const __grid_con
 
 }  // namespace chol
 
+#ifndef CHOL_CPU_EMU  // the launchers are not part of the CPU emulation (tests/emu)
 // 1 if the descriptor is one the small-tile kernel takes (and the switch is on)
 extern "C" int chol_gemm_small_eligible(const chol_gemm_desc *d) {
   static const bool on = [] { const char *e = getenv("CHOL_SMALL_GEMM"); return e != nullptr && atoi(e) != 0; }();
@@ -143,3 +144,4 @@ extern "C" int chol_gemm_small_launch(const chol_gemm_desc *d) {
   CHOL_COUNT_LAUNCH();
   return (int)cudaGetLastError();
 }
+#endif  // CHOL_CPU_EMU

@@ -15,8 +15,11 @@
 #include <stdlib.h>
 
 #include "chol_kernels.h"
+#include "emu_compat.cuh"
 #include "launch_count.h"
+#ifndef CHOL_CPU_EMU
 #include "ptx_sm100.cuh"
+#endif
 #include "scalar_ops.cuh"
 
 namespace chol {
@@ -76,7 +79,7 @@ __global__ void __launch_bounds__(PANEL_THREADS) potf2_kernel(int upper, int n, 
         d = __shfl_sync(0xffffffffu, re_of(reg[ao][bo]), lo);
         if (!(d > Real(0))) {  // <= 0 or NaN: not positive definite (lapack/dpotrf.c:70-73)
           if (lane == 0) {
-            sfail = 1;
+            sfail = c + 1;
             *dinfo = info_base + c + 1;
             A[(long long)c * lda + c] = from_real<T>(d);
           }
@@ -94,7 +97,7 @@ __global__ void __launch_bounds__(PANEL_THREADS) potf2_kernel(int upper, int n, 
         }
       }
       __syncthreads();
-      if (sfail) return;
+      if (sfail == c + 1) return;  // (see the note on sfail in potf2_inv_kernel)
       // rank-1 update of the trailing window: columns k > c, rows i >= k
       T li[NA];
 #pragma unroll
@@ -121,7 +124,7 @@ __global__ void __launch_bounds__(PANEL_THREADS) potf2_kernel(int upper, int n, 
 template <typename T, int NQ, int NC>
 __global__ void __launch_bounds__(PANEL_THREADS) trti2_kernel(int upper, int unit, int n, const T *A, long long lda, T *B,
                                                               long long ldb, int zero_other, long *dinfo, long info_base) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CHOL_DYN_SMEM(smem_raw);
   T *L = reinterpret_cast<T *>(smem_raw);
   const int LD = n | 1;
   T *dinv = L + (size_t)n * LD;
@@ -238,7 +241,7 @@ template <typename T, int NA, int NB, int NQ, int NC, bool V2>
 __global__ void __launch_bounds__(PANEL_THREADS) potf2_inv_kernel(int upper, int n, T *A, long long lda, T *X, long long ldx,
                                                                   long *dinfo, long info_base) {
   using Real = typename ScalarOf<T>::Real;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CHOL_DYN_SMEM(smem_raw);
   constexpr int NMAX = 32 * NA, LD = NMAX + 1;
   T *Ls = reinterpret_cast<T *>(smem_raw);          // L(i,c) at Ls[i + c*LD]
   Real *dinv = reinterpret_cast<Real *>(Ls + (size_t)NMAX * LD);
@@ -269,7 +272,7 @@ __global__ void __launch_bounds__(PANEL_THREADS) potf2_inv_kernel(int upper, int
         const Real d = __shfl_sync(0xffffffffu, re_of(reg[ao][bo]), c & 31);
         if (!(d > Real(0))) {  // <= 0 or NaN: not positive definite (lapack/dpotrf.c:70-73)
           if (lane == 0) {
-            sfail = 1;
+            sfail = c + 1;
             *dinfo = info_base + c + 1;
             A[(long long)c * lda + c] = from_real<T>(d);
           }
@@ -291,7 +294,12 @@ __global__ void __launch_bounds__(PANEL_THREADS) potf2_inv_kernel(int upper, int
         }
       }
       __syncthreads();
-      if (sfail) {
+      // sfail holds the failing column + 1.  The owner of column c+1 may already have run ahead through its
+      // update, found ITS pivot bad and written sfail while a slow warp is only now testing the flag for
+      // column c: a plain "nonzero" test would let that warp leave one barrier early and hang the block
+      // (found by the CPU emulation, tests/emu).  Comparing with c + 1 makes every thread leave after the
+      // same barrier; nobody can be more than one column ahead.
+      if (sfail == c + 1) {
         if constexpr (V2) store_factor_columns<T, NA, LD>(upper, n, c, Ls, A, lda, warp, lane);  // columns finished so far
         return;
       }
@@ -366,7 +374,7 @@ __global__ void __launch_bounds__(PANEL_THREADS) potf2_inv_kernel(int upper, int
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(PANEL_THREADS) lauu2_kernel(int upper, int n, T *A, long long lda) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CHOL_DYN_SMEM(smem_raw);
   T *L = reinterpret_cast<T *>(smem_raw);
   const int LD = n | 1;
   load_lower_form(L, LD, upper, true, n, A, lda);  // upper: L = U^H, so U*U^H = L^H*L
@@ -464,6 +472,7 @@ __global__ void __launch_bounds__(LOGDET_THREADS) logdet_kernel(const T *x, long
   }
 }
 
+#ifndef CHOL_CPU_EMU  // everything below launches kernels or uses inline PTX: not part of the CPU emulation
 // ------------------------------------------------------------------------------------------------
 // FP64 peak probes (registers only, no memory traffic):
 //   kind 0 = DMMA, the GEMM engine's own instruction mix: 8 A-fragments x 4 B-fragments -> 32
@@ -668,3 +677,6 @@ extern "C" int chol_probe_fp64(int kind, int iters, double *tflops, float *ms_ou
   cudaFree(out);
   return (int)cudaGetLastError();
 }
+#else
+}  // namespace chol (the emulation build stops before the launchers)
+#endif  // CHOL_CPU_EMU

@@ -1,0 +1,256 @@
+// emu_panel.cpp — the diagonal-block kernels of csrc/panel_kernels.cu executed on the CPU
+// (tests/emu/cuda_emu.h): potf2_inv (measured variant and V2), potf2, trti2, lauu2 against plain
+// loops, for lower / upper storage, full and ragged block sizes, and a non-positive-definite block.
+// Prints one line per case and "EMU PASSED" at the end; exit code 1 on the first mismatch.
+#define CUDA_EMU_IMPLEMENTATION
+#include "cuda_emu.h"
+
+#include "../../cuda-cholesky_b200/csrc/panel_kernels.cu"
+
+#include <complex>
+#include <random>
+
+using namespace chol;
+
+template <typename T> struct Host;  // device element type -> std type
+template <> struct Host<double> { using type = double; };
+template <> struct Host<float> { using type = float; };
+template <> struct Host<double2> { using type = std::complex<double>; };
+template <> struct Host<float2> { using type = std::complex<float>; };
+template <typename H> static H cj(H x) { return x; }
+template <typename R> static std::complex<R> cj(std::complex<R> x) { return std::conj(x); }
+template <typename H> static double ab(H x) { return std::abs(x); }
+
+template <typename T, typename H>
+static void spd(int n, int lda, std::vector<H> &A, unsigned seed) {  // Hermitian positive definite, both triangles filled
+  std::mt19937 g(seed);
+  std::uniform_real_distribution<double> u(-0.5, 0.5);
+  std::vector<H> B((size_t)n * n);
+  for (auto &x : B) {
+    if constexpr (ScalarOf<T>::cplx) x = H((typename H::value_type)u(g), (typename H::value_type)u(g));
+    else x = (H)u(g);
+  }
+  A.assign((size_t)lda * n, H(77));  // padding rows keep a sentinel
+  for (int j = 0; j < n; ++j)
+    for (int i = 0; i < n; ++i) {
+      H s = (i == j) ? H(n) : H(0);
+      for (int k = 0; k < n; ++k) s += B[i + (size_t)k * n] * cj(B[j + (size_t)k * n]);
+      A[i + (size_t)j * lda] = s;
+    }
+}
+
+template <typename H>
+static int ref_potrf_lower(int n, std::vector<H> &L, int ld) {  // in place, lower of a full Hermitian matrix; returns info
+  for (int c = 0; c < n; ++c) {
+    double d = std::real(L[c + (size_t)c * ld]);
+    if (!(d > 0)) return c + 1;
+    const double r = std::sqrt(d);
+    L[c + (size_t)c * ld] = H(r);
+    for (int i = c + 1; i < n; ++i) L[i + (size_t)c * ld] = L[i + (size_t)c * ld] / H(r);
+    for (int k = c + 1; k < n; ++k)
+      for (int i = k; i < n; ++i) L[i + (size_t)k * ld] -= L[i + (size_t)c * ld] * cj(L[k + (size_t)c * ld]);
+  }
+  return 0;
+}
+
+static int failures = 0;
+static void check(bool ok, const char *what, double err) {
+  std::printf("%-72s %s (%.2e)\n", what, ok ? "ok" : "MISMATCH", err);
+  if (!ok) ++failures;
+}
+
+template <typename T, int NMAX, bool V2>
+static void run_potf2_inv(int upper, int n, int lda, std::vector<typename Host<T>::type> &A, std::vector<typename Host<T>::type> &X,
+                          long *info, long base) {
+  using Real = typename ScalarOf<T>::Real;
+  const size_t sm = (size_t)NMAX * (NMAX + 1) * sizeof(T) + NMAX * sizeof(Real);
+  X.assign((size_t)lda * n, typename Host<T>::type(55));
+  T *dA = reinterpret_cast<T *>(A.data()), *dX = reinterpret_cast<T *>(X.data());
+  emu::launch(dim3(1), dim3(PANEL_THREADS), sm, [&] {
+    potf2_inv_kernel<T, NMAX / 32, NMAX / 16, NMAX / 32, NMAX / 16, V2>(upper, n, dA, lda, dX, lda, info, base);
+  });
+}
+
+template <typename T, int NMAX>
+static void case_potf2_inv(const char *name, int n, double tol) {
+  using H = typename Host<T>::type;
+  const int lda = n + 3;
+  for (int upper = 0; upper < 2; ++upper) {
+    std::vector<H> A0, A1, A2, X1, X2;
+    spd<T, H>(n, lda, A0, 11u + n);
+    A1 = A0; A2 = A0;
+    long i1 = 0, i2 = 0;
+    if (getenv("EMU_TRACE")) std::fprintf(stderr, "[%s n=%d upper=%d] measured variant...\n", name, n, upper);
+    run_potf2_inv<T, NMAX, false>(upper, n, lda, A1, X1, &i1, 100);
+    if (getenv("EMU_TRACE")) std::fprintf(stderr, "  V2...\n");
+    run_potf2_inv<T, NMAX, true>(upper, n, lda, A2, X2, &i2, 100);
+    if (getenv("EMU_TRACE")) std::fprintf(stderr, "  reference + checks...\n");
+    // reference factor (lower form); for upper storage the kernel holds U = L^H
+    std::vector<H> L = A0;
+    const int ri = ref_potrf_lower(n, L, lda);
+    double e_ref = 0, e_v = 0, e_x = 0, e_other = 0, e_inv = 0;
+    for (int j = 0; j < n; ++j)
+      for (int i = 0; i < n; ++i) {
+        const bool in_tri = upper ? (i <= j) : (i >= j);
+        const H a1 = A1[i + (size_t)j * lda], a2 = A2[i + (size_t)j * lda];
+        if (in_tri) {
+          const H want = upper ? cj(L[j + (size_t)i * lda]) : L[i + (size_t)j * lda];
+          e_ref = std::max(e_ref, ab(a1 - want));
+          e_v = std::max(e_v, ab(a1 - a2));
+          e_x = std::max(e_x, ab(X1[i + (size_t)j * lda] - X2[i + (size_t)j * lda]));
+        } else {
+          e_other = std::max(e_other, ab(a1 - A0[i + (size_t)j * lda]) + ab(a2 - A0[i + (size_t)j * lda]));  // untouched
+          e_x = std::max(e_x, ab(X1[i + (size_t)j * lda]) + ab(X2[i + (size_t)j * lda]));                  // zeroed
+        }
+      }
+    // X * F = I  (lower: X = L^-1, F = L; upper: X = U^-1, F = U)
+    for (int j = 0; j < n; ++j)
+      for (int i = 0; i < n; ++i) {
+        H s = 0;
+        for (int k = 0; k < n; ++k) {
+          const bool xin = upper ? (i <= k) : (i >= k), fin = upper ? (k <= j) : (k >= j);
+          if (xin && fin) s += X2[i + (size_t)k * lda] * A2[k + (size_t)j * lda];
+        }
+        e_inv = std::max(e_inv, ab(s - H(i == j ? 1 : 0)));
+      }
+    char what[160];
+    std::snprintf(what, sizeof what, "%s potf2_inv %s n=%d: info, factor vs loops, V2 == measured variant, X F = I", name, upper ? "upper" : "lower", n);
+    check(ri == 0 && i1 == 0 && i2 == 0 && e_ref <= tol && e_v == 0.0 && e_x == 0.0 && e_other == 0.0 && e_inv <= 50 * tol, what,
+          std::max(std::max(e_ref, e_v), std::max(e_x, e_inv)));
+    for (int j = 0; j < n; ++j)  // padding rows never touched
+      for (int i = n; i < lda; ++i)
+        if (A2[i + (size_t)j * lda] != H(77)) { check(false, "padding rows of A overwritten", 0); return; }
+  }
+}
+
+template <typename T, int NMAX>
+static void case_not_pd(const char *name, int n, int bad) {
+  using H = typename Host<T>::type;
+  const int lda = n;
+  for (int upper = 0; upper < 2; ++upper) {
+    std::vector<H> A0, A1, A2, X1, X2;
+    spd<T, H>(n, lda, A0, 5);
+    A0[bad + (size_t)bad * lda] = H(-3);
+    A1 = A0; A2 = A0;
+    long i1 = 0, i2 = 0;
+    if (getenv("EMU_TRACE")) std::fprintf(stderr, "[not PD %s n=%d upper=%d] measured variant...\n", name, n, upper);
+    run_potf2_inv<T, NMAX, false>(upper, n, lda, A1, X1, &i1, 1000);
+    if (getenv("EMU_TRACE")) std::fprintf(stderr, "  V2...\n");
+    run_potf2_inv<T, NMAX, true>(upper, n, lda, A2, X2, &i2, 1000);
+    if (getenv("EMU_TRACE")) std::fprintf(stderr, "  done\n");
+    double e = 0;
+    for (size_t k = 0; k < A1.size(); ++k) e = std::max(e, ab(A1[k] - A2[k]));
+    char what[160];
+    std::snprintf(what, sizeof what, "%s potf2_inv %s n=%d not PD at column %d: info and partial factor agree", name, upper ? "upper" : "lower", n, bad);
+    check(i1 == 1000 + bad + 1 && i2 == i1 && e == 0.0, what, e);
+    // a kernel that finds *dinfo != 0 on entry must not touch anything
+    std::vector<H> A3 = A0, X3;
+    long i3 = 42;
+    run_potf2_inv<T, NMAX, true>(upper, n, lda, A3, X3, &i3, 0);
+    bool same = (i3 == 42);
+    for (size_t k = 0; k < A3.size(); ++k) same = same && (A3[k] == A0[k]);
+    check(same, "  ... and a block entered with info != 0 is left alone", 0);
+  }
+}
+
+// ---- the unfused kernels: potf2 (the last diagonal block of a factorisation), trti2, lauu2 ----
+template <typename T, int NMAX>
+static void case_unfused(const char *name, int n, double tol) {
+  using H = typename Host<T>::type;
+  const int lda = n + 1;
+  for (int upper = 0; upper < 2; ++upper) {
+    std::vector<H> A0, A;
+    spd<T, H>(n, lda, A0, 23u + n);
+    A = A0;
+    long info = 0;
+    T *dA = reinterpret_cast<T *>(A.data());
+    emu::launch(dim3(1), dim3(PANEL_THREADS), 0, [&] { potf2_kernel<T, NMAX / 32, NMAX / 16>(upper, n, dA, lda, &info, 7); });
+    std::vector<H> L = A0;
+    ref_potrf_lower(n, L, lda);
+    double e = 0, e_other = 0;
+    for (int j = 0; j < n; ++j)
+      for (int i = 0; i < n; ++i) {
+        const bool in_tri = upper ? (i <= j) : (i >= j);
+        if (in_tri) e = std::max(e, ab(A[i + (size_t)j * lda] - (upper ? cj(L[j + (size_t)i * lda]) : L[i + (size_t)j * lda])));
+        else e_other = std::max(e_other, ab(A[i + (size_t)j * lda] - A0[i + (size_t)j * lda]));
+      }
+    char what[160];
+    std::snprintf(what, sizeof what, "%s potf2 %s n=%d vs loops, other triangle untouched", name, upper ? "upper" : "lower", n);
+    check(info == 0 && e <= tol && e_other == 0.0, what, e);
+
+    // trti2 of that factor, out of place with the other triangle zeroed: X F = I
+    std::vector<H> X((size_t)lda * n, H(55));
+    T *dX = reinterpret_cast<T *>(X.data());
+    long tinfo = 0;
+    const size_t sm = ((size_t)(n | 1) * n + n) * sizeof(T);
+    emu::launch(dim3(1), dim3(PANEL_THREADS), sm, [&] {
+      trti2_kernel<T, NMAX / 32, NMAX / 16>(upper, 0, n, dA, lda, dX, lda, 1, &tinfo, 0);
+    });
+    double e_inv = 0;
+    for (int j = 0; j < n; ++j)
+      for (int i = 0; i < n; ++i) {
+        H sum = 0;
+        for (int k = 0; k < n; ++k) {
+          const bool fin = upper ? (k <= j) : (k >= j);
+          if (fin) sum += X[i + (size_t)k * lda] * A[k + (size_t)j * lda];  // X's other triangle is zero
+        }
+        e_inv = std::max(e_inv, ab(sum - H(i == j ? 1 : 0)));
+      }
+    std::snprintf(what, sizeof what, "%s trti2 %s n=%d: X F = I", name, upper ? "upper" : "lower", n);
+    check(tinfo == 0 && e_inv <= 50 * tol, what, e_inv);
+
+    // lauu2 of the factor: lower L^H L, upper U U^H, triangle only
+    std::vector<H> P = A;
+    T *dP = reinterpret_cast<T *>(P.data());
+    emu::launch(dim3(1), dim3(PANEL_THREADS), (size_t)(n | 1) * n * sizeof(T), [&] { lauu2_kernel<T>(upper, n, dP, lda); });
+    double e_l = 0;
+    for (int j = 0; j < n; ++j)
+      for (int i = 0; i < n; ++i) {
+        const bool in_tri = upper ? (i <= j) : (i >= j);
+        if (!in_tri) { e_l = std::max(e_l, ab(P[i + (size_t)j * lda] - A[i + (size_t)j * lda])); continue; }
+        H sum = 0;
+        for (int k = 0; k < n; ++k) {
+          if (!upper) { if (k >= i && k >= j) sum += cj(A[k + (size_t)i * lda]) * A[k + (size_t)j * lda]; }  // (L^H L)(i,j)
+          else if (k >= i && k >= j) sum += A[i + (size_t)k * lda] * cj(A[j + (size_t)k * lda]);              // (U U^H)(i,j)
+        }
+        e_l = std::max(e_l, ab(P[i + (size_t)j * lda] - sum));
+      }
+    std::snprintf(what, sizeof what, "%s lauu2 %s n=%d vs loops", name, upper ? "upper" : "lower", n);
+    check(e_l <= 200 * tol * n, what, e_l);
+  }
+  // potf2: a non-positive pivot
+  std::vector<H> A0;
+  spd<T, H>(n, n, A0, 3);
+  const int bad = n / 2;
+  A0[bad + (size_t)bad * n] = H(-1);
+  long info = 0;
+  T *dA = reinterpret_cast<T *>(A0.data());
+  emu::launch(dim3(1), dim3(PANEL_THREADS), 0, [&] { potf2_kernel<T, NMAX / 32, NMAX / 16>(0, n, dA, n, &info, 500); });
+  char what[160];
+  std::snprintf(what, sizeof what, "%s potf2 n=%d not PD at column %d: info", name, n, bad);
+  check(info == 500 + bad + 1, what, 0);
+}
+
+int main() {
+  std::setvbuf(stdout, nullptr, _IOLBF, 0);
+  if (!getenv("EMU_ONLY_NOT_PD")) {
+  case_potf2_inv<double, 128>("d", 128, 1e-12);
+  case_potf2_inv<double, 128>("d", 100, 1e-12);
+  case_potf2_inv<double, 128>("d", 37, 1e-12);
+  case_potf2_inv<double, 128>("d", 1, 1e-12);
+  case_potf2_inv<double2, 64>("z", 64, 1e-12);
+  case_potf2_inv<double2, 64>("z", 45, 1e-12);
+  case_potf2_inv<float, 128>("s", 97, 2e-4);
+  case_potf2_inv<float2, 128>("c", 80, 2e-4);
+  }
+  case_not_pd<double, 128>("d", 128, 70);
+  case_not_pd<double, 128>("d", 50, 0);
+  case_not_pd<double2, 64>("z", 64, 33);
+  case_unfused<double, 128>("d", 128, 1e-12);
+  case_unfused<double, 128>("d", 70, 1e-12);
+  case_unfused<double2, 64>("z", 50, 1e-12);
+  case_unfused<float, 128>("s", 90, 2e-4);
+  if (failures) { std::printf("EMU FAILED: %d mismatches\n", failures); return 1; }
+  std::printf("EMU PASSED\n");
+  return 0;
+}
