@@ -4,6 +4,10 @@
 #pragma once
 #ifndef CHOL_CPU_EMU
 #define CHOL_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define CHOL_CP_ASYNC_COMMIT() asm volatile("cp.async.commit_group;" ::: "memory")
+#define CHOL_CP_ASYNC_WAIT(n) asm volatile("cp.async.wait_group %0;" ::"n"(n) : "memory")
 #else
 #define CHOL_DYN_SMEM(name) unsigned char *name = emu::dyn_smem()
+#define CHOL_CP_ASYNC_COMMIT() emu::cp_async_commit()   /* the emulation completes a group as LATE as wait_group allows */
+#define CHOL_CP_ASYNC_WAIT(n) emu::cp_async_wait(n)
 #endif

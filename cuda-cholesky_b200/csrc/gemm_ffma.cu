@@ -58,13 +58,13 @@ __global__ void __launch_bounds__(256, 2) gemm_ffma_kernel(const __grid_constant
       f_fill<T, BM, BK, LDS>(As[s], p.A, p.lda, p.opA, p.triA, p.unitA, false, m0, p.M, rowsA, k0, ke, p.vecA, tid);
       f_fill<T, BN, BK, LDS>(Bs[s], p.B, p.ldb, p.opB, p.triB, p.unitB, true, g0, p.N, rowsB, k0, ke, p.vecB, tid);
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    CHOL_CP_ASYNC_COMMIT();
   };
 #pragma unroll
   for (int kt = 0; kt < ST - 1; ++kt) issue(kt);
 
   for (int kt = 0; kt < nk; ++kt) {
-    asm volatile("cp.async.wait_group %0;" ::"n"(ST - 2) : "memory");
+    CHOL_CP_ASYNC_WAIT(ST - 2);
     __syncthreads();          // stage kt has landed for everyone; stage kt-1 is no longer being read
     issue(kt + ST - 1);       // refill the slot that stage kt-1 used
     const int cur = kt % ST;
@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(256, 2) gemm_ffma_kernel(const __grid_constant
   }
 }
 
+#ifndef CHOL_CPU_EMU  // the launchers are not part of the CPU emulation (tests/emu)
 template <typename T>
 static int launch_f(const chol_gemm_desc *d) {
   using Cfg = FCfg<T>;
@@ -159,10 +160,14 @@ static int launch_f(const chol_gemm_desc *d) {
   return (int)cudaGetLastError();
 }
 
+#endif  // CHOL_CPU_EMU
+
 }  // namespace chol
 
+#ifndef CHOL_CPU_EMU
 int chol_gemm_fp32_launch(const chol_gemm_desc *d) {
   if (d->prec == 's') return chol::launch_f<float>(d);
   if (d->prec == 'c') return chol::launch_f<float2>(d);
   return (int)cudaErrorInvalidValue;
 }
+#endif  // CHOL_CPU_EMU

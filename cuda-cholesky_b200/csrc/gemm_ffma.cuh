@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include "chol_kernels.h"
+#include "emu_compat.cuh"
 #include "launch_count.h"
 #include "gemm_common.cuh"
 
@@ -43,9 +44,13 @@ __device__ __forceinline__ bool f_tri_clear(int tri, bool along_rows, int r0, in
 }
 template <int BYTES>
 __device__ __forceinline__ void f_cp_async(void *dst, const void *src) {
+#ifdef CHOL_CPU_EMU
+  emu::cp_async(dst, src, BYTES);
+#else
   const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
   if constexpr (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
   else asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(src), "n"(BYTES) : "memory");
+#endif
 }
 
 // One ROWS x BK operand tile -> shared [k][row] (pitch LDS).  Interior, unmasked tiles go through

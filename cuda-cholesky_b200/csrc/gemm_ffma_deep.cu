@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(256, 2) gemm_ffma_deep_kernel(const __grid_con
   using Cfg = FCfg<T>;
   constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = 16, LDS = Cfg::LDS, VW = Cfg::VW, TM = Cfg::TM, TN = Cfg::TN;
   constexpr int ST = 4;  // cp.async stages
-  extern __shared__ __align__(16) unsigned char f_dyn_smem[];
+  CHOL_DYN_SMEM(f_dyn_smem);
   typedef T Stage[BK * LDS];
   Stage *As = reinterpret_cast<Stage *>(f_dyn_smem), *Bs = As + ST;
 
@@ -78,13 +78,13 @@ __global__ void __launch_bounds__(256, 2) gemm_ffma_deep_kernel(const __grid_con
       pa += 2 * halfA;
       pb += 2 * halfB;
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    CHOL_CP_ASYNC_COMMIT();
   };
 #pragma unroll
   for (int kt = 0; kt < ST - 1; ++kt) issue(kt);
 
   for (int kt = 0; kt < nk; ++kt) {
-    asm volatile("cp.async.wait_group %0;" ::"n"(ST - 2) : "memory");
+    CHOL_CP_ASYNC_WAIT(ST - 2);
     __syncthreads();          // stage kt has landed for everyone; stage kt-1 is no longer being read
     issue(kt + ST - 1);       // refill the slot that stage kt-1 used
     const int cur = kt % ST;
@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(256, 2) gemm_ffma_deep_kernel(const __grid_con
   }
 }
 
+#ifndef CHOL_CPU_EMU  // the launchers are not part of the CPU emulation (tests/emu)
 template <typename T>
 static int deep_launch_t(const FArgs<T> &a, unsigned tiles, cudaStream_t st) {
   constexpr int bytes = 2 * 4 * 16 * FCfg<T>::LDS * (int)sizeof(T);
@@ -157,5 +158,6 @@ static int deep_launch_t(const FArgs<T> &a, unsigned tiles, cudaStream_t st) {
 
 int chol_gemm_fp32_deep_launch(const FArgs<float> &a, unsigned tiles, cudaStream_t st) { return deep_launch_t<float>(a, tiles, st); }
 int chol_gemm_fp32_deep_launch(const FArgs<float2> &a, unsigned tiles, cudaStream_t st) { return deep_launch_t<float2>(a, tiles, st); }
+#endif  // CHOL_CPU_EMU
 
 }  // namespace chol

@@ -50,6 +50,22 @@ struct Block {
 };
 
 inline Block *&current() { static Block *b = nullptr; return b; }
+
+// cp.async (LDGSTS) groups, completed as LATE as the program allows: a copy lands only when a
+// wait_group forces its group - the adversarial end of what the hardware may do, so code that
+// reads a stage before waiting for it reads stale data here.
+struct Copy { void *dst; const void *src; int bytes; };
+inline std::vector<Copy> &cp_open() { thread_local std::vector<Copy> v; return v; }
+inline std::vector<std::vector<Copy>> &cp_groups() { thread_local std::vector<std::vector<Copy>> v; return v; }
+inline void cp_async(void *dst, const void *src, int bytes) { cp_open().push_back(Copy{dst, src, bytes}); }
+inline void cp_async_commit() { cp_groups().push_back(cp_open()); cp_open().clear(); }
+inline void cp_async_wait(int keep) {
+  auto &g = cp_groups();
+  while ((int)g.size() > keep) {
+    for (const Copy &c : g.front()) std::memcpy(c.dst, c.src, (size_t)c.bytes);
+    g.erase(g.begin());
+  }
+}
 inline unsigned char *dyn_smem() {  // 16-byte aligned start of the block's dynamic shared memory
   auto p = reinterpret_cast<uintptr_t>(current()->dyn.data());
   return reinterpret_cast<unsigned char *>((p + 15) & ~uintptr_t(15));

@@ -1,7 +1,9 @@
 """Kernel LOGIC on the CPU: the CUDA sources of the diagonal-block kernels (csrc/panel_kernels.cu:
-potf2_inv in its measured and V2 variants, potf2, trti2, lauu2) and of the small-tile FP64 GEMM
-(csrc/gemm_small.cu) are compiled as host C++ behind tests/emu/cuda_emu.h - one OS thread per CUDA
-thread, real barriers, warp shuffles through a per-warp exchange - and run against plain loops.
+potf2_inv in its measured and V2 variants, potf2, trti2, lauu2), of the small-tile FP64 GEMM
+(csrc/gemm_small.cu) and of the FP32 GEMM engine (csrc/gemm_ffma.cu and its deeper-k variant
+csrc/gemm_ffma_deep.cu) are compiled as host C++ behind tests/emu/cuda_emu.h - one OS thread per CUDA
+thread, real barriers, warp shuffles through a per-warp exchange, cp.async groups that complete as
+late as wait_group allows - and run against plain loops.
 
 This is how variants written without GPU access get checked before they ever reach hardware; it
 also found a latent race in the measured potf2 kernels (a fast warp could raise the not-positive-
@@ -42,3 +44,11 @@ def test_panel_kernels_emulated(tmp_path):
 def test_small_gemm_kernel_emulated(tmp_path):
     out = _build_and_run("emu_small_gemm.cpp", tmp_path, 600)
     assert "147 cases" in out
+
+
+def test_fp32_gemm_engine_emulated(tmp_path):
+    """measured kernel and deep-k variant: ops, conjugation, triangular masks, unit diagonals, k-range
+    skip, triangle-only / Hermitian output, ragged edges, aligned and unaligned operands (s and c)"""
+    out = _build_and_run("emu_ffma.cpp", tmp_path, 1200)
+    assert "measured kernels: 86 cases so far, 0 mismatches" in out
+    assert "deep-k kernels: 172 cases so far, 0 mismatches" in out
