@@ -41,6 +41,7 @@
 #include <type_traits>
 
 #include "chol_kernels.h"
+#include "emu_compat.cuh"
 #include "launch_count.h"
 #include "gemm_common.cuh"
 #include "ptx_sm100.cuh"
@@ -472,7 +473,7 @@ __global__ void __launch_bounds__(GemmCfg<CPLX>::THREADS, 2) gemm_dmma_kernel(co
   using Cfg = GemmCfg<CPLX>;
   using T = typename GemmArgs<CPLX>::T;
   constexpr int BM = Cfg::BM, BN = Cfg::BN, ST = Cfg::STAGES;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  CHOL_DYN_SMEM128(smem_raw);
   T *As = reinterpret_cast<T *>(smem_raw);
   T *Bs = As + ST * Cfg::A_STAGE;
   uint64_t *full = reinterpret_cast<uint64_t *>(Bs + ST * Cfg::B_STAGE);
@@ -510,7 +511,7 @@ __global__ void __launch_bounds__(GemmCfg<CPLX>::PP_THREADS, 1) gemm_dmma_pp_ker
   using Cfg = GemmCfg<CPLX>;
   using T = typename GemmArgs<CPLX>::T;
   constexpr int BM = Cfg::BM, BN = Cfg::BN, ST = Cfg::STAGES;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  CHOL_DYN_SMEM128(smem_raw);
   constexpr int RING = ST * (Cfg::A_STAGE + Cfg::B_STAGE);  // elements per group
   T *base = reinterpret_cast<T *>(smem_raw);
   uint64_t *bars = reinterpret_cast<uint64_t *>(base + 2 * RING);  // [group][full ST | empty ST], then mid[2]
@@ -534,7 +535,7 @@ __global__ void __launch_bounds__(GemmCfg<CPLX>::PP_THREADS, 1) gemm_dmma_pp_ker
   // the 4 producer warps give registers back, the 8 consumer warps (64 accumulator doubles +
   // double-buffered fragments each) take them
   if (warp >= 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    CHOL_SETMAXNREG_DEC(56);
     const int gq = (warp - 8) >> 1;
     T *As = base + gq * RING, *Bs = As + ST * Cfg::A_STAGE;
     uint64_t *full = bars + gq * 2 * ST, *empty = full + ST;
@@ -547,6 +548,11 @@ __global__ void __launch_bounds__(GemmCfg<CPLX>::PP_THREADS, 1) gemm_dmma_pp_ker
       // stagger: group 0 waits for group 1's half-way mark of tile i-1, group 1 for group 0's of tile i
       if (gq == 0) { if (i >= 1) mbar_wait(&mid[1], (i - 1) & 1); }
       else mbar_wait(&mid[0], i & 1);
+      // Reconverge before lane 0 may pass a mark on: with independent thread scheduling nothing else
+      // stops lane 0 from leaving the poll loop first and - through empty slots, which take no time -
+      // running two marks ahead of its own warp, which the 1-bit parity cannot tell apart (the CPU
+      // emulation, where every lane is its own thread, does exactly that).
+      __syncwarp();
       if (valid) produce_tile<CPLX, MODE, 2>(p, bi, bj, As, Bs, full, empty, it, nullptr, warp & 1, lane);
       else if (lane == 0) mbar_arrive_n(&mid[gq], MODE == 0 ? 4 : 2);
       // (an empty slot passes its mark on behalf of the 4 consumer warps, but only after the gate
@@ -554,7 +560,7 @@ __global__ void __launch_bounds__(GemmCfg<CPLX>::PP_THREADS, 1) gemm_dmma_pp_ker
       //  fall two marks behind, which is what the 1-bit mbarrier phase can tell apart)
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    CHOL_SETMAXNREG_INC(224);
     const int gq = warp >> 2;
     const T *As = base + gq * RING, *Bs = As + ST * Cfg::A_STAGE;
     uint64_t *full = bars + gq * 2 * ST, *empty = full + ST;
@@ -584,12 +590,15 @@ static bool tma_eligible(const chol_gemm_desc *d) {
   return true;
 }
 
+// descriptor -> kernel arguments (host only, no CUDA calls: also used by the CPU emulation, tests/emu).
+// Returns 0 and sets `tiles` (0: nothing to do) and `tma`, or a cudaError_t value.
 template <bool CPLX>
-static int launch_t(const chol_gemm_desc *d) {
+static int fill_args(const chol_gemm_desc *d, GemmArgs<CPLX> &a, long long &tiles, bool &tma) {
   using Cfg = GemmCfg<CPLX>;
   using T = typename GemmArgs<CPLX>::T;
+  tiles = 0;
+  tma = false;
   if (d->m == 0 || d->n == 0) return 0;
-  GemmArgs<CPLX> a;
   a.A = (const T *)d->A; a.B = (const T *)d->B; a.C = (const T *)d->C; a.D = (T *)d->D;
   a.lda = (long long)d->lda; a.ldb = (long long)d->ldb; a.ldc = (long long)d->ldc; a.ldd = (long long)d->ldd;
   a.M = (int)d->m; a.N = (int)d->n; a.K = (int)d->k;
@@ -620,12 +629,28 @@ static int launch_t(const chol_gemm_desc *d) {
   a.conjB_regs = CPLX && d->opB == 'C';
   a.cm.cnb = d->cyc_nb; a.cm.cP = d->cyc_p; a.cm.coff = d->cyc_off;
   if (a.cm.cnb && (a.cm.cnb % Cfg::BN || a.cuplo == 2 || d->triA || d->triB || a.cm.cP < 1)) return (int)cudaErrorInvalidValue;
-  const bool tma = !alpha_zero && tma_eligible<CPLX>(d);
+  tma = !alpha_zero && tma_eligible<CPLX>(d);
   a.group = (a.NI >= 2 * Cfg::GROUP && a.NJ >= 2 * Cfg::GROUP) ? Cfg::GROUP : 8;  // big in both dimensions
-  const long long tiles = total_tiles<Cfg::BM, Cfg::BN>(a.group, a.cuplo, a.NI, a.NJ, a.cm);
-  if (tiles <= 0) return 0;
+  tiles = total_tiles<Cfg::BM, Cfg::BN>(a.group, a.cuplo, a.NI, a.NJ, a.cm);
+  if (tiles <= 0) { tiles = 0; return 0; }
+  if (tiles > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
   a.total_tiles = tiles;
   build_sched_table<Cfg::BM, Cfg::BN>(a.tb, a.group, a.cuplo, a.NI, a.NJ, a.cm);
+  a.prefetch_c = 0;
+  a.stage_c = 1;
+  a.tps = 8;
+  return 0;
+}
+
+#ifndef CHOL_CPU_EMU  // the launchers are not part of the CPU emulation (tests/emu)
+template <bool CPLX>
+static int launch_t(const chol_gemm_desc *d) {
+  using Cfg = GemmCfg<CPLX>;
+  GemmArgs<CPLX> a;
+  long long tiles = 0;
+  bool tma = false;
+  const int rc = fill_args<CPLX>(d, a, tiles, tma);
+  if (rc != 0 || tiles == 0) return rc;
   cudaStream_t st = (cudaStream_t)d->stream;
   // per-device one-time setup; launch_t runs concurrently on the worker threads of the multi-GPU
   // runtime (one device each), so the flags are atomics and the attribute calls are idempotent
@@ -665,7 +690,6 @@ static int launch_t(const chol_gemm_desc *d) {
   const int persist = tun.persist, prefetch = tun.prefetch, pingpong = tun.pingpong, tps = tun.tps, stagec = tun.stagec;
   a.prefetch_c = prefetch;
   a.stage_c = stagec;
-  if (tiles > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
   const int sms = sm_count[dev & 63].load(std::memory_order_relaxed);
   if ((pingpong < 0 ? CPLX : pingpong != 0) && tiles >= 4LL * sms && a.K > 0) {  // (K = 0: no stages to pace the groups with)
     a.tps = tps;
@@ -679,8 +703,11 @@ static int launch_t(const chol_gemm_desc *d) {
   return (int)cudaGetLastError();
 }
 
+#endif  // CHOL_CPU_EMU
+
 }  // namespace chol
 
+#ifndef CHOL_CPU_EMU
 int chol_gemm_fp32_launch(const chol_gemm_desc *d);  // gemm_ffma.cu
 extern "C" int chol_gemm_small_eligible(const chol_gemm_desc *d);  // gemm_small.cu (CHOL_SMALL_GEMM=1, off by default)
 extern "C" int chol_gemm_small_launch(const chol_gemm_desc *d);
@@ -725,3 +752,4 @@ extern "C" int chol_gemm_uses_tma(const chol_gemm_desc *d) {
   if (d->prec == 'z') return chol::tma_eligible<true>(d) ? 1 : 0;
   return 0;
 }
+#endif  // CHOL_CPU_EMU

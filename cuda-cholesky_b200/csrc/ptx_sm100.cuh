@@ -7,6 +7,10 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#ifdef CHOL_CPU_EMU
+#include "ptx_emu.h"  // tests/emu: CPU stand-ins with the same names and signatures
+#else
+
 namespace chol {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -74,3 +78,5 @@ __device__ __forceinline__ void dmma_884(double &d0, double &d1, double a, doubl
 }
 
 }  // namespace chol
+
+#endif  // CHOL_CPU_EMU

@@ -46,7 +46,7 @@ struct Block {
   Barrier bar;
   std::vector<Warp> warps;
   std::vector<unsigned char> dyn;
-  explicit Block(unsigned n, size_t dyn_bytes) : nthreads(n), bar(n), warps((n + 31) / 32), dyn(dyn_bytes + 64) {}
+  explicit Block(unsigned n, size_t dyn_bytes) : nthreads(n), bar(n), warps((n + 31) / 32), dyn(dyn_bytes + 256) {}
 };
 
 inline Block *&current() { static Block *b = nullptr; return b; }
@@ -66,9 +66,9 @@ inline void cp_async_wait(int keep) {
     g.erase(g.begin());
   }
 }
-inline unsigned char *dyn_smem() {  // 16-byte aligned start of the block's dynamic shared memory
+inline unsigned char *dyn_smem() {  // 128-byte aligned start of the block's dynamic shared memory
   auto p = reinterpret_cast<uintptr_t>(current()->dyn.data());
-  return reinterpret_cast<unsigned char *>((p + 15) & ~uintptr_t(15));
+  return reinterpret_cast<unsigned char *>((p + 127) & ~uintptr_t(127));
 }
 
 }  // namespace emu

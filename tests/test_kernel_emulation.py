@@ -3,7 +3,11 @@ potf2_inv in its measured and V2 variants, potf2, trti2, lauu2), of the small-ti
 (csrc/gemm_small.cu) and of the FP32 GEMM engine (csrc/gemm_ffma.cu and its deeper-k variant
 csrc/gemm_ffma_deep.cu) are compiled as host C++ behind tests/emu/cuda_emu.h - one OS thread per CUDA
 thread, real barriers, warp shuffles through a per-warp exchange, cp.async groups that complete as
-late as wait_group allows - and run against plain loops.
+late as wait_group allows - and run against plain loops.  The FP64 tensor-core engine (csrc/gemm_dmma.cu)
+runs the same way on top of tests/emu/ptx_emu.h: mbarriers with phase / arrival / transaction-byte
+accounting and blocking waits, TMA bulk rows, cp.async with barrier arrival, the m8n8k4 MMA as a warp
+exchange - so the producer / consumer protocol of all three schedules is exercised, and a protocol
+deadlock blocks here (watchdog report: who waits on which barrier) instead of on a GPU.
 
 This is how variants written without GPU access get checked before they ever reach hardware; it
 also found a latent race in the measured potf2 kernels (a fast warp could raise the not-positive-
@@ -12,6 +16,7 @@ left the block one barrier short).  It does not replace the GPU parity tests: on
 follow from the program's barrier structure show up here, and nothing about speed."""
 import os
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 
 import pytest
 
@@ -23,32 +28,59 @@ INC = ["-I" + EMU, "-I/usr/local/cuda/include", "-I" + os.path.join(ROOT, "cuda-
        "-I" + os.path.join(ROOT, "include")]
 
 
-def _build_and_run(src, tmp_path, timeout):
+HARNESSES = {"emu_panel.cpp": 900, "emu_small_gemm.cpp": 600, "emu_ffma.cpp": 1200, "emu_dmma.cpp": 1500}
+
+
+def _build_and_run(src, tmpdir, timeout):
+    exe = os.path.join(tmpdir, os.path.splitext(src)[0])
+    try:
+        subprocess.check_call(["g++", "-std=c++17", "-O1", *INC, os.path.join(EMU, src), "-o", exe, "-lpthread"])
+        p = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=timeout,
+                           env=dict(os.environ, EMU_WATCHDOG=str(timeout - 60)))
+        return p.returncode, p.stdout.decode()
+    except (subprocess.CalledProcessError, subprocess.TimeoutExpired) as e:
+        return -1, "%r" % (e,)
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    """all four harnesses are built and run side by side (they mostly sleep in barriers)"""
     if not os.path.exists("/usr/local/cuda/include/cuda_runtime.h"):
         pytest.skip("CUDA headers not installed")
-    exe = str(tmp_path / os.path.splitext(src)[0])
-    subprocess.check_call(["g++", "-std=c++17", "-O1", *INC, os.path.join(EMU, src), "-o", exe, "-lpthread"])
-    p = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=timeout)
-    out = p.stdout.decode()
-    assert p.returncode == 0 and "EMU PASSED" in out, out[-4000:]
+    tmpdir = str(tmp_path_factory.mktemp("emu"))
+    with ThreadPoolExecutor(max_workers=len(HARNESSES)) as ex:
+        futs = {src: ex.submit(_build_and_run, src, tmpdir, t) for src, t in HARNESSES.items()}
+        return {src: f.result() for src, f in futs.items()}
+
+
+def _passed(emu, src):
+    rc, out = emu[src]
+    assert rc == 0 and "EMU PASSED" in out and "MISMATCH" not in out, out[-4000:]
     return out
 
 
-def test_panel_kernels_emulated(tmp_path):
-    out = _build_and_run("emu_panel.cpp", tmp_path, 900)
-    assert "MISMATCH" not in out
+def test_panel_kernels_emulated(emu):
+    out = _passed(emu, "emu_panel.cpp")
     assert out.count("V2 == measured variant") >= 16  # d, z, s, c x lower/upper x full and ragged blocks
     assert out.count("not PD") >= 6
 
 
-def test_small_gemm_kernel_emulated(tmp_path):
-    out = _build_and_run("emu_small_gemm.cpp", tmp_path, 600)
-    assert "147 cases" in out
+def test_small_gemm_kernel_emulated(emu):
+    assert "147 cases" in _passed(emu, "emu_small_gemm.cpp")
 
 
-def test_fp32_gemm_engine_emulated(tmp_path):
+def test_fp32_gemm_engine_emulated(emu):
     """measured kernel and deep-k variant: ops, conjugation, triangular masks, unit diagonals, k-range
     skip, triangle-only / Hermitian output, ragged edges, aligned and unaligned operands (s and c)"""
-    out = _build_and_run("emu_ffma.cpp", tmp_path, 1200)
+    out = _passed(emu, "emu_ffma.cpp")
     assert "measured kernels: 86 cases so far, 0 mismatches" in out
     assert "deep-k kernels: 172 cases so far, 0 mismatches" in out
+
+
+def test_fp64_tensor_core_engine_emulated(emu):
+    """classic (TMA-staged C epilogue), persistent and staggered schedules; TMA and generic loaders; d and z;
+    triangular masks, triangle-only / Hermitian output, block-cyclic column map, K = 0"""
+    out = _passed(emu, "emu_dmma.cpp")
+    assert "44 cases" in out
+    for sched in ("classic", "persistent", "staggered"):
+        assert out.count(sched) >= 4
