@@ -1,0 +1,280 @@
+// mock_kernels.cpp — TEST INFRASTRUCTURE ONLY.  The launcher ABI of csrc/chol_kernels.h implemented
+// as plain CPU loops that follow the documented semantics of each launcher (not the kernels' code):
+// with tests/mock/mock_cuda.c this lets the host drivers run without a GPU
+// (tests/test_host_drivers_mock.py).  Every "launch" completes before it returns.
+#include <cmath>
+#include <complex>
+#include <cstring>
+#include <vector>
+
+#include "../../cuda-cholesky_b200/csrc/chol_kernels.h"
+
+namespace {
+
+unsigned long long launches = 0;
+template <typename T> struct RealOf { using type = T; };
+template <typename R> struct RealOf<std::complex<R>> { using type = R; };
+template <typename T> T cj(T x) { return x; }
+template <typename R> std::complex<R> cj(std::complex<R> x) { return std::conj(x); }
+template <typename T> double re(T x) { return (double)std::real(x); }
+template <typename T> T from_re(double r) { return T((typename RealOf<T>::type)r); }
+
+long long gcol(const chol_gemm_desc *d, long long n) {
+  return d->cyc_nb ? ((n / d->cyc_nb) * d->cyc_p + d->cyc_off) * d->cyc_nb + n % d->cyc_nb : n;
+}
+
+template <typename T>
+int gemm_t(const chol_gemm_desc *d) {
+  constexpr bool CPLX = !std::is_same<typename RealOf<T>::type, T>::value;
+  using W = typename std::conditional<CPLX, std::complex<double>, double>::type;  // accumulate in double
+  const T *A = (const T *)d->A, *B = (const T *)d->B, *C = (const T *)d->C;
+  T *D = (T *)d->D;
+  const size_t M = d->m, N = d->n, K = d->k;
+  W alpha, beta;
+  if constexpr (CPLX) { alpha = W(d->alpha[0], d->alpha[1]); beta = W(d->beta[0], d->beta[1]); }
+  else { alpha = d->alpha[0]; beta = d->beta[0]; }
+  const bool alpha_zero = alpha == W(0), beta_zero = beta == W(0);
+  if (d->cyc_nb && (d->opB == 'N' || d->cuplo == 'U' || d->triA || d->triB)) return 1;
+  // op(A) as a dense M x K array and op(B) as K x N (N = local columns; the B row of local column n is
+  // its GLOBAL column), masks and implicit unit diagonals applied: then the product is a plain loop nest
+  std::vector<W> Aop(M * K), Bop(K * N);
+  for (size_t k = 0; k < K && !alpha_zero; ++k)
+    for (size_t m = 0; m < M; ++m) {
+      const size_t r = d->opA == 'N' ? m : k, c = d->opA == 'N' ? k : m;
+      W v;
+      if ((d->triA == 'L' && r < c) || (d->triA == 'U' && r > c)) v = W(0);
+      else if (d->triA && d->unitA && r == c) v = W(1);
+      else v = W(A[r + c * d->lda]);
+      if constexpr (CPLX) { if (d->opA == 'C') v = std::conj(v); }
+      Aop[m + k * M] = v;
+    }
+  for (size_t n = 0; n < N && !alpha_zero; ++n) {
+    const size_t ng = (size_t)gcol(d, (long long)n);
+    for (size_t k = 0; k < K; ++k) {
+      const size_t r = d->opB == 'N' ? k : ng, c = d->opB == 'N' ? ng : k;
+      W v;
+      if ((d->triB == 'L' && r < c) || (d->triB == 'U' && r > c)) v = W(0);
+      else if (d->triB && d->unitB && r == c) v = W(1);
+      else v = W(B[r + c * d->ldb]);
+      if constexpr (CPLX) { if (d->opB == 'C') v = std::conj(v); }
+      Bop[k + n * K] = v;
+    }
+  }
+  // every output element depends on C(m,n) alone, so C == D is fine; operands may alias D (the drivers
+  // route such products through scratch, but a spec implementation should not care): finish the whole
+  // product before the first store
+  std::vector<W> acc(M * N, W(0));
+  if (!alpha_zero)
+    for (size_t n = 0; n < N; ++n)
+      for (size_t k = 0; k < K; ++k) {
+        const W b = Bop[k + n * K];
+        if (b == W(0)) continue;
+        W *an = &acc[n * M];
+        const W *ak = &Aop[k * M];
+        for (size_t m = 0; m < M; ++m) an[m] += ak[m] * b;
+      }
+  for (size_t n = 0; n < N; ++n) {
+    const size_t ng = (size_t)gcol(d, (long long)n);
+    for (size_t m = 0; m < M; ++m) {
+      if ((d->cuplo == 'L' && m < ng) || (d->cuplo == 'U' && m > ng)) continue;
+      W o = alpha * acc[m + n * M];
+      if (!beta_zero) o += beta * W(C[m + n * d->ldc]);
+      if constexpr (CPLX) {
+        if (d->herm && m == ng) o = W(o.real(), 0.0);
+        D[m + n * d->ldd] = T((typename RealOf<T>::type)o.real(), (typename RealOf<T>::type)o.imag());
+      } else {
+        D[m + n * d->ldd] = (T)o;
+      }
+    }
+  }
+  return 0;
+}
+
+// lower-form view of a triangle stored as uplo: L(i,c) for i >= c
+template <typename T> T getL(const T *A, size_t lda, bool upper, size_t i, size_t c) { return upper ? cj(A[c + i * lda]) : A[i + c * lda]; }
+template <typename T> void putL(T *A, size_t lda, bool upper, size_t i, size_t c, T v) { if (upper) A[c + i * lda] = cj(v); else A[i + c * lda] = v; }
+
+template <typename T>
+int potf2_t(bool upper, size_t n, T *A, size_t lda, long *dinfo, long base, T *X, size_t ldx) {
+  if (*dinfo != 0) return 0;
+  std::vector<T> L(n * n, T(0));
+  for (size_t c = 0; c < n; ++c)
+    for (size_t i = c; i < n; ++i) L[i + c * n] = getL(A, lda, upper, i, c);
+  for (size_t c = 0; c < n; ++c) {
+    const double dd = re(L[c + c * n]);
+    if (!(dd > 0)) {
+      *dinfo = base + (long)c + 1;
+      A[c + c * lda] = from_re<T>(dd);
+      return 0;  // the columns finished so far have been written, nothing else is touched
+    }
+    const double r = std::sqrt(dd);
+    L[c + c * n] = from_re<T>(r);
+    putL(A, lda, upper, c, c, L[c + c * n]);
+    for (size_t i = c + 1; i < n; ++i) {
+      L[i + c * n] = L[i + c * n] / from_re<T>(r);
+      putL(A, lda, upper, i, c, L[i + c * n]);
+    }
+    for (size_t k = c + 1; k < n; ++k)
+      for (size_t i = k; i < n; ++i) L[i + k * n] -= L[i + c * n] * cj(L[k + c * n]);
+  }
+  if (X != nullptr) {  // X := inverse of the factor, uplo triangle, other triangle zero
+    for (size_t j = 0; j < n; ++j) {
+      std::vector<T> x(n, T(0));
+      x[j] = T(1) / L[j + j * n];
+      for (size_t i = j + 1; i < n; ++i) {
+        T s = 0;
+        for (size_t k = j; k < i; ++k) s += L[i + k * n] * x[k];
+        x[i] = -s / L[i + i * n];
+      }
+      for (size_t i = 0; i < n; ++i) {
+        const T v = i >= j ? x[i] : T(0);
+        if (!upper) X[i + j * ldx] = v; else X[j + i * ldx] = cj(v);
+      }
+    }
+  }
+  return 0;
+}
+
+template <typename T>
+int trti2_t(bool upper, bool unit, size_t n, const T *A, size_t lda, T *B, size_t ldb, int zero_other, long *dinfo, long base) {
+  if (*dinfo != 0) return 0;
+  std::vector<T> L(n * n, T(0));  // lower form WITHOUT conjugation: inv(U) = (inv(U^T))^T
+  for (size_t c = 0; c < n; ++c)
+    for (size_t i = c; i < n; ++i) L[i + c * n] = upper ? A[c + i * lda] : A[i + c * lda];
+  if (!unit) {
+    long lo = -1, hi = -1;
+    for (size_t i = 0; i < n; ++i)
+      if (L[i + i * n] == T(0)) { if (lo < 0) lo = (long)i; hi = (long)i; }
+    if (hi >= 0) { *dinfo = base + (upper ? lo : hi) + 1; return 0; }  // the reference's sweep direction
+  }
+  for (size_t j = 0; j < n; ++j) {
+    std::vector<T> x(n, T(0));
+    x[j] = unit ? T(1) : T(1) / L[j + j * n];
+    for (size_t i = j + 1; i < n; ++i) {
+      T s = 0;
+      for (size_t k = j; k < i; ++k) s += L[i + k * n] * x[k];
+      x[i] = unit ? -s : -s / L[i + i * n];
+    }
+    for (size_t i = 0; i < n; ++i) {
+      if (i >= j) { if (!upper) B[i + j * ldb] = x[i]; else B[j + i * ldb] = x[i]; }
+      else if (zero_other) { if (!upper) B[i + j * ldb] = T(0); else B[j + i * ldb] = T(0); }
+    }
+  }
+  return 0;
+}
+
+template <typename T>
+int lauu2_t(bool upper, size_t n, T *A, size_t lda) {
+  std::vector<T> L(n * n, T(0));  // lower form with conjugation: upper U -> L = U^H, U U^H = L^H L
+  for (size_t c = 0; c < n; ++c)
+    for (size_t i = c; i < n; ++i) L[i + c * n] = getL(A, lda, upper, i, c);
+  for (size_t b = 0; b < n; ++b)
+    for (size_t a = b; a < n; ++a) {
+      T acc = 0;
+      for (size_t k = a; k < n; ++k) acc += cj(L[k + a * n]) * L[k + b * n];
+      if (!upper) A[a + b * lda] = acc; else A[b + a * lda] = cj(acc);
+    }
+  return 0;
+}
+
+bool keep(int uplo, size_t r, size_t c) {
+  return uplo == 0 || (uplo == 'L' && r >= c) || (uplo == 'U' && r <= c) || (uplo == 'l' && r > c) || (uplo == 'u' && r < c);
+}
+template <typename T>
+int copy_t(int trans, int uplo, size_t m, size_t n, const T *A, size_t lda, T *B, size_t ldb) {
+  for (size_t c = 0; c < n; ++c)
+    for (size_t r = 0; r < m; ++r) {
+      if (!keep(uplo, r, c)) continue;
+      if (trans == 'N') B[r + c * ldb] = A[r + c * lda];
+      else B[c + r * ldb] = trans == 'C' ? cj(A[r + c * lda]) : A[r + c * lda];
+    }
+  return 0;
+}
+template <typename T>
+int fill_t(int uplo, size_t m, size_t n, T v, T *A, size_t lda) {
+  for (size_t c = 0; c < n; ++c)
+    for (size_t r = 0; r < m; ++r)
+      if (uplo == 0 || (uplo == 'L' && r > c) || (uplo == 'U' && r < c)) A[r + c * lda] = v;
+  return 0;
+}
+
+}  // namespace
+
+#define DISPATCH(prec, CALL)                                           \
+  switch (prec) {                                                      \
+    case 's': { using T = float; return CALL; }                        \
+    case 'd': { using T = double; return CALL; }                       \
+    case 'c': { using T = std::complex<float>; return CALL; }          \
+    case 'z': { using T = std::complex<double>; return CALL; }         \
+    default: return 1;                                                 \
+  }
+
+extern "C" {
+unsigned long long chol_launch_count(int reset) { const unsigned long long v = launches; if (reset) launches = 0; return v; }
+int chol_diag_max(int prec) { return prec == 'z' ? 64 : 128; }
+int chol_gemm_uses_tma(const chol_gemm_desc *) { return 0; }
+int chol_probe_fp64(int, int, double *tflops, float *ms) { *tflops = 1.0; if (ms) *ms = 1.0f; return 0; }
+size_t chol_logdet_scratch_bytes(void) { return 4096; }
+
+int chol_gemm_launch(const chol_gemm_desc *d) {
+  ++launches;
+  if (d->m == 0 || d->n == 0) return 0;
+  DISPATCH(d->prec, gemm_t<T>(d));
+}
+int chol_potf2_launch(int prec, int uplo, size_t n, void *A, size_t lda, long *dinfo, long base, void *) {
+  ++launches;
+  if (n == 0) return 0;
+  if (n > (size_t)chol_diag_max(prec)) return 1;
+  DISPATCH(prec, potf2_t<T>(uplo == 'U', n, (T *)A, lda, dinfo, base, (T *)nullptr, 0));
+}
+int chol_potf2_inv_launch(int prec, int uplo, size_t n, void *A, size_t lda, void *X, size_t ldx, long *dinfo, long base, void *) {
+  ++launches;
+  if (n == 0) return 0;
+  if (n > (size_t)chol_diag_max(prec)) return 1;
+  DISPATCH(prec, potf2_t<T>(uplo == 'U', n, (T *)A, lda, dinfo, base, (T *)X, ldx));
+}
+int chol_trti2_launch(int prec, int uplo, int diag, size_t n, const void *A, size_t lda, void *B, size_t ldb, int zero_other, long *dinfo,
+                      long base, void *) {
+  ++launches;
+  if (n == 0) return 0;
+  if (n > (size_t)chol_diag_max(prec)) return 1;
+  DISPATCH(prec, trti2_t<T>(uplo == 'U', diag == 'U', n, (const T *)A, lda, (T *)B, ldb, zero_other, dinfo, base));
+}
+int chol_lauu2_launch(int prec, int uplo, size_t n, void *A, size_t lda, void *) {
+  ++launches;
+  if (n == 0) return 0;
+  if (n > (size_t)chol_diag_max(prec)) return 1;
+  DISPATCH(prec, lauu2_t<T>(uplo == 'U', n, (T *)A, lda));
+}
+int chol_copy_launch(int prec, int trans, int uplo, size_t m, size_t n, const void *A, size_t lda, void *B, size_t ldb, void *) {
+  ++launches;
+  if (m == 0 || n == 0) return 0;
+  DISPATCH(prec, copy_t<T>(trans, uplo, m, n, (const T *)A, lda, (T *)B, ldb));
+}
+int chol_fill_launch(int prec, int uplo, size_t m, size_t n, double re_, double im_, void *A, size_t lda, void *) {
+  ++launches;
+  if (m == 0 || n == 0) return 0;
+  switch (prec) {
+    case 's': return fill_t<float>(uplo, m, n, (float)re_, (float *)A, lda);
+    case 'd': return fill_t<double>(uplo, m, n, re_, (double *)A, lda);
+    case 'c': return fill_t<std::complex<float>>(uplo, m, n, std::complex<float>((float)re_, (float)im_), (std::complex<float> *)A, lda);
+    case 'z': return fill_t<std::complex<double>>(uplo, m, n, std::complex<double>(re_, im_), (std::complex<double> *)A, lda);
+    default: return 1;
+  }
+}
+int chol_logdet_launch(int prec, const void *x, size_t incx, size_t n, void *dresult, void *, void *) {
+  ++launches;
+  double s = 0.0;
+  for (size_t i = 0; i < n; ++i) {
+    switch (prec) {
+      case 's': s += (double)std::log(((const float *)x)[i * incx]); break;
+      case 'd': s += std::log(((const double *)x)[i * incx]); break;
+      case 'c': s += (double)std::log(((const std::complex<float> *)x)[i * incx].real()); break;
+      case 'z': s += std::log(((const std::complex<double> *)x)[i * incx].real()); break;
+      default: return 1;
+    }
+  }
+  if (prec == 's' || prec == 'c') *(float *)dresult = (float)(2.0 * s); else *(double *)dresult = 2.0 * s;
+  return 0;
+}
+}

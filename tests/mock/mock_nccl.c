@@ -1,0 +1,59 @@
+/*
+ * mock_nccl.c — TEST INFRASTRUCTURE ONLY: a libnccl.so.2 stand-in for the single-process,
+ * one-thread-per-GPU form (ncclCommInitAll) used by the cuMultiGPU* drivers, so that the
+ * distributed factorisation's control flow (ownership, panel broadcast order, look-ahead, info
+ * combination) can run on a machine without GPUs (tests/test_host_drivers_mock.py).  A broadcast is a
+ * rendezvous of the group's threads: the root publishes its buffer, the others copy from it.
+ */
+#define _GNU_SOURCE
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct { char internal[128]; } ncclUniqueId;
+struct group { int n; pthread_barrier_t bar; const void *src; int refs; };
+struct comm { struct group *g; int rank; };
+typedef struct comm *ncclComm_t;
+
+const char *ncclGetErrorString(int e) { return e == 0 ? "no error" : "mock NCCL error"; }
+int ncclGetUniqueId(ncclUniqueId *id) { memset(id, 0, sizeof *id); return 0; }
+int ncclGroupStart(void) { return 0; }
+int ncclGroupEnd(void) { return 0; }
+
+int ncclCommInitAll(ncclComm_t *comms, int n, const int *devs) {
+  (void)devs;
+  struct group *g = calloc(1, sizeof *g);
+  if (g == NULL) return 1;
+  g->n = n;
+  g->refs = n;
+  pthread_barrier_init(&g->bar, NULL, (unsigned)n);
+  for (int i = 0; i < n; i++) {
+    comms[i] = calloc(1, sizeof **comms);
+    comms[i]->g = g;
+    comms[i]->rank = i;
+  }
+  return 0;
+}
+/* one process per GPU is not something a single test process can stand in for */
+int ncclCommInitRank(ncclComm_t *c, int n, ncclUniqueId id, int rank) { (void)c; (void)n; (void)id; (void)rank; return 3; }
+int ncclCommInitRankConfig(ncclComm_t *c, int n, ncclUniqueId id, int rank, void *cfg) { (void)cfg; return ncclCommInitRank(c, n, id, rank); }
+
+int ncclCommDestroy(ncclComm_t c) {
+  if (__sync_sub_and_fetch(&c->g->refs, 1) == 0) {
+    pthread_barrier_destroy(&c->g->bar);
+    free(c->g);
+  }
+  free(c);
+  return 0;
+}
+
+int ncclBroadcast(const void *send, void *recv, size_t count, int dtype, int root, ncclComm_t c, void *stream) {
+  (void)stream;
+  if (dtype != 1 /* ncclUint8: the library broadcasts bytes */) return 4;
+  struct group *g = c->g;
+  if (c->rank == root) g->src = send;
+  pthread_barrier_wait(&g->bar);
+  if (c->rank != root && recv != g->src) memcpy(recv, g->src, count);
+  pthread_barrier_wait(&g->bar);
+  return 0;
+}

@@ -1,0 +1,68 @@
+"""The C host drivers (cuda-cholesky_b200/host/*.c) run end to end WITHOUT a GPU on a mock back
+end: tests/mock/mock_cuda.c (the ~30 CUDA driver entry points the host code uses; "device" memory is
+host memory, every stream operation is immediate), tests/mock/mock_kernels.cpp (the launcher ABI of
+csrc/chol_kernels.h as plain loops written from the launchers' documented semantics) and
+tests/mock/mock_nccl.c (libnccl.so.2 as a rendezvous of the worker threads).  The product sources are
+compiled unchanged; only what they link against differs.  tests/mock/run_host_driver_checks.py then
+compares every driver with the CPU oracle, on 1 and on 3 mock devices:
+
+  blocked POTRF with look-ahead and the diagonal-block recursion, TRTRI, LAUUM, POTRI, POTRS, logdet,
+  TRSM / TRMM in all side / uplo / trans / diag variants, `info` for non-PD and singular inputs,
+  argument errors, context push/pop balance, allocation balance, the CUmultiGPU runtime, the
+  distributed POTRF (ownership, broadcast order, block-cyclic update, page-locked overlapped
+  download and - CHOL_MGPU_H2D_OVERLAP - upload paths), the slab-distributed inverse
+  (CHOL_MGPU_INVERSE=slab), the host-pointer BLAS, and a device allocation failure that must fail
+  the call on every rank instead of leaving some of them in a broadcast.
+
+Synchronous streams cannot show ordering bugs and plain-loop kernels say nothing about the CUDA
+kernels: those are the jobs of tests/test_kernel_emulation.py and of the GPU parity tests."""
+import glob
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+import pytest
+
+import harness as H
+
+ROOT = H.ROOT
+MOCK = os.path.join(ROOT, "tests", "mock")
+INC = ["-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include"]
+
+
+@pytest.fixture(scope="module")
+def mock_runs(tmp_path_factory):
+    if not os.path.exists("/usr/local/cuda/include/cuda.h"):
+        pytest.skip("CUDA headers not installed")
+    d = str(tmp_path_factory.mktemp("mock"))
+    objs = []
+    for src in sorted(glob.glob(os.path.join(ROOT, "cuda-cholesky_b200", "host", "*.c"))) + [os.path.join(MOCK, "mock_cuda.c")]:
+        o = os.path.join(d, os.path.basename(src)[:-2] + ".o")
+        subprocess.check_call(["gcc", "-std=c99", "-O1", "-fPIC", "-D_POSIX_C_SOURCE=200809L", *INC, "-c", src, "-o", o])
+        objs.append(o)
+    ko = os.path.join(d, "mock_kernels.o")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-c", os.path.join(MOCK, "mock_kernels.cpp"), "-o", ko])
+    lib = os.path.join(d, "libcholesky_b200_mock.so")
+    subprocess.check_call(["g++", "-shared", "-o", lib, *objs, ko, "-lpthread", "-ldl", "-lm"])
+    subprocess.check_call(["gcc", "-std=c99", "-O1", "-fPIC", "-shared", os.path.join(MOCK, "mock_nccl.c"), "-o",
+                           os.path.join(d, "libnccl.so.2"), "-lpthread"])
+    env = dict(os.environ, LD_LIBRARY_PATH=d + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""),
+               OMP_NUM_THREADS="2")  # four groups run side by side: keep the oracle's OpenMP teams small
+
+    def run(group):
+        p = subprocess.run([sys.executable, os.path.join(MOCK, "run_host_driver_checks.py"), lib, group], stdout=subprocess.PIPE,
+                           stderr=subprocess.STDOUT, env=env, timeout=1500)
+        return p.returncode, p.stdout.decode()
+
+    groups = ("lapack", "blas", "multi1", "multi3")
+    with ThreadPoolExecutor(max_workers=len(groups)) as ex:
+        return dict(zip(groups, ex.map(run, groups)))
+
+
+@pytest.mark.parametrize("group,min_checks", [("lapack", 700), ("blas", 80), ("multi1", 800), ("multi3", 800)])
+def test_host_drivers_on_mock_backend(mock_runs, group, min_checks):
+    rc, out = mock_runs[group]
+    assert rc == 0 and "MOCK PASSED" in out, out[-3000:]
+    n = int([l for l in out.splitlines() if l.endswith(" checks")][-1].split()[0])
+    assert n >= min_checks
