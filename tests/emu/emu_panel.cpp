@@ -231,6 +231,67 @@ static void case_unfused(const char *name, int n, double tol) {
   check(info == 500 + bad + 1, what, 0);
 }
 
+// ---- data movement and the logdet reduction ----
+template <typename T>
+static void case_copy_fill_logdet(const char *name) {
+  using H = typename Host<T>::type;
+  const int m = 70, n = 45, lda = 73, ldb = 81;
+  std::mt19937 g(17);
+  std::uniform_real_distribution<double> u(0.5, 1.5);
+  std::vector<H> A((size_t)lda * n);
+  for (auto &x : A) { if constexpr (ScalarOf<T>::cplx) x = H((typename H::value_type)u(g), (typename H::value_type)u(g)); else x = (H)u(g); }
+  const T *dA = reinterpret_cast<const T *>(A.data());
+  for (int trans = 0; trans < 3; ++trans)     // 0 N, 1 T, 2 C
+    for (int uplo = 0; uplo < 5; ++uplo) {    // 0 all, 1 lower, 2 upper, 3 strictly lower, 4 strictly upper (of the SOURCE)
+      std::vector<H> B((size_t)ldb * std::max(m, n), H(9)), W = B;
+      T *dB = reinterpret_cast<T *>(B.data());
+      emu::launch(dim3((m + 31) / 32, (n + 31) / 32), dim3(256), 0, [&] { copy_kernel<T>(trans, uplo, m, n, dA, lda, dB, ldb); });
+      for (int c = 0; c < n; ++c)
+        for (int r = 0; r < m; ++r) {
+          const bool keep = uplo == 0 || (uplo == 1 && r >= c) || (uplo == 2 && r <= c) || (uplo == 3 && r > c) || (uplo == 4 && r < c);
+          if (!keep) continue;
+          const H v = A[r + (size_t)c * lda];
+          if (trans == 0) W[r + (size_t)c * ldb] = v; else W[c + (size_t)r * ldb] = trans == 2 ? cj(v) : v;
+        }
+      char what[120];
+      std::snprintf(what, sizeof what, "%s copy trans=%d uplo=%d", name, trans, uplo);
+      check(B == W, what, 0);
+    }
+  for (int uplo = 0; uplo < 3; ++uplo) {  // 0 all, 1 strictly lower, 2 strictly upper
+    std::vector<H> B((size_t)lda * n, H(3)), W = B;
+    T *dB = reinterpret_cast<T *>(B.data());
+    const H val = ScalarOf<T>::cplx ? H(cj(H(2)) ) : H(2);
+    T tv;
+    std::memcpy(&tv, &val, sizeof tv);
+    emu::launch(dim3((m + 31) / 32, (n + 31) / 32), dim3(256), 0, [&] { fill_kernel<T>(uplo, m, n, tv, dB, lda); });
+    for (int c = 0; c < n; ++c)
+      for (int r = 0; r < m; ++r)
+        if (uplo == 0 || (uplo == 1 && r > c) || (uplo == 2 && r < c)) W[r + (size_t)c * lda] = val;
+    char what[120];
+    std::snprintf(what, sizeof what, "%s fill uplo=%d", name, uplo);
+    check(B == W, what, 0);
+  }
+  // logdet: 2 * sum log(Re x[i*incx]), several blocks, the last one to finish adds the partials
+  using Real = typename ScalarOf<T>::Real;
+  const long long cnt = 1500, incx = 3;
+  std::vector<H> x((size_t)cnt * incx);
+  for (auto &v : x) { if constexpr (ScalarOf<T>::cplx) v = H((typename H::value_type)u(g), (typename H::value_type)u(g)); else v = (H)u(g); }
+  double want = 0;
+  for (long long i = 0; i < cnt; ++i) want += std::log((double)std::real(x[(size_t)(i * incx)]));
+  want *= 2;
+  LogdetScratch scr;
+  std::memset(&scr, 0, sizeof scr);
+  Real res = -1;
+  const int blocks = (int)((cnt + LOGDET_THREADS - 1) / LOGDET_THREADS);
+  for (int rep = 0; rep < 2; ++rep) {  // twice: the ticket must have been reset by the first launch
+    res = -1;
+    emu::launch(dim3(blocks), dim3(LOGDET_THREADS), 0, [&] { logdet_kernel<T>(reinterpret_cast<const T *>(x.data()), incx, cnt, &res, &scr); });
+    char what[120];
+    std::snprintf(what, sizeof what, "%s logdet, %d blocks, launch %d", name, blocks, rep);
+    check(std::fabs((double)res - want) <= (sizeof(Real) == 4 ? 2e-4 : 1e-12) * std::fabs(want), what, std::fabs((double)res - want));
+  }
+}
+
 int main() {
   std::setvbuf(stdout, nullptr, _IOLBF, 0);
   if (!getenv("EMU_ONLY_NOT_PD")) {
@@ -250,6 +311,9 @@ int main() {
   case_unfused<double, 128>("d", 70, 1e-12);
   case_unfused<double2, 64>("z", 50, 1e-12);
   case_unfused<float, 128>("s", 90, 2e-4);
+  case_copy_fill_logdet<double>("d");
+  case_copy_fill_logdet<double2>("z");
+  case_copy_fill_logdet<float>("s");
   if (failures) { std::printf("EMU FAILED: %d mismatches\n", failures); return 1; }
   std::printf("EMU PASSED\n");
   return 0;
