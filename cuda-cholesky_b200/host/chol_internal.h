@@ -109,6 +109,7 @@ typedef struct chol_ws {
   CUdeviceptr T1;   /* nb x nb : temporary of the blocked small inverse */
   CUdeviceptr Tinv; /* db x db : inverse of a potf2 sub-block */
   CUdeviceptr Wd;   /* nb x db : panel of the diagonal-block recursion */
+  CUdeviceptr Tp;   /* ldw x db: temporary of the blocked panel solve (0 unless CHOL_PANEL_BLOCKED) */
 } chol_ws;
 
 size_t chol_default_nb(int prec, size_t n);
@@ -119,6 +120,12 @@ CUresult chol_potrf_diag(int prec, int uplo, size_t jb, CUdeviceptr A, size_t ld
                          const chol_ws *w, CUstream st);
 CUresult chol_diag_factor_inverse(int prec, int uplo, size_t jb, CUdeviceptr A, size_t lda, CUdeviceptr X, size_t ldx,
                                   long *dinfo, long base, const chol_ws *w, CUstream st);
+CUresult chol_diag_factor_inverse_ex(int prec, int uplo, size_t jb, CUdeviceptr A, size_t lda, CUdeviceptr X, size_t ldx,
+                                     long *dinfo, long base, const chol_ws *w, CUstream st, int diag_only);
+bool chol_panel_blocked(void);
+/* POTRF panel step (lower): factor the jb x jb diagonal block at Ajj, solve the rest x jb panel P below it into W */
+CUresult chol_panel_factor_solve_lower(int prec, size_t jb, size_t rest, CUdeviceptr Ajj, CUdeviceptr P, size_t lda, CUdeviceptr W,
+                                       size_t ldw, long *dinfo, long base, const chol_ws *w, CUstream st);
 CUresult chol_trtri_small(int prec, int uplo, int diag, size_t jb, CUdeviceptr A, size_t lda, CUdeviceptr X,
                           size_t ldx, long *dinfo, long base, const chol_ws *w, CUstream st);
 

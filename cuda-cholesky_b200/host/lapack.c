@@ -21,6 +21,7 @@
  * info is accumulated on the device (csrc/panel_kernels.cu) and read once at the end.
  */
 #include <complex.h>
+#include <stdlib.h>
 
 #include "chol_internal.h"
 
@@ -50,14 +51,16 @@ CUresult chol_carve_nb(CULAPACKhandle h, int prec, size_t n, size_t nb, chol_ws 
   w->ldw = chol_roundup(n > w->nb ? n : w->nb, 16);
   const size_t szW = chol_roundup(w->ldw * w->nb * w->es, 256), szX = chol_roundup(w->nb * w->nb * w->es, 256),
                szT = chol_roundup(w->db * w->db * w->es, 256), szWd = chol_roundup(w->nb * w->db * w->es, 256);
+  const size_t szTp = chol_panel_blocked() ? chol_roundup(w->ldw * w->db * w->es, 256) : 0;
   CUdeviceptr base;
-  CU_ERROR_CHECK(chol_lapack_workspace(h, 2 * szW + 2 * szX + szT + szWd, &base));
+  CU_ERROR_CHECK(chol_lapack_workspace(h, 2 * szW + 2 * szX + szT + szWd + szTp, &base));
   w->W[0] = base;
   w->W[1] = base + szW;
   w->Xd = base + 2 * szW;
   w->T1 = w->Xd + szX;
   w->Tinv = w->T1 + szX;
   w->Wd = w->Tinv + szT;
+  w->Tp = szTp ? w->Wd + szWd : 0;
   return CUDA_SUCCESS;
 }
 
@@ -134,9 +137,16 @@ CUresult chol_trtri_small(int prec, int uplo, int diag, size_t jb, CUdeviceptr A
  * is one fused potf2+inverse launch; the blocks are tied together with small GEMMs. */
 CUresult chol_diag_factor_inverse(int prec, int uplo, size_t jb, CUdeviceptr A, size_t lda, CUdeviceptr X, size_t ldx,
                                   long *dinfo, long base, const chol_ws *w, CUstream st) {
+  return chol_diag_factor_inverse_ex(prec, uplo, jb, A, lda, X, ldx, dinfo, base, w, st, 0);
+}
+
+/* diag_only != 0: X receives only the inverses of the db x db diagonal sub-blocks (what the blocked
+ * panel solve needs); the rest of X is left alone */
+CUresult chol_diag_factor_inverse_ex(int prec, int uplo, size_t jb, CUdeviceptr A, size_t lda, CUdeviceptr X, size_t ldx,
+                                     long *dinfo, long base, const chol_ws *w, CUstream st, int diag_only) {
   const size_t es = w->es, db = w->db, nblk = (jb + db - 1) / db;
   const int herm = chol_is_complex(prec);
-  if (nblk > 1) RT_CHECK(chol_fill_launch(prec, 0, jb, jb, 0.0, 0.0, (void *)X, ldx, (void *)st));
+  if (nblk > 1 && !diag_only) RT_CHECK(chol_fill_launch(prec, 0, jb, jb, 0.0, 0.0, (void *)X, ldx, (void *)st));
   for (size_t c = 0; c < nblk; c++) {
     const size_t i = c * db, ib = chol_min(db, jb - i), r = jb - i - ib;
     const CUdeviceptr Aii = chol_at(A, lda, i, i, es), Xii = chol_at(X, ldx, i, i, es);
@@ -156,7 +166,7 @@ CUresult chol_diag_factor_inverse(int prec, int uplo, size_t jb, CUdeviceptr A, 
                                 lda, A22, lda, st));
   }
   /* off-diagonal blocks of the inverse (same recurrences as chol_trtri_small) */
-  for (size_t b = 1; b < nblk; b++) {
+  for (size_t b = 1; b < nblk && !diag_only; b++) {
     const size_t c = (uplo == 'L') ? nblk - 1 - b : b;
     const size_t i = c * db, ib = chol_min(db, jb - i);
     const CUdeviceptr Xcc = chol_at(X, ldx, i, i, es);
@@ -171,6 +181,44 @@ CUresult chol_diag_factor_inverse(int prec, int uplo, size_t jb, CUdeviceptr A, 
                                w->nb, st));
       CU_ERROR_CHECK(chol_gemm(prec, 'N', 'N', i, ib, i, MONE, X, ldx, w->T1, w->nb, ZERO, 0, 0, chol_at(X, ldx, 0, i, es),
                                ldx, st));
+    }
+  }
+  return CUDA_SUCCESS;
+}
+
+/* CHOL_PANEL_BLOCKED=1 (lower; written after the round-1 GPU budget was spent, off until measured):
+ * instead of inverting the whole jb x jb diagonal block (nblk(nblk-1) small, serial GEMMs to tie the
+ * db-blocks of the inverse together) and solving the panel with one GEMM, invert only the db x db
+ * diagonal sub-blocks and solve the panel by block forward substitution with full-height GEMMs:
+ *     W_c = (P_c - W[:, 0:c] * L[c, 0:c]^H) * inv(L_cc)^H        c = 0 .. nblk-1
+ * 10/16 of the flops at nblk = 4, no small GEMMs on the chain. */
+bool chol_panel_blocked(void) {
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("CHOL_PANEL_BLOCKED");
+    on = (e != NULL && atoi(e) != 0) ? 1 : 0;
+  }
+  return on != 0;
+}
+
+/* factor the jb x jb lower diagonal block at Ajj and solve the rest x jb panel P below it into W */
+CUresult chol_panel_factor_solve_lower(int prec, size_t jb, size_t rest, CUdeviceptr Ajj, CUdeviceptr P, size_t lda, CUdeviceptr W,
+                                       size_t ldw, long *dinfo, long base, const chol_ws *w, CUstream st) {
+  const size_t es = w->es, db = w->db, nb = w->nb, nblk = (jb + db - 1) / db;
+  if (!chol_panel_blocked() || nblk < 2 || w->Tp == 0) {
+    CU_ERROR_CHECK(chol_diag_factor_inverse(prec, 'L', jb, Ajj, lda, w->Xd, nb, dinfo, base, w, st));
+    return chol_gemm(prec, 'N', 'C', rest, jb, jb, ONE, P, lda, w->Xd, nb, ZERO, 0, 0, W, ldw, st);
+  }
+  CU_ERROR_CHECK(chol_diag_factor_inverse_ex(prec, 'L', jb, Ajj, lda, w->Xd, nb, dinfo, base, w, st, 1));
+  for (size_t c = 0; c < nblk; c++) {
+    const size_t i = c * db, ib = chol_min(db, jb - i);
+    const CUdeviceptr Pc = chol_at(P, lda, 0, i, es), Wc = chol_at(W, ldw, 0, i, es), Xcc = chol_at(w->Xd, nb, i, i, es);
+    if (c == 0) {
+      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'C', rest, ib, ib, ONE, Pc, lda, Xcc, nb, ZERO, 0, 0, Wc, ldw, st));
+    } else {
+      /* T = P_c - W[:, 0:i] * L[i:i+ib, 0:i]^H  (C = P_c in the matrix, D = T), then W_c = T * inv(L_cc)^H */
+      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'C', rest, ib, i, MONE, W, ldw, chol_at(Ajj, lda, i, 0, es), lda, ONE, Pc, lda, w->Tp, w->ldw, st));
+      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'C', rest, ib, ib, ONE, w->Tp, w->ldw, Xcc, nb, ZERO, 0, 0, Wc, ldw, st));
     }
   }
   return CUDA_SUCCESS;
@@ -197,12 +245,12 @@ static CUresult potrf_body(CULAPACKhandle h, int prec, int uplo, size_t n, CUdev
       CU_ERROR_CHECK(chol_potrf_diag(prec, uplo, jb, Ajj, lda, dinfo, (long)j, &w, sp));
       break;
     }
-    CU_ERROR_CHECK(chol_diag_factor_inverse(prec, uplo, jb, Ajj, lda, w.Xd, nb, dinfo, (long)j, &w, sp));
     if (uplo == 'L') {
       const CUdeviceptr P = chol_at(A, lda, j + jb, j, es); /* rest x jb */
-      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'C', rest, jb, jb, ONE, P, lda, w.Xd, nb, ZERO, 0, 0, W, w.ldw, sp));
+      CU_ERROR_CHECK(chol_panel_factor_solve_lower(prec, jb, rest, Ajj, P, lda, W, w.ldw, dinfo, (long)j, &w, sp));
       RT_CHECK(chol_copy_launch(prec, 'N', 0, rest, jb, (const void *)W, w.ldw, (void *)P, lda, (void *)sp));
     } else {
+      CU_ERROR_CHECK(chol_diag_factor_inverse(prec, uplo, jb, Ajj, lda, w.Xd, nb, dinfo, (long)j, &w, sp));
       const CUdeviceptr P = chol_at(A, lda, j, j + jb, es); /* jb x rest; W = P^H * U11^-1 */
       CU_ERROR_CHECK(chol_gemm(prec, 'C', 'N', rest, jb, jb, ONE, P, lda, w.Xd, nb, ZERO, 0, 0, W, w.ldw, sp));
       RT_CHECK(chol_copy_launch(prec, 'C', 0, rest, jb, (const void *)W, w.ldw, (void *)P, lda, (void *)sp));

@@ -33,7 +33,6 @@
 #include "chol_internal.h"
 
 static const double ONE[2] = {1.0, 0.0};
-static const double ZERO[2] = {0.0, 0.0};
 static const double MONE[2] = {-1.0, 0.0};
 
 /* =============================================================================================
@@ -433,8 +432,7 @@ static CUresult dist_potrf(chol_rank *R, int prec, size_t n, CUdeviceptr Aloc, s
       }
       if (rest) {
         const CUdeviceptr Pn = chol_at(Aloc, ldl, j + jb, lc * nb, es);
-        CU_ERROR_CHECK(chol_diag_factor_inverse(prec, 'L', jb, Ajj, ldl, w.Xd, nb, dinfo, (long)j, &w, sp));
-        CU_ERROR_CHECK(chol_gemm(prec, 'N', 'C', rest, jb, jb, ONE, Pn, ldl, w.Xd, nb, ZERO, 0, 0, W, ldw, sp));
+        CU_ERROR_CHECK(chol_panel_factor_solve_lower(prec, jb, rest, Ajj, Pn, ldl, W, ldw, dinfo, (long)j, &w, sp));
       }
     }
     if (rest == 0) break;

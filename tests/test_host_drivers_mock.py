@@ -51,16 +51,20 @@ def mock_runs(tmp_path_factory):
                OMP_NUM_THREADS="2")  # four groups run side by side: keep the oracle's OpenMP teams small
 
     def run(group):
-        p = subprocess.run([sys.executable, os.path.join(MOCK, "run_host_driver_checks.py"), lib, group], stdout=subprocess.PIPE,
-                           stderr=subprocess.STDOUT, env=env, timeout=1500)
+        # "<group>+blocked": the same checks with the blocked panel solve switched on (read once per process)
+        name, _, variant = group.partition("+")
+        e = dict(env, CHOL_PANEL_BLOCKED="1") if variant == "blocked" else env
+        p = subprocess.run([sys.executable, os.path.join(MOCK, "run_host_driver_checks.py"), lib, name], stdout=subprocess.PIPE,
+                           stderr=subprocess.STDOUT, env=e, timeout=1500)
         return p.returncode, p.stdout.decode()
 
-    groups = ("lapack", "blas", "multi1", "multi3")
+    groups = ("lapack", "blas", "multi1", "multi3", "lapack+blocked", "multi3+blocked")
     with ThreadPoolExecutor(max_workers=len(groups)) as ex:
         return dict(zip(groups, ex.map(run, groups)))
 
 
-@pytest.mark.parametrize("group,min_checks", [("lapack", 700), ("blas", 80), ("multi1", 800), ("multi3", 800)])
+@pytest.mark.parametrize("group,min_checks", [("lapack", 700), ("blas", 80), ("multi1", 800), ("multi3", 800),
+                                              ("lapack+blocked", 700), ("multi3+blocked", 800)])
 def test_host_drivers_on_mock_backend(mock_runs, group, min_checks):
     rc, out = mock_runs[group]
     assert rc == 0 and "MOCK PASSED" in out, out[-3000:]
