@@ -129,3 +129,18 @@ CUresult cuMemcpy2DAsync(const CUDA_MEMCPY2D *c, CUstream s) {
     memcpy(dst + (c->dstY + r) * c->dstPitch + c->dstXInBytes, src + (c->srcY + r) * c->srcPitch + c->srcXInBytes, c->WidthInBytes);
   return CUDA_SUCCESS;
 }
+
+/* ---- used by the C test programs (tests/c), not by the library ---- */
+CUresult cuDeviceGetName(char *name, int len, CUdevice d) { (void)d; strncpy(name, "mock device", (size_t)len); if (len > 0) name[len - 1] = 0; return CUDA_SUCCESS; }
+CUresult cuDeviceTotalMem(size_t *bytes, CUdevice d) { (void)d; *bytes = (size_t)180 << 30; return CUDA_SUCCESS; }
+CUresult cuCtxCreate(CUcontext *c, unsigned int flags, CUdevice d) {
+  (void)flags;
+  if (d < 0 || d >= ndev()) return CUDA_ERROR_INVALID_DEVICE;
+  ctxs[d].device = d;
+  *c = &ctxs[d];
+  return cuCtxPushCurrent(*c);
+}
+CUresult cuCtxDestroy(CUcontext c) { (void)c; if (top > 0) --top; return CUDA_SUCCESS; }
+CUresult cuMemcpyHtoD(CUdeviceptr d, const void *h, size_t n) { memcpy((void *)(uintptr_t)d, h, n); return CUDA_SUCCESS; }
+CUresult cuMemcpyDtoH(void *h, CUdeviceptr d, size_t n) { memcpy(h, (const void *)(uintptr_t)d, n); return CUDA_SUCCESS; }
+CUresult cuMemcpy2D(const CUDA_MEMCPY2D *c) { return cuMemcpy2DAsync(c, NULL); }

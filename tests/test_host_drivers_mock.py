@@ -58,9 +58,22 @@ def mock_runs(tmp_path_factory):
                            stderr=subprocess.STDOUT, env=e, timeout=1500)
         return p.returncode, p.stdout.decode()
 
+    def run_c(src, devices, args=()):
+        """the plain-C callers of tests/c, linked against the mock library instead of libcholesky_b200 + libcuda"""
+        exe = os.path.join(d, os.path.basename(src)[:-2] + "_%d" % devices)
+        subprocess.check_call(["gcc", "-std=c99", "-O1", *INC, src, "-o", exe, "-L" + d, "-lcholesky_b200_mock", "-lm", "-Wl,-rpath," + d])
+        p = subprocess.run([exe, *args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=dict(env, MOCK_CUDA_DEVICES=str(devices)),
+                           timeout=600)
+        return p.returncode, p.stdout.decode()
+
     groups = ("lapack", "blas", "multi1", "multi3", "lapack+blocked", "multi3+blocked")
     with ThreadPoolExecutor(max_workers=len(groups)) as ex:
-        return dict(zip(groups, ex.map(run, groups)))
+        res = dict(zip(groups, ex.map(run, groups)))
+    cdir = os.path.join(ROOT, "tests", "c")
+    res["c:cumultigpu_unit:1"] = run_c(os.path.join(cdir, "cumultigpu_unit.c"), 1)
+    res["c:cumultigpu_unit:3"] = run_c(os.path.join(cdir, "cumultigpu_unit.c"), 3)
+    res["c:dropin_dpotrf"] = run_c(os.path.join(cdir, "dropin_dpotrf.c"), 1, ("300",))
+    return res
 
 
 @pytest.mark.parametrize("group,min_checks", [("lapack", 700), ("blas", 80), ("multi1", 800), ("multi3", 800),
@@ -70,3 +83,11 @@ def test_host_drivers_on_mock_backend(mock_runs, group, min_checks):
     assert rc == 0 and "MOCK PASSED" in out, out[-3000:]
     n = int([l for l in out.splitlines() if l.endswith(" checks")][-1].split()[0])
     assert n >= min_checks
+
+
+@pytest.mark.parametrize("prog", ["c:cumultigpu_unit:1", "c:cumultigpu_unit:3", "c:dropin_dpotrf"])
+def test_c_callers_on_mock_backend(mock_runs, prog):
+    """tests/c/cumultigpu_unit.c (the reference's cumultigpu.c / cutask.c unit tests plus error latching and
+    submission order, then cuMultiGPUDpotrf on every device) and tests/c/dropin_dpotrf.c, without a GPU"""
+    rc, out = mock_runs[prog]
+    assert rc == 0 and "PASSED" in out, out[-3000:]
