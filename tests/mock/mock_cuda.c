@@ -3,8 +3,17 @@
  * code (cuda-cholesky_b200/host) calls, so that the C drivers - blocked POTRF / TRTRI / LAUUM /
  * POTRI / POTRS, TRSM / TRMM, the CUmultiGPU runtime, the distributed factorisation with its
  * look-ahead, the slab-distributed inverse - can be exercised on a machine without a GPU
- * (tests/test_host_drivers_mock.py).  "Device" memory is host memory, every stream operation runs
- * at once, events do nothing: this checks algebra, indexing and control flow, NOT stream ordering.
+ * (tests/test_host_drivers_mock.py).  "Device" memory is host memory.
+ *
+ * Streams are REAL asynchronous queues: every CUstream owns a worker thread that runs the
+ * operations queued on it in order (copies, memsets, the mock kernels of mock_kernels.cpp, the
+ * mock NCCL broadcast), cuEventRecord / cuStreamWaitEvent carry the CUDA semantics (a wait refers
+ * to the most recent record at the time of the call; waiting on a never-recorded event is a
+ * no-op), the NULL stream synchronises with everything.  So a missing dependency between the
+ * panel, update, upload and download streams is a real race here too; MOCK_CUDA_JITTER=1 makes
+ * every stream stall for a random few hundred microseconds before each operation to shake such
+ * races out, MOCK_CUDA_SLOW_H2D_US=n makes every host-to-device copy take n microseconds.
+ * MOCK_CUDA_SYNC=1 falls back to running every operation at once.
  * MOCK_CUDA_DEVICES (default 1) sets the number of devices.  Linked only into the mock test library.
  */
 #define _GNU_SOURCE
@@ -12,13 +21,12 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <cuda.h>
 
 #define MAXDEV 16
 struct CUctx_st { int device; };
-struct CUstream_st { int dummy; };
-struct CUevent_st { int dummy; };
 static struct CUctx_st ctxs[MAXDEV];
 static __thread CUcontext stack[16];
 static __thread int top = 0; /* stack[top-1] is current */
@@ -40,20 +48,166 @@ CUresult cuCtxSetCurrent(CUcontext c) { if (top == 0) top = 1; stack[top - 1] = 
 CUresult cuCtxPushCurrent(CUcontext c) { if (top >= 16) return CUDA_ERROR_INVALID_VALUE; stack[top++] = c; return CUDA_SUCCESS; }
 CUresult cuCtxPopCurrent(CUcontext *c) { if (top == 0) return CUDA_ERROR_INVALID_CONTEXT; *c = stack[--top]; return CUDA_SUCCESS; }
 CUresult cuCtxGetDevice(CUdevice *d) { if (top == 0 || stack[top - 1] == NULL) return CUDA_ERROR_INVALID_CONTEXT; *d = stack[top - 1]->device; return CUDA_SUCCESS; }
-CUresult cuCtxSynchronize(void) { return CUDA_SUCCESS; }
 CUresult cuCtxGetStreamPriorityRange(int *lo, int *hi) { *lo = 0; *hi = -5; return CUDA_SUCCESS; }
 
 /* the test harness asks how deep the calling thread's context stack is (push / pop balance) */
 int mock_cuda_ctx_depth(void) { return top; }
 
-CUresult cuStreamCreate(CUstream *s, unsigned int f) { (void)f; *s = calloc(1, sizeof **s); return *s ? CUDA_SUCCESS : CUDA_ERROR_OUT_OF_MEMORY; }
+/* ---- streams: a worker thread and a FIFO of operations each ---- */
+struct op { void (*fn)(void *); void *arg; struct op *next; };
+struct CUstream_st {
+  pthread_t thread;
+  pthread_mutex_t mu;
+  pthread_cond_t cv;      /* work available / queue drained */
+  struct op *head, *tail;
+  int busy, stop;
+  unsigned rng;
+  struct CUstream_st *next_stream; /* registry, for device-wide synchronisation */
+};
+struct CUevent_st { pthread_mutex_t mu; pthread_cond_t cv; unsigned long long recorded, completed; };
+static pthread_mutex_t streams_lock = PTHREAD_MUTEX_INITIALIZER;
+static struct CUstream_st *all_streams = NULL;
+
+static int sync_mode(void) { const char *e = getenv("MOCK_CUDA_SYNC"); return e && atoi(e); }
+static int jitter(void) { const char *e = getenv("MOCK_CUDA_JITTER"); return e && atoi(e); }
+
+static void *stream_main(void *p) {
+  struct CUstream_st *s = p;
+  for (;;) {
+    pthread_mutex_lock(&s->mu);
+    while (s->head == NULL && !s->stop) pthread_cond_wait(&s->cv, &s->mu);
+    struct op *o = s->head;
+    if (o == NULL) { pthread_mutex_unlock(&s->mu); break; }
+    s->head = o->next;
+    if (s->head == NULL) s->tail = NULL;
+    s->busy = 1;
+    pthread_mutex_unlock(&s->mu);
+    if (jitter()) {
+      s->rng = s->rng * 1664525u + 1013904223u;
+      if ((s->rng >> 16) % 3 == 0) { struct timespec ts = {0, (long)((s->rng >> 8) % 400) * 1000}; nanosleep(&ts, NULL); }
+    }
+    o->fn(o->arg);
+    free(o);
+    pthread_mutex_lock(&s->mu);
+    s->busy = 0;
+    pthread_cond_broadcast(&s->cv);
+    pthread_mutex_unlock(&s->mu);
+  }
+  return NULL;
+}
+
+static void drain(struct CUstream_st *s) {
+  pthread_mutex_lock(&s->mu);
+  while (s->head != NULL || s->busy) pthread_cond_wait(&s->cv, &s->mu);
+  pthread_mutex_unlock(&s->mu);
+}
+static void drain_all(void) {
+  pthread_mutex_lock(&streams_lock);
+  /* the registry only grows or shrinks under this lock; draining while holding it is fine because
+   * stream workers never take it */
+  for (struct CUstream_st *s = all_streams; s; s = s->next_stream) drain(s);
+  pthread_mutex_unlock(&streams_lock);
+}
+
+/* queue fn(arg) on the stream (NULL stream, or MOCK_CUDA_SYNC: run now, after everything queued anywhere).
+ * Exported for mock_kernels.cpp and mock_nccl.c. */
+void mock_stream_enqueue(CUstream s, void (*fn)(void *), void *arg) {
+  if (s == NULL || sync_mode()) {
+    if (s == NULL) drain_all(); else drain(s);
+    fn(arg);
+    return;
+  }
+  struct op *o = malloc(sizeof *o);
+  o->fn = fn; o->arg = arg; o->next = NULL;
+  pthread_mutex_lock(&s->mu);
+  if (s->tail) s->tail->next = o; else s->head = o;
+  s->tail = o;
+  pthread_cond_broadcast(&s->cv);
+  pthread_mutex_unlock(&s->mu);
+}
+
+CUresult cuStreamCreate(CUstream *out, unsigned int f) {
+  (void)f;
+  struct CUstream_st *s = calloc(1, sizeof *s);
+  if (s == NULL) return CUDA_ERROR_OUT_OF_MEMORY;
+  pthread_mutex_init(&s->mu, NULL);
+  pthread_cond_init(&s->cv, NULL);
+  s->rng = (unsigned)(uintptr_t)s;
+  if (pthread_create(&s->thread, NULL, stream_main, s) != 0) { free(s); return CUDA_ERROR_OPERATING_SYSTEM; }
+  pthread_mutex_lock(&streams_lock);
+  s->next_stream = all_streams;
+  all_streams = s;
+  pthread_mutex_unlock(&streams_lock);
+  *out = s;
+  return CUDA_SUCCESS;
+}
 CUresult cuStreamCreateWithPriority(CUstream *s, unsigned int f, int p) { (void)p; return cuStreamCreate(s, f); }
-CUresult cuStreamDestroy(CUstream s) { free(s); return CUDA_SUCCESS; }
-CUresult cuStreamSynchronize(CUstream s) { (void)s; return CUDA_SUCCESS; }
-CUresult cuStreamWaitEvent(CUstream s, CUevent e, unsigned int f) { (void)s; (void)e; (void)f; return CUDA_SUCCESS; }
-CUresult cuEventCreate(CUevent *e, unsigned int f) { (void)f; *e = calloc(1, sizeof **e); return *e ? CUDA_SUCCESS : CUDA_ERROR_OUT_OF_MEMORY; }
-CUresult cuEventDestroy(CUevent e) { free(e); return CUDA_SUCCESS; }
-CUresult cuEventRecord(CUevent e, CUstream s) { (void)e; (void)s; return CUDA_SUCCESS; }
+CUresult cuStreamDestroy(CUstream s) {
+  drain(s);
+  pthread_mutex_lock(&streams_lock);
+  for (struct CUstream_st **pp = &all_streams; *pp; pp = &(*pp)->next_stream)
+    if (*pp == s) { *pp = s->next_stream; break; }
+  pthread_mutex_unlock(&streams_lock);
+  pthread_mutex_lock(&s->mu);
+  s->stop = 1;
+  pthread_cond_broadcast(&s->cv);
+  pthread_mutex_unlock(&s->mu);
+  pthread_join(s->thread, NULL);
+  pthread_mutex_destroy(&s->mu);
+  pthread_cond_destroy(&s->cv);
+  free(s);
+  return CUDA_SUCCESS;
+}
+CUresult cuStreamSynchronize(CUstream s) { if (s == NULL) drain_all(); else drain(s); return CUDA_SUCCESS; }
+CUresult cuCtxSynchronize(void) { drain_all(); return CUDA_SUCCESS; }
+
+CUresult cuEventCreate(CUevent *out, unsigned int f) {
+  (void)f;
+  struct CUevent_st *e = calloc(1, sizeof *e);
+  if (e == NULL) return CUDA_ERROR_OUT_OF_MEMORY;
+  pthread_mutex_init(&e->mu, NULL);
+  pthread_cond_init(&e->cv, NULL);
+  *out = e;
+  return CUDA_SUCCESS;
+}
+CUresult cuEventDestroy(CUevent e) { pthread_mutex_destroy(&e->mu); pthread_cond_destroy(&e->cv); free(e); return CUDA_SUCCESS; }
+struct evop { struct CUevent_st *e; unsigned long long seq; };
+static void op_record(void *p) {
+  struct evop *o = p;
+  pthread_mutex_lock(&o->e->mu);
+  if (o->seq > o->e->completed) o->e->completed = o->seq;
+  pthread_cond_broadcast(&o->e->cv);
+  pthread_mutex_unlock(&o->e->mu);
+  free(o);
+}
+static void op_wait(void *p) {
+  struct evop *o = p;
+  pthread_mutex_lock(&o->e->mu);
+  while (o->e->completed < o->seq) pthread_cond_wait(&o->e->cv, &o->e->mu);
+  pthread_mutex_unlock(&o->e->mu);
+  free(o);
+}
+CUresult cuEventRecord(CUevent e, CUstream s) {
+  struct evop *o = malloc(sizeof *o);
+  pthread_mutex_lock(&e->mu);
+  o->e = e;
+  o->seq = ++e->recorded;
+  pthread_mutex_unlock(&e->mu);
+  mock_stream_enqueue(s, op_record, o);
+  return CUDA_SUCCESS;
+}
+CUresult cuStreamWaitEvent(CUstream s, CUevent e, unsigned int f) {
+  (void)f;
+  pthread_mutex_lock(&e->mu);
+  const unsigned long long target = e->recorded; /* the most recent record at the time of this call */
+  pthread_mutex_unlock(&e->mu);
+  if (target == 0) return CUDA_SUCCESS; /* never recorded: no-op, as in CUDA */
+  struct evop *o = malloc(sizeof *o);
+  o->e = e;
+  o->seq = target;
+  mock_stream_enqueue(s, op_wait, o);
+  return CUDA_SUCCESS;
+}
 CUresult cuEventElapsedTime(float *ms, CUevent a, CUevent b) { (void)a; (void)b; *ms = 1.0f; return CUDA_SUCCESS; }
 
 /* ---- memory: "device" = host.  MOCK_CUDA_MEM_LIMIT (bytes) makes larger device allocations fail. ---- */
@@ -72,7 +226,7 @@ CUresult cuMemAlloc(CUdeviceptr *d, size_t bytes) {
   __sync_fetch_and_add(&live_device_allocs, 1);
   return CUDA_SUCCESS;
 }
-CUresult cuMemFree(CUdeviceptr d) { free((void *)(uintptr_t)d); __sync_fetch_and_sub(&live_device_allocs, 1); return CUDA_SUCCESS; }
+CUresult cuMemFree(CUdeviceptr d) { drain_all(); /* cuMemFree synchronises the device */ free((void *)(uintptr_t)d); __sync_fetch_and_sub(&live_device_allocs, 1); return CUDA_SUCCESS; }
 CUresult cuMemAllocHost(void **p, size_t bytes) {
   if (posix_memalign(p, 256, bytes ? bytes : 1) != 0) return CUDA_ERROR_OUT_OF_MEMORY;
   pthread_mutex_lock(&reg_lock);
@@ -115,18 +269,49 @@ CUresult cuPointerGetAttribute(void *data, CUpointer_attribute attr, CUdeviceptr
   pthread_mutex_unlock(&reg_lock);
   return r;
 }
-CUresult cuMemsetD8(CUdeviceptr d, unsigned char v, size_t n) { memset((void *)(uintptr_t)d, v, n); return CUDA_SUCCESS; }
-CUresult cuMemsetD8Async(CUdeviceptr d, unsigned char v, size_t n, CUstream s) { (void)s; return cuMemsetD8(d, v, n); }
-CUresult cuMemcpyDtoHAsync(void *h, CUdeviceptr d, size_t n, CUstream s) { (void)s; memcpy(h, (const void *)(uintptr_t)d, n); return CUDA_SUCCESS; }
-CUresult cuMemcpy2DAsync(const CUDA_MEMCPY2D *c, CUstream s) {
-  (void)s;
+struct memop { int kind; void *dst; const void *src; size_t n; unsigned char v; CUDA_MEMCPY2D c2; };
+static void copy2d_now(const CUDA_MEMCPY2D *c) {
   const char *src = c->srcMemoryType == CU_MEMORYTYPE_HOST ? (const char *)c->srcHost : (const char *)(uintptr_t)c->srcDevice;
   char *dst = c->dstMemoryType == CU_MEMORYTYPE_HOST ? (char *)c->dstHost : (char *)(uintptr_t)c->dstDevice;
-  if (c->WidthInBytes > c->srcPitch || c->WidthInBytes > c->dstPitch) {
-    if (c->Height > 1) return CUDA_ERROR_INVALID_VALUE; /* the driver rejects a width larger than the pitch */
-  }
   for (size_t r = 0; r < c->Height; r++)
     memcpy(dst + (c->dstY + r) * c->dstPitch + c->dstXInBytes, src + (c->srcY + r) * c->srcPitch + c->srcXInBytes, c->WidthInBytes);
+}
+static void op_mem(void *p) {
+  struct memop *o = p;
+  if (o->kind == 0) memset(o->dst, o->v, o->n);
+  else if (o->kind == 1) memcpy(o->dst, o->src, o->n);
+  else {
+    /* MOCK_CUDA_SLOW_H2D_US: a host -> device copy takes that long, as if it crossed PCIe - anything that
+     * touches the destination without waiting for the copy then works on stale data */
+    const char *e = getenv("MOCK_CUDA_SLOW_H2D_US");
+    if (e && o->c2.srcMemoryType == CU_MEMORYTYPE_HOST && o->c2.dstMemoryType == CU_MEMORYTYPE_DEVICE) {
+      const long us = atol(e);
+      struct timespec ts = {us / 1000000, (us % 1000000) * 1000};
+      nanosleep(&ts, NULL);
+    }
+    copy2d_now(&o->c2);
+  }
+  free(o);
+}
+CUresult cuMemsetD8(CUdeviceptr d, unsigned char v, size_t n) { drain_all(); memset((void *)(uintptr_t)d, v, n); return CUDA_SUCCESS; }
+CUresult cuMemsetD8Async(CUdeviceptr d, unsigned char v, size_t n, CUstream s) {
+  struct memop *o = calloc(1, sizeof *o);
+  o->kind = 0; o->dst = (void *)(uintptr_t)d; o->v = v; o->n = n;
+  mock_stream_enqueue(s, op_mem, o);
+  return CUDA_SUCCESS;
+}
+CUresult cuMemcpyDtoHAsync(void *h, CUdeviceptr d, size_t n, CUstream s) {
+  struct memop *o = calloc(1, sizeof *o);
+  o->kind = 1; o->dst = h; o->src = (const void *)(uintptr_t)d; o->n = n;
+  mock_stream_enqueue(s, op_mem, o);
+  return CUDA_SUCCESS;
+}
+CUresult cuMemcpy2DAsync(const CUDA_MEMCPY2D *c, CUstream s) {
+  if ((c->WidthInBytes > c->srcPitch || c->WidthInBytes > c->dstPitch) && c->Height > 1)
+    return CUDA_ERROR_INVALID_VALUE; /* the driver rejects a width larger than the pitch */
+  struct memop *o = calloc(1, sizeof *o);
+  o->kind = 2; o->c2 = *c;
+  mock_stream_enqueue(s, op_mem, o);
   return CUDA_SUCCESS;
 }
 
@@ -141,6 +326,6 @@ CUresult cuCtxCreate(CUcontext *c, unsigned int flags, CUdevice d) {
   return cuCtxPushCurrent(*c);
 }
 CUresult cuCtxDestroy(CUcontext c) { (void)c; if (top > 0) --top; return CUDA_SUCCESS; }
-CUresult cuMemcpyHtoD(CUdeviceptr d, const void *h, size_t n) { memcpy((void *)(uintptr_t)d, h, n); return CUDA_SUCCESS; }
-CUresult cuMemcpyDtoH(void *h, CUdeviceptr d, size_t n) { memcpy(h, (const void *)(uintptr_t)d, n); return CUDA_SUCCESS; }
-CUresult cuMemcpy2D(const CUDA_MEMCPY2D *c) { return cuMemcpy2DAsync(c, NULL); }
+CUresult cuMemcpyHtoD(CUdeviceptr d, const void *h, size_t n) { drain_all(); memcpy((void *)(uintptr_t)d, h, n); return CUDA_SUCCESS; }
+CUresult cuMemcpyDtoH(void *h, CUdeviceptr d, size_t n) { drain_all(); memcpy(h, (const void *)(uintptr_t)d, n); return CUDA_SUCCESS; }
+CUresult cuMemcpy2D(const CUDA_MEMCPY2D *c) { drain_all(); copy2d_now(c); return CUDA_SUCCESS; }

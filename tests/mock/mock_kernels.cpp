@@ -1,17 +1,30 @@
 // mock_kernels.cpp — TEST INFRASTRUCTURE ONLY.  The launcher ABI of csrc/chol_kernels.h implemented
 // as plain CPU loops that follow the documented semantics of each launcher (not the kernels' code):
 // with tests/mock/mock_cuda.c this lets the host drivers run without a GPU
-// (tests/test_host_drivers_mock.py).  Every "launch" completes before it returns.
+// (tests/test_host_drivers_mock.py).  A "launch" is queued on its stream (mock_cuda.c runs every
+// stream on its own thread, in order), so launches are asynchronous as on the device.
 #include <cmath>
 #include <complex>
 #include <cstring>
+#include <functional>
 #include <vector>
 
 #include "../../cuda-cholesky_b200/csrc/chol_kernels.h"
 
+extern "C" void mock_stream_enqueue(void *stream, void (*fn)(void *), void *arg);  // mock_cuda.c
+
 namespace {
 
 unsigned long long launches = 0;
+void run_fn(void *p) {
+  auto *f = static_cast<std::function<void()> *>(p);
+  (*f)();
+  delete f;
+}
+template <typename F> int enqueue(void *stream, F f) {
+  mock_stream_enqueue(stream, run_fn, new std::function<void()>(std::move(f)));
+  return 0;
+}
 template <typename T> struct RealOf { using type = T; };
 template <typename R> struct RealOf<std::complex<R>> { using type = R; };
 template <typename T> T cj(T x) { return x; }
@@ -202,12 +215,12 @@ int fill_t(int uplo, size_t m, size_t n, T v, T *A, size_t lda) {
 
 #define DISPATCH(prec, CALL)                                           \
   switch (prec) {                                                      \
-    case 's': { using T = float; return CALL; }                        \
-    case 'd': { using T = double; return CALL; }                       \
-    case 'c': { using T = std::complex<float>; return CALL; }          \
-    case 'z': { using T = std::complex<double>; return CALL; }         \
-    default: return 1;                                                 \
+    case 's': { using T = float; CALL; break; }                        \
+    case 'd': { using T = double; CALL; break; }                       \
+    case 'c': { using T = std::complex<float>; CALL; break; }          \
+    case 'z': { using T = std::complex<double>; CALL; break; }         \
   }
+static bool known(int prec) { return prec == 's' || prec == 'd' || prec == 'c' || prec == 'z'; }
 
 extern "C" {
 unsigned long long chol_launch_count(int reset) { const unsigned long long v = launches; if (reset) launches = 0; return v; }
@@ -216,65 +229,72 @@ int chol_gemm_uses_tma(const chol_gemm_desc *) { return 0; }
 int chol_probe_fp64(int, int, double *tflops, float *ms) { *tflops = 1.0; if (ms) *ms = 1.0f; return 0; }
 size_t chol_logdet_scratch_bytes(void) { return 4096; }
 
-int chol_gemm_launch(const chol_gemm_desc *d) {
-  ++launches;
-  if (d->m == 0 || d->n == 0) return 0;
-  DISPATCH(d->prec, gemm_t<T>(d));
+int chol_gemm_launch(const chol_gemm_desc *dp) {
+  __sync_fetch_and_add(&launches, 1);
+  if (dp->m == 0 || dp->n == 0) return 0;
+  if (!known(dp->prec)) return 1;
+  if (dp->cyc_nb && (dp->opB == 'N' || dp->cuplo == 'U' || dp->triA || dp->triB)) return 1;
+  const chol_gemm_desc d = *dp;
+  return enqueue(d.stream, [d] { DISPATCH(d.prec, gemm_t<T>(&d)) });
 }
-int chol_potf2_launch(int prec, int uplo, size_t n, void *A, size_t lda, long *dinfo, long base, void *) {
-  ++launches;
+int chol_potf2_launch(int prec, int uplo, size_t n, void *A, size_t lda, long *dinfo, long base, void *st) {
+  __sync_fetch_and_add(&launches, 1);
   if (n == 0) return 0;
-  if (n > (size_t)chol_diag_max(prec)) return 1;
-  DISPATCH(prec, potf2_t<T>(uplo == 'U', n, (T *)A, lda, dinfo, base, (T *)nullptr, 0));
+  if (!known(prec) || n > (size_t)chol_diag_max(prec)) return 1;
+  return enqueue(st, [=] { DISPATCH(prec, potf2_t<T>(uplo == 'U', n, (T *)A, lda, dinfo, base, (T *)nullptr, 0)) });
 }
-int chol_potf2_inv_launch(int prec, int uplo, size_t n, void *A, size_t lda, void *X, size_t ldx, long *dinfo, long base, void *) {
-  ++launches;
+int chol_potf2_inv_launch(int prec, int uplo, size_t n, void *A, size_t lda, void *X, size_t ldx, long *dinfo, long base, void *st) {
+  __sync_fetch_and_add(&launches, 1);
   if (n == 0) return 0;
-  if (n > (size_t)chol_diag_max(prec)) return 1;
-  DISPATCH(prec, potf2_t<T>(uplo == 'U', n, (T *)A, lda, dinfo, base, (T *)X, ldx));
+  if (!known(prec) || n > (size_t)chol_diag_max(prec)) return 1;
+  return enqueue(st, [=] { DISPATCH(prec, potf2_t<T>(uplo == 'U', n, (T *)A, lda, dinfo, base, (T *)X, ldx)) });
 }
 int chol_trti2_launch(int prec, int uplo, int diag, size_t n, const void *A, size_t lda, void *B, size_t ldb, int zero_other, long *dinfo,
-                      long base, void *) {
-  ++launches;
+                      long base, void *st) {
+  __sync_fetch_and_add(&launches, 1);
   if (n == 0) return 0;
-  if (n > (size_t)chol_diag_max(prec)) return 1;
-  DISPATCH(prec, trti2_t<T>(uplo == 'U', diag == 'U', n, (const T *)A, lda, (T *)B, ldb, zero_other, dinfo, base));
+  if (!known(prec) || n > (size_t)chol_diag_max(prec)) return 1;
+  return enqueue(st, [=] { DISPATCH(prec, trti2_t<T>(uplo == 'U', diag == 'U', n, (const T *)A, lda, (T *)B, ldb, zero_other, dinfo, base)) });
 }
-int chol_lauu2_launch(int prec, int uplo, size_t n, void *A, size_t lda, void *) {
-  ++launches;
+int chol_lauu2_launch(int prec, int uplo, size_t n, void *A, size_t lda, void *st) {
+  __sync_fetch_and_add(&launches, 1);
   if (n == 0) return 0;
-  if (n > (size_t)chol_diag_max(prec)) return 1;
-  DISPATCH(prec, lauu2_t<T>(uplo == 'U', n, (T *)A, lda));
+  if (!known(prec) || n > (size_t)chol_diag_max(prec)) return 1;
+  return enqueue(st, [=] { DISPATCH(prec, lauu2_t<T>(uplo == 'U', n, (T *)A, lda)) });
 }
-int chol_copy_launch(int prec, int trans, int uplo, size_t m, size_t n, const void *A, size_t lda, void *B, size_t ldb, void *) {
-  ++launches;
+int chol_copy_launch(int prec, int trans, int uplo, size_t m, size_t n, const void *A, size_t lda, void *B, size_t ldb, void *st) {
+  __sync_fetch_and_add(&launches, 1);
   if (m == 0 || n == 0) return 0;
-  DISPATCH(prec, copy_t<T>(trans, uplo, m, n, (const T *)A, lda, (T *)B, ldb));
+  if (!known(prec)) return 1;
+  return enqueue(st, [=] { DISPATCH(prec, copy_t<T>(trans, uplo, m, n, (const T *)A, lda, (T *)B, ldb)) });
 }
-int chol_fill_launch(int prec, int uplo, size_t m, size_t n, double re_, double im_, void *A, size_t lda, void *) {
-  ++launches;
+int chol_fill_launch(int prec, int uplo, size_t m, size_t n, double re_, double im_, void *A, size_t lda, void *st) {
+  __sync_fetch_and_add(&launches, 1);
   if (m == 0 || n == 0) return 0;
-  switch (prec) {
-    case 's': return fill_t<float>(uplo, m, n, (float)re_, (float *)A, lda);
-    case 'd': return fill_t<double>(uplo, m, n, re_, (double *)A, lda);
-    case 'c': return fill_t<std::complex<float>>(uplo, m, n, std::complex<float>((float)re_, (float)im_), (std::complex<float> *)A, lda);
-    case 'z': return fill_t<std::complex<double>>(uplo, m, n, std::complex<double>(re_, im_), (std::complex<double> *)A, lda);
-    default: return 1;
-  }
-}
-int chol_logdet_launch(int prec, const void *x, size_t incx, size_t n, void *dresult, void *, void *) {
-  ++launches;
-  double s = 0.0;
-  for (size_t i = 0; i < n; ++i) {
+  if (!known(prec)) return 1;
+  return enqueue(st, [=] {
     switch (prec) {
-      case 's': s += (double)std::log(((const float *)x)[i * incx]); break;
-      case 'd': s += std::log(((const double *)x)[i * incx]); break;
-      case 'c': s += (double)std::log(((const std::complex<float> *)x)[i * incx].real()); break;
-      case 'z': s += std::log(((const std::complex<double> *)x)[i * incx].real()); break;
-      default: return 1;
+      case 's': fill_t<float>(uplo, m, n, (float)re_, (float *)A, lda); break;
+      case 'd': fill_t<double>(uplo, m, n, re_, (double *)A, lda); break;
+      case 'c': fill_t<std::complex<float>>(uplo, m, n, std::complex<float>((float)re_, (float)im_), (std::complex<float> *)A, lda); break;
+      case 'z': fill_t<std::complex<double>>(uplo, m, n, std::complex<double>(re_, im_), (std::complex<double> *)A, lda); break;
     }
-  }
-  if (prec == 's' || prec == 'c') *(float *)dresult = (float)(2.0 * s); else *(double *)dresult = 2.0 * s;
-  return 0;
+  });
+}
+int chol_logdet_launch(int prec, const void *x, size_t incx, size_t n, void *dresult, void *, void *st) {
+  __sync_fetch_and_add(&launches, 1);
+  if (!known(prec)) return 1;
+  return enqueue(st, [=] {
+    double s = 0.0;
+    for (size_t i = 0; i < n; ++i) {
+      switch (prec) {
+        case 's': s += (double)std::log(((const float *)x)[i * incx]); break;
+        case 'd': s += std::log(((const double *)x)[i * incx]); break;
+        case 'c': s += (double)std::log(((const std::complex<float> *)x)[i * incx].real()); break;
+        case 'z': s += std::log(((const std::complex<double> *)x)[i * incx].real()); break;
+      }
+    }
+    if (prec == 's' || prec == 'c') *(float *)dresult = (float)(2.0 * s); else *(double *)dresult = 2.0 * s;
+  });
 }
 }

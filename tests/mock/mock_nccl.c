@@ -2,8 +2,9 @@
  * mock_nccl.c — TEST INFRASTRUCTURE ONLY: a libnccl.so.2 stand-in for the single-process,
  * one-thread-per-GPU form (ncclCommInitAll) used by the cuMultiGPU* drivers, so that the
  * distributed factorisation's control flow (ownership, panel broadcast order, look-ahead, info
- * combination) can run on a machine without GPUs (tests/test_host_drivers_mock.py).  A broadcast is a
- * rendezvous of the group's threads: the root publishes its buffer, the others copy from it.
+ * combination) can run on a machine without GPUs (tests/test_host_drivers_mock.py).  A broadcast is queued on
+ * the caller's (mock) stream like a kernel; when it runs it is a rendezvous of the group's ranks: the
+ * root publishes its buffer, the others copy from it.
  */
 #define _GNU_SOURCE
 #include <pthread.h>
@@ -47,13 +48,23 @@ int ncclCommDestroy(ncclComm_t c) {
   return 0;
 }
 
+void mock_stream_enqueue(void *stream, void (*fn)(void *), void *arg); /* mock_cuda.c, in the mock library */
+
+struct bcast { const void *send; void *recv; size_t count; int root; struct comm *c; };
+static void do_bcast(void *p) {
+  struct bcast *b = p;
+  struct group *g = b->c->g;
+  if (b->c->rank == b->root) g->src = b->send;
+  pthread_barrier_wait(&g->bar);
+  if (b->c->rank != b->root && b->recv != g->src) memcpy(b->recv, g->src, b->count);
+  pthread_barrier_wait(&g->bar);
+  free(b);
+}
+
 int ncclBroadcast(const void *send, void *recv, size_t count, int dtype, int root, ncclComm_t c, void *stream) {
-  (void)stream;
   if (dtype != 1 /* ncclUint8: the library broadcasts bytes */) return 4;
-  struct group *g = c->g;
-  if (c->rank == root) g->src = send;
-  pthread_barrier_wait(&g->bar);
-  if (c->rank != root && recv != g->src) memcpy(recv, g->src, count);
-  pthread_barrier_wait(&g->bar);
+  struct bcast *b = malloc(sizeof *b);
+  b->send = send; b->recv = recv; b->count = count; b->root = root; b->c = c;
+  mock_stream_enqueue(stream, do_bcast, b);
   return 0;
 }

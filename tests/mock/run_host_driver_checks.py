@@ -3,12 +3,16 @@ CPU stand-in for the CUDA driver, plain-loop implementations of the kernel launc
 thread-rendezvous libnccl) and compare with the CPU oracle.  TEST INFRASTRUCTURE ONLY - executed in
 its own process by tests/test_host_drivers_mock.py with
     argv[1] = the mock library,  LD_LIBRARY_PATH = the directory holding the mock libnccl.so.2.
+The mock streams are real asynchronous queues (one thread each) with CUDA's event semantics, uploads can
+be made slow and every stream can be made to stall at random, so a missing dependency between the
+panel / update / upload / download streams shows up as a wrong result (checked by mutation: dropping the
+update's wait for the panel, or a group update's wait for its upload, fails these checks).
 What this covers: blocking, look-ahead bookkeeping, workspace carving, recursion of the diagonal
 block, TRSM/TRMM/TRTRI/LAUUM/POTRI/POTRS drivers, argument errors, context push/pop balance,
 allocation balance, the CUmultiGPU runtime with several (mock) devices, the distributed POTRF incl.
 the page-locked overlapped paths, the slab-distributed inverse, the host-pointer BLAS.  What it
-cannot cover: stream ordering (everything is synchronous here) and the kernels themselves
-(tests/test_kernel_emulation.py, and the GPU parity tests)."""
+cannot cover: the kernels themselves (tests/test_kernel_emulation.py, and the GPU parity tests) and
+timing."""
 import ctypes as C
 import os
 import sys
@@ -197,11 +201,13 @@ def multi_device(P):
     potrf_cases("pageable", False)
     potrf_cases("page-locked (download overlapped)", True)
     os.environ["CHOL_MGPU_H2D_OVERLAP"] = "1"
+    os.environ["MOCK_CUDA_SLOW_H2D_US"] = "30000"  # uploads lag behind the factorisation: every missing wait shows
     for gbps in ("50", "0.000001"):  # the tiny rate sends EVERY step through the group-by-group update
         os.environ["CHOL_H2D_GBPS"] = gbps
         potrf_cases("page-locked, upload overlapped (assumed %s GB/s)" % gbps, True)
     os.environ.pop("CHOL_MGPU_H2D_OVERLAP")
     os.environ.pop("CHOL_H2D_GBPS")
+    os.environ.pop("MOCK_CUDA_SLOW_H2D_US")
 
     # not positive definite: the first failing column over all ranks
     for uplo in "LU":

@@ -1,6 +1,7 @@
 """The C host drivers (cuda-cholesky_b200/host/*.c) run end to end WITHOUT a GPU on a mock back
 end: tests/mock/mock_cuda.c (the ~30 CUDA driver entry points the host code uses; "device" memory is
-host memory, every stream operation is immediate), tests/mock/mock_kernels.cpp (the launcher ABI of
+host memory; streams are asynchronous queues on their own threads with CUDA's event semantics, optional
+random stalls and slow uploads), tests/mock/mock_kernels.cpp (the launcher ABI of
 csrc/chol_kernels.h as plain loops written from the launchers' documented semantics) and
 tests/mock/mock_nccl.c (libnccl.so.2 as a rendezvous of the worker threads).  The product sources are
 compiled unchanged; only what they link against differs.  tests/mock/run_host_driver_checks.py then
@@ -14,8 +15,8 @@ compares every driver with the CPU oracle, on 1 and on 3 mock devices:
   (CHOL_MGPU_INVERSE=slab), the host-pointer BLAS, and a device allocation failure that must fail
   the call on every rank instead of leaving some of them in a broadcast.
 
-Synchronous streams cannot show ordering bugs and plain-loop kernels say nothing about the CUDA
-kernels: those are the jobs of tests/test_kernel_emulation.py and of the GPU parity tests."""
+Plain-loop kernels say nothing about the CUDA kernels: that is the job of
+tests/test_kernel_emulation.py and of the GPU parity tests."""
 import glob
 import os
 import subprocess
@@ -52,8 +53,9 @@ def mock_runs(tmp_path_factory):
 
     def run(group):
         # "<group>+blocked": the same checks with the blocked panel solve switched on (read once per process)
+        # "<group>+jitter": every mock stream stalls at random before its operations (ordering races)
         name, _, variant = group.partition("+")
-        e = dict(env, CHOL_PANEL_BLOCKED="1") if variant == "blocked" else env
+        e = dict(env, CHOL_PANEL_BLOCKED="1") if variant == "blocked" else (dict(env, MOCK_CUDA_JITTER="1") if variant == "jitter" else env)
         p = subprocess.run([sys.executable, os.path.join(MOCK, "run_host_driver_checks.py"), lib, name], stdout=subprocess.PIPE,
                            stderr=subprocess.STDOUT, env=e, timeout=1500)
         return p.returncode, p.stdout.decode()
@@ -66,7 +68,7 @@ def mock_runs(tmp_path_factory):
                            timeout=600)
         return p.returncode, p.stdout.decode()
 
-    groups = ("lapack", "blas", "multi1", "multi3", "lapack+blocked", "multi3+blocked")
+    groups = ("lapack", "blas", "multi1", "multi3", "lapack+blocked", "multi3+blocked", "lapack+jitter", "multi3+jitter")
     with ThreadPoolExecutor(max_workers=len(groups)) as ex:
         res = dict(zip(groups, ex.map(run, groups)))
     cdir = os.path.join(ROOT, "tests", "c")
@@ -77,7 +79,8 @@ def mock_runs(tmp_path_factory):
 
 
 @pytest.mark.parametrize("group,min_checks", [("lapack", 700), ("blas", 80), ("multi1", 800), ("multi3", 800),
-                                              ("lapack+blocked", 700), ("multi3+blocked", 800)])
+                                              ("lapack+blocked", 700), ("multi3+blocked", 800),
+                                              ("lapack+jitter", 700), ("multi3+jitter", 800)])
 def test_host_drivers_on_mock_backend(mock_runs, group, min_checks):
     rc, out = mock_runs[group]
     assert rc == 0 and "MOCK PASSED" in out, out[-3000:]
