@@ -167,6 +167,29 @@ def single_device_blas():
                             getattr(blas, name)(p, side, uplo, trans, diag, m, n, alpha, ptr(Tm), ld(Tm), ptr(got), ld(got))
                             close(got, want, p, na, "%s%s %s%s%s%s" % (p, name, side, uplo, trans, diag))
     ok(mock.mock_cuda_ctx_depth() == depth0, "BLAS left contexts on the stack")
+    # two TRSMs / TRMMs on DIFFERENT streams of one handle share the handle's scratch: the library orders them
+    # (an event), so both must still be right when the streams run side by side
+    s1, s2 = C.c_void_p(), C.c_void_p()
+    mock.cuStreamCreate(C.byref(s1), C.c_uint(1))
+    mock.cuStreamCreate(C.byref(s2), C.c_uint(1))
+    m, n = 400, 90
+    T0 = H.spd_matrix("d", m, seed=8, k=16)
+    ORA.potrf("d", "L", T0)
+    for rep in range(6):
+        Bs = [H.rand_matrix("d", m, n, seed=20 + 2 * rep + i) for i in range(2)]
+        wants = [b.copy(order="F") for b in Bs]
+        names = ("trsm", "trmm") if rep % 2 else ("trsm", "trsm")
+        for w, nm in zip(wants, names):
+            getattr(ORA, nm)("d", "L", "L", "N", "N", m, n, 1.0, T0, w)
+        gots = [b.copy(order="F") for b in Bs]
+        for g, st, nm in zip(gots, (s1, s2), names):
+            getattr(blas, nm)("d", "L", "L", "N", "N", m, n, 1.0, ptr(T0), ld(T0), ptr(g), ld(g), stream=st.value)
+        mock.cuStreamSynchronize(s1)
+        mock.cuStreamSynchronize(s2)
+        for g, w, nm in zip(gots, wants, names):
+            close(g, w, "d", m, "two streams, one handle: %s" % nm)
+    mock.cuStreamDestroy_v2(s1)
+    mock.cuStreamDestroy_v2(s2)
     blas.close()
 
 

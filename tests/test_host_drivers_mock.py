@@ -78,7 +78,7 @@ def mock_runs(tmp_path_factory):
     return res
 
 
-@pytest.mark.parametrize("group,min_checks", [("lapack", 700), ("blas", 80), ("multi1", 800), ("multi3", 800),
+@pytest.mark.parametrize("group,min_checks", [("lapack", 700), ("blas", 90), ("multi1", 800), ("multi3", 800),
                                               ("lapack+blocked", 700), ("multi3+blocked", 800),
                                               ("lapack+jitter", 700), ("multi3+jitter", 800)])
 def test_host_drivers_on_mock_backend(mock_runs, group, min_checks):
