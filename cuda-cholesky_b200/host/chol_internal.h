@@ -126,6 +126,9 @@ bool chol_panel_blocked(void);
 /* POTRF panel step (lower): factor the jb x jb diagonal block at Ajj, solve the rest x jb panel P below it into W */
 CUresult chol_panel_factor_solve_lower(int prec, size_t jb, size_t rest, CUdeviceptr Ajj, CUdeviceptr P, size_t lda, CUdeviceptr W,
                                        size_t ldw, long *dinfo, long base, const chol_ws *w, CUstream st);
+/* ... upper: the jb x rest block row P right of the diagonal block, W = P^H * inv(U11) (rest x jb) */
+CUresult chol_panel_factor_solve_upper(int prec, size_t jb, size_t rest, CUdeviceptr Ajj, CUdeviceptr P, size_t lda, CUdeviceptr W,
+                                       size_t ldw, long *dinfo, long base, const chol_ws *w, CUstream st);
 CUresult chol_trtri_small(int prec, int uplo, int diag, size_t jb, CUdeviceptr A, size_t lda, CUdeviceptr X,
                           size_t ldx, long *dinfo, long base, const chol_ws *w, CUstream st);
 

@@ -186,7 +186,7 @@ CUresult chol_diag_factor_inverse_ex(int prec, int uplo, size_t jb, CUdeviceptr 
   return CUDA_SUCCESS;
 }
 
-/* CHOL_PANEL_BLOCKED=1 (lower; written after the round-1 GPU budget was spent, off until measured):
+/* CHOL_PANEL_BLOCKED=1 (written after the round-1 GPU budget was spent, off until measured):
  * instead of inverting the whole jb x jb diagonal block (nblk(nblk-1) small, serial GEMMs to tie the
  * db-blocks of the inverse together) and solving the panel with one GEMM, invert only the db x db
  * diagonal sub-blocks and solve the panel by block forward substitution with full-height GEMMs:
@@ -224,6 +224,31 @@ CUresult chol_panel_factor_solve_lower(int prec, size_t jb, size_t rest, CUdevic
   return CUDA_SUCCESS;
 }
 
+/* the same for upper storage: the jb x rest block row P right of the diagonal block, W = P^H * inv(U11) (rest x jb):
+ *     W_c = (P_c^H - W[:, 0:c] * U[0:c, c]) * inv(U_cc) */
+CUresult chol_panel_factor_solve_upper(int prec, size_t jb, size_t rest, CUdeviceptr Ajj, CUdeviceptr P, size_t lda, CUdeviceptr W,
+                                       size_t ldw, long *dinfo, long base, const chol_ws *w, CUstream st) {
+  const size_t es = w->es, db = w->db, nb = w->nb, nblk = (jb + db - 1) / db;
+  if (!chol_panel_blocked() || nblk < 2 || w->Tp == 0) {
+    CU_ERROR_CHECK(chol_diag_factor_inverse(prec, 'U', jb, Ajj, lda, w->Xd, nb, dinfo, base, w, st));
+    return chol_gemm(prec, 'C', 'N', rest, jb, jb, ONE, P, lda, w->Xd, nb, ZERO, 0, 0, W, ldw, st);
+  }
+  CU_ERROR_CHECK(chol_diag_factor_inverse_ex(prec, 'U', jb, Ajj, lda, w->Xd, nb, dinfo, base, w, st, 1));
+  for (size_t c = 0; c < nblk; c++) {
+    const size_t i = c * db, ib = chol_min(db, jb - i);
+    const CUdeviceptr Pc = chol_at(P, lda, i, 0, es), Wc = chol_at(W, ldw, 0, i, es), Xcc = chol_at(w->Xd, nb, i, i, es);
+    if (c == 0) {
+      CU_ERROR_CHECK(chol_gemm(prec, 'C', 'N', rest, ib, ib, ONE, Pc, lda, Xcc, nb, ZERO, 0, 0, Wc, ldw, st));
+    } else {
+      RT_CHECK(chol_copy_launch(prec, 'C', 0, ib, rest, (const void *)Pc, lda, (void *)w->Tp, w->ldw, (void *)st)); /* T = P_c^H */
+      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'N', rest, ib, i, MONE, W, ldw, chol_at(Ajj, lda, 0, i, es), lda, ONE, w->Tp, w->ldw, w->Tp,
+                               w->ldw, st));
+      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'N', rest, ib, ib, ONE, w->Tp, w->ldw, Xcc, nb, ZERO, 0, 0, Wc, ldw, st));
+    }
+  }
+  return CUDA_SUCCESS;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 static CUresult potrf_body(CULAPACKhandle h, int prec, int uplo, size_t n, CUdeviceptr A, size_t lda, long *info) {
   chol_ws w;
@@ -250,9 +275,8 @@ static CUresult potrf_body(CULAPACKhandle h, int prec, int uplo, size_t n, CUdev
       CU_ERROR_CHECK(chol_panel_factor_solve_lower(prec, jb, rest, Ajj, P, lda, W, w.ldw, dinfo, (long)j, &w, sp));
       RT_CHECK(chol_copy_launch(prec, 'N', 0, rest, jb, (const void *)W, w.ldw, (void *)P, lda, (void *)sp));
     } else {
-      CU_ERROR_CHECK(chol_diag_factor_inverse(prec, uplo, jb, Ajj, lda, w.Xd, nb, dinfo, (long)j, &w, sp));
       const CUdeviceptr P = chol_at(A, lda, j, j + jb, es); /* jb x rest; W = P^H * U11^-1 */
-      CU_ERROR_CHECK(chol_gemm(prec, 'C', 'N', rest, jb, jb, ONE, P, lda, w.Xd, nb, ZERO, 0, 0, W, w.ldw, sp));
+      CU_ERROR_CHECK(chol_panel_factor_solve_upper(prec, jb, rest, Ajj, P, lda, W, w.ldw, dinfo, (long)j, &w, sp));
       RT_CHECK(chol_copy_launch(prec, 'C', 0, rest, jb, (const void *)W, w.ldw, (void *)P, lda, (void *)sp));
     }
     CU_ERROR_CHECK(cuEventRecord(h->ev_panel[step % CHOL_EVENT_RING], sp));
