@@ -177,8 +177,21 @@ __device__ __forceinline__ bool c_staged(const GemmArgs<CPLX> &p, int m0, int n0
   return p.cuplo == 0 || (p.cuplo == 1 && m0 >= g0 + Cfg::BN - 1) || (p.cuplo == 2 && m0 + Cfg::BM - 1 <= g0);
 }
 
+// RINGC (staggered kernel variant gemm_dmma_ppc_kernel, CHOL_GEMM_PP=2; written after the round-1 GPU budget
+// was spent, logic checked on the CPU emulation): the C tile travels through the NORMAL full / empty ring as four
+// extra pseudo-stages after the k loop - 16 tile columns each (d: in the A region of the stage; z: 8 columns in
+// the A region and 8 in the B region) - so it needs no barriers of its own, works for CTAs that own many tiles,
+// and covers z.  Producer and consumers evaluate the same predicate and both advance their ring counters by 4.
+template <bool CPLX>
+__device__ __forceinline__ bool c_ring_staged(const GemmArgs<CPLX> &p, int m0, int n0, int g0) {
+  using Cfg = GemmCfg<CPLX>;
+  if (p.stage_c != 2 || p.beta_zero || !p.vec_ok) return false;
+  if (m0 + Cfg::BM > p.M || n0 + Cfg::BN > p.N) return false;
+  return p.cuplo == 0 || (p.cuplo == 1 && m0 >= g0 + Cfg::BN - 1) || (p.cuplo == 2 && m0 + Cfg::BM - 1 <= g0);
+}
+
 // One tile's worth of producer work: fill the group's stage ring (TMA bulk rows or cp.async gather).
-template <bool CPLX, int MODE, int NPW>
+template <bool CPLX, int MODE, int NPW, bool RINGC = false>
 __device__ __forceinline__ void produce_tile(const GemmArgs<CPLX> &p, int bi, int bj, typename GemmArgs<CPLX>::T *As,
                                              typename GemmArgs<CPLX>::T *Bs, uint64_t *full, uint64_t *empty, uint32_t &it,
                                              uint64_t *cbar, int pw, int lane) {
@@ -249,6 +262,20 @@ __device__ __forceinline__ void produce_tile(const GemmArgs<CPLX> &p, int bi, in
       mbar_arrive(&full[s]);
     }
   }
+  if constexpr (RINGC && MODE == 0) {
+    if (pw == 0 && c_ring_staged<CPLX>(p, m0, n0, g0)) {
+      for (int ps = 0; ps < 4; ++ps, ++it) {  // pseudo-stage ps = tile columns 16 ps .. 16 ps + 15
+        const int s = it % ST;
+        mbar_wait(&empty[s], ((it / ST) & 1) ^ 1);
+        if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)(16 * BM * Cfg::ESZ));
+        __syncwarp();
+        if (lane < 16) {
+          T *dst = (!CPLX || lane < 8) ? As + s * Cfg::A_STAGE + lane * LDA : Bs + s * Cfg::B_STAGE + (lane - 8) * LDB;
+          tma_bulk_g2s(dst, p.C + (long long)(n0 + 16 * ps + lane) * p.ldc + m0, BM * Cfg::ESZ, &full[s]);
+        }
+      }
+    }
+  }
   if constexpr (!CPLX) {
     if (cbar != nullptr && pw == 0 && c_staged<CPLX>(p, m0, n0, g0)) {
 #pragma unroll
@@ -265,7 +292,7 @@ __device__ __forceinline__ void produce_tile(const GemmArgs<CPLX> &p, int bi, in
 }
 
 // One tile's worth of consumer work for a group of 4 warps: DMMA main loop + epilogue.
-template <bool CPLX, int MODE>
+template <bool CPLX, int MODE, bool RINGC = false>
 __device__ __forceinline__ void consume_tile(const GemmArgs<CPLX> &p, int bi, int bj, const typename GemmArgs<CPLX>::T *As,
                                              const typename GemmArgs<CPLX>::T *Bs, uint64_t *full, uint64_t *empty, uint32_t &it,
                                              uint64_t *mid, uint64_t *cbar, int warp, int lane) {
@@ -320,6 +347,37 @@ __device__ __forceinline__ void consume_tile(const GemmArgs<CPLX> &p, int bi, in
     const double alpha = p.alpha, beta = p.beta;
     const bool interior = (m0 + BM <= p.M) && (n0 + BN <= p.N) &&
                           (p.cuplo == 0 || (p.cuplo == 1 && m0 >= g0 + BN - 1) || (p.cuplo == 2 && m0 + BM - 1 <= g0));
+    if constexpr (RINGC && MODE == 0) {
+      if (c_ring_staged<CPLX>(p, m0, n0, g0)) {
+#pragma unroll  // static accumulator indices: a rolled loop would push the accumulators to local memory
+        for (int ps = 0; ps < 4; ++ps, ++it) {
+          const int s = it % ST;
+          mbar_wait(&full[s], (it / ST) & 1);
+          if ((ps >> 1) == wn) {  // this warp's 32 columns are pseudo-stages 2 wn and 2 wn + 1
+            const int jh = ps & 1;
+            const double *cs = As + s * Cfg::A_STAGE;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int ml = wm * 64 + 16 * q + 2 * g;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int j = jh * 2 + (e >> 1), c = e & 1;
+                const int nl16 = 2 * (2 * t4 + c) + (j & 1);
+                const double2 cv = *reinterpret_cast<const double2 *>(cs + nl16 * LDA + ml);
+                const long long n = n0 + wn * 32 + 16 * jh + nl16;
+                double2 o;
+                o.x = alpha * acc[2 * q][j][c] + beta * cv.x;
+                o.y = alpha * acc[2 * q + 1][j][c] + beta * cv.y;
+                *reinterpret_cast<double2 *>(p.D + n * p.ldd + (m0 + ml)) = o;
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[s]);
+        }
+        return;
+      }
+    }
     if (cbar != nullptr && c_staged<CPLX>(p, m0, n0, g0)) {
       // C comes from shared memory: chunk (wn*2 + (j>>1)) sits in the A region of stage (it + chunk) % ST
 #pragma unroll
@@ -433,6 +491,37 @@ __device__ __forceinline__ void consume_tile(const GemmArgs<CPLX> &p, int bi, in
     }
 
     const double2 alpha = p.alpha, beta = p.beta;
+    if constexpr (RINGC && MODE == 0) {
+      if (c_ring_staged<CPLX>(p, m0, n0, g0)) {  // interior tile: no triangle mask, no Hermitian diagonal inside
+#pragma unroll  // static accumulator indices: a rolled loop would push the accumulators to local memory
+        for (int ps = 0; ps < 4; ++ps, ++it) {
+          const int s = it % ST;
+          mbar_wait(&full[s], (it / ST) & 1);
+          if ((ps >> 1) == wn) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {  // columns 16 ps + 8 half .. + 7: A region, then B region
+              const int j = (ps & 1) * 2 + half;
+              const double2 *cs = half ? Bs + s * Cfg::B_STAGE : As + s * Cfg::A_STAGE;
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                  const int ml = wm * 32 + 8 * i + g, nl8 = 2 * t4 + c;
+                  const double2 cv = cs[nl8 * LDA + ml];
+                  const double xr = accr[i][j][c], xi = acci[i][j][c];
+                  double2 o = make_double2(alpha.x * xr - alpha.y * xi, alpha.x * xi + alpha.y * xr);
+                  o.x += beta.x * cv.x - beta.y * cv.y;
+                  o.y += beta.x * cv.y + beta.y * cv.x;
+                  p.D[(long long)(n0 + wn * 32 + 8 * j + nl8) * p.ldd + (m0 + ml)] = o;
+                }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[s]);
+        }
+        return;
+      }
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -574,6 +663,64 @@ __global__ void __launch_bounds__(GemmCfg<CPLX>::PP_THREADS, 1) gemm_dmma_pp_ker
   }
 }
 
+// ---- staggered schedule with the C tile staged through the ring (CHOL_GEMM_PP=2; TMA descriptors only) ----
+//      Same shell as gemm_dmma_pp_kernel; producers and consumers are instantiated with RINGC, so after every
+//      interior tile's k loop four pseudo-stages carry the C tile through the group's ring and the epilogue
+//      reads C from shared memory instead of waiting for HBM (d and z).  A separate kernel so that the measured
+//      staggered kernel (the default for z) stays as it is until this one has been verified and timed on hardware.
+template <bool CPLX>
+__global__ void __launch_bounds__(GemmCfg<CPLX>::PP_THREADS, 1) gemm_dmma_ppc_kernel(const __grid_constant__ GemmArgs<CPLX> p) {
+  using Cfg = GemmCfg<CPLX>;
+  using T = typename GemmArgs<CPLX>::T;
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, ST = Cfg::STAGES;
+  CHOL_DYN_SMEM128(smem_raw);
+  constexpr int RING = ST * (Cfg::A_STAGE + Cfg::B_STAGE);
+  T *base = reinterpret_cast<T *>(smem_raw);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(base + 2 * RING);
+  uint64_t *mid = bars + 4 * ST;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    init_ring<CPLX, 0, 2>(bars, bars + ST);
+    init_ring<CPLX, 0, 2>(bars + 2 * ST, bars + 3 * ST);
+    mbar_init(&mid[0], 4);
+    mbar_init(&mid[1], 4);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const int imax = p.tps;
+  const long long tbase = (long long)blockIdx.x * 2 * p.tps;
+  if (warp >= 8) {
+    CHOL_SETMAXNREG_DEC(56);
+    const int gq = (warp - 8) >> 1;
+    T *As = base + gq * RING, *Bs = As + ST * Cfg::A_STAGE;
+    uint64_t *full = bars + gq * 2 * ST, *empty = full + ST;
+    uint32_t it = 0;
+    if (warp & 1) return;  // TMA path: one producer warp per group
+    for (int i = 0; i < imax; ++i) {
+      const long long t = tbase + gq + 2 * i;
+      int bi, bj;
+      const bool valid = t < p.total_tiles && tile_coords_tb<BM, BN>(p.tb, p.group, p.cuplo, p.NI, p.NJ, p.cm, t, bi, bj);
+      if (gq == 0) { if (i >= 1) mbar_wait(&mid[1], (i - 1) & 1); }
+      else mbar_wait(&mid[0], i & 1);
+      __syncwarp();
+      if (valid) produce_tile<CPLX, 0, 2, true>(p, bi, bj, As, Bs, full, empty, it, nullptr, 0, lane);
+      else if (lane == 0) mbar_arrive_n(&mid[gq], 4);
+    }
+  } else {
+    CHOL_SETMAXNREG_INC(224);
+    const int gq = warp >> 2;
+    const T *As = base + gq * RING, *Bs = As + ST * Cfg::A_STAGE;
+    uint64_t *full = bars + gq * 2 * ST, *empty = full + ST;
+    uint32_t it = 0;
+    for (int i = 0; i < imax; ++i) {
+      const long long t = tbase + gq + 2 * i;
+      int bi, bj;
+      const bool valid = t < p.total_tiles && tile_coords_tb<BM, BN>(p.tb, p.group, p.cuplo, p.NI, p.NJ, p.cm, t, bi, bj);
+      if (valid) consume_tile<CPLX, 0, true>(p, bi, bj, As, Bs, full, empty, it, &mid[gq], nullptr, warp & 3, lane);
+    }
+  }
+}
+
 template <bool CPLX>
 static bool tma_eligible(const chol_gemm_desc *d) {
   using Cfg = GemmCfg<CPLX>;
@@ -663,6 +810,8 @@ static int launch_t(const chol_gemm_desc *d) {
   if (!attr_set[dev & 63][CPLX][tma].load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_pp, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::PP_SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_dmma_ppc_kernel<CPLX>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::PP_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     int n_sm = 0;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
@@ -670,7 +819,8 @@ static int launch_t(const chol_gemm_desc *d) {
     attr_set[dev & 63][CPLX][tma].store(1, std::memory_order_release);
   }
   // tuning switches (environment, read once - thread-safe static initialisation):
-  //   CHOL_GEMM_PP=0/1      staggered two-group kernel for grids with >= 4 tiles per SM (default: z only)
+  //   CHOL_GEMM_PP=0/1/2    staggered two-group kernel for grids with >= 4 tiles per SM (default: z only);
+  //                         2 = the variant that stages the C tile through the ring (TMA descriptors only)
   //   CHOL_GEMM_PERSIST=n   classic kernel as n persistent CTAs per SM (default 0: one CTA per tile - the
   //                         hardware's dynamic CTA placement beats a static persistent walk)
   //   CHOL_GEMM_PREFETCH=1  enable the L2 prefetch of C tiles (default off: ncu showed +50 % DRAM reads,
@@ -691,7 +841,11 @@ static int launch_t(const chol_gemm_desc *d) {
   a.prefetch_c = prefetch;
   a.stage_c = stagec;
   const int sms = sm_count[dev & 63].load(std::memory_order_relaxed);
-  if ((pingpong < 0 ? CPLX : pingpong != 0) && tiles >= 4LL * sms && a.K > 0) {  // (K = 0: no stages to pace the groups with)
+  if (pingpong == 2 && tma && tiles >= 4LL * sms && a.K > 0) {  // staggered + ring-staged C (off until verified on hardware)
+    a.tps = tps;
+    a.stage_c = 2;
+    gemm_dmma_ppc_kernel<CPLX><<<(unsigned)((tiles + 2 * tps - 1) / (2 * tps)), Cfg::PP_THREADS, Cfg::PP_SMEM_BYTES, st>>>(a);
+  } else if ((pingpong < 0 ? CPLX : pingpong != 0) && tiles >= 4LL * sms && a.K > 0) {  // (K = 0: no stages to pace the groups with)
     a.tps = tps;
     kern_pp<<<(unsigned)((tiles + 2 * tps - 1) / (2 * tps)), Cfg::PP_THREADS, Cfg::PP_SMEM_BYTES, st>>>(a);
   } else {

@@ -3,13 +3,13 @@
 # (tests marked `staged`, library paths behind environment switches - DESIGN.md §4.1) and A/B it.
 #   gpurun --timeout 3000 -- 'bash scripts/verify_staged.sh'            # everything, ~45 min
 #   gpurun --timeout 1200 -- 'STAGES="tests chain" bash scripts/verify_staged.sh'
-# Stages, in order of importance: tests chain e2e fp32 inverse memcheck.  Every command runs under its
+# Stages, in order of importance: tests chain engine e2e fp32 inverse memcheck.  Every command runs under its
 # own `timeout`; results land in gpurun_out/staged_* with a one-page gpurun_out/staged_summary.txt.
 set -u
 cd "$(dirname "$0")/.."
 OUT=gpurun_out
 mkdir -p $OUT
-STAGES=${STAGES:-"tests chain e2e fp32 inverse memcheck"}
+STAGES=${STAGES:-"tests chain engine e2e fp32 inverse memcheck"}
 SUM=$OUT/staged_summary.txt
 : > $SUM
 say() { echo "$@" | tee -a $SUM; }
@@ -49,6 +49,21 @@ if has chain; then
     set -- $CFG
     CHOL_POTF2_V2=$1 CHOL_SMALL_GEMM=$2 CHOL_PANEL_BLOCKED=$3 timeout 300 python scripts/configs_bench.py cfg1 2>&1 | grep -E "^dpotrf" \
       | sed "s/^/POTF2_V2=$1 SMALL_GEMM=$2 PANEL_BLOCKED=$3 /" | tee -a $SUM
+  done
+fi
+
+if has engine; then
+  say "== tile engine: staggered kernel with the C tile staged through the ring (CHOL_GEMM_PP=2) =="
+  CHOL_GEMM_PP=2 timeout 1200 python -m pytest tests/test_gpu_blas.py tests/test_gpu_lapack.py tests/test_gpu_multigpu.py -m gpu -q -x \
+    > $OUT/staged_ppc_tests.log 2>&1
+  say "parity with CHOL_GEMM_PP=2 rc=$?"; tail -2 $OUT/staged_ppc_tests.log | tee -a $SUM
+  for PP in 0 1 2; do
+    CHOL_GEMM_PP=$PP timeout 400 python bench.py --order 65536 --steps 2 --warmup 2 --e2e-steps 1 --skip-cpu-baseline \
+      > $OUT/staged_pp${PP}_n65536.json 2> $OUT/staged_pp${PP}_n65536.err
+    bench_line $OUT/staged_pp${PP}_n65536.json 65536 "CHOL_GEMM_PP=$PP (dpotrf)"
+  done
+  for PP in 1 2; do
+    CHOL_GEMM_PP=$PP timeout 400 python scripts/configs_bench.py cfg2 2>&1 | grep -E "^zpotrf" | sed "s/^/GEMM_PP=$PP /" | tee -a $SUM
   done
 fi
 

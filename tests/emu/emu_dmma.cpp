@@ -22,7 +22,7 @@ static int failures = 0, cases = 0;
 static std::complex<double> cj(std::complex<double> x) { return std::conj(x); }
 static double cj(double x) { return x; }
 
-enum Sched { CLASSIC, PERSISTENT, STAGGERED };
+enum Sched { CLASSIC, PERSISTENT, STAGGERED, STAGGERED_RINGC };
 
 struct Case {
   int M, N, K;
@@ -73,7 +73,13 @@ static void run_case(const Case &c, Sched sched) {
   const H beta = [&] { if constexpr (CPLX) return H(d.beta[0], d.beta[1]); else return H(d.beta[0]); }();
 
   auto go = [&](auto kern_classic, auto kern_pp) {
-    if (sched == STAGGERED) {
+    if (sched == STAGGERED_RINGC) {
+      if (!tma) { std::printf("ring-staged case is not TMA-eligible\n"); ++failures; return; }
+      a.tps = 2;
+      a.stage_c = 2;
+      emu::launch(dim3((unsigned)((tiles + 2 * a.tps - 1) / (2 * a.tps))), dim3(Cfg::PP_THREADS), Cfg::PP_SMEM_BYTES,
+                  [&] { gemm_dmma_ppc_kernel<CPLX>(a); });
+    } else if (sched == STAGGERED) {
       a.tps = 2;
       emu::launch(dim3((unsigned)((tiles + 2 * a.tps - 1) / (2 * a.tps))), dim3(Cfg::PP_THREADS), Cfg::PP_SMEM_BYTES, [&] { kern_pp(a); });
     } else {
@@ -117,7 +123,7 @@ static void run_case(const Case &c, Sched sched) {
   ++cases;
   const bool ok = err <= 1e-13 * (c.K + 8);
   std::printf("%s %-10s %s M=%d N=%d K=%d op=%c%c tri=%c%c cuplo=%c herm=%d cyc=%d/%d stage_c=%d tiles=%lld: %s (%.1e)\n", CPLX ? "z" : "d",
-              sched == CLASSIC ? "classic" : (sched == PERSISTENT ? "persistent" : "staggered"), tma ? "TMA    " : "generic", c.M, c.N, c.K, c.opA,
+              sched == CLASSIC ? "classic" : (sched == PERSISTENT ? "persistent" : (sched == STAGGERED ? "staggered" : "stag+ringC")), tma ? "TMA    " : "generic", c.M, c.N, c.K, c.opA,
               c.opB, c.triA ? c.triA : '-', c.triB ? c.triB : '-', c.cuplo ? c.cuplo : '-', c.herm, c.cyc_nb, c.cyc_p, c.stage_c, tiles,
               ok ? "ok" : "MISMATCH", err);
   if (!ok) ++failures;
@@ -132,6 +138,13 @@ static void sweep() {
     run_case<CPLX>({3 * BM, 192, 48, 'N', hT, 0, 0, 0, 0, 'L', 1, true, 0, 0, 0, 1}, s);
     run_case<CPLX>({2 * BM + 10, 150, 32, 'N', hT, 0, 0, 0, 0, 0, 0, true, 0, 0, 0, 1}, s);  // ragged edges
   }
+  // the staggered kernel with the C tile staged through the ring: interior, diagonal-crossing and ragged tiles,
+  // both triangles, the block-cyclic map, short and long k loops
+  run_case<CPLX>({3 * BM, 192, 48, 'N', hT, 0, 0, 0, 0, 'L', 1, true, 0, 0, 0, 1}, STAGGERED_RINGC);
+  run_case<CPLX>({3 * BM, 192, 16, 'N', hT, 0, 0, 0, 0, 'U', 1, true, 0, 0, 0, 1}, STAGGERED_RINGC);
+  run_case<CPLX>({2 * BM + 10, 150, 32, 'N', hT, 0, 0, 0, 0, 0, 0, true, 0, 0, 0, 1}, STAGGERED_RINGC);
+  run_case<CPLX>({4 * BM, 256, 80, 'N', hT, 0, 0, 0, 0, 0, 0, true, 0, 0, 0, 1}, STAGGERED_RINGC);
+  run_case<CPLX>({5 * BM, 128, 32, 'N', hT, 0, 0, 0, 0, 'L', 1, true, 64, 2, 1, 1}, STAGGERED_RINGC);
   run_case<CPLX>({3 * BM, 192, 48, 'N', hT, 0, 0, 0, 0, 'U', 1, true, 0, 0, 0, 1}, CLASSIC);
   run_case<CPLX>({2 * BM, 128, 64, 'N', hT, 0, 0, 0, 0, 0, 0, true, 0, 0, 0, 0}, CLASSIC);   // C read from global memory
   // block-cyclic column map of the distributed update (P = 2, this rank's offset 1), lower

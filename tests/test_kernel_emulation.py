@@ -78,9 +78,9 @@ def test_fp32_gemm_engine_emulated(emu):
 
 
 def test_fp64_tensor_core_engine_emulated(emu):
-    """classic (TMA-staged C epilogue), persistent and staggered schedules; TMA and generic loaders; d and z;
+    """classic (TMA-staged C epilogue), persistent, staggered and staggered-with-ring-staged-C schedules; TMA and generic loaders; d and z;
     triangular masks, triangle-only / Hermitian output, block-cyclic column map, K = 0"""
     out = _passed(emu, "emu_dmma.cpp")
-    assert "44 cases" in out
-    for sched in ("classic", "persistent", "staggered"):
+    assert "54 cases" in out
+    for sched in ("classic", "persistent", "staggered", "stag+ringC"):
         assert out.count(sched) >= 4
