@@ -40,8 +40,10 @@ struct __culapackhandle_st {
   CUcontext context;
   CUstream s_panel;  /* high priority: diagonal block, panel solve, look-ahead update */
   CUstream s_update; /* trailing-matrix update */
+  CUstream s_look;   /* lower part of the look-ahead column when the look-ahead is split (CHOL_LOOKAHEAD_SPLIT) */
   CUevent ev_panel[CHOL_EVENT_RING];
   CUevent ev_rest[CHOL_EVENT_RING];
+  CUevent ev_look[CHOL_EVENT_RING];
   CUdeviceptr ws; /* workspace, cached across calls (the reference allocates per call, dpotrf.c:200) */
   size_t ws_bytes;
   CUdeviceptr dinfo;      /* device long */
@@ -125,10 +127,11 @@ CUresult chol_diag_factor_inverse_ex(int prec, int uplo, size_t jb, CUdeviceptr 
 bool chol_panel_blocked(void);
 /* POTRF panel step (lower): factor the jb x jb diagonal block at Ajj, solve the rest x jb panel P below it into W */
 CUresult chol_panel_factor_solve_lower(int prec, size_t jb, size_t rest, CUdeviceptr Ajj, CUdeviceptr P, size_t lda, CUdeviceptr W,
-                                       size_t ldw, long *dinfo, long base, const chol_ws *w, CUstream st);
+                                       size_t ldw, long *dinfo, long base, const chol_ws *w, CUstream st, CUevent before_solve);
+bool chol_lookahead_split(void);
 /* ... upper: the jb x rest block row P right of the diagonal block, W = P^H * inv(U11) (rest x jb) */
 CUresult chol_panel_factor_solve_upper(int prec, size_t jb, size_t rest, CUdeviceptr Ajj, CUdeviceptr P, size_t lda, CUdeviceptr W,
-                                       size_t ldw, long *dinfo, long base, const chol_ws *w, CUstream st);
+                                       size_t ldw, long *dinfo, long base, const chol_ws *w, CUstream st, CUevent before_solve);
 CUresult chol_trtri_small(int prec, int uplo, int diag, size_t jb, CUdeviceptr A, size_t lda, CUdeviceptr X,
                           size_t ldx, long *dinfo, long base, const chol_ws *w, CUstream st);
 

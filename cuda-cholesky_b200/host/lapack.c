@@ -69,6 +69,7 @@ static CUresult finish_info(CULAPACKhandle h, CUstream producer, long *info) {
   CU_ERROR_CHECK(cuMemcpyDtoHAsync(h->hinfo, h->dinfo, sizeof(long), producer));
   CU_ERROR_CHECK(cuStreamSynchronize(h->s_panel));
   CU_ERROR_CHECK(cuStreamSynchronize(h->s_update));
+  CU_ERROR_CHECK(cuStreamSynchronize(h->s_look));
   *info = *h->hinfo;
   return CUDA_SUCCESS;
 }
@@ -201,15 +202,33 @@ bool chol_panel_blocked(void) {
   return on != 0;
 }
 
+/* CHOL_LOOKAHEAD_SPLIT=1 (written after the round-1 GPU budget was spent, off until measured): the look-ahead
+ * update of the next block column is split - its jb2 x jb2 diagonal block stays on the panel stream, so the next
+ * diagonal block can be factored at once, while the rows below it (the bulk of the column) are updated on a
+ * third stream at the same time; the next panel solve waits for that part.  Takes the look-ahead GEMM off the
+ * serial panel chain (stream dependencies mutation-tested on the asynchronous mock back end). */
+bool chol_lookahead_split(void) {
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("CHOL_LOOKAHEAD_SPLIT");
+    on = (e != NULL && atoi(e) != 0) ? 1 : 0;
+  }
+  return on != 0;
+}
+
 /* factor the jb x jb lower diagonal block at Ajj and solve the rest x jb panel P below it into W */
+/* before_solve (may be NULL): an event the stream must have seen before the panel P is read - the lower part of
+ * a split look-ahead runs on another stream while the diagonal block is factored here */
 CUresult chol_panel_factor_solve_lower(int prec, size_t jb, size_t rest, CUdeviceptr Ajj, CUdeviceptr P, size_t lda, CUdeviceptr W,
-                                       size_t ldw, long *dinfo, long base, const chol_ws *w, CUstream st) {
+                                       size_t ldw, long *dinfo, long base, const chol_ws *w, CUstream st, CUevent before_solve) {
   const size_t es = w->es, db = w->db, nb = w->nb, nblk = (jb + db - 1) / db;
   if (!chol_panel_blocked() || nblk < 2 || w->Tp == 0) {
     CU_ERROR_CHECK(chol_diag_factor_inverse(prec, 'L', jb, Ajj, lda, w->Xd, nb, dinfo, base, w, st));
+    if (before_solve) CU_ERROR_CHECK(cuStreamWaitEvent(st, before_solve, 0));
     return chol_gemm(prec, 'N', 'C', rest, jb, jb, ONE, P, lda, w->Xd, nb, ZERO, 0, 0, W, ldw, st);
   }
   CU_ERROR_CHECK(chol_diag_factor_inverse_ex(prec, 'L', jb, Ajj, lda, w->Xd, nb, dinfo, base, w, st, 1));
+  if (before_solve) CU_ERROR_CHECK(cuStreamWaitEvent(st, before_solve, 0));
   for (size_t c = 0; c < nblk; c++) {
     const size_t i = c * db, ib = chol_min(db, jb - i);
     const CUdeviceptr Pc = chol_at(P, lda, 0, i, es), Wc = chol_at(W, ldw, 0, i, es), Xcc = chol_at(w->Xd, nb, i, i, es);
@@ -227,13 +246,15 @@ CUresult chol_panel_factor_solve_lower(int prec, size_t jb, size_t rest, CUdevic
 /* the same for upper storage: the jb x rest block row P right of the diagonal block, W = P^H * inv(U11) (rest x jb):
  *     W_c = (P_c^H - W[:, 0:c] * U[0:c, c]) * inv(U_cc) */
 CUresult chol_panel_factor_solve_upper(int prec, size_t jb, size_t rest, CUdeviceptr Ajj, CUdeviceptr P, size_t lda, CUdeviceptr W,
-                                       size_t ldw, long *dinfo, long base, const chol_ws *w, CUstream st) {
+                                       size_t ldw, long *dinfo, long base, const chol_ws *w, CUstream st, CUevent before_solve) {
   const size_t es = w->es, db = w->db, nb = w->nb, nblk = (jb + db - 1) / db;
   if (!chol_panel_blocked() || nblk < 2 || w->Tp == 0) {
     CU_ERROR_CHECK(chol_diag_factor_inverse(prec, 'U', jb, Ajj, lda, w->Xd, nb, dinfo, base, w, st));
+    if (before_solve) CU_ERROR_CHECK(cuStreamWaitEvent(st, before_solve, 0));
     return chol_gemm(prec, 'C', 'N', rest, jb, jb, ONE, P, lda, w->Xd, nb, ZERO, 0, 0, W, ldw, st);
   }
   CU_ERROR_CHECK(chol_diag_factor_inverse_ex(prec, 'U', jb, Ajj, lda, w->Xd, nb, dinfo, base, w, st, 1));
+  if (before_solve) CU_ERROR_CHECK(cuStreamWaitEvent(st, before_solve, 0));
   for (size_t c = 0; c < nblk; c++) {
     const size_t i = c * db, ib = chol_min(db, jb - i);
     const CUdeviceptr Pc = chol_at(P, lda, i, 0, es), Wc = chol_at(W, ldw, 0, i, es), Xcc = chol_at(w->Xd, nb, i, i, es);
@@ -256,9 +277,11 @@ static CUresult potrf_body(CULAPACKhandle h, int prec, int uplo, size_t n, CUdev
   const size_t es = w.es, nb = w.nb;
   const int herm = chol_is_complex(prec);
   long *dinfo = (long *)h->dinfo;
-  CUstream sp = h->s_panel, su = h->s_update;
+  CUstream sp = h->s_panel, su = h->s_update, sl = h->s_look;
   CU_ERROR_CHECK(cuMemsetD8Async(h->dinfo, 0, sizeof(long), sp));
   h->prof_n = 0;
+  const bool split = chol_lookahead_split();
+  CUevent look_pending = NULL; /* the lower part of this step's block column is still being updated on sl */
 
   size_t step = 0;
   for (size_t j = 0; j < n; j += nb, step++) {
@@ -270,13 +293,15 @@ static CUresult potrf_body(CULAPACKhandle h, int prec, int uplo, size_t n, CUdev
       CU_ERROR_CHECK(chol_potrf_diag(prec, uplo, jb, Ajj, lda, dinfo, (long)j, &w, sp));
       break;
     }
+    const CUevent before_solve = look_pending;
+    look_pending = NULL;
     if (uplo == 'L') {
       const CUdeviceptr P = chol_at(A, lda, j + jb, j, es); /* rest x jb */
-      CU_ERROR_CHECK(chol_panel_factor_solve_lower(prec, jb, rest, Ajj, P, lda, W, w.ldw, dinfo, (long)j, &w, sp));
+      CU_ERROR_CHECK(chol_panel_factor_solve_lower(prec, jb, rest, Ajj, P, lda, W, w.ldw, dinfo, (long)j, &w, sp, before_solve));
       RT_CHECK(chol_copy_launch(prec, 'N', 0, rest, jb, (const void *)W, w.ldw, (void *)P, lda, (void *)sp));
     } else {
       const CUdeviceptr P = chol_at(A, lda, j, j + jb, es); /* jb x rest; W = P^H * U11^-1 */
-      CU_ERROR_CHECK(chol_panel_factor_solve_upper(prec, jb, rest, Ajj, P, lda, W, w.ldw, dinfo, (long)j, &w, sp));
+      CU_ERROR_CHECK(chol_panel_factor_solve_upper(prec, jb, rest, Ajj, P, lda, W, w.ldw, dinfo, (long)j, &w, sp, before_solve));
       RT_CHECK(chol_copy_launch(prec, 'C', 0, rest, jb, (const void *)W, w.ldw, (void *)P, lda, (void *)sp));
     }
     CU_ERROR_CHECK(cuEventRecord(h->ev_panel[step % CHOL_EVENT_RING], sp));
@@ -302,7 +327,27 @@ static CUresult potrf_body(CULAPACKhandle h, int prec, int uplo, size_t n, CUdev
     if (step > 0) CU_ERROR_CHECK(cuStreamWaitEvent(sp, h->ev_rest[(step - 1) % CHOL_EVENT_RING], 0));
     {
       const CUdeviceptr A22 = chol_at(A, lda, j + jb, j + jb, es);
-      if (uplo == 'L') /* rest x jb2 block column, lower part */
+      const size_t below = rest - jb2; /* rows (columns, upper) of the look-ahead column outside its diagonal block */
+      if (split && below) {
+        /* diagonal block here; the rest on the look-ahead stream, which needs W (panel event) and the previous
+         * trailing update of this column */
+        CU_ERROR_CHECK(cuStreamWaitEvent(sl, h->ev_panel[step % CHOL_EVENT_RING], 0));
+        if (step > 0) CU_ERROR_CHECK(cuStreamWaitEvent(sl, h->ev_rest[(step - 1) % CHOL_EVENT_RING], 0));
+        const CUdeviceptr Wb = chol_at(W, w.ldw, jb2, 0, es);
+        if (uplo == 'L') {
+          CU_ERROR_CHECK(chol_gemm_ex(prec, 'N', 'C', 0, 0, 0, 0, 'L', herm, jb2, jb2, jb, MONE, W, w.ldw, W, w.ldw, ONE, A22, lda, A22,
+                                      lda, sp));
+          const CUdeviceptr A32 = chol_at(A22, lda, jb2, 0, es);
+          CU_ERROR_CHECK(chol_gemm(prec, 'N', 'C', below, jb2, jb, MONE, Wb, w.ldw, W, w.ldw, ONE, A32, lda, A32, lda, sl));
+        } else {
+          CU_ERROR_CHECK(chol_gemm_ex(prec, 'N', 'C', 0, 0, 0, 0, 'U', herm, jb2, jb2, jb, MONE, W, w.ldw, W, w.ldw, ONE, A22, lda, A22,
+                                      lda, sp));
+          const CUdeviceptr A23 = chol_at(A22, lda, 0, jb2, es);
+          CU_ERROR_CHECK(chol_gemm(prec, 'N', 'C', jb2, below, jb, MONE, W, w.ldw, Wb, w.ldw, ONE, A23, lda, A23, lda, sl));
+        }
+        look_pending = h->ev_look[step % CHOL_EVENT_RING];
+        CU_ERROR_CHECK(cuEventRecord(look_pending, sl));
+      } else if (uplo == 'L') /* rest x jb2 block column, lower part */
         CU_ERROR_CHECK(chol_gemm_ex(prec, 'N', 'C', 0, 0, 0, 0, 'L', herm, rest, jb2, jb, MONE, W, w.ldw, W, w.ldw, ONE, A22,
                                     lda, A22, lda, sp));
       else /* jb2 x rest block row, upper part */

@@ -400,7 +400,9 @@ static CUresult dist_potrf(chol_rank *R, int prec, size_t n, CUdeviceptr Aloc, s
   const size_t es = w.es, nb = w.nb, nblk = (n + nb - 1) / nb;
   const int herm = chol_is_complex(prec);
   long *dinfo = (long *)h->dinfo;
-  CUstream sp = h->s_panel, su = h->s_update;
+  CUstream sp = h->s_panel, su = h->s_update, sl = h->s_look;
+  const bool split = chol_lookahead_split();
+  CUevent look_pending = NULL; /* lower part of the block column this rank factors next, still being updated on sl */
   const size_t my_cols = local_cols(n, nb, me, P);
   CU_ERROR_CHECK(cuMemsetD8Async(h->dinfo, 0, sizeof(long), sp));
   h->prof_n = 0;
@@ -432,7 +434,8 @@ static CUresult dist_potrf(chol_rank *R, int prec, size_t n, CUdeviceptr Aloc, s
       }
       if (rest) {
         const CUdeviceptr Pn = chol_at(Aloc, ldl, j + jb, lc * nb, es);
-        CU_ERROR_CHECK(chol_panel_factor_solve_lower(prec, jb, rest, Ajj, Pn, ldl, W, ldw, dinfo, (long)j, &w, sp));
+        CU_ERROR_CHECK(chol_panel_factor_solve_lower(prec, jb, rest, Ajj, Pn, ldl, W, ldw, dinfo, (long)j, &w, sp, look_pending));
+        look_pending = NULL;
       }
     }
     if (rest == 0) break;
@@ -495,13 +498,26 @@ static CUresult dist_potrf(chol_rank *R, int prec, size_t n, CUdeviceptr Aloc, s
       const CUdeviceptr A22 = chol_at(Aloc, ldl, j + jb, lc1 * nb, es);
       if (c >= 1) CU_ERROR_CHECK(cuStreamWaitEvent(sp, h->ev_rest[(c - 1) % CHOL_EVENT_RING], 0));
       if (staged) CU_ERROR_CHECK(cuStreamWaitEvent(sp, sg->ev[lc1 / sg->gblk], 0));
-      CU_ERROR_CHECK(chol_gemm_ex(prec, 'N', 'C', 0, 0, 0, 0, 'L', herm, rest, jb2, jb, MONE, W, ldw, W, ldw, ONE, A22, ldl,
-                                  A22, ldl, sp));
+      const size_t below = rest - jb2;
+      if (split && below) { /* diagonal block here, the rows below it on the look-ahead stream (see chol_lookahead_split) */
+        CU_ERROR_CHECK(cuStreamWaitEvent(sl, h->ev_panel[c % CHOL_EVENT_RING], 0)); /* W has arrived / been solved */
+        if (c >= 1) CU_ERROR_CHECK(cuStreamWaitEvent(sl, h->ev_rest[(c - 1) % CHOL_EVENT_RING], 0));
+        if (staged) CU_ERROR_CHECK(cuStreamWaitEvent(sl, sg->ev[lc1 / sg->gblk], 0));
+        CU_ERROR_CHECK(chol_gemm_ex(prec, 'N', 'C', 0, 0, 0, 0, 'L', herm, jb2, jb2, jb, MONE, W, ldw, W, ldw, ONE, A22, ldl, A22, ldl, sp));
+        const CUdeviceptr A32 = chol_at(A22, ldl, jb2, 0, es);
+        CU_ERROR_CHECK(chol_gemm(prec, 'N', 'C', below, jb2, jb, MONE, chol_at(W, ldw, jb2, 0, es), ldw, W, ldw, ONE, A32, ldl, A32, ldl, sl));
+        look_pending = h->ev_look[c % CHOL_EVENT_RING];
+        CU_ERROR_CHECK(cuEventRecord(look_pending, sl));
+      } else {
+        CU_ERROR_CHECK(chol_gemm_ex(prec, 'N', 'C', 0, 0, 0, 0, 'L', herm, rest, jb2, jb, MONE, W, ldw, W, ldw, ONE, A22, ldl,
+                                    A22, ldl, sp));
+      }
     }
   }
   CU_ERROR_CHECK(cuMemcpyDtoHAsync(h->hinfo, h->dinfo, sizeof(long), sp));
   CU_ERROR_CHECK(cuStreamSynchronize(sp));
   CU_ERROR_CHECK(cuStreamSynchronize(su));
+  CU_ERROR_CHECK(cuStreamSynchronize(sl));
   if (ga != NULL) CU_ERROR_CHECK(cuStreamSynchronize(ga->s_copy));
   *info = *h->hinfo;
   for (int i = 0; i < h->prof_n; i++) {

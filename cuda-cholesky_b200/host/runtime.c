@@ -122,9 +122,11 @@ CUresult cuLAPACKCreate(CULAPACKhandle *handle) {
   e = cuCtxGetStreamPriorityRange(&lo, &hi); /* hi = numerically smallest = greatest priority */
   if (e == CUDA_SUCCESS) e = cuStreamCreateWithPriority(&h->s_panel, CU_STREAM_DEFAULT, hi);
   if (e == CUDA_SUCCESS) e = cuStreamCreateWithPriority(&h->s_update, CU_STREAM_DEFAULT, lo);
+  if (e == CUDA_SUCCESS) e = cuStreamCreateWithPriority(&h->s_look, CU_STREAM_DEFAULT, hi);
   for (int i = 0; i < CHOL_EVENT_RING && e == CUDA_SUCCESS; i++) {
     e = cuEventCreate(&h->ev_panel[i], CU_EVENT_DISABLE_TIMING);
     if (e == CUDA_SUCCESS) e = cuEventCreate(&h->ev_rest[i], CU_EVENT_DISABLE_TIMING);
+    if (e == CUDA_SUCCESS) e = cuEventCreate(&h->ev_look[i], CU_EVENT_DISABLE_TIMING);
   }
   if (e == CUDA_SUCCESS) e = cuMemAlloc(&h->dinfo, sizeof(long));
   if (e == CUDA_SUCCESS) e = cuMemAllocHost((void **)&h->hinfo, sizeof(long));
@@ -145,9 +147,11 @@ CUresult cuLAPACKDestroy(CULAPACKhandle h) {
     CU_ERROR_CHECK(cuCtxPushCurrent(h->context));
     if (h->s_panel) cuStreamDestroy(h->s_panel);
     if (h->s_update) cuStreamDestroy(h->s_update);
+    if (h->s_look) cuStreamDestroy(h->s_look);
     for (int i = 0; i < CHOL_EVENT_RING; i++) {
       if (h->ev_panel[i]) cuEventDestroy(h->ev_panel[i]);
       if (h->ev_rest[i]) cuEventDestroy(h->ev_rest[i]);
+      if (h->ev_look[i]) cuEventDestroy(h->ev_look[i]);
     }
     if (h->ws) cuMemFree(h->ws);
     if (h->dinfo) cuMemFree(h->dinfo);

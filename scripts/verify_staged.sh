@@ -36,7 +36,7 @@ if has tests; then
 fi
 
 if has chain; then
-  say "== panel chain: diagonal-block kernel V2 (CHOL_POTF2_V2), small-tile GEMM (CHOL_SMALL_GEMM), blocked panel solve (CHOL_PANEL_BLOCKED) =="
+  say "== panel chain: diagonal-block kernel V2 (CHOL_POTF2_V2), small-tile GEMM (CHOL_SMALL_GEMM), blocked panel solve (CHOL_PANEL_BLOCKED), split look-ahead (CHOL_LOOKAHEAD_SPLIT) =="
   CHOL_POTF2_V2=1 CHOL_SMALL_GEMM=1 timeout 1200 python -m pytest tests/test_gpu_blas.py tests/test_gpu_lapack.py tests/test_gpu_multigpu.py -m gpu -q -x \
     > $OUT/staged_chain_tests.log 2>&1
   say "parity with both switches on rc=$?"; tail -2 $OUT/staged_chain_tests.log | tee -a $SUM
@@ -45,10 +45,12 @@ if has chain; then
   done
   CHOL_PANEL_BLOCKED=1 timeout 900 python -m pytest tests/test_gpu_lapack.py tests/test_gpu_multigpu.py -m gpu -q -x > $OUT/staged_blocked_tests.log 2>&1
   say "parity with the blocked panel solve (CHOL_PANEL_BLOCKED) rc=$?"; tail -2 $OUT/staged_blocked_tests.log | tee -a $SUM
-  for CFG in "0 0 0" "1 0 0" "0 1 0" "0 0 1" "1 1 1"; do
+  CHOL_LOOKAHEAD_SPLIT=1 timeout 900 python -m pytest tests/test_gpu_lapack.py tests/test_gpu_multigpu.py -m gpu -q -x > $OUT/staged_split_tests.log 2>&1
+  say "parity with the split look-ahead (CHOL_LOOKAHEAD_SPLIT) rc=$?"; tail -2 $OUT/staged_split_tests.log | tee -a $SUM
+  for CFG in "0 0 0 0" "1 0 0 0" "0 1 0 0" "0 0 1 0" "0 0 0 1" "1 1 1 1"; do
     set -- $CFG
-    CHOL_POTF2_V2=$1 CHOL_SMALL_GEMM=$2 CHOL_PANEL_BLOCKED=$3 timeout 300 python scripts/configs_bench.py cfg1 2>&1 | grep -E "^dpotrf" \
-      | sed "s/^/POTF2_V2=$1 SMALL_GEMM=$2 PANEL_BLOCKED=$3 /" | tee -a $SUM
+    CHOL_POTF2_V2=$1 CHOL_SMALL_GEMM=$2 CHOL_PANEL_BLOCKED=$3 CHOL_LOOKAHEAD_SPLIT=$4 timeout 300 python scripts/configs_bench.py cfg1 2>&1 \
+      | grep -E "^dpotrf" | sed "s/^/POTF2_V2=$1 SMALL_GEMM=$2 PANEL_BLOCKED=$3 LOOKAHEAD_SPLIT=$4 /" | tee -a $SUM
   done
 fi
 

@@ -52,10 +52,16 @@ def mock_runs(tmp_path_factory):
                OMP_NUM_THREADS="2")  # four groups run side by side: keep the oracle's OpenMP teams small
 
     def run(group):
-        # "<group>+blocked": the same checks with the blocked panel solve switched on (read once per process)
-        # "<group>+jitter": every mock stream stalls at random before its operations (ordering races)
-        name, _, variant = group.partition("+")
-        e = dict(env, CHOL_PANEL_BLOCKED="1") if variant == "blocked" else (dict(env, MOCK_CUDA_JITTER="1") if variant == "jitter" else env)
+        # "<group>+<variant>+...": blocked = blocked panel solve, split = split look-ahead (library switches, read once
+        # per process), jitter = every mock stream stalls at random before its operations (ordering races)
+        name, *variants = group.split("+")
+        e = dict(env)
+        if "blocked" in variants:
+            e["CHOL_PANEL_BLOCKED"] = "1"
+        if "split" in variants:
+            e["CHOL_LOOKAHEAD_SPLIT"] = "1"
+        if "jitter" in variants:
+            e["MOCK_CUDA_JITTER"] = "1"
         p = subprocess.run([sys.executable, os.path.join(MOCK, "run_host_driver_checks.py"), lib, name], stdout=subprocess.PIPE,
                            stderr=subprocess.STDOUT, env=e, timeout=1500)
         return p.returncode, p.stdout.decode()
@@ -68,7 +74,8 @@ def mock_runs(tmp_path_factory):
                            timeout=600)
         return p.returncode, p.stdout.decode()
 
-    groups = ("lapack", "blas", "multi1", "multi3", "lapack+blocked", "multi3+blocked", "lapack+jitter", "multi3+jitter")
+    groups = ("lapack", "blas", "multi1", "multi3", "lapack+blocked", "multi3+blocked", "lapack+jitter", "multi3+jitter",
+              "lapack+split+jitter", "multi3+split+blocked+jitter")
     with ThreadPoolExecutor(max_workers=len(groups)) as ex:
         res = dict(zip(groups, ex.map(run, groups)))
     cdir = os.path.join(ROOT, "tests", "c")
@@ -80,7 +87,8 @@ def mock_runs(tmp_path_factory):
 
 @pytest.mark.parametrize("group,min_checks", [("lapack", 700), ("blas", 90), ("multi1", 800), ("multi3", 800),
                                               ("lapack+blocked", 700), ("multi3+blocked", 800),
-                                              ("lapack+jitter", 700), ("multi3+jitter", 800)])
+                                              ("lapack+jitter", 700), ("multi3+jitter", 800),
+                                              ("lapack+split+jitter", 700), ("multi3+split+blocked+jitter", 800)])
 def test_host_drivers_on_mock_backend(mock_runs, group, min_checks):
     rc, out = mock_runs[group]
     assert rc == 0 and "MOCK PASSED" in out, out[-3000:]
