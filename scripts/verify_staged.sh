@@ -3,7 +3,7 @@
 # (tests marked `staged`, library paths behind environment switches - DESIGN.md §4.1) and A/B it.
 #   gpurun --timeout 3000 -- 'bash scripts/verify_staged.sh'            # everything, ~45 min
 #   gpurun --timeout 1200 -- 'STAGES="tests chain" bash scripts/verify_staged.sh'
-# Stages, in order of importance: tests chain engine e2e fp32 inverse memcheck.  Every command runs under its
+# Stages, in order of importance: tests chain engine e2e fp32 inverse memcheck (and `scale`, only on request, under gpurun --gpus N).  Every command runs under its
 # own `timeout`; results land in gpurun_out/staged_* with a one-page gpurun_out/staged_summary.txt.
 set -u
 cd "$(dirname "$0")/.."
@@ -104,5 +104,16 @@ if has memcheck; then
   else
     say "slice failed without the sanitizer; memcheck skipped"
   fi
+fi
+if has scale; then  # not in the default list: run under `gpurun --gpus N`, e.g. STAGES=scale bash scripts/verify_staged.sh
+  NG=$(python -c "import torch; print(torch.cuda.device_count())")
+  say "== multi-GPU ($NG GPUs): default vs the shorter panel chain (POTF2_V2 + SMALL_GEMM + PANEL_BLOCKED + LOOKAHEAD_SPLIT) =="
+  for MODE in default chain; do
+    if [ $MODE = chain ]; then export CHOL_POTF2_V2=1 CHOL_SMALL_GEMM=1 CHOL_PANEL_BLOCKED=1 CHOL_LOOKAHEAD_SPLIT=1; fi
+    timeout 900 python bench.py --gpus $NG --order 65536 --steps 2 --warmup 2 --e2e-steps 1 --skip-cpu-baseline \
+      > $OUT/staged_scale_${NG}gpu_$MODE.json 2> $OUT/staged_scale_${NG}gpu_$MODE.err
+    bench_line $OUT/staged_scale_${NG}gpu_$MODE.json 65536 "$NG GPUs, $MODE"
+  done
+  unset CHOL_POTF2_V2 CHOL_SMALL_GEMM CHOL_PANEL_BLOCKED CHOL_LOOKAHEAD_SPLIT
 fi
 say "== done =="
