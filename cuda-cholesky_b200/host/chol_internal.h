@@ -129,6 +129,7 @@ bool chol_panel_blocked(void);
 CUresult chol_panel_factor_solve_lower(int prec, size_t jb, size_t rest, CUdeviceptr Ajj, CUdeviceptr P, size_t lda, CUdeviceptr W,
                                        size_t ldw, long *dinfo, long base, const chol_ws *w, CUstream st, CUevent before_solve);
 bool chol_lookahead_split(void);
+bool chol_trtri_lookahead(void);
 /* ... upper: the jb x rest block row P right of the diagonal block, W = P^H * inv(U11) (rest x jb) */
 CUresult chol_panel_factor_solve_upper(int prec, size_t jb, size_t rest, CUdeviceptr Ajj, CUdeviceptr P, size_t lda, CUdeviceptr W,
                                        size_t ldw, long *dinfo, long base, const chol_ws *w, CUstream st, CUevent before_solve);

@@ -216,6 +216,15 @@ bool chol_lookahead_split(void) {
   return on != 0;
 }
 
+bool chol_trtri_lookahead(void) {
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("CHOL_TRTRI_LOOKAHEAD");
+    on = (e != NULL && atoi(e) != 0) ? 1 : 0;
+  }
+  return on != 0;
+}
+
 /* factor the jb x jb lower diagonal block at Ajj and solve the rest x jb panel P below it into W */
 /* before_solve (may be NULL): an event the stream must have seen before the panel P is read - the lower part of
  * a split look-ahead runs on another stream while the diagonal block is factored here */
@@ -380,31 +389,55 @@ static CUresult trtri_body(CULAPACKhandle h, int prec, int uplo, int diag, size_
   CUstream st = h->s_update;
   const int unit = (diag == 'U');
   const int strict = (uplo == 'L') ? 'l' : 'u';
-  CU_ERROR_CHECK(cuMemsetD8Async(h->dinfo, 0, sizeof(long), st));
   const size_t nblk = (n + nb - 1) / nb;
+  /* CHOL_TRTRI_LOOKAHEAD=1 (written after the round-1 GPU budget was spent, off until measured): the small inverse
+   * of a diagonal block depends on nothing but that block, so the NEXT block's inverse runs on the panel stream
+   * while this block's two large GEMMs run on the update stream (two X buffers; the info-writing kernels stay
+   * on one stream, in sweep order, so `info` is unchanged). */
+  const bool la = chol_trtri_lookahead() && nblk > 1;
+  CUstream sp = la ? h->s_panel : st;
+  const CUdeviceptr Xb[2] = {w.Xd, la ? w.W[1] : w.Xd};
+  CU_ERROR_CHECK(cuMemsetD8Async(h->dinfo, 0, sizeof(long), sp));
   for (size_t b = 0; b < nblk; b++) {
     const size_t blk = (uplo == 'L') ? nblk - 1 - b : b; /* reference sweep: lapack/dtrtri.c:119,:137 */
     const size_t j = blk * nb, jb = chol_min(nb, n - j);
     const CUdeviceptr Ajj = chol_at(A, lda, j, j, es);
-    CU_ERROR_CHECK(chol_trtri_small(prec, uplo, diag, jb, Ajj, lda, w.Xd, nb, dinfo, (long)j, &w, st));
+    const CUdeviceptr Xd = Xb[b & 1];
+    if (!la) {
+      CU_ERROR_CHECK(chol_trtri_small(prec, uplo, diag, jb, Ajj, lda, Xd, nb, dinfo, (long)j, &w, st));
+    } else {
+      if (b == 0) {
+        CU_ERROR_CHECK(chol_trtri_small(prec, uplo, diag, jb, Ajj, lda, Xd, nb, dinfo, (long)j, &w, sp));
+        CU_ERROR_CHECK(cuEventRecord(h->ev_panel[0], sp));
+      }
+      if (b + 1 < nblk) { /* the next block's small inverse, into the other X buffer (last used by block b-1) */
+        const size_t blk1 = (uplo == 'L') ? nblk - 2 - b : b + 1, j1 = blk1 * nb, jb1 = chol_min(nb, n - j1);
+        if (b >= 1) CU_ERROR_CHECK(cuStreamWaitEvent(sp, h->ev_rest[(b - 1) % CHOL_EVENT_RING], 0));
+        CU_ERROR_CHECK(chol_trtri_small(prec, uplo, diag, jb1, chol_at(A, lda, j1, j1, es), lda, Xb[(b + 1) & 1], nb, dinfo, (long)j1, &w,
+                                        sp));
+        CU_ERROR_CHECK(cuEventRecord(h->ev_panel[(b + 1) % CHOL_EVENT_RING], sp));
+      }
+      CU_ERROR_CHECK(cuStreamWaitEvent(st, h->ev_panel[b % CHOL_EVENT_RING], 0));
+    }
     if (uplo == 'L') {
       const size_t rest = n - j - jb;
       if (rest) { /* A21 = -inv(A22) * (A21 * inv(A11)) ; inv(A22) is already in place */
         const CUdeviceptr A21 = chol_at(A, lda, j + jb, j, es), A22 = chol_at(A, lda, j + jb, j + jb, es);
-        CU_ERROR_CHECK(chol_gemm(prec, 'N', 'N', rest, jb, jb, ONE, A21, lda, w.Xd, nb, ZERO, 0, 0, w.W[0], w.ldw, st));
+        CU_ERROR_CHECK(chol_gemm(prec, 'N', 'N', rest, jb, jb, ONE, A21, lda, Xd, nb, ZERO, 0, 0, w.W[0], w.ldw, st));
         CU_ERROR_CHECK(chol_gemm_ex(prec, 'N', 'N', 'L', unit, 0, 0, 0, 0, rest, jb, rest, MONE, A22, lda, w.W[0], w.ldw,
                                     ZERO, 0, 0, A21, lda, st));
       }
     } else if (j) { /* A12 = -inv(A11) * (A12 * inv(A22)) */
       const CUdeviceptr A12 = chol_at(A, lda, 0, j, es);
-      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'N', j, jb, jb, ONE, A12, lda, w.Xd, nb, ZERO, 0, 0, w.W[0], w.ldw, st));
+      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'N', j, jb, jb, ONE, A12, lda, Xd, nb, ZERO, 0, 0, w.W[0], w.ldw, st));
       CU_ERROR_CHECK(chol_gemm_ex(prec, 'N', 'N', 'U', unit, 0, 0, 0, 0, j, jb, j, MONE, A, lda, w.W[0], w.ldw, ZERO, 0, 0,
                                   A12, lda, st));
     }
     /* a unit-diagonal inverse leaves the caller's diagonal untouched (lapack/dtrtri.c:56-57) */
-    RT_CHECK(chol_copy_launch(prec, 'N', unit ? strict : uplo, jb, jb, (const void *)w.Xd, nb, (void *)Ajj, lda, (void *)st));
+    RT_CHECK(chol_copy_launch(prec, 'N', unit ? strict : uplo, jb, jb, (const void *)Xd, nb, (void *)Ajj, lda, (void *)st));
+    if (la) CU_ERROR_CHECK(cuEventRecord(h->ev_rest[b % CHOL_EVENT_RING], st));
   }
-  CU_ERROR_CHECK(finish_info(h, st, info));
+  CU_ERROR_CHECK(finish_info(h, sp, info));
   return CUDA_SUCCESS;
 }
 

@@ -54,6 +54,15 @@ if has chain; then
   done
 fi
 
+if has chain; then
+  say "== TRTRI look-ahead (CHOL_TRTRI_LOOKAHEAD): parity, then dpotrf + dpotri N=32768 =="
+  CHOL_TRTRI_LOOKAHEAD=1 timeout 600 python -m pytest tests/test_gpu_lapack.py -m gpu -q -x -k "trtri or potri" > $OUT/staged_trtri_la_tests.log 2>&1
+  say "parity rc=$?"; tail -2 $OUT/staged_trtri_la_tests.log | tee -a $SUM
+  for LA in 0 1; do
+    CHOL_TRTRI_LOOKAHEAD=$LA timeout 400 python scripts/configs_bench.py cfg3 2>&1 | grep -iE "potri|trtri" | sed "s/^/TRTRI_LOOKAHEAD=$LA /" | tee -a $SUM
+  done
+fi
+
 if has engine; then
   say "== tile engine: staggered kernel with the C tile staged through the ring (CHOL_GEMM_PP=2) =="
   CHOL_GEMM_PP=2 timeout 1200 python -m pytest tests/test_gpu_blas.py tests/test_gpu_lapack.py tests/test_gpu_multigpu.py -m gpu -q -x \

@@ -52,7 +52,7 @@ def mock_runs(tmp_path_factory):
                OMP_NUM_THREADS="2")  # four groups run side by side: keep the oracle's OpenMP teams small
 
     def run(group):
-        # "<group>+<variant>+...": blocked = blocked panel solve, split = split look-ahead (library switches, read once
+        # "<group>+<variant>+...": blocked = blocked panel solve, split = split POTRF look-ahead + TRTRI look-ahead (library switches, read once
         # per process), jitter = every mock stream stalls at random before its operations (ordering races)
         name, *variants = group.split("+")
         e = dict(env)
@@ -60,6 +60,7 @@ def mock_runs(tmp_path_factory):
             e["CHOL_PANEL_BLOCKED"] = "1"
         if "split" in variants:
             e["CHOL_LOOKAHEAD_SPLIT"] = "1"
+            e["CHOL_TRTRI_LOOKAHEAD"] = "1"
         if "jitter" in variants:
             e["MOCK_CUDA_JITTER"] = "1"
         p = subprocess.run([sys.executable, os.path.join(MOCK, "run_host_driver_checks.py"), lib, name], stdout=subprocess.PIPE,
