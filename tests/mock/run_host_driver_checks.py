@@ -317,6 +317,22 @@ def multi_device(P):
                     getattr(mg, name)(p, side, uplo, trans, "N", m, n, a1, ptr(T0), na, ptr(got), m)
                     close(got, want, p, na, "cuMultiGPU %s %s%s%s" % (name, side, uplo, trans))
 
+    # the one-process-per-GPU entry points with a single rank (what bench.py times at N = 1): the packed
+    # layout is then the plain column-major matrix, resident in "device" memory
+    if P == 1:
+        for p in "dz":
+            for n, nb in ((700, 0), (1000, 128)):
+                d = chol.Dist(0, 1, nb=nb)
+                A0 = H.spd_matrix(p, n, k=48)
+                want = A0.copy(order="F")
+                ORA.potrf(p, "L", want)
+                A = A0.copy(order="F")
+                ok(d.potrf(p, n, ptr(A), ld(A)) == 0, "cholDist info")
+                close(np.tril(A), np.tril(want), p, n, "cholDist%spotrf n=%d nb=%d" % (p, n, nb))
+                other_untouched(A, A0, "L", "cholDist potrf")
+                ok(d.block_size(p, n) == (nb or (128 if p == "z" else 256)), "cholDist block size")
+                d.close()
+
     # an allocation failure on the devices fails the call cleanly (no rank is left in a broadcast)
     os.environ["MOCK_CUDA_MEM_LIMIT"] = str(1 << 20)
     A = H.spd_matrix("d", 1200, k=16)
