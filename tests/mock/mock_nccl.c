@@ -1,6 +1,7 @@
 /*
  * mock_nccl.c — TEST INFRASTRUCTURE ONLY: a libnccl.so.2 stand-in for the single-process,
- * one-thread-per-GPU form (ncclCommInitAll) used by the cuMultiGPU* drivers, so that the
+ * one-thread-per-GPU form (ncclCommInitAll) used by the cuMultiGPU* drivers and for the one-rank-per-GPU
+ * form (ncclCommInitRank; the ranks are threads of the test process), so that the
  * distributed factorisation's control flow (ownership, panel broadcast order, look-ahead, info
  * combination) can run on a machine without GPUs (tests/test_host_drivers_mock.py).  A broadcast is queued on
  * the caller's (mock) stream like a kernel; when it runs it is a rendezvous of the group's ranks: the
@@ -16,8 +17,14 @@ struct group { int n; pthread_barrier_t bar; const void *src; int refs; };
 struct comm { struct group *g; int rank; };
 typedef struct comm *ncclComm_t;
 
+static int next_id = 1;
 const char *ncclGetErrorString(int e) { return e == 0 ? "no error" : "mock NCCL error"; }
-int ncclGetUniqueId(ncclUniqueId *id) { memset(id, 0, sizeof *id); return 0; }
+int ncclGetUniqueId(ncclUniqueId *id) {
+  memset(id, 0, sizeof *id);
+  const int k = __sync_fetch_and_add(&next_id, 1);
+  memcpy(id->internal, &k, sizeof k);
+  return 0;
+}
 int ncclGroupStart(void) { return 0; }
 int ncclGroupEnd(void) { return 0; }
 
@@ -35,8 +42,45 @@ int ncclCommInitAll(ncclComm_t *comms, int n, const int *devs) {
   }
   return 0;
 }
-/* one process per GPU is not something a single test process can stand in for */
-int ncclCommInitRank(ncclComm_t *c, int n, ncclUniqueId id, int rank) { (void)c; (void)n; (void)id; (void)rank; return 3; }
+/* ncclCommInitRank: in the tests the "processes" of a one-rank-per-GPU job are threads of the test process; the
+ * n callers that present the same unique id meet here and share one group */
+static pthread_mutex_t reg_mu = PTHREAD_MUTEX_INITIALIZER;
+static pthread_cond_t reg_cv = PTHREAD_COND_INITIALIZER;
+static struct { int key; struct group *g; int joined; } pending[16];
+
+int ncclCommInitRank(ncclComm_t *c, int n, ncclUniqueId id, int rank) {
+  int key;
+  memcpy(&key, id.internal, sizeof key);
+  if (key == 0 || n < 1 || rank < 0 || rank >= n) return 4;
+  pthread_mutex_lock(&reg_mu);
+  int slot = -1;
+  for (int i = 0; i < 16; i++)
+    if (pending[i].key == key) slot = i;
+  if (slot < 0) {
+    for (int i = 0; i < 16 && slot < 0; i++)
+      if (pending[i].key == 0) slot = i;
+    if (slot < 0) { pthread_mutex_unlock(&reg_mu); return 1; }
+    struct group *g = calloc(1, sizeof *g);
+    g->n = n;
+    g->refs = n;
+    pthread_barrier_init(&g->bar, NULL, (unsigned)n);
+    pending[slot].key = key;
+    pending[slot].g = g;
+    pending[slot].joined = 0;
+  }
+  struct group *g = pending[slot].g;
+  if (++pending[slot].joined == n) {
+    pending[slot].key = 0; /* complete: the slot can be reused */
+    pthread_cond_broadcast(&reg_cv);
+  } else {
+    while (pending[slot].g == g && pending[slot].key == key) pthread_cond_wait(&reg_cv, &reg_mu);
+  }
+  pthread_mutex_unlock(&reg_mu);
+  *c = calloc(1, sizeof **c);
+  (*c)->g = g;
+  (*c)->rank = rank;
+  return 0;
+}
 int ncclCommInitRankConfig(ncclComm_t *c, int n, ncclUniqueId id, int rank, void *cfg) { (void)cfg; return ncclCommInitRank(c, n, id, rank); }
 
 int ncclCommDestroy(ncclComm_t c) {

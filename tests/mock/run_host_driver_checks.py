@@ -348,6 +348,45 @@ def multi_device(P):
     ok(mock.mock_cuda_live_allocs() == allocs0, "multi-GPU device allocations leaked: %d" % (mock.mock_cuda_live_allocs() - allocs0))
 
 
+def dist_ranks(P):
+    """cholDist* with P ranks (threads of this process standing in for torchrun's processes): every rank packs its
+    block-cyclic share the way bench.py does, all factor together, the pieces are put back and compared."""
+    import threading
+    sys.path.insert(0, ROOT)
+    from bench import owned_columns  # the launcher-side layout helper that bench.py itself uses
+    for p in "dz":
+        for n, nb in ((900, 128), (1300, 0), (700, 256)):
+            uid = chol.dist_unique_id()
+            A0 = H.spd_matrix(p, n, k=48)
+            want = A0.copy(order="F")
+            ORA.potrf(p, "L", want)
+            got = A0.copy(order="F")
+            infos, errs = [None] * P, []
+
+            def rank_main(r):
+                try:
+                    d = chol.Dist(r, P, uid, nb=nb)
+                    bs = d.block_size(p, n)
+                    cols = owned_columns(n, bs, r, P)
+                    loc = np.asfortranarray(A0[:, cols]) if len(cols) else H.fmat(n, 1, PREC[p]["np"])
+                    infos[r] = d.potrf(p, n, ptr(loc), ld(loc))
+                    if len(cols):
+                        got[:, cols] = loc
+                    d.close()
+                except Exception as e:  # noqa: BLE001 - reported below
+                    errs.append(repr(e))
+
+            ts = [threading.Thread(target=rank_main, args=(r,)) for r in range(P)]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join(600)
+            ok(not errs and all(not t.is_alive() for t in ts), "cholDist ranks: %s" % errs)
+            ok(all(i == 0 for i in infos), "cholDist infos %s" % infos)
+            close(np.tril(got), np.tril(want), p, n, "cholDist%spotrf P=%d n=%d nb=%d" % (p, P, n, nb))
+            other_untouched(got, A0, "L", "cholDist P=%d" % P)
+
+
 if __name__ == "__main__":
     which = sys.argv[2] if len(sys.argv) > 2 else "all"
     if which in ("all", "lapack"):
@@ -358,5 +397,7 @@ if __name__ == "__main__":
         multi_device(1)
     if which in ("all", "multi3"):
         multi_device(3)
+    if which in ("all", "dist3"):
+        dist_ranks(3)
     print("%d checks" % checks)
     print("MOCK PASSED")

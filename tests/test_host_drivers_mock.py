@@ -12,8 +12,10 @@ compares every driver with the CPU oracle, on 1 and on 3 mock devices:
   argument errors, context push/pop balance, allocation balance, the CUmultiGPU runtime, the
   distributed POTRF (ownership, broadcast order, block-cyclic update, page-locked overlapped
   download and - CHOL_MGPU_H2D_OVERLAP - upload paths), the slab-distributed inverse
-  (CHOL_MGPU_INVERSE=slab), the host-pointer BLAS, and a device allocation failure that must fail
-  the call on every rank instead of leaving some of them in a broadcast.
+  (CHOL_MGPU_INVERSE=slab), the host-pointer BLAS, a device allocation failure that must fail
+  the call on every rank instead of leaving some of them in a broadcast, and the one-rank-per-GPU
+  cholDist* form with three ranks (threads standing in for torchrun's processes) on matrices packed
+  with bench.py's own layout helper.
 
 Plain-loop kernels say nothing about the CUDA kernels: that is the job of
 tests/test_kernel_emulation.py and of the GPU parity tests."""
@@ -76,7 +78,7 @@ def mock_runs(tmp_path_factory):
         return p.returncode, p.stdout.decode()
 
     groups = ("lapack", "blas", "multi1", "multi3", "lapack+blocked", "multi3+blocked", "lapack+jitter", "multi3+jitter",
-              "lapack+split+jitter", "multi3+split+blocked+jitter")
+              "lapack+split+jitter", "multi3+split+blocked+jitter", "dist3+jitter")
     with ThreadPoolExecutor(max_workers=len(groups)) as ex:
         res = dict(zip(groups, ex.map(run, groups)))
     cdir = os.path.join(ROOT, "tests", "c")
@@ -89,7 +91,8 @@ def mock_runs(tmp_path_factory):
 @pytest.mark.parametrize("group,min_checks", [("lapack", 700), ("blas", 90), ("multi1", 800), ("multi3", 800),
                                               ("lapack+blocked", 700), ("multi3+blocked", 800),
                                               ("lapack+jitter", 700), ("multi3+jitter", 800),
-                                              ("lapack+split+jitter", 700), ("multi3+split+blocked+jitter", 800)])
+                                              ("lapack+split+jitter", 700), ("multi3+split+blocked+jitter", 800),
+                                              ("dist3+jitter", 20)])
 def test_host_drivers_on_mock_backend(mock_runs, group, min_checks):
     rc, out = mock_runs[group]
     assert rc == 0 and "MOCK PASSED" in out, out[-3000:]
