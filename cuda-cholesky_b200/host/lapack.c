@@ -29,6 +29,19 @@ static const double ONE[2] = {1.0, 0.0};
 static const double ZERO[2] = {0.0, 0.0};
 static const double MONE[2] = {-1.0, 0.0};
 
+/* an environment switch, read once per process; the cached value is published with atomics because the
+ * multi-GPU worker threads ask concurrently (every reader would compute the same value anyway) */
+static bool chol_env_switch(int *state, const char *name) {
+  int v = __atomic_load_n(state, __ATOMIC_RELAXED);
+  if (v < 0) {
+    const char *e = getenv(name);
+    v = (e != NULL && atoi(e) != 0) ? 1 : 0;
+    __atomic_store_n(state, v, __ATOMIC_RELAXED);
+  }
+  return v != 0;
+}
+static int chol_panel_blocked_state = -1, chol_lookahead_split_state = -1, chol_trtri_lookahead_state = -1;
+
 /* outer block size: k of the trailing update.  Larger k amortises the C-tile epilogue (measured on
  * B200, d: 512 beats 256 from N ~ 32768 up), smaller k shortens the serial panel chain. */
 size_t chol_default_nb(int prec, size_t n) {
@@ -193,37 +206,16 @@ CUresult chol_diag_factor_inverse_ex(int prec, int uplo, size_t jb, CUdeviceptr 
  * diagonal sub-blocks and solve the panel by block forward substitution with full-height GEMMs:
  *     W_c = (P_c - W[:, 0:c] * L[c, 0:c]^H) * inv(L_cc)^H        c = 0 .. nblk-1
  * 10/16 of the flops at nblk = 4, no small GEMMs on the chain. */
-bool chol_panel_blocked(void) {
-  static int on = -1;
-  if (on < 0) {
-    const char *e = getenv("CHOL_PANEL_BLOCKED");
-    on = (e != NULL && atoi(e) != 0) ? 1 : 0;
-  }
-  return on != 0;
-}
+bool chol_panel_blocked(void) { return chol_env_switch(&chol_panel_blocked_state, "CHOL_PANEL_BLOCKED"); }
 
 /* CHOL_LOOKAHEAD_SPLIT=1 (written after the round-1 GPU budget was spent, off until measured): the look-ahead
  * update of the next block column is split - its jb2 x jb2 diagonal block stays on the panel stream, so the next
  * diagonal block can be factored at once, while the rows below it (the bulk of the column) are updated on a
  * third stream at the same time; the next panel solve waits for that part.  Takes the look-ahead GEMM off the
  * serial panel chain (stream dependencies mutation-tested on the asynchronous mock back end). */
-bool chol_lookahead_split(void) {
-  static int on = -1;
-  if (on < 0) {
-    const char *e = getenv("CHOL_LOOKAHEAD_SPLIT");
-    on = (e != NULL && atoi(e) != 0) ? 1 : 0;
-  }
-  return on != 0;
-}
+bool chol_lookahead_split(void) { return chol_env_switch(&chol_lookahead_split_state, "CHOL_LOOKAHEAD_SPLIT"); }
 
-bool chol_trtri_lookahead(void) {
-  static int on = -1;
-  if (on < 0) {
-    const char *e = getenv("CHOL_TRTRI_LOOKAHEAD");
-    on = (e != NULL && atoi(e) != 0) ? 1 : 0;
-  }
-  return on != 0;
-}
+bool chol_trtri_lookahead(void) { return chol_env_switch(&chol_trtri_lookahead_state, "CHOL_TRTRI_LOOKAHEAD"); }
 
 /* factor the jb x jb lower diagonal block at Ajj and solve the rest x jb panel P below it into W */
 /* before_solve (may be NULL): an event the stream must have seen before the panel P is read - the lower part of
