@@ -376,7 +376,9 @@ def run_ours(args):
             "config": {"workload": "dpotrf lower N=%d, FP64 DMMA trailing update (BASELINE configs[1]/[4] family at the metric's N)" % N,
                        "N": N, "uplo": "L", "nb": nb, "layout": "1-D block-cyclic block columns over %d rank(s)" % P,
                        "parallelism": "bc%d" % P, "l2": "inputs (%.1f GB per rank) are larger than L2" % (nloc * N * 8 / 1e9),
-                       "restore_in_timed_region": True, "info": info, "probe_resid": probe_resid},
+                       "restore_in_timed_region": True, "info": info, "probe_resid": probe_resid,
+                       # library switches in effect (empty = the defaults the committed numbers were measured with)
+                       "switches": {k: v for k, v in sorted(os.environ.items()) if k.startswith("CHOL_") and k != "CHOL_BENCH_HIST"}},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_gflops, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "s_per_step": e2e_s, "steps": e2e_steps, "api": e2e_api, "info": info2},
