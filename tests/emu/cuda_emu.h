@@ -19,6 +19,7 @@
 #include <pthread.h>
 
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -80,7 +81,18 @@ thread_local uint3 threadIdx, blockIdx;
 thread_local dim3 blockDim, gridDim;
 #endif
 
-inline void __syncthreads() { emu::current()->bar.wait(); }
+// EMU_JITTER=1: every thread stalls for a random short while now and then (after barriers, around waits), so that
+// the relative progress of warps and lanes varies from run to run far more than the OS scheduler alone would do
+namespace emu {
+inline bool jitter_on() { static const bool on = [] { const char *e = std::getenv("EMU_JITTER"); return e && std::atoi(e); }(); return on; }
+inline void jitter() {
+  if (!jitter_on()) return;
+  thread_local unsigned rng = 2463534242u ^ (unsigned)(uintptr_t)&rng;
+  rng ^= rng << 13; rng ^= rng >> 17; rng ^= rng << 5;
+  if ((rng & 7u) == 0) std::this_thread::sleep_for(std::chrono::microseconds((rng >> 8) % 300));
+}
+}  // namespace emu
+inline void __syncthreads() { emu::current()->bar.wait(); emu::jitter(); }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::current()->warps[threadIdx.x >> 5].bar.wait(); }
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 

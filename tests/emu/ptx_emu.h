@@ -62,12 +62,13 @@ inline void mbar_init(uint64_t *bar, uint32_t count) {
   emu_mbar::table()[bar] = s;
 }
 inline void mbar_fence_init() {}
-inline void mbar_arrive(uint64_t *bar) { emu_mbar::arrive(bar, 1, 0); }
+inline void mbar_arrive(uint64_t *bar) { ::emu::jitter(); emu_mbar::arrive(bar, 1, 0); }
 inline void mbar_arrive_n(uint64_t *bar, uint32_t n) { emu_mbar::arrive(bar, n, 0); }
 inline void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) { emu_mbar::arrive(bar, 1, bytes); }
 // returns once the phase with this parity has completed (phase k has parity k & 1; a waiter is never
 // two phases behind in a correct protocol - the 1-bit parity cannot tell, neither here nor on the GPU)
 inline void mbar_wait(uint64_t *bar, uint32_t parity) {
+  ::emu::jitter();
   std::unique_lock<std::mutex> l(emu_mbar::mu());
   emu_mbar::State &s = emu_mbar::table()[bar];
   emu_mbar::waiting()[threadIdx.x & 1023] = emu_mbar::Waiting{bar, parity};
