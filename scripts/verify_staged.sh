@@ -69,7 +69,7 @@ if has engine; then
     > $OUT/staged_ppc_tests.log 2>&1
   say "parity with CHOL_GEMM_PP=2 rc=$?"; tail -2 $OUT/staged_ppc_tests.log | tee -a $SUM
   for PP in 0 1 2; do
-    CHOL_GEMM_PP=$PP timeout 400 python bench.py --order 65536 --steps 2 --warmup 2 --e2e-steps 1 --skip-cpu-baseline \
+    CHOL_GEMM_PP=$PP timeout 400 python bench.py --order 65536 --steps 2 --warmup 3 --e2e-steps 1 --skip-cpu-baseline \
       > $OUT/staged_pp${PP}_n65536.json 2> $OUT/staged_pp${PP}_n65536.err
     bench_line $OUT/staged_pp${PP}_n65536.json 65536 "CHOL_GEMM_PP=$PP (dpotrf)"
   done
@@ -119,7 +119,7 @@ if has scale; then  # not in the default list: run under `gpurun --gpus N`, e.g.
   say "== multi-GPU ($NG GPUs): default vs the shorter panel chain (POTF2_V2 + SMALL_GEMM + PANEL_BLOCKED + LOOKAHEAD_SPLIT) =="
   for MODE in default chain; do
     if [ $MODE = chain ]; then export CHOL_POTF2_V2=1 CHOL_SMALL_GEMM=1 CHOL_PANEL_BLOCKED=1 CHOL_LOOKAHEAD_SPLIT=1; fi
-    timeout 900 python bench.py --gpus $NG --order 65536 --steps 2 --warmup 2 --e2e-steps 1 --skip-cpu-baseline \
+    timeout 900 python bench.py --gpus $NG --order 65536 --steps 2 --warmup 3 --e2e-steps 1 --skip-cpu-baseline \
       > $OUT/staged_scale_${NG}gpu_$MODE.json 2> $OUT/staged_scale_${NG}gpu_$MODE.err
     bench_line $OUT/staged_scale_${NG}gpu_$MODE.json 65536 "$NG GPUs, $MODE"
   done
