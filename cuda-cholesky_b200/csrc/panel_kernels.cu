@@ -121,7 +121,9 @@ __global__ void __launch_bounds__(PANEL_THREADS) potf2_kernel(int upper, int n, 
 // EIGHT columns at once (columns warp+16c): the residuals live in registers (lane = row mod 32), the
 // current unknown is broadcast by shuffle, and the eight independent chains hide each other's latency
 // while sharing the loads of L's column k.
-template <typename T, int NQ, int NC>
+// V2 (same switch as the fused kernel's V2, CHOL_POTF2_V2): chains that cannot have started in the current
+// 32-row slice are pruned at compile time, as in potf2_inv_kernel's phase 2.
+template <typename T, int NQ, int NC, bool V2 = false>
 __global__ void __launch_bounds__(PANEL_THREADS) trti2_kernel(int upper, int unit, int n, const T *A, long long lda, T *B,
                                                               long long ldb, int zero_other, long *dinfo, long info_base) {
   CHOL_DYN_SMEM(smem_raw);
@@ -171,6 +173,7 @@ __global__ void __launch_bounds__(PANEL_THREADS) trti2_kernel(int upper, int uni
       }
 #pragma unroll
       for (int c = 0; c < NC; ++c) {  // branch-free: the NC chains interleave
+        if (V2 && 16 * c > 32 * q + 31) continue;  // compile-time: column warp+16c lies below this whole row slice
         const bool active = (k >= warp + 16 * c);
         T rk;
         if constexpr (ScalarOf<T>::cplx) { rk.x = __shfl_sync(0xffffffffu, r[c][q].x, kk); rk.y = __shfl_sync(0xffffffffu, r[c][q].y, kk); }
@@ -546,9 +549,11 @@ static int potf2_inv_t(int uplo, size_t n, void *A, size_t lda, void *X, size_t 
 template <typename T>
 static int trti2_t(int uplo, int diag, size_t n, const void *A, size_t lda, void *B, size_t ldb, int zo, long *dinfo, long base, cudaStream_t st) {
   const size_t sm = panel_smem<T>(n, n);
-  int e = set_smem(trti2_kernel<T, (sizeof(T) == 16 ? 64 : 128) / 32, (sizeof(T) == 16 ? 64 : 128) / 16>, sm); if (e) return e;
   constexpr int NMAX = sizeof(T) == 16 ? 64 : 128;
-  trti2_kernel<T, NMAX / 32, NMAX / 16><<<1, PANEL_THREADS, sm, st>>>(uplo == 'U', diag == 'U', (int)n, (const T *)A, (long long)lda, (T *)B, (long long)ldb, zo, dinfo, base);
+  static const bool v2 = [] { const char *e = getenv("CHOL_POTF2_V2"); return e != nullptr && atoi(e) != 0; }();
+  auto kern = v2 ? trti2_kernel<T, NMAX / 32, NMAX / 16, true> : trti2_kernel<T, NMAX / 32, NMAX / 16, false>;
+  int e = set_smem(kern, sm); if (e) return e;
+  kern<<<1, PANEL_THREADS, sm, st>>>(uplo == 'U', diag == 'U', (int)n, (const T *)A, (long long)lda, (T *)B, (long long)ldb, zo, dinfo, base);
   CHOL_COUNT_LAUNCH();
   return (int)cudaGetLastError();
 }

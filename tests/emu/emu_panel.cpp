@@ -186,6 +186,17 @@ static void case_unfused(const char *name, int n, double tol) {
     emu::launch(dim3(1), dim3(PANEL_THREADS), sm, [&] {
       trti2_kernel<T, NMAX / 32, NMAX / 16>(upper, 0, n, dA, lda, dX, lda, 1, &tinfo, 0);
     });
+    {  // the pruned-chain variant must give the same bits
+      std::vector<H> X2((size_t)lda * n, H(55));
+      T *dX2 = reinterpret_cast<T *>(X2.data());
+      long t2 = 0;
+      emu::launch(dim3(1), dim3(PANEL_THREADS), sm, [&] {
+        trti2_kernel<T, NMAX / 32, NMAX / 16, true>(upper, 0, n, dA, lda, dX2, lda, 1, &t2, 0);
+      });
+      char w2[120];
+      std::snprintf(w2, sizeof w2, "%s trti2 %s n=%d: V2 == measured variant", name, upper ? "upper" : "lower", n);
+      check(t2 == tinfo && X2 == X, w2, 0);
+    }
     double e_inv = 0;
     for (int j = 0; j < n; ++j)
       for (int i = 0; i < n; ++i) {
