@@ -11,8 +11,9 @@
  * routine on resident data and downloads its slab: PCIe traffic is the minimum (each operand
  * element crosses once per GPU that needs it) and no host BLAS is involved (the reference computes
  * diagonal blocks on the CPU, dsyrk.c:287-288, dtrsm.c:267-389).
- * TRTRI/LAUUM/POTRI on host pointers run staged on the first GPU of the CUmultiGPU for now; their
- * block-cyclic distribution is the next row of SURVEY.md §8(f).
+ * TRTRI/LAUUM/POTRI on host pointers run staged on the first GPU of the CUmultiGPU by default; the
+ * slab-distributed form further down is selected with CHOL_MGPU_INVERSE=slab until it
+ * has been timed on hardware.
  */
 #define _GNU_SOURCE
 #include <complex.h>
