@@ -4,7 +4,7 @@
  * What the reference does (lapack/dpotrf.c:172-296, dtrtri.c:326-468, dlauum.c:154-292): a
  * left-looking loop whose diagonal block makes a D2H -> CPU -> H2D round trip every step.
  * What this file does instead (B200-first):
- *   POTRF  right-looking, block size nb (256): per step
+ *   POTRF  right-looking, block size nb (256 ... 1024 by precision and n, chol_default_nb): per step
  *            [panel stream, high priority]  potf2 of the diagonal block in shared memory ->
  *            in-shared-memory inverse of it -> panel solve as ONE tensor-core GEMM into a
  *            contiguous panel buffer W -> write-back -> look-ahead update of the next block column
@@ -17,8 +17,11 @@
  *          small out-of-place inverse + two GEMMs (the "two-TRMM" form of lapack/strtri.c:408-424)
  *   LAUUM  per block row one masked GEMM + one masked HERK over the trapezoid L[i:,i] / U[i,i:]
  *   POTRI  = TRTRI(NonUnit) then LAUUM (lapack/dpotri.c:19-22); input is the Cholesky factor
+ *   POTRS  (addition) two blocked TRSMs on the factor
  *   logdet one single-pass reduction kernel (lapack/dlogdet.c:37-74)
  * info is accumulated on the device (csrc/panel_kernels.cu) and read once at the end.
+ * Variants behind environment switches (blocked panel solve, split look-ahead, TRTRI look-ahead) are
+ * described where they are implemented and in DESIGN.md §4.1; they are off until measured on hardware.
  */
 #include <complex.h>
 #include <stdlib.h>
