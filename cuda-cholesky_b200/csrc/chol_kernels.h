@@ -46,6 +46,19 @@ int chol_gemm_launch(const chol_gemm_desc *d);
 /* 1 if the descriptor would take the TMA (cp.async.bulk) operand path, 0 for the generic loader */
 int chol_gemm_uses_tma(const chol_gemm_desc *d);
 
+/* ---- s-precision tensor-core engine (csrc/gemm_tf32x3.cu): D = alpha * A * B^T + beta * C as a 3xTF32 split
+ * on tcgen05 with FP32 accumulation in TMEM.  Operands are given as TF32 (hi, lo) planes, K-major with
+ * pitch kp = chol_tf32_kpitch(k) floats: plane[r * kp + c] for r < rows, zero for k <= c < kp. ---- */
+size_t chol_tf32_kpitch(size_t k);
+/* split the stored FP32 operand into its planes.  trans == 0: element (r, c) at A[c * lda + r] (rows x k,
+ * column-major); trans != 0: at A[r * lda + c] */
+int chol_tf32_split_launch(int trans, size_t rows, size_t k, const void *A, size_t lda, void *hi, void *lo, size_t kp,
+                           void *stream);
+/* cuplo 0 / 'L' / 'U': all of D, or only that triangle of C read and of D written (C may equal D) */
+int chol_tf32x3_gemm_launch(size_t m, size_t n, size_t k, double alpha, const void *Ahi, const void *Alo, const void *Bhi,
+                            const void *Blo, size_t kp, double beta, const void *C, size_t ldc, void *D, size_t ldd, int cuplo,
+                            void *stream);
+
 /* ---- diagonal-block kernels: one CTA, block staged in shared memory (n <= CHOL_DIAG_MAX) ---- */
 #define CHOL_DIAG_MAX 128
 int chol_diag_max(int prec); /* largest n the one-CTA diagonal kernels accept: 128 (s,d,c), 64 (z) */
@@ -58,8 +71,16 @@ int chol_potf2_launch(int prec, int uplo, size_t n, void *A, size_t lda, long *d
 int chol_potf2_inv_launch(int prec, int uplo, size_t n, void *A, size_t lda, void *X, size_t ldx, long *dinfo,
                           long info_base, void *stream);
 /* inverse of an n x n triangular block, out of place (B may equal A).  Only the uplo triangle of
- * B is written; if zero_other != 0 the opposite triangle of B is set to zero as well.  Zero pivot
- * -> *dinfo = info_base + column (1-based) when *dinfo == 0 (lapack/dtrtri.c:49-52). */
+ * B is written; if (zero_other & 1) the opposite triangle of B is set to zero as well.  Zero pivot
+ * -> *dinfo = info_base + column (1-based) when *dinfo == 0 (lapack/dtrtri.c:49-52); a nonzero
+ * *dinfo on entry makes the launch a no-op (sticky, for the LAPACK drivers).  Two more protocols,
+ * selected by bits of zero_other:
+ *   CHOL_TRTI2_INFO_INT32   dinfo points to a 32-bit int that the kernel zeroes itself on entry and
+ *                           sets on a zero pivot - the reference's device-kernel contract
+ *                           (lapack/dtrtri.cu:23-29), used by cu*trti22;
+ *   CHOL_TRTI2_NO_INFO      dinfo is not touched; a zero pivot yields Inf/NaN as a BLAS TRSM does. */
+#define CHOL_TRTI2_INFO_INT32 2
+#define CHOL_TRTI2_NO_INFO 4
 int chol_trti2_launch(int prec, int uplo, int diag, size_t n, const void *A, size_t lda, void *B, size_t ldb,
                       int zero_other, long *dinfo, long info_base, void *stream);
 /* A := U*U^H (upper) or L^H*L (lower) of an n x n triangular block in place (lapack/dlauum.c:43-69) */

@@ -819,8 +819,10 @@ static int launch_t(const chol_gemm_desc *d) {
     attr_set[dev & 63][CPLX][tma].store(1, std::memory_order_release);
   }
   // tuning switches (environment, read once - thread-safe static initialisation):
-  //   CHOL_GEMM_PP=0/1/2    staggered two-group kernel for grids with >= 4 tiles per SM (default: z only);
-  //                         2 = the variant that stages the C tile through the ring (TMA descriptors only)
+  //   CHOL_GEMM_PP=0/1/2    staggered two-group kernel for grids with >= 4 tiles per SM; 2 = the variant that
+  //                         stages the C tile through the ring (TMA descriptors only).  Default (measured on
+  //                         B200, profiles/r02_staged_ab.txt): z -> 2 (zpotrf N = 32768 28.3 -> 32.0 TFLOP/s,
+  //                         falling back to 1 for generic-loader descriptors), d -> 0 (33.7 vs 32.8 / 33.0)
   //   CHOL_GEMM_PERSIST=n   classic kernel as n persistent CTAs per SM (default 0: one CTA per tile - the
   //                         hardware's dynamic CTA placement beats a static persistent walk)
   //   CHOL_GEMM_PREFETCH=1  enable the L2 prefetch of C tiles (default off: ncu showed +50 % DRAM reads,
@@ -829,7 +831,7 @@ static int launch_t(const chol_gemm_desc *d) {
   //   CHOL_GEMM_STAGEC=0    classic kernel: read C from global memory in the epilogue instead of TMA-staging it
   struct Tuning { int persist, prefetch, pingpong, tps, stagec; };
   static const Tuning tun = [] {
-    Tuning t{0, 0, -1, 8, 1};  // pingpong -1 = auto: z yes (+9 % on zpotrf: short main loops), d no (within +-2 %)
+    Tuning t{0, 0, -1, 8, 1};  // pingpong -1 = auto (see above)
     if (const char *e = getenv("CHOL_GEMM_PERSIST")) t.persist = atoi(e);
     if (const char *e = getenv("CHOL_GEMM_PREFETCH")) t.prefetch = atoi(e);
     if (const char *e = getenv("CHOL_GEMM_PP")) t.pingpong = atoi(e);
@@ -841,7 +843,7 @@ static int launch_t(const chol_gemm_desc *d) {
   a.prefetch_c = prefetch;
   a.stage_c = stagec;
   const int sms = sm_count[dev & 63].load(std::memory_order_relaxed);
-  if (pingpong == 2 && tma && tiles >= 4LL * sms && a.K > 0) {  // staggered + ring-staged C (off until verified on hardware)
+  if ((pingpong == 2 || (pingpong < 0 && CPLX)) && tma && tiles >= 4LL * sms && a.K > 0) {  // staggered + ring-staged C
     a.tps = tps;
     a.stage_c = 2;
     gemm_dmma_ppc_kernel<CPLX><<<(unsigned)((tiles + 2 * tps - 1) / (2 * tps)), Cfg::PP_THREADS, Cfg::PP_SMEM_BYTES, st>>>(a);
@@ -863,7 +865,7 @@ static int launch_t(const chol_gemm_desc *d) {
 
 #ifndef CHOL_CPU_EMU
 int chol_gemm_fp32_launch(const chol_gemm_desc *d);  // gemm_ffma.cu
-extern "C" int chol_gemm_small_eligible(const chol_gemm_desc *d);  // gemm_small.cu (CHOL_SMALL_GEMM=1, off by default)
+extern "C" int chol_gemm_small_eligible(const chol_gemm_desc *d);  // gemm_small.cu
 extern "C" int chol_gemm_small_launch(const chol_gemm_desc *d);
 
 extern "C" int chol_gemm_launch(const chol_gemm_desc *d) {

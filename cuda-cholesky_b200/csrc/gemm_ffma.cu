@@ -5,28 +5,31 @@
 // (reference: blas/sgemm.c:148, cgemm.c:226, ssyrk.c:163, cherk.c:190).  north_star allows "FP32
 // FFMA or a 3xTF32 split" for s/c; this is the FFMA choice: exact FP32 products, FP32 accumulate,
 // so the s/c tolerance is the plain FP32 one.
-//   * CTA tile 128x128 (s) / 64x64 (c), BK = 8, 256 threads, 8x8 (s) / 4x4-complex (c) register
+//   * CTA tile 128x128 (s) / 64x64 (c), BK = 16, 256 threads, 8x8 (s) / 4x4-complex (c) register
 //     tile per thread, operands in shared memory as [k][m] / [k][n], 128-bit shared loads;
-//   * 4-stage cp.async (LDGSTS) pipeline straight into shared memory, one __syncthreads per k-tile;
+//   * 4-stage cp.async (LDGSTS) pipeline straight into dynamic shared memory (66 KB, 2 CTAs/SM), one
+//     __syncthreads per k-tile; for the hot shape (interior NT tile, aligned operands) the loader is
+//     hoisted out of the k loop: fixed shared slots and running source pointers, 4 cp.async + 2 pointer
+//     bumps per k-tile and thread.  (Round 1 shipped BK = 8: FFMA held ~73 % of the issue slots; BK = 16
+//     measured 37.3 -> 43.6 TFLOP/s on spotrf N = 32768, profiles/r02_staged_ab.txt.)
+//   * the trailing updates of spotrf run on the tensor cores instead (gemm_tf32x3.cu);
 //   * any transpose / conjugate / triangular mask handled by the loader, k-ranges that are
 //     structurally zero are skipped, triangular (cuplo) grids launch only the needed tiles.
 #include <stdlib.h>
+#include <atomic>
 
 #include "gemm_ffma.cuh"
 
 namespace chol {
 
-// gemm_ffma_deep.cu
-int chol_gemm_fp32_deep_launch(const FArgs<float> &a, unsigned tiles, cudaStream_t st);
-int chol_gemm_fp32_deep_launch(const FArgs<float2> &a, unsigned tiles, cudaStream_t st);
-
 template <typename T>
 __global__ void __launch_bounds__(256, 2) gemm_ffma_kernel(const __grid_constant__ FArgs<T> p) {
   using Cfg = FCfg<T>;
-  constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, LDS = Cfg::LDS, VW = Cfg::VW, TM = Cfg::TM, TN = Cfg::TN;
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = 16, LDS = Cfg::LDS, VW = Cfg::VW, TM = Cfg::TM, TN = Cfg::TN;
   constexpr int ST = 4;  // cp.async stages
-  __shared__ __align__(16) T As[ST][BK * LDS];
-  __shared__ __align__(16) T Bs[ST][BK * LDS];
+  CHOL_DYN_SMEM(f_dyn_smem);
+  typedef T Stage[BK * LDS];
+  Stage *As = reinterpret_cast<Stage *>(f_dyn_smem), *Bs = As + ST;
 
   int bi, bj;
   if (!tile_coords<BM, BN>(8, p.cuplo, p.NI, p.NJ, p.cm, (long long)blockIdx.x, bi, bj)) return;
@@ -52,11 +55,34 @@ __global__ void __launch_bounds__(256, 2) gemm_ffma_kernel(const __grid_constant
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = zero_of<T>();
 
-  auto issue = [&](int kt) {
+  // Hoisted loader for the hot shape (interior tile, op(A) = N, op(B) = T/C, no masks, 16-byte
+  // aligned): every thread owns two fixed 16-byte slots per operand and k-tile; its source pointers
+  // advance by a constant stride, so a k-tile costs 4 cp.async + 2 pointer bumps instead of the
+  // generic loader's predicates and 64-bit address arithmetic.
+  constexpr int VPR = BM / VW;                 // 16-byte vectors per k-row (BM == BN): 32 for s and c
+  constexpr int KPT = 256 / VPR;               // k-rows covered by one pass of the 256 threads: 8
+  static_assert(BM == BN && 256 % VPR == 0 && BK == 2 * KPT, "hoisted loader layout: two passes per k-tile");
+  const bool hoist = rowsA == BM && rowsB == BN && p.opA == 0 && p.opB != 0 && !p.triA && !p.triB && p.vecA && p.vecB;
+  const int rv = tid % VPR, kk0 = tid / VPR;
+  const int doff = kk0 * LDS + rv * VW;        // slot of the first pass; the second pass is KPT k-rows further
+  const T *pa = p.A + (long long)(kb + kk0) * p.lda + m0 + rv * VW;  // running source pointers (one per operand)
+  const T *pb = p.B + (long long)(kb + kk0) * p.ldb + g0 + rv * VW;
+  const long long halfA = (long long)KPT * p.lda, halfB = (long long)KPT * p.ldb;
+
+  auto issue = [&](int kt) {  // called with kt = 0, 1, 2, ... in order
     if (kt < nk) {
       const int s = kt % ST, k0 = kb + kt * BK;
-      f_fill<T, BM, BK, LDS>(As[s], p.A, p.lda, p.opA, p.triA, p.unitA, false, m0, p.M, rowsA, k0, ke, p.vecA, tid);
-      f_fill<T, BN, BK, LDS>(Bs[s], p.B, p.ldb, p.opB, p.triB, p.unitB, true, g0, p.N, rowsB, k0, ke, p.vecB, tid);
+      if (hoist && k0 + BK <= ke) {
+        f_cp_async<16>(&As[s][doff], pa);
+        f_cp_async<16>(&As[s][doff + KPT * LDS], pa + halfA);
+        f_cp_async<16>(&Bs[s][doff], pb);
+        f_cp_async<16>(&Bs[s][doff + KPT * LDS], pb + halfB);
+      } else {
+        f_fill<T, BM, BK, LDS>(As[s], p.A, p.lda, p.opA, p.triA, p.unitA, false, m0, p.M, rowsA, k0, ke, p.vecA, tid);
+        f_fill<T, BN, BK, LDS>(Bs[s], p.B, p.ldb, p.opB, p.triB, p.unitB, true, g0, p.N, rowsB, k0, ke, p.vecB, tid);
+      }
+      pa += 2 * halfA;
+      pb += 2 * halfB;
     }
     CHOL_CP_ASYNC_COMMIT();
   };
@@ -152,10 +178,16 @@ static int launch_f(const chol_gemm_desc *d) {
   const long long tiles = total_tiles<Cfg::BM, Cfg::BN>(8, a.cuplo, a.NI, a.NJ, a.cm);
   if (tiles <= 0) return 0;
   if (tiles > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
-  // CHOL_FFMA_BK=16: the deeper-k-tile variant (gemm_ffma_deep.cu), off until verified and measured on hardware
-  static const bool deep = [] { const char *e = getenv("CHOL_FFMA_BK"); return e != nullptr && atoi(e) == 16; }();
-  if (deep) return chol_gemm_fp32_deep_launch(a, (unsigned)tiles, (cudaStream_t)d->stream);
-  gemm_ffma_kernel<T><<<(unsigned)tiles, 256, 0, (cudaStream_t)d->stream>>>(a);
+  constexpr int bytes = 2 * 4 * 16 * Cfg::LDS * (int)sizeof(T);
+  static std::atomic<int> attr_set[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63].load(std::memory_order_acquire)) {
+    const cudaError_t e = cudaFuncSetAttribute(gemm_ffma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return (int)e;
+    attr_set[dev & 63].store(1, std::memory_order_release);
+  }
+  gemm_ffma_kernel<T><<<(unsigned)tiles, 256, bytes, (cudaStream_t)d->stream>>>(a);
   CHOL_COUNT_LAUNCH();
   return (int)cudaGetLastError();
 }

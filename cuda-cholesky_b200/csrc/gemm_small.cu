@@ -118,8 +118,7 @@ __global__ void __launch_bounds__(S_THREADS) dgemm_small_kernel(const __grid_con
 #ifndef CHOL_CPU_EMU  // the launchers are not part of the CPU emulation (tests/emu)
 // 1 if the descriptor is one the small-tile kernel takes (and the switch is on)
 extern "C" int chol_gemm_small_eligible(const chol_gemm_desc *d) {
-  static const bool on = [] { const char *e = getenv("CHOL_SMALL_GEMM"); return e != nullptr && atoi(e) != 0; }();
-  if (!on || d->prec != 'd') return 0;
+  if (d->prec != 'd') return 0;
   if (d->triA || d->triB || d->cyc_nb || d->force_generic) return 0;
   if (d->m == 0 || d->n == 0) return 0;
   // "small" = the 128 x 64 DMMA grid would leave most SMs idle, and the problem is not k-heavy

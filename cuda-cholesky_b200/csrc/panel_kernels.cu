@@ -131,15 +131,25 @@ __global__ void __launch_bounds__(PANEL_THREADS) trti2_kernel(int upper, int uni
   const int LD = n | 1;
   T *dinv = L + (size_t)n * LD;
   __shared__ int fail_lo, fail_hi;
-  if (*dinfo != 0) return;
-  if (threadIdx.x == 0) { fail_lo = 0x7fffffff; fail_hi = -1; }
+  // info protocol (bits 1-2 of the flags word, csrc/chol_kernels.h):
+  //   0  LAPACK drivers: *dinfo is a sticky 64-bit word - skip if already set, first failure wins
+  //   2  the reference's own device kernel contract (lapack/dtrtri.cu:23-29): a 32-bit int that the
+  //      kernel itself sets to 0 on entry, no early-out
+  //   4  BLAS use (TRSM diagonal blocks): no info word at all; a zero pivot gives Inf like the BLAS
+  const int info_mode = zero_other & 6;
+  zero_other &= 1;
+  if (info_mode == 0 && *dinfo != 0) return;
+  if (threadIdx.x == 0) {
+    fail_lo = 0x7fffffff; fail_hi = -1;
+    if (info_mode == 2) *reinterpret_cast<int *>(dinfo) = 0;
+  }
   load_lower_form(L, LD, upper, false, n, A, lda);
   __syncthreads();
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     if (unit) dinv[i] = one_of<T>();
     else {
       const T d = L[i + i * LD];
-      if (is_zero(d)) { atomicMin(&fail_lo, i); atomicMax(&fail_hi, i); dinv[i] = zero_of<T>(); }
+      if (is_zero(d) && info_mode != 4) { atomicMin(&fail_lo, i); atomicMax(&fail_hi, i); dinv[i] = zero_of<T>(); }
       else dinv[i] = recip(d);
     }
   }
@@ -147,7 +157,10 @@ __global__ void __launch_bounds__(PANEL_THREADS) trti2_kernel(int upper, int uni
   if (fail_hi >= 0) {
     // the reference sweeps columns upwards for Upper and downwards for Lower and reports the first
     // zero pivot it meets (lapack/dtrtri.c:49-52, :73-77)
-    if (threadIdx.x == 0) *dinfo = info_base + (upper ? fail_lo : fail_hi) + 1;
+    if (threadIdx.x == 0) {
+      const long v = info_base + (upper ? fail_lo : fail_hi) + 1;
+      if (info_mode == 2) *reinterpret_cast<int *>(dinfo) = (int)v; else *dinfo = v;
+    }
     return;
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -538,9 +551,9 @@ static int potf2_inv_t(int uplo, size_t n, void *A, size_t lda, void *X, size_t 
   constexpr int NMAX = sizeof(T) == 16 ? 64 : 128;
   using Real = typename ScalarOf<T>::Real;
   const size_t sm = (size_t)NMAX * (NMAX + 1) * sizeof(T) + NMAX * sizeof(Real);
-  static const bool v2 = [] { const char *e = getenv("CHOL_POTF2_V2"); return e != nullptr && atoi(e) != 0; }();
-  auto kern = v2 ? potf2_inv_kernel<T, NMAX / 32, NMAX / 16, NMAX / 32, NMAX / 16, true>
-                 : potf2_inv_kernel<T, NMAX / 32, NMAX / 16, NMAX / 32, NMAX / 16, false>;
+  // V2 = short serial section (d: 109.6 -> 82.9 us per 128-block on B200, profiles/r02_staged_ab.txt); the V = false
+  // instantiation only exists in the CPU emulation, which checks that both give the same bits
+  auto kern = potf2_inv_kernel<T, NMAX / 32, NMAX / 16, NMAX / 32, NMAX / 16, true>;
   int e = set_smem(kern, sm); if (e) return e;
   kern<<<1, PANEL_THREADS, sm, st>>>(uplo == 'U', (int)n, (T *)A, (long long)lda, (T *)X, (long long)ldx, dinfo, base);
   CHOL_COUNT_LAUNCH();
@@ -550,8 +563,7 @@ template <typename T>
 static int trti2_t(int uplo, int diag, size_t n, const void *A, size_t lda, void *B, size_t ldb, int zo, long *dinfo, long base, cudaStream_t st) {
   const size_t sm = panel_smem<T>(n, n);
   constexpr int NMAX = sizeof(T) == 16 ? 64 : 128;
-  static const bool v2 = [] { const char *e = getenv("CHOL_POTF2_V2"); return e != nullptr && atoi(e) != 0; }();
-  auto kern = v2 ? trti2_kernel<T, NMAX / 32, NMAX / 16, true> : trti2_kernel<T, NMAX / 32, NMAX / 16, false>;
+  auto kern = trti2_kernel<T, NMAX / 32, NMAX / 16, true>;
   int e = set_smem(kern, sm); if (e) return e;
   kern<<<1, PANEL_THREADS, sm, st>>>(uplo == 'U', diag == 'U', (int)n, (const T *)A, (long long)lda, (T *)B, (long long)ldb, zo, dinfo, base);
   CHOL_COUNT_LAUNCH();

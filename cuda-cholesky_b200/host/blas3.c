@@ -85,8 +85,6 @@ static CUresult trsm_body(CUBLAShandle h, int prec, int side, int uplo, int tran
   CUdeviceptr scr;
   CU_ERROR_CHECK(chol_blas_scratch(h, (tb * tb + s_elems) * es + 256, &scr));
   const CUdeviceptr Ainv = scr, S = scr + (CUdeviceptr)(chol_roundup(tb * tb * es, 256));
-  CU_ERROR_CHECK(cuMemsetD8Async(h->dinfo, 0, sizeof(long), stream));
-
   const size_t nblk = (na + tb - 1) / tb;
   for (size_t b = 0; b < nblk; b++) {
     const size_t blk = forward ? b : nblk - 1 - b;
@@ -96,8 +94,10 @@ static CUresult trsm_body(CUBLAShandle h, int prec, int side, int uplo, int tran
     const double *b_upd = first ? alpha : ONE;
     /* rows/cols still to be solved after this block */
     const size_t r0 = forward ? i + ib : 0, rn = forward ? na - i - ib : i;
-    RT_CHECK(chol_trti2_launch(prec, uplo, diag, ib, (const void *)chol_at(A, lda, i, i, es), lda, (void *)Ainv, tb, 1,
-                               (long *)h->dinfo, 0, (void *)stream));
+    /* no info word: a zero pivot gives Inf/NaN in B exactly as a substitution TRSM would (blas/dtrsm.c), and one
+     * singular block cannot turn the later blocks' inverses into no-ops */
+    RT_CHECK(chol_trti2_launch(prec, uplo, diag, ib, (const void *)chol_at(A, lda, i, i, es), lda, (void *)Ainv, tb,
+                               1 | CHOL_TRTI2_NO_INFO, (long *)h->dinfo, 0, (void *)stream));
     if (side == 'L') {
       const CUdeviceptr Bi = chol_at(B, ldb, i, 0, es);
       CU_ERROR_CHECK(chol_gemm(prec, trans, 'N', ib, n, ib, a_diag, Ainv, tb, Bi, ldb, ZERO, 0, 0, S, lds, stream));

@@ -33,6 +33,7 @@ struct __cublashandle_st {
 };
 
 #define CHOL_EVENT_RING 4
+#define CHOL_DIAG_EVENTS 16 /* sub-blocks of one diagonal block whose completion the pipelined panel solve can wait for */
 
 /* reference lapack/handle.h:4-11 */
 struct __culapackhandle_st {
@@ -40,15 +41,21 @@ struct __culapackhandle_st {
   CUcontext context;
   CUstream s_panel;  /* high priority: diagonal block, panel solve, look-ahead update */
   CUstream s_update; /* trailing-matrix update */
-  CUstream s_look;   /* lower part of the look-ahead column when the look-ahead is split (CHOL_LOOKAHEAD_SPLIT) */
+  CUstream s_look;   /* second high-priority stream: full-height GEMMs of the pipelined panel solve; lower part of the
+                      * look-ahead column when the look-ahead is split (CHOL_LOOKAHEAD_SPLIT) */
   CUevent ev_panel[CHOL_EVENT_RING];
   CUevent ev_rest[CHOL_EVENT_RING];
   CUevent ev_look[CHOL_EVENT_RING];
+  CUevent ev_dx[CHOL_DIAG_EVENTS], ev_dcol[CHOL_DIAG_EVENTS], ev_solve; /* pipelined panel solve (lapack.c panel_factor_solve) */
   CUdeviceptr ws; /* workspace, cached across calls (the reference allocates per call, dpotrf.c:200) */
   size_t ws_bytes;
   CUdeviceptr dinfo;      /* device long */
   long *hinfo;            /* pinned host mirror */
-  CUdeviceptr logdet_scr; /* reduction scratch + result */
+  CUdeviceptr logdet_scr; /* reduction scratch + result; shared by every logdet call on the handle: calls on
+                           * different streams are ordered through logdet_done (same stream: stream order) */
+  CUevent logdet_done;
+  CUstream logdet_stream;
+  bool logdet_in_use;
   void *hlogdet;          /* pinned */
   size_t nb;              /* outer block size (0 = default per precision) */
   /* optional per-launch timing of the dominant kernel (the trailing-matrix update): CUDA events
@@ -111,7 +118,9 @@ typedef struct chol_ws {
   CUdeviceptr T1;   /* nb x nb : temporary of the blocked small inverse */
   CUdeviceptr Tinv; /* db x db : inverse of a potf2 sub-block */
   CUdeviceptr Wd;   /* nb x db : panel of the diagonal-block recursion */
-  CUdeviceptr Tp;   /* ldw x db: temporary of the blocked panel solve (0 unless CHOL_PANEL_BLOCKED) */
+  CUdeviceptr Tp;   /* ldw x db: temporary of the blocked panel solve (0 with CHOL_PANEL_BLOCKED=0) */
+  size_t kp;        /* s with the tensor-core update: K pitch of the TF32 planes (0 = FFMA path) */
+  CUdeviceptr Whi[2], Wlo[2]; /* ldw x kp floats, K-major: tf32 hi / lo planes of W[0], W[1] */
 } chol_ws;
 
 size_t chol_default_nb(int prec, size_t n);
@@ -125,14 +134,22 @@ CUresult chol_diag_factor_inverse(int prec, int uplo, size_t jb, CUdeviceptr A, 
 CUresult chol_diag_factor_inverse_ex(int prec, int uplo, size_t jb, CUdeviceptr A, size_t lda, CUdeviceptr X, size_t ldx,
                                      long *dinfo, long base, const chol_ws *w, CUstream st, int diag_only);
 bool chol_panel_blocked(void);
-/* POTRF panel step (lower): factor the jb x jb diagonal block at Ajj, solve the rest x jb panel P below it into W */
-CUresult chol_panel_factor_solve_lower(int prec, size_t jb, size_t rest, CUdeviceptr Ajj, CUdeviceptr P, size_t lda, CUdeviceptr W,
-                                       size_t ldw, long *dinfo, long base, const chol_ws *w, CUstream st, CUevent before_solve);
+/* POTRF panel step: factor the jb x jb diagonal block at Ajj, solve the panel next to it into W (rest x jb).
+ * h != NULL: the solve is pipelined with the diagonal chain on the handle's second high-priority stream */
+CUresult chol_panel_factor_solve_lower(CULAPACKhandle h, int prec, size_t jb, size_t rest, CUdeviceptr Ajj, CUdeviceptr P, size_t lda,
+                                       CUdeviceptr W, size_t ldw, long *dinfo, long base, const chol_ws *w, CUstream st,
+                                       CUevent before_solve);
+CUresult chol_diag_factor_inverse_ev(int prec, int uplo, size_t jb, CUdeviceptr A, size_t lda, CUdeviceptr X, size_t ldx,
+                                     long *dinfo, long base, const chol_ws *w, CUstream st, int diag_only, CUevent *ev_x,
+                                     CUevent *ev_col);
+bool chol_panel_pipeline(void);
 bool chol_lookahead_split(void);
+bool chol_s_tensor(void);
 bool chol_trtri_lookahead(void);
 /* ... upper: the jb x rest block row P right of the diagonal block, W = P^H * inv(U11) (rest x jb) */
-CUresult chol_panel_factor_solve_upper(int prec, size_t jb, size_t rest, CUdeviceptr Ajj, CUdeviceptr P, size_t lda, CUdeviceptr W,
-                                       size_t ldw, long *dinfo, long base, const chol_ws *w, CUstream st, CUevent before_solve);
+CUresult chol_panel_factor_solve_upper(CULAPACKhandle h, int prec, size_t jb, size_t rest, CUdeviceptr Ajj, CUdeviceptr P, size_t lda,
+                                       CUdeviceptr W, size_t ldw, long *dinfo, long base, const chol_ws *w, CUstream st,
+                                       CUevent before_solve);
 CUresult chol_trtri_small(int prec, int uplo, int diag, size_t jb, CUdeviceptr A, size_t lda, CUdeviceptr X,
                           size_t ldx, long *dinfo, long base, const chol_ws *w, CUstream st);
 

@@ -34,16 +34,19 @@ static const double MONE[2] = {-1.0, 0.0};
 
 /* an environment switch, read once per process; the cached value is published with atomics because the
  * multi-GPU worker threads ask concurrently (every reader would compute the same value anyway) */
-static bool chol_env_switch(int *state, const char *name) {
+static bool chol_env_switch(int *state, const char *name, int dflt) {
   int v = __atomic_load_n(state, __ATOMIC_RELAXED);
   if (v < 0) {
     const char *e = getenv(name);
-    v = (e != NULL && atoi(e) != 0) ? 1 : 0;
+    v = (e != NULL) ? (atoi(e) != 0) : dflt;
     __atomic_store_n(state, v, __ATOMIC_RELAXED);
   }
   return v != 0;
 }
-static int chol_panel_blocked_state = -1, chol_lookahead_split_state = -1, chol_trtri_lookahead_state = -1;
+static int chol_panel_blocked_state = -1, chol_lookahead_split_state = -1, chol_trtri_lookahead_state = -1, chol_s_tensor_state = -1, chol_panel_pipeline_state = -1;
+/* s-precision POTRF: trailing and look-ahead updates on the tcgen05 tensor cores as a 3xTF32 split (default;
+ * CHOL_S_TENSOR=0 keeps them on the FP32 FFMA engine for A/B runs and for the plain-FP32 tolerance) */
+bool chol_s_tensor(void) { return chol_env_switch(&chol_s_tensor_state, "CHOL_S_TENSOR", 1); }
 
 /* outer block size: k of the trailing update.  Larger k amortises the C-tile epilogue (measured on
  * B200, d: 512 beats 256 from N ~ 32768 up), smaller k shortens the serial panel chain. */
@@ -68,8 +71,11 @@ CUresult chol_carve_nb(CULAPACKhandle h, int prec, size_t n, size_t nb, chol_ws 
   const size_t szW = chol_roundup(w->ldw * w->nb * w->es, 256), szX = chol_roundup(w->nb * w->nb * w->es, 256),
                szT = chol_roundup(w->db * w->db * w->es, 256), szWd = chol_roundup(w->nb * w->db * w->es, 256);
   const size_t szTp = chol_panel_blocked() ? chol_roundup(w->ldw * w->db * w->es, 256) : 0;
+  /* s: TF32 (hi, lo) planes of the two panel buffers for the tensor-core trailing update (csrc/gemm_tf32x3.cu) */
+  w->kp = (prec == 's' && chol_s_tensor()) ? chol_tf32_kpitch(w->nb) : 0;
+  const size_t szS = chol_roundup(w->ldw * w->kp * sizeof(float), 1024);
   CUdeviceptr base;
-  CU_ERROR_CHECK(chol_lapack_workspace(h, 2 * szW + 2 * szX + szT + szWd + szTp, &base));
+  CU_ERROR_CHECK(chol_lapack_workspace(h, 2 * szW + 2 * szX + szT + szWd + szTp + 4 * szS + 1024, &base));
   w->W[0] = base;
   w->W[1] = base + szW;
   w->Xd = base + 2 * szW;
@@ -77,6 +83,11 @@ CUresult chol_carve_nb(CULAPACKhandle h, int prec, size_t n, size_t nb, chol_ws 
   w->Tinv = w->T1 + szX;
   w->Wd = w->Tinv + szT;
   w->Tp = szTp ? w->Wd + szWd : 0;
+  const CUdeviceptr planes = chol_roundup(w->Wd + szWd + szTp, 1024);
+  for (int i = 0; i < 2; i++) {
+    w->Whi[i] = w->kp ? planes + (CUdeviceptr)(2 * i) * szS : 0;
+    w->Wlo[i] = w->kp ? planes + (CUdeviceptr)(2 * i + 1) * szS : 0;
+  }
   return CUDA_SUCCESS;
 }
 
@@ -161,6 +172,15 @@ CUresult chol_diag_factor_inverse(int prec, int uplo, size_t jb, CUdeviceptr A, 
  * panel solve needs); the rest of X is left alone */
 CUresult chol_diag_factor_inverse_ex(int prec, int uplo, size_t jb, CUdeviceptr A, size_t lda, CUdeviceptr X, size_t ldx,
                                      long *dinfo, long base, const chol_ws *w, CUstream st, int diag_only) {
+  return chol_diag_factor_inverse_ev(prec, uplo, jb, A, lda, X, ldx, dinfo, base, w, st, diag_only, NULL, NULL);
+}
+
+/* ev_x / ev_col (both or neither; at least nblk events each): ev_x[c] is recorded on st when X_cc (the inverse of
+ * diagonal sub-block c) is ready, ev_col[c] when the factor's sub-block column (lower) / row (upper) c is final in
+ * the matrix - what a panel solve running on another stream has to wait for */
+CUresult chol_diag_factor_inverse_ev(int prec, int uplo, size_t jb, CUdeviceptr A, size_t lda, CUdeviceptr X, size_t ldx,
+                                     long *dinfo, long base, const chol_ws *w, CUstream st, int diag_only, CUevent *ev_x,
+                                     CUevent *ev_col) {
   const size_t es = w->es, db = w->db, nblk = (jb + db - 1) / db;
   const int herm = chol_is_complex(prec);
   if (nblk > 1 && !diag_only) RT_CHECK(chol_fill_launch(prec, 0, jb, jb, 0.0, 0.0, (void *)X, ldx, (void *)st));
@@ -168,6 +188,7 @@ CUresult chol_diag_factor_inverse_ex(int prec, int uplo, size_t jb, CUdeviceptr 
     const size_t i = c * db, ib = chol_min(db, jb - i), r = jb - i - ib;
     const CUdeviceptr Aii = chol_at(A, lda, i, i, es), Xii = chol_at(X, ldx, i, i, es);
     RT_CHECK(chol_potf2_inv_launch(prec, uplo, ib, (void *)Aii, lda, (void *)Xii, ldx, dinfo, base + (long)i, (void *)st));
+    if (ev_x) CU_ERROR_CHECK(cuEventRecord(ev_x[c], st));
     if (r == 0) break;
     const CUdeviceptr A22 = chol_at(A, lda, i + ib, i + ib, es);
     if (uplo == 'L') {
@@ -179,6 +200,7 @@ CUresult chol_diag_factor_inverse_ex(int prec, int uplo, size_t jb, CUdeviceptr 
       CU_ERROR_CHECK(chol_gemm(prec, 'C', 'N', r, ib, ib, ONE, A12, lda, Xii, ldx, ZERO, 0, 0, w->Wd, w->nb, st));
       RT_CHECK(chol_copy_launch(prec, 'C', 0, r, ib, (const void *)w->Wd, w->nb, (void *)A12, lda, (void *)st));
     }
+    if (ev_col) CU_ERROR_CHECK(cuEventRecord(ev_col[c], st));
     CU_ERROR_CHECK(chol_gemm_ex(prec, 'N', 'C', 0, 0, 0, 0, uplo, herm, r, r, ib, MONE, w->Wd, w->nb, w->Wd, w->nb, ONE, A22,
                                 lda, A22, lda, st));
   }
@@ -203,75 +225,92 @@ CUresult chol_diag_factor_inverse_ex(int prec, int uplo, size_t jb, CUdeviceptr 
   return CUDA_SUCCESS;
 }
 
-/* CHOL_PANEL_BLOCKED=1 (written after the round-1 GPU budget was spent, off until measured):
+/* Blocked panel solve (default; CHOL_PANEL_BLOCKED=0 selects the one-GEMM form for A/B runs - dpotrf N = 16384
+ * 25.7 -> 26.7 TFLOP/s alone, 28.4 together with the other chain cuts, profiles/r02_staged_ab.txt):
  * instead of inverting the whole jb x jb diagonal block (nblk(nblk-1) small, serial GEMMs to tie the
  * db-blocks of the inverse together) and solving the panel with one GEMM, invert only the db x db
  * diagonal sub-blocks and solve the panel by block forward substitution with full-height GEMMs:
  *     W_c = (P_c - W[:, 0:c] * L[c, 0:c]^H) * inv(L_cc)^H        c = 0 .. nblk-1
  * 10/16 of the flops at nblk = 4, no small GEMMs on the chain. */
-bool chol_panel_blocked(void) { return chol_env_switch(&chol_panel_blocked_state, "CHOL_PANEL_BLOCKED"); }
+bool chol_panel_blocked(void) { return chol_env_switch(&chol_panel_blocked_state, "CHOL_PANEL_BLOCKED", 1); }
 
 /* CHOL_LOOKAHEAD_SPLIT=1 (written after the round-1 GPU budget was spent, off until measured): the look-ahead
  * update of the next block column is split - its jb2 x jb2 diagonal block stays on the panel stream, so the next
  * diagonal block can be factored at once, while the rows below it (the bulk of the column) are updated on a
  * third stream at the same time; the next panel solve waits for that part.  Takes the look-ahead GEMM off the
  * serial panel chain (stream dependencies mutation-tested on the asynchronous mock back end). */
-bool chol_lookahead_split(void) { return chol_env_switch(&chol_lookahead_split_state, "CHOL_LOOKAHEAD_SPLIT"); }
+bool chol_lookahead_split(void) { return chol_env_switch(&chol_lookahead_split_state, "CHOL_LOOKAHEAD_SPLIT", 0); }
 
-bool chol_trtri_lookahead(void) { return chol_env_switch(&chol_trtri_lookahead_state, "CHOL_TRTRI_LOOKAHEAD"); }
+bool chol_trtri_lookahead(void) { return chol_env_switch(&chol_trtri_lookahead_state, "CHOL_TRTRI_LOOKAHEAD", 1); }
 
-/* factor the jb x jb lower diagonal block at Ajj and solve the rest x jb panel P below it into W */
-/* before_solve (may be NULL): an event the stream must have seen before the panel P is read - the lower part of
- * a split look-ahead runs on another stream while the diagonal block is factored here */
-CUresult chol_panel_factor_solve_lower(int prec, size_t jb, size_t rest, CUdeviceptr Ajj, CUdeviceptr P, size_t lda, CUdeviceptr W,
-                                       size_t ldw, long *dinfo, long base, const chol_ws *w, CUstream st, CUevent before_solve) {
+/* Panel step of POTRF: factor the jb x jb diagonal block at Ajj and solve the panel next to it into W (rest x jb).
+ *   lower: P = the rest x jb block below Ajj,      W_c = (P_c   - W[:, 0:c] * L[c, 0:c]^H) * inv(L_cc)^H
+ *   upper: P = the jb x rest block right of Ajj,   W_c = (P_c^H - W[:, 0:c] * U[0:c, c])   * inv(U_cc)
+ * Blocked form (default): only the db x db diagonal sub-blocks are inverted and the panel is solved by block
+ * forward substitution with full-height GEMMs.  With a handle the two halves are PIPELINED: the diagonal chain
+ * (potf2+inverse, small GEMMs) runs on `st`, the full-height GEMMs on the handle's second high-priority stream,
+ * sub-block c of the solve starting as soon as sub-block c of the chain is done (events), so only the last
+ * sub-block's solve is left on the critical path.  `st` has seen everything when the function returns.
+ * before_solve (may be NULL): an event that must have completed before P is read - the lower part of a split
+ * look-ahead runs on another stream while the diagonal block is factored here. */
+bool chol_panel_pipeline(void) { return chol_env_switch(&chol_panel_pipeline_state, "CHOL_PANEL_PIPELINE", 1); }
+
+static CUresult panel_factor_solve(CULAPACKhandle h, int prec, int uplo, size_t jb, size_t rest, CUdeviceptr Ajj, CUdeviceptr P,
+                                   size_t lda, CUdeviceptr W, size_t ldw, long *dinfo, long base, const chol_ws *w, CUstream st,
+                                   CUevent before_solve) {
   const size_t es = w->es, db = w->db, nb = w->nb, nblk = (jb + db - 1) / db;
-  if (!chol_panel_blocked() || nblk < 2 || w->Tp == 0) {
-    CU_ERROR_CHECK(chol_diag_factor_inverse(prec, 'L', jb, Ajj, lda, w->Xd, nb, dinfo, base, w, st));
+  const bool lower = uplo == 'L';
+  if (!chol_panel_blocked() || nblk < 2 || w->Tp == 0) { /* whole inverse, one GEMM */
+    CU_ERROR_CHECK(chol_diag_factor_inverse(prec, uplo, jb, Ajj, lda, w->Xd, nb, dinfo, base, w, st));
     if (before_solve) CU_ERROR_CHECK(cuStreamWaitEvent(st, before_solve, 0));
-    return chol_gemm(prec, 'N', 'C', rest, jb, jb, ONE, P, lda, w->Xd, nb, ZERO, 0, 0, W, ldw, st);
+    return chol_gemm(prec, lower ? 'N' : 'C', lower ? 'C' : 'N', rest, jb, jb, ONE, P, lda, w->Xd, nb, ZERO, 0, 0, W, ldw, st);
   }
-  CU_ERROR_CHECK(chol_diag_factor_inverse_ex(prec, 'L', jb, Ajj, lda, w->Xd, nb, dinfo, base, w, st, 1));
-  if (before_solve) CU_ERROR_CHECK(cuStreamWaitEvent(st, before_solve, 0));
+  const bool pipe = h != NULL && nblk <= CHOL_DIAG_EVENTS && chol_panel_pipeline();
+  CUstream ss = pipe ? h->s_look : st;
+  if (pipe) { /* the solve stream starts from what `st` has seen (P's look-ahead update may have run there) */
+    CU_ERROR_CHECK(cuEventRecord(h->ev_solve, st));
+    CU_ERROR_CHECK(cuStreamWaitEvent(ss, h->ev_solve, 0));
+    if (before_solve) CU_ERROR_CHECK(cuStreamWaitEvent(ss, before_solve, 0));
+  }
+  CU_ERROR_CHECK(chol_diag_factor_inverse_ev(prec, uplo, jb, Ajj, lda, w->Xd, nb, dinfo, base, w, st, 1, pipe ? h->ev_dx : NULL,
+                                             pipe ? h->ev_dcol : NULL));
+  if (!pipe && before_solve) CU_ERROR_CHECK(cuStreamWaitEvent(st, before_solve, 0));
   for (size_t c = 0; c < nblk; c++) {
     const size_t i = c * db, ib = chol_min(db, jb - i);
-    const CUdeviceptr Pc = chol_at(P, lda, 0, i, es), Wc = chol_at(W, ldw, 0, i, es), Xcc = chol_at(w->Xd, nb, i, i, es);
+    const CUdeviceptr Wc = chol_at(W, ldw, 0, i, es), Xcc = chol_at(w->Xd, nb, i, i, es);
+    const CUdeviceptr Pc = lower ? chol_at(P, lda, 0, i, es) : chol_at(P, lda, i, 0, es);
     if (c == 0) {
-      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'C', rest, ib, ib, ONE, Pc, lda, Xcc, nb, ZERO, 0, 0, Wc, ldw, st));
-    } else {
-      /* T = P_c - W[:, 0:i] * L[i:i+ib, 0:i]^H  (C = P_c in the matrix, D = T), then W_c = T * inv(L_cc)^H */
-      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'C', rest, ib, i, MONE, W, ldw, chol_at(Ajj, lda, i, 0, es), lda, ONE, Pc, lda, w->Tp, w->ldw, st));
-      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'C', rest, ib, ib, ONE, w->Tp, w->ldw, Xcc, nb, ZERO, 0, 0, Wc, ldw, st));
+      if (pipe) CU_ERROR_CHECK(cuStreamWaitEvent(ss, h->ev_dx[0], 0));
+      CU_ERROR_CHECK(chol_gemm(prec, lower ? 'N' : 'C', lower ? 'C' : 'N', rest, ib, ib, ONE, Pc, lda, Xcc, nb, ZERO, 0, 0, Wc, ldw, ss));
+      continue;
     }
+    if (pipe) CU_ERROR_CHECK(cuStreamWaitEvent(ss, h->ev_dcol[c - 1], 0)); /* L[c, 0:i] / U[0:i, c] is final */
+    if (lower) { /* T = P_c - W[:, 0:i] * L[i:i+ib, 0:i]^H  (C = P_c in the matrix, D = T) */
+      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'C', rest, ib, i, MONE, W, ldw, chol_at(Ajj, lda, i, 0, es), lda, ONE, Pc, lda, w->Tp, w->ldw, ss));
+    } else {     /* T = P_c^H, then T -= W[:, 0:i] * U[0:i, i:i+ib] */
+      RT_CHECK(chol_copy_launch(prec, 'C', 0, ib, rest, (const void *)Pc, lda, (void *)w->Tp, w->ldw, (void *)ss));
+      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'N', rest, ib, i, MONE, W, ldw, chol_at(Ajj, lda, 0, i, es), lda, ONE, w->Tp, w->ldw, w->Tp,
+                               w->ldw, ss));
+    }
+    if (pipe) CU_ERROR_CHECK(cuStreamWaitEvent(ss, h->ev_dx[c], 0)); /* X_cc */
+    CU_ERROR_CHECK(chol_gemm(prec, 'N', lower ? 'C' : 'N', rest, ib, ib, ONE, w->Tp, w->ldw, Xcc, nb, ZERO, 0, 0, Wc, ldw, ss));
+  }
+  if (pipe) {
+    CU_ERROR_CHECK(cuEventRecord(h->ev_solve, ss));
+    CU_ERROR_CHECK(cuStreamWaitEvent(st, h->ev_solve, 0));
   }
   return CUDA_SUCCESS;
 }
 
-/* the same for upper storage: the jb x rest block row P right of the diagonal block, W = P^H * inv(U11) (rest x jb):
- *     W_c = (P_c^H - W[:, 0:c] * U[0:c, c]) * inv(U_cc) */
-CUresult chol_panel_factor_solve_upper(int prec, size_t jb, size_t rest, CUdeviceptr Ajj, CUdeviceptr P, size_t lda, CUdeviceptr W,
-                                       size_t ldw, long *dinfo, long base, const chol_ws *w, CUstream st, CUevent before_solve) {
-  const size_t es = w->es, db = w->db, nb = w->nb, nblk = (jb + db - 1) / db;
-  if (!chol_panel_blocked() || nblk < 2 || w->Tp == 0) {
-    CU_ERROR_CHECK(chol_diag_factor_inverse(prec, 'U', jb, Ajj, lda, w->Xd, nb, dinfo, base, w, st));
-    if (before_solve) CU_ERROR_CHECK(cuStreamWaitEvent(st, before_solve, 0));
-    return chol_gemm(prec, 'C', 'N', rest, jb, jb, ONE, P, lda, w->Xd, nb, ZERO, 0, 0, W, ldw, st);
-  }
-  CU_ERROR_CHECK(chol_diag_factor_inverse_ex(prec, 'U', jb, Ajj, lda, w->Xd, nb, dinfo, base, w, st, 1));
-  if (before_solve) CU_ERROR_CHECK(cuStreamWaitEvent(st, before_solve, 0));
-  for (size_t c = 0; c < nblk; c++) {
-    const size_t i = c * db, ib = chol_min(db, jb - i);
-    const CUdeviceptr Pc = chol_at(P, lda, i, 0, es), Wc = chol_at(W, ldw, 0, i, es), Xcc = chol_at(w->Xd, nb, i, i, es);
-    if (c == 0) {
-      CU_ERROR_CHECK(chol_gemm(prec, 'C', 'N', rest, ib, ib, ONE, Pc, lda, Xcc, nb, ZERO, 0, 0, Wc, ldw, st));
-    } else {
-      RT_CHECK(chol_copy_launch(prec, 'C', 0, ib, rest, (const void *)Pc, lda, (void *)w->Tp, w->ldw, (void *)st)); /* T = P_c^H */
-      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'N', rest, ib, i, MONE, W, ldw, chol_at(Ajj, lda, 0, i, es), lda, ONE, w->Tp, w->ldw, w->Tp,
-                               w->ldw, st));
-      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'N', rest, ib, ib, ONE, w->Tp, w->ldw, Xcc, nb, ZERO, 0, 0, Wc, ldw, st));
-    }
-  }
-  return CUDA_SUCCESS;
+CUresult chol_panel_factor_solve_lower(CULAPACKhandle h, int prec, size_t jb, size_t rest, CUdeviceptr Ajj, CUdeviceptr P, size_t lda,
+                                       CUdeviceptr W, size_t ldw, long *dinfo, long base, const chol_ws *w, CUstream st,
+                                       CUevent before_solve) {
+  return panel_factor_solve(h, prec, 'L', jb, rest, Ajj, P, lda, W, ldw, dinfo, base, w, st, before_solve);
+}
+CUresult chol_panel_factor_solve_upper(CULAPACKhandle h, int prec, size_t jb, size_t rest, CUdeviceptr Ajj, CUdeviceptr P, size_t lda,
+                                       CUdeviceptr W, size_t ldw, long *dinfo, long base, const chol_ws *w, CUstream st,
+                                       CUevent before_solve) {
+  return panel_factor_solve(h, prec, 'U', jb, rest, Ajj, P, lda, W, ldw, dinfo, base, w, st, before_solve);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -301,13 +340,17 @@ static CUresult potrf_body(CULAPACKhandle h, int prec, int uplo, size_t n, CUdev
     look_pending = NULL;
     if (uplo == 'L') {
       const CUdeviceptr P = chol_at(A, lda, j + jb, j, es); /* rest x jb */
-      CU_ERROR_CHECK(chol_panel_factor_solve_lower(prec, jb, rest, Ajj, P, lda, W, w.ldw, dinfo, (long)j, &w, sp, before_solve));
+      CU_ERROR_CHECK(chol_panel_factor_solve_lower(h, prec, jb, rest, Ajj, P, lda, W, w.ldw, dinfo, (long)j, &w, sp, before_solve));
       RT_CHECK(chol_copy_launch(prec, 'N', 0, rest, jb, (const void *)W, w.ldw, (void *)P, lda, (void *)sp));
     } else {
       const CUdeviceptr P = chol_at(A, lda, j, j + jb, es); /* jb x rest; W = P^H * U11^-1 */
-      CU_ERROR_CHECK(chol_panel_factor_solve_upper(prec, jb, rest, Ajj, P, lda, W, w.ldw, dinfo, (long)j, &w, sp, before_solve));
+      CU_ERROR_CHECK(chol_panel_factor_solve_upper(h, prec, jb, rest, Ajj, P, lda, W, w.ldw, dinfo, (long)j, &w, sp, before_solve));
       RT_CHECK(chol_copy_launch(prec, 'C', 0, rest, jb, (const void *)W, w.ldw, (void *)P, lda, (void *)sp));
     }
+    /* s: the updates of this step run on the tensor cores - split W once into its TF32 (hi, lo) planes */
+    const bool tens = w.kp != 0 && rest >= 512 && jb >= 64;
+    const CUdeviceptr Whi = w.Whi[step & 1], Wlo = w.Wlo[step & 1];
+    if (tens) RT_CHECK(chol_tf32_split_launch(0, rest, jb, (const void *)W, w.ldw, (void *)Whi, (void *)Wlo, w.kp, (void *)sp));
     CU_ERROR_CHECK(cuEventRecord(h->ev_panel[step % CHOL_EVENT_RING], sp));
 
     /* --- trailing update  A22 -= W W^H, split into the next block column/row (look-ahead, panel
@@ -319,8 +362,13 @@ static CUresult potrf_body(CULAPACKhandle h, int prec, int uplo, size_t n, CUdev
       const CUdeviceptr A33 = chol_at(A, lda, j + jb + jb2, j + jb + jb2, es);
       const bool prof = h->profile && h->prof_n < h->prof_cap;
       if (prof) CU_ERROR_CHECK(cuEventRecord(h->prof_e0[h->prof_n], su));
-      CU_ERROR_CHECK(chol_gemm_ex(prec, 'N', 'C', 0, 0, 0, 0, uplo, herm, rest2, rest2, jb, MONE, W2, w.ldw, W2, w.ldw, ONE,
-                                  A33, lda, A33, lda, su));
+      if (tens) {
+        const CUdeviceptr H2 = Whi + (CUdeviceptr)(jb2 * w.kp * sizeof(float)), L2 = Wlo + (CUdeviceptr)(jb2 * w.kp * sizeof(float));
+        RT_CHECK(chol_tf32x3_gemm_launch(rest2, rest2, jb, -1.0, (const void *)H2, (const void *)L2, (const void *)H2, (const void *)L2,
+                                         w.kp, 1.0, (const void *)A33, lda, (void *)A33, lda, uplo, (void *)su));
+      } else
+        CU_ERROR_CHECK(chol_gemm_ex(prec, 'N', 'C', 0, 0, 0, 0, uplo, herm, rest2, rest2, jb, MONE, W2, w.ldw, W2, w.ldw, ONE,
+                                    A33, lda, A33, lda, su));
       if (prof) {
         CU_ERROR_CHECK(cuEventRecord(h->prof_e1[h->prof_n], su));
         h->prof_flops[h->prof_n++] = (double)rest2 * (double)(rest2 + 1) * (double)jb * (herm ? 4.0 : 1.0);
@@ -351,6 +399,10 @@ static CUresult potrf_body(CULAPACKhandle h, int prec, int uplo, size_t n, CUdev
         }
         look_pending = h->ev_look[step % CHOL_EVENT_RING];
         CU_ERROR_CHECK(cuEventRecord(look_pending, sl));
+      } else if (tens) { /* the same block column / block row on the tensor cores */
+        const size_t lm = uplo == 'L' ? rest : jb2, ln = uplo == 'L' ? jb2 : rest;
+        RT_CHECK(chol_tf32x3_gemm_launch(lm, ln, jb, -1.0, (const void *)Whi, (const void *)Wlo, (const void *)Whi, (const void *)Wlo,
+                                         w.kp, 1.0, (const void *)A22, lda, (void *)A22, lda, uplo, (void *)sp));
       } else if (uplo == 'L') /* rest x jb2 block column, lower part */
         CU_ERROR_CHECK(chol_gemm_ex(prec, 'N', 'C', 0, 0, 0, 0, 'L', herm, rest, jb2, jb, MONE, W, w.ldw, W, w.ldw, ONE, A22,
                                     lda, A22, lda, sp));
@@ -523,8 +575,14 @@ CUresult chol_potrs(CULAPACKhandle h, int prec, int uplo, size_t n, size_t nrhs,
 static CUresult logdet_body(CULAPACKhandle h, int prec, CUdeviceptr x, size_t incx, size_t n, void *result, CUstream stream) {
   const size_t rs = (prec == 's' || prec == 'c') ? 4 : 8;
   const CUdeviceptr dres = h->logdet_scr + (CUdeviceptr)chol_roundup(chol_logdet_scratch_bytes(), 16);
+  /* partials, ticket and result slot are one per handle (the reference allocates its temporary per call,
+   * lapack/dlogdet.c:37-74): a call on another stream first waits for the previous call's read-back */
+  if (h->logdet_in_use && h->logdet_stream != stream) CU_ERROR_CHECK(cuStreamWaitEvent(stream, h->logdet_done, 0));
   RT_CHECK(chol_logdet_launch(prec, (const void *)x, incx, n, (void *)dres, (void *)h->logdet_scr, (void *)stream));
   CU_ERROR_CHECK(cuMemcpyDtoHAsync(result, dres, rs, stream));
+  CU_ERROR_CHECK(cuEventRecord(h->logdet_done, stream));
+  h->logdet_stream = stream;
+  h->logdet_in_use = true;
   return CUDA_SUCCESS;
 }
 CUresult chol_logdet(CULAPACKhandle h, int prec, CUdeviceptr x, size_t incx, size_t n, void *result, CUstream stream) {
@@ -564,8 +622,9 @@ CUresult chol_logdet(CULAPACKhandle h, int prec, CUdeviceptr x, size_t incx, siz
                          CUdeviceptr B, size_t ldb, CUdeviceptr info, CUstream stream) {                             \
     (void)h;                                                                                                         \
     if (n > (size_t)chol_diag_max(p) || lda < n || ldb < n) return CUDA_ERROR_INVALID_VALUE;                         \
-    RT_CHECK(chol_trti2_launch(p, uplo, diag, n, (const void *)A, lda, (void *)B, ldb, 0, (long *)info, 0,           \
-                               (void *)stream));                                                                     \
+    /* info: device int, zeroed by the kernel itself on entry (the reference kernel's contract, dtrtri.cu:23-29) */  \
+    RT_CHECK(chol_trti2_launch(p, uplo, diag, n, (const void *)A, lda, (void *)B, ldb, CHOL_TRTI2_INFO_INT32,        \
+                               (long *)info, 0, (void *)stream));                                                    \
     return CUDA_SUCCESS;                                                                                             \
   }                                                                                                                  \
   CUresult cu##U##lauum(CULAPACKhandle h, CBlasUplo uplo, size_t n, CUdeviceptr A, size_t lda, long *info) {         \

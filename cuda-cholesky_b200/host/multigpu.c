@@ -434,7 +434,7 @@ static CUresult dist_potrf(chol_rank *R, int prec, size_t n, CUdeviceptr Aloc, s
       }
       if (rest) {
         const CUdeviceptr Pn = chol_at(Aloc, ldl, j + jb, lc * nb, es);
-        CU_ERROR_CHECK(chol_panel_factor_solve_lower(prec, jb, rest, Ajj, Pn, ldl, W, ldw, dinfo, (long)j, &w, sp, look_pending));
+        CU_ERROR_CHECK(chol_panel_factor_solve_lower(h, prec, jb, rest, Ajj, Pn, ldl, W, ldw, dinfo, (long)j, &w, sp, look_pending));
         look_pending = NULL;
       }
     }
@@ -837,11 +837,12 @@ static CUresult rank_potrf_prepare_task(const void *argp) {
   return CUDA_SUCCESS;
 }
 
-/* CHOL_MGPU_H2D_OVERLAP=1: start factoring while the block columns are still being uploaded
- * (lower, page-locked host memory).  Off by default until it has been measured on hardware. */
+/* start factoring while the block columns are still being uploaded (lower, page-locked host memory).
+ * Measured on B200 (profiles/r02_staged_ab.txt): e2e dpotrf N = 65536 30.36 -> 31.65 TFLOP/s.
+ * CHOL_MGPU_H2D_OVERLAP=0 turns it off for A/B runs. */
 static bool h2d_overlap_enabled(void) {
   const char *e = getenv("CHOL_MGPU_H2D_OVERLAP");
-  return e != NULL && atoi(e) != 0;
+  return e == NULL || atoi(e) != 0;
 }
 
 /* number of leading steps whose update must be split by upload group: those that can start before

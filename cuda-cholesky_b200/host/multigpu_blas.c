@@ -123,13 +123,11 @@ static CUresult mb_task(const void *argp) {
       TRY(chol_gemm_ex(prec, oa, ob, 0, 0, 0, 0, a->uplo, herm, ns, ns, k, a->alpha, AROW(lo), lA, AROW(lo), lA, a->beta,
                        chol_at(dC, lC, lo, 0, es), lC, chol_at(dC, lC, lo, 0, es), lC, st));
 #undef AROW
-      /* download: rectangle + the diagonal square's own triangle (column by column keeps the
-       * caller's other triangle untouched) */
+      /* download: rectangle + the diagonal square.  The whole square (both triangles) was uploaded and the
+       * cuplo-masked GEMM never writes the other triangle, so one 2-D copy returns the caller's other triangle
+       * bit-identical (the argument the POTRF gather already uses) - no per-column copies. */
       if (rect_rows) TRY(d2h(a->C + (lo * a->ldc + rect_r0) * es, a->ldc, chol_at(dC, lC, rect_r0, 0, es), lC, rect_rows, ns, es, st));
-      for (size_t c = 0; c < ns && e == CUDA_SUCCESS; c++) {
-        const size_t rr0 = a->uplo == 'L' ? lo + c : lo, cnt = a->uplo == 'L' ? ns - c : c + 1;
-        e = cuMemcpyDtoHAsync(a->C + ((lo + c) * a->ldc + rr0) * es, chol_at(dC, lC, rr0, c, es), cnt * es, st);
-      }
+      TRY(d2h(a->C + (lo * a->ldc + lo) * es, a->ldc, chol_at(dC, lC, lo, 0, es), lC, ns, ns, es, st));
       break;
     }
     case OP_TRMM:
@@ -235,9 +233,14 @@ static const double ONE[2] = {1.0, 0.0};
 static const double ZERO[2] = {0.0, 0.0};
 static const double MONE[2] = {-1.0, 0.0};
 
-int chol_inverse_slabs_enabled(void) {
+/* cuMultiGPU*{trtri,lauum,potri}: split by output slab over all GPUs when there is more than one (with one GPU
+ * the plain single-GPU routine on a staged copy does the same work with fewer transfers).
+ * CHOL_MGPU_INVERSE=slab / staged forces either form (tests, A/B runs). */
+int chol_inverse_slabs_enabled(CUmultiGPU m) {
   const char *e = getenv("CHOL_MGPU_INVERSE");
-  return e != NULL && strcmp(e, "slab") == 0;
+  if (e != NULL && strcmp(e, "slab") == 0) return 1;
+  if (e != NULL && strcmp(e, "staged") == 0) return 0;
+  return m != NULL && cuMultiGPUGetContextCount(m) > 1;
 }
 
 /* cost profile over the split dimension: 0 -> (n-x)^2, 1 -> x^2, 2 -> x (n-x) */
@@ -273,6 +276,10 @@ static CUresult inv_upload(inv_slab *a, CUstream st) {
       const size_t r0 = a->uplo == 'L' ? c0 : 0, rows = a->uplo == 'L' ? s - c0 : c0 + cb;
       CU_ERROR_CHECK(h2d(a->A + ((o + c0) * a->lda + o + r0) * es, a->lda, chol_at(a->dT, ldt, r0, c0, es), ldt, rows, cb, es, st));
     }
+    /* the slab's own w x w diagonal block with BOTH triangles: its result goes back as one 2-D copy of the whole
+     * square (the in-place inverse never writes the other triangle, so the caller gets those bits back unchanged) */
+    const size_t d0 = a->uplo == 'L' ? 0 : lo;
+    CU_ERROR_CHECK(h2d(a->A + (lo * a->lda + lo) * es, a->lda, chol_at(a->dT, ldt, d0, d0, es), ldt, w, w, es, st));
     const size_t r = s - w;
     if (r) CU_ERROR_CHECK(cuMemAlloc(&a->dY, chol_roundup(r, 16) * w * es));
   } else { /* LAUUM: lower R = A[lo:n, 0:hi) (k x hi), upper R = A[0:hi, lo:n) (hi x k) */
@@ -282,18 +289,19 @@ static CUresult inv_upload(inv_slab *a, CUstream st) {
     CU_ERROR_CHECK(h2d(a->uplo == 'L' ? a->A + lo * es : a->A + lo * a->lda * es, a->lda, a->dT, ldr, rows, cols, es, st));
     if (lo) CU_ERROR_CHECK(cuMemAlloc(&a->dY, chol_roundup(a->uplo == 'L' ? w : lo, 16) * (a->uplo == 'L' ? lo : w) * es));
     CU_ERROR_CHECK(cuMemAlloc(&a->dD, chol_roundup(w, 16) * w * es));
+    /* the product block starts as the caller's square: the masked HERK writes its own triangle only, and the whole
+     * square is downloaded with one copy */
+    CU_ERROR_CHECK(h2d(a->A + (lo * a->lda + lo) * es, a->lda, a->dD, chol_roundup(w, 16), w, w, es, st));
   }
   return CUDA_SUCCESS;
 }
 
-/* the uplo triangle (diagonal included) of a w x w device block -> the caller's matrix */
+/* the w x w diagonal block of a slab -> the caller's matrix.  The device copy holds the caller's other triangle
+ * (uploaded with the slab, never written by the triangle-masked kernels), so ONE 2-D copy of the whole square
+ * returns the result and leaves the other triangle bit-identical - instead of one small copy per column. */
 static CUresult inv_download_triangle(const inv_slab *a, CUdeviceptr D, size_t ldd, CUstream st) {
   const size_t es = chol_esize(a->prec), lo = a->lo, w = a->hi - a->lo;
-  for (size_t c = 0; c < w; c++) {
-    const size_t r0 = a->uplo == 'L' ? c : 0, cnt = a->uplo == 'L' ? w - c : c + 1;
-    CU_ERROR_CHECK(cuMemcpyDtoHAsync(a->A + ((lo + c) * a->lda + lo + r0) * es, chol_at(D, ldd, r0, c, es), cnt * es, st));
-  }
-  return CUDA_SUCCESS;
+  return d2h(a->A + (lo * a->lda + lo) * es, a->lda, D, ldd, w, w, es, st);
 }
 
 static CUresult inv_compute(inv_slab *a, CUstream st) {
@@ -504,7 +512,7 @@ CUresult chol_mgpu_inverse_slabs(CUmultiGPU m, int op, int prec, int uplo, int d
     if (n == 0) return CUDA_SUCCESS;                                                                                   \
     mb_args a;                                                                                                         \
     memset(&a, 0, sizeof a);                                                                                           \
-    if (chol_inverse_slabs_enabled())                                                                                  \
+    if (chol_inverse_slabs_enabled(chol_mgpu_of_lapack(h)))                                                                                  \
       return chol_mgpu_inverse_slabs(chol_mgpu_of_lapack(h), OP_TRTRI, p, uplo, diag, n, A, lda, info);                \
     a.op = OP_TRTRI; a.prec = p; a.uplo = uplo; a.diag = diag; a.n = n;                                                \
     a.A = (const char *)A; a.lda = lda; a.C = (char *)A; a.ldc = lda;                                                  \
@@ -519,7 +527,7 @@ CUresult chol_mgpu_inverse_slabs(CUmultiGPU m, int op, int prec, int uplo, int d
     if (n == 0) return CUDA_SUCCESS;                                                                                   \
     mb_args a;                                                                                                         \
     memset(&a, 0, sizeof a);                                                                                           \
-    if (chol_inverse_slabs_enabled())                                                                                  \
+    if (chol_inverse_slabs_enabled(chol_mgpu_of_lapack(h)))                                                                                  \
       return chol_mgpu_inverse_slabs(chol_mgpu_of_lapack(h), OP_LAUUM, p, uplo, 'N', n, A, lda, info);                 \
     a.op = OP_LAUUM; a.prec = p; a.uplo = uplo; a.n = n;                                                               \
     a.A = (const char *)A; a.lda = lda; a.C = (char *)A; a.ldc = lda;                                                  \
@@ -534,7 +542,7 @@ CUresult chol_mgpu_inverse_slabs(CUmultiGPU m, int op, int prec, int uplo, int d
     if (n == 0) return CUDA_SUCCESS;                                                                                   \
     mb_args a;                                                                                                         \
     memset(&a, 0, sizeof a);                                                                                           \
-    if (chol_inverse_slabs_enabled())                                                                                  \
+    if (chol_inverse_slabs_enabled(chol_mgpu_of_lapack(h)))                                                                                  \
       return chol_mgpu_inverse_slabs(chol_mgpu_of_lapack(h), OP_POTRI, p, uplo, 'N', n, A, lda, info);                 \
     a.op = OP_POTRI; a.prec = p; a.uplo = uplo; a.n = n;                                                               \
     a.A = (const char *)A; a.lda = lda; a.C = (char *)A; a.ldc = lda;                                                  \

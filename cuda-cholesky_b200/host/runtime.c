@@ -128,11 +128,17 @@ CUresult cuLAPACKCreate(CULAPACKhandle *handle) {
     if (e == CUDA_SUCCESS) e = cuEventCreate(&h->ev_rest[i], CU_EVENT_DISABLE_TIMING);
     if (e == CUDA_SUCCESS) e = cuEventCreate(&h->ev_look[i], CU_EVENT_DISABLE_TIMING);
   }
+  for (int i = 0; i < CHOL_DIAG_EVENTS && e == CUDA_SUCCESS; i++) {
+    e = cuEventCreate(&h->ev_dx[i], CU_EVENT_DISABLE_TIMING);
+    if (e == CUDA_SUCCESS) e = cuEventCreate(&h->ev_dcol[i], CU_EVENT_DISABLE_TIMING);
+  }
+  if (e == CUDA_SUCCESS) e = cuEventCreate(&h->ev_solve, CU_EVENT_DISABLE_TIMING);
   if (e == CUDA_SUCCESS) e = cuMemAlloc(&h->dinfo, sizeof(long));
   if (e == CUDA_SUCCESS) e = cuMemAllocHost((void **)&h->hinfo, sizeof(long));
   if (e == CUDA_SUCCESS) e = cuMemAlloc(&h->logdet_scr, chol_logdet_scratch_bytes() + 64);
   if (e == CUDA_SUCCESS) e = cuMemsetD8(h->logdet_scr, 0, chol_logdet_scratch_bytes() + 64);
   if (e == CUDA_SUCCESS) e = cuMemAllocHost(&h->hlogdet, 16);
+  if (e == CUDA_SUCCESS) e = cuEventCreate(&h->logdet_done, CU_EVENT_DISABLE_TIMING);
   if (e != CUDA_SUCCESS) {
     cuLAPACKDestroy(h);
     CU_ERROR_CHECK(e);
@@ -153,11 +159,17 @@ CUresult cuLAPACKDestroy(CULAPACKhandle h) {
       if (h->ev_rest[i]) cuEventDestroy(h->ev_rest[i]);
       if (h->ev_look[i]) cuEventDestroy(h->ev_look[i]);
     }
+    for (int i = 0; i < CHOL_DIAG_EVENTS; i++) {
+      if (h->ev_dx[i]) cuEventDestroy(h->ev_dx[i]);
+      if (h->ev_dcol[i]) cuEventDestroy(h->ev_dcol[i]);
+    }
+    if (h->ev_solve) cuEventDestroy(h->ev_solve);
     if (h->ws) cuMemFree(h->ws);
     if (h->dinfo) cuMemFree(h->dinfo);
     if (h->hinfo) cuMemFreeHost(h->hinfo);
     if (h->logdet_scr) cuMemFree(h->logdet_scr);
     if (h->hlogdet) cuMemFreeHost(h->hlogdet);
+    if (h->logdet_done) cuEventDestroy(h->logdet_done);
     for (int i = 0; i < h->prof_cap; i++) {
       cuEventDestroy(h->prof_e0[i]);
       cuEventDestroy(h->prof_e1[i]);

@@ -37,7 +37,9 @@ CUresult cuSpotrf(CULAPACKhandle, CBlasUplo, size_t n, CUdeviceptr A, size_t lda
 /* A := A^-1 for triangular A, in place (lapack/strtri.c cuStrtri) */
 CUresult cuStrtri(CULAPACKhandle, CBlasUplo, CBlasDiag, size_t n, CUdeviceptr A, size_t lda, long *info);
 /* unblocked out-of-place inverse of one small block (n <= 128; 64 for z): B_tri := A_tri^-1; the
- * info argument is a DEVICE pointer to a long, as in the reference (lapack.h:91-98) */
+ * info argument is a DEVICE pointer to a 32-bit int which the kernel sets to 0 on entry and to the
+ * 1-based column of a zero pivot, as the reference's kernel does (lapack.h:91-98, lapack/dtrtri.cu:23-29);
+ * it need not be initialised */
 CUresult cuStrti22(CULAPACKhandle, CBlasUplo, CBlasDiag, size_t n, CUdeviceptr A, size_t lda,
                  CUdeviceptr B, size_t ldb, CUdeviceptr info, CUstream);
 #define cuStrti2(handle, uplo, diag, n, A, lda, info) cuStrti22(handle, uplo, diag, n, A, lda, A, lda, info, 0)
@@ -55,7 +57,9 @@ CUresult cuDpotrf(CULAPACKhandle, CBlasUplo, size_t n, CUdeviceptr A, size_t lda
 /* A := A^-1 for triangular A, in place (lapack/dtrtri.c cuDtrtri) */
 CUresult cuDtrtri(CULAPACKhandle, CBlasUplo, CBlasDiag, size_t n, CUdeviceptr A, size_t lda, long *info);
 /* unblocked out-of-place inverse of one small block (n <= 128; 64 for z): B_tri := A_tri^-1; the
- * info argument is a DEVICE pointer to a long, as in the reference (lapack.h:91-98) */
+ * info argument is a DEVICE pointer to a 32-bit int which the kernel sets to 0 on entry and to the
+ * 1-based column of a zero pivot, as the reference's kernel does (lapack.h:91-98, lapack/dtrtri.cu:23-29);
+ * it need not be initialised */
 CUresult cuDtrti22(CULAPACKhandle, CBlasUplo, CBlasDiag, size_t n, CUdeviceptr A, size_t lda,
                  CUdeviceptr B, size_t ldb, CUdeviceptr info, CUstream);
 #define cuDtrti2(handle, uplo, diag, n, A, lda, info) cuDtrti22(handle, uplo, diag, n, A, lda, A, lda, info, 0)
@@ -73,7 +77,9 @@ CUresult cuCpotrf(CULAPACKhandle, CBlasUplo, size_t n, CUdeviceptr A, size_t lda
 /* A := A^-1 for triangular A, in place (lapack/ctrtri.c cuCtrtri) */
 CUresult cuCtrtri(CULAPACKhandle, CBlasUplo, CBlasDiag, size_t n, CUdeviceptr A, size_t lda, long *info);
 /* unblocked out-of-place inverse of one small block (n <= 128; 64 for z): B_tri := A_tri^-1; the
- * info argument is a DEVICE pointer to a long, as in the reference (lapack.h:91-98) */
+ * info argument is a DEVICE pointer to a 32-bit int which the kernel sets to 0 on entry and to the
+ * 1-based column of a zero pivot, as the reference's kernel does (lapack.h:91-98, lapack/dtrtri.cu:23-29);
+ * it need not be initialised */
 CUresult cuCtrti22(CULAPACKhandle, CBlasUplo, CBlasDiag, size_t n, CUdeviceptr A, size_t lda,
                  CUdeviceptr B, size_t ldb, CUdeviceptr info, CUstream);
 #define cuCtrti2(handle, uplo, diag, n, A, lda, info) cuCtrti22(handle, uplo, diag, n, A, lda, A, lda, info, 0)
@@ -91,7 +97,9 @@ CUresult cuZpotrf(CULAPACKhandle, CBlasUplo, size_t n, CUdeviceptr A, size_t lda
 /* A := A^-1 for triangular A, in place (lapack/ztrtri.c cuZtrtri) */
 CUresult cuZtrtri(CULAPACKhandle, CBlasUplo, CBlasDiag, size_t n, CUdeviceptr A, size_t lda, long *info);
 /* unblocked out-of-place inverse of one small block (n <= 128; 64 for z): B_tri := A_tri^-1; the
- * info argument is a DEVICE pointer to a long, as in the reference (lapack.h:91-98) */
+ * info argument is a DEVICE pointer to a 32-bit int which the kernel sets to 0 on entry and to the
+ * 1-based column of a zero pivot, as the reference's kernel does (lapack.h:91-98, lapack/dtrtri.cu:23-29);
+ * it need not be initialised */
 CUresult cuZtrti22(CULAPACKhandle, CBlasUplo, CBlasDiag, size_t n, CUdeviceptr A, size_t lda,
                  CUdeviceptr B, size_t ldb, CUdeviceptr info, CUstream);
 #define cuZtrti2(handle, uplo, diag, n, A, lda, info) cuZtrti22(handle, uplo, diag, n, A, lda, A, lda, info, 0)

@@ -55,7 +55,7 @@ if "cfg1" in which:
     del A0, A, Lt, R
 if "cfg2" in which:
     n = 32768
-    for p in "scz":
+    for p in os.environ.get("CFG2_PRECS", "scz"):
         A0 = spd(p, n)  # Hermitian; a row-major Hermitian matrix read column-major is its conjugate = still HPD
         best = 1e9
         for _ in range(2):
@@ -99,4 +99,4 @@ if "cfg3" in which:
     print("dpotrf+dpotri L N=%d: potrf %.3f s (%.2f TF/s), potri %.3f s (%.2f TF/s), |A*Ainv-I|max(lead 8192 rows) %.2e, logdet relerr %.1e"
           % (n, t_potrf, n ** 3 / 3 / t_potrf / 1e12, t_potri, 2 * n ** 3 / 3 / t_potri / 1e12, chk, abs(ld - want) / abs(want)), flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(out, open(os.path.join(ROOT, "gpurun_out", "configs_bench.json"), "w"), indent=1)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", os.environ.get("CFG_OUT", "configs_bench.json")), "w"), indent=1)

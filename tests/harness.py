@@ -254,18 +254,3 @@ def tri(A, uplo):
 
 def eps(p):
     return float(np.finfo(PREC[p]["real"]).eps)
-
-
-# ---------------------------------------------------------------------------------------------
-# Code paths written after the round's GPU budget was spent are off by default in the library
-# (environment switches) or are new entry points; their GPU tests run only on request, so that the
-# next GPU session can verify them in one go and then drop the marker:
-#     CHOL_TEST_STAGED=1 python -m pytest tests -m gpu -k staged
-# ---------------------------------------------------------------------------------------------
-try:  # bench.py and smoke() import this module too; they do not need pytest
-    import pytest  # noqa: E402
-
-    staged = pytest.mark.skipif(os.environ.get("CHOL_TEST_STAGED") != "1",
-                                reason="not yet verified on hardware; CHOL_TEST_STAGED=1 runs it")
-except ImportError:  # pragma: no cover
-    staged = None

@@ -150,15 +150,22 @@ int potf2_t(bool upper, size_t n, T *A, size_t lda, long *dinfo, long base, T *X
 
 template <typename T>
 int trti2_t(bool upper, bool unit, size_t n, const T *A, size_t lda, T *B, size_t ldb, int zero_other, long *dinfo, long base) {
-  if (*dinfo != 0) return 0;
+  const int info_mode = zero_other & 6;  // csrc/chol_kernels.h: 0 sticky long, 2 self-zeroed int, 4 none (Inf on a zero pivot)
+  zero_other &= 1;
+  if (info_mode == 0 && *dinfo != 0) return 0;
+  if (info_mode == 2) *reinterpret_cast<int *>(dinfo) = 0;
   std::vector<T> L(n * n, T(0));  // lower form WITHOUT conjugation: inv(U) = (inv(U^T))^T
   for (size_t c = 0; c < n; ++c)
     for (size_t i = c; i < n; ++i) L[i + c * n] = upper ? A[c + i * lda] : A[i + c * lda];
-  if (!unit) {
+  if (!unit && info_mode != 4) {
     long lo = -1, hi = -1;
     for (size_t i = 0; i < n; ++i)
       if (L[i + i * n] == T(0)) { if (lo < 0) lo = (long)i; hi = (long)i; }
-    if (hi >= 0) { *dinfo = base + (upper ? lo : hi) + 1; return 0; }  // the reference's sweep direction
+    if (hi >= 0) {  // the reference's sweep direction
+      const long v = base + (upper ? lo : hi) + 1;
+      if (info_mode == 2) *reinterpret_cast<int *>(dinfo) = (int)v; else *dinfo = v;
+      return 0;
+    }
   }
   for (size_t j = 0; j < n; ++j) {
     std::vector<T> x(n, T(0));
@@ -279,6 +286,46 @@ int chol_fill_launch(int prec, int uplo, size_t m, size_t n, double re_, double 
       case 'c': fill_t<std::complex<float>>(uplo, m, n, std::complex<float>((float)re_, (float)im_), (std::complex<float> *)A, lda); break;
       case 'z': fill_t<std::complex<double>>(uplo, m, n, std::complex<double>(re_, im_), (std::complex<double> *)A, lda); break;
     }
+  });
+}
+// the s-precision tensor-core engine (csrc/gemm_tf32x3.cu) from its documented semantics: the planes carry
+// hi = x rounded to 11 significant bits, lo = x - hi; the product is hi*hi + hi*lo + lo*hi in FP32
+size_t chol_tf32_kpitch(size_t k) { return (k + 31) / 32 * 32; }
+static float mock_tf32(float x) {
+  uint32_t u;
+  std::memcpy(&u, &x, 4);
+  u = (u + 0x1000u) & 0xffffe000u;  // round to nearest (ties away), 10 explicit mantissa bits
+  std::memcpy(&x, &u, 4);
+  return x;
+}
+int chol_tf32_split_launch(int trans, size_t rows, size_t k, const void *A, size_t lda, void *hi, void *lo, size_t kp, void *st) {
+  __sync_fetch_and_add(&launches, 1);
+  return enqueue(st, [=] {
+    const float *a = (const float *)A;
+    float *h = (float *)hi, *l = (float *)lo;
+    for (size_t r = 0; r < rows; ++r)
+      for (size_t c = 0; c < kp; ++c) {
+        const float x = c < k ? (trans ? a[r * lda + c] : a[c * lda + r]) : 0.f;
+        h[r * kp + c] = mock_tf32(x);
+        l[r * kp + c] = mock_tf32(x - h[r * kp + c]);
+      }
+  });
+}
+int chol_tf32x3_gemm_launch(size_t m, size_t n, size_t k, double alpha, const void *Ahi, const void *Alo, const void *Bhi, const void *Blo,
+                            size_t kp, double beta, const void *C, size_t ldc, void *D, size_t ldd, int cuplo, void *st) {
+  __sync_fetch_and_add(&launches, 1);
+  return enqueue(st, [=] {
+    const float *ah = (const float *)Ahi, *al = (const float *)Alo, *bh = (const float *)Bhi, *bl = (const float *)Blo;
+    const float *c = (const float *)C;
+    float *d = (float *)D;
+    for (size_t j = 0; j < n; ++j)
+      for (size_t i = 0; i < m; ++i) {
+        if ((cuplo == 'L' && i < j) || (cuplo == 'U' && i > j)) continue;
+        float acc = 0.f;
+        for (size_t q = 0; q < k; ++q)
+          acc += al[i * kp + q] * bh[j * kp + q] + ah[i * kp + q] * bl[j * kp + q] + ah[i * kp + q] * bh[j * kp + q];
+        d[j * ldd + i] = (float)alpha * acc + (beta != 0.0 ? (float)beta * c[j * ldc + i] : 0.f);
+      }
   });
 }
 int chol_logdet_launch(int prec, const void *x, size_t incx, size_t n, void *dresult, void *, void *st) {

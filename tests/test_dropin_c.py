@@ -63,8 +63,7 @@ def test_multigpu_unit_program_compiles_and_links(tmp_path):
 
 
 @pytest.mark.gpu
-@H.staged
-def test_staged_multigpu_unit_program_runs_on_gpu(tmp_path):
+def test_multigpu_unit_program_runs_on_gpu(tmp_path):
     """reference test/multigpu/cumultigpu.c + cutask.c semantics from C, on every visible device"""
     exe = str(tmp_path / "mgpu_unit")
     _build(exe, SRC_MGPU)

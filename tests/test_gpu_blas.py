@@ -163,6 +163,31 @@ def test_trmm2_trmm_trsm(blas, p, m, n):
             assert np.abs(got - want).max() <= 64 * na * H.eps(p) * np.abs(want).max(), ("trsm", side, uplo, trans, diag)
 
 
+@pytest.mark.parametrize("p", "ds")
+def test_trsm_singular_operand_gives_non_finite_like_the_blas(blas, p):
+    """A zero on the triangular operand's diagonal: the reference's substitution TRSM (blas/dtrsm.c) divides by
+    it and returns Inf/NaN.  The inverse-based TRSM here must not return finite garbage instead, and one
+    singular 128-block must not disable the blocks after it (the later, unaffected rows stay correct)."""
+    m, n = 300, 40
+    T0 = H.spd_matrix(p, m, seed=6, k=16)
+    ORA.potrf(p, "L", T0)
+    T0 = np.tril(T0).copy(order="F")
+    Tm = T0.copy(order="F")
+    Tm[150, 150] = 0.0  # inside the second 128-block
+    B0 = H.rand_matrix(p, m, n, seed=7, ld=m + 1)
+    want = B0.copy(order="F")
+    ORA.trsm(p, "L", "L", "N", "N", m, n, 1.0, Tm, want)
+    dT, ldt = G.to_dev(Tm)
+    dB, ldb = G.to_dev(B0)
+    blas.trsm(p, "L", "L", "N", "N", m, n, 1.0, dT.data_ptr(), ldt, dB.data_ptr(), ldb)
+    G.sync()
+    got = G.to_host(dB, m)
+    assert not np.isfinite(want[150:]).all()  # the oracle's own result is Inf/NaN from the singular row on
+    assert not np.isfinite(got[150:]).all(), "singular TRSM returned finite values"
+    # rows before the singular block row depend on nothing singular (forward substitution): still exact
+    assert np.abs(got[:128] - want[:128]).max() <= 64 * m * H.eps(p) * np.abs(want[:128]).max()
+
+
 def test_blas_argument_errors(blas):
     G.chol.set_xerbla_silent()
     d = torch.zeros(64, dtype=torch.float64, device="cuda").data_ptr()

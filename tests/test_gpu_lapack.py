@@ -138,11 +138,20 @@ def test_trtri_singular_info_and_trti22(lapack, p, uplo):
     ORA.trtri(p, uplo, "N", wantb)
     dB, ldb = G.to_dev(Bm)
     dX = torch.zeros_like(dB)
-    dinfo = torch.zeros(1, dtype=torch.int64, device="cuda")
+    # the reference's contract (lapack/dtrtri.cu:23-29): info is a device *int* the kernel zeroes itself -
+    # neither 8 bytes wide nor pre-zeroed; the guard word behind it must survive
+    dinfo = torch.full((2,), 0x5A5A5A5A, dtype=torch.int32, device="cuda")
     lapack.trti22(p, uplo, "N", nb, dB.data_ptr(), ldb, dX.data_ptr(), ldb, dinfo.data_ptr())
     G.sync()
-    assert int(dinfo.item()) == 0
+    assert dinfo.tolist() == [0, 0x5A5A5A5A]
     assert np.abs(H.tri(G.to_host(dX, nb), uplo) - H.tri(wantb, uplo)).max() <= elem_tol(p, nb) * np.abs(wantb).max()
+    # zero pivots: the first one the reference's sweep meets (bottom-up for lower, top-down for upper)
+    Bm[10, 10] = 0
+    Bm[40, 40] = 0
+    dB, ldb = G.to_dev(Bm)
+    lapack.trti22(p, uplo, "N", nb, dB.data_ptr(), ldb, dX.data_ptr(), ldb, dinfo.data_ptr())
+    G.sync()
+    assert dinfo.tolist() == [41 if uplo == "L" else 11, 0x5A5A5A5A]
 
 
 @pytest.mark.parametrize("p", "dzsc")
@@ -221,11 +230,10 @@ def test_potrf_full_elementwise_vs_oracle_mid_size(lapack, p, uplo, n):
     assert err <= elem_tol(p, n), err
 
 
-@H.staged
 @pytest.mark.parametrize("p", "dzsc")
 @pytest.mark.parametrize("uplo", "LU")
 @pytest.mark.parametrize("n,nrhs", [(1, 1), (100, 7), (300, 64), (700, 130)])
-def test_staged_potrs_solves_the_system(lapack, p, uplo, n, nrhs):
+def test_potrs_solves_the_system(lapack, p, uplo, n, nrhs):
     """cu*potrs (extension): X from the GPU factor against the oracle's two triangular solves on the
     oracle's factor, and the residual ||A X - B|| / (||A|| ||X||)."""
     A0 = H.spd_matrix(p, n, k=min(n, 64))
@@ -247,8 +255,7 @@ def test_staged_potrs_solves_the_system(lapack, p, uplo, n, nrhs):
     assert np.linalg.norm(R) <= 16 * n * H.eps(p) * np.linalg.norm(A0) * np.linalg.norm(got)
 
 
-@H.staged
-def test_staged_potrs_argument_errors(lapack):
+def test_potrs_argument_errors(lapack):
     G.chol.set_xerbla_silent()
     A = H.spd_matrix("d", 8)
     dA, lda = G.to_dev(A)
@@ -257,11 +264,10 @@ def test_staged_potrs_argument_errors(lapack):
     assert lapack.potrs("d", "L", 0, 3, dA.data_ptr(), lda, dA.data_ptr(), lda) == 0
 
 
-@H.staged
 @pytest.mark.parametrize("p", "dzsc")
 @pytest.mark.parametrize("uplo", "LU")
 @pytest.mark.parametrize("n", [2, 64, 300, 1000])
-def test_staged_reference_test_inputs_latmc(lapack, p, uplo, n):
+def test_reference_test_inputs_latmc(lapack, p, uplo, n):
     """The reference's LAPACK tests factor latmc(n, c = 2) after srand(0) and check `info` only
     (test/lapack/dpotrf.c:56-67): same inputs here, info AND values, for the whole chain
     potrf -> trtri / lauum / potri -> logdet."""

@@ -61,13 +61,11 @@ def test_multigpu_potrf_pinned_host_overlapped_gather(mgpu, uplo):
     assert np.array_equal(other, other0)
 
 
-staged = H.staged
 
 
-@staged
 @pytest.mark.parametrize("gbps", ["50", "0.0001"])
 @pytest.mark.parametrize("n", [700, 1500, 3000])
-def test_staged_multigpu_potrf_upload_overlap(mgpu, n, gbps, monkeypatch):
+def test_multigpu_potrf_upload_overlap(mgpu, n, gbps, monkeypatch):
     """CHOL_MGPU_H2D_OVERLAP=1: the factorisation starts while block columns are still being
     uploaded; a tiny assumed PCIe rate forces EVERY step through the group-by-group update."""
     monkeypatch.setenv("CHOL_MGPU_H2D_OVERLAP", "1")
@@ -83,11 +81,10 @@ def test_staged_multigpu_potrf_upload_overlap(mgpu, n, gbps, monkeypatch):
     assert np.array_equal(np.triu(got, 1), np.triu(A, 1))
 
 
-@staged
 @pytest.mark.parametrize("p", "dzs")
 @pytest.mark.parametrize("uplo", "LU")
 @pytest.mark.parametrize("n,slabs", [(400, 1), (400, 3), (1500, 4)])
-def test_staged_multigpu_inverse_slabs(mgpu, p, uplo, n, slabs, monkeypatch):
+def test_multigpu_inverse_slabs(mgpu, p, uplo, n, slabs, monkeypatch):
     """CHOL_MGPU_INVERSE=slab: TRTRI / LAUUM / POTRI split into independent slabs (several per GPU
     here, so one GPU exercises the slab algebra) against the oracle, other triangle untouched."""
     monkeypatch.setenv("CHOL_MGPU_INVERSE", "slab")
@@ -113,9 +110,8 @@ def test_staged_multigpu_inverse_slabs(mgpu, p, uplo, n, slabs, monkeypatch):
         assert np.array_equal(other, other0), (name, diag)
 
 
-@staged
 @pytest.mark.parametrize("uplo", "LU")
-def test_staged_multigpu_inverse_slabs_zero_pivot(mgpu, uplo, monkeypatch):
+def test_multigpu_inverse_slabs_zero_pivot(mgpu, uplo, monkeypatch):
     monkeypatch.setenv("CHOL_MGPU_INVERSE", "slab")
     monkeypatch.setenv("CHOL_MGPU_INVERSE_SLABS", "3")
     n = 600
