@@ -36,8 +36,9 @@ def flops_potrf(p, n):
 
 
 which = sys.argv[1:] or ["cfg1", "cfg2", "cfg3"]
-if "cfg1" in which:
-    n = 16384
+for cfg, n in (("cfg0", 8192), ("cfg1", 16384)):
+    if cfg not in which:
+        continue
     A0 = spd("d", n)
     for uplo in "LU":
         best = 1e9

@@ -9,6 +9,7 @@
 #include <functional>
 #include <vector>
 
+#include <cstdint>
 #include "../../cuda-cholesky_b200/csrc/chol_kernels.h"
 
 extern "C" void mock_stream_enqueue(void *stream, void (*fn)(void *), void *arg);  // mock_cuda.c
