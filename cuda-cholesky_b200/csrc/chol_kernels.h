@@ -59,6 +59,16 @@ int chol_tf32x3_gemm_launch(size_t m, size_t n, size_t k, double alpha, const vo
                             const void *Blo, size_t kp, double beta, const void *C, size_t ldc, void *D, size_t ldd, int cuplo,
                             void *stream);
 
+/* c-precision: the same engine on the real embedding of the complex product.  chol_tf32_split_c_launch writes, for a
+ * complex operand W (rows x k, column-major), planes of 2*rows rows and pitch kp = chol_tf32_kpitch(2*k) floats:
+ * plane row 2i = (Re, Im) pairs of W's row i, plane row 2i+1 = (Im, -Re) pairs.  chol_tf32x3_herk_launch computes
+ * D (m x n complex) = alpha * A * B^H + beta * C (real alpha, beta; cuplo on complex indices; herm != 0: Im(diag) = 0)
+ * where Ahi/Alo point at the plane row of A's first row (2 * i0 * kp floats into the planes) and Bhi/Blo likewise. */
+int chol_tf32_split_c_launch(size_t rows, size_t k, const void *W, size_t ldw, void *hi, void *lo, size_t kp, void *stream);
+int chol_tf32x3_herk_launch(size_t m, size_t n, size_t k, double alpha, const void *Ahi, const void *Alo, const void *Bhi,
+                            const void *Blo, size_t kp, double beta, const void *C, size_t ldc, void *D, size_t ldd, int cuplo,
+                            int herm, void *stream);
+
 /* ---- diagonal-block kernels: one CTA, block staged in shared memory (n <= CHOL_DIAG_MAX) ---- */
 #define CHOL_DIAG_MAX 128
 int chol_diag_max(int prec); /* largest n the one-CTA diagonal kernels accept: 128 (s,d,c), 64 (z) */
@@ -66,10 +76,13 @@ int chol_diag_max(int prec); /* largest n the one-CTA diagonal kernels accept: 1
  * info_base + failing column (1-based) if it is still 0 and a pivot is <= 0 or NaN; when
  * *dinfo != 0 on entry the kernel does nothing (lapack/dpotrf.c:70-73 semantics). */
 int chol_potf2_launch(int prec, int uplo, size_t n, void *A, size_t lda, long *dinfo, long info_base, void *stream);
-/* fused: Cholesky of the block in place AND X := inverse of the factor (uplo triangle; the other
- * triangle of X is set to zero).  Same info semantics as chol_potf2_launch. */
-int chol_potf2_inv_launch(int prec, int uplo, size_t n, void *A, size_t lda, void *X, size_t ldx, long *dinfo,
-                          long info_base, void *stream);
+/* X (m x n) = B * L^-H by substitution, L = the n x n lower-triangular factor of a diagonal block (uplo 'L': stored
+ * as such; uplo 'U': stored as U = L^H, so this is X = B * U^-1).  Any number of rows m; rows are independent, the
+ * launch spreads them over the SMs.  transB / transX != 0: the operand is given / wanted as its conjugate transpose
+ * (n x m: element (row, j) at ptr[j + row * ld], conjugated).  X may equal B.  dinfo (may be NULL): if *dinfo != 0
+ * on entry the launch does nothing (the factorisation has already failed).  No inverse is formed anywhere. */
+int chol_trsm_rows_launch(int prec, int uplo, size_t n, const void *L, size_t ldl, size_t m, int transB, const void *B,
+                          size_t ldb, int transX, void *X, size_t ldx, const long *dinfo, void *stream);
 /* inverse of an n x n triangular block, out of place (B may equal A).  Only the uplo triangle of
  * B is written; if (zero_other & 1) the opposite triangle of B is set to zero as well.  Zero pivot
  * -> *dinfo = info_base + column (1-based) when *dinfo == 0 (lapack/dtrtri.c:49-52); a nonzero
@@ -105,6 +118,8 @@ unsigned long long chol_launch_count(int reset);
 /* ---- measurement probes (used by bench.py / profiles, not by the library path) ---- */
 /* kind 0: DMMA m8n8k4 only; 1: DFMA only; 2: both interleaved.  Returns achieved TFLOP/s. */
 int chol_probe_fp64(int kind, int iters, double *tflops, float *ms);
+/* dependent-issue latency in cycles: kind 0 DFMA, 1 DMUL, 2 rsqrt(double), 3 64-bit shuffle, 4 shared-memory load */
+int chol_probe_latency(int kind, double *cycles_per_op);
 
 #ifdef __cplusplus
 }

@@ -43,6 +43,8 @@ struct TArgs {
   int M, N, nk;      // nk = k steps of TBK
   int NI, NJ;        // row / column tiles
   int cuplo;         // 0 all, 1 lower, 2 upper
+  int rs;            // row shift of the triangle test: D's row r stands for matrix row r >> rs (1 = interleaved complex rows)
+  int herm;          // rs == 1: force Im(diag) = 0 (HERK)
   int ntiles;
   float alpha, beta;
   const float *C;
@@ -128,7 +130,7 @@ __device__ __forceinline__ void t_tile_coords(const TArgs &p, int t, int &bi, in
     bi = t - bj * p.NI;
     return;
   }
-  constexpr int R = TBN / TBM;  // row tiles per column tile
+  const int R = (TBN << p.rs) / TBM;  // row tiles per column tile
   for (bj = 0;; ++bj) {
     const int lo = (p.cuplo == 1) ? min(R * bj, p.NI) : 0;
     const int hi = (p.cuplo == 1) ? p.NI : min(p.NI, R * bj + R);
@@ -140,9 +142,9 @@ __device__ __forceinline__ void t_tile_coords(const TArgs &p, int t, int &bi, in
     t -= cnt;
   }
 }
-static int t_count_tiles(int cuplo, int NI, int NJ) {
+static int t_count_tiles(int cuplo, int rs, int NI, int NJ) {
   if (cuplo == 0) return NI * NJ;
-  constexpr int R = TBN / TBM;
+  const int R = (TBN << rs) / TBM;
   int tot = 0;
   for (int bj = 0; bj < NJ; ++bj) {
     const int lo = (cuplo == 1) ? (R * bj < NI ? R * bj : NI) : 0;
@@ -250,27 +252,32 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
         const int col0 = bj * TBN + half * (TBN / 2) + c * 32;
         // warp-uniform: anything of this 32 x 32 patch inside the matrix and the triangle?
         bool any = rw0 < p.M && col0 < p.N;
-        if (p.cuplo == 1) any = any && (rw0 + 31 >= col0);
-        if (p.cuplo == 2) any = any && (rw0 <= col0 + 31);
+        if (p.cuplo == 1) any = any && (((rw0 + 31) >> p.rs) >= col0);
+        if (p.cuplo == 2) any = any && ((rw0 >> p.rs) <= col0 + 31);
         if (!any) continue;
         float acc[32];
         tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + ab * TBN + half * (TBN / 2) + c * 32, acc);
         float cv[32];
+        const long long mrow = row >> p.rs;  // the matrix row this (real) row belongs to
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const long long col = col0 + j;
           bool keep = row < p.M && col < p.N;
-          if (p.cuplo == 1) keep = keep && row >= col;
-          if (p.cuplo == 2) keep = keep && row <= col;
+          if (p.cuplo == 1) keep = keep && mrow >= col;
+          if (p.cuplo == 2) keep = keep && mrow <= col;
           cv[j] = (keep && p.beta != 0.f) ? p.C[col * p.ldc + row] : 0.f;
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const long long col = col0 + j;
           bool keep = row < p.M && col < p.N;
-          if (p.cuplo == 1) keep = keep && row >= col;
-          if (p.cuplo == 2) keep = keep && row <= col;
-          if (keep) p.D[col * p.ldd + row] = p.alpha * acc[j] + p.beta * cv[j];
+          if (p.cuplo == 1) keep = keep && mrow >= col;
+          if (p.cuplo == 2) keep = keep && mrow <= col;
+          if (keep) {
+            float o = p.alpha * acc[j] + p.beta * cv[j];
+            if (p.herm && mrow == col && (row & 1)) o = 0.f;  // Im of a Hermitian diagonal (blas/cherk.c: the diagonal is real)
+            p.D[col * p.ldd + row] = o;
+          }
         }
       }
       tc_fence_before();
@@ -329,9 +336,40 @@ __global__ void __launch_bounds__(256) tf32_split_kernel(int trans, int rows, in
   }
 }
 
-static int make_map(CUtensorMap *map, const void *base, size_t rows, size_t kp, unsigned box_rows) {
+// complex operand W (rows x k, column-major, interleaved re/im) -> the REAL planes of the embedding
+//   Re(W W^H)(i,j) = [a_i | b_i] . [a_j | b_j],   Im(W W^H)(i,j) = [b_i | -a_i] . [a_j | b_j]        (W = a + i b)
+// plane row 2i   = (a_i0, b_i0, a_i1, b_i1, ...)   - also the B operand's row i (read with twice the row pitch)
+// plane row 2i+1 = (b_i0, -a_i0, b_i1, -a_i1, ...)
+// so that ONE real product  D'(2m x n) = A'(2m x 2k) * B'(n x 2k)^T  writes the interleaved complex matrix in place.
+__global__ void __launch_bounds__(256) tf32_split_c_kernel(int rows, int k, int kp, const float2 *__restrict__ W, long long ldw,
+                                                           float *__restrict__ hi, float *__restrict__ lo) {
+  __shared__ float2 tile[32][33];
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;  // c in complex columns
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int cc = ty; cc < 32; cc += 8) {
+    const int r = r0 + tx, c = c0 + cc;
+    tile[cc][tx] = (r < rows && c < k) ? W[(long long)c * ldw + r] : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  for (int rr = ty; rr < 32; rr += 8) {
+    const int r = r0 + rr, c = c0 + tx;
+    if (r < rows && 2 * c < kp) {
+      const float2 w = tile[tx][rr];
+      float ah, al, bh, bl;
+      tf32_split(w.x, ah, al);
+      tf32_split(w.y, bh, bl);
+      const long long e = (long long)(2 * r) * kp + 2 * c, o = e + kp;
+      *reinterpret_cast<float2 *>(hi + e) = make_float2(ah, bh);
+      *reinterpret_cast<float2 *>(lo + e) = make_float2(al, bl);
+      *reinterpret_cast<float2 *>(hi + o) = make_float2(bh, -ah);
+      *reinterpret_cast<float2 *>(lo + o) = make_float2(bl, -al);
+    }
+  }
+}
+
+static int make_map(CUtensorMap *map, const void *base, size_t rows, size_t kp, size_t row_pitch, unsigned box_rows) {
   cuuint64_t gdim[2] = {(cuuint64_t)kp, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)kp * 4};
+  cuuint64_t gstr[1] = {(cuuint64_t)row_pitch * 4};
   cuuint32_t box[2] = {(cuuint32_t)TBK, box_rows};
   cuuint32_t estr[2] = {1, 1};
   const CUresult r = cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), gdim, gstr, box, estr,
@@ -356,9 +394,19 @@ extern "C" int chol_tf32_split_launch(int trans, size_t rows, size_t k, const vo
   return (int)cudaGetLastError();
 }
 
-extern "C" int chol_tf32x3_gemm_launch(size_t m, size_t n, size_t k, double alpha, const void *Ahi, const void *Alo, const void *Bhi,
-                                       const void *Blo, size_t kp, double beta, const void *C, size_t ldc, void *D, size_t ldd,
-                                       int cuplo, void *stream) {
+extern "C" int chol_tf32_split_c_launch(size_t rows, size_t k, const void *W, size_t ldw, void *hi, void *lo, size_t kp, void *stream) {
+  if (rows == 0 || kp == 0) return 0;
+  dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((kp / 2 + 31) / 32));
+  CHOL_COUNT_LAUNCH();
+  tf32_split_c_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((int)rows, (int)k, (int)kp, (const float2 *)W, (long long)ldw, (float *)hi,
+                                                               (float *)lo);
+  return (int)cudaGetLastError();
+}
+
+// general form: separate row pitches of the A and B planes, interleaved-complex rows (rowshift = 1) and the Hermitian diagonal
+static int tf32x3_launch(size_t m, size_t n, size_t k, double alpha, const void *Ahi, const void *Alo, size_t pitchA, const void *Bhi,
+                         const void *Blo, size_t pitchB, size_t kp, double beta, const void *C, size_t ldc, void *D, size_t ldd,
+                         int cuplo, int rowshift, int herm, void *stream) {
   if (m == 0 || n == 0) return 0;
   int sm_count = 0, dev = 0;  // per call: the library serves several devices / contexts from one process
   cudaError_t e = cudaGetDevice(&dev);
@@ -372,7 +420,9 @@ extern "C" int chol_tf32x3_gemm_launch(size_t m, size_t n, size_t k, double alph
   p.NI = (int)((m + TBM - 1) / TBM);
   p.NJ = (int)((n + TBN - 1) / TBN);
   p.cuplo = cuplo == 'L' ? 1 : (cuplo == 'U' ? 2 : 0);
-  p.ntiles = t_count_tiles(p.cuplo, p.NI, p.NJ);
+  p.rs = rowshift;
+  p.herm = herm;
+  p.ntiles = t_count_tiles(p.cuplo, p.rs, p.NI, p.NJ);
   p.alpha = (float)alpha;
   p.beta = (float)beta;
   p.C = (const float *)C;
@@ -381,11 +431,26 @@ extern "C" int chol_tf32x3_gemm_launch(size_t m, size_t n, size_t k, double alph
   p.ldd = (long long)ldd;
   if (p.ntiles == 0 || p.nk == 0) return 0;
   CUtensorMap mAhi, mAlo, mBhi, mBlo;
-  if (make_map(&mAhi, Ahi, m, kp, TBM) || make_map(&mAlo, Alo, m, kp, TBM) || make_map(&mBhi, Bhi, n, kp, TBN) ||
-      make_map(&mBlo, Blo, n, kp, TBN))
+  if (make_map(&mAhi, Ahi, m, kp, pitchA, TBM) || make_map(&mAlo, Alo, m, kp, pitchA, TBM) || make_map(&mBhi, Bhi, n, kp, pitchB, TBN) ||
+      make_map(&mBlo, Blo, n, kp, pitchB, TBN))
     return (int)cudaErrorInvalidValue;
   const int grid = p.ntiles < sm_count ? p.ntiles : sm_count;
   CHOL_COUNT_LAUNCH();
   gemm_tf32x3_kernel<<<grid, T_THREADS, T_SMEM_BYTES, (cudaStream_t)stream>>>(mAhi, mAlo, mBhi, mBlo, p);
   return (int)cudaGetLastError();
+}
+
+extern "C" int chol_tf32x3_gemm_launch(size_t m, size_t n, size_t k, double alpha, const void *Ahi, const void *Alo, const void *Bhi,
+                                       const void *Blo, size_t kp, double beta, const void *C, size_t ldc, void *D, size_t ldd,
+                                       int cuplo, void *stream) {
+  return tf32x3_launch(m, n, k, alpha, Ahi, Alo, kp, Bhi, Blo, kp, kp, beta, C, ldc, D, ldd, cuplo, 0, 0, stream);
+}
+
+// D (m x n complex, interleaved, ldd in complex elements) = alpha * A * B^H + beta * C with real alpha, beta; A and B are
+// row ranges of planes written by chol_tf32_split_c_launch (Ahi/Alo point at plane row 2*i0 of A's first row i0, Bhi/Blo
+// at plane row 2*j0 of B's first row j0); cuplo on complex indices; herm != 0 zeroes Im of the diagonal (HERK).
+extern "C" int chol_tf32x3_herk_launch(size_t m, size_t n, size_t k, double alpha, const void *Ahi, const void *Alo, const void *Bhi,
+                                       const void *Blo, size_t kp, double beta, const void *C, size_t ldc, void *D, size_t ldd,
+                                       int cuplo, int herm, void *stream) {
+  return tf32x3_launch(2 * m, n, 2 * k, alpha, Ahi, Alo, kp, Bhi, Blo, 2 * kp, kp, beta, C, 2 * ldc, D, 2 * ldd, cuplo, 1, herm, stream);
 }

@@ -26,91 +26,314 @@ namespace chol {
 
 constexpr int PANEL_THREADS = 512;
 
+// Stage the triangle of an n x n block (n <= 128) in shared memory in LOWER form: S[i + k*LD] (i >= k) = A(i,k) for
+// lower storage, op(A(k,i)) for upper storage.  Lanes run along the contiguous direction of the storage, and every
+// thread issues a batch of independent loads before the first store: a one-CTA kernel has nothing else to hide
+// the HBM latency with (the round-1 loop, one load -> one store per trip, cost ~20 round trips of ~0.6 us each).
 template <typename T>
 __device__ __forceinline__ void load_lower_form(T *S, int LD, int upper, bool conj_upper, int n, const T *A, long long lda) {
-  // S[i + k*LD] (i >= k) = A(i,k) for lower storage, op(A(k,i)) for upper storage
-  for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
-    const int r = idx % n, c = idx / n;  // coalesced along r
-    if (!upper) {
-      if (r >= c) S[r + c * LD] = A[(long long)c * lda + r];
-    } else if (r <= c) {
-      T v = A[(long long)c * lda + r];
-      S[c + r * LD] = conj_upper ? conj_of(v) : v;
+  constexpr int U = 8;
+  const int total = 128 * n;  // idx = c * 128 + r: r fast (rows of the stored column), c = stored column
+  for (int base = threadIdx.x; base < total; base += U * blockDim.x) {
+    T v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int idx = base + u * blockDim.x, r = idx & 127, c = idx >> 7;
+      v[u] = zero_of<T>();
+      if (idx < total && r < n && (upper ? r <= c : r >= c)) v[u] = A[(long long)c * lda + r];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int idx = base + u * blockDim.x, r = idx & 127, c = idx >> 7;
+      if (idx < total && r < n) {
+        if (!upper) { if (r >= c) S[r + c * LD] = v[u]; }
+        else if (r <= c) S[c + r * LD] = conj_upper ? conj_of(v[u]) : v[u];
+      }
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// potf2: the block lives in REGISTERS, distributed 2-D cyclically over the CTA's 16 warps x 32 lanes
-// (thread (lane, w) owns rows lane+32a, columns w+16b): the active window stays load-balanced as it
-// shrinks.  Right-looking, one __syncthreads per column: the warp that owns column c takes the
-// pivot by shuffle, scales its column, publishes it through a double-buffered shared-memory vector
-// and streams it to HBM; every thread then applies the rank-1 update to its own registers.
-template <typename T, int NA, int NB>
-__global__ void __launch_bounds__(PANEL_THREADS) potf2_kernel(int upper, int n, T *A, long long lda, long *dinfo, long info_base) {
+// L(:, 0:ncols) from its shared-memory copy (Ls[i + c*LD], zeros above the diagonal) to the caller's
+// triangle, coalesced for both storages: lower A(i,c) = L(i,c) - a warp per column, lanes along rows;
+// upper A(c,i) = conj(L(i,c)) - a warp per ROW i, lanes along the columns c <= i (LD is odd: the
+// shared reads are conflict-free either way).
+template <typename T, int NA, int LD>
+__device__ __forceinline__ void store_factor_columns(int upper, int n, int ncols, const T *Ls, T *A, long long lda, int warp,
+                                                     int lane) {
+  if (!upper) {
+    for (int c = warp; c < ncols; c += PANEL_THREADS / 32)
+#pragma unroll
+      for (int a = 0; a < NA; ++a) {
+        const int i = lane + 32 * a;
+        if (i >= c && i < n) A[(long long)c * lda + i] = Ls[i + c * LD];
+      }
+  } else {
+    for (int i = warp; i < n; i += PANEL_THREADS / 32)
+#pragma unroll
+      for (int a = 0; a < NA; ++a) {
+        const int c = lane + 32 * a;
+        if (c <= i && c < ncols) A[(long long)i * lda + c] = conj_of(Ls[i + c * LD]);
+      }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T shfl_elem(T v, int src) {
+  if constexpr (ScalarOf<T>::cplx) {
+    T r;
+    r.x = __shfl_sync(0xffffffffu, v.x, src);
+    r.y = __shfl_sync(0xffffffffu, v.y, src);
+    return r;
+  } else {
+    return __shfl_sync(0xffffffffu, v, src);
+  }
+}
+
+// potf2: Cholesky of one diagonal block (n <= 128; z: 64) by ONE CTA.  The trailing part of the block lives in
+// REGISTERS: thread (lane, w) of the 16 warps owns rows lane + 32a (a < NA) of the CW columns CW*w .. CW*w + CW-1
+// ("panel w").  Blocked right-looking over the 16 panels:
+//   * the owning warp factors its panel BY ITSELF in shared memory (potf2_panel): the serial chain of a column is
+//     broadcast load -> rsqrt -> scale -> FMA -> store with no CTA barrier in it (measured on B200: DFMA 8,
+//     shuffle 30, rsqrt 62, shared load 29 cycles; r02 call 5), in a few dozen instructions of rolled loops;
+//   * the finished panel is thereby published, ONE __syncthreads per panel (16 per block, not 128), and every warp
+//     right of it applies the rank-CW update to its own panel from shared memory;
+//   * look-ahead: the owner of panel p+1 factors and publishes it right after its own update, while the other
+//     warps are still busy with theirs; warps left of the panel have retired and only meet the barriers.
+// Entries above the diagonal are never read as matrix data (the published columns have zeros there), so the update
+// needs no per-element mask.  History: the round-1/2 kernels did one barrier per COLUMN with a masked, branch-free
+// rank-1 update on all 16 warps - issue-bound at 600-850 cycles per column (80 us fused with the inverse, 45-51 us
+// alone); fully unrolled register-only variants of this kernel ran to 12k instructions (instruction-fetch bound).
+template <typename T, int NA, int CW, int LD>
+__device__ __forceinline__ void potf2_panel(T *Ls, int c0, int n, int lane, int *sfail, T *A, long long lda, long *dinfo, long info_base) {
   using Real = typename ScalarOf<T>::Real;
-  __shared__ T col[2][32 * NA];
-  __shared__ int sfail;
+  const int amin = c0 >> 5;  // 32-row slices above it hold only zeros of this panel
+#pragma unroll 1
+  for (int t = 0; t < CW; ++t) {
+    const int c = c0 + t;
+    if (c >= n) break;
+    T *colc = Ls + c * LD;
+    const Real d = re_of(colc[c]);
+    T x[NA], u[CW];
+#pragma unroll
+    for (int a = 0; a < NA; ++a) x[a] = colc[lane + 32 * a];
+#pragma unroll
+    for (int t2 = 1; t2 < CW; ++t2) u[t2] = colc[c0 + t2];  // unscaled L(c0 + t2, c) for the columns right of c (t2 > t)
+    __syncwarp();  // all lanes have read column c before anyone overwrites it
+    // rsqrt, scale, publish unconditionally: the positivity test stays off the chain (a bad pivot leaves garbage
+    // that nobody uses - every thread of the CTA leaves after the next barrier)
+    const Real rinv = rsqrt(d), r = d * rinv;
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+      const int i = lane + 32 * a;
+      x[a] = (i > c) ? rscale(x[a], rinv) : ((i == c) ? from_real<T>(r) : zero_of<T>());
+      colc[i] = x[a];
+    }
+    if (!(d > Real(0)) && lane == 0 && *sfail == 0) {  // <= 0 or NaN: not positive definite (lapack/dpotrf.c:70-73)
+      *sfail = c + 1;
+      *dinfo = info_base + c + 1;
+      A[(long long)c * lda + c] = from_real<T>(d);
+    }
+#pragma unroll
+    for (int t2 = 1; t2 < CW; ++t2) {
+      if (t2 > t) {  // uniform
+        T *col2 = Ls + (c0 + t2) * LD;
+        const T m = neg(conj_of(rscale(u[t2], rinv)));
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+          if (a >= amin) {
+            T v = col2[lane + 32 * a];
+            fma_acc(v, x[a], m);
+            col2[lane + 32 * a] = v;
+          }
+      }
+    }
+    __syncwarp();  // the updated columns are visible to all lanes before the next pivot is read
+  }
+}
+
+template <typename T, int NA, int CW>
+__global__ void __launch_bounds__(PANEL_THREADS) potf2_kernel(int upper, int n, T *A, long long lda, long *dinfo, long info_base) {
+  CHOL_DYN_SMEM(smem_raw);
+  constexpr int NMAX = 32 * NA, LD = NMAX + 1;
+  static_assert(16 * CW == NMAX, "16 warps x CW columns");
+  T *Ls = reinterpret_cast<T *>(smem_raw);  // L(i,c) at Ls[i + c*LD], zeros above the diagonal and beyond n
+  __shared__ int sfail;                      // first failing column + 1
   if (*dinfo != 0) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) sfail = 0;
-  T reg[NA][NB];
+  for (int idx = threadIdx.x; idx < NMAX * LD; idx += PANEL_THREADS) Ls[idx] = zero_of<T>();
+  __syncthreads();
+  // the block enters through the shared buffer, so that the HBM reads are coalesced for both storages
+  load_lower_form(Ls, LD, upper, true, n, A, lda);
+  __syncthreads();
+  T reg[NA][CW];
 #pragma unroll
   for (int a = 0; a < NA; ++a)
 #pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      const int i = lane + 32 * a, k = warp + 16 * b;
-      T v = zero_of<T>();
-      if (i < n && k < n && i >= k) v = upper ? conj_of(A[(long long)i * lda + k]) : A[(long long)k * lda + i];
-      reg[a][b] = v;
+    for (int b = 0; b < CW; ++b) reg[a][b] = Ls[lane + 32 * a + (CW * warp + b) * LD];  // zeros above the diagonal / beyond n
+  if (warp == 0) potf2_panel<T, NA, CW, LD>(Ls, 0, n, lane, &sfail, A, lda, dinfo, info_base);
+  __syncthreads();  // panel 0 is published
+#pragma unroll 1
+  for (int p = 0; p < 16; ++p) {
+    const int c0 = CW * p;
+    if (c0 >= n) break;  // uniform: n is a kernel argument
+    // Panel p is published.  A failure in it (or before) was flagged BEFORE the barrier that published it; a flag
+    // raised meanwhile by the owner of panel p+1 lies beyond c0 + CW and is ignored until the next round, so every
+    // thread leaves after the same barrier.
+    const int fail = sfail;
+    if (fail != 0 && fail <= c0 + CW) {
+      store_factor_columns<T, NA, LD>(upper, n, fail - 1, Ls, A, lda, warp, lane);  // the columns finished before it
+      return;
     }
-  __syncthreads();
+    if (warp > p) {
+      // rank-CW update of this warp's panel: a(i,k) -= sum_j L(i,cj) conj(L(k,cj)), cj = c0 + j
+      const int amin = (CW * warp) >> 5;  // slices above it lie entirely above this panel's diagonal
 #pragma unroll
-  for (int bo = 0; bo < NB; ++bo) {
-    constexpr int dummy = 0; (void)dummy;
-    const int ao = bo >> 1;  // rows 16bo..16bo+15 live in register slice a = (16bo + cw) / 32 = bo / 2
-    for (int cw = 0; cw < 16; ++cw) {
-      const int c = 16 * bo + cw;
-      if (c >= n) break;
-      T *cb = col[c & 1];
-      if (warp == cw) {  // this warp owns column c (register slice b = bo)
-        const int lo = c & 31;
-        Real d;
-        d = __shfl_sync(0xffffffffu, re_of(reg[ao][bo]), lo);
-        if (!(d > Real(0))) {  // <= 0 or NaN: not positive definite (lapack/dpotrf.c:70-73)
-          if (lane == 0) {
-            sfail = c + 1;
-            *dinfo = info_base + c + 1;
-            A[(long long)c * lda + c] = from_real<T>(d);
-          }
-        } else {
-          const Real r = sqrt(d), rinv = Real(1) / r;
+      for (int j = 0; j < CW; ++j) {
+        const T *col = Ls + (c0 + j) * LD;
+        T li[NA], f[CW];
 #pragma unroll
-          for (int a = 0; a < NA; ++a) {
-            const int i = lane + 32 * a;
-            if (i >= c && i < n) {
-              const T x = (i == c) ? from_real<T>(r) : rscale(reg[a][bo], rinv);
-              cb[i] = x;
-              if (!upper) A[(long long)c * lda + i] = x; else A[(long long)i * lda + c] = conj_of(x);
-            }
+        for (int a = 0; a < NA; ++a) li[a] = col[lane + 32 * a];
+#pragma unroll
+        for (int b = 0; b < CW; ++b) f[b] = neg(conj_of(col[CW * warp + b]));
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+          if (a >= amin) {
+#pragma unroll
+            for (int b = 0; b < CW; ++b) fma_acc(reg[a][b], li[a], f[b]);
           }
-        }
       }
-      __syncthreads();
-      if (sfail == c + 1) return;  // (see the note on sfail in potf2_inv_kernel)
-      // rank-1 update of the trailing window: columns k > c, rows i >= k
-      T li[NA];
+      // look-ahead: the owner of the next panel writes it back (zeros above the diagonal), factors and publishes it
+      if (warp == p + 1 && c0 + CW < n) {
 #pragma unroll
-      for (int a = 0; a < NA; ++a) li[a] = cb[lane + 32 * a];
+        for (int a = 0; a < NA; ++a)
 #pragma unroll
-      for (int b = bo; b < NB; ++b) {
-        const int k = warp + 16 * b;
-        if (k > c && k < n) {
-          const T f = neg(conj_of(cb[k]));
+          for (int b = 0; b < CW; ++b) {
+            const int i = lane + 32 * a, k = CW * warp + b;
+            Ls[i + k * LD] = (i >= k) ? reg[a][b] : zero_of<T>();
+          }
+        __syncwarp();
+        potf2_panel<T, NA, CW, LD>(Ls, c0 + CW, n, lane, &sfail, A, lda, dinfo, info_base);
+      }
+    }
+    __syncthreads();  // panel p+1 is published
+  }
+  {
+    const int fail = sfail;  // a failure in the last panel
+    store_factor_columns<T, NA, LD>(upper, n, fail != 0 ? fail - 1 : n, Ls, A, lda, warp, lane);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// trsm_rows: X = B * L^-H for an n x n lower-triangular block L (n <= 128; z: 64) and ANY number of rows m -
+// the panel solve of POTRF by substitution (what the reference's dtrsm does, blas/dtrsm.c:34-216; lower:
+// W = P L^-H, upper: W = P^H U^-1 with U = L^H), without forming an inverse.  The rows of B are independent
+// recurrences  x_k = (b_k - sum_{j<k} x_j conj(L_kj)) / L_kk,  so the kernel scales across SMs by rows while each
+// row's chain stays in registers:
+//   * L^H is staged once per CTA in shared memory (row k = the coefficients conj(L_jk), j > k, contiguous in j),
+//     the reciprocals of its diagonal next to it;
+//   * a row (RR rows) is owned by a GROUP of G lanes: lane g of the group holds columns g, g+G, g+2G, ... of
+//     the right-hand side in registers; step k: the owner's b_k is broadcast by shuffle, scaled to x_k, and
+//     every lane applies  b_j -= x_k conj(L_jk)  to the columns j > k it holds (right-looking), so a step is
+//     one shuffle + one multiply + a few independent FMAs deep;
+//   * G = 32, RR = 1 (one row per warp, 4 columns per lane) keeps the chain short for the small panels of the
+//     diagonal-block recursion; G = 8, RR = 4 (16 rows per warp, every coefficient load feeds 4 FMAs) is the
+//     throughput shape for the tall panel.
+// transB / transX: the operand is given / wanted as its conjugate transpose (n x m), i.e. element (row, j) sits
+// at ptr[j + row * ld] conjugated - upper storage, where the panel is the block ROW right of the diagonal block.
+template <typename T, int NMAX, int G, int RR>
+__global__ void __launch_bounds__(256) trsm_rows_kernel(int upper, int n, const T *L, long long ldl, long long m, int cwarps, int transB,
+                                                        const T *B, long long ldb, int transX, T *X, long long ldx,
+                                                        const long *dinfo) {
+  using Real = typename ScalarOf<T>::Real;
+  constexpr int LD = NMAX + 1, NT = NMAX / G, NG = 32 / G, U = 8;
+  CHOL_DYN_SMEM(smem_raw);
+  T *Ms = reinterpret_cast<T *>(smem_raw);                         // Ms[k * LD + j] = conj(L(j,k)) / L(k,k), j > k
+  Real *dinv = reinterpret_cast<Real *>(Ms + (size_t)NMAX * LD);   // 1 / L(k,k)
+  if (dinfo != nullptr && *dinfo != 0) return;                    // the factorisation has already failed
+  // With y_k = b_k - sum_{j<k} x_j conj(L_kj) and x_k = y_k / L_kk the recurrence reads
+  //     y_k = b_k - sum_{j<k} y_j * M[j][k],   M[j][k] = conj(L_kj) / L_jj,
+  // so the serial chain of a step is one shuffle and one FMA (no multiply); x = y / diag(L) at the very end.
+  for (int i = threadIdx.x; i < NMAX; i += blockDim.x) dinv[i] = (i < n) ? Real(1) / re_of(L[(long long)i * ldl + i]) : Real(0);
+  __syncthreads();
+  // all threads of the CTA stage (also the warps that have no rows), every thread a batch of independent loads;
+  // lanes along the contiguous direction of the storage: lower -> j (rows of L), upper -> k (rows of U)
+  for (int base = threadIdx.x; base < NMAX * NMAX; base += U * blockDim.x) {
+    T v[U];
 #pragma unroll
-          for (int a = 0; a < NA; ++a)
-            if (lane + 32 * a >= k) fma_acc(reg[a][b], li[a], f);
-        }
+    for (int u = 0; u < U; ++u) {
+      const int idx = base + u * blockDim.x, fast = idx % NMAX, slow = idx / NMAX;
+      const int j = upper ? slow : fast, k = upper ? fast : slow;
+      v[u] = zero_of<T>();
+      if (idx < NMAX * NMAX && j < n && j > k) v[u] = upper ? L[(long long)j * ldl + k] : conj_of(L[(long long)k * ldl + j]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int idx = base + u * blockDim.x, fast = idx % NMAX, slow = idx / NMAX;
+      const int j = upper ? slow : fast, k = upper ? fast : slow;
+      if (idx < NMAX * NMAX) Ms[k * LD + j] = rscale(v[u], dinv[k]);
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane % NG, lg = lane / NG;  // group within the warp, lane within the group
+  // rows of the warp: row0 + rr*NG + g (consecutive lanes of one lg read consecutive rows of a column)
+  const long long row0 = ((long long)blockIdx.x * cwarps + warp) * (NG * RR);
+  if (warp >= cwarps || row0 >= m) return;
+  T b[RR][NT];
+#pragma unroll
+  for (int rr = 0; rr < RR; ++rr) {
+    const long long row = row0 + rr * NG + g;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const int j = lg + G * t;
+      T v = zero_of<T>();
+      if (row < m && j < n) v = transB ? conj_of(B[(long long)row * ldb + j]) : B[(long long)j * ldb + row];
+      b[rr][t] = v;
+    }
+  }
+#pragma unroll
+  for (int kb = 0; kb < NT; ++kb) {
+    const int kend = min(G, n - G * kb);  // <= 0 beyond the block: nothing to do (keeps the kb loop fully unrollable)
+    // the steps of one register slice stay a LOOP: fully unrolled, the 128 steps are ~10k straight-line instructions
+    // that every warp executes once - instruction-fetch bound (875 cycles per step measured, r02 call 5)
+#pragma unroll 1
+    for (int kk = 0; kk < kend; ++kk) {
+      const int k = G * kb + kk;
+      const int src = g + NG * kk;
+      T yk[RR];  // -y_k
+#pragma unroll
+      for (int rr = 0; rr < RR; ++rr) {
+        T bk;
+        if constexpr (ScalarOf<T>::cplx) { bk.x = __shfl_sync(0xffffffffu, b[rr][kb].x, src); bk.y = __shfl_sync(0xffffffffu, b[rr][kb].y, src); }
+        else bk = __shfl_sync(0xffffffffu, b[rr][kb], src);
+        yk[rr] = neg(bk);
+      }
+      const T *mrow = Ms + k * LD + lg;
+      if (lg > kk) {  // slice kb: only the columns right of k (the owner's and the finished ones keep their y)
+        const T c0 = mrow[G * kb];
+#pragma unroll
+        for (int rr = 0; rr < RR; ++rr) fma_acc(b[rr][kb], yk[rr], c0);
+      }
+#pragma unroll
+      for (int t = kb + 1; t < NT; ++t) {
+        const T c1 = mrow[G * t];
+#pragma unroll
+        for (int rr = 0; rr < RR; ++rr) fma_acc(b[rr][t], yk[rr], c1);
+      }
+    }
+  }
+#pragma unroll
+  for (int rr = 0; rr < RR; ++rr) {
+    const long long row = row0 + rr * NG + g;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const int j = lg + G * t;
+      if (row < m && j < n) {
+        const T x = rscale(b[rr][t], dinv[j]);
+        if (transX) X[(long long)row * ldx + j] = conj_of(x); else X[(long long)j * ldx + row] = x;
       }
     }
   }
@@ -122,7 +345,7 @@ __global__ void __launch_bounds__(PANEL_THREADS) potf2_kernel(int upper, int n, 
 // current unknown is broadcast by shuffle, and the eight independent chains hide each other's latency
 // while sharing the loads of L's column k.
 // V2 (same switch as the fused kernel's V2, CHOL_POTF2_V2): chains that cannot have started in the current
-// 32-row slice are pruned at compile time, as in potf2_inv_kernel's phase 2.
+// 32-row slice are pruned at compile time.
 template <typename T, int NQ, int NC, bool V2 = false>
 __global__ void __launch_bounds__(PANEL_THREADS) trti2_kernel(int upper, int unit, int n, const T *A, long long lda, T *B,
                                                               long long ldb, int zero_other, long *dinfo, long info_base) {
@@ -210,178 +433,6 @@ __global__ void __launch_bounds__(PANEL_THREADS) trti2_kernel(int upper, int uni
       if (i < n) {
         if (i >= j) { if (!upper) B[(long long)j * ldb + i] = r[c][q]; else B[(long long)i * ldb + j] = r[c][q]; }
         else if (zero_other) { if (!upper) B[(long long)j * ldb + i] = zero_of<T>(); else B[(long long)i * ldb + j] = zero_of<T>(); }
-      }
-    }
-  }
-}
-
-// L(:, 0:ncols) from its shared-memory copy (Ls[i + c*LD], zeros above the diagonal) to the caller's
-// triangle, coalesced for both storages: lower A(i,c) = L(i,c) - a warp per column, lanes along rows;
-// upper A(c,i) = conj(L(i,c)) - a warp per ROW i, lanes along the columns c <= i (LD is odd: the
-// shared reads are conflict-free either way).
-template <typename T, int NA, int LD>
-__device__ __forceinline__ void store_factor_columns(int upper, int n, int ncols, const T *Ls, T *A, long long lda, int warp,
-                                                     int lane) {
-  if (!upper) {
-    for (int c = warp; c < ncols; c += PANEL_THREADS / 32)
-#pragma unroll
-      for (int a = 0; a < NA; ++a) {
-        const int i = lane + 32 * a;
-        if (i >= c && i < n) A[(long long)c * lda + i] = Ls[i + c * LD];
-      }
-  } else {
-    for (int i = warp; i < n; i += PANEL_THREADS / 32)
-#pragma unroll
-      for (int a = 0; a < NA; ++a) {
-        const int c = lane + 32 * a;
-        if (c <= i && c < ncols) A[(long long)i * lda + c] = conj_of(Ls[i + c * LD]);
-      }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// potf2 + inverse, fused (the POTRF panel chain needs both the factor L of a diagonal block and
-// L^-1, lapack/spotrf.c:253): phase 1 is the register-resident right-looking factorisation above,
-// except that every finished column is published into a persistent shared-memory copy of L (and
-// 1/L_cc is kept); phase 2 inverts that copy by forward substitution, eight columns per warp as
-// independent, branch-free chains.  One launch, one pass over HBM, no division after the rsqrt.
-//
-// V2 (CHOL_POTF2_V2=1; written after the round-1 GPU budget was spent, off until verified and measured):
-// the SASS of the owner warp's per-column section - the serial critical path, executed 128 times -
-// is dominated by the global stores of the finished column and their address arithmetic, and by
-// per-row branches.  V2 keeps only pivot -> rsqrt -> scale -> shared store before the barrier
-// (branch-free; rows beyond n hold zeros), writes L to HBM once after phase 1 from the shared copy
-// (coalesced for both triangles, overlapping phase 2), and prunes at compile time the phase-2 chains
-// that cannot have started in the current 32-row slice (column warp+16c >= 16c > 32q+31).
-template <typename T, int NA, int NB, int NQ, int NC, bool V2>
-__global__ void __launch_bounds__(PANEL_THREADS) potf2_inv_kernel(int upper, int n, T *A, long long lda, T *X, long long ldx,
-                                                                  long *dinfo, long info_base) {
-  using Real = typename ScalarOf<T>::Real;
-  CHOL_DYN_SMEM(smem_raw);
-  constexpr int NMAX = 32 * NA, LD = NMAX + 1;
-  T *Ls = reinterpret_cast<T *>(smem_raw);          // L(i,c) at Ls[i + c*LD]
-  Real *dinv = reinterpret_cast<Real *>(Ls + (size_t)NMAX * LD);
-  __shared__ int sfail;
-  if (*dinfo != 0) return;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) sfail = 0;
-  T reg[NA][NB];
-#pragma unroll
-  for (int a = 0; a < NA; ++a)
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      const int i = lane + 32 * a, k = warp + 16 * b;
-      T v = zero_of<T>();
-      if (i < n && k < n && i >= k) v = upper ? conj_of(A[(long long)i * lda + k]) : A[(long long)k * lda + i];
-      reg[a][b] = v;
-    }
-  __syncthreads();
-  // ---------------- phase 1: factor ----------------
-#pragma unroll
-  for (int bo = 0; bo < NB; ++bo) {
-    const int ao = bo >> 1;
-    for (int cw = 0; cw < 16; ++cw) {
-      const int c = 16 * bo + cw;
-      if (c >= n) break;
-      T *cb = Ls + c * LD;
-      if (warp == cw) {
-        const Real d = __shfl_sync(0xffffffffu, re_of(reg[ao][bo]), c & 31);
-        if (!(d > Real(0))) {  // <= 0 or NaN: not positive definite (lapack/dpotrf.c:70-73)
-          if (lane == 0) {
-            sfail = c + 1;
-            *dinfo = info_base + c + 1;
-            A[(long long)c * lda + c] = from_real<T>(d);
-          }
-        } else {
-          const Real rinv = rsqrt(d), r = d * rinv;
-          if (V2 || lane == 0) dinv[c] = rinv;  // V2: every lane stores the same value - no divergent block (ptxas duplicated the rsqrt for it)
-#pragma unroll
-          for (int a = 0; a < NA; ++a) {
-            const int i = lane + 32 * a;
-            if constexpr (V2) {  // branch-free; registers of rows >= n are zero, the shared column has NMAX rows
-              const T x = (i > c) ? rscale(reg[a][bo], rinv) : ((i == c) ? from_real<T>(r) : zero_of<T>());
-              cb[i] = x;
-            } else if (i < n) {
-              const T x = (i > c) ? rscale(reg[a][bo], rinv) : ((i == c) ? from_real<T>(r) : zero_of<T>());
-              cb[i] = x;  // rows above the diagonal are stored as zeros: phase 2 reads a full column
-              if (i >= c) { if (!upper) A[(long long)c * lda + i] = x; else A[(long long)i * lda + c] = conj_of(x); }
-            }
-          }
-        }
-      }
-      __syncthreads();
-      // sfail holds the failing column + 1.  The owner of column c+1 may already have run ahead through its
-      // update, found ITS pivot bad and written sfail while a slow warp is only now testing the flag for
-      // column c: a plain "nonzero" test would let that warp leave one barrier early and hang the block
-      // (found by the CPU emulation, tests/emu).  Comparing with c + 1 makes every thread leave after the
-      // same barrier; nobody can be more than one column ahead.
-      if (sfail == c + 1) {
-        if constexpr (V2) store_factor_columns<T, NA, LD>(upper, n, c, Ls, A, lda, warp, lane);  // columns finished so far
-        return;
-      }
-      T li[NA], f[NB];
-#pragma unroll
-      for (int a = 0; a < NA; ++a) li[a] = cb[lane + 32 * a];
-#pragma unroll
-      for (int b = bo; b < NB; ++b) {
-        const int k = warp + 16 * b;
-        f[b] = (k > c && k < n) ? neg(conj_of(cb[k])) : zero_of<T>();
-      }
-#pragma unroll
-      for (int b = bo; b < NB; ++b)
-#pragma unroll
-        for (int a = 0; a < NA; ++a)
-          if (32 * a + 31 >= 16 * b) fma_acc(reg[a][b], li[a], (lane + 32 * a >= warp + 16 * b) ? f[b] : zero_of<T>());
-    }
-  }
-  __syncthreads();
-  if constexpr (V2) store_factor_columns<T, NA, LD>(upper, n, n, Ls, A, lda, warp, lane);  // fire and forget: overlaps phase 2
-  // ---------------- phase 2: X = L^-1 ----------------
-  T r[NC][NQ];
-#pragma unroll
-  for (int c = 0; c < NC; ++c)
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) r[c][q] = (lane + 32 * q == warp + 16 * c) ? one_of<T>() : zero_of<T>();
-#pragma unroll
-  for (int q = 0; q < NQ; ++q) {
-    if (32 * q >= n) continue;
-    for (int kk = 0; kk < 32; ++kk) {
-      const int k = 32 * q + kk;
-      if (k >= n) break;
-      if (k < warp) continue;  // none of this warp's columns has started yet (warp-uniform)
-      const Real dk = dinv[k];
-      T lk[NQ];
-#pragma unroll
-      for (int q2 = 0; q2 < NQ; ++q2) {
-        const int i = lane + 32 * q2;
-        lk[q2] = (q2 >= q && i > k && i < n) ? Ls[i + k * LD] : zero_of<T>();
-      }
-#pragma unroll
-      for (int c = 0; c < NC; ++c) {  // branch-free: the NC chains interleave
-        if (V2 && 16 * c > 32 * q + 31) continue;  // compile-time: column warp+16c lies below this whole row slice
-        const bool active = (k >= warp + 16 * c);
-        T rk;
-        if constexpr (ScalarOf<T>::cplx) { rk.x = __shfl_sync(0xffffffffu, r[c][q].x, kk); rk.y = __shfl_sync(0xffffffffu, r[c][q].y, kk); }
-        else rk = __shfl_sync(0xffffffffu, r[c][q], kk);
-        const T xk = active ? rscale(rk, dk) : zero_of<T>();
-        if (lane == kk && active) r[c][q] = xk;
-        const T nxk = neg(xk);
-#pragma unroll
-        for (int q2 = 0; q2 < NQ; ++q2)
-          if (q2 >= q) fma_acc(r[c][q2], lk[q2], nxk);
-      }
-    }
-  }
-#pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    const int j = warp + 16 * c;
-    if (j >= n) continue;
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      const int i = lane + 32 * q;
-      if (i < n) {  // the other triangle of X is zeroed: the panel solve uses X as a dense operand
-        const T v = (i >= j) ? r[c][q] : zero_of<T>();
-        if (!upper) X[(long long)j * ldx + i] = v; else X[(long long)i * ldx + j] = conj_of(v);
       }
     }
   }
@@ -532,6 +583,25 @@ __global__ void __launch_bounds__(128, 2) probe_fp64_kernel(double *out, int ite
   if (s == 12345.678) out[0] = s;
 }
 
+// dependent-issue latencies of the FP64 pipe (one warp, clock64 around a chain of N dependent operations):
+//   kind 0 DFMA, 1 DMUL, 2 rsqrt(double) (MUFU.RSQ64H + Newton steps), 3 64-bit shuffle, 4 shared-memory load (pointer chase)
+__global__ void probe_latency_kernel(int kind, int n, double seed, long long *cycles, double *sink) {
+  __shared__ int chase[32];
+  if (threadIdx.x < 32) chase[threadIdx.x] = (threadIdx.x + 1) & 31;
+  __syncwarp();
+  double x = seed, y = 1.0 + 1e-9 * threadIdx.x;
+  int p = threadIdx.x & 31;
+  const long long t0 = clock64();
+  if (kind == 0) for (int i = 0; i < n; ++i) x = fma(x, y, seed);
+  else if (kind == 1) for (int i = 0; i < n; ++i) x = x * y;
+  else if (kind == 2) for (int i = 0; i < n; ++i) x = rsqrt(x) + seed;
+  else if (kind == 3) for (int i = 0; i < n; ++i) x = __shfl_sync(0xffffffffu, x, (threadIdx.x + 1) & 31);
+  else for (int i = 0; i < n; ++i) p = chase[p];
+  const long long t1 = clock64();
+  if (threadIdx.x == 0) *cycles = t1 - t0;
+  if (x == 12345.678 || p == 77) *sink = x;
+}
+
 template <typename T> static size_t panel_smem(size_t n, size_t extra) { return ((n | 1) * n + extra) * sizeof(T); }
 
 template <typename K> static int set_smem(K kern, size_t bytes) {
@@ -542,20 +612,40 @@ template <typename K> static int set_smem(K kern, size_t bytes) {
 template <typename T>
 static int potf2_t(int uplo, size_t n, void *A, size_t lda, long *dinfo, long base, cudaStream_t st) {
   constexpr int NMAX = sizeof(T) == 16 ? 64 : 128;  // chol_diag_max
-  potf2_kernel<T, NMAX / 32, NMAX / 16><<<1, PANEL_THREADS, 0, st>>>(uplo == 'U', (int)n, (T *)A, (long long)lda, dinfo, base);
+  const size_t sm = (size_t)NMAX * (NMAX + 1) * sizeof(T);
+  auto kern = potf2_kernel<T, NMAX / 32, NMAX / 16>;  // 16 warps x NMAX/16 columns
+  int e = set_smem(kern, sm); if (e) return e;
+  kern<<<1, PANEL_THREADS, sm, st>>>(uplo == 'U', (int)n, (T *)A, (long long)lda, dinfo, base);
   CHOL_COUNT_LAUNCH();
   return (int)cudaGetLastError();
 }
+// rows up to which the one-row-per-warp shape is used (8 warps per CTA, one CTA per SM: a single wave)
+constexpr size_t TRSM_ROWS_SMALL = 148 * 8;
 template <typename T>
-static int potf2_inv_t(int uplo, size_t n, void *A, size_t lda, void *X, size_t ldx, long *dinfo, long base, cudaStream_t st) {
+static int trsm_rows_t(int uplo, size_t n, const void *L, size_t ldl, size_t m, int transB, const void *B, size_t ldb, int transX,
+                       void *X, size_t ldx, const long *dinfo, cudaStream_t st) {
   constexpr int NMAX = sizeof(T) == 16 ? 64 : 128;
   using Real = typename ScalarOf<T>::Real;
   const size_t sm = (size_t)NMAX * (NMAX + 1) * sizeof(T) + NMAX * sizeof(Real);
-  // V2 = short serial section (d: 109.6 -> 82.9 us per 128-block on B200, profiles/r02_staged_ab.txt); the V = false
-  // instantiation only exists in the CPU emulation, which checks that both give the same bits
-  auto kern = potf2_inv_kernel<T, NMAX / 32, NMAX / 16, NMAX / 32, NMAX / 16, true>;
-  int e = set_smem(kern, sm); if (e) return e;
-  kern<<<1, PANEL_THREADS, sm, st>>>(uplo == 'U', (int)n, (T *)A, (long long)lda, (T *)X, (long long)ldx, dinfo, base);
+  // 256 threads per CTA in every shape: all of them stage the triangle; `cw` warps of the CTA own rows
+  if (m <= TRSM_ROWS_SMALL) {
+    auto kern = trsm_rows_kernel<T, NMAX, 32, 1>;
+    int e = set_smem(kern, sm); if (e) return e;
+    const unsigned cw = 8, grid = (unsigned)((m + cw - 1) / cw);
+    kern<<<grid, 256, sm, st>>>(uplo == 'U', (int)n, (const T *)L, (long long)ldl, (long long)m, (int)cw, transB, (const T *)B,
+                                (long long)ldb, transX, (T *)X, (long long)ldx, dinfo);
+  } else {
+    // 16 register slices per lane at most (c, n = 128: groups of 16 lanes, so that the step loop unrolls fully)
+    constexpr int GT = (ScalarOf<T>::cplx && NMAX == 128) ? 16 : 8, RPW = (32 / GT) * 4;  // rows per warp
+    auto kern = trsm_rows_kernel<T, NMAX, GT, 4>;
+    int e = set_smem(kern, sm); if (e) return e;
+    const size_t warps = (m + RPW - 1) / RPW;
+    unsigned cw = 1;
+    while (cw < 8 && (warps + cw - 1) / cw > 148) cw *= 2;  // fill the SMs before stacking warps on one
+    const unsigned grid = (unsigned)((warps + cw - 1) / cw);
+    kern<<<grid, 256, sm, st>>>(uplo == 'U', (int)n, (const T *)L, (long long)ldl, (long long)m, (int)cw, transB, (const T *)B,
+                                (long long)ldb, transX, (T *)X, (long long)ldx, dinfo);
+  }
   CHOL_COUNT_LAUNCH();
   return (int)cudaGetLastError();
 }
@@ -631,11 +721,11 @@ extern "C" int chol_potf2_launch(int prec, int uplo, size_t n, void *A, size_t l
   if (n > (size_t)chol_diag_max(prec)) return (int)cudaErrorInvalidValue;
   DISPATCH(prec, potf2_t<T>(uplo, n, A, lda, dinfo, info_base, (cudaStream_t)stream));
 }
-extern "C" int chol_potf2_inv_launch(int prec, int uplo, size_t n, void *A, size_t lda, void *X, size_t ldx, long *dinfo,
-                                     long info_base, void *stream) {
-  if (n == 0) return 0;
+extern "C" int chol_trsm_rows_launch(int prec, int uplo, size_t n, const void *L, size_t ldl, size_t m, int transB, const void *B,
+                                     size_t ldb, int transX, void *X, size_t ldx, const long *dinfo, void *stream) {
+  if (n == 0 || m == 0) return 0;
   if (n > (size_t)chol_diag_max(prec)) return (int)cudaErrorInvalidValue;
-  DISPATCH(prec, potf2_inv_t<T>(uplo, n, A, lda, X, ldx, dinfo, info_base, (cudaStream_t)stream));
+  DISPATCH(prec, trsm_rows_t<T>(uplo, n, L, ldl, m, transB, B, ldb, transX, X, ldx, dinfo, (cudaStream_t)stream));
 }
 extern "C" int chol_trti2_launch(int prec, int uplo, int diag, size_t n, const void *A, size_t lda, void *B, size_t ldb,
                                  int zero_other, long *dinfo, long info_base, void *stream) {
@@ -660,6 +750,23 @@ extern "C" int chol_fill_launch(int prec, int uplo, size_t m, size_t n, double r
 extern "C" size_t chol_logdet_scratch_bytes(void) { return sizeof(LogdetScratch); }
 extern "C" int chol_logdet_launch(int prec, const void *x, size_t incx, size_t n, void *dresult, void *dscratch, void *stream) {
   DISPATCH(prec, logdet_t<T>(x, incx, n, dresult, dscratch, (cudaStream_t)stream));
+}
+
+extern "C" int chol_probe_latency(int kind, double *cycles_per_op) {
+  long long *dc = nullptr;
+  double *sink = nullptr;
+  cudaMalloc(&dc, 8);
+  cudaMalloc(&sink, 8);
+  const int n = 4096;
+  long long c = 0;
+  for (int rep = 0; rep < 2; ++rep) {
+    probe_latency_kernel<<<1, 32>>>(kind, n, 1.0000001, dc, sink);
+    cudaMemcpy(&c, dc, 8, cudaMemcpyDeviceToHost);
+  }
+  *cycles_per_op = (double)c / n;
+  cudaFree(dc);
+  cudaFree(sink);
+  return (int)cudaGetLastError();
 }
 
 extern "C" int chol_probe_fp64(int kind, int iters, double *tflops, float *ms_out) {

@@ -114,34 +114,26 @@ CUresult chol_trsm(CUBLAShandle h, int prec, int side, int uplo, int trans, int 
 typedef struct chol_ws {
   size_t nb, db, ldw, es;
   CUdeviceptr W[2]; /* panel buffers, ldw x nb */
-  CUdeviceptr Xd;   /* nb x nb : inverse of the diagonal block (other triangle zero) */
+  CUdeviceptr Xd;   /* nb x nb : inverse of a diagonal block (TRTRI), product block (LAUUM) */
   CUdeviceptr T1;   /* nb x nb : temporary of the blocked small inverse */
-  CUdeviceptr Tinv; /* db x db : inverse of a potf2 sub-block */
-  CUdeviceptr Wd;   /* nb x db : panel of the diagonal-block recursion */
-  CUdeviceptr Tp;   /* ldw x db: temporary of the blocked panel solve (0 with CHOL_PANEL_BLOCKED=0) */
-  size_t kp;        /* s with the tensor-core update: K pitch of the TF32 planes (0 = FFMA path) */
-  CUdeviceptr Whi[2], Wlo[2]; /* ldw x kp floats, K-major: tf32 hi / lo planes of W[0], W[1] */
+  size_t kp;        /* s, c with the tensor-core update: K pitch of the TF32 planes (0 = FFMA path) */
+  CUdeviceptr Whi[2], Wlo[2]; /* ldw x kp floats (c: 2 ldw x kp, real embedding), K-major: tf32 hi / lo planes of W[0], W[1] */
 } chol_ws;
 
 size_t chol_default_nb(int prec, size_t n);
 CUresult chol_carve(CULAPACKhandle h, int prec, size_t n, chol_ws *w);
 CUresult chol_carve_nb(CULAPACKhandle h, int prec, size_t n, size_t nb, chol_ws *w);
-/* Cholesky of a jb x jb (jb <= nb) diagonal block / out-of-place inverse of one (other triangle zero) */
+/* Cholesky of a jb x jb (jb <= nb) diagonal block (potf2 + substitution + rank-db updates, no inverse);
+ * ev_fact[c] / ev_col[c] (optional): diagonal sub-block c factored / sub-block column (row) c final */
 CUresult chol_potrf_diag(int prec, int uplo, size_t jb, CUdeviceptr A, size_t lda, long *dinfo, long base,
                          const chol_ws *w, CUstream st);
-CUresult chol_diag_factor_inverse(int prec, int uplo, size_t jb, CUdeviceptr A, size_t lda, CUdeviceptr X, size_t ldx,
-                                  long *dinfo, long base, const chol_ws *w, CUstream st);
-CUresult chol_diag_factor_inverse_ex(int prec, int uplo, size_t jb, CUdeviceptr A, size_t lda, CUdeviceptr X, size_t ldx,
-                                     long *dinfo, long base, const chol_ws *w, CUstream st, int diag_only);
-bool chol_panel_blocked(void);
+CUresult chol_diag_factor_ev(int prec, int uplo, size_t jb, CUdeviceptr A, size_t lda, long *dinfo, long base,
+                             const chol_ws *w, CUstream st, CUevent *ev_fact, CUevent *ev_col);
 /* POTRF panel step: factor the jb x jb diagonal block at Ajj, solve the panel next to it into W (rest x jb).
  * h != NULL: the solve is pipelined with the diagonal chain on the handle's second high-priority stream */
 CUresult chol_panel_factor_solve_lower(CULAPACKhandle h, int prec, size_t jb, size_t rest, CUdeviceptr Ajj, CUdeviceptr P, size_t lda,
                                        CUdeviceptr W, size_t ldw, long *dinfo, long base, const chol_ws *w, CUstream st,
                                        CUevent before_solve);
-CUresult chol_diag_factor_inverse_ev(int prec, int uplo, size_t jb, CUdeviceptr A, size_t lda, CUdeviceptr X, size_t ldx,
-                                     long *dinfo, long base, const chol_ws *w, CUstream st, int diag_only, CUevent *ev_x,
-                                     CUevent *ev_col);
 bool chol_panel_pipeline(void);
 bool chol_lookahead_split(void);
 bool chol_s_tensor(void);

@@ -43,8 +43,8 @@ static bool chol_env_switch(int *state, const char *name, int dflt) {
   }
   return v != 0;
 }
-static int chol_panel_blocked_state = -1, chol_lookahead_split_state = -1, chol_trtri_lookahead_state = -1, chol_s_tensor_state = -1, chol_panel_pipeline_state = -1;
-/* s-precision POTRF: trailing and look-ahead updates on the tcgen05 tensor cores as a 3xTF32 split (default;
+static int chol_lookahead_split_state = -1, chol_trtri_lookahead_state = -1, chol_s_tensor_state = -1, chol_panel_pipeline_state = -1;
+/* s- and c-precision POTRF: trailing and look-ahead updates on the tcgen05 tensor cores as a 3xTF32 split (default;
  * CHOL_S_TENSOR=0 keeps them on the FP32 FFMA engine for A/B runs and for the plain-FP32 tolerance) */
 bool chol_s_tensor(void) { return chol_env_switch(&chol_s_tensor_state, "CHOL_S_TENSOR", 1); }
 
@@ -68,22 +68,19 @@ CUresult chol_carve_nb(CULAPACKhandle h, int prec, size_t n, size_t nb, chol_ws 
   w->db = (size_t)chol_diag_max(prec);
   if (w->nb < w->db) w->db = w->nb;
   w->ldw = chol_roundup(n > w->nb ? n : w->nb, 16);
-  const size_t szW = chol_roundup(w->ldw * w->nb * w->es, 256), szX = chol_roundup(w->nb * w->nb * w->es, 256),
-               szT = chol_roundup(w->db * w->db * w->es, 256), szWd = chol_roundup(w->nb * w->db * w->es, 256);
-  const size_t szTp = chol_panel_blocked() ? chol_roundup(w->ldw * w->db * w->es, 256) : 0;
-  /* s: TF32 (hi, lo) planes of the two panel buffers for the tensor-core trailing update (csrc/gemm_tf32x3.cu) */
-  w->kp = (prec == 's' && chol_s_tensor()) ? chol_tf32_kpitch(w->nb) : 0;
-  const size_t szS = chol_roundup(w->ldw * w->kp * sizeof(float), 1024);
+  const size_t szW = chol_roundup(w->ldw * w->nb * w->es, 256), szX = chol_roundup(w->nb * w->nb * w->es, 256);
+  /* s, c: TF32 (hi, lo) planes of the two panel buffers for the tensor-core trailing update (csrc/gemm_tf32x3.cu);
+   * c uses the real embedding of the complex product: two plane rows per matrix row, 2 nb columns */
+  const size_t cx = prec == 'c' ? 2 : 1;
+  w->kp = ((prec == 's' || prec == 'c') && chol_s_tensor()) ? chol_tf32_kpitch(cx * w->nb) : 0;
+  const size_t szS = chol_roundup(cx * w->ldw * w->kp * sizeof(float), 1024);
   CUdeviceptr base;
-  CU_ERROR_CHECK(chol_lapack_workspace(h, 2 * szW + 2 * szX + szT + szWd + szTp + 4 * szS + 1024, &base));
+  CU_ERROR_CHECK(chol_lapack_workspace(h, 2 * szW + 2 * szX + 4 * szS + 2048, &base));
   w->W[0] = base;
   w->W[1] = base + szW;
   w->Xd = base + 2 * szW;
   w->T1 = w->Xd + szX;
-  w->Tinv = w->T1 + szX;
-  w->Wd = w->Tinv + szT;
-  w->Tp = szTp ? w->Wd + szWd : 0;
-  const CUdeviceptr planes = chol_roundup(w->Wd + szWd + szTp, 1024);
+  const CUdeviceptr planes = chol_roundup(w->T1 + szX, 1024);
   for (int i = 0; i < 2; i++) {
     w->Whi[i] = w->kp ? planes + (CUdeviceptr)(2 * i) * szS : 0;
     w->Wlo[i] = w->kp ? planes + (CUdeviceptr)(2 * i + 1) * szS : 0;
@@ -101,32 +98,47 @@ static CUresult finish_info(CULAPACKhandle h, CUstream producer, long *info) {
   return CUDA_SUCCESS;
 }
 
-/* Cholesky of a jb x jb (jb <= nb) diagonal block, blocked by db on one stream */
-CUresult chol_potrf_diag(int prec, int uplo, size_t jb, CUdeviceptr A, size_t lda, long *dinfo, long base,
-                         const chol_ws *w, CUstream st) {
-  const size_t es = w->es, db = w->db;
+/* Cholesky of a jb x jb (jb <= nb) diagonal block on one stream, blocked by db (128; z 64): per sub-block
+ *   potf2 (one CTA, registers)  ->  the rows below / columns right of it solved by SUBSTITUTION, in place
+ *   (chol_trsm_rows_launch, rows spread over the SMs)  ->  rank-db update of the rest of the block.
+ * No inverse is formed (rounds 1-2 inverted every sub-block and multiplied: an 80 us fused kernel per 128 columns
+ * on the serial chain, and explicit inverses lose digits on ill-conditioned blocks that substitution keeps).
+ * ev_fact / ev_col (both or neither; at least nblk events each): ev_fact[c] is recorded on st when diagonal
+ * sub-block c is factored, ev_col[c] when the factor's sub-block column (lower) / row (upper) c is final -
+ * what a panel solve running on another stream waits for. */
+CUresult chol_diag_factor_ev(int prec, int uplo, size_t jb, CUdeviceptr A, size_t lda, long *dinfo, long base,
+                             const chol_ws *w, CUstream st, CUevent *ev_fact, CUevent *ev_col) {
+  const size_t es = w->es, db = w->db, nblk = (jb + db - 1) / db;
   const int herm = chol_is_complex(prec);
-  for (size_t i = 0; i < jb; i += db) {
-    const size_t ib = chol_min(db, jb - i), r = jb - i - ib;
+  for (size_t c = 0; c < nblk; c++) {
+    const size_t i = c * db, ib = chol_min(db, jb - i), r = jb - i - ib;
     const CUdeviceptr Aii = chol_at(A, lda, i, i, es);
     RT_CHECK(chol_potf2_launch(prec, uplo, ib, (void *)Aii, lda, dinfo, base + (long)i, (void *)st));
+    if (ev_fact) CU_ERROR_CHECK(cuEventRecord(ev_fact[c], st));
     if (r == 0) break;
-    RT_CHECK(chol_trti2_launch(prec, uplo, 'N', ib, (const void *)Aii, lda, (void *)w->Tinv, db, 1, dinfo,
-                               base + (long)i, (void *)st));
     const CUdeviceptr A22 = chol_at(A, lda, i + ib, i + ib, es);
-    if (uplo == 'L') {
+    if (uplo == 'L') { /* L21 = A21 * L11^-H, then A22 -= L21 * L21^H */
       const CUdeviceptr A21 = chol_at(A, lda, i + ib, i, es);
-      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'C', r, ib, ib, ONE, A21, lda, w->Tinv, db, ZERO, 0, 0, w->Wd, w->nb, st));
-      RT_CHECK(chol_copy_launch(prec, 'N', 0, r, ib, (const void *)w->Wd, w->nb, (void *)A21, lda, (void *)st));
-    } else {
+      RT_CHECK(chol_trsm_rows_launch(prec, 'L', ib, (const void *)Aii, lda, r, 0, (const void *)A21, lda, 0, (void *)A21, lda,
+                                     dinfo, (void *)st));
+      if (ev_col) CU_ERROR_CHECK(cuEventRecord(ev_col[c], st));
+      CU_ERROR_CHECK(chol_gemm_ex(prec, 'N', 'C', 0, 0, 0, 0, 'L', herm, r, r, ib, MONE, A21, lda, A21, lda, ONE, A22, lda, A22,
+                                  lda, st));
+    } else { /* U12 = U11^-H * A12, i.e. U12^H = A12^H * U11^-1 (rows = columns of A12), then A22 -= U12^H * U12 */
       const CUdeviceptr A12 = chol_at(A, lda, i, i + ib, es);
-      CU_ERROR_CHECK(chol_gemm(prec, 'C', 'N', r, ib, ib, ONE, A12, lda, w->Tinv, db, ZERO, 0, 0, w->Wd, w->nb, st));
-      RT_CHECK(chol_copy_launch(prec, 'C', 0, r, ib, (const void *)w->Wd, w->nb, (void *)A12, lda, (void *)st));
+      RT_CHECK(chol_trsm_rows_launch(prec, 'U', ib, (const void *)Aii, lda, r, 1, (const void *)A12, lda, 1, (void *)A12, lda,
+                                     dinfo, (void *)st));
+      if (ev_col) CU_ERROR_CHECK(cuEventRecord(ev_col[c], st));
+      CU_ERROR_CHECK(chol_gemm_ex(prec, 'C', 'N', 0, 0, 0, 0, 'U', herm, r, r, ib, MONE, A12, lda, A12, lda, ONE, A22, lda, A22,
+                                  lda, st));
     }
-    CU_ERROR_CHECK(chol_gemm_ex(prec, 'N', 'C', 0, 0, 0, 0, uplo, herm, r, r, ib, MONE, w->Wd, w->nb, w->Wd, w->nb, ONE,
-                                A22, lda, A22, lda, st));
   }
   return CUDA_SUCCESS;
+}
+
+CUresult chol_potrf_diag(int prec, int uplo, size_t jb, CUdeviceptr A, size_t lda, long *dinfo, long base,
+                         const chol_ws *w, CUstream st) {
+  return chol_diag_factor_ev(prec, uplo, jb, A, lda, dinfo, base, w, st, NULL, NULL);
 }
 
 /* X (jb x jb, ldx, other triangle zero) = inverse of the triangular jb x jb block A, jb <= nb */
@@ -160,111 +172,32 @@ CUresult chol_trtri_small(int prec, int uplo, int diag, size_t jb, CUdeviceptr A
   return CUDA_SUCCESS;
 }
 
-/* Factor the jb x jb (jb <= nb) diagonal block A in place AND produce X = inverse of its factor
- * (ldx, other triangle zero) - what every POTRF step needs for the panel solve.  Each db-block
- * is one fused potf2+inverse launch; the blocks are tied together with small GEMMs. */
-CUresult chol_diag_factor_inverse(int prec, int uplo, size_t jb, CUdeviceptr A, size_t lda, CUdeviceptr X, size_t ldx,
-                                  long *dinfo, long base, const chol_ws *w, CUstream st) {
-  return chol_diag_factor_inverse_ex(prec, uplo, jb, A, lda, X, ldx, dinfo, base, w, st, 0);
-}
-
-/* diag_only != 0: X receives only the inverses of the db x db diagonal sub-blocks (what the blocked
- * panel solve needs); the rest of X is left alone */
-CUresult chol_diag_factor_inverse_ex(int prec, int uplo, size_t jb, CUdeviceptr A, size_t lda, CUdeviceptr X, size_t ldx,
-                                     long *dinfo, long base, const chol_ws *w, CUstream st, int diag_only) {
-  return chol_diag_factor_inverse_ev(prec, uplo, jb, A, lda, X, ldx, dinfo, base, w, st, diag_only, NULL, NULL);
-}
-
-/* ev_x / ev_col (both or neither; at least nblk events each): ev_x[c] is recorded on st when X_cc (the inverse of
- * diagonal sub-block c) is ready, ev_col[c] when the factor's sub-block column (lower) / row (upper) c is final in
- * the matrix - what a panel solve running on another stream has to wait for */
-CUresult chol_diag_factor_inverse_ev(int prec, int uplo, size_t jb, CUdeviceptr A, size_t lda, CUdeviceptr X, size_t ldx,
-                                     long *dinfo, long base, const chol_ws *w, CUstream st, int diag_only, CUevent *ev_x,
-                                     CUevent *ev_col) {
-  const size_t es = w->es, db = w->db, nblk = (jb + db - 1) / db;
-  const int herm = chol_is_complex(prec);
-  if (nblk > 1 && !diag_only) RT_CHECK(chol_fill_launch(prec, 0, jb, jb, 0.0, 0.0, (void *)X, ldx, (void *)st));
-  for (size_t c = 0; c < nblk; c++) {
-    const size_t i = c * db, ib = chol_min(db, jb - i), r = jb - i - ib;
-    const CUdeviceptr Aii = chol_at(A, lda, i, i, es), Xii = chol_at(X, ldx, i, i, es);
-    RT_CHECK(chol_potf2_inv_launch(prec, uplo, ib, (void *)Aii, lda, (void *)Xii, ldx, dinfo, base + (long)i, (void *)st));
-    if (ev_x) CU_ERROR_CHECK(cuEventRecord(ev_x[c], st));
-    if (r == 0) break;
-    const CUdeviceptr A22 = chol_at(A, lda, i + ib, i + ib, es);
-    if (uplo == 'L') {
-      const CUdeviceptr A21 = chol_at(A, lda, i + ib, i, es);
-      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'C', r, ib, ib, ONE, A21, lda, Xii, ldx, ZERO, 0, 0, w->Wd, w->nb, st));
-      RT_CHECK(chol_copy_launch(prec, 'N', 0, r, ib, (const void *)w->Wd, w->nb, (void *)A21, lda, (void *)st));
-    } else {
-      const CUdeviceptr A12 = chol_at(A, lda, i, i + ib, es);
-      CU_ERROR_CHECK(chol_gemm(prec, 'C', 'N', r, ib, ib, ONE, A12, lda, Xii, ldx, ZERO, 0, 0, w->Wd, w->nb, st));
-      RT_CHECK(chol_copy_launch(prec, 'C', 0, r, ib, (const void *)w->Wd, w->nb, (void *)A12, lda, (void *)st));
-    }
-    if (ev_col) CU_ERROR_CHECK(cuEventRecord(ev_col[c], st));
-    CU_ERROR_CHECK(chol_gemm_ex(prec, 'N', 'C', 0, 0, 0, 0, uplo, herm, r, r, ib, MONE, w->Wd, w->nb, w->Wd, w->nb, ONE, A22,
-                                lda, A22, lda, st));
-  }
-  /* off-diagonal blocks of the inverse (same recurrences as chol_trtri_small) */
-  for (size_t b = 1; b < nblk && !diag_only; b++) {
-    const size_t c = (uplo == 'L') ? nblk - 1 - b : b;
-    const size_t i = c * db, ib = chol_min(db, jb - i);
-    const CUdeviceptr Xcc = chol_at(X, ldx, i, i, es);
-    if (uplo == 'L') {
-      const size_t r = jb - i - ib;
-      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'N', r, ib, ib, ONE, chol_at(A, lda, i + ib, i, es), lda, Xcc, ldx, ZERO, 0, 0,
-                               w->T1, w->nb, st));
-      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'N', r, ib, r, MONE, chol_at(X, ldx, i + ib, i + ib, es), ldx, w->T1, w->nb, ZERO,
-                               0, 0, chol_at(X, ldx, i + ib, i, es), ldx, st));
-    } else {
-      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'N', i, ib, ib, ONE, chol_at(A, lda, 0, i, es), lda, Xcc, ldx, ZERO, 0, 0, w->T1,
-                               w->nb, st));
-      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'N', i, ib, i, MONE, X, ldx, w->T1, w->nb, ZERO, 0, 0, chol_at(X, ldx, 0, i, es),
-                               ldx, st));
-    }
-  }
-  return CUDA_SUCCESS;
-}
-
-/* Blocked panel solve (default; CHOL_PANEL_BLOCKED=0 selects the one-GEMM form for A/B runs - dpotrf N = 16384
- * 25.7 -> 26.7 TFLOP/s alone, 28.4 together with the other chain cuts, profiles/r02_staged_ab.txt):
- * instead of inverting the whole jb x jb diagonal block (nblk(nblk-1) small, serial GEMMs to tie the
- * db-blocks of the inverse together) and solving the panel with one GEMM, invert only the db x db
- * diagonal sub-blocks and solve the panel by block forward substitution with full-height GEMMs:
- *     W_c = (P_c - W[:, 0:c] * L[c, 0:c]^H) * inv(L_cc)^H        c = 0 .. nblk-1
- * 10/16 of the flops at nblk = 4, no small GEMMs on the chain. */
-bool chol_panel_blocked(void) { return chol_env_switch(&chol_panel_blocked_state, "CHOL_PANEL_BLOCKED", 1); }
-
-/* CHOL_LOOKAHEAD_SPLIT=1 (written after the round-1 GPU budget was spent, off until measured): the look-ahead
- * update of the next block column is split - its jb2 x jb2 diagonal block stays on the panel stream, so the next
- * diagonal block can be factored at once, while the rows below it (the bulk of the column) are updated on a
- * third stream at the same time; the next panel solve waits for that part.  Takes the look-ahead GEMM off the
- * serial panel chain (stream dependencies mutation-tested on the asynchronous mock back end). */
+/* CHOL_LOOKAHEAD_SPLIT=1: the look-ahead update of the next block column is split - its jb2 x jb2 diagonal block
+ * stays on the panel stream, so the next diagonal block can be factored at once, while the rows below it (the
+ * bulk of the column) are updated on a third stream at the same time; the next panel solve waits for that part.
+ * Measured neutral on one GPU (dpotrf N = 16384 28.30 -> 28.41 TFLOP/s, profiles/r02_call2_*.txt), so off. */
 bool chol_lookahead_split(void) { return chol_env_switch(&chol_lookahead_split_state, "CHOL_LOOKAHEAD_SPLIT", 0); }
 
 bool chol_trtri_lookahead(void) { return chol_env_switch(&chol_trtri_lookahead_state, "CHOL_TRTRI_LOOKAHEAD", 1); }
 
 /* Panel step of POTRF: factor the jb x jb diagonal block at Ajj and solve the panel next to it into W (rest x jb).
- *   lower: P = the rest x jb block below Ajj,      W_c = (P_c   - W[:, 0:c] * L[c, 0:c]^H) * inv(L_cc)^H
- *   upper: P = the jb x rest block right of Ajj,   W_c = (P_c^H - W[:, 0:c] * U[0:c, c])   * inv(U_cc)
- * Blocked form (default): only the db x db diagonal sub-blocks are inverted and the panel is solved by block
- * forward substitution with full-height GEMMs.  With a handle the two halves are PIPELINED: the diagonal chain
- * (potf2+inverse, small GEMMs) runs on `st`, the full-height GEMMs on the handle's second high-priority stream,
- * sub-block c of the solve starting as soon as sub-block c of the chain is done (events), so only the last
- * sub-block's solve is left on the critical path.  `st` has seen everything when the function returns.
- * before_solve (may be NULL): an event that must have completed before P is read - the lower part of a split
- * look-ahead runs on another stream while the diagonal block is factored here. */
+ *   lower: P = the rest x jb block below Ajj,      W_c = (P_c   - W[:, 0:c] * L[c, 0:c]^H) * L_cc^-H
+ *   upper: P = the jb x rest block right of Ajj,   W_c = (P_c^H - W[:, 0:c] * U[0:c, c])   * U_cc^-1
+ * by block forward substitution over the db-wide sub-blocks c: one full-height GEMM (tensor cores) and one
+ * substitution with the db x db triangle (chol_trsm_rows_launch) per sub-block; nothing is inverted.
+ * With a handle the two halves are PIPELINED: the diagonal chain (chol_diag_factor_ev) runs on `st`, the
+ * full-height work on the handle's second high-priority stream, sub-block c of the solve starting as soon as
+ * sub-block c of the chain is done (events), so only the last sub-block's solve is left on the critical path.
+ * `st` has seen everything when the function returns.  before_solve (may be NULL): an event that must have
+ * completed before P is read - the lower part of a split look-ahead runs on another stream while the diagonal
+ * block is factored here.  CHOL_PANEL_PIPELINE=0 keeps everything on `st` (A/B runs). */
 bool chol_panel_pipeline(void) { return chol_env_switch(&chol_panel_pipeline_state, "CHOL_PANEL_PIPELINE", 1); }
 
 static CUresult panel_factor_solve(CULAPACKhandle h, int prec, int uplo, size_t jb, size_t rest, CUdeviceptr Ajj, CUdeviceptr P,
                                    size_t lda, CUdeviceptr W, size_t ldw, long *dinfo, long base, const chol_ws *w, CUstream st,
                                    CUevent before_solve) {
-  const size_t es = w->es, db = w->db, nb = w->nb, nblk = (jb + db - 1) / db;
+  const size_t es = w->es, db = w->db, nblk = (jb + db - 1) / db;
   const bool lower = uplo == 'L';
-  if (!chol_panel_blocked() || nblk < 2 || w->Tp == 0) { /* whole inverse, one GEMM */
-    CU_ERROR_CHECK(chol_diag_factor_inverse(prec, uplo, jb, Ajj, lda, w->Xd, nb, dinfo, base, w, st));
-    if (before_solve) CU_ERROR_CHECK(cuStreamWaitEvent(st, before_solve, 0));
-    return chol_gemm(prec, lower ? 'N' : 'C', lower ? 'C' : 'N', rest, jb, jb, ONE, P, lda, w->Xd, nb, ZERO, 0, 0, W, ldw, st);
-  }
   const bool pipe = h != NULL && nblk <= CHOL_DIAG_EVENTS && chol_panel_pipeline();
   CUstream ss = pipe ? h->s_look : st;
   if (pipe) { /* the solve stream starts from what `st` has seen (P's look-ahead update may have run there) */
@@ -272,28 +205,28 @@ static CUresult panel_factor_solve(CULAPACKhandle h, int prec, int uplo, size_t 
     CU_ERROR_CHECK(cuStreamWaitEvent(ss, h->ev_solve, 0));
     if (before_solve) CU_ERROR_CHECK(cuStreamWaitEvent(ss, before_solve, 0));
   }
-  CU_ERROR_CHECK(chol_diag_factor_inverse_ev(prec, uplo, jb, Ajj, lda, w->Xd, nb, dinfo, base, w, st, 1, pipe ? h->ev_dx : NULL,
-                                             pipe ? h->ev_dcol : NULL));
+  CU_ERROR_CHECK(chol_diag_factor_ev(prec, uplo, jb, Ajj, lda, dinfo, base, w, st, pipe ? h->ev_dx : NULL, pipe ? h->ev_dcol : NULL));
   if (!pipe && before_solve) CU_ERROR_CHECK(cuStreamWaitEvent(st, before_solve, 0));
   for (size_t c = 0; c < nblk; c++) {
     const size_t i = c * db, ib = chol_min(db, jb - i);
-    const CUdeviceptr Wc = chol_at(W, ldw, 0, i, es), Xcc = chol_at(w->Xd, nb, i, i, es);
+    const CUdeviceptr Wc = chol_at(W, ldw, 0, i, es), Lcc = chol_at(Ajj, lda, i, i, es);
     const CUdeviceptr Pc = lower ? chol_at(P, lda, 0, i, es) : chol_at(P, lda, i, 0, es);
-    if (c == 0) {
+    if (c == 0) { /* straight from the matrix (upper: read as its conjugate transpose) */
       if (pipe) CU_ERROR_CHECK(cuStreamWaitEvent(ss, h->ev_dx[0], 0));
-      CU_ERROR_CHECK(chol_gemm(prec, lower ? 'N' : 'C', lower ? 'C' : 'N', rest, ib, ib, ONE, Pc, lda, Xcc, nb, ZERO, 0, 0, Wc, ldw, ss));
+      RT_CHECK(chol_trsm_rows_launch(prec, uplo, ib, (const void *)Lcc, lda, rest, lower ? 0 : 1, (const void *)Pc, lda, 0, (void *)Wc,
+                                     ldw, dinfo, (void *)ss));
       continue;
     }
     if (pipe) CU_ERROR_CHECK(cuStreamWaitEvent(ss, h->ev_dcol[c - 1], 0)); /* L[c, 0:i] / U[0:i, c] is final */
-    if (lower) { /* T = P_c - W[:, 0:i] * L[i:i+ib, 0:i]^H  (C = P_c in the matrix, D = T) */
-      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'C', rest, ib, i, MONE, W, ldw, chol_at(Ajj, lda, i, 0, es), lda, ONE, Pc, lda, w->Tp, w->ldw, ss));
-    } else {     /* T = P_c^H, then T -= W[:, 0:i] * U[0:i, i:i+ib] */
-      RT_CHECK(chol_copy_launch(prec, 'C', 0, ib, rest, (const void *)Pc, lda, (void *)w->Tp, w->ldw, (void *)ss));
-      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'N', rest, ib, i, MONE, W, ldw, chol_at(Ajj, lda, 0, i, es), lda, ONE, w->Tp, w->ldw, w->Tp,
-                               w->ldw, ss));
+    if (lower) { /* W_c = P_c - W[:, 0:i] * L[i:i+ib, 0:i]^H  (C = P_c in the matrix, D = W_c) */
+      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'C', rest, ib, i, MONE, W, ldw, chol_at(Ajj, lda, i, 0, es), lda, ONE, Pc, lda, Wc, ldw, ss));
+    } else {     /* W_c = P_c^H, then W_c -= W[:, 0:i] * U[0:i, i:i+ib] */
+      RT_CHECK(chol_copy_launch(prec, 'C', 0, ib, rest, (const void *)Pc, lda, (void *)Wc, ldw, (void *)ss));
+      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'N', rest, ib, i, MONE, W, ldw, chol_at(Ajj, lda, 0, i, es), lda, ONE, Wc, ldw, Wc, ldw, ss));
     }
-    if (pipe) CU_ERROR_CHECK(cuStreamWaitEvent(ss, h->ev_dx[c], 0)); /* X_cc */
-    CU_ERROR_CHECK(chol_gemm(prec, 'N', lower ? 'C' : 'N', rest, ib, ib, ONE, w->Tp, w->ldw, Xcc, nb, ZERO, 0, 0, Wc, ldw, ss));
+    if (pipe) CU_ERROR_CHECK(cuStreamWaitEvent(ss, h->ev_dx[c], 0)); /* diagonal sub-block c is factored */
+    RT_CHECK(chol_trsm_rows_launch(prec, uplo, ib, (const void *)Lcc, lda, rest, 0, (const void *)Wc, ldw, 0, (void *)Wc, ldw, dinfo,
+                                   (void *)ss));
   }
   if (pipe) {
     CU_ERROR_CHECK(cuEventRecord(h->ev_solve, ss));
@@ -347,10 +280,12 @@ static CUresult potrf_body(CULAPACKhandle h, int prec, int uplo, size_t n, CUdev
       CU_ERROR_CHECK(chol_panel_factor_solve_upper(h, prec, jb, rest, Ajj, P, lda, W, w.ldw, dinfo, (long)j, &w, sp, before_solve));
       RT_CHECK(chol_copy_launch(prec, 'C', 0, rest, jb, (const void *)W, w.ldw, (void *)P, lda, (void *)sp));
     }
-    /* s: the updates of this step run on the tensor cores - split W once into its TF32 (hi, lo) planes */
+    /* s, c: the updates of this step run on the tensor cores - split W once into its TF32 (hi, lo) planes */
     const bool tens = w.kp != 0 && rest >= 512 && jb >= 64;
     const CUdeviceptr Whi = w.Whi[step & 1], Wlo = w.Wlo[step & 1];
-    if (tens) RT_CHECK(chol_tf32_split_launch(0, rest, jb, (const void *)W, w.ldw, (void *)Whi, (void *)Wlo, w.kp, (void *)sp));
+    const size_t prow = (herm ? 2 : 1) * w.kp * sizeof(float); /* bytes of planes per matrix row */
+    if (tens && !herm) RT_CHECK(chol_tf32_split_launch(0, rest, jb, (const void *)W, w.ldw, (void *)Whi, (void *)Wlo, w.kp, (void *)sp));
+    if (tens && herm) RT_CHECK(chol_tf32_split_c_launch(rest, jb, (const void *)W, w.ldw, (void *)Whi, (void *)Wlo, w.kp, (void *)sp));
     CU_ERROR_CHECK(cuEventRecord(h->ev_panel[step % CHOL_EVENT_RING], sp));
 
     /* --- trailing update  A22 -= W W^H, split into the next block column/row (look-ahead, panel
@@ -363,9 +298,13 @@ static CUresult potrf_body(CULAPACKhandle h, int prec, int uplo, size_t n, CUdev
       const bool prof = h->profile && h->prof_n < h->prof_cap;
       if (prof) CU_ERROR_CHECK(cuEventRecord(h->prof_e0[h->prof_n], su));
       if (tens) {
-        const CUdeviceptr H2 = Whi + (CUdeviceptr)(jb2 * w.kp * sizeof(float)), L2 = Wlo + (CUdeviceptr)(jb2 * w.kp * sizeof(float));
-        RT_CHECK(chol_tf32x3_gemm_launch(rest2, rest2, jb, -1.0, (const void *)H2, (const void *)L2, (const void *)H2, (const void *)L2,
-                                         w.kp, 1.0, (const void *)A33, lda, (void *)A33, lda, uplo, (void *)su));
+        const CUdeviceptr H2 = Whi + (CUdeviceptr)(jb2 * prow), L2 = Wlo + (CUdeviceptr)(jb2 * prow);
+        if (!herm)
+          RT_CHECK(chol_tf32x3_gemm_launch(rest2, rest2, jb, -1.0, (const void *)H2, (const void *)L2, (const void *)H2, (const void *)L2,
+                                           w.kp, 1.0, (const void *)A33, lda, (void *)A33, lda, uplo, (void *)su));
+        else
+          RT_CHECK(chol_tf32x3_herk_launch(rest2, rest2, jb, -1.0, (const void *)H2, (const void *)L2, (const void *)H2, (const void *)L2,
+                                           w.kp, 1.0, (const void *)A33, lda, (void *)A33, lda, uplo, 1, (void *)su));
       } else
         CU_ERROR_CHECK(chol_gemm_ex(prec, 'N', 'C', 0, 0, 0, 0, uplo, herm, rest2, rest2, jb, MONE, W2, w.ldw, W2, w.ldw, ONE,
                                     A33, lda, A33, lda, su));
@@ -401,8 +340,12 @@ static CUresult potrf_body(CULAPACKhandle h, int prec, int uplo, size_t n, CUdev
         CU_ERROR_CHECK(cuEventRecord(look_pending, sl));
       } else if (tens) { /* the same block column / block row on the tensor cores */
         const size_t lm = uplo == 'L' ? rest : jb2, ln = uplo == 'L' ? jb2 : rest;
-        RT_CHECK(chol_tf32x3_gemm_launch(lm, ln, jb, -1.0, (const void *)Whi, (const void *)Wlo, (const void *)Whi, (const void *)Wlo,
-                                         w.kp, 1.0, (const void *)A22, lda, (void *)A22, lda, uplo, (void *)sp));
+        if (!herm)
+          RT_CHECK(chol_tf32x3_gemm_launch(lm, ln, jb, -1.0, (const void *)Whi, (const void *)Wlo, (const void *)Whi, (const void *)Wlo,
+                                           w.kp, 1.0, (const void *)A22, lda, (void *)A22, lda, uplo, (void *)sp));
+        else
+          RT_CHECK(chol_tf32x3_herk_launch(lm, ln, jb, -1.0, (const void *)Whi, (const void *)Wlo, (const void *)Whi, (const void *)Wlo,
+                                           w.kp, 1.0, (const void *)A22, lda, (void *)A22, lda, uplo, 1, (void *)sp));
       } else if (uplo == 'L') /* rest x jb2 block column, lower part */
         CU_ERROR_CHECK(chol_gemm_ex(prec, 'N', 'C', 0, 0, 0, 0, 'L', herm, rest, jb2, jb, MONE, W, w.ldw, W, w.ldw, ONE, A22,
                                     lda, A22, lda, sp));

@@ -1,5 +1,5 @@
 // emu_panel.cpp — the diagonal-block kernels of csrc/panel_kernels.cu executed on the CPU
-// (tests/emu/cuda_emu.h): potf2_inv (measured variant and V2), potf2, trti2, lauu2 against plain
+// (tests/emu/cuda_emu.h): potf2 (in-kernel look-ahead), trsm_rows, trti2, lauu2 against plain
 // loops, for lower / upper storage, full and ragged block sizes, and a non-positive-definite block.
 // Prints one line per case and "EMU PASSED" at the end; exit code 1 on the first mismatch.
 #define CUDA_EMU_IMPLEMENTATION
@@ -59,67 +59,41 @@ static void check(bool ok, const char *what, double err) {
   if (!ok) ++failures;
 }
 
-template <typename T, int NMAX, bool V2>
-static void run_potf2_inv(int upper, int n, int lda, std::vector<typename Host<T>::type> &A, std::vector<typename Host<T>::type> &X,
-                          long *info, long base) {
-  using Real = typename ScalarOf<T>::Real;
-  const size_t sm = (size_t)NMAX * (NMAX + 1) * sizeof(T) + NMAX * sizeof(Real);
-  X.assign((size_t)lda * n, typename Host<T>::type(55));
-  T *dA = reinterpret_cast<T *>(A.data()), *dX = reinterpret_cast<T *>(X.data());
-  emu::launch(dim3(1), dim3(PANEL_THREADS), sm, [&] {
-    potf2_inv_kernel<T, NMAX / 32, NMAX / 16, NMAX / 32, NMAX / 16, V2>(upper, n, dA, lda, dX, lda, info, base);
-  });
+template <typename T, int NMAX>
+static void run_potf2(int upper, int n, int lda, std::vector<typename Host<T>::type> &A, long *info, long base) {
+  const size_t sm = (size_t)NMAX * (NMAX + 1) * sizeof(T);
+  T *dA = reinterpret_cast<T *>(A.data());
+  emu::launch(dim3(1), dim3(PANEL_THREADS), sm, [&] { potf2_kernel<T, NMAX / 32, NMAX / 16>(upper, n, dA, lda, info, base); });
 }
 
+// potf2 (register-resident, in-kernel look-ahead): factor vs plain loops, other triangle and padding rows untouched
 template <typename T, int NMAX>
-static void case_potf2_inv(const char *name, int n, double tol) {
+static void case_potf2(const char *name, int n, double tol) {
   using H = typename Host<T>::type;
   const int lda = n + 3;
   for (int upper = 0; upper < 2; ++upper) {
-    std::vector<H> A0, A1, A2, X1, X2;
+    std::vector<H> A0, A1;
     spd<T, H>(n, lda, A0, 11u + n);
-    A1 = A0; A2 = A0;
-    long i1 = 0, i2 = 0;
-    if (getenv("EMU_TRACE")) std::fprintf(stderr, "[%s n=%d upper=%d] measured variant...\n", name, n, upper);
-    run_potf2_inv<T, NMAX, false>(upper, n, lda, A1, X1, &i1, 100);
-    if (getenv("EMU_TRACE")) std::fprintf(stderr, "  V2...\n");
-    run_potf2_inv<T, NMAX, true>(upper, n, lda, A2, X2, &i2, 100);
-    if (getenv("EMU_TRACE")) std::fprintf(stderr, "  reference + checks...\n");
-    // reference factor (lower form); for upper storage the kernel holds U = L^H
+    A1 = A0;
+    long i1 = 0;
+    if (getenv("EMU_TRACE")) std::fprintf(stderr, "[%s n=%d upper=%d] potf2...\n", name, n, upper);
+    run_potf2<T, NMAX>(upper, n, lda, A1, &i1, 100);
     std::vector<H> L = A0;
     const int ri = ref_potrf_lower(n, L, lda);
-    double e_ref = 0, e_v = 0, e_x = 0, e_other = 0, e_inv = 0;
+    double e_ref = 0, e_other = 0;
     for (int j = 0; j < n; ++j)
       for (int i = 0; i < n; ++i) {
         const bool in_tri = upper ? (i <= j) : (i >= j);
-        const H a1 = A1[i + (size_t)j * lda], a2 = A2[i + (size_t)j * lda];
-        if (in_tri) {
-          const H want = upper ? cj(L[j + (size_t)i * lda]) : L[i + (size_t)j * lda];
-          e_ref = std::max(e_ref, ab(a1 - want));
-          e_v = std::max(e_v, ab(a1 - a2));
-          e_x = std::max(e_x, ab(X1[i + (size_t)j * lda] - X2[i + (size_t)j * lda]));
-        } else {
-          e_other = std::max(e_other, ab(a1 - A0[i + (size_t)j * lda]) + ab(a2 - A0[i + (size_t)j * lda]));  // untouched
-          e_x = std::max(e_x, ab(X1[i + (size_t)j * lda]) + ab(X2[i + (size_t)j * lda]));                  // zeroed
-        }
-      }
-    // X * F = I  (lower: X = L^-1, F = L; upper: X = U^-1, F = U)
-    for (int j = 0; j < n; ++j)
-      for (int i = 0; i < n; ++i) {
-        H s = 0;
-        for (int k = 0; k < n; ++k) {
-          const bool xin = upper ? (i <= k) : (i >= k), fin = upper ? (k <= j) : (k >= j);
-          if (xin && fin) s += X2[i + (size_t)k * lda] * A2[k + (size_t)j * lda];
-        }
-        e_inv = std::max(e_inv, ab(s - H(i == j ? 1 : 0)));
+        const H a1 = A1[i + (size_t)j * lda];
+        if (in_tri) e_ref = std::max(e_ref, ab(a1 - (upper ? cj(L[j + (size_t)i * lda]) : L[i + (size_t)j * lda])));
+        else e_other = std::max(e_other, ab(a1 - A0[i + (size_t)j * lda]));
       }
     char what[160];
-    std::snprintf(what, sizeof what, "%s potf2_inv %s n=%d: info, factor vs loops, V2 == measured variant, X F = I", name, upper ? "upper" : "lower", n);
-    check(ri == 0 && i1 == 0 && i2 == 0 && e_ref <= tol && e_v == 0.0 && e_x == 0.0 && e_other == 0.0 && e_inv <= 50 * tol, what,
-          std::max(std::max(e_ref, e_v), std::max(e_x, e_inv)));
+    std::snprintf(what, sizeof what, "%s potf2 %s n=%d: info, factor vs loops, other triangle untouched", name, upper ? "upper" : "lower", n);
+    check(ri == 0 && i1 == 0 && e_ref <= tol && e_other == 0.0, what, e_ref);
     for (int j = 0; j < n; ++j)  // padding rows never touched
       for (int i = n; i < lda; ++i)
-        if (A2[i + (size_t)j * lda] != H(77)) { check(false, "padding rows of A overwritten", 0); return; }
+        if (A1[i + (size_t)j * lda] != H(77)) { check(false, "padding rows of A overwritten", 0); return; }
   }
 }
 
@@ -128,29 +102,108 @@ static void case_not_pd(const char *name, int n, int bad) {
   using H = typename Host<T>::type;
   const int lda = n;
   for (int upper = 0; upper < 2; ++upper) {
-    std::vector<H> A0, A1, A2, X1, X2;
+    std::vector<H> A0, A1;
     spd<T, H>(n, lda, A0, 5);
     A0[bad + (size_t)bad * lda] = H(-3);
-    A1 = A0; A2 = A0;
-    long i1 = 0, i2 = 0;
-    if (getenv("EMU_TRACE")) std::fprintf(stderr, "[not PD %s n=%d upper=%d] measured variant...\n", name, n, upper);
-    run_potf2_inv<T, NMAX, false>(upper, n, lda, A1, X1, &i1, 1000);
-    if (getenv("EMU_TRACE")) std::fprintf(stderr, "  V2...\n");
-    run_potf2_inv<T, NMAX, true>(upper, n, lda, A2, X2, &i2, 1000);
-    if (getenv("EMU_TRACE")) std::fprintf(stderr, "  done\n");
+    A1 = A0;
+    long i1 = 0;
+    if (getenv("EMU_TRACE")) std::fprintf(stderr, "[not PD %s n=%d upper=%d]...\n", name, n, upper);
+    run_potf2<T, NMAX>(upper, n, lda, A1, &i1, 1000);
+    // the columns finished before the failure are the reference's
+    std::vector<H> L = A0;
+    ref_potrf_lower(n, L, lda);  // stops at the bad column; columns < bad are final
     double e = 0;
-    for (size_t k = 0; k < A1.size(); ++k) e = std::max(e, ab(A1[k] - A2[k]));
+    for (int j = 0; j < bad; ++j)
+      for (int i = j; i < n; ++i) e = std::max(e, ab(A1[upper ? j + (size_t)i * lda : i + (size_t)j * lda] - (upper ? cj(L[i + (size_t)j * lda]) : L[i + (size_t)j * lda])));
     char what[160];
-    std::snprintf(what, sizeof what, "%s potf2_inv %s n=%d not PD at column %d: info and partial factor agree", name, upper ? "upper" : "lower", n, bad);
-    check(i1 == 1000 + bad + 1 && i2 == i1 && e == 0.0, what, e);
+    std::snprintf(what, sizeof what, "%s potf2 %s n=%d not PD at column %d: info, finished columns", name, upper ? "upper" : "lower", n, bad);
+    check(i1 == 1000 + bad + 1 && e <= 1e-10, what, e);
     // a kernel that finds *dinfo != 0 on entry must not touch anything
-    std::vector<H> A3 = A0, X3;
+    std::vector<H> A3 = A0;
     long i3 = 42;
-    run_potf2_inv<T, NMAX, true>(upper, n, lda, A3, X3, &i3, 0);
+    run_potf2<T, NMAX>(upper, n, lda, A3, &i3, 0);
     bool same = (i3 == 42);
     for (size_t k = 0; k < A3.size(); ++k) same = same && (A3[k] == A0[k]);
     check(same, "  ... and a block entered with info != 0 is left alone", 0);
   }
+}
+
+// trsm_rows: X = B * L^-H against plain substitution; lower / upper storage of the triangle, B and X plain or as
+// their conjugate transposes, in place and out of place, row counts that do not fill the last warp
+template <typename T, int NMAX, int G, int RR>
+static void case_trsm_rows(const char *name, int n, int m, int nwarps, double tol) {
+  using H = typename Host<T>::type;
+  using Real = typename ScalarOf<T>::Real;
+  const int ldl = n + 2;
+  std::mt19937 g(99u + n + m);
+  std::uniform_real_distribution<double> u(-0.5, 0.5);
+  auto rnd = [&]() -> H { if constexpr (ScalarOf<T>::cplx) return H((typename H::value_type)u(g), (typename H::value_type)u(g)); else return (H)u(g); };
+  std::vector<H> Lf((size_t)n * n, H(0));  // lower factor, diagonal real positive
+  for (int j = 0; j < n; ++j)
+    for (int i = j; i < n; ++i) Lf[i + (size_t)j * n] = (i == j) ? H(2.0 + 0.01 * i) : rnd();
+  for (int upper = 0; upper < 2; ++upper)
+    for (int tb = 0; tb < 2; ++tb)
+      for (int tx = 0; tx < 2; ++tx)
+        for (int inplace = 0; inplace < 2; ++inplace) {
+          if (inplace && tb != tx) continue;
+          std::vector<H> Ls((size_t)ldl * n, H(33));  // the other triangle holds a sentinel that must never be read
+          for (int j = 0; j < n; ++j)
+            for (int i = j; i < n; ++i) {
+              if (!upper) Ls[i + (size_t)j * ldl] = Lf[i + (size_t)j * n]; else Ls[j + (size_t)i * ldl] = cj(Lf[i + (size_t)j * n]);
+            }
+          const int ldb = (tb ? n : m) + 1, ldx = (tx ? n : m) + 3;
+          std::vector<H> Bm((size_t)m * n), Bs((size_t)ldb * (tb ? m : n), H(5)), Xs((size_t)ldx * (tx ? m : n), H(7));
+          for (auto &v : Bm) v = rnd();
+          for (int r = 0; r < m; ++r)
+            for (int j = 0; j < n; ++j) {
+              if (tb) Bs[j + (size_t)r * ldb] = cj(Bm[r + (size_t)j * m]); else Bs[r + (size_t)j * ldb] = Bm[r + (size_t)j * m];
+            }
+          std::vector<H> want((size_t)m * n);
+          for (int r = 0; r < m; ++r)
+            for (int k = 0; k < n; ++k) {
+              H sacc = Bm[r + (size_t)k * m];
+              for (int j = 0; j < k; ++j) sacc -= want[r + (size_t)j * m] * cj(Lf[k + (size_t)j * n]);
+              want[r + (size_t)k * m] = sacc / Lf[k + (size_t)k * n];
+            }
+          const size_t sm = (size_t)NMAX * (NMAX + 1) * sizeof(T) + NMAX * sizeof(Real);
+          const int cw = nwarps > 1 ? nwarps - 1 : 1;  // computing warps; a CTA's last warp only helps staging
+          const int rows_per_cta = cw * (32 / G) * RR, grid = (m + rows_per_cta - 1) / rows_per_cta;
+          const T *dL = reinterpret_cast<const T *>(Ls.data());
+          std::vector<H> &Out = inplace ? Bs : Xs;
+          const int ldo = inplace ? ldb : ldx;
+          const T *dB = reinterpret_cast<const T *>(Bs.data());
+          T *dX = reinterpret_cast<T *>(Out.data());
+          long zero = 0;
+          emu::launch(dim3(grid), dim3(nwarps * 32), sm, [&] {
+            trsm_rows_kernel<T, NMAX, G, RR>(upper, n, dL, ldl, m, cw, tb, dB, ldb, tx, dX, ldo, &zero);
+          });
+          double e = 0;
+          for (int r = 0; r < m; ++r)
+            for (int j = 0; j < n; ++j) {
+              const H got = tx ? cj(Out[j + (size_t)r * ldo]) : Out[r + (size_t)j * ldo];
+              e = std::max(e, ab(got - want[r + (size_t)j * m]));
+            }
+          bool pad_ok = true;  // padding rows of the output keep their sentinel
+          const H sent = inplace ? H(5) : H(7);
+          const int orow = tx ? n : m, ocol = tx ? m : n;
+          for (int c2 = 0; c2 < ocol; ++c2)
+            for (int r2 = orow; r2 < ldo; ++r2) pad_ok = pad_ok && Out[r2 + (size_t)c2 * ldo] == sent;
+          char what[200];
+          std::snprintf(what, sizeof what, "%s trsm_rows<G=%d,RR=%d> %s n=%d m=%d transB=%d transX=%d %s", name, G, RR, upper ? "upper" : "lower", n,
+                        m, tb, tx, inplace ? "in place" : "out of place");
+          check(e <= tol && pad_ok, what, e);
+        }
+  // a launch that finds *dinfo != 0 leaves X alone
+  std::vector<H> Ls((size_t)n * n, H(1)), Bs((size_t)m * n, H(2)), Xs((size_t)m * n, H(9));
+  long bad = 3;
+  const size_t sm = (size_t)NMAX * (NMAX + 1) * sizeof(T) + NMAX * sizeof(Real);
+  emu::launch(dim3(1), dim3(nwarps * 32), sm, [&] {
+    trsm_rows_kernel<T, NMAX, G, RR>(0, n, reinterpret_cast<const T *>(Ls.data()), n, m, nwarps, 0, reinterpret_cast<const T *>(Bs.data()), m, 0,
+                                     reinterpret_cast<T *>(Xs.data()), m, &bad);
+  });
+  bool same = true;
+  for (auto &v : Xs) same = same && v == H(9);
+  check(same, "  ... trsm_rows entered with info != 0 leaves X alone", 0);
 }
 
 // ---- the unfused kernels: potf2 (the last diagonal block of a factorisation), trti2, lauu2 ----
@@ -164,7 +217,7 @@ static void case_unfused(const char *name, int n, double tol) {
     A = A0;
     long info = 0;
     T *dA = reinterpret_cast<T *>(A.data());
-    emu::launch(dim3(1), dim3(PANEL_THREADS), 0, [&] { potf2_kernel<T, NMAX / 32, NMAX / 16>(upper, n, dA, lda, &info, 7); });
+    emu::launch(dim3(1), dim3(PANEL_THREADS), (size_t)NMAX * (NMAX + 1) * sizeof(T), [&] { potf2_kernel<T, NMAX / 32, NMAX / 16>(upper, n, dA, lda, &info, 7); });
     std::vector<H> L = A0;
     ref_potrf_lower(n, L, lda);
     double e = 0, e_other = 0;
@@ -236,7 +289,7 @@ static void case_unfused(const char *name, int n, double tol) {
   A0[bad + (size_t)bad * n] = H(-1);
   long info = 0;
   T *dA = reinterpret_cast<T *>(A0.data());
-  emu::launch(dim3(1), dim3(PANEL_THREADS), 0, [&] { potf2_kernel<T, NMAX / 32, NMAX / 16>(0, n, dA, n, &info, 500); });
+  emu::launch(dim3(1), dim3(PANEL_THREADS), (size_t)NMAX * (NMAX + 1) * sizeof(T), [&] { potf2_kernel<T, NMAX / 32, NMAX / 16>(0, n, dA, n, &info, 500); });
   char what[160];
   std::snprintf(what, sizeof what, "%s potf2 n=%d not PD at column %d: info", name, n, bad);
   check(info == 500 + bad + 1, what, 0);
@@ -305,19 +358,31 @@ static void case_copy_fill_logdet(const char *name) {
 
 int main() {
   std::setvbuf(stdout, nullptr, _IOLBF, 0);
-  if (!getenv("EMU_ONLY_NOT_PD")) {
-  case_potf2_inv<double, 128>("d", 128, 1e-12);
-  case_potf2_inv<double, 128>("d", 100, 1e-12);
-  case_potf2_inv<double, 128>("d", 37, 1e-12);
-  case_potf2_inv<double, 128>("d", 1, 1e-12);
-  case_potf2_inv<double2, 64>("z", 64, 1e-12);
-  case_potf2_inv<double2, 64>("z", 45, 1e-12);
-  case_potf2_inv<float, 128>("s", 97, 2e-4);
-  case_potf2_inv<float2, 128>("c", 80, 2e-4);
-  }
+  case_potf2<double, 128>("d", 128, 1e-12);
+  case_potf2<double, 128>("d", 100, 1e-12);
+  case_potf2<double, 128>("d", 37, 1e-12);
+  case_potf2<double, 128>("d", 17, 1e-12);
+  case_potf2<double, 128>("d", 16, 1e-12);
+  case_potf2<double, 128>("d", 1, 1e-12);
+  case_potf2<double2, 64>("z", 64, 1e-12);
+  case_potf2<double2, 64>("z", 45, 1e-12);
+  case_potf2<float, 128>("s", 97, 2e-4);
+  case_potf2<float2, 128>("c", 80, 2e-4);
   case_not_pd<double, 128>("d", 128, 70);
+  case_not_pd<double, 128>("d", 128, 127);
+  case_not_pd<double, 128>("d", 128, 16);
   case_not_pd<double, 128>("d", 50, 0);
+  case_not_pd<double, 128>("d", 50, 1);
   case_not_pd<double2, 64>("z", 64, 33);
+  case_trsm_rows<double, 128, 32, 1>("d", 128, 5, 2, 1e-12);
+  case_trsm_rows<double, 128, 32, 1>("d", 77, 3, 4, 1e-12);
+  case_trsm_rows<double, 128, 8, 4>("d", 128, 37, 2, 1e-12);
+  case_trsm_rows<double, 128, 8, 4>("d", 50, 16, 1, 1e-12);
+  case_trsm_rows<double2, 64, 32, 1>("z", 64, 3, 2, 1e-12);
+  case_trsm_rows<double2, 64, 8, 4>("z", 41, 21, 2, 1e-12);
+  case_trsm_rows<float, 128, 8, 4>("s", 100, 20, 1, 2e-4);
+  case_trsm_rows<float2, 128, 16, 4>("c", 128, 11, 2, 2e-4);
+  case_trsm_rows<float2, 128, 32, 1>("c", 90, 2, 2, 2e-4);
   case_unfused<double, 128>("d", 128, 1e-12);
   case_unfused<double, 128>("d", 70, 1e-12);
   case_unfused<double2, 64>("z", 50, 1e-12);

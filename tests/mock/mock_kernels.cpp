@@ -198,6 +198,25 @@ int lauu2_t(bool upper, size_t n, T *A, size_t lda) {
   return 0;
 }
 
+// X = B * L^-H by substitution from the documented semantics (csrc/chol_kernels.h): element (row, j) of B / X sits
+// at ptr[j * ld + row], or - transposed forms - conjugated at ptr[row * ld + j]
+template <typename T>
+int trsm_rows_t(bool upper, size_t n, const T *L, size_t ldl, size_t m, int transB, const T *B, size_t ldb, int transX, T *X,
+                       size_t ldx, const long *dinfo) {
+  if (dinfo != nullptr && *dinfo != 0) return 0;
+  std::vector<T> x(n);
+  for (size_t r = 0; r < m; ++r) {
+    for (size_t j = 0; j < n; ++j) x[j] = transB ? cj(B[r * ldb + j]) : B[j * ldb + r];
+    for (size_t k = 0; k < n; ++k) {
+      T s = x[k];
+      for (size_t j = 0; j < k; ++j) s -= x[j] * cj(getL(L, ldl, upper, k, j));  // conj(L(k,j)), j < k
+      x[k] = s / getL(L, ldl, upper, k, k);
+    }
+    for (size_t j = 0; j < n; ++j) { if (transX) X[r * ldx + j] = cj(x[j]); else X[j * ldx + r] = x[j]; }
+  }
+  return 0;
+}
+
 bool keep(int uplo, size_t r, size_t c) {
   return uplo == 0 || (uplo == 'L' && r >= c) || (uplo == 'U' && r <= c) || (uplo == 'l' && r > c) || (uplo == 'u' && r < c);
 }
@@ -251,11 +270,12 @@ int chol_potf2_launch(int prec, int uplo, size_t n, void *A, size_t lda, long *d
   if (!known(prec) || n > (size_t)chol_diag_max(prec)) return 1;
   return enqueue(st, [=] { DISPATCH(prec, potf2_t<T>(uplo == 'U', n, (T *)A, lda, dinfo, base, (T *)nullptr, 0)) });
 }
-int chol_potf2_inv_launch(int prec, int uplo, size_t n, void *A, size_t lda, void *X, size_t ldx, long *dinfo, long base, void *st) {
+int chol_trsm_rows_launch(int prec, int uplo, size_t n, const void *L, size_t ldl, size_t m, int transB, const void *B, size_t ldb,
+                          int transX, void *X, size_t ldx, const long *dinfo, void *st) {
   __sync_fetch_and_add(&launches, 1);
-  if (n == 0) return 0;
+  if (n == 0 || m == 0) return 0;
   if (!known(prec) || n > (size_t)chol_diag_max(prec)) return 1;
-  return enqueue(st, [=] { DISPATCH(prec, potf2_t<T>(uplo == 'U', n, (T *)A, lda, dinfo, base, (T *)X, ldx)) });
+  return enqueue(st, [=] { DISPATCH(prec, trsm_rows_t<T>(uplo == 'U', n, (const T *)L, ldl, m, transB, (const T *)B, ldb, transX, (T *)X, ldx, dinfo)) });
 }
 int chol_trti2_launch(int prec, int uplo, int diag, size_t n, const void *A, size_t lda, void *B, size_t ldb, int zero_other, long *dinfo,
                       long base, void *st) {
@@ -326,6 +346,49 @@ int chol_tf32x3_gemm_launch(size_t m, size_t n, size_t k, double alpha, const vo
         for (size_t q = 0; q < k; ++q)
           acc += al[i * kp + q] * bh[j * kp + q] + ah[i * kp + q] * bl[j * kp + q] + ah[i * kp + q] * bh[j * kp + q];
         d[j * ldd + i] = (float)alpha * acc + (beta != 0.0 ? (float)beta * c[j * ldc + i] : 0.f);
+      }
+  });
+}
+// c: planes of the real embedding, from the documented layout (csrc/chol_kernels.h): plane row 2i = (Re, Im) pairs of
+// W's row i, plane row 2i+1 = (Im, -Re) pairs; pitch kp floats
+int chol_tf32_split_c_launch(size_t rows, size_t k, const void *W, size_t ldw, void *hi, void *lo, size_t kp, void *st) {
+  __sync_fetch_and_add(&launches, 1);
+  return enqueue(st, [=] {
+    const std::complex<float> *w = (const std::complex<float> *)W;
+    float *h = (float *)hi, *l = (float *)lo;
+    for (size_t r = 0; r < rows; ++r)
+      for (size_t c = 0; 2 * c < kp; ++c) {
+        const std::complex<float> x = c < k ? w[c * ldw + r] : std::complex<float>(0.f, 0.f);
+        const float v[2][2] = {{x.real(), x.imag()}, {x.imag(), -x.real()}};
+        for (int o = 0; o < 2; ++o)
+          for (int q = 0; q < 2; ++q) {
+            const size_t at = (2 * r + o) * kp + 2 * c + q;
+            h[at] = mock_tf32(v[o][q]);
+            l[at] = mock_tf32(v[o][q] - h[at]);
+          }
+      }
+  });
+}
+int chol_tf32x3_herk_launch(size_t m, size_t n, size_t k, double alpha, const void *Ahi, const void *Alo, const void *Bhi, const void *Blo,
+                            size_t kp, double beta, const void *C, size_t ldc, void *D, size_t ldd, int cuplo, int herm, void *st) {
+  __sync_fetch_and_add(&launches, 1);
+  return enqueue(st, [=] {
+    const float *ah = (const float *)Ahi, *al = (const float *)Alo, *bh = (const float *)Bhi, *bl = (const float *)Blo;
+    const std::complex<float> *c = (const std::complex<float> *)C;
+    std::complex<float> *d = (std::complex<float> *)D;
+    for (size_t j = 0; j < n; ++j)
+      for (size_t i = 0; i < m; ++i) {
+        if ((cuplo == 'L' && i < j) || (cuplo == 'U' && i > j)) continue;
+        float acc[2] = {0.f, 0.f};
+        for (int o = 0; o < 2; ++o)
+          for (size_t q = 0; q < 2 * k; ++q) {
+            const size_t ia = (2 * i + o) * kp + q, ib = (2 * j) * kp + q;
+            acc[o] += al[ia] * bh[ib] + ah[ia] * bl[ib] + ah[ia] * bh[ib];
+          }
+        std::complex<float> v = (float)alpha * std::complex<float>(acc[0], acc[1]);
+        if (beta != 0.0) v += (float)beta * c[j * ldc + i];
+        if (herm && i == j) v = std::complex<float>(v.real(), 0.f);
+        d[j * ldd + i] = v;
       }
   });
 }

@@ -214,7 +214,7 @@ def test_dpotrf_large_properties(lapack, uplo):
     assert abs(ld - want) <= 1e-12 * abs(want)
 
 
-@pytest.mark.parametrize("p,n", [("d", 4096), ("z", 2048), ("s", 4096)])
+@pytest.mark.parametrize("p,n", [("d", 4096), ("z", 2048), ("s", 4096), ("c", 2048)])
 @pytest.mark.parametrize("uplo", "LU")
 def test_potrf_full_elementwise_vs_oracle_mid_size(lapack, p, uplo, n):
     """SURVEY.md section 8d, config 2 style: the WHOLE factor against the CPU oracle (which is pinned to the

@@ -259,11 +259,45 @@ def test_dist_single_rank_core(p):
     d.close()
 
 
-@pytest.mark.skipif(NGPU < 2, reason="needs >= 2 GPUs")
-def test_multigpu_potrf_large_all_gpus(mgpu):
-    n = 6000
+def _cpu_potrf_fast(p, uplo, A):
+    """the compiled reference (OpenMP) when it is there, else the oracle port"""
+    lib = H.CpuLib("ref") if H.ref() is not None else ORA
+    return lib.potrf(p, uplo, A)
+
+
+@pytest.mark.parametrize("uplo", "LU")
+def test_multigpu_potrf_large_all_gpus(mgpu, uplo):
+    """In-process cuMultiGPUDpotrf over ALL visible devices (one worker thread per GPU, ncclCommInitAll inside the
+    library; the reference's model, lapack/dpotrf.c:298-366, test/lapack/cumultigpudpotrf.c:47-60) at a size with
+    several block columns per GPU, elementwise against the reference's CPU dpotrf."""
+    n = 6400
     A = H.spd_matrix("d", n, k=64)
     A0 = A.copy()
-    assert mgpu.potrf("d", "L", n, A.ctypes.data, n) == 0
-    L = np.tril(A)
-    assert np.linalg.norm(L @ L.T - A0) / np.linalg.norm(A0) <= 1e-13
+    want = A.copy(order="F")
+    assert _cpu_potrf_fast("d", uplo, want) == 0
+    assert mgpu.potrf("d", uplo, n, A.ctypes.data, n) == 0
+    assert np.abs(H.tri(A, uplo) - H.tri(want, uplo)).max() <= 64 * n * H.eps("d") * np.abs(want).max()
+    other = np.triu(A, 1) if uplo == "L" else np.tril(A, -1)
+    other0 = np.triu(A0, 1) if uplo == "L" else np.tril(A0, -1)
+    assert np.array_equal(other, other0)
+    F = H.tri(A, uplo)
+    R = F @ F.T if uplo == "L" else F.T @ F
+    assert np.linalg.norm(R - A0) / np.linalg.norm(A0) <= 1e-13
+
+
+@pytest.mark.skipif(NGPU < 2, reason="needs >= 2 GPUs")
+def test_cholDist_torchrun_parity_all_gpus(tmp_path):
+    """One process per GPU under torch.distributed.run (the form bench.py --gpus N times): every rank factors its
+    block-cyclic columns with cholDistDpotrf over NCCL; rank 0 gathers the factor and compares it elementwise with the
+    reference's CPU dpotrf."""
+    import subprocess
+    import sys
+    out = tmp_path / "dist_parity.json"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(NGPU), "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(H.ROOT, "tests", "dist_parity_worker.py"), "5000", str(out)]
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
+    assert p.returncode == 0, p.stdout.decode()[-4000:]
+    import json
+    r = json.load(open(out))
+    assert r["info"] == 0 and r["ranks"] == NGPU
+    assert r["maxrel"] <= 64 * r["n"] * H.eps("d"), r

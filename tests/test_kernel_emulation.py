@@ -1,5 +1,5 @@
 """Kernel LOGIC on the CPU: the CUDA sources of the diagonal-block kernels (csrc/panel_kernels.cu:
-potf2_inv in its measured and V2 variants, potf2, trti2, lauu2), of the small-tile FP64 GEMM
+potf2 with its in-kernel look-ahead, the substitution kernel trsm_rows, trti2, lauu2), of the small-tile FP64 GEMM
 (csrc/gemm_small.cu) and of the FP32 GEMM engine (csrc/gemm_ffma.cu) are compiled as host C++ behind tests/emu/cuda_emu.h - one OS thread per CUDA
 thread, real barriers, warp shuffles through a per-warp exchange, cp.async groups that complete as
 late as wait_group allows - and run against plain loops.  The FP64 tensor-core engine (csrc/gemm_dmma.cu)
@@ -60,8 +60,9 @@ def _passed(emu, src):
 
 def test_panel_kernels_emulated(emu):
     out = _passed(emu, "emu_panel.cpp")
-    assert out.count("V2 == measured variant") >= 16  # d, z, s, c x lower/upper x full and ragged blocks
-    assert out.count("not PD") >= 6
+    assert out.count("info, factor vs loops, other triangle untouched") >= 20  # potf2: d, z, s, c x lower/upper x full and ragged blocks
+    assert out.count("not PD") >= 12
+    assert out.count("trsm_rows<") >= 100  # both shapes x d, z, s, c x storage x transposed operands x in / out of place
 
 
 def test_small_gemm_kernel_emulated(emu):
