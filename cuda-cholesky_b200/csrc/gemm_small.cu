@@ -13,7 +13,7 @@
 // Scope (everything else stays on the DMMA engine): prec 'd', no triangular operand masks, no
 // block-cyclic map; any op(A)/op(B), any alignment, alpha/beta, C != D, cuplo (triangle-only
 // output, diagonal-crossing tiles masked per element).
-//   CTA 128 threads = 16 (m) x 8 (n), thread tile 2 x 4, CTA tile 32 x 32, k-chunks of 16 staged in
+//   CTA 128 threads = 16 (m) x 8 (n), thread tile 2 x 4, CTA tile 32 x 32, k-chunks of 32 staged in
 //   shared memory as [k][m] / [k][n] (pitch 34: 16-byte aligned rows), next chunk prefetched into
 //   registers while the current one is multiplied.
 #include <cuda_runtime.h>
@@ -36,7 +36,8 @@ struct SmallArgs {
   int beta_zero;
 };
 
-constexpr int S_BM = 32, S_BN = 32, S_BK = 16, S_LD = 34, S_THREADS = 128;
+constexpr int S_BM = 32, S_BN = 32, S_BK = 32, S_LD = 34, S_THREADS = 128;  // k-chunks of 32: the panel-chain shapes (k = 128) are four chunks
+constexpr int S_LPT = S_BM * S_BK / S_THREADS;  // operand elements per thread and chunk
 
 __global__ void __launch_bounds__(S_THREADS) dgemm_small_kernel(const __grid_constant__ SmallArgs p) {
   __shared__ __align__(16) double As[S_BK * S_LD];
@@ -47,18 +48,18 @@ __global__ void __launch_bounds__(S_THREADS) dgemm_small_kernel(const __grid_con
   if (p.cuplo == 2 && m0 > n0 + S_BN - 1) return;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;  // rows 2*tx, 2*tx+1; columns 4*ty .. 4*ty+3
 
-  // loader coordinates: 512 elements per operand chunk, 4 per thread; the fast index follows the
+  // loader coordinates: S_BM * S_BK elements per operand chunk, S_LPT per thread; the fast index follows the
   // stored (contiguous) direction so that global reads coalesce
-  int a_mm[4], a_kk[4], b_nn[4], b_kk[4];
+  int a_mm[S_LPT], a_kk[S_LPT], b_nn[S_LPT], b_kk[S_LPT];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
+  for (int r = 0; r < S_LPT; ++r) {
     const int idx = tid + S_THREADS * r;
     if (p.opA == 0) { a_mm[r] = idx % S_BM; a_kk[r] = idx / S_BM; } else { a_kk[r] = idx % S_BK; a_mm[r] = idx / S_BK; }
     if (p.opB != 0) { b_nn[r] = idx % S_BN; b_kk[r] = idx / S_BN; } else { b_kk[r] = idx % S_BK; b_nn[r] = idx / S_BK; }
   }
-  auto fetch = [&](int k0, double (&ra)[4], double (&rb)[4]) {
+  auto fetch = [&](int k0, double (&ra)[S_LPT], double (&rb)[S_LPT]) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < S_LPT; ++r) {
       const long long m = m0 + a_mm[r], n = n0 + b_nn[r], ka = k0 + a_kk[r], kb = k0 + b_kk[r];
       // op(A)(m, k): N -> A[k*lda + m], T -> A[m*lda + k];  op(B)(k, n): N -> B[n*ldb + k], T -> B[k*ldb + n]
       ra[r] = (m < p.M && ka < p.K) ? (p.opA == 0 ? p.A[ka * p.lda + m] : p.A[m * p.lda + ka]) : 0.0;
@@ -72,12 +73,12 @@ __global__ void __launch_bounds__(S_THREADS) dgemm_small_kernel(const __grid_con
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
 
-  double ra[4], rb[4];
+  double ra[S_LPT], rb[S_LPT];
   const int nk = (p.K + S_BK - 1) / S_BK;
   if (nk > 0) fetch(0, ra, rb);
   for (int kt = 0; kt < nk; ++kt) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < S_LPT; ++r) {
       As[a_kk[r] * S_LD + a_mm[r]] = ra[r];
       Bs[b_kk[r] * S_LD + b_nn[r]] = rb[r];
     }

@@ -105,51 +105,75 @@ __device__ __forceinline__ T shfl_elem(T v, int src) {
 // needs no per-element mask.  History: the round-1/2 kernels did one barrier per COLUMN with a masked, branch-free
 // rank-1 update on all 16 warps - issue-bound at 600-850 cycles per column (80 us fused with the inverse, 45-51 us
 // alone); fully unrolled register-only variants of this kernel ran to 12k instructions (instruction-fetch bound).
+// One warp factors its CW-column panel (columns c0 .. c0+CW-1, rows >= c0) held in reg[a][b] and publishes it in Ls.
+// The serial recurrence of a Cholesky column is SCALAR - d(c+1) needs only rsqrt(d(c)) and one entry of column c - so
+// every lane factors the panel's CW x CW diagonal block redundantly in its own registers (broadcast loads, then
+// rsqrt -> multiply -> FMA per column: ~80 cycles, no shuffle, no shared-memory round trip, no branch), and then
+// solves its own rows against that block by substitution, also in registers.  Measured alternatives (r02 calls
+// 5, 6): a barrier per column ~600 cycles per column, a shared-memory panel with per-column branches ~450.
 template <typename T, int NA, int CW, int LD>
-__device__ __forceinline__ void potf2_panel(T *Ls, int c0, int n, int lane, int *sfail, T *A, long long lda, long *dinfo, long info_base) {
+__device__ __forceinline__ void potf2_panel(T (&reg)[NA][CW], T *Ls, int c0, int n, int lane, int *sfail, T *A, long long lda,
+                                            long *dinfo, long info_base) {
   using Real = typename ScalarOf<T>::Real;
-  const int amin = c0 >> 5;  // 32-row slices above it hold only zeros of this panel
-#pragma unroll 1
-  for (int t = 0; t < CW; ++t) {
-    const int c = c0 + t;
-    if (c >= n) break;
-    T *colc = Ls + c * LD;
-    const Real d = re_of(colc[c]);
-    T x[NA], u[CW];
+  // the panel enters shared memory as it is (rows above the diagonal block hold finite garbage that is never used)
 #pragma unroll
-    for (int a = 0; a < NA; ++a) x[a] = colc[lane + 32 * a];
+  for (int a = 0; a < NA; ++a)
 #pragma unroll
-    for (int t2 = 1; t2 < CW; ++t2) u[t2] = colc[c0 + t2];  // unscaled L(c0 + t2, c) for the columns right of c (t2 > t)
-    __syncwarp();  // all lanes have read column c before anyone overwrites it
-    // rsqrt, scale, publish unconditionally: the positivity test stays off the chain (a bad pivot leaves garbage
-    // that nobody uses - every thread of the CTA leaves after the next barrier)
-    const Real rinv = rsqrt(d), r = d * rinv;
+    for (int b = 0; b < CW; ++b) Ls[lane + 32 * a + (c0 + b) * LD] = reg[a][b];
+  __syncwarp();
+  T D[CW][CW];  // lower triangle of the diagonal block, the same in every lane
 #pragma unroll
-    for (int a = 0; a < NA; ++a) {
-      const int i = lane + 32 * a;
-      x[a] = (i > c) ? rscale(x[a], rinv) : ((i == c) ? from_real<T>(r) : zero_of<T>());
-      colc[i] = x[a];
+  for (int s = 0; s < CW; ++s)
+#pragma unroll
+    for (int r = s; r < CW; ++r) D[r][s] = Ls[(c0 + r) + (c0 + s) * LD];
+  Real rinv[CW];
+  int bad = 0;  // first failing column of the panel + 1 (uniform over the warp)
+  Real dbad = Real(0);
+#pragma unroll
+  for (int s = 0; s < CW; ++s) {
+    const Real d = re_of(D[s][s]);
+    const bool live = c0 + s < n;  // columns beyond n are zero: keep them zero instead of dividing by it
+    if (live && !(d > Real(0)) && bad == 0) { bad = s + 1; dbad = d; }  // <= 0 or NaN: not positive definite (lapack/dpotrf.c:70-73)
+    rinv[s] = live ? rsqrt(d) : Real(0);
+    D[s][s] = from_real<T>(d * rinv[s]);
+#pragma unroll
+    for (int r = s + 1; r < CW; ++r) D[r][s] = rscale(D[r][s], rinv[s]);
+#pragma unroll
+    for (int s2 = s + 1; s2 < CW; ++s2) {
+      const T m = neg(conj_of(D[s2][s]));
+#pragma unroll
+      for (int r = s2; r < CW; ++r) fma_acc(D[r][s2], D[r][s], m);
     }
-    if (!(d > Real(0)) && lane == 0 && *sfail == 0) {  // <= 0 or NaN: not positive definite (lapack/dpotrf.c:70-73)
-      *sfail = c + 1;
-      *dinfo = info_base + c + 1;
-      A[(long long)c * lda + c] = from_real<T>(d);
+  }
+  if (bad != 0 && lane == 0 && *sfail == 0) {  // the columns after it hold garbage that nobody uses: the CTA leaves at the next barrier
+    const int c = c0 + bad - 1;
+    *sfail = c + 1;
+    *dinfo = info_base + c + 1;
+    A[(long long)c * lda + c] = from_real<T>(dbad);  // the reference leaves the updated pivot in place (dpotrf.c:45-49)
+  }
+  // every lane's rows: x(i, :) = a(i, :) * Ldd^-H by substitution (right-looking over the CW columns); for a row
+  // INSIDE the diagonal block the same recurrence reproduces the factor's row, beyond its diagonal it is masked.
+  // The rows are read back from the shared copy (the register copy is dead since the dump: the diagonal block
+  // above needs the registers).
+  __syncwarp();
+#pragma unroll
+  for (int a = 0; a < NA; ++a) {
+    const int i = lane + 32 * a;
+    T x[CW];
+#pragma unroll
+    for (int s = 0; s < CW; ++s) x[s] = Ls[i + (c0 + s) * LD];
+#pragma unroll
+    for (int s = 0; s < CW; ++s) {
+      x[s] = rscale(x[s], rinv[s]);
+#pragma unroll
+      for (int s2 = s + 1; s2 < CW; ++s2) fma_acc(x[s2], x[s], neg(conj_of(D[s2][s])));
     }
 #pragma unroll
-    for (int t2 = 1; t2 < CW; ++t2) {
-      if (t2 > t) {  // uniform
-        T *col2 = Ls + (c0 + t2) * LD;
-        const T m = neg(conj_of(rscale(u[t2], rinv)));
-#pragma unroll
-        for (int a = 0; a < NA; ++a)
-          if (a >= amin) {
-            T v = col2[lane + 32 * a];
-            fma_acc(v, x[a], m);
-            col2[lane + 32 * a] = v;
-          }
-      }
+    for (int s = 0; s < CW; ++s) {
+      T v = (i >= c0 + s) ? x[s] : zero_of<T>();
+      if constexpr (ScalarOf<T>::cplx) { if (i == c0 + s) v.y = 0; }  // the diagonal is real
+      Ls[i + (c0 + s) * LD] = v;
     }
-    __syncwarp();  // the updated columns are visible to all lanes before the next pivot is read
   }
 }
 
@@ -163,63 +187,95 @@ __global__ void __launch_bounds__(PANEL_THREADS) potf2_kernel(int upper, int n, 
   if (*dinfo != 0) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) sfail = 0;
-  for (int idx = threadIdx.x; idx < NMAX * LD; idx += PANEL_THREADS) Ls[idx] = zero_of<T>();
-  __syncthreads();
-  // the block enters through the shared buffer, so that the HBM reads are coalesced for both storages
-  load_lower_form(Ls, LD, upper, true, n, A, lda);
+  // The block enters through the shared buffer, so that the HBM reads are coalesced for both storages (lanes along
+  // the stored columns; upper: transposed on the way in).  Every thread issues ALL its loads before the first store -
+  // a one-CTA kernel has nothing else to hide the HBM latency with - and writes zeros for everything outside the
+  // triangle / beyond n, so the buffer is fully defined.
+  {
+    constexpr int PER = NMAX * NMAX / PANEL_THREADS;
+    T v[PER];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int idx = threadIdx.x + u * PANEL_THREADS, r = idx % NMAX, c = idx / NMAX;  // r fast: rows of the stored column c
+      v[u] = zero_of<T>();
+      if (r < n && c < n && (upper ? r <= c : r >= c)) v[u] = A[(long long)c * lda + r];
+    }
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int idx = threadIdx.x + u * PANEL_THREADS, r = idx % NMAX, c = idx / NMAX;
+      if (!upper) Ls[r + c * LD] = v[u];                 // (r, c): the triangle, zeros above it
+      else if (r <= c) Ls[c + r * LD] = conj_of(v[u]);   // L = U^H: element (c, r) of the lower form
+      else Ls[c + r * LD] = zero_of<T>();                // r > c: slot (c, r) lies above the diagonal of the lower form
+    }
+  }
   __syncthreads();
   T reg[NA][CW];
 #pragma unroll
   for (int a = 0; a < NA; ++a)
 #pragma unroll
     for (int b = 0; b < CW; ++b) reg[a][b] = Ls[lane + 32 * a + (CW * warp + b) * LD];  // zeros above the diagonal / beyond n
-  if (warp == 0) potf2_panel<T, NA, CW, LD>(Ls, 0, n, lane, &sfail, A, lda, dinfo, info_base);
-  __syncthreads();  // panel 0 is published
+  const int np = (n + CW - 1) / CW;  // panels (uniform: n is a kernel argument)
+  // Round p starts with panel p published.  A failure in it (or before) was flagged BEFORE the barrier that published
+  // it; a flag raised meanwhile by the owner of panel p+1 lies beyond CW*p + CW and is ignored until the next round,
+  // so every thread leaves after the same barrier.
+#define CHOL_POTF2_LEAVE_IF_FAILED(p)                                                                              \
+  do {                                                                                                             \
+    const int fail = sfail;                                                                                        \
+    if (fail != 0 && fail <= CW * (p) + CW) {                                                                      \
+      store_factor_columns<T, NA, LD>(upper, n, fail - 1, Ls, A, lda, warp, lane); /* the columns before it */     \
+      return;                                                                                                      \
+    }                                                                                                              \
+  } while (false)
+  // rank-CW update of this warp's panel with panel p: a(i,k) -= sum_j L(i,cj) conj(L(k,cj)), cj = CW*p + j
+  const int amin = (CW * warp) >> 5;  // slices above it lie entirely above this warp's diagonal block
+  auto update = [&](int p) {
+#pragma unroll
+    for (int j = 0; j < CW; ++j) {
+      const T *col = Ls + (CW * p + j) * LD;
+      T li[NA], f[CW];
+#pragma unroll
+      for (int a = 0; a < NA; ++a) li[a] = col[lane + 32 * a];
+#pragma unroll
+      for (int b = 0; b < CW; ++b) f[b] = neg(conj_of(col[CW * warp + b]));
+#pragma unroll
+      for (int a = 0; a < NA; ++a)
+        if (a >= amin) {
+#pragma unroll
+          for (int b = 0; b < CW; ++b) fma_acc(reg[a][b], li[a], f[b]);
+        }
+    }
+  };
+  int p = 0;
+  if (warp == 0) {  // panel 0 needs no update
+    potf2_panel<T, NA, CW, LD>(reg, Ls, 0, n, lane, &sfail, A, lda, dinfo, info_base);
+    __syncthreads();  // panel 0 is published
+  } else {
+    __syncthreads();
+    // rounds in which this warp updates its panel and waits ...
 #pragma unroll 1
-  for (int p = 0; p < 16; ++p) {
-    const int c0 = CW * p;
-    if (c0 >= n) break;  // uniform: n is a kernel argument
-    // Panel p is published.  A failure in it (or before) was flagged BEFORE the barrier that published it; a flag
-    // raised meanwhile by the owner of panel p+1 lies beyond c0 + CW and is ignored until the next round, so every
-    // thread leaves after the same barrier.
-    const int fail = sfail;
-    if (fail != 0 && fail <= c0 + CW) {
-      store_factor_columns<T, NA, LD>(upper, n, fail - 1, Ls, A, lda, warp, lane);  // the columns finished before it
-      return;
+    for (; p + 1 < warp && p < np; ++p) {
+      CHOL_POTF2_LEAVE_IF_FAILED(p);
+      update(p);
+      __syncthreads();
     }
-    if (warp > p) {
-      // rank-CW update of this warp's panel: a(i,k) -= sum_j L(i,cj) conj(L(k,cj)), cj = c0 + j
-      const int amin = (CW * warp) >> 5;  // slices above it lie entirely above this panel's diagonal
-#pragma unroll
-      for (int j = 0; j < CW; ++j) {
-        const T *col = Ls + (c0 + j) * LD;
-        T li[NA], f[CW];
-#pragma unroll
-        for (int a = 0; a < NA; ++a) li[a] = col[lane + 32 * a];
-#pragma unroll
-        for (int b = 0; b < CW; ++b) f[b] = neg(conj_of(col[CW * warp + b]));
-#pragma unroll
-        for (int a = 0; a < NA; ++a)
-          if (a >= amin) {
-#pragma unroll
-            for (int b = 0; b < CW; ++b) fma_acc(reg[a][b], li[a], f[b]);
-          }
-      }
-      // look-ahead: the owner of the next panel writes it back (zeros above the diagonal), factors and publishes it
-      if (warp == p + 1 && c0 + CW < n) {
-#pragma unroll
-        for (int a = 0; a < NA; ++a)
-#pragma unroll
-          for (int b = 0; b < CW; ++b) {
-            const int i = lane + 32 * a, k = CW * warp + b;
-            Ls[i + k * LD] = (i >= k) ? reg[a][b] : zero_of<T>();
-          }
-        __syncwarp();
-        potf2_panel<T, NA, CW, LD>(Ls, c0 + CW, n, lane, &sfail, A, lda, dinfo, info_base);
-      }
+    // ... the round in which it is the look-ahead owner: last update, then it factors and publishes its own panel
+    // while the warps right of it are still busy with their updates (the registers are dead from there on, which is
+    // what lets the panel routine keep its diagonal block in registers) ...
+    if (p < np && p == warp - 1) {
+      CHOL_POTF2_LEAVE_IF_FAILED(p);
+      update(p);
+      if (CW * warp < n) potf2_panel<T, NA, CW, LD>(reg, Ls, CW * warp, n, lane, &sfail, A, lda, dinfo, info_base);
+      __syncthreads();
+      ++p;
     }
-    __syncthreads();  // panel p+1 is published
   }
+  // ... and the rounds after it has retired: only the barriers
+#pragma unroll 1
+  for (; p < np; ++p) {
+    CHOL_POTF2_LEAVE_IF_FAILED(p);
+    __syncthreads();
+  }
+#undef CHOL_POTF2_LEAVE_IF_FAILED
   {
     const int fail = sfail;  // a failure in the last panel
     store_factor_columns<T, NA, LD>(upper, n, fail != 0 ? fail - 1 : n, Ls, A, lda, warp, lane);
@@ -248,7 +304,7 @@ __global__ void __launch_bounds__(256) trsm_rows_kernel(int upper, int n, const 
                                                         const T *B, long long ldb, int transX, T *X, long long ldx,
                                                         const long *dinfo) {
   using Real = typename ScalarOf<T>::Real;
-  constexpr int LD = NMAX + 1, NT = NMAX / G, NG = 32 / G, U = 8;
+  constexpr int LD = NMAX + 1, NT = NMAX / G, NG = 32 / G;
   CHOL_DYN_SMEM(smem_raw);
   T *Ms = reinterpret_cast<T *>(smem_raw);                         // Ms[k * LD + j] = conj(L(j,k)) / L(k,k), j > k
   Real *dinv = reinterpret_cast<Real *>(Ms + (size_t)NMAX * LD);   // 1 / L(k,k)
@@ -256,24 +312,26 @@ __global__ void __launch_bounds__(256) trsm_rows_kernel(int upper, int n, const 
   // With y_k = b_k - sum_{j<k} x_j conj(L_kj) and x_k = y_k / L_kk the recurrence reads
   //     y_k = b_k - sum_{j<k} y_j * M[j][k],   M[j][k] = conj(L_kj) / L_jj,
   // so the serial chain of a step is one shuffle and one FMA (no multiply); x = y / diag(L) at the very end.
-  for (int i = threadIdx.x; i < NMAX; i += blockDim.x) dinv[i] = (i < n) ? Real(1) / re_of(L[(long long)i * ldl + i]) : Real(0);
-  __syncthreads();
-  // all threads of the CTA stage (also the warps that have no rows), every thread a batch of independent loads;
-  // lanes along the contiguous direction of the storage: lower -> j (rows of L), upper -> k (rows of U)
-  for (int base = threadIdx.x; base < NMAX * NMAX; base += U * blockDim.x) {
-    T v[U];
+  // all 256 threads of the CTA stage (also the warps that own no rows), ALL loads of a thread in flight at once;
+  // lanes along the contiguous direction of the storage: lower -> j (rows of L), upper -> k (rows of U).  The
+  // reciprocals of the diagonal are computed while those loads are in flight.
+  {
+    constexpr int PER = NMAX * NMAX / 256;
+    T v[PER];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int idx = base + u * blockDim.x, fast = idx % NMAX, slow = idx / NMAX;
+    for (int u = 0; u < PER; ++u) {
+      const int idx = threadIdx.x + u * 256, fast = idx % NMAX, slow = idx / NMAX;
       const int j = upper ? slow : fast, k = upper ? fast : slow;
       v[u] = zero_of<T>();
-      if (idx < NMAX * NMAX && j < n && j > k) v[u] = upper ? L[(long long)j * ldl + k] : conj_of(L[(long long)k * ldl + j]);
+      if (j < n && j > k) v[u] = upper ? L[(long long)j * ldl + k] : conj_of(L[(long long)k * ldl + j]);
     }
+    if (threadIdx.x < NMAX) dinv[threadIdx.x] = ((int)threadIdx.x < n) ? Real(1) / re_of(L[(long long)threadIdx.x * ldl + threadIdx.x]) : Real(0);
+    __syncthreads();
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int idx = base + u * blockDim.x, fast = idx % NMAX, slow = idx / NMAX;
+    for (int u = 0; u < PER; ++u) {
+      const int idx = threadIdx.x + u * 256, fast = idx % NMAX, slow = idx / NMAX;
       const int j = upper ? slow : fast, k = upper ? fast : slow;
-      if (idx < NMAX * NMAX) Ms[k * LD + j] = rscale(v[u], dinv[k]);
+      Ms[k * LD + j] = rscale(v[u], dinv[k]);
     }
   }
   __syncthreads();

@@ -174,7 +174,7 @@ static void case_trsm_rows(const char *name, int n, int m, int nwarps, double to
           const T *dB = reinterpret_cast<const T *>(Bs.data());
           T *dX = reinterpret_cast<T *>(Out.data());
           long zero = 0;
-          emu::launch(dim3(grid), dim3(nwarps * 32), sm, [&] {
+          emu::launch(dim3(grid), dim3(256), sm, [&] {  // the kernel is written for 256 threads: all of them stage, cw warps own rows
             trsm_rows_kernel<T, NMAX, G, RR>(upper, n, dL, ldl, m, cw, tb, dB, ldb, tx, dX, ldo, &zero);
           });
           double e = 0;
@@ -197,7 +197,7 @@ static void case_trsm_rows(const char *name, int n, int m, int nwarps, double to
   std::vector<H> Ls((size_t)n * n, H(1)), Bs((size_t)m * n, H(2)), Xs((size_t)m * n, H(9));
   long bad = 3;
   const size_t sm = (size_t)NMAX * (NMAX + 1) * sizeof(T) + NMAX * sizeof(Real);
-  emu::launch(dim3(1), dim3(nwarps * 32), sm, [&] {
+  emu::launch(dim3(1), dim3(256), sm, [&] {
     trsm_rows_kernel<T, NMAX, G, RR>(0, n, reinterpret_cast<const T *>(Ls.data()), n, m, nwarps, 0, reinterpret_cast<const T *>(Bs.data()), m, 0,
                                      reinterpret_cast<T *>(Xs.data()), m, &bad);
   });
