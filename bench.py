@@ -493,7 +493,7 @@ def run_ours(args):
                 "peak_source": "FP64 DMMA (mma.sync.m8n8k4.f64) peak measured in this run by chol_probe_fp64; "
                                "MEASURED_PEAKS.json has no FP64 entry (bf16 %.0f TF/s, HBM %.0f GB/s)"
                                % (measured_peaks().get("bf16_tflops", 0), measured_peaks().get("hbm_gbs", 0)),
-                "whole_factorisation_frac_of_peak": gflops / 1e3 / peak_tf if peak_tf else None}
+                "whole_factorisation_frac_of_peak": gflops / 1e3 / (peak_tf * P) if peak_tf else None}
 
     # ---- the reference's CPU path on this box's host cores (bounded sample) ----
     cpu = None

@@ -120,6 +120,8 @@ unsigned long long chol_launch_count(int reset);
 int chol_probe_fp64(int kind, int iters, double *tflops, float *ms);
 /* dependent-issue latency in cycles: kind 0 DFMA, 1 DMUL, 2 rsqrt(double), 3 64-bit shuffle, 4 shared-memory load */
 int chol_probe_latency(int kind, double *cycles_per_op);
+/* test hook: later chol_potf2_launch calls write 64 clock64() phase timestamps to this device buffer (NULL = off) */
+void chol_potf2_set_debug(long long *device_buffer_64);
 
 #ifdef __cplusplus
 }

@@ -177,8 +177,9 @@ __device__ __forceinline__ void potf2_panel(T (&reg)[NA][CW], T *Ls, int c0, int
   }
 }
 
-template <typename T, int NA, int CW>
-__global__ void __launch_bounds__(PANEL_THREADS) potf2_kernel(int upper, int n, T *A, long long lda, long *dinfo, long info_base) {
+template <typename T, int NA, int CW, bool DBG = false>
+__global__ void __launch_bounds__(PANEL_THREADS) potf2_kernel(int upper, int n, T *A, long long lda, long *dinfo, long info_base,
+                                                              long long *dbg = nullptr) {
   CHOL_DYN_SMEM(smem_raw);
   constexpr int NMAX = 32 * NA, LD = NMAX + 1;
   static_assert(16 * CW == NMAX, "16 warps x CW columns");
@@ -187,6 +188,12 @@ __global__ void __launch_bounds__(PANEL_THREADS) potf2_kernel(int upper, int n, 
   if (*dinfo != 0) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) sfail = 0;
+#ifndef CHOL_CPU_EMU
+#define CHOL_DBG(slot) do { if constexpr (DBG) { if (lane == 0) dbg[slot] = clock64(); } } while (false)  /* phase timestamps (scripts/potf2_ab.py) */
+#else
+#define CHOL_DBG(slot) ((void)0)
+#endif
+  if (warp == 0) CHOL_DBG(0);
   // The block enters through the shared buffer, so that the HBM reads are coalesced for both storages (lanes along
   // the stored columns; upper: transposed on the way in).  Every thread issues ALL its loads before the first store -
   // a one-CTA kernel has nothing else to hide the HBM latency with - and writes zeros for everything outside the
@@ -247,7 +254,9 @@ __global__ void __launch_bounds__(PANEL_THREADS) potf2_kernel(int upper, int n, 
   };
   int p = 0;
   if (warp == 0) {  // panel 0 needs no update
+    CHOL_DBG(1);
     potf2_panel<T, NA, CW, LD>(reg, Ls, 0, n, lane, &sfail, A, lda, dinfo, info_base);
+    CHOL_DBG(2);
     __syncthreads();  // panel 0 is published
   } else {
     __syncthreads();
@@ -263,8 +272,11 @@ __global__ void __launch_bounds__(PANEL_THREADS) potf2_kernel(int upper, int n, 
     // what lets the panel routine keep its diagonal block in registers) ...
     if (p < np && p == warp - 1) {
       CHOL_POTF2_LEAVE_IF_FAILED(p);
+      CHOL_DBG(4 + 3 * p);
       update(p);
+      CHOL_DBG(5 + 3 * p);
       if (CW * warp < n) potf2_panel<T, NA, CW, LD>(reg, Ls, CW * warp, n, lane, &sfail, A, lda, dinfo, info_base);
+      CHOL_DBG(6 + 3 * p);
       __syncthreads();
       ++p;
     }
@@ -276,10 +288,13 @@ __global__ void __launch_bounds__(PANEL_THREADS) potf2_kernel(int upper, int n, 
     __syncthreads();
   }
 #undef CHOL_POTF2_LEAVE_IF_FAILED
+  if (warp == 0) CHOL_DBG(60);
   {
     const int fail = sfail;  // a failure in the last panel
     store_factor_columns<T, NA, LD>(upper, n, fail != 0 ? fail - 1 : n, Ls, A, lda, warp, lane);
   }
+  if (warp == 0) CHOL_DBG(61);
+#undef CHOL_DBG
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -356,8 +371,9 @@ __global__ void __launch_bounds__(256) trsm_rows_kernel(int upper, int n, const 
   for (int kb = 0; kb < NT; ++kb) {
     const int kend = min(G, n - G * kb);  // <= 0 beyond the block: nothing to do (keeps the kb loop fully unrollable)
     // the steps of one register slice stay a LOOP: fully unrolled, the 128 steps are ~10k straight-line instructions
-    // that every warp executes once - instruction-fetch bound (875 cycles per step measured, r02 call 5)
-#pragma unroll 1
+    // that every warp executes once - instruction-fetch bound (875 cycles per step measured, r02 call 5); two steps per
+    // trip let the coefficient loads of one step overlap the FMAs of the other
+#pragma unroll 2
     for (int kk = 0; kk < kend; ++kk) {
       const int k = G * kb + kk;
       const int src = g + NG * kk;
@@ -667,13 +683,20 @@ template <typename K> static int set_smem(K kern, size_t bytes) {
   return 0;
 }
 
+static long long *g_potf2_dbg = nullptr;  // test hook: 64 phase timestamps of the next potf2 launches (chol_potf2_set_debug)
 template <typename T>
 static int potf2_t(int uplo, size_t n, void *A, size_t lda, long *dinfo, long base, cudaStream_t st) {
   constexpr int NMAX = sizeof(T) == 16 ? 64 : 128;  // chol_diag_max
   const size_t sm = (size_t)NMAX * (NMAX + 1) * sizeof(T);
+  if (g_potf2_dbg != nullptr) {  // instrumented instantiation (test hook)
+    auto kd = potf2_kernel<T, NMAX / 32, NMAX / 16, true>;
+    int ed = set_smem(kd, sm); if (ed) return ed;
+    kd<<<1, PANEL_THREADS, sm, st>>>(uplo == 'U', (int)n, (T *)A, (long long)lda, dinfo, base, g_potf2_dbg);
+    return (int)cudaGetLastError();
+  }
   auto kern = potf2_kernel<T, NMAX / 32, NMAX / 16>;  // 16 warps x NMAX/16 columns
   int e = set_smem(kern, sm); if (e) return e;
-  kern<<<1, PANEL_THREADS, sm, st>>>(uplo == 'U', (int)n, (T *)A, (long long)lda, dinfo, base);
+  kern<<<1, PANEL_THREADS, sm, st>>>(uplo == 'U', (int)n, (T *)A, (long long)lda, dinfo, base, nullptr);
   CHOL_COUNT_LAUNCH();
   return (int)cudaGetLastError();
 }
@@ -809,6 +832,8 @@ extern "C" size_t chol_logdet_scratch_bytes(void) { return sizeof(LogdetScratch)
 extern "C" int chol_logdet_launch(int prec, const void *x, size_t incx, size_t n, void *dresult, void *dscratch, void *stream) {
   DISPATCH(prec, logdet_t<T>(x, incx, n, dresult, dscratch, (cudaStream_t)stream));
 }
+
+extern "C" void chol_potf2_set_debug(long long *device_buffer_64) { g_potf2_dbg = device_buffer_64; }
 
 extern "C" int chol_probe_latency(int kind, double *cycles_per_op) {
   long long *dc = nullptr;

@@ -176,7 +176,7 @@ CUresult chol_trtri_small(int prec, int uplo, int diag, size_t jb, CUdeviceptr A
  * stays on the panel stream, so the next diagonal block can be factored at once, while the rows below it (the
  * bulk of the column) are updated on a third stream at the same time; the next panel solve waits for that part.
  * Measured neutral on one GPU (dpotrf N = 16384 28.30 -> 28.41 TFLOP/s, profiles/r02_call2_*.txt), so off. */
-bool chol_lookahead_split(void) { return chol_env_switch(&chol_lookahead_split_state, "CHOL_LOOKAHEAD_SPLIT", 0); }
+bool chol_lookahead_split(void) { return chol_env_switch(&chol_lookahead_split_state, "CHOL_LOOKAHEAD_SPLIT", 1); }
 
 bool chol_trtri_lookahead(void) { return chol_env_switch(&chol_trtri_lookahead_state, "CHOL_TRTRI_LOOKAHEAD", 1); }
 
@@ -271,15 +271,17 @@ static CUresult potrf_body(CULAPACKhandle h, int prec, int uplo, size_t n, CUdev
     }
     const CUevent before_solve = look_pending;
     look_pending = NULL;
-    if (uplo == 'L') {
-      const CUdeviceptr P = chol_at(A, lda, j + jb, j, es); /* rest x jb */
+    /* The solved panel goes back into the matrix OFF the serial chain: nothing in the factorisation reads it there
+     * (the updates read W), so the write-back rides on the update stream behind this step's trailing update; W is
+     * not reused before that has finished (ev_rest).  Without a trailing update it stays on the panel stream. */
+    const size_t jb2 = chol_min(nb, rest), rest2 = rest - jb2;
+    const CUdeviceptr P = uplo == 'L' ? chol_at(A, lda, j + jb, j, es) /* rest x jb */ : chol_at(A, lda, j, j + jb, es) /* jb x rest */;
+    const int wb_trans = uplo == 'L' ? 'N' : 'C'; /* upper: W = P^H * U11^-1 */
+    if (uplo == 'L')
       CU_ERROR_CHECK(chol_panel_factor_solve_lower(h, prec, jb, rest, Ajj, P, lda, W, w.ldw, dinfo, (long)j, &w, sp, before_solve));
-      RT_CHECK(chol_copy_launch(prec, 'N', 0, rest, jb, (const void *)W, w.ldw, (void *)P, lda, (void *)sp));
-    } else {
-      const CUdeviceptr P = chol_at(A, lda, j, j + jb, es); /* jb x rest; W = P^H * U11^-1 */
+    else
       CU_ERROR_CHECK(chol_panel_factor_solve_upper(h, prec, jb, rest, Ajj, P, lda, W, w.ldw, dinfo, (long)j, &w, sp, before_solve));
-      RT_CHECK(chol_copy_launch(prec, 'C', 0, rest, jb, (const void *)W, w.ldw, (void *)P, lda, (void *)sp));
-    }
+    if (!rest2) RT_CHECK(chol_copy_launch(prec, wb_trans, 0, rest, jb, (const void *)W, w.ldw, (void *)P, lda, (void *)sp));
     /* s, c: the updates of this step run on the tensor cores - split W once into its TF32 (hi, lo) planes */
     const bool tens = w.kp != 0 && rest >= 512 && jb >= 64;
     const CUdeviceptr Whi = w.Whi[step & 1], Wlo = w.Wlo[step & 1];
@@ -290,7 +292,6 @@ static CUresult potrf_body(CULAPACKhandle h, int prec, int uplo, size_t n, CUdev
 
     /* --- trailing update  A22 -= W W^H, split into the next block column/row (look-ahead, panel
      *     stream) and the rest (update stream) --- */
-    const size_t jb2 = chol_min(nb, rest), rest2 = rest - jb2;
     if (rest2) {
       CU_ERROR_CHECK(cuStreamWaitEvent(su, h->ev_panel[step % CHOL_EVENT_RING], 0));
       const CUdeviceptr W2 = chol_at(W, w.ldw, jb2, 0, es);
@@ -312,6 +313,7 @@ static CUresult potrf_body(CULAPACKhandle h, int prec, int uplo, size_t n, CUdev
         CU_ERROR_CHECK(cuEventRecord(h->prof_e1[h->prof_n], su));
         h->prof_flops[h->prof_n++] = (double)rest2 * (double)(rest2 + 1) * (double)jb * (herm ? 4.0 : 1.0);
       }
+      RT_CHECK(chol_copy_launch(prec, wb_trans, 0, rest, jb, (const void *)W, w.ldw, (void *)P, lda, (void *)su)); /* write-back */
       CU_ERROR_CHECK(cuEventRecord(h->ev_rest[step % CHOL_EVENT_RING], su));
     }
     /* the look-ahead block was last written by the previous step's trailing update */

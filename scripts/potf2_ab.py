@@ -18,6 +18,37 @@ for kind, name in ((0, "DFMA"), (1, "DMUL"), (2, "rsqrt(double)"), (3, "shfl 64-
     cyc = C.c_double(0)
     lib.chol_probe_latency(C.c_int(kind), C.byref(cyc))
     print("latency %-14s %.1f cycles" % (name, cyc.value), flush=True)
+def potf2_phases(p="d", n=128, uplo="L"):
+    """clock64 phase timestamps of ONE potf2 launch (test hook chol_potf2_set_debug)"""
+    rt = torch.float64 if p in "dz" else torch.float32
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B = torch.rand(n, n, dtype=rt, device="cuda", generator=g) - 0.5
+    A = B @ B.T + n * torch.eye(n, dtype=rt, device="cuda")
+    dbg = torch.zeros(64, dtype=torch.int64, device="cuda")
+    dinfo = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for rep in range(2):
+        A2 = A.clone()
+        dbg.zero_()
+        lib.chol_potf2_set_debug(C.c_void_p(dbg.data_ptr()))
+        lib.chol_potf2_launch(C.c_int(ord(p)), C.c_int(ord(uplo)), C.c_size_t(n), C.c_void_p(A2.data_ptr()), C.c_size_t(n),
+                              C.c_void_p(dinfo.data_ptr()), C.c_long(0), C.c_void_p(0))
+        torch.cuda.synchronize()
+        lib.chol_potf2_set_debug(C.c_void_p(0))
+    t = dbg.cpu().tolist()
+    t0 = t[0]
+    print("potf2 %s n=%d phases (cycles since kernel start): staged+regs %d, panel0 done %d, main loop done %d, stored %d"
+          % (p, n, t[1] - t0, t[2] - t0, t[60] - t0, t[61] - t0), flush=True)
+    rounds = []
+    for q in range(15):
+        a, b, c_ = t[4 + 3 * q], t[5 + 3 * q], t[6 + 3 * q]
+        if a:
+            rounds.append("r%d: start %d update %d panel %d" % (q, a - t0, b - a, c_ - b))
+    print("  owner of panel p+1 per round: " + "; ".join(rounds), flush=True)
+
+
+if os.environ.get("AB_PHASES", "1") != "0":
+    potf2_phases("d")
+    potf2_phases("s")
 for p in os.environ.get("AB_PRECS", "dzsc"):
     n = 64 if p == "z" else 128
     rt = torch.float64 if p in "dz" else torch.float32
