@@ -105,6 +105,10 @@ int chol_lauu2_launch(int prec, int uplo, size_t n, void *A, size_t lda, void *s
  * 'l'/'u' = the same without the diagonal. */
 int chol_copy_launch(int prec, int trans, int uplo, size_t m, size_t n, const void *A, size_t lda, void *B,
                      size_t ldb, void *stream);
+/* B(g(r), c) := A(r, c), r < m, c < n, with the block-cyclic row map g(r) = ((r / cyc_nb) * cyc_p + cyc_off) * cyc_nb + r % cyc_nb
+ * (a rank's packed piece of a row block goes to its global positions; distributed LAUUM) */
+int chol_scatter_rows_launch(int prec, size_t m, size_t n, const void *A, size_t lda, void *B, size_t ldb, int cyc_nb, int cyc_p,
+                             int cyc_off, void *stream);
 /* A(m x n) := value on the chosen part: uplo 0 all, 'L' strictly-lower, 'U' strictly-upper */
 int chol_fill_launch(int prec, int uplo, size_t m, size_t n, double re, double im, void *A, size_t lda, void *stream);
 

@@ -563,6 +563,20 @@ __global__ void __launch_bounds__(256) copy_kernel(int trans, int uplo, int m, i
   }
 }
 
+// B(g(r), c) := A(r, c) for an m x n block: the rows of a rank's packed piece go to their block-cyclic positions
+// g(r) = ((r / cnb) * cp + coff) * cnb + r % cnb  (the distributed LAUUM assembles a row block of the factor this way)
+template <typename T>
+__global__ void __launch_bounds__(256) scatter_rows_kernel(int m, int n, const T *A, long long lda, T *B, long long ldb, int cnb, int cp,
+                                                           int coff) {
+  const int r = blockIdx.x * 32 + (threadIdx.x & 31);
+  if (r >= m) return;
+  const long long gr = ((long long)(r / cnb) * cp + coff) * cnb + r % cnb;
+  for (int cc = threadIdx.x >> 5; cc < 32; cc += 8) {
+    const int c = blockIdx.y * 32 + cc;
+    if (c < n) B[(long long)c * ldb + gr] = A[(long long)c * lda + r];
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) fill_kernel(int uplo, int m, int n, T value, T *A, long long lda) {
   const int r = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -758,6 +772,13 @@ static int copy_t(int trans, int uplo, size_t m, size_t n, const void *A, size_t
   return (int)cudaGetLastError();
 }
 template <typename T>
+static int scatter_rows_t(size_t m, size_t n, const void *A, size_t lda, void *B, size_t ldb, int cnb, int cp, int coff, cudaStream_t st) {
+  dim3 grid((unsigned)((m + 31) / 32), (unsigned)((n + 31) / 32));
+  scatter_rows_kernel<T><<<grid, 256, 0, st>>>((int)m, (int)n, (const T *)A, (long long)lda, (T *)B, (long long)ldb, cnb, cp, coff);
+  CHOL_COUNT_LAUNCH();
+  return (int)cudaGetLastError();
+}
+template <typename T>
 static int fill_t(int uplo, size_t m, size_t n, T v, void *A, size_t lda, cudaStream_t st) {
   dim3 grid((unsigned)((m + 31) / 32), (unsigned)((n + 31) / 32));
   const int uc = uplo == 'L' ? 1 : (uplo == 'U' ? 2 : 0);
@@ -823,6 +844,12 @@ extern "C" int chol_copy_launch(int prec, int trans, int uplo, size_t m, size_t 
                                 size_t ldb, void *stream) {
   if (m == 0 || n == 0) return 0;
   DISPATCH(prec, copy_t<T>(trans, uplo, m, n, A, lda, B, ldb, (cudaStream_t)stream));
+}
+extern "C" int chol_scatter_rows_launch(int prec, size_t m, size_t n, const void *A, size_t lda, void *B, size_t ldb, int cyc_nb, int cyc_p,
+                                        int cyc_off, void *stream) {
+  if (m == 0 || n == 0) return 0;
+  if (cyc_nb <= 0 || cyc_p <= 0) return (int)cudaErrorInvalidValue;
+  DISPATCH(prec, scatter_rows_t<T>(m, n, A, lda, B, ldb, cyc_nb, cyc_p, cyc_off, (cudaStream_t)stream));
 }
 extern "C" int chol_fill_launch(int prec, int uplo, size_t m, size_t n, double re, double im, void *A, size_t lda, void *stream) {
   if (m == 0 || n == 0) return 0;

@@ -51,10 +51,13 @@ bool chol_s_tensor(void) { return chol_env_switch(&chol_s_tensor_state, "CHOL_S_
 /* outer block size: k of the trailing update.  Larger k amortises the C-tile epilogue (measured on
  * B200, d: 512 beats 256 from N ~ 32768 up), smaller k shortens the serial panel chain. */
 size_t chol_default_nb(int prec, size_t n) {
-  /* measured on B200 (scripts/nb_sweep.py, profiles/r01_first_light.md) */
-  if (prec == 'z') return n >= 8192 ? 256 : 128;
-  if (prec == 'd') return n >= 49152 ? 1024 : (n >= 12288 ? 512 : 256);
-  return n >= 16384 ? 512 : 256;
+  /* measured on B200 with the substitution-based panel chain (scripts/nb_sweep.py, profiles/r02_call10_summary.txt):
+   * d  N = 8192: nb 256 / 512 -> 18.7 / 20.1 TFLOP/s;  16384: 512 / 768 / 1024 -> 28.9 / 29.3 / 29.3;  32768: 512 / 1024 -> 32.1 / 33.0
+   * z  N = 16384: 256 / 512 -> 29.8 / 30.0;  s 16384, 32768: 512 best;  c 16384: 256 / 512 -> 118 / 105 */
+  if (prec == 'z') return n >= 12288 ? 512 : (n >= 8192 ? 256 : 128);
+  if (prec == 'd') return n >= 24576 ? 1024 : (n >= 12288 ? 768 : (n >= 6144 ? 512 : 256));
+  if (prec == 'c') return 256;
+  return n >= 12288 ? 512 : 256;
 }
 
 CUresult chol_carve(CULAPACKhandle h, int prec, size_t n, chol_ws *w) {
@@ -373,9 +376,16 @@ static CUresult potrf_body(CULAPACKhandle h, int prec, int uplo, size_t n, CUdev
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* TRTRI's own block size (its per-block small inverse grows with nb^2 launches; measured in round 1, nb_sweep) */
+static size_t trtri_default_nb(int prec, size_t n) {
+  if (prec == 'z') return n >= 8192 ? 256 : 128;
+  if (prec == 'd') return n >= 49152 ? 1024 : (n >= 12288 ? 512 : 256);
+  return n >= 16384 ? 512 : 256;
+}
+
 static CUresult trtri_body(CULAPACKhandle h, int prec, int uplo, int diag, size_t n, CUdeviceptr A, size_t lda, long *info) {
   chol_ws w;
-  CU_ERROR_CHECK(chol_carve(h, prec, n, &w));
+  CU_ERROR_CHECK(chol_carve_nb(h, prec, n, h->nb ? h->nb : trtri_default_nb(prec, n), &w));
   const size_t es = w.es, nb = w.nb;
   long *dinfo = (long *)h->dinfo;
   CUstream st = h->s_update;

@@ -34,6 +34,7 @@
 
 static const double ONE[2] = {1.0, 0.0};
 static const double MONE[2] = {-1.0, 0.0};
+static const double ZERO2[2] = {0.0, 0.0};
 
 /* =============================================================================================
  * NCCL, bound at run time (dlopen by soname: inside a PyTorch process this resolves to the copy
@@ -330,6 +331,30 @@ static size_t local_cols(size_t n, size_t nb, int r, int P) {
   return cols;
 }
 
+/* D (m x n packed local columns, global triangle column of local column c: gcol(c) with block-cyclic parameters
+ * cnb, cP, coff) += alpha * W[0:m, :] * W[gcol(c), :]^H on the global lower triangle (m >= gcol(c)) */
+static CUresult gemm_cyc_ex(int prec, int herm, double alpha, size_t m, size_t n, size_t k, CUdeviceptr W, size_t ldw, CUdeviceptr D,
+                            size_t ldd, int cnb, int cP, int coff, CUstream st) {
+  chol_gemm_desc d;
+  memset(&d, 0, sizeof d);
+  d.prec = prec;
+  d.opA = 'N';
+  d.opB = 'C';
+  d.cuplo = 'L';
+  d.herm = herm;
+  d.m = m; d.n = n; d.k = k;
+  d.alpha[0] = alpha;
+  d.beta[0] = 1.0;
+  d.A = (const void *)W; d.lda = ldw;
+  d.B = (const void *)W; d.ldb = ldw;
+  d.C = (const void *)D; d.ldc = ldd;
+  d.D = (void *)D; d.ldd = ldd;
+  d.stream = (void *)st;
+  d.cyc_nb = cnb; d.cyc_p = cP; d.cyc_off = coff;
+  RT_CHECK(chol_gemm_launch(&d));
+  return CUDA_SUCCESS;
+}
+
 static CUresult gemm_cyc(int prec, int herm, size_t m, size_t n, size_t k, CUdeviceptr W, size_t ldw, CUdeviceptr D,
                          size_t ldd, int cnb, int cP, CUstream st) {
   chol_gemm_desc d;
@@ -532,6 +557,150 @@ static CUresult dist_potrf(chol_rank *R, int prec, size_t n, CUdeviceptr Aloc, s
     }
   }
   h->prof_n = 0;
+  return CUDA_SUCCESS;
+}
+
+/* =============================================================================================
+ * Distributed TRTRI / LAUUM / POTRI on the same 1-D block-cyclic layout (reference entry
+ * points lapack/dtrtri.c:470-530, dlauum.c:294-352, dpotri.c:48-69).  Lower form; one exchange per block step.
+ *
+ * TRTRI (in place, X = inv(L)), sweep over block columns k = 0, 1, ...  State before step k: the first k block columns
+ * hold  [ X00 ; M ]  with X00 = inv(L00) and M = -L_B0 X00 ("still to be multiplied by inv(L_BR) from the left"),
+ * block columns >= k hold the untouched L.  Step k with L_BR = [L11 0; L21 L22], M = [M1; M2]:
+ *      X11 = inv(L11)                      owner of column k, then BROADCAST of the panel [X11; L21]
+ *      X10 = X11 M1                        every rank, on its own columns < k  (row block k becomes final)
+ *      M2 -= L21 X10                       every rank, on its own columns < k  (the n^3/3 flops, one GEMM per rank)
+ *      L21 <- -L21 X11, L11 <- X11         owner of column k
+ * The panels are columns of the ORIGINAL factor (steps < k never write block columns >= k), so the broadcasts do not
+ * wait for any update: they run ahead on the panel stream, double-buffered, while the update stream computes.
+ *
+ * LAUUM (in place, C = L^H L, lower), sweep over block ROWS k = 0, 1, ...:  C[0:k+1, 0:k+1] += L[k, 0:k+1]^H L[k, 0:k+1].
+ * Every rank contributes its columns' piece of row block k (conjugate-transposed and packed), the pieces are broadcast
+ * in one NCCL group and scattered to their block-cyclic rows of a tall panel TT = L[k, 0:k+1]^H ((k+1) nb x nb); then
+ * C(i, c) += TT(i, :) TT(gcol(c), :)^H for the rank's own columns c - the same block-cyclic-aware tile launch as the
+ * POTRF trailing update, with alpha = +1.  Row block k of the matrix is consumed in step k and turns from L into C.
+ * ===========================================================================================*/
+static size_t cols_upto_block(size_t n, size_t nb, int r, int P, long kmax) { /* columns of rank r with global block <= kmax */
+  size_t cols = 0;
+  for (long c = r; c <= kmax && (size_t)c * nb < n; c += P) cols += chol_min(nb, n - (size_t)c * nb);
+  return cols;
+}
+
+static CUresult dist_trtri(chol_rank *R, int prec, int diag, size_t n, CUdeviceptr Aloc, size_t ldl, CUdeviceptr tmp) {
+  CULAPACKhandle h = R->lap;
+  const int P = R->nranks, me = R->rank;
+  chol_ws w;
+  CU_ERROR_CHECK(dist_carve(R, prec, n, &w));
+  const size_t es = w.es, nb = w.nb, nblk = (n + nb - 1) / nb;
+  const int unit = diag == 'U';
+  long *dinfo = (long *)h->dinfo;
+  CUstream sc = h->s_panel, su = h->s_update;
+  CU_ERROR_CHECK(cuMemsetD8Async(h->dinfo, 0, sizeof(long), sc)); /* zero pivots were excluded on the host: a sink */
+  for (size_t k = 0; k < nblk; k++) {
+    const size_t j = k * nb, jb = chol_min(nb, n - j), rest = n - j - jb;
+    const int owner = (int)(k % (size_t)P);
+    const CUdeviceptr W = w.W[k & 1];
+    const size_t ldp = chol_roundup(jb + rest, 16);
+    const size_t lc = k / (size_t)P;
+    const CUdeviceptr Ajj = chol_at(Aloc, ldl, j, lc * nb, es), A21 = chol_at(Aloc, ldl, j + jb, lc * nb, es);
+    /* ---- panel stream: [X11; L21] into W, broadcast ---- */
+    if (k >= 2) CU_ERROR_CHECK(cuStreamWaitEvent(sc, h->ev_rest[(k - 2) % CHOL_EVENT_RING], 0)); /* W's last reader */
+    if (me == owner) {
+      CU_ERROR_CHECK(chol_trtri_small(prec, 'L', diag, jb, Ajj, ldl, W, ldp, dinfo, (long)j, &w, sc));
+      if (rest) RT_CHECK(chol_copy_launch(prec, 'N', 0, rest, jb, (const void *)A21, ldl, (void *)chol_at(W, ldp, jb, 0, es), ldp, (void *)sc));
+    }
+    if (P > 1) NCCL_CHECK(nccl.Broadcast((const void *)W, (void *)W, ldp * jb * es, CHOL_NCCL_UINT8, owner, R->comm, sc));
+    CU_ERROR_CHECK(cuEventRecord(h->ev_panel[k % CHOL_EVENT_RING], sc));
+    /* ---- update stream ---- */
+    CU_ERROR_CHECK(cuStreamWaitEvent(su, h->ev_panel[k % CHOL_EVENT_RING], 0));
+    const size_t cb = k ? cols_upto_block(n, nb, me, P, (long)k - 1) : 0; /* own columns left of block column k */
+    if (cb) {
+      const CUdeviceptr M1 = chol_at(Aloc, ldl, j, 0, es);
+      CU_ERROR_CHECK(chol_gemm(prec, 'N', 'N', jb, cb, jb, ONE, W, ldp, M1, ldl, ZERO2, 0, 0, tmp, jb, su));
+      RT_CHECK(chol_copy_launch(prec, 'N', 0, jb, cb, (const void *)tmp, jb, (void *)M1, ldl, (void *)su));
+      if (rest) {
+        const CUdeviceptr M2 = chol_at(Aloc, ldl, j + jb, 0, es);
+        CU_ERROR_CHECK(chol_gemm(prec, 'N', 'N', rest, cb, jb, MONE, chol_at(W, ldp, jb, 0, es), ldp, tmp, jb, ONE, M2, ldl, M2, ldl, su));
+      }
+    }
+    if (me == owner) {
+      if (rest)
+        CU_ERROR_CHECK(chol_gemm(prec, 'N', 'N', rest, jb, jb, MONE, chol_at(W, ldp, jb, 0, es), ldp, W, ldp, ZERO2, 0, 0, A21, ldl, su));
+      /* a unit-diagonal inverse leaves the caller's diagonal untouched (lapack/dtrtri.c:56-57) */
+      RT_CHECK(chol_copy_launch(prec, 'N', unit ? 'l' : 'L', jb, jb, (const void *)W, ldp, (void *)Ajj, ldl, (void *)su));
+    }
+    CU_ERROR_CHECK(cuEventRecord(h->ev_rest[k % CHOL_EVENT_RING], su));
+  }
+  CU_ERROR_CHECK(cuStreamSynchronize(sc));
+  CU_ERROR_CHECK(cuStreamSynchronize(su));
+  return CUDA_SUCCESS;
+}
+
+static CUresult dist_lauum(chol_rank *R, int prec, size_t n, CUdeviceptr Aloc, size_t ldl) {
+  CULAPACKhandle h = R->lap;
+  const int P = R->nranks, me = R->rank;
+  chol_ws w;
+  CU_ERROR_CHECK(dist_carve(R, prec, n, &w));
+  const size_t es = w.es, nb = w.nb, nblk = (n + nb - 1) / nb;
+  const int herm = chol_is_complex(prec);
+  CUstream su = h->s_update;
+  const CUdeviceptr TT = w.W[0], S = w.W[1]; /* TT: (k+1) nb x nb in global row order; S: the P packed pieces, one after the other */
+  const size_t ldt = w.ldw;
+  for (size_t k = 0; k < nblk; k++) {
+    const size_t j = k * nb, jb = chol_min(nb, n - j); /* row block k: rows j .. j+jb-1, columns 0 .. j+jb-1 */
+    const int owner = (int)(k % (size_t)P);
+    /* pieces: rank r holds cols_r columns of row block k (its block columns <= k); piece r = their conjugate transpose,
+     * cols_r x jb, packed with leading dimension cols_r at element offset off_r of S */
+    size_t off = 0, my_off = 0, my_cols = 0;
+    for (int r = 0; r < P; r++) {
+      const size_t cr = cols_upto_block(n, nb, r, P, (long)k);
+      if (r == me) { my_off = off; my_cols = cr; }
+      off += cr * jb;
+    }
+    const size_t cb = k ? cols_upto_block(n, nb, me, P, (long)k - 1) : 0; /* own columns left of the diagonal block */
+    const CUdeviceptr Rk = chol_at(Aloc, ldl, j, 0, es);                  /* row block k of the own columns */
+    if (my_cols) {
+      const CUdeviceptr Sme = S + (CUdeviceptr)(my_off * es);
+      if (cb) RT_CHECK(chol_copy_launch(prec, 'C', 0, jb, cb, (const void *)Rk, ldl, (void *)Sme, my_cols, (void *)su));
+      if (me == owner) { /* the diagonal block: only its lower triangle is the factor (the other triangle is the caller's) */
+        const CUdeviceptr Sd = Sme + (CUdeviceptr)(cb * es);
+        RT_CHECK(chol_fill_launch(prec, 0, jb, jb, 0.0, 0.0, (void *)Sd, my_cols, (void *)su));
+        RT_CHECK(chol_copy_launch(prec, 'C', 'L', jb, jb, (const void *)chol_at(Rk, ldl, 0, cb, es), ldl, (void *)Sd, my_cols, (void *)su));
+      }
+    }
+    if (P > 1) {
+      NCCL_CHECK(nccl.GroupStart());
+      size_t o = 0;
+      for (int r = 0; r < P; r++) {
+        const size_t cr = cols_upto_block(n, nb, r, P, (long)k);
+        if (cr) {
+          const CUdeviceptr Sr = S + (CUdeviceptr)(o * es);
+          NCCL_CHECK(nccl.Broadcast((const void *)Sr, (void *)Sr, cr * jb * es, CHOL_NCCL_UINT8, r, R->comm, su));
+        }
+        o += cr * jb;
+      }
+      NCCL_CHECK(nccl.GroupEnd());
+    }
+    { /* scatter every piece to its block-cyclic rows of TT */
+      size_t o = 0;
+      for (int r = 0; r < P; r++) {
+        const size_t cr = cols_upto_block(n, nb, r, P, (long)k);
+        if (cr)
+          RT_CHECK(chol_scatter_rows_launch(prec, cr, jb, (const void *)(S + (CUdeviceptr)(o * es)), cr, (void *)TT, ldt, (int)nb, P, r, (void *)su));
+        o += cr * jb;
+      }
+    }
+    if (cb) {
+      /* row block k of the own columns has been read: it becomes an accumulator of C */
+      RT_CHECK(chol_fill_launch(prec, 0, jb, cb, 0.0, 0.0, (void *)Rk, ldl, (void *)su));
+      CU_ERROR_CHECK(gemm_cyc_ex(prec, herm, 1.0, j + jb, cb, jb, TT, ldt, Aloc, ldl, (int)nb, P, me, su));
+    }
+    if (me == owner) { /* C_kk = L_kk^H L_kk replaces the factor's diagonal block (lower triangle only) */
+      const CUdeviceptr TTk = chol_at(TT, ldt, j, 0, es), Ckk = chol_at(Rk, ldl, 0, cb, es);
+      CU_ERROR_CHECK(chol_gemm_ex(prec, 'N', 'C', 0, 0, 0, 0, 'L', herm, jb, jb, jb, ONE, TTk, ldt, TTk, ldt, ZERO2, 0, 0, Ckk, ldl, su));
+    }
+  }
+  CU_ERROR_CHECK(cuStreamSynchronize(su));
   return CUDA_SUCCESS;
 }
 
@@ -992,6 +1161,117 @@ static CUresult mgpu_potrf(CUmultiGPULAPACKhandle handle, int prec, int uplo, si
   *info = first;
   free(args);
   free(ptrs);
+  return e;
+}
+
+/* =============================================================================================
+ * host-pointer TRTRI / LAUUM / POTRI over all GPUs: scatter into the block-cyclic layout, the distributed sweeps
+ * above, gather.  Upper inputs travel as U^H (a lower factor): inv(U) = inv(L)^H and U U^H = L^H L.
+ * ===========================================================================================*/
+typedef struct {
+  chol_rank *R;
+  int op, prec, uplo, diag; /* op: 0 trtri, 1 lauum, 2 potri */
+  size_t n, lda;
+  void *hostA;
+} inverse_args;
+
+static CUresult rank_inverse_task(const void *argp) {
+  inverse_args *a = *(inverse_args *const *)argp;
+  chol_rank *R = a->R;
+  const int P = R->nranks, me = R->rank, prec = a->prec;
+  const size_t n = a->n, es = chol_esize(prec), lda = a->lda;
+  chol_ws w;
+  CU_ERROR_CHECK(dist_carve(R, prec, n, &w));
+  const size_t nb = w.nb, nblk = (n + nb - 1) / nb, my_cols = local_cols(n, nb, me, P), ldl = chol_roundup(n, 16);
+  CUstream st = R->lap->s_update;
+  char *hostA = a->hostA;
+  CUdeviceptr tmp = 0;
+  if (a->op != 1) CU_ERROR_CHECK(cuMemAlloc(&tmp, nb * (my_cols ? my_cols : 1) * es));
+  CUresult e = CUDA_SUCCESS;
+  for (size_t c = (size_t)me, lc = 0; c < nblk && e == CUDA_SUCCESS; c += (size_t)P, lc++) {
+    const size_t j = c * nb, jb = chol_min(nb, n - j), rows = n - j;
+    const CUdeviceptr dst = chol_at(R->local, ldl, j, lc * nb, es);
+    if (a->uplo == 'L') {
+      e = copy2d(1, hostA + (j * lda + j) * es, lda, dst, ldl, rows, jb, es, st);
+    } else { /* U[j:j+jb, j:n] -> staging (jb x rows) -> conjugate transpose into the local column */
+      const size_t lds = chol_roundup(jb, 2);
+      e = copy2d(1, hostA + (j * lda + j) * es, lda, w.W[lc & 1], lds, jb, rows, es, st);
+      if (e == CUDA_SUCCESS && chol_copy_launch(prec, 'C', 0, jb, rows, (const void *)w.W[lc & 1], lds, (void *)dst, ldl, (void *)st) != 0)
+        e = CUDA_ERROR_LAUNCH_FAILED;
+    }
+  }
+  if (e == CUDA_SUCCESS) e = cuStreamSynchronize(st);
+  if (e == CUDA_SUCCESS && a->op != 1) e = dist_trtri(R, prec, a->diag, n, R->local, ldl, tmp);
+  if (e == CUDA_SUCCESS && a->op != 0) e = dist_lauum(R, prec, n, R->local, ldl);
+  for (size_t c = (size_t)me, lc = 0; c < nblk && e == CUDA_SUCCESS; c += (size_t)P, lc++) {
+    const size_t j = c * nb, jb = chol_min(nb, n - j), rows = n - j;
+    const CUdeviceptr src = chol_at(R->local, ldl, j, lc * nb, es);
+    if (a->uplo == 'L') {
+      e = copy2d(0, hostA + (j * lda + j) * es, lda, src, ldl, rows, jb, es, st);
+    } else {
+      const size_t lds = chol_roundup(jb, 2);
+      if (chol_copy_launch(prec, 'C', 0, rows, jb, (const void *)src, ldl, (void *)w.W[lc & 1], lds, (void *)st) != 0) e = CUDA_ERROR_LAUNCH_FAILED;
+      if (e == CUDA_SUCCESS) e = copy2d(0, hostA + (j * lda + j) * es, lda, w.W[lc & 1], lds, jb, rows, es, st);
+    }
+  }
+  const CUresult es2 = cuStreamSynchronize(st);
+  if (e == CUDA_SUCCESS) e = es2;
+  if (tmp) cuMemFree(tmp);
+  CU_ERROR_CHECK(e);
+  return CUDA_SUCCESS;
+}
+
+/* a zero on the diagonal of a non-unit triangular matrix: the reference reports the first one its sweep meets -
+ * bottom-up for lower, top-down for upper (lapack/dtrtri.c:49-52, :73-77) - and stops; here nothing is computed */
+static long host_zero_pivot(int prec, int uplo, size_t n, const void *A, size_t lda) {
+  long found = 0;
+  for (size_t i = 0; i < n; i++) {
+    const size_t at = i * lda + i;
+    bool zero;
+    switch (prec) {
+      case 's': zero = ((const float *)A)[at] == 0.0f; break;
+      case 'd': zero = ((const double *)A)[at] == 0.0; break;
+      case 'c': zero = ((const float *)A)[2 * at] == 0.0f && ((const float *)A)[2 * at + 1] == 0.0f; break;
+      default: zero = ((const double *)A)[2 * at] == 0.0 && ((const double *)A)[2 * at + 1] == 0.0; break;
+    }
+    if (zero) {
+      if (uplo != 'L') return (long)i + 1;
+      found = (long)i + 1;
+    }
+  }
+  return found;
+}
+
+/* op: 0 trtri, 1 lauum, 2 potri */
+CUresult chol_mgpu_inverse_dist(CUmultiGPU m, int op, int prec, int uplo, int diag, size_t n, void *A, size_t lda, long *info) {
+  if (m == NULL || A == NULL) return CUDA_ERROR_INVALID_VALUE;
+  *info = 0;
+  if (op != 1 && diag != 'U') {
+    *info = host_zero_pivot(prec, uplo, n, A, lda);
+    if (*info != 0) return CUDA_SUCCESS;
+  }
+  CU_ERROR_CHECK(ensure_ranks(m));
+  const int P = m->n;
+  inverse_args *args = calloc((size_t)P, sizeof *args);
+  inverse_args **ptrs = calloc((size_t)P, sizeof *ptrs);
+  potrf_args *pargs = calloc((size_t)P, sizeof *pargs);
+  potrf_args **pptrs = calloc((size_t)P, sizeof *pptrs);
+  if (args == NULL || ptrs == NULL || pargs == NULL || pptrs == NULL) {
+    free(args); free(ptrs); free(pargs); free(pptrs);
+    return CUDA_ERROR_OUT_OF_MEMORY;
+  }
+  for (int i = 0; i < P; i++) {
+    args[i].R = &m->ranks[i]; args[i].op = op; args[i].prec = prec; args[i].uplo = uplo; args[i].diag = diag;
+    args[i].n = n; args[i].lda = lda; args[i].hostA = A;
+    ptrs[i] = &args[i];
+    pargs[i].R = &m->ranks[i]; pargs[i].prec = prec; pargs[i].n = n;
+    pptrs[i] = &pargs[i];
+  }
+  /* phase 1: every rank's resident block columns (an allocation failure fails the call on all ranks before anyone
+   * waits in a broadcast), phase 2: the sweeps */
+  CUresult e = run_on_all(m, rank_potrf_prepare_task, pptrs, sizeof(*pptrs), sizeof(*pptrs));
+  if (e == CUDA_SUCCESS) e = run_on_all(m, rank_inverse_task, ptrs, sizeof(*ptrs), sizeof(*ptrs));
+  free(args); free(ptrs); free(pargs); free(pptrs);
   return e;
 }
 

@@ -233,15 +233,19 @@ static const double ONE[2] = {1.0, 0.0};
 static const double ZERO[2] = {0.0, 0.0};
 static const double MONE[2] = {-1.0, 0.0};
 
-/* cuMultiGPU*{trtri,lauum,potri}: split by output slab over all GPUs when there is more than one (with one GPU
- * the plain single-GPU routine on a staged copy does the same work with fewer transfers).
- * CHOL_MGPU_INVERSE=slab / staged forces either form (tests, A/B runs). */
-int chol_inverse_slabs_enabled(CUmultiGPU m) {
+/* cuMultiGPU*{trtri,lauum,potri} with more than one GPU: the distributed block-cyclic sweeps of host/multigpu.c (one NCCL
+ * exchange per block step, like POTRF).  With one GPU the plain single-GPU routine on a staged copy does the same work.
+ * CHOL_MGPU_INVERSE=slab selects the exchange-free split by output slab further down (2 B200, N = 32768: 0.99 s against
+ * 1.18 s staged - PCIe-bound, profiles/r02_call8_2gpu_summary.txt), =staged the one-GPU form, =dist this default. */
+CUresult chol_mgpu_inverse_dist(CUmultiGPU m, int op, int prec, int uplo, int diag, size_t n, void *A, size_t lda, long *info);
+static int inverse_mode(CUmultiGPU m) { /* 0 staged, 1 slab, 2 distributed */
   const char *e = getenv("CHOL_MGPU_INVERSE");
   if (e != NULL && strcmp(e, "slab") == 0) return 1;
   if (e != NULL && strcmp(e, "staged") == 0) return 0;
-  return m != NULL && cuMultiGPUGetContextCount(m) > 1;
+  if (e != NULL && strcmp(e, "dist") == 0) return 2;
+  return (m != NULL && cuMultiGPUGetContextCount(m) > 1) ? 2 : 0;
 }
+int chol_inverse_slabs_enabled(CUmultiGPU m) { return inverse_mode(m) == 1; }
 
 /* cost profile over the split dimension: 0 -> (n-x)^2, 1 -> x^2, 2 -> x (n-x) */
 void chol_inverse_slab_bounds(int profile, size_t n, int nslabs, size_t *bounds /* nslabs + 1 */) {
@@ -512,6 +516,8 @@ CUresult chol_mgpu_inverse_slabs(CUmultiGPU m, int op, int prec, int uplo, int d
     if (n == 0) return CUDA_SUCCESS;                                                                                   \
     mb_args a;                                                                                                         \
     memset(&a, 0, sizeof a);                                                                                           \
+    if (inverse_mode(chol_mgpu_of_lapack(h)) == 2)                                                                    \
+      return chol_mgpu_inverse_dist(chol_mgpu_of_lapack(h), 0, p, uplo, diag, n, A, lda, info);                      \
     if (chol_inverse_slabs_enabled(chol_mgpu_of_lapack(h)))                                                                                  \
       return chol_mgpu_inverse_slabs(chol_mgpu_of_lapack(h), OP_TRTRI, p, uplo, diag, n, A, lda, info);                \
     a.op = OP_TRTRI; a.prec = p; a.uplo = uplo; a.diag = diag; a.n = n;                                                \
@@ -527,6 +533,8 @@ CUresult chol_mgpu_inverse_slabs(CUmultiGPU m, int op, int prec, int uplo, int d
     if (n == 0) return CUDA_SUCCESS;                                                                                   \
     mb_args a;                                                                                                         \
     memset(&a, 0, sizeof a);                                                                                           \
+    if (inverse_mode(chol_mgpu_of_lapack(h)) == 2)                                                                    \
+      return chol_mgpu_inverse_dist(chol_mgpu_of_lapack(h), 1, p, uplo, 'N', n, A, lda, info);                      \
     if (chol_inverse_slabs_enabled(chol_mgpu_of_lapack(h)))                                                                                  \
       return chol_mgpu_inverse_slabs(chol_mgpu_of_lapack(h), OP_LAUUM, p, uplo, 'N', n, A, lda, info);                 \
     a.op = OP_LAUUM; a.prec = p; a.uplo = uplo; a.n = n;                                                               \
@@ -542,6 +550,8 @@ CUresult chol_mgpu_inverse_slabs(CUmultiGPU m, int op, int prec, int uplo, int d
     if (n == 0) return CUDA_SUCCESS;                                                                                   \
     mb_args a;                                                                                                         \
     memset(&a, 0, sizeof a);                                                                                           \
+    if (inverse_mode(chol_mgpu_of_lapack(h)) == 2)                                                                    \
+      return chol_mgpu_inverse_dist(chol_mgpu_of_lapack(h), 2, p, uplo, 'N', n, A, lda, info);                      \
     if (chol_inverse_slabs_enabled(chol_mgpu_of_lapack(h)))                                                                                  \
       return chol_mgpu_inverse_slabs(chol_mgpu_of_lapack(h), OP_POTRI, p, uplo, 'N', n, A, lda, info);                 \
     a.op = OP_POTRI; a.prec = p; a.uplo = uplo; a.n = n;                                                               \

@@ -1,6 +1,6 @@
-"""A/B of the host-pointer cuMultiGPU{trtri,lauum,potri}: whole matrix staged on the first GPU
-(default) against the slab-distributed path (CHOL_MGPU_INVERSE=slab) on all visible GPUs, and on
-one GPU with several slabs (overhead of the slab form itself).  Prints seconds and max |A A^-1 - I|."""
+"""A/B of the host-pointer cuMultiGPUDpotri on all visible GPUs: whole matrix staged on the first GPU, the distributed
+block-cyclic sweeps (default with more than one GPU), and the exchange-free slab split (CHOL_MGPU_INVERSE=staged /
+dist / slab).  Page-locked host matrix.  Prints seconds and max |A A^-1 - I|."""
 import os
 import sys
 import time
@@ -35,9 +35,12 @@ factor = F.cpu().numpy().T.copy(order="F")  # column-major lower factor as a num
 del F
 torch.cuda.synchronize()
 
-for label, env, devs in (("staged on GPU 0", {"CHOL_MGPU_INVERSE": "staged"}, list(range(ngpu))),
-                         ("slab, all GPUs", {"CHOL_MGPU_INVERSE": "slab"}, list(range(ngpu))),
-                         ("slab, 1 GPU x 4 slabs", {"CHOL_MGPU_INVERSE": "slab", "CHOL_MGPU_INVERSE_SLABS": "4"}, [0])):
+MODES = (("staged on GPU 0", {"CHOL_MGPU_INVERSE": "staged"}, list(range(ngpu))),
+         ("distributed, all GPUs", {"CHOL_MGPU_INVERSE": "dist"}, list(range(ngpu))),
+         ("slab, all GPUs", {"CHOL_MGPU_INVERSE": "slab"}, list(range(ngpu))))
+for label, env, devs in MODES:
+    if os.environ.get("AB_MODES") and label.split(",")[0].split()[0] not in os.environ["AB_MODES"].split(","):
+        continue
     for k in ("CHOL_MGPU_INVERSE", "CHOL_MGPU_INVERSE_SLABS"):
         os.environ.pop(k, None)
     os.environ.update(env)

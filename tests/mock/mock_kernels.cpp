@@ -296,6 +296,19 @@ int chol_copy_launch(int prec, int trans, int uplo, size_t m, size_t n, const vo
   if (!known(prec)) return 1;
   return enqueue(st, [=] { DISPATCH(prec, copy_t<T>(trans, uplo, m, n, (const T *)A, lda, (T *)B, ldb)) });
 }
+int chol_scatter_rows_launch(int prec, size_t m, size_t n, const void *A, size_t lda, void *B, size_t ldb, int cnb, int cp, int coff, void *st) {
+  __sync_fetch_and_add(&launches, 1);
+  if (m == 0 || n == 0) return 0;
+  if (!known(prec) || cnb <= 0 || cp <= 0) return 1;
+  const size_t es = prec == 's' ? 4 : (prec == 'z' ? 16 : 8);
+  return enqueue(st, [=] {
+    for (size_t c = 0; c < n; ++c)
+      for (size_t r = 0; r < m; ++r) {
+        const size_t gr = ((r / (size_t)cnb) * (size_t)cp + (size_t)coff) * (size_t)cnb + r % (size_t)cnb;
+        std::memcpy((char *)B + (c * ldb + gr) * es, (const char *)A + (c * lda + r) * es, es);
+      }
+  });
+}
 int chol_fill_launch(int prec, int uplo, size_t m, size_t n, double re_, double im_, void *A, size_t lda, void *st) {
   __sync_fetch_and_add(&launches, 1);
   if (m == 0 || n == 0) return 0;

@@ -239,17 +239,20 @@ def multi_device(P):
         A[100, 100] = -1.0
         ok(mg.potrf("d", uplo, 900, ptr(A), 900) == 101, "multi-GPU not-PD info")
 
-    # host-pointer TRTRI / LAUUM / POTRI: staged on one device, then slab-distributed
-    for mode in ("staged", "slab", "slab x2"):
+    # host-pointer TRTRI / LAUUM / POTRI: staged on one device, the distributed block-cyclic sweeps (the default with
+    # more than one device), then the slab split
+    for mode in ("staged", "dist", "slab", "slab x2"):
         os.environ.pop("CHOL_MGPU_INVERSE", None)
         os.environ.pop("CHOL_MGPU_INVERSE_SLABS", None)
-        if mode != "staged":
+        if mode in ("staged", "dist"):
+            os.environ["CHOL_MGPU_INVERSE"] = mode
+        else:
             os.environ["CHOL_MGPU_INVERSE"] = "slab"
         if mode == "slab x2":
             os.environ["CHOL_MGPU_INVERSE_SLABS"] = "2"
         for p in "dz":
             for uplo in "LU":
-                for n in (70, 400, 900):
+                for n in (70, 400, 900) + ((1300,) if mode == "dist" and p == "d" else ()):
                     F = H.spd_matrix(p, n, k=48)
                     ORA.potrf(p, uplo, F)
                     for name, diag in (("trtri", "N"), ("trtri", "U"), ("lauum", None), ("potri", None)):
@@ -335,9 +338,9 @@ def multi_device(P):
 
     # an allocation failure on the devices fails the call cleanly (no rank is left in a broadcast)
     os.environ["MOCK_CUDA_MEM_LIMIT"] = str(1 << 20)
-    A = H.spd_matrix("d", 1200, k=16)
+    A = H.spd_matrix("d", 2000, k=16)  # larger than anything factored so far: the resident block columns must grow
     try:
-        mg.potrf("d", "L", 1200, ptr(A), 1200)
+        mg.potrf("d", "L", 2000, ptr(A), 2000)
         ok(False, "expected CUDA_ERROR_OUT_OF_MEMORY")
     except chol.CholeskyError as e:
         ok(e.code == 2, "out-of-memory code %d" % e.code)
