@@ -73,6 +73,17 @@ __global__ void __launch_bounds__(S_THREADS) dgemm_small_kernel(const __grid_con
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
 
+  // the C tile is requested before the k loop: in the panel chain these launches are a few microseconds long and a
+  // load issued after the loop would add a full memory round trip to every one of them
+  double cpre[2][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const long long n = n0 + 4 * ty + j, m = m0 + 2 * tx + i;
+      const bool keep = n < p.N && m < p.M && !(p.cuplo == 1 && m < n) && !(p.cuplo == 2 && m > n);
+      cpre[i][j] = (keep && !p.beta_zero) ? p.C[n * p.ldc + m] : 0.0;
+    }
   double ra[S_LPT], rb[S_LPT];
   const int nk = (p.K + S_BK - 1) / S_BK;
   if (nk > 0) fetch(0, ra, rb);
@@ -108,7 +119,7 @@ __global__ void __launch_bounds__(S_THREADS) dgemm_small_kernel(const __grid_con
       if (p.cuplo == 1 && m < n) continue;
       if (p.cuplo == 2 && m > n) continue;
       double o = p.alpha * acc[i][j];
-      if (!p.beta_zero) o += p.beta * p.C[n * p.ldc + m];
+      if (!p.beta_zero) o += p.beta * cpre[i][j];
       p.D[n * p.ldd + m] = o;
     }
   }

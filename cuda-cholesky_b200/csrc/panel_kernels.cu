@@ -185,7 +185,8 @@ __global__ void __launch_bounds__(PANEL_THREADS) potf2_kernel(int upper, int n, 
   static_assert(16 * CW == NMAX, "16 warps x CW columns");
   T *Ls = reinterpret_cast<T *>(smem_raw);  // L(i,c) at Ls[i + c*LD], zeros above the diagonal and beyond n
   __shared__ int sfail;                      // first failing column + 1
-  if (*dinfo != 0) return;
+  // (the "already failed" test of *dinfo is taken AFTER the staging loads have been issued: a dependent global load
+  // in front of them costs a full memory round trip on the serial chain of the factorisation)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) sfail = 0;
 #ifndef CHOL_CPU_EMU
@@ -207,6 +208,7 @@ __global__ void __launch_bounds__(PANEL_THREADS) potf2_kernel(int upper, int n, 
       v[u] = zero_of<T>();
       if (r < n && c < n && (upper ? r <= c : r >= c)) v[u] = A[(long long)c * lda + r];
     }
+    if (*dinfo != 0) return;  // an earlier block has failed: nothing is touched (uniform over the CTA)
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
       const int idx = threadIdx.x + u * PANEL_THREADS, r = idx % NMAX, c = idx / NMAX;
@@ -323,10 +325,32 @@ __global__ void __launch_bounds__(256) trsm_rows_kernel(int upper, int n, const 
   CHOL_DYN_SMEM(smem_raw);
   T *Ms = reinterpret_cast<T *>(smem_raw);                         // Ms[k * LD + j] = conj(L(j,k)) / L(k,k), j > k
   Real *dinv = reinterpret_cast<Real *>(Ms + (size_t)NMAX * LD);   // 1 / L(k,k)
-  if (dinfo != nullptr && *dinfo != 0) return;                    // the factorisation has already failed
   // With y_k = b_k - sum_{j<k} x_j conj(L_kj) and x_k = y_k / L_kk the recurrence reads
   //     y_k = b_k - sum_{j<k} y_j * M[j][k],   M[j][k] = conj(L_kj) / L_jj,
   // so the serial chain of a step is one shuffle and one FMA (no multiply); x = y / diag(L) at the very end.
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane % NG, lg = lane / NG;  // group within the warp, lane within the group
+  // rows of the warp: row0 + rr*NG + g (consecutive lanes of one lg read consecutive rows of a column)
+  const long long row0 = ((long long)blockIdx.x * cwarps + warp) * (NG * RR);
+  const bool owns_rows = warp < cwarps && row0 < m;  // helper warps only stage
+  T b[RR][NT];
+  auto load_rows = [&]() {
+#pragma unroll
+    for (int rr = 0; rr < RR; ++rr) {
+      const long long row = row0 + rr * NG + g;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const int j = lg + G * t;
+        T v = zero_of<T>();
+        if (owns_rows && row < m && j < n) v = transB ? conj_of(B[(long long)row * ldb + j]) : B[(long long)j * ldb + row];
+        b[rr][t] = v;
+      }
+    }
+  };
+  // one-row-per-warp shape: the few right-hand side values are requested first and arrive while the triangle is staged
+  // (the tall shape needs its registers for the staging batch)
+  constexpr bool EARLY_ROWS = RR * NT <= 8;
+  if constexpr (EARLY_ROWS) load_rows();
   // all 256 threads of the CTA stage (also the warps that own no rows), ALL loads of a thread in flight at once;
   // lanes along the contiguous direction of the storage: lower -> j (rows of L), upper -> k (rows of U).  The
   // reciprocals of the diagonal are computed while those loads are in flight.
@@ -341,6 +365,8 @@ __global__ void __launch_bounds__(256) trsm_rows_kernel(int upper, int n, const 
       if (j < n && j > k) v[u] = upper ? L[(long long)j * ldl + k] : conj_of(L[(long long)k * ldl + j]);
     }
     if (threadIdx.x < NMAX) dinv[threadIdx.x] = ((int)threadIdx.x < n) ? Real(1) / re_of(L[(long long)threadIdx.x * ldl + threadIdx.x]) : Real(0);
+    // the factorisation has already failed: leave X alone (tested here, behind the loads, not in front of them)
+    if (dinfo != nullptr && *dinfo != 0) return;
     __syncthreads();
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
@@ -350,23 +376,8 @@ __global__ void __launch_bounds__(256) trsm_rows_kernel(int upper, int n, const 
     }
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane % NG, lg = lane / NG;  // group within the warp, lane within the group
-  // rows of the warp: row0 + rr*NG + g (consecutive lanes of one lg read consecutive rows of a column)
-  const long long row0 = ((long long)blockIdx.x * cwarps + warp) * (NG * RR);
-  if (warp >= cwarps || row0 >= m) return;
-  T b[RR][NT];
-#pragma unroll
-  for (int rr = 0; rr < RR; ++rr) {
-    const long long row = row0 + rr * NG + g;
-#pragma unroll
-    for (int t = 0; t < NT; ++t) {
-      const int j = lg + G * t;
-      T v = zero_of<T>();
-      if (row < m && j < n) v = transB ? conj_of(B[(long long)row * ldb + j]) : B[(long long)j * ldb + row];
-      b[rr][t] = v;
-    }
-  }
+  if (!owns_rows) return;
+  if constexpr (!EARLY_ROWS) load_rows();
 #pragma unroll
   for (int kb = 0; kb < NT; ++kb) {
     const int kend = min(G, n - G * kb);  // <= 0 beyond the block: nothing to do (keeps the kb loop fully unrollable)

@@ -56,7 +56,7 @@ size_t chol_default_nb(int prec, size_t n) {
    * z  N = 16384: 256 / 512 -> 29.8 / 30.0;  s 16384, 32768: 512 best;  c 16384: 256 / 512 -> 118 / 105 */
   if (prec == 'z') return n >= 12288 ? 512 : (n >= 8192 ? 256 : 128);
   if (prec == 'd') return n >= 24576 ? 1024 : (n >= 12288 ? 768 : (n >= 6144 ? 512 : 256));
-  if (prec == 'c') return 256;
+  if (prec == 'c') return n >= 24576 ? 512 : 256; /* N = 32768: 512 / 256 -> 150 / 146 */
   return n >= 12288 ? 512 : 256;
 }
 
