@@ -389,7 +389,10 @@ def run_ours(args):
     e2e_steps = max(1, min(K, args.e2e_steps))
     e2e_times = []
     e2e_note = None
-    if P == 1:
+    if args.e2e_steps == 0:  # records at sizes whose host matrix does not fit a sensible run (N = 131072: 137 GB)
+        h2d_bytes = d2h_bytes = 0
+        e2e_times, info2, e2e_api = [float("nan")], 0, "skipped (--e2e-steps 0)"
+    elif P == 1:
         h2d_bytes = d2h_bytes = nloc * N * 8
         hostA = torch.empty(nloc, N, dtype=torch.float64, pin_memory=True)
         del A  # the host-pointer API owns its own device copy
