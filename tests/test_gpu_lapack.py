@@ -230,6 +230,43 @@ def test_potrf_full_elementwise_vs_oracle_mid_size(lapack, p, uplo, n):
     assert err <= elem_tol(p, n), err
 
 
+@pytest.mark.slow
+@pytest.mark.parametrize("uplo", "LU")
+def test_potrf_full_elementwise_n16384_vs_reference(lapack, uplo):
+    """BASELINE.json configs[1] at its stated size: dpotrf N = 16384, the WHOLE factor elementwise against the
+    reference's own CPU dpotrf (oracle/_ref, OpenMP on the box's host cores: ~1 min per triangle), tolerance
+    64 n eps max|L_ref| (SURVEY.md section 8d cfg 2), plus one non-PD case with equal info."""
+    if H.ref() is None:
+        pytest.skip("compiled reference (oracle/_ref) not available")
+    import ctypes
+    try:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(ctypes.c_int(len(os.sched_getaffinity(0))))
+    except OSError:
+        pass
+    REF = H.CpuLib("ref")
+    n = 16384
+    g = torch.Generator(device="cuda").manual_seed(H.SEED)
+    B = torch.rand(n, 1024, dtype=torch.float64, device="cuda", generator=g) - 0.5
+    A = B @ B.T
+    A.diagonal().add_(float(n))
+    del B
+    want = np.asfortranarray(A.cpu().numpy())  # symmetric: row-major == column-major
+    assert REF.potrf("d", uplo, want) == 0
+    F = A.clone()
+    assert lapack.potrf("d", uplo, n, F.data_ptr(), n) == 0
+    got = F.cpu().numpy().T  # column-major view
+    err = np.abs(H.tri(got, uplo) - H.tri(want, uplo)).max() / np.abs(H.tri(want, uplo)).max()
+    assert err <= elem_tol("d", n), err
+    # not positive definite at a column deep inside: same info as the reference (leading block only, to keep it short)
+    m = 3000
+    Ab = np.asfortranarray(A[:m, :m].cpu().numpy())
+    Ab[2500, 2500] = -1.0
+    wantb = Ab.copy(order="F")
+    winfo = REF.potrf("d", uplo, wantb)
+    dA, lda = G.to_dev(Ab)
+    assert lapack.potrf("d", uplo, m, dA.data_ptr(), lda) == winfo == 2501
+
+
 @pytest.mark.parametrize("p", "dzsc")
 @pytest.mark.parametrize("uplo", "LU")
 @pytest.mark.parametrize("n,nrhs", [(1, 1), (100, 7), (300, 64), (700, 130)])
