@@ -198,6 +198,12 @@ class LapackHandle:
                                   C.c_void_p(B), C.c_size_t(ldb), C.byref(info)), allow_invalid)
         return (info.value, rc) if allow_invalid else info.value
 
+    def potrf_logdet(self):
+        """log det A accumulated by the diagonal-block kernels during the last potrf on this handle (extension)."""
+        v = C.c_double(0)
+        _check("cuLAPACKPotrfLogdet", lib().cuLAPACKPotrfLogdet(self.h, C.byref(v)))
+        return v.value
+
     def trti22(self, p, uplo, diag, n, A, lda, B, ldb, dinfo, stream=0):
         f = getattr(lib(), "cu%strti22" % _U[p])
         return _check(f.__name__, f(self.h, C.c_int(ord(uplo)), C.c_int(ord(diag)), C.c_size_t(n), C.c_void_p(A),

@@ -76,6 +76,10 @@ int chol_diag_max(int prec); /* largest n the one-CTA diagonal kernels accept: 1
  * info_base + failing column (1-based) if it is still 0 and a pivot is <= 0 or NaN; when
  * *dinfo != 0 on entry the kernel does nothing (lapack/dpotrf.c:70-73 semantics). */
 int chol_potf2_launch(int prec, int uplo, size_t n, void *A, size_t lda, long *dinfo, long info_base, void *stream);
+/* the same, and on success *logacc (device double, may be NULL) += 2 * sum_c log Re L(c,c): the log-determinant of the
+ * factored matrix accumulates over the diagonal-block launches of one factorisation (they are serialised on one stream) */
+int chol_potf2_logdet_launch(int prec, int uplo, size_t n, void *A, size_t lda, long *dinfo, long info_base, double *logacc,
+                             void *stream);
 /* X (m x n) = B * L^-H by substitution, L = the n x n lower-triangular factor of a diagonal block (uplo 'L': stored
  * as such; uplo 'U': stored as U = L^H, so this is X = B * U^-1).  Any number of rows m; rows are independent, the
  * launch spreads them over the SMs.  transB / transX != 0: the operand is given / wanted as its conjugate transpose

@@ -179,7 +179,7 @@ __device__ __forceinline__ void potf2_panel(T (&reg)[NA][CW], T *Ls, int c0, int
 
 template <typename T, int NA, int CW, bool DBG = false>
 __global__ void __launch_bounds__(PANEL_THREADS) potf2_kernel(int upper, int n, T *A, long long lda, long *dinfo, long info_base,
-                                                              long long *dbg = nullptr) {
+                                                              double *logacc, long long *dbg = nullptr) {
   CHOL_DYN_SMEM(smem_raw);
   constexpr int NMAX = 32 * NA, LD = NMAX + 1;
   static_assert(16 * CW == NMAX, "16 warps x CW columns");
@@ -294,6 +294,23 @@ __global__ void __launch_bounds__(PANEL_THREADS) potf2_kernel(int upper, int n, 
   {
     const int fail = sfail;  // a failure in the last panel
     store_factor_columns<T, NA, LD>(upper, n, fail != 0 ? fail - 1 : n, Ls, A, lda, warp, lane);
+    // fused logdet ("the diagonal is in shared memory anyway"): *logacc += 2 sum log L(c,c), off
+    // the serial chain, summed in a fixed order; the diagonal-block launches of one factorisation are serialised on
+    // their stream, so a plain read-modify-write by one thread is enough
+    if (logacc != nullptr && fail == 0) {
+      __shared__ double part[PANEL_THREADS / 32];
+      const int c = CW * warp + lane;
+      double v = (lane < CW && c < n) ? log((double)re_of(Ls[c + c * LD])) : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) part[warp] = v;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double sum = 0.0;
+        for (int q = 0; q < PANEL_THREADS / 32; ++q) sum += part[q];
+        *logacc += 2.0 * sum;
+      }
+    }
   }
   if (warp == 0) CHOL_DBG(61);
 #undef CHOL_DBG
@@ -710,18 +727,18 @@ template <typename K> static int set_smem(K kern, size_t bytes) {
 
 static long long *g_potf2_dbg = nullptr;  // test hook: 64 phase timestamps of the next potf2 launches (chol_potf2_set_debug)
 template <typename T>
-static int potf2_t(int uplo, size_t n, void *A, size_t lda, long *dinfo, long base, cudaStream_t st) {
+static int potf2_t(int uplo, size_t n, void *A, size_t lda, long *dinfo, long base, double *logacc, cudaStream_t st) {
   constexpr int NMAX = sizeof(T) == 16 ? 64 : 128;  // chol_diag_max
   const size_t sm = (size_t)NMAX * (NMAX + 1) * sizeof(T);
   if (g_potf2_dbg != nullptr) {  // instrumented instantiation (test hook)
     auto kd = potf2_kernel<T, NMAX / 32, NMAX / 16, true>;
     int ed = set_smem(kd, sm); if (ed) return ed;
-    kd<<<1, PANEL_THREADS, sm, st>>>(uplo == 'U', (int)n, (T *)A, (long long)lda, dinfo, base, g_potf2_dbg);
+    kd<<<1, PANEL_THREADS, sm, st>>>(uplo == 'U', (int)n, (T *)A, (long long)lda, dinfo, base, logacc, g_potf2_dbg);
     return (int)cudaGetLastError();
   }
   auto kern = potf2_kernel<T, NMAX / 32, NMAX / 16>;  // 16 warps x NMAX/16 columns
   int e = set_smem(kern, sm); if (e) return e;
-  kern<<<1, PANEL_THREADS, sm, st>>>(uplo == 'U', (int)n, (T *)A, (long long)lda, dinfo, base, nullptr);
+  kern<<<1, PANEL_THREADS, sm, st>>>(uplo == 'U', (int)n, (T *)A, (long long)lda, dinfo, base, logacc, nullptr);
   CHOL_COUNT_LAUNCH();
   return (int)cudaGetLastError();
 }
@@ -829,10 +846,14 @@ extern "C" unsigned long long chol_launch_count(int reset) {
 
 extern "C" int chol_diag_max(int prec) { return prec == 'z' ? 64 : 128; }
 
-extern "C" int chol_potf2_launch(int prec, int uplo, size_t n, void *A, size_t lda, long *dinfo, long info_base, void *stream) {
+extern "C" int chol_potf2_logdet_launch(int prec, int uplo, size_t n, void *A, size_t lda, long *dinfo, long info_base, double *logacc,
+                                        void *stream) {
   if (n == 0) return 0;
   if (n > (size_t)chol_diag_max(prec)) return (int)cudaErrorInvalidValue;
-  DISPATCH(prec, potf2_t<T>(uplo, n, A, lda, dinfo, info_base, (cudaStream_t)stream));
+  DISPATCH(prec, potf2_t<T>(uplo, n, A, lda, dinfo, info_base, logacc, (cudaStream_t)stream));
+}
+extern "C" int chol_potf2_launch(int prec, int uplo, size_t n, void *A, size_t lda, long *dinfo, long info_base, void *stream) {
+  return chol_potf2_logdet_launch(prec, uplo, n, A, lda, dinfo, info_base, nullptr, stream);
 }
 extern "C" int chol_trsm_rows_launch(int prec, int uplo, size_t n, const void *L, size_t ldl, size_t m, int transB, const void *B,
                                      size_t ldb, int transX, void *X, size_t ldx, const long *dinfo, void *stream) {

@@ -49,8 +49,10 @@ struct __culapackhandle_st {
   CUevent ev_dx[CHOL_DIAG_EVENTS], ev_dcol[CHOL_DIAG_EVENTS], ev_solve; /* pipelined panel solve (lapack.c panel_factor_solve) */
   CUdeviceptr ws; /* workspace, cached across calls (the reference allocates per call, dpotrf.c:200) */
   size_t ws_bytes;
-  CUdeviceptr dinfo;      /* device long */
-  long *hinfo;            /* pinned host mirror */
+  CUdeviceptr dinfo;      /* device: long info, then double = the log-determinant accumulated by the diagonal-block kernels */
+  long *hinfo;            /* pinned host mirror (16 bytes) */
+  double last_logdet;     /* of the last POTRF on this handle (cuLAPACKPotrfLogdet) */
+  bool last_logdet_valid;
   CUdeviceptr logdet_scr; /* reduction scratch + result; shared by every logdet call on the handle: calls on
                            * different streams are ordered through logdet_done (same stream: stream order) */
   CUevent logdet_done;
@@ -116,6 +118,7 @@ typedef struct chol_ws {
   CUdeviceptr W[2]; /* panel buffers, ldw x nb */
   CUdeviceptr Xd;   /* nb x nb : inverse of a diagonal block (TRTRI), product block (LAUUM) */
   CUdeviceptr T1;   /* nb x nb : temporary of the blocked small inverse */
+  CUdeviceptr logacc; /* device double the diagonal-block kernels add 2 sum log L(c,c) to (0 = none) */
   size_t kp;        /* s, c with the tensor-core update: K pitch of the TF32 planes (0 = FFMA path) */
   CUdeviceptr Whi[2], Wlo[2]; /* ldw x kp floats (c: 2 ldw x kp, real embedding), K-major: tf32 hi / lo planes of W[0], W[1] */
 } chol_ws;

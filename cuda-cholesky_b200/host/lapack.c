@@ -68,6 +68,7 @@ CUresult chol_carve(CULAPACKhandle h, int prec, size_t n, chol_ws *w) {
 CUresult chol_carve_nb(CULAPACKhandle h, int prec, size_t n, size_t nb, chol_ws *w) {
   w->es = chol_esize(prec);
   w->nb = nb;
+  w->logacc = h->dinfo + sizeof(long);
   w->db = (size_t)chol_diag_max(prec);
   if (w->nb < w->db) w->db = w->nb;
   w->ldw = chol_roundup(n > w->nb ? n : w->nb, 16);
@@ -93,7 +94,7 @@ CUresult chol_carve_nb(CULAPACKhandle h, int prec, size_t n, size_t nb, chol_ws 
 
 /* `producer` = the stream on which the info-writing kernels ran */
 static CUresult finish_info(CULAPACKhandle h, CUstream producer, long *info) {
-  CU_ERROR_CHECK(cuMemcpyDtoHAsync(h->hinfo, h->dinfo, sizeof(long), producer));
+  CU_ERROR_CHECK(cuMemcpyDtoHAsync(h->hinfo, h->dinfo, 16, producer)); /* info and the fused log-determinant */
   CU_ERROR_CHECK(cuStreamSynchronize(h->s_panel));
   CU_ERROR_CHECK(cuStreamSynchronize(h->s_update));
   CU_ERROR_CHECK(cuStreamSynchronize(h->s_look));
@@ -116,7 +117,7 @@ CUresult chol_diag_factor_ev(int prec, int uplo, size_t jb, CUdeviceptr A, size_
   for (size_t c = 0; c < nblk; c++) {
     const size_t i = c * db, ib = chol_min(db, jb - i), r = jb - i - ib;
     const CUdeviceptr Aii = chol_at(A, lda, i, i, es);
-    RT_CHECK(chol_potf2_launch(prec, uplo, ib, (void *)Aii, lda, dinfo, base + (long)i, (void *)st));
+    RT_CHECK(chol_potf2_logdet_launch(prec, uplo, ib, (void *)Aii, lda, dinfo, base + (long)i, (double *)w->logacc, (void *)st));
     if (ev_fact) CU_ERROR_CHECK(cuEventRecord(ev_fact[c], st));
     if (r == 0) break;
     const CUdeviceptr A22 = chol_at(A, lda, i + ib, i + ib, es);
@@ -257,7 +258,8 @@ static CUresult potrf_body(CULAPACKhandle h, int prec, int uplo, size_t n, CUdev
   const int herm = chol_is_complex(prec);
   long *dinfo = (long *)h->dinfo;
   CUstream sp = h->s_panel, su = h->s_update, sl = h->s_look;
-  CU_ERROR_CHECK(cuMemsetD8Async(h->dinfo, 0, sizeof(long), sp));
+  CU_ERROR_CHECK(cuMemsetD8Async(h->dinfo, 0, 16, sp)); /* info and the log-determinant accumulator */
+  h->last_logdet_valid = false;
   h->prof_n = 0;
   const bool split = chol_lookahead_split();
   CUevent look_pending = NULL; /* the lower part of this step's block column is still being updated on sl */
@@ -360,6 +362,8 @@ static CUresult potrf_body(CULAPACKhandle h, int prec, int uplo, size_t n, CUdev
     }
   }
   CU_ERROR_CHECK(finish_info(h, sp, info));
+  h->last_logdet = ((const double *)h->hinfo)[1];
+  h->last_logdet_valid = (*info == 0);
   for (int i = 0; i < h->prof_n; i++) { /* the streams are idle: all events have completed */
     float ms = 0.f;
     CU_ERROR_CHECK(cuEventElapsedTime(&ms, h->prof_e0[i], h->prof_e1[i]));
@@ -525,6 +529,14 @@ static CUresult potrs_body(CULAPACKhandle h, int prec, int uplo, size_t n, size_
 CUresult chol_potrs(CULAPACKhandle h, int prec, int uplo, size_t n, size_t nrhs, CUdeviceptr A, size_t lda, CUdeviceptr B,
                     size_t ldb) {
   IN_HANDLE_CONTEXT(h, potrs_body(h, prec, uplo, n, nrhs, A, lda, B, ldb));
+}
+
+/* log det A = 2 sum log L(i,i) of the last cu*potrf on this handle, accumulated by the diagonal-block kernels while they
+ * factored; INVALID_VALUE when that factorisation failed or none has run */
+CUresult cuLAPACKPotrfLogdet(CULAPACKhandle h, double *logdet) {
+  if (h == NULL || logdet == NULL || !h->last_logdet_valid) return CUDA_ERROR_INVALID_VALUE;
+  *logdet = h->last_logdet;
+  return CUDA_SUCCESS;
 }
 
 static CUresult logdet_body(CULAPACKhandle h, int prec, CUdeviceptr x, size_t incx, size_t n, void *result, CUstream stream) {

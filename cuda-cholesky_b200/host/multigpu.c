@@ -429,7 +429,8 @@ static CUresult dist_potrf(chol_rank *R, int prec, size_t n, CUdeviceptr Aloc, s
   const bool split = chol_lookahead_split();
   CUevent look_pending = NULL; /* lower part of the block column this rank factors next, still being updated on sl */
   const size_t my_cols = local_cols(n, nb, me, P);
-  CU_ERROR_CHECK(cuMemsetD8Async(h->dinfo, 0, sizeof(long), sp));
+  CU_ERROR_CHECK(cuMemsetD8Async(h->dinfo, 0, 16, sp)); /* info and this rank's share of the fused log-determinant */
+  h->last_logdet_valid = false;
   h->prof_n = 0;
 
   for (size_t c = 0; c < nblk; c++) {
@@ -539,12 +540,14 @@ static CUresult dist_potrf(chol_rank *R, int prec, size_t n, CUdeviceptr Aloc, s
       }
     }
   }
-  CU_ERROR_CHECK(cuMemcpyDtoHAsync(h->hinfo, h->dinfo, sizeof(long), sp));
+  CU_ERROR_CHECK(cuMemcpyDtoHAsync(h->hinfo, h->dinfo, 16, sp));
   CU_ERROR_CHECK(cuStreamSynchronize(sp));
   CU_ERROR_CHECK(cuStreamSynchronize(su));
   CU_ERROR_CHECK(cuStreamSynchronize(sl));
   if (ga != NULL) CU_ERROR_CHECK(cuStreamSynchronize(ga->s_copy));
   *info = *h->hinfo;
+  h->last_logdet = ((const double *)h->hinfo)[1]; /* the diagonal blocks THIS rank factored: sum over ranks = log det A */
+  h->last_logdet_valid = (*info == 0);
   for (int i = 0; i < h->prof_n; i++) {
     float ms = 0.f;
     CU_ERROR_CHECK(cuEventElapsedTime(&ms, h->prof_e0[i], h->prof_e1[i]));

@@ -133,8 +133,9 @@ CUresult cuLAPACKCreate(CULAPACKhandle *handle) {
     if (e == CUDA_SUCCESS) e = cuEventCreate(&h->ev_dcol[i], CU_EVENT_DISABLE_TIMING);
   }
   if (e == CUDA_SUCCESS) e = cuEventCreate(&h->ev_solve, CU_EVENT_DISABLE_TIMING);
-  if (e == CUDA_SUCCESS) e = cuMemAlloc(&h->dinfo, sizeof(long));
-  if (e == CUDA_SUCCESS) e = cuMemAllocHost((void **)&h->hinfo, sizeof(long));
+  if (e == CUDA_SUCCESS) e = cuMemAlloc(&h->dinfo, 16);
+  if (e == CUDA_SUCCESS) e = cuMemsetD8(h->dinfo, 0, 16);
+  if (e == CUDA_SUCCESS) e = cuMemAllocHost((void **)&h->hinfo, 16);
   if (e == CUDA_SUCCESS) e = cuMemAlloc(&h->logdet_scr, chol_logdet_scratch_bytes() + 64);
   if (e == CUDA_SUCCESS) e = cuMemsetD8(h->logdet_scr, 0, chol_logdet_scratch_bytes() + 64);
   if (e == CUDA_SUCCESS) e = cuMemAllocHost(&h->hlogdet, 16);

@@ -70,6 +70,14 @@ CUresult cuCpotrs(CULAPACKhandle, CBlasUplo, size_t n, size_t nrhs, CUdeviceptr 
 CUresult cuZpotrs(CULAPACKhandle, CBlasUplo, size_t n, size_t nrhs, CUdeviceptr A, size_t lda, CUdeviceptr B, size_t ldb, long *info);
 
 /* ---------------------------------------------------------------------------------------------
+ * Fused log-determinant: the diagonal-block kernel of POTRF adds 2 log L(i,i) while it factors, so log det A of the
+ * matrix the last cu{S,D,C,Z}potrf on this handle factored is available without another pass (the reference needs
+ * cu*logdet on the factor's diagonal, lapack/dlogdet.c:37-74).  CUDA_ERROR_INVALID_VALUE if that call failed (info > 0)
+ * or none has run.  With cholDist*potrf every rank holds the share of the diagonal blocks it factored: sum over ranks.
+ * ------------------------------------------------------------------------------------------- */
+CUresult cuLAPACKPotrfLogdet(CULAPACKhandle, double *logdet);
+
+/* ---------------------------------------------------------------------------------------------
  * Tuning / measurement hooks
  * ------------------------------------------------------------------------------------------- */
 /* outer block size of the LAPACK drivers (k of the trailing update); 0 = built-in default

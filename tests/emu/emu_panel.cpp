@@ -60,10 +60,10 @@ static void check(bool ok, const char *what, double err) {
 }
 
 template <typename T, int NMAX>
-static void run_potf2(int upper, int n, int lda, std::vector<typename Host<T>::type> &A, long *info, long base) {
+static void run_potf2(int upper, int n, int lda, std::vector<typename Host<T>::type> &A, long *info, long base, double *logacc = nullptr) {
   const size_t sm = (size_t)NMAX * (NMAX + 1) * sizeof(T);
   T *dA = reinterpret_cast<T *>(A.data());
-  emu::launch(dim3(1), dim3(PANEL_THREADS), sm, [&] { potf2_kernel<T, NMAX / 32, NMAX / 16>(upper, n, dA, lda, info, base); });
+  emu::launch(dim3(1), dim3(PANEL_THREADS), sm, [&] { potf2_kernel<T, NMAX / 32, NMAX / 16>(upper, n, dA, lda, info, base, logacc); });
 }
 
 // potf2 (register-resident, in-kernel look-ahead): factor vs plain loops, other triangle and padding rows untouched
@@ -76,10 +76,14 @@ static void case_potf2(const char *name, int n, double tol) {
     spd<T, H>(n, lda, A0, 11u + n);
     A1 = A0;
     long i1 = 0;
+    double logacc = 1.5;  // the fused logdet ADDS to what is there
     if (getenv("EMU_TRACE")) std::fprintf(stderr, "[%s n=%d upper=%d] potf2...\n", name, n, upper);
-    run_potf2<T, NMAX>(upper, n, lda, A1, &i1, 100);
+    run_potf2<T, NMAX>(upper, n, lda, A1, &i1, 100, &logacc);
     std::vector<H> L = A0;
     const int ri = ref_potrf_lower(n, L, lda);
+    double want_ld = 1.5;
+    for (int c = 0; c < n; ++c) want_ld += 2.0 * std::log((double)std::real(L[c + (size_t)c * lda]));
+    if (std::fabs(logacc - want_ld) > 1e-4 * std::fabs(want_ld) + 1e-4) { check(false, "fused logdet", std::fabs(logacc - want_ld)); }
     double e_ref = 0, e_other = 0;
     for (int j = 0; j < n; ++j)
       for (int i = 0; i < n; ++i) {
@@ -217,7 +221,7 @@ static void case_unfused(const char *name, int n, double tol) {
     A = A0;
     long info = 0;
     T *dA = reinterpret_cast<T *>(A.data());
-    emu::launch(dim3(1), dim3(PANEL_THREADS), (size_t)NMAX * (NMAX + 1) * sizeof(T), [&] { potf2_kernel<T, NMAX / 32, NMAX / 16>(upper, n, dA, lda, &info, 7); });
+    emu::launch(dim3(1), dim3(PANEL_THREADS), (size_t)NMAX * (NMAX + 1) * sizeof(T), [&] { potf2_kernel<T, NMAX / 32, NMAX / 16>(upper, n, dA, lda, &info, 7, nullptr); });
     std::vector<H> L = A0;
     ref_potrf_lower(n, L, lda);
     double e = 0, e_other = 0;
@@ -289,7 +293,7 @@ static void case_unfused(const char *name, int n, double tol) {
   A0[bad + (size_t)bad * n] = H(-1);
   long info = 0;
   T *dA = reinterpret_cast<T *>(A0.data());
-  emu::launch(dim3(1), dim3(PANEL_THREADS), (size_t)NMAX * (NMAX + 1) * sizeof(T), [&] { potf2_kernel<T, NMAX / 32, NMAX / 16>(0, n, dA, n, &info, 500); });
+  emu::launch(dim3(1), dim3(PANEL_THREADS), (size_t)NMAX * (NMAX + 1) * sizeof(T), [&] { potf2_kernel<T, NMAX / 32, NMAX / 16>(0, n, dA, n, &info, 500, nullptr); });
   char what[160];
   std::snprintf(what, sizeof what, "%s potf2 n=%d not PD at column %d: info", name, n, bad);
   check(info == 500 + bad + 1, what, 0);

@@ -264,6 +264,27 @@ int chol_gemm_launch(const chol_gemm_desc *dp) {
   const chol_gemm_desc d = *dp;
   return enqueue(d.stream, [d] { DISPATCH(d.prec, gemm_t<T>(&d)) });
 }
+int chol_potf2_logdet_launch(int prec, int uplo, size_t n, void *A, size_t lda, long *dinfo, long base, double *logacc, void *st) {
+  __sync_fetch_and_add(&launches, 1);
+  if (n == 0) return 0;
+  if (!known(prec) || n > (size_t)chol_diag_max(prec)) return 1;
+  return enqueue(st, [=] {
+    if (*dinfo != 0) return;
+    DISPATCH(prec, potf2_t<T>(uplo == 'U', n, (T *)A, lda, dinfo, base, (T *)nullptr, 0))
+    if (*dinfo == 0 && logacc != nullptr) {
+      double s = 0.0;
+      for (size_t i = 0; i < n; ++i) {
+        switch (prec) {
+          case 's': s += std::log((double)((const float *)A)[i * lda + i]); break;
+          case 'd': s += std::log(((const double *)A)[i * lda + i]); break;
+          case 'c': s += std::log((double)((const std::complex<float> *)A)[i * lda + i].real()); break;
+          default: s += std::log(((const std::complex<double> *)A)[i * lda + i].real()); break;
+        }
+      }
+      *logacc += 2.0 * s;
+    }
+  });
+}
 int chol_potf2_launch(int prec, int uplo, size_t n, void *A, size_t lda, long *dinfo, long base, void *st) {
   __sync_fetch_and_add(&launches, 1);
   if (n == 0) return 0;

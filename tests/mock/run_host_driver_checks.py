@@ -89,10 +89,12 @@ def single_device_lapack():
                 close(H.tri(A, uplo), H.tri(want, uplo), p, n, tag)
                 other_untouched(A, A0, uplo, tag)
                 if n in (5, 300, 700) and nb in (0, 128):
-                    # logdet of the factor
+                    # logdet of the factor, and the one the diagonal-block launches accumulated while factoring
                     got_ld = lap.logdet(p, ptr(A), ld(A) + 1, n)
                     want_ld = ORA.logdet(p, want, ld(want) + 1, n)
                     ok(abs(got_ld - want_ld) <= 1e-5 * abs(want_ld) + 1e-5, tag + " logdet")
+                    fused = lap.potrf_logdet()
+                    ok(abs(fused - want_ld) <= 1e-5 * abs(want_ld) + 1e-5, tag + " fused logdet %r vs %r" % (fused, want_ld))
                     # potrs: solve A X = B from the factor
                     nrhs = 7
                     B0 = H.rand_matrix(p, n, nrhs, seed=5, ld=n + 1)

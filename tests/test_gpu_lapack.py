@@ -292,6 +292,31 @@ def test_potrs_solves_the_system(lapack, p, uplo, n, nrhs):
     assert np.linalg.norm(R) <= 16 * n * H.eps(p) * np.linalg.norm(A0) * np.linalg.norm(got)
 
 
+@pytest.mark.parametrize("p", "dzsc")
+@pytest.mark.parametrize("uplo", "LU")
+@pytest.mark.parametrize("n", [1, 100, 129, 777, 2000])
+def test_potrf_fused_logdet(lapack, p, uplo, n):
+    """cuLAPACKPotrfLogdet (extension): the log-determinant the diagonal-block kernels accumulate
+    while they factor equals the reference-style logdet of the factor's diagonal; a failed factorisation has none."""
+    A = H.spd_matrix(p, n, k=min(n, 64))
+    F = A.copy(order="F")
+    assert ORA.potrf(p, uplo, F) == 0
+    want = ORA.logdet(p, F, F.strides[1] // F.itemsize + 1, n)
+    dA, lda = G.to_dev(A)
+    assert lapack.potrf(p, uplo, n, dA.data_ptr(), lda) == 0
+    got = lapack.potrf_logdet()
+    tol = 1e-12 if p in "dz" else 2e-6
+    assert abs(got - want) <= tol * max(1.0, abs(want)), (got, want)
+    sep = lapack.logdet(p, dA.data_ptr(), lda + 1, n)
+    assert abs(got - sep) <= (1e-12 if p in "dz" else 1e-5) * max(1.0, abs(sep))
+    if n >= 100:
+        A[n // 2, n // 2] = -1.0
+        dA, lda = G.to_dev(A)
+        assert lapack.potrf(p, uplo, n, dA.data_ptr(), lda) == n // 2 + 1
+        with pytest.raises(G.chol.CholeskyError):
+            lapack.potrf_logdet()
+
+
 def test_potrs_argument_errors(lapack):
     G.chol.set_xerbla_silent()
     A = H.spd_matrix("d", 8)
