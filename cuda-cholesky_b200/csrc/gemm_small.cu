@@ -1,8 +1,7 @@
-// gemm_small.cu — small-tile FP64 GEMM for the latency-bound GEMMs of the panel chain
-// (CHOL_SMALL_GEMM=1; written after the round-1 GPU budget was spent: off until verified and
-// measured on hardware, own translation unit so the measured kernels stay bit-identical).
+// gemm_small.cu — small-tile FP64 GEMM for the latency-bound GEMMs of the panel chain (measured on B200:
+// dpotrf N = 16384 25.7 -> 26.9 TFLOP/s when it was introduced, profiles/r02_staged_ab.txt).
 //
-// Why: the diagonal-block recursion of POTRF (host/lapack.c chol_diag_factor_inverse) issues GEMMs
+// Why: the diagonal-block recursion of POTRF (host/lapack.c chol_diag_factor_ev) issues GEMMs
 // such as 384 x 128 x 128 or 256 x 256 x 128.  On the 128 x 64 DMMA tiles they are 6-16 CTAs: 6-16 of
 // 148 SMs, each needing >= 16k cycles of its FP64 pipe per tile (profiles/r01_static_analysis.md §3),
 // ~25 us per launch on the serial panel chain.  The plain DFMA rate of a B200 SM is close to its

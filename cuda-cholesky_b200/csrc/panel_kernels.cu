@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(256) trsm_rows_kernel(int upper, int n, const 
 // EIGHT columns at once (columns warp+16c): the residuals live in registers (lane = row mod 32), the
 // current unknown is broadcast by shuffle, and the eight independent chains hide each other's latency
 // while sharing the loads of L's column k.
-// V2 (same switch as the fused kernel's V2, CHOL_POTF2_V2): chains that cannot have started in the current
+// Chains that cannot have started in the current
 // 32-row slice are pruned at compile time.
 template <typename T, int NQ, int NC, bool V2 = false>
 __global__ void __launch_bounds__(PANEL_THREADS) trti2_kernel(int upper, int unit, int n, const T *A, long long lda, T *B,

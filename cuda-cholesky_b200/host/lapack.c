@@ -5,10 +5,13 @@
  * left-looking loop whose diagonal block makes a D2H -> CPU -> H2D round trip every step.
  * What this file does instead (B200-first):
  *   POTRF  right-looking, block size nb (256 ... 1024 by precision and n, chol_default_nb): per step
- *            [panel stream, high priority]  potf2 of the diagonal block in shared memory ->
- *            in-shared-memory inverse of it -> panel solve as ONE tensor-core GEMM into a
- *            contiguous panel buffer W -> write-back -> look-ahead update of the next block column
- *            [update stream]                trailing-matrix HERK/SYRK  A22 -= W*W^H  on DMMA tiles
+ *            [panel stream, high priority]  diagonal block sub-block by sub-block: potf2 in registers -> the rows
+ *            below it by substitution (trsm_rows, rows spread over the SMs) -> rank-128 update; no inverse
+ *            [second high-priority stream]  panel solve into a contiguous buffer W, sub-block by sub-block
+ *            (full-height tensor-core GEMM + substitution), pipelined with the diagonal chain
+ *            [update stream]                trailing-matrix HERK/SYRK  A22 -= W*W^H  on tensor-core tiles, then the
+ *            write-back of W into the matrix; the next block column is updated first (look-ahead, split in
+ *            its diagonal block and the rows below)
  *          The panel chain of step j+1 overlaps the trailing update of step j (depth-1
  *          look-ahead); nothing runs on the CPU and nothing crosses PCIe.
  *          Upper is the same algorithm on W = U12^H, so the trailing update is the identical
@@ -20,8 +23,8 @@
  *   POTRS  (addition) two blocked TRSMs on the factor
  *   logdet one single-pass reduction kernel (lapack/dlogdet.c:37-74)
  * info is accumulated on the device (csrc/panel_kernels.cu) and read once at the end.
- * Variants behind environment switches (blocked panel solve, split look-ahead, TRTRI look-ahead) are
- * described where they are implemented and in DESIGN.md §4.1; they are off until measured on hardware.
+ * The stream schedule has A/B switches (CHOL_PANEL_PIPELINE, CHOL_LOOKAHEAD_SPLIT, CHOL_TRTRI_LOOKAHEAD, all on by
+ * default and measured on hardware, profiles/r02_*); cu*potrf also leaves log det A for cuLAPACKPotrfLogdet.
  */
 #include <complex.h>
 #include <stdlib.h>

@@ -13,7 +13,7 @@ g++ -shared -fsanitize=address -o $D/libcholesky_b200_mock.so $D/*.o -lpthread -
 gcc -std=c99 -O1 -g -fsanitize=address -fPIC -shared tests/mock/mock_nccl.c -o $D/libnccl.so.2 -lpthread
 ASAN=$(gcc -print-file-name=libasan.so)
 for g in ${@:-lapack blas multi1 multi3 dist3}; do
-  for sw in "" "CHOL_PANEL_BLOCKED=1 CHOL_LOOKAHEAD_SPLIT=1 CHOL_TRTRI_LOOKAHEAD=1"; do
+  for sw in "" "CHOL_PANEL_PIPELINE=0 CHOL_LOOKAHEAD_SPLIT=0 CHOL_TRTRI_LOOKAHEAD=0"; do
     echo "== $g ${sw:-(defaults)}"
     env $sw ASAN_OPTIONS=detect_leaks=0:halt_on_error=1 LD_PRELOAD=$ASAN LD_LIBRARY_PATH=$D OMP_NUM_THREADS=2 \
       python tests/mock/run_host_driver_checks.py $D/libcholesky_b200_mock.so $g 2>&1 | grep -E "AddressSanitizer|MOCK PASSED|FAILED|checks" | head -5

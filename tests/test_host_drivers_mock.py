@@ -54,15 +54,16 @@ def mock_runs(tmp_path_factory):
                OMP_NUM_THREADS="2")  # four groups run side by side: keep the oracle's OpenMP teams small
 
     def run(group):
-        # "<group>+<variant>+...": blocked = blocked panel solve, split = split POTRF look-ahead + TRTRI look-ahead (library switches, read once
-        # per process), jitter = every mock stream stalls at random before its operations (ordering races)
+        # "<group>+<variant>+...": nopipe = panel solve on the panel stream instead of pipelined on the second one, nosplit = POTRF
+        # look-ahead in one piece and no TRTRI look-ahead (the library's A/B switches, read once per process; the defaults
+        # are pipelined / split), jitter = every mock stream stalls at random before its operations (ordering races)
         name, *variants = group.split("+")
         e = dict(env)
-        if "blocked" in variants:
-            e["CHOL_PANEL_BLOCKED"] = "1"
-        if "split" in variants:
-            e["CHOL_LOOKAHEAD_SPLIT"] = "1"
-            e["CHOL_TRTRI_LOOKAHEAD"] = "1"
+        if "nopipe" in variants:
+            e["CHOL_PANEL_PIPELINE"] = "0"
+        if "nosplit" in variants:
+            e["CHOL_LOOKAHEAD_SPLIT"] = "0"
+            e["CHOL_TRTRI_LOOKAHEAD"] = "0"
         if "jitter" in variants:
             e["MOCK_CUDA_JITTER"] = "1"
         p = subprocess.run([sys.executable, os.path.join(MOCK, "run_host_driver_checks.py"), lib, name], stdout=subprocess.PIPE,
@@ -77,8 +78,8 @@ def mock_runs(tmp_path_factory):
                            timeout=600)
         return p.returncode, p.stdout.decode()
 
-    groups = ("lapack", "blas", "multi1", "multi3", "lapack+blocked", "multi3+blocked", "lapack+jitter", "multi3+jitter",
-              "lapack+split+jitter", "multi3+split+blocked+jitter", "dist3+jitter")
+    groups = ("lapack", "blas", "multi1", "multi3", "lapack+nopipe", "multi3+nopipe", "lapack+jitter", "multi3+jitter",
+              "lapack+nosplit+jitter", "multi3+nosplit+nopipe+jitter", "dist3+jitter")
     with ThreadPoolExecutor(max_workers=len(groups)) as ex:
         res = dict(zip(groups, ex.map(run, groups)))
     cdir = os.path.join(ROOT, "tests", "c")
@@ -89,9 +90,9 @@ def mock_runs(tmp_path_factory):
 
 
 @pytest.mark.parametrize("group,min_checks", [("lapack", 700), ("blas", 90), ("multi1", 800), ("multi3", 800),
-                                              ("lapack+blocked", 700), ("multi3+blocked", 800),
+                                              ("lapack+nopipe", 700), ("multi3+nopipe", 800),
                                               ("lapack+jitter", 700), ("multi3+jitter", 800),
-                                              ("lapack+split+jitter", 700), ("multi3+split+blocked+jitter", 800),
+                                              ("lapack+nosplit+jitter", 700), ("multi3+nosplit+nopipe+jitter", 800),
                                               ("dist3+jitter", 20)])
 def test_host_drivers_on_mock_backend(mock_runs, group, min_checks):
     rc, out = mock_runs[group]
