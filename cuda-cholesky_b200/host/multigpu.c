@@ -1055,7 +1055,7 @@ static CUresult rank_potrf_task(const void *argp) {
 
   if (a->uplo == 'L' && pinned && h2d_overlap_enabled() && nlocb >= 2) {
     /* ---- upload, factorisation and download all overlap ---- */
-    enum { MAXG = 8 };
+    enum { MAXG = 16 }; /* upload groups: the factorisation starts when the first one (1/16 of the rank's block columns) has arrived */
     CUevent up_ev[MAXG] = {0};
     dist_stage sg;
     dist_gather ga;
