@@ -159,6 +159,26 @@ assert bench.combine_info(0) == 0
 # 4. max-over-ranks timing reduction
 t = bench.max_over_ranks(1.0 + rank)
 assert t == float(P)
+# 5. the leading-block parity check of bench.py: every rank holds its block-cyclic columns of a factor (here numpy's),
+#    rank 0 assembles the leading block and compares it with the CPU reference's dpotrf; a corrupted shard must show
+n, nb = 600, 128
+rng = np.random.default_rng(5)
+Bm = rng.random((n, 64)) - 0.5
+A0 = Bm @ Bm.T + n * np.eye(n)
+L = np.linalg.cholesky(A0)
+cols = bench.owned_columns(n, nb, rank, P)
+fac = torch.from_numpy(np.ascontiguousarray(L[:, cols].T))     # (nloc, n) row-major == column-major n x nloc
+inp = torch.from_numpy(np.ascontiguousarray(A0[:, cols].T))
+res = bench.lead_block_parity(fac, inp, cols, n, P, rank)
+if rank == 0:
+    assert res[0] <= 64 * n * 2.3e-16 and res[0] <= res[1], res
+else:
+    assert res is None
+if rank == 1:
+    fac[0, 300] += 1e-6  # one entry of the lower triangle (column 128 of the matrix, row 300)
+res = bench.lead_block_parity(fac, inp, cols, n, P, rank)
+if rank == 0:
+    assert res[0] > res[1], res
 dist.barrier()
 dist.destroy_process_group()
 print("OK", rank)
