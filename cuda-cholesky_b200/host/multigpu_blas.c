@@ -11,9 +11,9 @@
  * routine on resident data and downloads its slab: PCIe traffic is the minimum (each operand
  * element crosses once per GPU that needs it) and no host BLAS is involved (the reference computes
  * diagonal blocks on the CPU, dsyrk.c:287-288, dtrsm.c:267-389).
- * TRTRI/LAUUM/POTRI on host pointers run staged on the first GPU of the CUmultiGPU by default; the
- * slab-distributed form further down is selected with CHOL_MGPU_INVERSE=slab until it
- * has been timed on hardware.
+ * TRTRI/LAUUM/POTRI on host pointers: with one GPU staged on it; with more, the distributed block-cyclic sweeps of
+ * host/multigpu.c.  An exchange-free split by output slab is kept further down
+ * (CHOL_MGPU_INVERSE=slab; PCIe-bound: 2 B200, N = 32768: 0.91-0.99 s against 0.63 s distributed).
  */
 #define _GNU_SOURCE
 #include <complex.h>
@@ -200,8 +200,8 @@ static CUresult mb_run(CUmultiGPU m, mb_args *proto) {
 }
 
 /* =============================================================================================
- * Slab-distributed TRTRI / LAUUM / POTRI on host pointers (CHOL_MGPU_INVERSE=slab; the default
- * still stages the whole matrix on the first GPU until this path has been verified on hardware).
+ * Slab-distributed TRTRI / LAUUM / POTRI on host pointers (CHOL_MGPU_INVERSE=slab; verified on 2 B200,
+ * profiles/r02_call8_2gpu_summary.txt; the default with more than one GPU is the distributed form).
  *
  * Both operations split by output slab with no GPU-to-GPU exchange:
  *   TRTRI lower: columns J = [lo,hi) of inv(L) depend on T = L[lo:n, lo:n] only:
