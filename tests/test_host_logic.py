@@ -291,3 +291,39 @@ def test_slab_inverse_decomposition_model(uplo, n, nslabs):
     want = T.T @ T if uplo == "L" else T @ T.T
     assert np.abs(_tri(out, uplo) - _tri(want, uplo)).max() <= 1e-10 * np.abs(want).max()
     assert np.array_equal(strict(out), strict(St))
+
+
+def test_default_block_sizes_are_consistent():
+    """chol_default_nb (host/lapack.c, through cholDistBlockSize without a handle): every default is a multiple of the
+    diagonal-block size of its precision (128; z 64) and of the 64-column tile, does not decrease with n, and keeps
+    the pipelined panel solve within its event ring (nb / db <= 16)."""
+    lib = chol.lib()
+    f = lib.cholDistBlockSize
+    f.restype = C.c_size_t
+    lib.chol_diag_max.restype = C.c_int
+    for p in "sdcz":
+        db = lib.chol_diag_max(C.c_int(ord(p)))
+        last = 0
+        for n in (1, 100, 1000, 4096, 6144, 8192, 12288, 16384, 24576, 32768, 49152, 65536, 131072):
+            nb = int(f(None, C.c_int(ord(p)), C.c_size_t(n)))
+            assert nb % db == 0 and nb % 64 == 0 and 128 <= nb <= 1024, (p, n, nb)
+            assert nb // db <= 16
+            assert nb >= last, (p, n, nb, last)
+            last = nb
+
+
+def test_bench_reference_arm_runs_on_cpu(tmp_path):
+    """`bench.py --impl reference` (the arm the driver runs next to ours): one JSON line with the contract's keys, the
+    reference's CPU dpotrf timed on a bounded sample, e2e repeating the value with zero transfer bytes."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--order", "1024"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600, check=True).stdout.decode()
+    line = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["unit"] == "GFLOP/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["config"]["sample_resid"] < 1e-13 and "sample_N" in line["config"]
+    # a rank other than 0 under torchrun prints nothing and exits 0
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                       env=dict(os.environ, RANK="1", WORLD_SIZE="2"), stdout=subprocess.PIPE, timeout=120)
+    assert p.returncode == 0 and p.stdout.decode().strip() == ""
