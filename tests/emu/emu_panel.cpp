@@ -360,6 +360,24 @@ static void case_copy_fill_logdet(const char *name) {
   }
 }
 
+// scatter_rows: a rank's packed piece of a row block to its block-cyclic rows (distributed LAUUM)
+template <typename T>
+static void case_scatter_rows(const char *name) {
+  using H = typename Host<T>::type;
+  const int m = 300, n = 37, lda = 301, cnb = 128, cp = 3, coff = 2;
+  const int rows_out = ((m - 1) / cnb * cp + coff) * cnb + (m - 1) % cnb + 1, ldb = rows_out + 2;
+  std::vector<H> A((size_t)lda * n), B((size_t)ldb * n, H(9)), W = B;
+  for (size_t k = 0; k < A.size(); ++k) A[k] = H((double)(k % 1013) + 0.25);
+  emu::launch(dim3((m + 31) / 32, (n + 31) / 32), dim3(256), 0, [&] {
+    scatter_rows_kernel<T>(m, n, reinterpret_cast<const T *>(A.data()), lda, reinterpret_cast<T *>(B.data()), ldb, cnb, cp, coff);
+  });
+  for (int c = 0; c < n; ++c)
+    for (int r = 0; r < m; ++r) W[(size_t)c * ldb + ((r / cnb) * cp + coff) * cnb + r % cnb] = A[(size_t)c * lda + r];
+  char what[120];
+  std::snprintf(what, sizeof what, "%s scatter_rows to block-cyclic rows (everything else untouched)", name);
+  check(B == W, what, 0);
+}
+
 int main() {
   std::setvbuf(stdout, nullptr, _IOLBF, 0);
   case_potf2<double, 128>("d", 128, 1e-12);
@@ -391,6 +409,9 @@ int main() {
   case_unfused<double, 128>("d", 70, 1e-12);
   case_unfused<double2, 64>("z", 50, 1e-12);
   case_unfused<float, 128>("s", 90, 2e-4);
+  case_scatter_rows<double>("d");
+  case_scatter_rows<double2>("z");
+  case_scatter_rows<float>("s");
   case_copy_fill_logdet<double>("d");
   case_copy_fill_logdet<double2>("z");
   case_copy_fill_logdet<float>("s");

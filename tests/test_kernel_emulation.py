@@ -63,6 +63,7 @@ def test_panel_kernels_emulated(emu):
     assert out.count("info, factor vs loops, other triangle untouched") >= 20  # potf2: d, z, s, c x lower/upper x full and ragged blocks
     assert out.count("not PD") >= 12
     assert out.count("trsm_rows<") >= 100  # both shapes x d, z, s, c x storage x transposed operands x in / out of place
+    assert out.count("scatter_rows to block-cyclic rows") == 3
 
 
 def test_small_gemm_kernel_emulated(emu):
