@@ -120,6 +120,19 @@ int chol_fill_launch(int prec, int uplo, size_t m, size_t n, double re, double i
 int chol_logdet_launch(int prec, const void *x, size_t incx, size_t n, void *dresult, void *dscratch, void *stream);
 size_t chol_logdet_scratch_bytes(void);
 
+/* ---- device dSFMT-19937 (csrc/rng_dsfmt.cu, host/rng.c).  A state is 192 128-bit words (191 + the lung). ----
+ * jump: states[g] (g < nseg, 3072 bytes each) = XOR over the set bits i < D of polys[g] (poly_u32 32-bit words per row)
+ * of K[i] (the seed's first D states): the state after any number of refills as a GF(2) combination. */
+int chol_dsfmt_jump_launch(const void *K, const void *polys, int poly_u32, int D, void *states, int nseg, void *stream);
+/* generate: one warp per segment g, from states[g] = the state before refill refill0 + g * seg_refills, produces that
+ * segment's refills (refill r = stream words 191 r .. 191 r + 190) and stores the words inside [w_begin, w_end):
+ * word t -> elements 2 (t - w_begin), +1 of out (element index < n_out), converted per kind (0 raw 64-bit, 1 [0,1),
+ * 2 (0,1], 3 (0,1), 4 the reference's getCloseClose).  snap != NULL (nseg = 1): the raw state after refill r goes to
+ * snap[(r + 1) * 192 words] instead (the Krylov block), nothing to out. */
+int chol_dsfmt_generate_launch(const void *states, unsigned long long refill0, unsigned seg_refills, int nseg,
+                               unsigned long long w_begin, unsigned long long w_end, void *out, unsigned long long n_out,
+                               int kind, void *snap, void *stream);
+
 /* number of kernels launched by the library so far (optionally resetting the counter) */
 unsigned long long chol_launch_count(int reset);
 

@@ -78,3 +78,44 @@ void oracle_dsfmt_fill_close_open(oracle_dsfmt_t *g, double *out, size_t n) {
     if (i < n) out[i++] = d[1] - 1.0;
   }
 }
+
+/* The reference's five output forms (rng/dsfmt.c), as raw 64-bit patterns so that they can be compared exactly:
+ *   kind 0  the 64-bit halves themselves (`get`, rng/dsfmt.c:127-146 - there the last pair of an even request is
+ *           lost to a `while (n > 2)`; the restatement hands out all n)
+ *   kind 1  getCloseOpen  :231  d - 1.0
+ *   kind 2  getOpenClose  :196  2.0 - d
+ *   kind 3  getOpenOpen   :160-161  (bits | 1) - 1.0
+ *   kind 4  getCloseClose :266  (double)(bits >> 10) * (1.0 / 9007199254740991.0)   (shift by 10 as written there)
+ * Pairs come from one 128-bit word; an odd tail uses the low half and discards the high half. */
+static uint64_t ds_convert(uint64_t w, int kind) {
+  double d, r;
+  memcpy(&d, &w, sizeof d);
+  switch (kind) {
+    case 0: return w;
+    case 1: r = d - 1.0; break;
+    case 2: r = 2.0 - d; break;
+    case 3: {
+      uint64_t v = w | 1u;
+      memcpy(&d, &v, sizeof d);
+      r = d - 1.0;
+      break;
+    }
+    default: {
+      volatile double p = (double)(w >> 10) * (1.0 / 9007199254740991.0);
+      r = p;
+    }
+  }
+  uint64_t o;
+  memcpy(&o, &r, sizeof o);
+  return o;
+}
+
+void oracle_dsfmt_fill(oracle_dsfmt_t *g, uint64_t *out, size_t n, int kind) {
+  size_t i = 0;
+  while (i < n) {
+    if (g->idx >= DS_N) ds_refill(g);
+    const uint64_t *wrd = g->s[g->idx++];
+    out[i++] = ds_convert(wrd[0], kind);
+    if (i < n) out[i++] = ds_convert(wrd[1], kind);
+  }
+}

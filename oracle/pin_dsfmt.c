@@ -5,6 +5,11 @@
  * SURVEY.md §2.5) and prints the first N doubles of getCloseOpen for a seed, so that
  * oracle/dsfmt_oracle.c can be pinned to the reference's generator bit for bit.
  *   gcc -O2 -msse2 -I/root/reference/rng oracle/pin_dsfmt.c -o oracle/_ref/pin_dsfmt
+ *   pin_dsfmt SEED N [KIND [SKIP]]   KIND 1 getCloseOpen (default, printed as %.17g), 2 getOpenClose, 3 getOpenOpen,
+ *                                    4 getCloseClose, 0 get - kinds 0, 2, 3, 4 are printed as 16 hex digits (the
+ *                                    bit patterns); SKIP values are drawn with the same call first and thrown away.
+ * The reference's `get` (rng/dsfmt.c:127-146) indexes its result wrongly after the loop and loses the last pair;
+ * for kind 0 only the values its loop stored, 2 * ((N - 1) / 2) of them, are printed.
  */
 #include <stddef.h>
 #include <stdint.h>
@@ -25,11 +30,26 @@ typedef struct {
 int main(int argc, char **argv) {
   uint64_t seed = argc > 1 ? strtoull(argv[1], NULL, 10) : 20121018u;
   size_t n = argc > 2 ? strtoull(argv[2], NULL, 10) : 16;
+  int kind = argc > 3 ? atoi(argv[3]) : 1;
+  size_t skip = argc > 4 ? strtoull(argv[4], NULL, 10) : 0;
   void *st = malloc(type.size);
-  double *out = malloc(n * sizeof(double));
-  vectord v = {n, 1, out};
+  double *out = calloc((n > skip ? n : skip) + 2, sizeof(double));
   type.set(seed, st);
-  type.getCloseOpen(&v, st);
-  for (size_t i = 0; i < n; i++) printf("%.17g\n", out[i]);
+  for (int pass = skip ? 0 : 1; pass < 2; pass++) {
+    vectord v = {pass ? n : skip, 1, out};
+    switch (kind) {
+      case 0: type.get((uint64_t *)out, v.n, st); break;
+      case 1: type.getCloseOpen(&v, st); break;
+      case 2: type.getOpenClose(&v, st); break;
+      case 3: type.getOpenOpen(&v, st); break;
+      default: type.getCloseClose(&v, st); break;
+    }
+  }
+  if (kind == 1) {
+    for (size_t i = 0; i < n; i++) printf("%.17g\n", out[i]);
+  } else {
+    const size_t m = kind == 0 ? 2 * ((n - 1) / 2) : n;
+    for (size_t i = 0; i < m; i++) printf("%016llx\n", (unsigned long long)((uint64_t *)out)[i]);
+  }
   return 0;
 }

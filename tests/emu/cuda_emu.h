@@ -110,12 +110,22 @@ inline T __shfl_sync(unsigned, T v, int src) {
 }
 template <typename T>
 inline T __shfl_xor_sync(unsigned m, T v, int lanemask) { return __shfl_sync(m, v, (int)((threadIdx.x & 31) ^ lanemask)); }
+// lanes below `delta` get their own value back, as on the device
+template <typename T>
+inline T __shfl_up_sync(unsigned m, T v, unsigned delta) {
+  const int lane = (int)(threadIdx.x & 31);
+  return __shfl_sync(m, v, lane >= (int)delta ? lane - (int)delta : lane);
+}
 
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
 inline float rsqrt(float x) { return 1.0f / std::sqrt(x); }
 
 template <typename T> inline T atomicAdd(T *p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+template <typename T> inline T atomicXor(T *p, T v) { return __atomic_fetch_xor(p, v, __ATOMIC_SEQ_CST); }
+inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
+inline long long __double_as_longlong(double d) { long long v; std::memcpy(&v, &d, 8); return v; }
+inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 inline int atomicMin(int *p, int v) { int o = __atomic_load_n(p, __ATOMIC_SEQ_CST); while (v < o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {} return o; }
 inline int atomicMax(int *p, int v) { int o = __atomic_load_n(p, __ATOMIC_SEQ_CST); while (v > o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {} return o; }
 using ::fma;

@@ -38,10 +38,33 @@ def latmc_golden():
     np.savez_compressed(os.path.join(HERE, "latmc.npz"), **d)
 
 
+def dsfmt_kinds_golden(exe=None):
+    """1b. every output form of the reference's dSFMT-19937 (get, getOpenClose, getOpenOpen, getCloseClose; getCloseOpen again)
+    as bit patterns, from the start of the stream and after an odd-sized first call (which drops half a word)."""
+    if exe is None:
+        exe = os.path.join(H.ORACLE_DIR, "_ref", "pin_dsfmt")
+        subprocess.check_call(["gcc", "-O2", "-msse2", "-w", "-I/root/reference/rng", os.path.join(H.ORACLE_DIR, "pin_dsfmt.c"), "-o", exe])
+    d = {"seed": H.SEED, "source": "reference rng/dsfmt_19937.c: get / getCloseOpen / getOpenClose / getOpenOpen / getCloseClose",
+         "n": 1001, "skip": 7, "kinds": {}}
+    for name, kind in H.DSFMT_KINDS.items():
+        if kind == 1:
+            first = [np.float64(x).view(np.uint64).item() for x in map(float, subprocess.check_output([exe, str(H.SEED), "1001", "1"]).decode().split())]
+            after = [np.float64(x).view(np.uint64).item() for x in map(float, subprocess.check_output([exe, str(H.SEED), "1001", "1", "7"]).decode().split())]
+        else:
+            first = [int(x, 16) for x in subprocess.check_output([exe, str(H.SEED), "1001", str(kind)]).decode().split()]
+            after = [int(x, 16) for x in subprocess.check_output([exe, str(H.SEED), "1001", str(kind), "7"]).decode().split()]
+        d["kinds"][name] = {"first": ["%016x" % v for v in first], "after_skip": ["%016x" % v for v in after]}
+    with open(os.path.join(HERE, "dsfmt19937_kinds.json"), "w") as f:
+        json.dump(d, f)
+
+
 def main():
     subprocess.check_call(["make", "-C", H.ORACLE_DIR, "ref", "oracle"])
     if "--only-latmc" in sys.argv:
         latmc_golden()
+        return
+    if "--only-dsfmt-kinds" in sys.argv:
+        dsfmt_kinds_golden()
         return
     # 1. dSFMT-19937: compile the reference's rng/dsfmt_19937.c behind oracle/pin_dsfmt.c
     exe = os.path.join(H.ORACLE_DIR, "_ref", "pin_dsfmt")
@@ -51,6 +74,7 @@ def main():
     with open(os.path.join(HERE, "dsfmt19937_seed20121018.json"), "w") as f:
         json.dump({"seed": H.SEED, "source": "reference rng/dsfmt_19937.c getCloseOpen",
                    "close_open": [float(x) for x in out]}, f)
+    dsfmt_kinds_golden(exe)
     # 2. potrf factors of the seeded SPD inputs, from the reference's CPU {s,d,c,z}potrf
     REF = H.CpuLib("ref")
     for p in "sdcz":

@@ -175,6 +175,26 @@ def dsfmt_uniform(seed, n):
     return out
 
 
+DSFMT_KINDS = {"raw": 0, "close_open": 1, "open_close": 2, "open_open": 3, "close_close": 4}
+
+
+class OracleDsfmt:
+    """The oracle's sequential dSFMT-19937 (oracle/dsfmt_oracle.c) as a stateful generator: fill(n, kind) continues the
+    stream like successive calls of the reference's rng64Get* do (an odd n drops the high half of its last word)."""
+
+    def __init__(self, seed):
+        self.lib = oracle()
+        self.lib.oracle_dsfmt_state_size.restype = C.c_size_t
+        self.st = C.create_string_buffer(self.lib.oracle_dsfmt_state_size())
+        self.lib.oracle_dsfmt_seed(self.st, C.c_uint64(seed))
+
+    def fill(self, n, kind="close_open"):
+        """n values as raw 64-bit patterns (np.uint64); .view(np.float64) gives the doubles"""
+        out = np.empty(n, dtype=np.uint64)
+        self.lib.oracle_dsfmt_fill(self.st, _ptr(out), C.c_size_t(n), C.c_int(DSFMT_KINDS[kind]))
+        return out
+
+
 def fmat(m, n, dtype, ld=None):
     """Column-major m x n array with leading dimension ld (>= m)."""
     ld = ld or max(m, 1)

@@ -27,13 +27,19 @@ INC = ["-I" + EMU, "-I/usr/local/cuda/include", "-I" + os.path.join(ROOT, "cuda-
        "-I" + os.path.join(ROOT, "include")]
 
 
-HARNESSES = {"emu_panel.cpp": 900, "emu_small_gemm.cpp": 600, "emu_ffma.cpp": 1200, "emu_dmma.cpp": 1500}
+HARNESSES = {"emu_panel.cpp": 900, "emu_small_gemm.cpp": 600, "emu_ffma.cpp": 1200, "emu_dmma.cpp": 1500, "emu_rng.cpp": 600}
+# plain-C sources a harness links (compiled as C): the product's polynomial code and the oracle's sequential generator
+EXTRA_C = {"emu_rng.cpp": [os.path.join(ROOT, "cuda-cholesky_b200", "host", "rng_poly.c"), os.path.join(ROOT, "oracle", "dsfmt_oracle.c")]}
 
 
 def _build_and_run(src, tmpdir, timeout):
     exe = os.path.join(tmpdir, os.path.splitext(src)[0])
     try:
-        subprocess.check_call(["g++", "-std=c++17", "-O1", *INC, os.path.join(EMU, src), "-o", exe, "-lpthread"])
+        objs = []
+        for c in EXTRA_C.get(src, ()):
+            objs.append(os.path.join(tmpdir, os.path.basename(c)[:-2] + ".o"))
+            subprocess.check_call(["gcc", "-std=c99", "-O2", "-D_POSIX_C_SOURCE=200809L", "-c", c, "-o", objs[-1]])
+        subprocess.check_call(["g++", "-std=c++17", "-O1", *INC, os.path.join(EMU, src), *objs, "-o", exe, "-lpthread"])
         p = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=timeout,
                            env=dict(os.environ, EMU_WATCHDOG=str(timeout - 60)))
         return p.returncode, p.stdout.decode()
@@ -43,7 +49,7 @@ def _build_and_run(src, tmpdir, timeout):
 
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
-    """all four harnesses are built and run side by side (they mostly sleep in barriers)"""
+    """all harnesses are built and run side by side (they mostly sleep in barriers)"""
     if not os.path.exists("/usr/local/cuda/include/cuda_runtime.h"):
         pytest.skip("CUDA headers not installed")
     tmpdir = str(tmp_path_factory.mktemp("emu"))
@@ -75,6 +81,15 @@ def test_fp32_gemm_engine_emulated(emu):
     skip, triangle-only / Hermitian output, ragged edges, aligned and unaligned operands (s and c)"""
     out = _passed(emu, "emu_ffma.cpp")
     assert "deep-k kernels: 86 cases so far, 0 mismatches" in out
+
+
+def test_device_dsfmt_kernels_emulated(emu):
+    """csrc/rng_dsfmt.cu: the warp-parallel refill (64 steps per round through one warp scan), windowed conversion and store in
+    all five output forms, Krylov snapshots, and the GF(2) jump kernel with the product's own polynomial rows - bit for bit
+    against the oracle's sequential generator"""
+    out = _passed(emu, "emu_rng.cpp")
+    assert "29 cases, 0 mismatches" in out
+    assert out.count("identical to the oracle") >= 6
 
 
 def test_fp64_tensor_core_engine_emulated(emu):
