@@ -265,6 +265,49 @@ def probe_fp64(kind, iters=20000):
 
 
 # ---------------------------------------------------------------------------------------------
+# device random numbers: CUrng64 (include/rng.h; reference include/rng.h:326-413)
+# ---------------------------------------------------------------------------------------------
+RNG_KINDS = {"raw": "cuRng64Get", "close_open": "cuRng64GetCloseOpen", "open_close": "cuRng64GetOpenClose",
+             "open_open": "cuRng64GetOpenOpen", "close_close": "cuRng64GetCloseClose"}
+
+
+class Rng64:
+    """CUrng64 of type cu_dsfmt_19937_t: dSFMT-19937 on the device, the same stream as the reference's CPU generator.
+    `x` is a device pointer (int) to n 8-byte values; calls are asynchronous on the generator's stream (default 0)."""
+
+    def __init__(self, seed=None):
+        self.h = C.c_void_p()
+        t = C.c_void_p.in_dll(lib(), "cu_dsfmt_19937_t")
+        _check("cuRng64Create", lib().cuRng64Create(C.byref(self.h), t))
+        if seed is not None:
+            self.set(seed)
+
+    def close(self):
+        if self.h:
+            _check("cuRng64Destroy", lib().cuRng64Destroy(self.h))
+            self.h = C.c_void_p()
+
+    def set(self, seed):
+        _check("cuRng64Set", lib().cuRng64Set(self.h, C.c_uint64(seed)))
+
+    def set_stream(self, stream):
+        _check("cuRng64SetStream", lib().cuRng64SetStream(self.h, C.c_void_p(stream)))
+
+    def get(self, x, n, kind="close_open", allow_invalid=False):
+        f = getattr(lib(), RNG_KINDS[kind])
+        return _check(f.__name__, f(self.h, C.c_void_p(x), C.c_size_t(n)), allow_invalid)
+
+    def discard(self, n):
+        _check("cuRng64Discard", lib().cuRng64Discard(self.h, C.c_size_t(n)))
+
+    @property
+    def position(self):
+        f = lib().cuRng64Position
+        f.restype = C.c_ulonglong
+        return int(f(self.h))
+
+
+# ---------------------------------------------------------------------------------------------
 # multi-GPU: the reference's host-pointer API (one process, one worker thread per GPU) ...
 # ---------------------------------------------------------------------------------------------
 class MultiGPU:

@@ -154,6 +154,7 @@ dsfmt_generate_kernel(const W128 *__restrict__ states, unsigned long long refill
     if (snap != nullptr) {
       W128 *dst = snap + (size_t)(r + 1) * DS_STATE_WORDS;
       for (int i = lane; i < DS_STATE_WORDS; i += 32) dst[i] = st[i];
+      __syncwarp();  // the next refill overwrites st
       continue;
     }
     if (t0 + DS_N <= w_begin) continue;  // before the window: the state only moves on

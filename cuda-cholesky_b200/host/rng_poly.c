@@ -7,10 +7,10 @@
  * Nothing here is on the data path: the refill below runs only to find / verify p (once per process and, as a
  * check, once per seed); every output value is produced by the device kernels.
  *
- * p does not depend on the seed for all but a vanishing set of states, so it is kept per process; every new seed is
- * checked against it exactly (p(T) s0 must be the zero state) and p is extended by the missing factor if it is not.
- * deg p = 19991 for the states seen so far: 19937 (the Mersenne exponent) plus the 54 dimensions the generator's
- * fixed point adds.
+ * p is kept per process.  Every seed is checked against it exactly (p(T) s0 must be the zero state) and p is multiplied
+ * by the missing factor if it is not - this happens: the state of seed 20121018 has a minimal polynomial of degree 19991,
+ * that of seed 12345 one of degree 19993 = 191 * 104 + 128 + 1, the dimension bound (the top 12 bits of the 382 doubles
+ * never change), which then serves both.  `generation` tells the callers that p changed (their Krylov blocks are stale).
  */
 #include <pthread.h>
 #include <stdint.h>

@@ -20,8 +20,9 @@
  * n1 values followed by n2 values equal n1 + n2 values in one call only when n1 is even.
  * The four floating-point conversions are the reference's arithmetic (rng/dsfmt.c:148-285) literally - including
  * getCloseClose's shift by 10 (its comment says 12), which makes that one return values in [0.4995, 0.5].
- * cuRng64Get returns the raw 64-bit halves (bit patterns of doubles in [1, 2)), all n of them (the reference's CPU
- * `get` stops one pair short for even n, rng/dsfmt.c:127-146; that slip is not reproduced).
+ * cuRng64Get returns the raw 64-bit halves (bit patterns of doubles in [1, 2)), all n of them in order (the reference's
+ * CPU `get`, rng/dsfmt.c:127-146, stores whole words while more than two values remain and then writes the low half of
+ * one more word to the wrong index; that slip is not reproduced - the values it does store in place are the same).
  *
  * Calls are asynchronous on the generator's stream (default: the legacy default stream 0); a generator is not
  * thread-safe; different generators may be used from different threads.

@@ -208,6 +208,13 @@ CUresult cuStreamWaitEvent(CUstream s, CUevent e, unsigned int f) {
   mock_stream_enqueue(s, op_wait, o);
   return CUDA_SUCCESS;
 }
+CUresult cuEventSynchronize(CUevent e) {
+  pthread_mutex_lock(&e->mu);
+  const unsigned long long target = e->recorded;
+  while (e->completed < target) pthread_cond_wait(&e->cv, &e->mu);
+  pthread_mutex_unlock(&e->mu);
+  return CUDA_SUCCESS;
+}
 CUresult cuEventElapsedTime(float *ms, CUevent a, CUevent b) { (void)a; (void)b; *ms = 1.0f; return CUDA_SUCCESS; }
 
 /* ---- memory: "device" = host.  MOCK_CUDA_MEM_LIMIT (bytes) makes larger device allocations fail. ---- */
@@ -298,6 +305,34 @@ CUresult cuMemsetD8Async(CUdeviceptr d, unsigned char v, size_t n, CUstream s) {
   struct memop *o = calloc(1, sizeof *o);
   o->kind = 0; o->dst = (void *)(uintptr_t)d; o->v = v; o->n = n;
   mock_stream_enqueue(s, op_mem, o);
+  return CUDA_SUCCESS;
+}
+/* host -> device, asynchronous.  From page-locked memory the source is read when the copy EXECUTES (overwriting the
+ * buffer before then corrupts the copy, as on the device); from pageable memory the driver stages the data before it
+ * returns, so the source is snapshotted now. */
+static void op_h2d_staged(void *p) {
+  struct memop *o = p;
+  memcpy(o->dst, o->src, o->n);
+  free((void *)o->src);
+  free(o);
+}
+CUresult cuMemcpyHtoDAsync(CUdeviceptr d, const void *h, size_t n, CUstream s) {
+  struct memop *o = calloc(1, sizeof *o);
+  o->dst = (void *)(uintptr_t)d; o->n = n;
+  int is_pinned = 0;
+  pthread_mutex_lock(&reg_lock);
+  for (int i = 0; i < 256; i++)
+    if (pinned[i].p && (const char *)h >= (const char *)pinned[i].p && (const char *)h < (const char *)pinned[i].p + pinned[i].n) is_pinned = 1;
+  pthread_mutex_unlock(&reg_lock);
+  if (is_pinned) {
+    o->kind = 1; o->src = h;
+    mock_stream_enqueue(s, op_mem, o);
+  } else {
+    void *copy = malloc(n ? n : 1);
+    memcpy(copy, h, n);
+    o->src = copy;
+    mock_stream_enqueue(s, op_h2d_staged, o);
+  }
   return CUDA_SUCCESS;
 }
 CUresult cuMemcpyDtoHAsync(void *h, CUdeviceptr d, size_t n, CUstream s) {

@@ -442,4 +442,74 @@ int chol_logdet_launch(int prec, const void *x, size_t incx, size_t n, void *dre
     if (prec == 's' || prec == 'c') *(float *)dresult = (float)(2.0 * s); else *(double *)dresult = 2.0 * s;
   });
 }
+
+// ---- device dSFMT-19937 launchers (csrc/chol_kernels.h) as plain loops written from their documented semantics ----
+// a state = 192 words of 128 bits (two uint64_t each), word 191 = the lung; one refill = the 191 steps of the generator
+static void mock_refill(uint64_t (*st)[2]) {
+  uint64_t l0 = st[191][0], l1 = st[191][1];
+  for (int i = 0; i < 191; ++i) {
+    const uint64_t *b = st[(i + 117) % 191];
+    const uint64_t t0 = st[i][0], t1 = st[i][1];
+    const uint64_t n0 = (t0 << 19) ^ (l1 >> 32) ^ (l1 << 32) ^ b[0], n1 = (t1 << 19) ^ (l0 >> 32) ^ (l0 << 32) ^ b[1];
+    l0 = n0; l1 = n1;
+    st[i][0] = (l0 >> 12) ^ (l0 & 0x000ffafffffffb3fULL) ^ t0;
+    st[i][1] = (l1 >> 12) ^ (l1 & 0x000ffdfffc90fffdULL) ^ t1;
+  }
+  st[191][0] = l0; st[191][1] = l1;
+}
+static uint64_t mock_convert(uint64_t w, int kind) {
+  double d, r;
+  std::memcpy(&d, &w, 8);
+  if (kind == 0) return w;
+  if (kind == 1) r = d - 1.0;
+  else if (kind == 2) r = 2.0 - d;
+  else if (kind == 3) { const uint64_t v = w | 1u; std::memcpy(&d, &v, 8); r = d - 1.0; }
+  else { volatile double p = (double)(w >> 10) * (1.0 / 9007199254740991.0); r = p; }
+  uint64_t o;
+  std::memcpy(&o, &r, 8);
+  return o;
+}
+int chol_dsfmt_jump_launch(const void *K, const void *polys, int poly_u32, int D, void *states, int nseg, void *st) {
+  __sync_fetch_and_add(&launches, 1);
+  if (nseg <= 0 || D <= 0 || poly_u32 * 32 < D) return 1;
+  return enqueue(st, [=] {
+    const uint32_t *k = (const uint32_t *)K, *p = (const uint32_t *)polys;
+    uint32_t *out = (uint32_t *)states;
+    for (int g = 0; g < nseg; ++g) {
+      uint32_t acc[768] = {0};
+      for (int i = 0; i < D; ++i)
+        if ((p[(size_t)g * poly_u32 + i / 32] >> (i % 32)) & 1u)
+          for (int w = 0; w < 768; ++w) acc[w] ^= k[(size_t)i * 768 + w];
+      std::memcpy(out + (size_t)g * 768, acc, sizeof acc);
+    }
+  });
+}
+int chol_dsfmt_generate_launch(const void *states, unsigned long long refill0, unsigned seg_refills, int nseg, unsigned long long w_begin,
+                               unsigned long long w_end, void *out, unsigned long long n_out, int kind, void *snap, void *st) {
+  __sync_fetch_and_add(&launches, 1);
+  if (nseg <= 0 || seg_refills == 0 || kind < 0 || kind > 4 || (snap != nullptr && nseg != 1)) return 1;
+  return enqueue(st, [=] {
+    for (int g = 0; g < nseg; ++g) {
+      uint64_t cur[192][2];
+      std::memcpy(cur, (const char *)states + (size_t)g * sizeof cur, sizeof cur);
+      for (unsigned k = 0; k < seg_refills; ++k) {
+        const unsigned long long r = refill0 + (unsigned long long)g * seg_refills + k;
+        if (snap == nullptr && r * 191 >= w_end) break;
+        mock_refill(cur);
+        if (snap != nullptr) {
+          std::memcpy((char *)snap + (size_t)(r + 1) * sizeof cur, cur, sizeof cur);
+          continue;
+        }
+        for (int i = 0; i < 191; ++i) {
+          const unsigned long long t = r * 191 + i;
+          if (t < w_begin || t >= w_end) continue;
+          const unsigned long long e = 2 * (t - w_begin);
+          uint64_t *o = (uint64_t *)out;
+          if (e < n_out) o[e] = mock_convert(cur[i][0], kind);
+          if (e + 1 < n_out) o[e + 1] = mock_convert(cur[i][1], kind);
+        }
+      }
+    }
+  });
+}
 }

@@ -392,8 +392,127 @@ def dist_ranks(P):
             other_untouched(got, A0, "L", "cholDist P=%d" % P)
 
 
+def device_rng():
+    """cuRng64* (host/rng.c + host/rng_poly.c) against the oracle's sequential dSFMT-19937: segmenting on the absolute grid,
+    windows that start / end inside a refill, odd counts (half a word dropped), every output form, a stream that continues
+    over many calls, re-seeding, Discard, two generators with different seeds (the second one's state forces the process-wide
+    polynomial to be extended, after which the first must rebuild its jump table), a user stream, argument errors."""
+    allocs0 = mock.mock_cuda_live_allocs()
+    mock.mock_cuda_ctx_depth.restype = C.c_int
+    stream = C.c_void_p()
+    ok(mock.cuInit(0) == 0, "cuInit")
+    g = chol.Rng64()
+    depth0 = mock.mock_cuda_ctx_depth()
+    buf = np.zeros(1, dtype=np.uint64)
+    try:
+        g.get(ptr(buf), 1)
+        ok(False, "Get before Set must fail")
+    except chol.CholeskyError as e:
+        ok(e.code == 3, "Get before Set: CUDA_ERROR_NOT_INITIALIZED")
+    ok(mock.cuStreamCreate(C.byref(stream), 0) == 0, "stream")
+    seed = H.SEED
+    for use_stream in (False, True):
+        g.set_stream(stream.value if use_stream else 0)
+        for kind in H.DSFMT_KINDS:
+            g.set(seed)
+            ora = H.OracleDsfmt(seed)
+            # sizes chosen to cross refill (382 values) and segment (16 refills = 6112 values) boundaries, odd ones included
+            for n in (1, 2, 3, 381, 382, 383, 1000, 6111, 6113, 20001, 7, 150000, 2, 400001, 5):
+                out = np.full(n + 2, 0x5555555555555555, dtype=np.uint64)
+                g.get(ptr(out[1:]), n, kind)
+                mock.cuStreamSynchronize(stream if use_stream else None)
+                want = ora.fill(n, kind)
+                ok(np.array_equal(out[1:n + 1], want), "rng %s n=%d stream=%s: stream differs from the oracle" % (kind, n, use_stream))
+                ok(out[0] == 0x5555555555555555 and out[n + 1] == 0x5555555555555555, "rng %s n=%d: wrote outside the request" % (kind, n))
+            if kind == "close_open":
+                d = out[1:n + 1].view(np.float64)
+                ok(bool((d >= 0).all() and (d < 1).all()), "close_open range")
+    # a burst of requests on the user stream with no synchronisation in between: each one needs other polynomial rows, staged
+    # through the same page-locked buffer (the library must wait for the previous upload before it refills the buffer)
+    g.set_stream(stream.value)
+    g.set(seed)
+    ora = H.OracleDsfmt(seed)
+    sizes = (50000, 3, 250001, 40000, 777777, 12)
+    outs = [np.zeros(n, dtype=np.uint64) for n in sizes]
+    for o_, n in zip(outs, sizes):
+        g.get(ptr(o_), n, "open_close")
+    mock.cuStreamSynchronize(stream)
+    for o_, n in zip(outs, sizes):
+        ok(np.array_equal(o_, ora.fill(n, "open_close")), "burst of requests: n=%d" % n)
+    # Discard = a Get without the values; Position counts 128-bit words
+    g.set_stream(0)
+    g.set(seed)
+    ora = H.OracleDsfmt(seed)
+    g.discard(12345)
+    ora.fill(12345)
+    ok(g.position == 6173, "position after discarding 12345 values")
+    out = np.zeros(777, dtype=np.uint64)
+    g.get(ptr(out), 777)
+    ok(np.array_equal(out, ora.fill(777)), "rng after Discard")
+    # three generators fill the block columns r, r + 3, ... of one column-major matrix from ONE global stream
+    m_, n_, nb_, P_ = 640, 1100, 128, 3
+    want = H.OracleDsfmt(seed).fill(m_ * n_).reshape(n_, m_)
+    got = np.zeros((n_, m_), dtype=np.uint64)
+    for r in range(P_):
+        gr = chol.Rng64(seed)
+        pos = 0
+        for c0 in range(r * nb_, n_, P_ * nb_):
+            cols = min(nb_, n_ - c0)
+            gr.discard(c0 * m_ - pos)
+            gr.get(ptr(got[c0:]), cols * m_)
+            pos = (c0 + cols) * m_
+        ok(gr.position == pos // 2, "position of rank %d" % r)
+        gr.close()
+    ok(np.array_equal(got, want), "block-cyclic windows of one global stream")
+    # far ahead: a window 3e8 values into the stream (checkpointed polynomial walk), then back to the start with a new seed
+    g.set(seed)
+    far = 300_000_001
+    g.discard(far)
+    out = np.zeros(5000, dtype=np.uint64)
+    g.get(ptr(out), 5000)
+    ora = H.OracleDsfmt(seed)
+    left = far
+    while left > 0:  # the oracle has to walk there (an even chunk size keeps the word alignment; the odd total drops half a word)
+        step = min(left, 1 << 22)
+        ora.fill(step)
+        left -= step
+    ok(np.array_equal(out, ora.fill(5000)), "rng window 3e8 values into the stream")
+    # a second generator whose seed needs a larger polynomial than the first one's (seed 20121018: degree 19991, seed 12345:
+    # 19993): the first generator, in the middle of its stream, must notice, rebuild its jump table and carry on
+    g.set(seed)
+    ora = H.OracleDsfmt(seed)
+    out = np.zeros(10001, dtype=np.uint64)
+    g.get(ptr(out), 10001)
+    ok(np.array_equal(out, ora.fill(10001)), "first generator before the polynomial changes")
+    g2 = chol.Rng64(12345)
+    o2 = H.OracleDsfmt(12345)
+    out = np.zeros(30001, dtype=np.uint64)
+    g2.get(ptr(out), 30001)
+    ok(np.array_equal(out, o2.fill(30001)), "second generator (seed 12345)")
+    for n in (30001, 999):
+        out = np.zeros(n, dtype=np.uint64)
+        g.get(ptr(out), n)
+        ok(np.array_equal(out, ora.fill(n)), "first generator after the polynomial was extended, n=%d" % n)
+    g3 = chol.Rng64(seed)  # same seed, fresh object, interleaved with g
+    o3 = H.OracleDsfmt(seed)
+    out = np.zeros(4097, dtype=np.uint64)
+    g3.get(ptr(out), 4097, "open_open")
+    ok(np.array_equal(out, o3.fill(4097, "open_open")), "third generator")
+    # argument errors
+    ok(g.get(0, 4, allow_invalid=True) == 1, "NULL pointer")
+    ok(g.get(ptr(out) + 4, 4, allow_invalid=True) == 1, "misaligned pointer")
+    ok(g.get(ptr(out), 0) == 0, "n = 0")
+    ok(mock.mock_cuda_ctx_depth() == depth0, "context stack balanced")
+    for x in (g, g2, g3):
+        x.close()
+    mock.cuStreamDestroy_v2(stream)
+    ok(mock.mock_cuda_live_allocs() == allocs0, "device allocations balanced: %d vs %d" % (mock.mock_cuda_live_allocs(), allocs0))
+
+
 if __name__ == "__main__":
     which = sys.argv[2] if len(sys.argv) > 2 else "all"
+    if which in ("all", "rng"):
+        device_rng()
     if which in ("all", "lapack"):
         single_device_lapack()
     if which in ("all", "blas"):

@@ -20,7 +20,7 @@ ROOT = H.ROOT
 def test_library_loads_and_exports_every_declared_symbol():
     lib = chol.lib()
     decl = set()
-    for f in ("blas.h", "lapack.h", "cumultigpu.h", "error.h", "cholesky_b200.h"):
+    for f in ("blas.h", "lapack.h", "cumultigpu.h", "error.h", "cholesky_b200.h", "rng.h"):
         s = open(os.path.join(ROOT, "include", f)).read()
         s = re.sub(r"/\*.*?\*/", "", s, flags=re.S)
         s = re.sub(r"#define[^\n]*(\\\n[^\n]*)*", "", s)
@@ -29,7 +29,9 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert len(decl) >= 90
     for name in sorted(decl):
         assert hasattr(lib, name), name
-    for var in ("xerbla", "errorHandler"):
+    assert {"cuRng64Create", "cuRng64Destroy", "cuRng64Set", "cuRng64Get", "cuRng64GetOpenOpen", "cuRng64GetOpenClose",
+            "cuRng64GetCloseOpen", "cuRng64GetCloseClose"} <= decl  # reference include/rng.h:346-410
+    for var in ("xerbla", "errorHandler", "cu_dsfmt_19937_t"):
         C.c_void_p.in_dll(lib, var)
     # the product library has no CPU path: none of the reference's un-prefixed CPU names
     out = subprocess.check_output(["nm", "-D", "--defined-only", chol.LIB_PATH]).decode()
@@ -39,6 +41,70 @@ def test_library_loads_and_exports_every_declared_symbol():
     # ... and it does not link the oracle
     ldd = subprocess.check_output(["readelf", "-d", chol.LIB_PATH]).decode()
     assert "oracle" not in ldd
+
+
+def test_dsfmt_jump_polynomial_host_code():
+    """host/rng_poly.c without a GPU (the functions are exported by the product library): the seed state equals the oracle's,
+    the host refill equals the oracle's stream, the minimal polynomial annihilates the seed state (checked exactly inside
+    chol_dsfmt_poly_ensure), and x^r mod p applied to the first D states gives the state after r refills - the identity the
+    device jump kernel relies on.  Seed 20121018 has a polynomial of degree 19991; a second seed needs 19993, which must
+    extend the process-wide polynomial (generation changes) and still serve the first seed."""
+    import numpy as np
+    lib = chol.lib()
+    lib.chol_dsfmt_poly_reset()
+    W = 192
+    State = C.c_uint64 * (2 * W)
+
+    def seeded(seed):
+        st = State()
+        lib.chol_dsfmt_seed_state(C.c_uint64(seed), st)
+        return st
+
+    def words(st):
+        return np.frombuffer(st, dtype=np.uint64).copy()
+
+    s0 = seeded(H.SEED)
+    cur = State.from_buffer_copy(s0)
+    ora = H.OracleDsfmt(H.SEED)
+    for _ in range(3):  # one refill = 382 raw values = the first 191 words of the new state
+        lib.chol_dsfmt_refill_host(cur)
+        assert np.array_equal(words(cur)[:382], ora.fill(382, "raw"))
+    D, gen = C.c_int(0), C.c_uint(0)
+    assert lib.chol_dsfmt_poly_ensure(s0, C.byref(D), C.byref(gen)) == 0
+    assert D.value == 19991
+    gen0 = gen.value
+    # Krylov block and direct states
+    nk = D.value
+    K = np.empty((nk, 2 * W), dtype=np.uint64)
+    cur = State.from_buffer_copy(s0)
+    for i in range(nk):
+        K[i] = words(cur)
+        lib.chol_dsfmt_refill_host(cur)
+    pw32 = 2 * ((D.value + 63) // 64)
+    rows = (C.c_uint32 * (3 * pw32))()
+    level, j0 = 10, 18  # refills 18432, 19456, 20480: below and above D
+    assert lib.chol_dsfmt_poly_rows(C.c_uint(gen0), C.c_int(level), C.c_uint64(j0), C.c_size_t(3), rows, C.c_size_t(pw32)) == 0
+    r_have, state = nk, words(cur)  # `cur` is T^nk s0
+    a = np.frombuffer(rows, dtype=np.uint32).reshape(3, pw32)
+    for i in range(3):
+        r = (j0 + i) << level
+        bits = np.unpackbits(a[i].view(np.uint8), bitorder="little")[:nk].astype(bool)
+        combo = np.bitwise_xor.reduce(K[bits], axis=0)
+        if r < nk:
+            want = K[r]
+        else:
+            while r_have < r:
+                lib.chol_dsfmt_refill_host(cur)
+                r_have += 1
+            want = words(cur)
+        assert np.array_equal(combo, want), r
+    # stale generation is refused; a seed that needs a larger polynomial extends it
+    assert lib.chol_dsfmt_poly_rows(C.c_uint(gen0 + 1), C.c_int(level), C.c_uint64(0), C.c_size_t(1), rows, C.c_size_t(pw32)) != 0
+    s1 = seeded(12345)
+    assert lib.chol_dsfmt_poly_ensure(s1, C.byref(D), C.byref(gen)) == 0
+    assert D.value == 19993 and gen.value != gen0
+    assert lib.chol_dsfmt_poly_ensure(s0, C.byref(D), C.byref(gen)) == 0 and D.value == 19993  # the larger polynomial serves both
+    lib.chol_dsfmt_poly_reset()
 
 
 TASKFN = C.CFUNCTYPE(C.c_int, C.c_void_p)
