@@ -306,6 +306,21 @@ class Rng64:
         f.restype = C.c_ulonglong
         return int(f(self.h))
 
+    def set_segment_bias(self, bias):
+        _check("cuRng64SetSegmentBias", lib().cuRng64SetSegmentBias(self.h, C.c_int(bias)))
+
+    def set_pipeline_chunks(self, chunks):
+        _check("cuRng64SetPipelineChunks", lib().cuRng64SetPipelineChunks(self.h, C.c_int(chunks)))
+
+    def profile(self, enable=True):
+        _check("cuRng64Profile", lib().cuRng64Profile(self.h, C.c_int(1 if enable else 0)))
+
+    def profile_read(self):
+        """(jump ms, generate ms, segments, refills per segment) of the last get since profile(True)"""
+        j, g, s, l = C.c_float(0), C.c_float(0), C.c_int(0), C.c_int(0)
+        _check("cuRng64ProfileRead", lib().cuRng64ProfileRead(self.h, C.byref(j), C.byref(g), C.byref(s), C.byref(l)))
+        return j.value, g.value, s.value, l.value
+
 
 # ---------------------------------------------------------------------------------------------
 # multi-GPU: the reference's host-pointer API (one process, one worker thread per GPU) ...

@@ -41,8 +41,9 @@ constexpr unsigned long long DS_MSK2 = 0x000ffdfffc90fffdULL;
 constexpr int DS_STATE_WORDS = DS_N + 1;        // with the lung
 constexpr int DS_STATE_U32 = DS_STATE_WORDS * 4;  // 768
 constexpr int GEN_WARPS = 4;                    // segments per CTA of the generation kernel
-constexpr int JUMP_THREADS = 256;               // 768 / 256 = 3 state columns per thread
-constexpr int JUMP_GT = 8;                      // segments per CTA of the jump kernel
+constexpr int JUMP_THREADS = DS_STATE_WORDS;    // one 128-bit column of the state per thread (6 warps)
+constexpr int JUMP_GT = 16;                     // segments per CTA of the jump kernel
+constexpr int JUMP_BATCH = 8;                   // K rows a thread holds in registers (and as many in flight)
 
 struct __align__(16) W128 {
   unsigned long long lo, hi;
@@ -71,10 +72,54 @@ __device__ __forceinline__ W128 shfl_w(W128 v, int src) {
   return r;
 }
 
-// One refill of the warp's state st[0..191] (st[191] = lung) in shared memory: three rounds of up to 64 steps.
-// On return st holds the new state; the caller must __syncwarp() before other lanes' words are read.
-__device__ __forceinline__ void dsfmt_refill_warp(W128 *st, int lane) {
-  W128 lung = st[DS_N];  // every lane keeps the running lung
+// output kinds (include/rng.h): what is stored for a 64-bit half `w` of a state word, a double in [1, 2)
+enum { DS_RAW = 0, DS_CLOSE_OPEN = 1, DS_OPEN_CLOSE = 2, DS_OPEN_OPEN = 3, DS_CLOSE_CLOSE = 4 };
+
+template <int KIND>
+__device__ __forceinline__ unsigned long long ds_convert(unsigned long long w) {
+  if (KIND == DS_RAW) return w;
+  double d;
+  if (KIND == DS_CLOSE_OPEN) d = __longlong_as_double((long long)w) - 1.0;                 // rng/dsfmt.c:231
+  else if (KIND == DS_OPEN_CLOSE) d = 2.0 - __longlong_as_double((long long)w);            // rng/dsfmt.c:196
+  else if (KIND == DS_OPEN_OPEN) d = __longlong_as_double((long long)(w | 1ULL)) - 1.0;    // rng/dsfmt.c:160-161
+  else d = __dmul_rn((double)(w >> 10), 1.0 / 9007199254740991.0);                         // rng/dsfmt.c:266 (shift by 10, as there)
+  return (unsigned long long)__double_as_longlong(d);
+}
+
+// what happens to word i of a refill the moment its owner lane has it in registers
+template <int KIND>
+struct EmitWindow {  // converted and stored if the stream word lies inside the request
+  unsigned long long t0, w_begin, w_end, n_out;
+  unsigned long long *out;
+  bool aligned16;
+  __device__ __forceinline__ void operator()(int i, W128 v) const {
+    const unsigned long long t = t0 + (unsigned)i;
+    if (t < w_begin || t >= w_end) return;
+    const unsigned long long e = 2 * (t - w_begin);
+    const unsigned long long a = ds_convert<KIND>(v.lo), b = ds_convert<KIND>(v.hi);
+    if (e + 1 < n_out) {
+      if (aligned16) {
+        *reinterpret_cast<ulonglong2 *>(out + e) = make_ulonglong2(a, b);
+      } else {
+        out[e] = a;
+        out[e + 1] = b;
+      }
+    } else if (e < n_out) {
+      out[e] = a;  // odd tail: the high half of the last word is dropped (rng/dsfmt.c:245-251)
+    }
+  }
+};
+struct EmitSnapshot {  // the raw state (Krylov block)
+  W128 *dst;
+  __device__ __forceinline__ void operator()(int i, W128 v) const { dst[i] = v; }
+};
+
+// One refill of the warp's state st[0..190] in shared memory, three rounds of up to 64 steps; `lung` lives in registers
+// (every lane holds it).  Each new word goes to st and to `emit` straight from the registers of the lane that made it:
+// a lane's two words are 32 contiguous bytes of the stream, a round is 1 KB, so the stores fill whole sectors and stay
+// off the critical path (the next round does not wait for them).  Ends with a __syncwarp(): st is consistent on return.
+template <typename Emit>
+__device__ __forceinline__ void dsfmt_refill_warp(W128 *st, W128 &lung, int lane, const Emit &emit) {
 #pragma unroll 1
   for (int c0 = 0; c0 < DS_N; c0 += 64) {
     const int i0 = c0 + 2 * lane, i1 = i0 + 1;
@@ -104,26 +149,19 @@ __device__ __forceinline__ void dsfmt_refill_warp(W128 *st, int lane) {
     const W128 lin = lung ^ incl ^ c;  // exclusive prefix: the lung entering step i0
     const W128 y0 = perm(lin) ^ x0;    // lung after step i0
     const W128 y1 = perm(y0) ^ x1;     // lung after step i1
-    if (has0) st[i0] = mix_out(y0, s0);
-    if (has1) st[i1] = mix_out(y1, s1);
     lung = shfl_w(has1 ? y1 : y0, 31);
+    if (has0) {
+      const W128 r0 = mix_out(y0, s0);
+      st[i0] = r0;
+      emit(i0, r0);
+    }
+    if (has1) {
+      const W128 r1 = mix_out(y1, s1);
+      st[i1] = r1;
+      emit(i1, r1);
+    }
     __syncwarp();  // the next round reads words this round wrote (s[i-74]) from other lanes
   }
-  if (lane == 0) st[DS_N] = lung;
-}
-
-// output kinds (include/rng.h): what is stored for a 64-bit half `w` of a state word, a double in [1, 2)
-enum { DS_RAW = 0, DS_CLOSE_OPEN = 1, DS_OPEN_CLOSE = 2, DS_OPEN_OPEN = 3, DS_CLOSE_CLOSE = 4 };
-
-template <int KIND>
-__device__ __forceinline__ unsigned long long ds_convert(unsigned long long w) {
-  if (KIND == DS_RAW) return w;
-  double d;
-  if (KIND == DS_CLOSE_OPEN) d = __longlong_as_double((long long)w) - 1.0;                 // rng/dsfmt.c:231
-  else if (KIND == DS_OPEN_CLOSE) d = 2.0 - __longlong_as_double((long long)w);            // rng/dsfmt.c:196
-  else if (KIND == DS_OPEN_OPEN) d = __longlong_as_double((long long)(w | 1ULL)) - 1.0;    // rng/dsfmt.c:160-161
-  else d = __dmul_rn((double)(w >> 10), 1.0 / 9007199254740991.0);                         // rng/dsfmt.c:266 (shift by 10, as there)
-  return (unsigned long long)__double_as_longlong(d);
 }
 
 // One warp per segment.  Segment g starts from states[g] = T^(refill0 + g * seg_refills) s0 and produces refills
@@ -136,110 +174,96 @@ __global__ void __launch_bounds__(GEN_WARPS * 32)
 dsfmt_generate_kernel(const W128 *__restrict__ states, unsigned long long refill0, unsigned seg_refills, int nseg,
                       unsigned long long w_begin, unsigned long long w_end, unsigned long long *__restrict__ out,
                       unsigned long long n_out, W128 *__restrict__ snap) {
-  __shared__ W128 smem[GEN_WARPS][DS_STATE_WORDS];
+  __shared__ W128 smem[GEN_WARPS][DS_N];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int g = blockIdx.x * GEN_WARPS + wid;
   if (g >= nseg) return;  // whole warps leave; no block-wide barrier below
   W128 *st = smem[wid];
-  for (int i = lane; i < DS_STATE_WORDS; i += 32) st[i] = states[(size_t)g * DS_STATE_WORDS + i];
+  const W128 *src = states + (size_t)g * DS_STATE_WORDS;
+  for (int i = lane; i < DS_N; i += 32) st[i] = src[i];
+  W128 lung = src[DS_N];
   __syncwarp();
   const unsigned long long r_begin = refill0 + (unsigned long long)g * seg_refills;
   const bool aligned16 = (((size_t)out) & 15) == 0;
   for (unsigned k = 0; k < seg_refills; ++k) {
     const unsigned long long r = r_begin + k;
     const unsigned long long t0 = r * DS_N;  // first stream word of this refill
-    if (snap == nullptr && t0 >= w_end) break;
-    dsfmt_refill_warp(st, lane);
-    __syncwarp();
     if (snap != nullptr) {
       W128 *dst = snap + (size_t)(r + 1) * DS_STATE_WORDS;
-      for (int i = lane; i < DS_STATE_WORDS; i += 32) dst[i] = st[i];
-      __syncwarp();  // the next refill overwrites st
-      continue;
+      dsfmt_refill_warp(st, lung, lane, EmitSnapshot{dst});
+      if (lane == 0) dst[DS_N] = lung;
+    } else {
+      if (t0 >= w_end) break;
+      dsfmt_refill_warp(st, lung, lane, EmitWindow<KIND>{t0, w_begin, w_end, n_out, out, aligned16});
     }
-    if (t0 + DS_N <= w_begin) continue;  // before the window: the state only moves on
-#pragma unroll 1
-    for (int i = lane; i < DS_N; i += 32) {
-      const unsigned long long t = t0 + i;
-      if (t < w_begin || t >= w_end) continue;
-      const W128 v = st[i];
-      const unsigned long long e = 2 * (t - w_begin);
-      const unsigned long long a = ds_convert<KIND>(v.lo), b = ds_convert<KIND>(v.hi);
-      if (e + 1 < n_out) {
-        if (aligned16) {
-          *reinterpret_cast<ulonglong2 *>(out + e) = make_ulonglong2(a, b);
-        } else {
-          out[e] = a;
-          out[e + 1] = b;
-        }
-      } else if (e < n_out) {
-        out[e] = a;  // odd tail: the high half of the last word is dropped (rng/dsfmt.c:245-251)
-      }
-    }
-    __syncwarp();  // stores read st; the next refill overwrites it
   }
 }
 
-// states[g][:] ^= XOR over i in this CTA's slice of [0, D) with bit i of polys[g] set of K[i][:]
-// (K: D states of 768 32-bit words; polys: nseg rows of poly_u32 words; states zeroed by the caller).
-// grid.x = segment tiles of JUMP_GT, grid.y = slices of the i range; a thread owns 3 of the 768 columns.
+// states[g][:] ^= XOR over the rows i of this CTA's slice of [0, D) with bit i of polys[g] set of K[i][:]
+// (K: D states of 192 128-bit words; polys: nseg rows of poly_u32 32-bit words; states zeroed by the caller when
+// gridDim.y > 1).  grid.x = tiles of JUMP_GT segments, grid.y = slices of the row range (whole 32-bit words of the
+// polynomials).  A thread owns one 128-bit column of the state for all JUMP_GT segments (64 accumulator registers) and
+// streams the K rows through registers eight at a time, the next eight already in flight (the table lives in L2; one
+// row is read once per CTA, i.e. once per JUMP_GT segments).
+__device__ __forceinline__ void jump_load_rows(uint4 (&k)[JUMP_BATCH], const uint4 *__restrict__ K, int row0, int D, int t) {
+#pragma unroll
+  for (int j = 0; j < JUMP_BATCH; ++j)
+    k[j] = (row0 + j < D) ? K[(size_t)(row0 + j) * DS_STATE_WORDS + t] : make_uint4(0u, 0u, 0u, 0u);
+}
+
 __global__ void __launch_bounds__(JUMP_THREADS)
-dsfmt_jump_kernel(const uint32_t *__restrict__ K, const uint32_t *__restrict__ polys, int poly_u32, int D,
+dsfmt_jump_kernel(const uint4 *__restrict__ K, const uint32_t *__restrict__ polys, int poly_u32, int D,
                   uint32_t *__restrict__ states, int nseg) {
-  __shared__ uint32_t bits[JUMP_GT][32];  // one 1024-bit stretch of every segment's polynomial at a time
+  __shared__ uint32_t bits[JUMP_GT][32];  // one 1024-row stretch of every segment's polynomial at a time
   const int t = threadIdx.x;
   const int g0 = blockIdx.x * JUMP_GT;
   const int words = (D + 31) / 32;
   const int per = (words + gridDim.y - 1) / gridDim.y;
   const int w_lo = blockIdx.y * per, w_hi = min(words, w_lo + per);
-  uint32_t acc[JUMP_GT][3];
+  uint4 acc[JUMP_GT];
 #pragma unroll
-  for (int g = 0; g < JUMP_GT; ++g) acc[g][0] = acc[g][1] = acc[g][2] = 0u;
-  for (int wb = w_lo; wb < w_hi; wb += 32) {
-    __syncthreads();
-    {
-      const int g = t >> 5, w = wb + (t & 31);  // 8 x 32 = 256 threads
-      bits[g][t & 31] = (g0 + g < nseg && w < w_hi && w < poly_u32) ? polys[(size_t)(g0 + g) * poly_u32 + w] : 0u;
-    }
-    __syncthreads();
-    const int wn = min(32, w_hi - wb);
-    for (int wi = 0; wi < wn; ++wi) {
-      uint32_t a[JUMP_GT];
-      uint32_t any = 0u;
-#pragma unroll
-      for (int g = 0; g < JUMP_GT; ++g) {
-        a[g] = bits[g][wi];
-        any |= a[g];
+  for (int g = 0; g < JUMP_GT; ++g) acc[g] = make_uint4(0u, 0u, 0u, 0u);
+  const int r_lo = w_lo * 32, r_hi = min(D, w_hi * 32);
+  uint4 kc[JUMP_BATCH], kn[JUMP_BATCH];
+  if (r_lo < r_hi) jump_load_rows(kc, K, r_lo, D, t);
+  for (int rb = r_lo; rb < r_hi; rb += JUMP_BATCH) {
+    if (rb + JUMP_BATCH < r_hi) jump_load_rows(kn, K, rb + JUMP_BATCH, D, t);  // in flight while this batch is applied
+    const int w = rb >> 5;
+    if (((w - w_lo) & 31) == 0 && (rb & 31) == 0) {  // a new 1024-row stretch: stage its polynomial words
+      __syncthreads();
+      for (int e = t; e < JUMP_GT * 32; e += JUMP_THREADS) {
+        const int g = e >> 5, ww = w + (e & 31);
+        bits[g][e & 31] = (g0 + g < nseg && ww < w_hi && ww < poly_u32) ? polys[(size_t)(g0 + g) * poly_u32 + ww] : 0u;
       }
-      if (any == 0u) continue;  // uniform across the CTA
-      const int ibase = (wb + wi) * 32;
-      const int nb = min(32, D - ibase);
-#pragma unroll 4
-      for (int ib = 0; ib < nb; ++ib) {
-        const uint32_t *row = K + (size_t)(ibase + ib) * DS_STATE_U32;
-        const uint32_t k0 = row[t], k1 = row[t + JUMP_THREADS], k2 = row[t + 2 * JUMP_THREADS];
+      __syncthreads();
+    }
+    const int wi = (w - w_lo) & 31, sh = rb & 31;
 #pragma unroll
-        for (int g = 0; g < JUMP_GT; ++g) {
-          const uint32_t m = 0u - ((a[g] >> ib) & 1u);
-          acc[g][0] ^= k0 & m;
-          acc[g][1] ^= k1 & m;
-          acc[g][2] ^= k2 & m;
+    for (int g = 0; g < JUMP_GT; ++g) {
+      const uint32_t m = bits[g][wi] >> sh;  // bit j = row rb + j (rows beyond D have zero bits: deg a < D)
+#pragma unroll
+      for (int j = 0; j < JUMP_BATCH; ++j)
+        if ((m >> j) & 1u) {
+          acc[g].x ^= kc[j].x;
+          acc[g].y ^= kc[j].y;
+          acc[g].z ^= kc[j].z;
+          acc[g].w ^= kc[j].w;
         }
-      }
     }
+#pragma unroll
+    for (int j = 0; j < JUMP_BATCH; ++j) kc[j] = kn[j];
   }
 #pragma unroll
   for (int g = 0; g < JUMP_GT; ++g) {
     if (g0 + g >= nseg) break;
-    uint32_t *dst = states + (size_t)(g0 + g) * DS_STATE_U32;
+    uint32_t *dst = states + (size_t)(g0 + g) * DS_STATE_U32 + 4 * t;
     if (gridDim.y == 1) {
-      dst[t] = acc[g][0];
-      dst[t + JUMP_THREADS] = acc[g][1];
-      dst[t + 2 * JUMP_THREADS] = acc[g][2];
+      *reinterpret_cast<uint4 *>(dst) = acc[g];
     } else {
-      if (acc[g][0]) atomicXor(dst + t, acc[g][0]);
-      if (acc[g][1]) atomicXor(dst + t + JUMP_THREADS, acc[g][1]);
-      if (acc[g][2]) atomicXor(dst + t + 2 * JUMP_THREADS, acc[g][2]);
+      if (acc[g].x) atomicXor(dst + 0, acc[g].x);
+      if (acc[g].y) atomicXor(dst + 1, acc[g].y);
+      if (acc[g].z) atomicXor(dst + 2, acc[g].z);
+      if (acc[g].w) atomicXor(dst + 3, acc[g].w);
     }
   }
 }
@@ -286,7 +310,7 @@ extern "C" int chol_dsfmt_jump_launch(const void *K, const void *polys, int poly
     cudaError_t e = cudaMemsetAsync(states, 0, (size_t)nseg * DS_STATE_U32 * sizeof(uint32_t), st);
     if (e != cudaSuccess) return (int)e;
   }
-  dsfmt_jump_kernel<<<dim3(gx, gy), JUMP_THREADS, 0, st>>>((const uint32_t *)K, (const uint32_t *)polys, poly_u32, D,
+  dsfmt_jump_kernel<<<dim3(gx, gy), JUMP_THREADS, 0, st>>>((const uint4 *)K, (const uint32_t *)polys, poly_u32, D,
                                                           (uint32_t *)states, nseg);
   CHOL_COUNT_LAUNCH();
   return (int)cudaGetLastError();

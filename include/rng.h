@@ -67,6 +67,18 @@ CUresult cuRng64SetStream(CUrng64, CUstream stream);
 CUresult cuRng64Discard(CUrng64, size_t n);
 /* 128-bit words of the stream consumed since cuRng64Set */
 unsigned long long cuRng64Position(CUrng64);
+/* tuning / measurement hooks (like cuLAPACKSetBlockSize / cuLAPACKProfile): a request is cut into segments of 2^level
+ * refills (382 values each); bias (-8 .. 8) shifts the level the library would choose - the values produced do not
+ * depend on it.  Profile(1) times the two kernels of every later Get with events on the generator's stream; ProfileRead
+ * waits for the last Get and returns its jump and generation times, segment count and segment length (any pointer
+ * may be NULL); CUDA_ERROR_NOT_READY if no Get has run since Profile(1). */
+CUresult cuRng64SetSegmentBias(CUrng64, int bias);
+/* a request of at least 32 * chunks segments is produced in `chunks` (1 .. 8; 0 = the library's default) pieces: the
+ * generation of one piece runs on an internal high-priority stream while the next piece's start states are computed
+ * on the caller's stream, which waits for the internal one before the call's work counts as done */
+CUresult cuRng64SetPipelineChunks(CUrng64, int chunks);
+CUresult cuRng64Profile(CUrng64, int enable);
+CUresult cuRng64ProfileRead(CUrng64, float *jump_ms, float *generate_ms, int *segments, int *segment_refills);
 
 #ifdef __cplusplus
 }

@@ -145,7 +145,7 @@ int main() {
       chol_dsfmt_refill_host(cur);
     }
     const int poly_u32 = 2 * ((D + 63) / 64);
-    struct { int level; uint64_t j0; int nseg; unsigned gy; } jc[] = {{4, 3, 11, 3}, {6, 0, 8, 1}, {5, 700, 3, 20}};
+    struct { int level; uint64_t j0; int nseg; unsigned gy; } jc[] = {{4, 3, 11, 3}, {6, 0, 8, 1}, {5, 700, 3, 20}, {4, 100, 37, 7}, {7, 1, 16, 14}};
     for (auto &c : jc) {
       std::vector<uint32_t> polys((size_t)c.nseg * poly_u32);
       if (chol_dsfmt_poly_rows(gen, c.level, c.j0, (size_t)c.nseg, polys.data(), (size_t)poly_u32) != 0) {
@@ -154,7 +154,7 @@ int main() {
       }
       std::vector<uint32_t> states((size_t)c.nseg * DS_STATE_U32, c.gy > 1 ? 0u : 0xdeadbeefu);
       const dim3 grid((c.nseg + JUMP_GT - 1) / JUMP_GT, c.gy);
-      emu::launch(grid, dim3(JUMP_THREADS), 0, [&] { dsfmt_jump_kernel(K.data(), polys.data(), poly_u32, D, states.data(), c.nseg); });
+      emu::launch(grid, dim3(JUMP_THREADS), 0, [&] { dsfmt_jump_kernel((const uint4 *)K.data(), polys.data(), poly_u32, D, states.data(), c.nseg); });
       // direct: iterate the host refill to every segment start
       bool ok = true;
       std::memcpy(cur, s0, sizeof cur);

@@ -128,6 +128,24 @@ def test_far_window_and_second_seed(rng):
     assert np.array_equal(got, ora.fill(5000))
 
 
+def test_tuning_hooks_do_not_change_the_stream():
+    """segment length (cuRng64SetSegmentBias) and pipelined pieces (cuRng64SetPipelineChunks: generation of one piece on the
+    internal stream while the next piece jumps) are tuning parameters only; the profiling hook reports the split"""
+    g = G.chol.Rng64()
+    for chunks, bias in ((1, -2), (1, 2), (2, -2), (4, -3), (8, -4), (3, 0)):
+        g.set_pipeline_chunks(chunks)
+        g.set_segment_bias(bias)
+        g.set(H.SEED)
+        g.profile(True)
+        ora = H.OracleDsfmt(H.SEED)
+        for n in (1500001, 7, 4000000, 123457):
+            assert np.array_equal(device_get(g, n), ora.fill(n)), (chunks, bias, n)
+        jump_ms, gen_ms, nseg, seglen = g.profile_read()
+        assert jump_ms > 0 and gen_ms >= 0 and nseg >= 1 and seglen >= 16 and seglen & (seglen - 1) == 0
+        g.profile(False)
+    g.close()
+
+
 def test_user_stream_burst_and_argument_errors():
     g = G.chol.Rng64()
     with pytest.raises(G.chol.CholeskyError) as e:
