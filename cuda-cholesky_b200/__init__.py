@@ -309,9 +309,6 @@ class Rng64:
     def set_segment_bias(self, bias):
         _check("cuRng64SetSegmentBias", lib().cuRng64SetSegmentBias(self.h, C.c_int(bias)))
 
-    def set_pipeline_chunks(self, chunks):
-        _check("cuRng64SetPipelineChunks", lib().cuRng64SetPipelineChunks(self.h, C.c_int(chunks)))
-
     def profile(self, enable=True):
         _check("cuRng64Profile", lib().cuRng64Profile(self.h, C.c_int(1 if enable else 0)))
 
@@ -320,6 +317,12 @@ class Rng64:
         j, g, s, l = C.c_float(0), C.c_float(0), C.c_int(0), C.c_int(0)
         _check("cuRng64ProfileRead", lib().cuRng64ProfileRead(self.h, C.byref(j), C.byref(g), C.byref(s), C.byref(l)))
         return j.value, g.value, s.value, l.value
+
+
+def dsfmt_set_variant(gen=-1, jump=-1):
+    """A/B hook of csrc/rng_dsfmt.cu (process-wide): generation 0 = read-back stores, 1 = register stores; jump 0 / 1 / 2 / 3 =
+    16 / 32 / 48 / 64 segments per CTA; -1 leaves a setting as it is."""
+    lib().chol_dsfmt_set_variant(C.c_int(gen), C.c_int(jump))
 
 
 # ---------------------------------------------------------------------------------------------

@@ -28,9 +28,6 @@ const CUrng64_t cu_dsfmt_19937_t = &dsfmt_19937_type;
 #define RNG_MIN_LEVEL 4      /* segments of at least 16 refills */
 #define RNG_LEVEL_BIAS 0     /* default shift of the segment level against "L^2 >= refills" (measured) */
 #define RNG_MAX_SEGMENTS 4096
-#define RNG_MAX_CHUNKS 8
-#define RNG_CHUNKS 1         /* default number of pipelined pieces (measured); a piece has >= 32 segments */
-#define RNG_CHUNK_MIN_SEGMENTS 32
 
 struct __curng64_st {
   CUcontext context;
@@ -57,9 +54,6 @@ struct __curng64_st {
   size_t res_count;
   unsigned res_generation;
   int level_bias;    /* tuning hook: added to the default segment level (cuRng64SetSegmentBias) */
-  int chunks;        /* tuning hook: pieces a large request is pipelined in (0 = default; cuRng64SetPipelineChunks) */
-  CUstream aux;      /* high-priority non-blocking stream: generation of piece c runs here while piece c + 1 jumps */
-  CUevent ev_jump[RNG_MAX_CHUNKS], ev_aux_done;
   bool profile;      /* time the two kernels of every Get with events on the generator's stream */
   CUevent prof_ev[3];
   bool prof_valid;
@@ -112,12 +106,6 @@ CUresult cuRng64Destroy(CUrng64 r) {
   if (r->upload_done) cuEventDestroy(r->upload_done);
   for (int i = 0; i < 3; i++)
     if (r->prof_ev[i]) cuEventDestroy(r->prof_ev[i]);
-  if (r->aux) {
-    cuStreamSynchronize(r->aux);
-    cuStreamDestroy(r->aux);
-    for (int i = 0; i < RNG_MAX_CHUNKS; i++) cuEventDestroy(r->ev_jump[i]);
-    cuEventDestroy(r->ev_aux_done);
-  }
   CUcontext dummy;
   CU_ERROR_CHECK(cuCtxPopCurrent(&dummy));
   if (r->primary_retained) cuDevicePrimaryCtxRelease(r->device);
@@ -202,16 +190,6 @@ static CUresult rng_reserve(CUrng64 r, size_t nseg, size_t poly_u32) {
   return CUDA_SUCCESS;
 }
 
-static CUresult rng_aux(CUrng64 r) {
-  if (r->aux != NULL) return CUDA_SUCCESS;
-  int lo = 0, hi = 0;
-  CU_ERROR_CHECK(cuCtxGetStreamPriorityRange(&lo, &hi));
-  CU_ERROR_CHECK(cuStreamCreateWithPriority(&r->aux, CU_STREAM_NON_BLOCKING, hi));
-  for (int i = 0; i < RNG_MAX_CHUNKS; i++) CU_ERROR_CHECK(cuEventCreate(&r->ev_jump[i], CU_EVENT_DISABLE_TIMING));
-  CU_ERROR_CHECK(cuEventCreate(&r->ev_aux_done, CU_EVENT_DISABLE_TIMING));
-  return CUDA_SUCCESS;
-}
-
 static CUresult rng_get(CUrng64 r, int kind, CUdeviceptr x, size_t n) {
   if (!r->seeded) return CUDA_ERROR_NOT_INITIALIZED; /* the CPU generator has no default seed either */
   if (n == 0) return CUDA_SUCCESS;
@@ -254,40 +232,13 @@ static CUresult rng_get(CUrng64 r, int kind, CUdeviceptr x, size_t n) {
       r->res_count = nseg;
       r->res_generation = r->generation;
     }
-    /* pieces: jump(c) on the caller's stream, generate(c) on the auxiliary stream behind it - so generate(c) overlaps
-     * jump(c + 1); one piece = the plain two-launch sequence on the caller's stream */
-    int chunks = r->chunks > 0 ? r->chunks : RNG_CHUNKS;
-    if ((size_t)chunks > nseg / RNG_CHUNK_MIN_SEGMENTS) chunks = (int)(nseg / RNG_CHUNK_MIN_SEGMENTS);
-    if (chunks < 1) chunks = 1;
-    if (chunks > 1) CU_ERROR_CHECK(rng_aux(r));
     const CUdeviceptr rows = r->dpolys + row0 * poly_u32 * sizeof(uint32_t);
     if (r->profile) CU_ERROR_CHECK(cuEventRecord(r->prof_ev[0], r->stream));
-    size_t s0 = 0;
-    for (int c = 0; c < chunks; c++) {
-      /* piece boundaries on multiples of 16 segments (the jump kernel's tile) */
-      size_t s1 = c + 1 == chunks ? nseg : chol_roundup(nseg * (size_t)(c + 1) / (size_t)chunks, 16);
-      if (s1 > nseg) s1 = nseg;
-      if (s1 <= s0) continue;
-      const CUdeviceptr st = r->states + s0 * CHOL_DSFMT_STATE_BYTES;
-      RT_CHECK(chol_dsfmt_jump_launch((const void *)r->K, (const void *)(rows + s0 * poly_u32 * sizeof(uint32_t)), (int)poly_u32, r->D,
-                                      (void *)st, (int)(s1 - s0), (void *)r->stream));
-      CUstream gs = r->stream;
-      if (chunks > 1) {
-        CU_ERROR_CHECK(cuEventRecord(r->ev_jump[c], r->stream));
-        CU_ERROR_CHECK(cuStreamWaitEvent(r->aux, r->ev_jump[c], 0));
-        gs = r->aux;
-      } else if (r->profile) {
-        CU_ERROR_CHECK(cuEventRecord(r->prof_ev[1], r->stream));
-      }
-      RT_CHECK(chol_dsfmt_generate_launch((const void *)st, (unsigned long long)((j0 + s0) << level), 1u << level, (int)(s1 - s0), w0, w1,
-                                          (void *)x, (unsigned long long)n, kind, NULL, (void *)gs));
-      s0 = s1;
-    }
-    if (chunks > 1) {
-      if (r->profile) CU_ERROR_CHECK(cuEventRecord(r->prof_ev[1], r->stream)); /* the last jump is done */
-      CU_ERROR_CHECK(cuEventRecord(r->ev_aux_done, r->aux));
-      CU_ERROR_CHECK(cuStreamWaitEvent(r->stream, r->ev_aux_done, 0)); /* the caller's stream owns the result again */
-    }
+    RT_CHECK(chol_dsfmt_jump_launch((const void *)r->K, (const void *)rows, (int)poly_u32, r->D, (void *)r->states, (int)nseg,
+                                    (void *)r->stream));
+    if (r->profile) CU_ERROR_CHECK(cuEventRecord(r->prof_ev[1], r->stream));
+    RT_CHECK(chol_dsfmt_generate_launch((const void *)r->states, (unsigned long long)(j0 << level), 1u << level, (int)nseg, w0, w1,
+                                        (void *)x, (unsigned long long)n, kind, NULL, (void *)r->stream));
     if (r->profile) {
       CU_ERROR_CHECK(cuEventRecord(r->prof_ev[2], r->stream));
       r->prof_valid = true;
@@ -340,12 +291,6 @@ CUresult cuRng64Discard(CUrng64 r, size_t n) {
 }
 
 unsigned long long cuRng64Position(CUrng64 r) { return r == NULL ? 0ull : r->pos; }
-
-CUresult cuRng64SetPipelineChunks(CUrng64 r, int chunks) {
-  if (r == NULL || chunks < 0 || chunks > RNG_MAX_CHUNKS) return CUDA_ERROR_INVALID_VALUE;
-  r->chunks = chunks;
-  return CUDA_SUCCESS;
-}
 
 CUresult cuRng64SetSegmentBias(CUrng64 r, int bias) {
   if (r == NULL || bias < -8 || bias > 8) return CUDA_ERROR_INVALID_VALUE;

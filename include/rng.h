@@ -73,10 +73,6 @@ unsigned long long cuRng64Position(CUrng64);
  * waits for the last Get and returns its jump and generation times, segment count and segment length (any pointer
  * may be NULL); CUDA_ERROR_NOT_READY if no Get has run since Profile(1). */
 CUresult cuRng64SetSegmentBias(CUrng64, int bias);
-/* a request of at least 32 * chunks segments is produced in `chunks` (1 .. 8; 0 = the library's default) pieces: the
- * generation of one piece runs on an internal high-priority stream while the next piece's start states are computed
- * on the caller's stream, which waits for the internal one before the call's work counts as done */
-CUresult cuRng64SetPipelineChunks(CUrng64, int chunks);
 CUresult cuRng64Profile(CUrng64, int enable);
 CUresult cuRng64ProfileRead(CUrng64, float *jump_ms, float *generate_ms, int *segments, int *segment_refills);
 

@@ -1,7 +1,8 @@
-"""One process, one GPU call: the device generator's GPU parity tests (pytest in-process), then its timing over the tuning
-space - segment-length bias x pipelined pieces x request size - with the jump / generation split from the library's own
-events (cuRng64Profile).  Every timed configuration is also compared with the oracle on its first 2^20 values.
-Prints one JSON line per configuration; RNG_FINAL_SKIP_TESTS=1 skips the tests."""
+"""One process, one GPU call: the device generator's GPU parity tests (pytest in-process, once per candidate jump variant),
+then its timing over the variants - generation (read-back / register stores) x jump tile (16 / 32 / 48 / 64 segments per
+CTA) x segment-length bias x request size - with the jump / generation split from the library's own events
+(cuRng64Profile).  Every timed configuration is also compared with the oracle on its first 2^20 values.
+Prints one JSON line per configuration."""
 import json
 import os
 import sys
@@ -15,51 +16,53 @@ import numpy as np  # noqa: E402
 import pytest  # noqa: E402
 import torch  # noqa: E402
 
-rc = 0
-if not os.environ.get("RNG_FINAL_SKIP_TESTS"):
-    rc = int(pytest.main(["-q", "-x", "-p", "no:cacheprovider", os.path.join(ROOT, "tests", "test_zz_gpu_rng.py")]))
-    print(json.dumps({"what": "pytest tests/test_zz_gpu_rng.py", "rc": rc, "elapsed_s": time.time() - t_start}), flush=True)
-
 import harness as H  # noqa: E402
 from cholesky_b200_loader import load  # noqa: E402
 
 chol = load()
-deadline = t_start + float(os.environ.get("RNG_FINAL_BUDGET_S", "60"))
-sizes = [int(x) for x in os.environ.get("RNG_SIZES", "%d,%d,%d" % (1 << 26, 1 << 28, 1 << 30)).split(",")]
+rc = 0
+for jump in [int(x) for x in os.environ.get("RNG_TEST_JUMPS", "2,3").split(",") if x != ""]:
+    chol.dsfmt_set_variant(0, jump)
+    r = int(pytest.main(["-q", "-x", "-p", "no:cacheprovider", os.path.join(ROOT, "tests", "test_zz_gpu_rng.py")]))
+    print(json.dumps({"what": "pytest tests/test_zz_gpu_rng.py", "gen": 0, "jump": jump, "rc": r, "elapsed_s": time.time() - t_start}), flush=True)
+    rc = rc or r
+
+deadline = t_start + float(os.environ.get("RNG_FINAL_BUDGET_S", "40"))
+sizes = [int(x) for x in os.environ.get("RNG_SIZES", "%d,%d" % (1 << 26, 1 << 30)).split(",")]
 want = H.OracleDsfmt(H.SEED).fill(1 << 20)
 g = chol.Rng64()
 g.set(H.SEED)
+g.profile(True)
 buf = torch.empty(max(sizes), dtype=torch.float64, device="cuda")
+configs = [(0, j, b) for b in (0, 1, -1) for j in (2, 3, 1, 0)] + [(1, 2, 0), (1, 3, 0)]
 for n in sizes:
-    for chunks in (1, 4):
-        for bias in (0, 1, 2, -1, 3):
-            if time.time() > deadline:
-                print(json.dumps({"what": "time budget reached", "n": n, "chunks": chunks, "bias": bias}), flush=True)
-                continue
-            g.set_pipeline_chunks(chunks)
-            g.set_segment_bias(bias)
-            g.profile(True)
+    for gen, jump, bias in configs:
+        if time.time() > deadline:
+            print(json.dumps({"what": "time budget reached", "n": n, "gen": gen, "jump": jump, "bias": bias}), flush=True)
+            continue
+        chol.dsfmt_set_variant(gen, jump)
+        g.set_segment_bias(bias)
+        g.set(H.SEED)
+        g.get(buf.data_ptr(), n)  # first call of this shape: polynomial rows computed on the host and uploaded
+        best = None
+        for _ in range(2):
             g.set(H.SEED)
-            g.get(buf.data_ptr(), n)  # first call of this shape: polynomial rows computed on the host and uploaded
-            best = None
-            for _ in range(3):
-                g.set(H.SEED)
-                torch.cuda.synchronize()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                g.get(buf.data_ptr(), n)
-                e1.record()
-                torch.cuda.synchronize()
-                ms = e0.elapsed_time(e1)
-                jm, gm, nseg, seglen = g.profile_read()
-                if best is None or ms < best["ms"]:
-                    best = {"ms": ms, "jump_ms": jm, "generate_ms": gm, "segments": nseg, "segment_refills": seglen}
-            k = min(n, 1 << 20)
-            ok = bool(np.array_equal(buf[:k].cpu().numpy().view(np.uint64), want[:k]))
-            best.update({"what": "cuRng64GetCloseOpen", "n": n, "chunks": chunks, "bias": bias, "GBps": 8e-6 * n / best["ms"],
-                         "frac_of_hbm_peak_6550": 8e-6 * n / best["ms"] / 6550.4, "equal_oracle_first_1M": ok})
-            print(json.dumps(best), flush=True)
-            if not ok:
-                rc = rc or 3
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.get(buf.data_ptr(), n)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            jm, gm, nseg, seglen = g.profile_read()
+            if best is None or ms < best["ms"]:
+                best = {"ms": ms, "jump_ms": jm, "generate_ms": gm, "segments": nseg, "segment_refills": seglen}
+        k = min(n, 1 << 20)
+        ok = bool(np.array_equal(buf[:k].cpu().numpy().view(np.uint64), want[:k]))
+        best.update({"what": "cuRng64GetCloseOpen", "n": n, "gen": gen, "jump": jump, "bias": bias, "GBps": 8e-6 * n / best["ms"],
+                     "frac_of_hbm_peak_6550": 8e-6 * n / best["ms"] / 6550.4, "equal_oracle_first_1M": ok})
+        print(json.dumps(best), flush=True)
+        if not ok:
+            rc = rc or 3
 g.close()
 sys.exit(rc)

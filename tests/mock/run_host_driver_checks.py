@@ -464,25 +464,6 @@ def device_rng():
         ok(nseg >= 1 and seglen >= 16 and (seglen & (seglen - 1)) == 0, "profile_read: %d segments of %d refills" % (nseg, seglen))
         g.profile(False)
     g.set_segment_bias(0)
-    # pipelined pieces (generation of piece c on the internal stream while piece c + 1 jumps): same values, on the NULL stream
-    # and on a user stream, also back to back without synchronisation
-    for use_stream in (False, True):
-        g.set_stream(stream.value if use_stream else 0)
-        for chunks, bias in ((2, -2), (4, -3), (8, -4), (3, -1)):
-            g.set_pipeline_chunks(chunks)
-            g.set_segment_bias(bias)
-            g.set(seed)
-            ora = H.OracleDsfmt(seed)
-            sizes = (1500001, 7, 2000000, 123457)
-            outs = [np.zeros(n, dtype=np.uint64) for n in sizes]
-            for o_, n in zip(outs, sizes):
-                g.get(ptr(o_), n)
-            mock.cuStreamSynchronize(stream if use_stream else None)
-            for o_, n in zip(outs, sizes):
-                ok(np.array_equal(o_, ora.fill(n)), "pipelined in %d pieces (bias %d, stream %s): n=%d" % (chunks, bias, use_stream, n))
-    g.set_pipeline_chunks(0)
-    g.set_segment_bias(0)
-    g.set_stream(0)
     # three generators fill the block columns r, r + 3, ... of one column-major matrix from ONE global stream
     m_, n_, nb_, P_ = 640, 1100, 128, 3
     want = H.OracleDsfmt(seed).fill(m_ * n_).reshape(n_, m_)

@@ -93,7 +93,7 @@ def mock_runs(tmp_path_factory):
                                               ("lapack+nopipe", 700), ("multi3+nopipe", 800),
                                               ("lapack+jitter", 700), ("multi3+jitter", 800),
                                               ("lapack+nosplit+jitter", 700), ("multi3+nosplit+nopipe+jitter", 800),
-                                              ("dist3+jitter", 20), ("rng+jitter", 370)])
+                                              ("dist3+jitter", 20), ("rng+jitter", 340)])
 def test_host_drivers_on_mock_backend(mock_runs, group, min_checks):
     rc, out = mock_runs[group]
     assert rc == 0 and "MOCK PASSED" in out, out[-3000:]

@@ -129,17 +129,15 @@ def test_far_window_and_second_seed(rng):
 
 
 def test_tuning_hooks_do_not_change_the_stream():
-    """segment length (cuRng64SetSegmentBias) and pipelined pieces (cuRng64SetPipelineChunks: generation of one piece on the
-    internal stream while the next piece jumps) are tuning parameters only; the profiling hook reports the split"""
+    """the segment length (cuRng64SetSegmentBias) is a tuning parameter only; the profiling hook reports the jump / generation split"""
     g = G.chol.Rng64()
-    for chunks, bias in ((1, -2), (1, 2), (2, -2), (4, -3), (8, -4), (3, 0)):
-        g.set_pipeline_chunks(chunks)
+    for bias in (-3, -2, -1, 1, 2, 4):
         g.set_segment_bias(bias)
         g.set(H.SEED)
         g.profile(True)
         ora = H.OracleDsfmt(H.SEED)
         for n in (1500001, 7, 4000000, 123457):
-            assert np.array_equal(device_get(g, n), ora.fill(n)), (chunks, bias, n)
+            assert np.array_equal(device_get(g, n), ora.fill(n)), (bias, n)
         jump_ms, gen_ms, nseg, seglen = g.profile_read()
         assert jump_ms > 0 and gen_ms >= 0 and nseg >= 1 and seglen >= 16 and seglen & (seglen - 1) == 0
         g.profile(False)
