@@ -28,7 +28,7 @@ for jump in [int(x) for x in os.environ.get("RNG_TEST_JUMPS", "2,3").split(",") 
     rc = rc or r
 
 deadline = t_start + float(os.environ.get("RNG_FINAL_BUDGET_S", "40"))
-sizes = [int(x) for x in os.environ.get("RNG_SIZES", "%d,%d" % (1 << 26, 1 << 30)).split(",")]
+sizes = [int(x) for x in os.environ.get("RNG_SIZES", "%d,%d" % (1 << 30, 1 << 26)).split(",")]
 want = H.OracleDsfmt(H.SEED).fill(1 << 20)
 g = chol.Rng64()
 g.set(H.SEED)
