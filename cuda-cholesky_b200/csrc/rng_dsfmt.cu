@@ -212,6 +212,109 @@ dsfmt_generate_kernel(const W128 *__restrict__ states, unsigned long long refill
   }
 }
 
+// ---- generation, four segments per warp: a group of 8 lanes owns one segment, lane a the 8 consecutive steps
+// c0 + 8a .. c0 + 8a + 7 of a 64-step round.  Eight steps leave the lung as lung ^ P(x0 ^ x2 ^ x4 ^ x6) ^ (x1 ^ x3 ^ x5 ^ x7),
+// so the scan is 3 steps inside the group instead of 5 across the warp, one shuffle instruction serves four segments,
+// and a lane's 8 words are 128 contiguous bytes of the stream.  Shared-memory slot of word i: the low three bits are
+// XORed with bits 3..5 (both "lanes read 8a + k" and "lanes read 8k' + a" hit distinct banks).
+constexpr int G8_WARPS = 2;
+__device__ __forceinline__ int g8_slot(int i) { return (i & ~7) | ((i ^ (i >> 3)) & 7); }
+__device__ __forceinline__ W128 shfl_up_w8(W128 v, int d) {
+  W128 r;
+  r.lo = __shfl_up_sync(0xffffffffu, v.lo, d, 8);
+  r.hi = __shfl_up_sync(0xffffffffu, v.hi, d, 8);
+  return r;
+}
+__device__ __forceinline__ W128 shfl_w8(W128 v, int src) {
+  W128 r;
+  r.lo = __shfl_sync(0xffffffffu, v.lo, src, 8);
+  r.hi = __shfl_sync(0xffffffffu, v.hi, src, 8);
+  return r;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(G8_WARPS * 32)
+dsfmt_generate8_kernel(const W128 *__restrict__ states, unsigned long long refill0, unsigned seg_refills, int nseg,
+                       unsigned long long w_begin, unsigned long long w_end, unsigned long long *__restrict__ out,
+                       unsigned long long n_out, W128 *__restrict__ snap) {
+  __shared__ W128 smem[G8_WARPS * 4][DS_STATE_WORDS];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, grp = lane >> 3, l8 = lane & 7;
+  const int g_first = (blockIdx.x * G8_WARPS + wid) * 4;
+  if (g_first >= nseg) return;  // whole warps leave; no block-wide barrier below
+  const bool live = g_first + grp < nseg;
+  const int g = live ? g_first + grp : nseg - 1;  // a group without a segment shadows the last one and stores nothing
+  W128 *st = smem[wid * 4 + grp];
+  const W128 *src = states + (size_t)g * DS_STATE_WORDS;
+  for (int i = l8; i < DS_N; i += 8) st[g8_slot(i)] = src[i];
+  W128 lung = src[DS_N];
+  __syncwarp();
+  const unsigned long long r_begin = refill0 + (unsigned long long)g * seg_refills;
+  const unsigned long long r_warp = refill0 + (unsigned long long)g_first * seg_refills;  // the warp's earliest segment
+  const bool aligned16 = (((size_t)out) & 15) == 0;
+  for (unsigned k = 0; k < seg_refills; ++k) {
+    const unsigned long long t0 = (r_begin + k) * DS_N;  // first stream word of this refill
+    if (snap == nullptr && (r_warp + k) * DS_N >= w_end) break;  // uniform: later groups are later in the stream
+    const EmitWindow<KIND> window{t0, w_begin, w_end, n_out, out, aligned16};
+    W128 *dst = snap != nullptr ? snap + (size_t)(r_begin + k + 1) * DS_STATE_WORDS : nullptr;
+#pragma unroll 1
+    for (int c0 = 0; c0 < DS_N; c0 += 64) {
+      const int base = c0 + 8 * l8;
+      const int cnt = min(8, DS_N - base);  // 7 for the last lane of the last round, else 8
+      W128 s[8], x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] = W128{0, 0};
+        x[j] = W128{0, 0};
+        if (j < cnt) {
+          const int i = base + j;
+          int b = i + DS_POS1;
+          if (b >= DS_N) b -= DS_N;
+          s[j] = st[g8_slot(i)];
+          x[j] = mix_in(s[j], st[g8_slot(b)]);
+        }
+      }
+      const W128 c = perm(x[0] ^ x[2] ^ x[4] ^ x[6]) ^ (x[1] ^ x[3] ^ x[5] ^ x[7]);
+      W128 incl = c;
+#pragma unroll
+      for (int d = 1; d < 8; d <<= 1) {
+        const W128 up = shfl_up_w8(incl, d);
+        if (l8 >= d) incl = incl ^ up;
+      }
+      W128 y = lung ^ incl ^ c;  // the lung entering this lane's first step
+      W128 y_last = y;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        y = perm(y) ^ x[j];
+        if (j < cnt) {
+          s[j] = mix_out(y, s[j]);  // the new word
+          st[g8_slot(base + j)] = s[j];
+          y_last = y;
+        }
+      }
+      lung = shfl_w8(y_last, 7);
+      if (live) {
+        const unsigned long long tb = t0 + (unsigned)base;  // this lane's words are stream words tb .. tb + cnt - 1
+        if (dst != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (j < cnt) dst[base + j] = s[j];
+        } else if (aligned16 && tb >= w_begin && tb + cnt <= w_end && 2 * (tb + cnt - w_begin) <= n_out) {
+          ulonglong2 *p = reinterpret_cast<ulonglong2 *>(out + 2 * (tb - w_begin));  // all of them inside the request: 128 contiguous bytes
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (j < cnt) p[j] = make_ulonglong2(ds_convert<KIND>(s[j].lo), ds_convert<KIND>(s[j].hi));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)  // a request boundary inside these words (unrolled: s stays in registers)
+            if (j < cnt) window(base + j, s[j]);
+        }
+      }
+      __syncwarp();  // the next round reads words this round wrote (s[i-74]) from other lanes
+    }
+    if (dst != nullptr && live && l8 == 0) dst[DS_N] = lung;
+  }
+}
+
 // states[g][:] ^= XOR over the rows i of this CTA's slice of [0, D) with bit i of polys[g] set of K[i][:]
 // (K: D states of 3072 bytes; polys: nseg rows of poly_u32 32-bit words; states zeroed by the caller when
 // gridDim.y > 1).  grid.x = tiles of GT segments, grid.y = slices of the row range (whole 32-bit words of the
@@ -297,9 +400,9 @@ dsfmt_jump_kernel(const COL *__restrict__ K, const uint32_t *__restrict__ polys,
 #ifndef CHOL_CPU_EMU  // the launchers are not part of the CPU emulation (tests/emu)
 using namespace chol;
 
-// A/B hooks (tests, scripts/rng_final.py): generation 0 = read-back stores, 1 = register stores;
+// A/B hooks (tests, scripts/rng_final.py): generation 0 = read-back stores, 1 = register stores, 2 = four segments per warp;
 // jump 0 = 16 segments per CTA (192 threads x 128-bit columns), 1 / 2 / 3 = 32 / 48 / 64 (384 threads x 64-bit columns)
-static int g_gen_variant = 0, g_jump_variant = 2;
+static int g_gen_variant = 2, g_jump_variant = 0;
 extern "C" void chol_dsfmt_set_variant(int gen, int jump) {
   if (gen >= 0) g_gen_variant = gen;
   if (jump >= 0) g_jump_variant = jump;
@@ -314,7 +417,10 @@ extern "C" int chol_dsfmt_generate_launch(const void *states, unsigned long long
   cudaStream_t st = (cudaStream_t)stream;
 #define DS_LAUNCH(KIND)                                                                                                       \
   do {                                                                                                                        \
-    if (g_gen_variant == 1)                                                                                                   \
+    if (g_gen_variant == 2)                                                                                                   \
+      dsfmt_generate8_kernel<KIND><<<dim3((unsigned)((nseg + G8_WARPS * 4 - 1) / (G8_WARPS * 4))), G8_WARPS * 32, 0, st>>>(   \
+          (const W128 *)states, refill0, seg_refills, nseg, w_begin, w_end, (unsigned long long *)out, n_out, (W128 *)snap);  \
+    else if (g_gen_variant == 1)                                                                                              \
       dsfmt_generate_kernel<KIND, true><<<grid, GEN_WARPS * 32, 0, st>>>((const W128 *)states, refill0, seg_refills, nseg,    \
                                                                         w_begin, w_end, (unsigned long long *)out, n_out,    \
                                                                         (W128 *)snap);                                       \

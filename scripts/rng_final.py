@@ -1,6 +1,6 @@
 """One process, one GPU call: the device generator's GPU parity tests (pytest in-process, once per candidate jump variant),
-then its timing over the variants - generation (read-back / register stores) x jump tile (16 / 32 / 48 / 64 segments per
-CTA) x segment-length bias x request size - with the jump / generation split from the library's own events
+then its timing over the variants - generation (0 read-back, 1 register stores, 2 four segments per warp) x jump tile
+(0 / 1 / 2 / 3 = 16 / 32 / 48 / 64 segments per CTA) x segment-length bias (RNG_CONFIGS = gen:jump:bias,...) x request size - with the jump / generation split from the library's own events
 (cuRng64Profile).  Every timed configuration is also compared with the oracle on its first 2^20 values.
 Prints one JSON line per configuration."""
 import json
@@ -21,10 +21,11 @@ from cholesky_b200_loader import load  # noqa: E402
 
 chol = load()
 rc = 0
-for jump in [int(x) for x in os.environ.get("RNG_TEST_JUMPS", "2,3").split(",") if x != ""]:
-    chol.dsfmt_set_variant(0, jump)
+for gj in [x for x in os.environ.get("RNG_TEST_VARIANTS", "2:0").split(",") if x != ""]:
+    gen, jump = (int(v) for v in gj.split(":"))
+    chol.dsfmt_set_variant(gen, jump)
     r = int(pytest.main(["-q", "-x", "-p", "no:cacheprovider", os.path.join(ROOT, "tests", "test_zz_gpu_rng.py")]))
-    print(json.dumps({"what": "pytest tests/test_zz_gpu_rng.py", "gen": 0, "jump": jump, "rc": r, "elapsed_s": time.time() - t_start}), flush=True)
+    print(json.dumps({"what": "pytest tests/test_zz_gpu_rng.py", "gen": gen, "jump": jump, "rc": r, "elapsed_s": time.time() - t_start}), flush=True)
     rc = rc or r
 
 deadline = t_start + float(os.environ.get("RNG_FINAL_BUDGET_S", "40"))
@@ -34,7 +35,7 @@ g = chol.Rng64()
 g.set(H.SEED)
 g.profile(True)
 buf = torch.empty(max(sizes), dtype=torch.float64, device="cuda")
-configs = [(0, j, b) for b in (0, 1, -1) for j in (2, 3, 1, 0)] + [(1, 2, 0), (1, 3, 0)]
+configs = [tuple(int(v) for v in c.split(":")) for c in os.environ.get("RNG_CONFIGS", "2:0:0,2:0:1,1:0:0,2:0:2,2:0:-1").split(",")]
 for n in sizes:
     for gen, jump, bias in configs:
         if time.time() > deadline:

@@ -98,13 +98,14 @@ inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst
 
 // all 32 lanes of the warp must call (full-mask use only, as in the kernels)
 template <typename T>
-inline T __shfl_sync(unsigned, T v, int src) {
+inline T __shfl_sync(unsigned, T v, int src, int width = 32) {  // width: power of two; lanes exchange inside their sub-group
   static_assert(sizeof(T) <= 16, "shuffle payload");
   emu::Warp &w = emu::current()->warps[threadIdx.x >> 5];
-  std::memcpy(w.slot[threadIdx.x & 31], &v, sizeof(T));
+  const int lane = (int)(threadIdx.x & 31);
+  std::memcpy(w.slot[lane], &v, sizeof(T));
   w.bar.wait();
   T r;
-  std::memcpy(&r, w.slot[src & 31], sizeof(T));
+  std::memcpy(&r, w.slot[(lane & ~(width - 1)) | (src & (width - 1))], sizeof(T));
   w.bar.wait();
   return r;
 }
@@ -112,9 +113,9 @@ template <typename T>
 inline T __shfl_xor_sync(unsigned m, T v, int lanemask) { return __shfl_sync(m, v, (int)((threadIdx.x & 31) ^ lanemask)); }
 // lanes below `delta` get their own value back, as on the device
 template <typename T>
-inline T __shfl_up_sync(unsigned m, T v, unsigned delta) {
-  const int lane = (int)(threadIdx.x & 31);
-  return __shfl_sync(m, v, lane >= (int)delta ? lane - (int)delta : lane);
+inline T __shfl_up_sync(unsigned m, T v, unsigned delta, int width = 32) {
+  const int sub = (int)(threadIdx.x & 31) & (width - 1);
+  return __shfl_sync(m, v, sub >= (int)delta ? sub - (int)delta : sub, width);
 }
 
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }

@@ -42,6 +42,19 @@ static std::vector<uint64_t> oracle_window(uint64_t seed, unsigned long long w_b
 }
 
 static bool reg_store = false;  // which generation variant run_generate launches
+static bool groups_of_8 = false;
+
+static void run_generate8(int kind, const W128 *states, unsigned long long refill0, unsigned seg, int nseg, unsigned long long w0,
+                          unsigned long long w1, unsigned long long *out, unsigned long long n_out, W128 *snap) {
+  const dim3 grid((nseg + G8_WARPS * 4 - 1) / (G8_WARPS * 4)), block(G8_WARPS * 32);
+  switch (kind) {
+    case 0: emu::launch(grid, block, 0, [&] { dsfmt_generate8_kernel<0>(states, refill0, seg, nseg, w0, w1, out, n_out, snap); }); break;
+    case 1: emu::launch(grid, block, 0, [&] { dsfmt_generate8_kernel<1>(states, refill0, seg, nseg, w0, w1, out, n_out, snap); }); break;
+    case 2: emu::launch(grid, block, 0, [&] { dsfmt_generate8_kernel<2>(states, refill0, seg, nseg, w0, w1, out, n_out, snap); }); break;
+    case 3: emu::launch(grid, block, 0, [&] { dsfmt_generate8_kernel<3>(states, refill0, seg, nseg, w0, w1, out, n_out, snap); }); break;
+    default: emu::launch(grid, block, 0, [&] { dsfmt_generate8_kernel<4>(states, refill0, seg, nseg, w0, w1, out, n_out, snap); }); break;
+  }
+}
 
 template <bool RS>
 static void run_generate_t(int kind, const W128 *states, unsigned long long refill0, unsigned seg, int nseg, unsigned long long w0,
@@ -57,7 +70,8 @@ static void run_generate_t(int kind, const W128 *states, unsigned long long refi
 }
 static void run_generate(int kind, const W128 *states, unsigned long long refill0, unsigned seg, int nseg, unsigned long long w0,
                          unsigned long long w1, unsigned long long *out, unsigned long long n_out, W128 *snap) {
-  if (reg_store) run_generate_t<true>(kind, states, refill0, seg, nseg, w0, w1, out, n_out, snap);
+  if (groups_of_8) run_generate8(kind, states, refill0, seg, nseg, w0, w1, out, n_out, snap);
+  else if (reg_store) run_generate_t<true>(kind, states, refill0, seg, nseg, w0, w1, out, n_out, snap);
   else run_generate_t<false>(kind, states, refill0, seg, nseg, w0, w1, out, n_out, snap);
 }
 
@@ -72,9 +86,10 @@ int main() {
   state_t s0;
   chol_dsfmt_seed_state(seed, s0);
 
-  for (int variant = 0; variant < 2; ++variant) {
+  for (int variant = 0; variant < 3; ++variant) {
   reg_store = variant == 1;
-  std::printf("== generation kernel, %s ==\n", reg_store ? "stores from registers inside the round" : "read-back stores");
+  groups_of_8 = variant == 2;
+  std::printf("== generation kernel, %s ==\n", groups_of_8 ? "four segments per warp (groups of 8 lanes)" : reg_store ? "stores from registers inside the round" : "read-back stores");
   // ---- 1. one segment from the seed state: the warp-parallel refill against the oracle, every output kind ----
   for (int kind = 0; kind < 5; ++kind) {
     const unsigned refills = 4;
@@ -147,6 +162,7 @@ int main() {
 
   }  // generation variants
   reg_store = false;
+  groups_of_8 = true;  // the jump checks below continue the stream with this variant
 
   // ---- 4. the jump kernel: start states as GF(2) combinations of the Krylov block, with the product's own polynomial rows ----
   for (int jv = 0; jv < 4; ++jv) {
