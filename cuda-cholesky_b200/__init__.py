@@ -319,12 +319,6 @@ class Rng64:
         return j.value, g.value, s.value, l.value
 
 
-def dsfmt_set_variant(gen=-1, jump=-1):
-    """A/B hook of csrc/rng_dsfmt.cu (process-wide): generation 0 = read-back stores, 1 = register stores; jump 0 / 1 / 2 / 3 =
-    16 / 32 / 48 / 64 segments per CTA; -1 leaves a setting as it is."""
-    lib().chol_dsfmt_set_variant(C.c_int(gen), C.c_int(jump))
-
-
 # ---------------------------------------------------------------------------------------------
 # multi-GPU: the reference's host-pointer API (one process, one worker thread per GPU) ...
 # ---------------------------------------------------------------------------------------------

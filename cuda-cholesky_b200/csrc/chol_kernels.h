@@ -133,10 +133,6 @@ int chol_dsfmt_generate_launch(const void *states, unsigned long long refill0, u
                                unsigned long long w_begin, unsigned long long w_end, void *out, unsigned long long n_out,
                                int kind, void *snap, void *stream);
 
-/* A/B hook (process-wide; -1 keeps a setting): generation kernel 0 = read-back stores, 1 = stores from registers; jump kernel
- * 0 / 1 / 2 / 3 = 16 / 32 / 48 / 64 segments per CTA */
-void chol_dsfmt_set_variant(int gen, int jump);
-
 /* number of kernels launched by the library so far (optionally resetting the counter) */
 unsigned long long chol_launch_count(int reset);
 

@@ -41,6 +41,9 @@ constexpr unsigned long long DS_MSK2 = 0x000ffdfffc90fffdULL;
 constexpr int DS_STATE_WORDS = DS_N + 1;        // with the lung
 constexpr int DS_STATE_U32 = DS_STATE_WORDS * 4;  // 768
 constexpr int GEN_WARPS = 4;                    // segments per CTA of the generation kernel
+constexpr int JUMP_THREADS = DS_STATE_WORDS;    // one 128-bit column of the state per thread (6 warps)
+constexpr int JUMP_GT = 16;                     // segments per CTA of the jump kernel
+constexpr int JUMP_BATCH = 8;                   // K rows a thread holds in registers (and as many in flight)
 
 struct __align__(16) W128 {
   unsigned long long lo, hi;
@@ -166,14 +169,7 @@ __device__ __forceinline__ void dsfmt_refill_warp(W128 *st, W128 &lung, int lane
 // [w_begin, w_end) are converted and stored: word t -> elements 2 (t - w_begin), 2 (t - w_begin) + 1 of `out`
 // (the last one only if it is < n_out).  snap != NULL (Krylov mode, one segment): the raw state after refill r is
 // stored at snap[(r + 1) * 192 ...] instead, nothing goes to `out`.
-struct EmitNone {
-  __device__ __forceinline__ void operator()(int, W128) const {}
-};
-
-// REGSTORE = false: the refill's words are read back from shared memory and stored by consecutive lanes (512
-// contiguous bytes per store instruction); true: every lane stores its own two words straight from registers inside
-// the round (measured slower on B200: 1.33 vs 0.62 us per refill, profiles/r02_call20_summary.txt).
-template <int KIND, bool REGSTORE>
+template <int KIND>
 __global__ void __launch_bounds__(GEN_WARPS * 32)
 dsfmt_generate_kernel(const W128 *__restrict__ states, unsigned long long refill0, unsigned seg_refills, int nseg,
                       unsigned long long w_begin, unsigned long long w_end, unsigned long long *__restrict__ out,
@@ -196,182 +192,46 @@ dsfmt_generate_kernel(const W128 *__restrict__ states, unsigned long long refill
       W128 *dst = snap + (size_t)(r + 1) * DS_STATE_WORDS;
       dsfmt_refill_warp(st, lung, lane, EmitSnapshot{dst});
       if (lane == 0) dst[DS_N] = lung;
-      continue;
-    }
-    if (t0 >= w_end) break;
-    const EmitWindow<KIND> emit{t0, w_begin, w_end, n_out, out, aligned16};
-    if (REGSTORE) {
-      dsfmt_refill_warp(st, lung, lane, emit);
     } else {
-      dsfmt_refill_warp(st, lung, lane, EmitNone{});
-      if (t0 + DS_N <= w_begin) continue;  // before the window: the state only moves on
-#pragma unroll 2
-      for (int i = lane; i < DS_N; i += 32) emit(i, st[i]);
-      __syncwarp();  // the read-back reads st; the next refill overwrites it
+      if (t0 >= w_end) break;
+      dsfmt_refill_warp(st, lung, lane, EmitWindow<KIND>{t0, w_begin, w_end, n_out, out, aligned16});
     }
-  }
-}
-
-// ---- generation, four segments per warp: a group of 8 lanes owns one segment, lane a the 8 consecutive steps
-// c0 + 8a .. c0 + 8a + 7 of a 64-step round.  Eight steps leave the lung as lung ^ P(x0 ^ x2 ^ x4 ^ x6) ^ (x1 ^ x3 ^ x5 ^ x7),
-// so the scan is 3 steps inside the group instead of 5 across the warp, one shuffle instruction serves four segments,
-// and a lane's 8 words are 128 contiguous bytes of the stream.  Shared-memory slot of word i: the low three bits are
-// XORed with bits 3..5 (both "lanes read 8a + k" and "lanes read 8k' + a" hit distinct banks).
-constexpr int G8_WARPS = 2;
-__device__ __forceinline__ int g8_slot(int i) { return (i & ~7) | ((i ^ (i >> 3)) & 7); }
-__device__ __forceinline__ W128 shfl_up_w8(W128 v, int d) {
-  W128 r;
-  r.lo = __shfl_up_sync(0xffffffffu, v.lo, d, 8);
-  r.hi = __shfl_up_sync(0xffffffffu, v.hi, d, 8);
-  return r;
-}
-__device__ __forceinline__ W128 shfl_w8(W128 v, int src) {
-  W128 r;
-  r.lo = __shfl_sync(0xffffffffu, v.lo, src, 8);
-  r.hi = __shfl_sync(0xffffffffu, v.hi, src, 8);
-  return r;
-}
-
-template <int KIND>
-__global__ void __launch_bounds__(G8_WARPS * 32)
-dsfmt_generate8_kernel(const W128 *__restrict__ states, unsigned long long refill0, unsigned seg_refills, int nseg,
-                       unsigned long long w_begin, unsigned long long w_end, unsigned long long *__restrict__ out,
-                       unsigned long long n_out, W128 *__restrict__ snap) {
-  __shared__ W128 smem[G8_WARPS * 4][DS_STATE_WORDS];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, grp = lane >> 3, l8 = lane & 7;
-  const int g_first = (blockIdx.x * G8_WARPS + wid) * 4;
-  if (g_first >= nseg) return;  // whole warps leave; no block-wide barrier below
-  const bool live = g_first + grp < nseg;
-  const int g = live ? g_first + grp : nseg - 1;  // a group without a segment shadows the last one and stores nothing
-  W128 *st = smem[wid * 4 + grp];
-  const W128 *src = states + (size_t)g * DS_STATE_WORDS;
-  for (int i = l8; i < DS_N; i += 8) st[g8_slot(i)] = src[i];
-  W128 lung = src[DS_N];
-  __syncwarp();
-  const unsigned long long r_begin = refill0 + (unsigned long long)g * seg_refills;
-  const unsigned long long r_warp = refill0 + (unsigned long long)g_first * seg_refills;  // the warp's earliest segment
-  const bool aligned16 = (((size_t)out) & 15) == 0;
-  for (unsigned k = 0; k < seg_refills; ++k) {
-    const unsigned long long t0 = (r_begin + k) * DS_N;  // first stream word of this refill
-    if (snap == nullptr && (r_warp + k) * DS_N >= w_end) break;  // uniform: later groups are later in the stream
-    const EmitWindow<KIND> window{t0, w_begin, w_end, n_out, out, aligned16};
-    W128 *dst = snap != nullptr ? snap + (size_t)(r_begin + k + 1) * DS_STATE_WORDS : nullptr;
-#pragma unroll 1
-    for (int c0 = 0; c0 < DS_N; c0 += 64) {
-      const int base = c0 + 8 * l8;
-      const int cnt = min(8, DS_N - base);  // 7 for the last lane of the last round, else 8
-      W128 s[8], x[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s[j] = W128{0, 0};
-        x[j] = W128{0, 0};
-        if (j < cnt) {
-          const int i = base + j;
-          int b = i + DS_POS1;
-          if (b >= DS_N) b -= DS_N;
-          s[j] = st[g8_slot(i)];
-          x[j] = mix_in(s[j], st[g8_slot(b)]);
-        }
-      }
-      const W128 c = perm(x[0] ^ x[2] ^ x[4] ^ x[6]) ^ (x[1] ^ x[3] ^ x[5] ^ x[7]);
-      W128 incl = c;
-#pragma unroll
-      for (int d = 1; d < 8; d <<= 1) {
-        const W128 up = shfl_up_w8(incl, d);
-        if (l8 >= d) incl = incl ^ up;
-      }
-      W128 y = lung ^ incl ^ c;  // the lung entering this lane's first step
-      W128 y_last = y;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        y = perm(y) ^ x[j];
-        if (j < cnt) {
-          s[j] = mix_out(y, s[j]);  // the new word
-          st[g8_slot(base + j)] = s[j];
-          y_last = y;
-        }
-      }
-      lung = shfl_w8(y_last, 7);
-      if (live) {
-        const unsigned long long tb = t0 + (unsigned)base;  // this lane's words are stream words tb .. tb + cnt - 1
-        if (dst != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (j < cnt) dst[base + j] = s[j];
-        } else if (aligned16 && tb >= w_begin && tb + cnt <= w_end && 2 * (tb + cnt - w_begin) <= n_out) {
-          ulonglong2 *p = reinterpret_cast<ulonglong2 *>(out + 2 * (tb - w_begin));  // all of them inside the request: 128 contiguous bytes
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (j < cnt) p[j] = make_ulonglong2(ds_convert<KIND>(s[j].lo), ds_convert<KIND>(s[j].hi));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)  // a request boundary inside these words (unrolled: s stays in registers)
-            if (j < cnt) window(base + j, s[j]);
-        }
-      }
-      __syncwarp();  // the next round reads words this round wrote (s[i-74]) from other lanes
-    }
-    if (dst != nullptr && live && l8 == 0) dst[DS_N] = lung;
   }
 }
 
 // states[g][:] ^= XOR over the rows i of this CTA's slice of [0, D) with bit i of polys[g] set of K[i][:]
-// (K: D states of 3072 bytes; polys: nseg rows of poly_u32 32-bit words; states zeroed by the caller when
-// gridDim.y > 1).  grid.x = tiles of GT segments, grid.y = slices of the row range (whole 32-bit words of the
-// polynomials).  A thread owns one column (COL = uint4 or uint2) of the state for all GT segments of the tile and
-// streams the K rows through registers BATCH at a time, the next BATCH already in flight.  The table lives in L2 and a
-// row is read once per CTA, i.e. once per GT segments: measured on B200 the kernel is bound by exactly that traffic
-// (61 MB per tile at 2.1 TB/s = 29 us / GT per segment), so GT is as large as the register file allows.
-template <typename COL> struct ColOps;
-template <> struct ColOps<uint4> {
-  static __device__ __forceinline__ uint4 zero() { return make_uint4(0u, 0u, 0u, 0u); }
-  static __device__ __forceinline__ void xor_into(uint4 &a, const uint4 &k) { a.x ^= k.x; a.y ^= k.y; a.z ^= k.z; a.w ^= k.w; }
-  static __device__ __forceinline__ void flush(uint32_t *dst, const uint4 &a, bool atomic) {
-    if (!atomic) { *reinterpret_cast<uint4 *>(dst) = a; return; }
-    if (a.x) atomicXor(dst + 0, a.x);
-    if (a.y) atomicXor(dst + 1, a.y);
-    if (a.z) atomicXor(dst + 2, a.z);
-    if (a.w) atomicXor(dst + 3, a.w);
-  }
-};
-template <> struct ColOps<uint2> {
-  static __device__ __forceinline__ uint2 zero() { return make_uint2(0u, 0u); }
-  static __device__ __forceinline__ void xor_into(uint2 &a, const uint2 &k) { a.x ^= k.x; a.y ^= k.y; }
-  static __device__ __forceinline__ void flush(uint32_t *dst, const uint2 &a, bool atomic) {
-    if (!atomic) { *reinterpret_cast<uint2 *>(dst) = a; return; }
-    if (a.x) atomicXor(dst + 0, a.x);
-    if (a.y) atomicXor(dst + 1, a.y);
-  }
-};
+// (K: D states of 192 128-bit words; polys: nseg rows of poly_u32 32-bit words; states zeroed by the caller when
+// gridDim.y > 1).  grid.x = tiles of JUMP_GT segments, grid.y = slices of the row range (whole 32-bit words of the
+// polynomials).  A thread owns one 128-bit column of the state for all JUMP_GT segments (64 accumulator registers) and
+// streams the K rows through registers eight at a time, the next eight already in flight (the table lives in L2; one
+// row is read once per CTA, i.e. once per JUMP_GT segments).
+__device__ __forceinline__ void jump_load_rows(uint4 (&k)[JUMP_BATCH], const uint4 *__restrict__ K, int row0, int D, int t) {
+#pragma unroll
+  for (int j = 0; j < JUMP_BATCH; ++j)
+    k[j] = (row0 + j < D) ? K[(size_t)(row0 + j) * DS_STATE_WORDS + t] : make_uint4(0u, 0u, 0u, 0u);
+}
 
-template <int THREADS, int GT, int BATCH, typename COL>
-__global__ void __launch_bounds__(THREADS)
-dsfmt_jump_kernel(const COL *__restrict__ K, const uint32_t *__restrict__ polys, int poly_u32, int D,
+__global__ void __launch_bounds__(JUMP_THREADS)
+dsfmt_jump_kernel(const uint4 *__restrict__ K, const uint32_t *__restrict__ polys, int poly_u32, int D,
                   uint32_t *__restrict__ states, int nseg) {
-  static_assert(THREADS * sizeof(COL) == DS_STATE_WORDS * 16, "one column per thread covers the state");
-  static_assert(32 % BATCH == 0, "a batch lies inside one polynomial word");
-  __shared__ uint32_t bits[GT][32];  // one 1024-row stretch of every segment's polynomial at a time
+  __shared__ uint32_t bits[JUMP_GT][32];  // one 1024-row stretch of every segment's polynomial at a time
   const int t = threadIdx.x;
-  const int g0 = blockIdx.x * GT;
+  const int g0 = blockIdx.x * JUMP_GT;
   const int words = (D + 31) / 32;
   const int per = (words + gridDim.y - 1) / gridDim.y;
   const int w_lo = blockIdx.y * per, w_hi = min(words, w_lo + per);
-  COL acc[GT];
+  uint4 acc[JUMP_GT];
 #pragma unroll
-  for (int g = 0; g < GT; ++g) acc[g] = ColOps<COL>::zero();
+  for (int g = 0; g < JUMP_GT; ++g) acc[g] = make_uint4(0u, 0u, 0u, 0u);
   const int r_lo = w_lo * 32, r_hi = min(D, w_hi * 32);
-  COL kc[BATCH], kn[BATCH];
-  auto load_rows = [&](COL (&k)[BATCH], int row0) {
-#pragma unroll
-    for (int j = 0; j < BATCH; ++j) k[j] = (row0 + j < D) ? K[(size_t)(row0 + j) * THREADS + t] : ColOps<COL>::zero();
-  };
-  if (r_lo < r_hi) load_rows(kc, r_lo);
-  for (int rb = r_lo; rb < r_hi; rb += BATCH) {
-    if (rb + BATCH < r_hi) load_rows(kn, rb + BATCH);  // in flight while this batch is applied
+  uint4 kc[JUMP_BATCH], kn[JUMP_BATCH];
+  if (r_lo < r_hi) jump_load_rows(kc, K, r_lo, D, t);
+  for (int rb = r_lo; rb < r_hi; rb += JUMP_BATCH) {
+    if (rb + JUMP_BATCH < r_hi) jump_load_rows(kn, K, rb + JUMP_BATCH, D, t);  // in flight while this batch is applied
     const int w = rb >> 5;
     if (((w - w_lo) & 31) == 0 && (rb & 31) == 0) {  // a new 1024-row stretch: stage its polynomial words
       __syncthreads();
-      for (int e = t; e < GT * 32; e += THREADS) {
+      for (int e = t; e < JUMP_GT * 32; e += JUMP_THREADS) {
         const int g = e >> 5, ww = w + (e & 31);
         bits[g][e & 31] = (g0 + g < nseg && ww < w_hi && ww < poly_u32) ? polys[(size_t)(g0 + g) * poly_u32 + ww] : 0u;
       }
@@ -379,19 +239,32 @@ dsfmt_jump_kernel(const COL *__restrict__ K, const uint32_t *__restrict__ polys,
     }
     const int wi = (w - w_lo) & 31, sh = rb & 31;
 #pragma unroll
-    for (int g = 0; g < GT; ++g) {
+    for (int g = 0; g < JUMP_GT; ++g) {
       const uint32_t m = bits[g][wi] >> sh;  // bit j = row rb + j (rows beyond D have zero bits: deg a < D)
 #pragma unroll
-      for (int j = 0; j < BATCH; ++j)
-        if ((m >> j) & 1u) ColOps<COL>::xor_into(acc[g], kc[j]);
+      for (int j = 0; j < JUMP_BATCH; ++j)
+        if ((m >> j) & 1u) {
+          acc[g].x ^= kc[j].x;
+          acc[g].y ^= kc[j].y;
+          acc[g].z ^= kc[j].z;
+          acc[g].w ^= kc[j].w;
+        }
     }
 #pragma unroll
-    for (int j = 0; j < BATCH; ++j) kc[j] = kn[j];
+    for (int j = 0; j < JUMP_BATCH; ++j) kc[j] = kn[j];
   }
 #pragma unroll
-  for (int g = 0; g < GT; ++g) {
+  for (int g = 0; g < JUMP_GT; ++g) {
     if (g0 + g >= nseg) break;
-    ColOps<COL>::flush(states + (size_t)(g0 + g) * DS_STATE_U32 + (sizeof(COL) / 4) * t, acc[g], gridDim.y != 1);
+    uint32_t *dst = states + (size_t)(g0 + g) * DS_STATE_U32 + 4 * t;
+    if (gridDim.y == 1) {
+      *reinterpret_cast<uint4 *>(dst) = acc[g];
+    } else {
+      if (acc[g].x) atomicXor(dst + 0, acc[g].x);
+      if (acc[g].y) atomicXor(dst + 1, acc[g].y);
+      if (acc[g].z) atomicXor(dst + 2, acc[g].z);
+      if (acc[g].w) atomicXor(dst + 3, acc[g].w);
+    }
   }
 }
 
@@ -400,14 +273,6 @@ dsfmt_jump_kernel(const COL *__restrict__ K, const uint32_t *__restrict__ polys,
 #ifndef CHOL_CPU_EMU  // the launchers are not part of the CPU emulation (tests/emu)
 using namespace chol;
 
-// A/B hooks (tests, scripts/rng_final.py): generation 0 = read-back stores, 1 = register stores, 2 = four segments per warp;
-// jump 0 = 16 segments per CTA (192 threads x 128-bit columns), 1 / 2 / 3 = 32 / 48 / 64 (384 threads x 64-bit columns)
-static int g_gen_variant = 2, g_jump_variant = 0;
-extern "C" void chol_dsfmt_set_variant(int gen, int jump) {
-  if (gen >= 0) g_gen_variant = gen;
-  if (jump >= 0) g_jump_variant = jump;
-}
-
 extern "C" int chol_dsfmt_generate_launch(const void *states, unsigned long long refill0, unsigned seg_refills, int nseg,
                                           unsigned long long w_begin, unsigned long long w_end, void *out,
                                           unsigned long long n_out, int kind, void *snap, void *stream) {
@@ -415,20 +280,9 @@ extern "C" int chol_dsfmt_generate_launch(const void *states, unsigned long long
   if (snap != nullptr && nseg != 1) return (int)cudaErrorInvalidValue;
   const dim3 grid((unsigned)((nseg + GEN_WARPS - 1) / GEN_WARPS));
   cudaStream_t st = (cudaStream_t)stream;
-#define DS_LAUNCH(KIND)                                                                                                       \
-  do {                                                                                                                        \
-    if (g_gen_variant == 2)                                                                                                   \
-      dsfmt_generate8_kernel<KIND><<<dim3((unsigned)((nseg + G8_WARPS * 4 - 1) / (G8_WARPS * 4))), G8_WARPS * 32, 0, st>>>(   \
-          (const W128 *)states, refill0, seg_refills, nseg, w_begin, w_end, (unsigned long long *)out, n_out, (W128 *)snap);  \
-    else if (g_gen_variant == 1)                                                                                              \
-      dsfmt_generate_kernel<KIND, true><<<grid, GEN_WARPS * 32, 0, st>>>((const W128 *)states, refill0, seg_refills, nseg,    \
-                                                                        w_begin, w_end, (unsigned long long *)out, n_out,    \
-                                                                        (W128 *)snap);                                       \
-    else                                                                                                                      \
-      dsfmt_generate_kernel<KIND, false><<<grid, GEN_WARPS * 32, 0, st>>>((const W128 *)states, refill0, seg_refills, nseg,   \
-                                                                         w_begin, w_end, (unsigned long long *)out, n_out,   \
-                                                                         (W128 *)snap);                                      \
-  } while (0)
+#define DS_LAUNCH(KIND)                                                                                                  \
+  dsfmt_generate_kernel<KIND><<<grid, GEN_WARPS * 32, 0, st>>>((const W128 *)states, refill0, seg_refills, nseg, w_begin, \
+                                                              w_end, (unsigned long long *)out, n_out, (W128 *)snap)
   switch (kind) {
     case DS_RAW: DS_LAUNCH(DS_RAW); break;
     case DS_CLOSE_OPEN: DS_LAUNCH(DS_CLOSE_OPEN); break;
@@ -442,34 +296,23 @@ extern "C" int chol_dsfmt_generate_launch(const void *states, unsigned long long
   return (int)cudaGetLastError();
 }
 
-template <int THREADS, int GT, int BATCH, typename COL>
-static int jump_launch_t(const void *K, const void *polys, int poly_u32, int D, void *states, int nseg, cudaStream_t st) {
-  const unsigned gx = (unsigned)((nseg + GT - 1) / GT);
-  // enough CTAs to fill the 148 SMs (twice for the small-tile variant) when there are few segments
+extern "C" int chol_dsfmt_jump_launch(const void *K, const void *polys, int poly_u32, int D, void *states, int nseg,
+                                      void *stream) {
+  if (nseg <= 0 || D <= 0 || poly_u32 * 32 < D) return (int)cudaErrorInvalidValue;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned gx = (unsigned)((nseg + JUMP_GT - 1) / JUMP_GT);
+  // enough CTAs to fill the 148 SMs twice when there are few segments; slices are whole 1024-bit stretches
   const unsigned stretches = (unsigned)((D + 1023) / 1024);
-  const unsigned want = THREADS <= 192 ? 2 * 148 : 148;
-  unsigned gy = (want + gx - 1) / gx;
+  unsigned gy = (2 * 148 + gx - 1) / gx;
   if (gy > stretches) gy = stretches;
   if (gy < 1) gy = 1;
   if (gy > 1) {
     cudaError_t e = cudaMemsetAsync(states, 0, (size_t)nseg * DS_STATE_U32 * sizeof(uint32_t), st);
     if (e != cudaSuccess) return (int)e;
   }
-  dsfmt_jump_kernel<THREADS, GT, BATCH, COL><<<dim3(gx, gy), THREADS, 0, st>>>((const COL *)K, (const uint32_t *)polys, poly_u32, D,
-                                                                             (uint32_t *)states, nseg);
+  dsfmt_jump_kernel<<<dim3(gx, gy), JUMP_THREADS, 0, st>>>((const uint4 *)K, (const uint32_t *)polys, poly_u32, D,
+                                                          (uint32_t *)states, nseg);
   CHOL_COUNT_LAUNCH();
   return (int)cudaGetLastError();
-}
-
-extern "C" int chol_dsfmt_jump_launch(const void *K, const void *polys, int poly_u32, int D, void *states, int nseg,
-                                      void *stream) {
-  if (nseg <= 0 || D <= 0 || poly_u32 * 32 < D) return (int)cudaErrorInvalidValue;
-  cudaStream_t st = (cudaStream_t)stream;
-  switch (g_jump_variant) {
-    case 0: return jump_launch_t<192, 16, 8, uint4>(K, polys, poly_u32, D, states, nseg, st);
-    case 1: return jump_launch_t<384, 32, 8, uint2>(K, polys, poly_u32, D, states, nseg, st);
-    case 3: return jump_launch_t<384, 64, 4, uint2>(K, polys, poly_u32, D, states, nseg, st);
-    default: return jump_launch_t<384, 48, 8, uint2>(K, polys, poly_u32, D, states, nseg, st);
-  }
 }
 #endif  // CHOL_CPU_EMU

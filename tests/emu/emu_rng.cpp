@@ -41,44 +41,16 @@ static std::vector<uint64_t> oracle_window(uint64_t seed, unsigned long long w_b
   return out;
 }
 
-static bool reg_store = false;  // which generation variant run_generate launches
-static bool groups_of_8 = false;
-
-static void run_generate8(int kind, const W128 *states, unsigned long long refill0, unsigned seg, int nseg, unsigned long long w0,
-                          unsigned long long w1, unsigned long long *out, unsigned long long n_out, W128 *snap) {
-  const dim3 grid((nseg + G8_WARPS * 4 - 1) / (G8_WARPS * 4)), block(G8_WARPS * 32);
-  switch (kind) {
-    case 0: emu::launch(grid, block, 0, [&] { dsfmt_generate8_kernel<0>(states, refill0, seg, nseg, w0, w1, out, n_out, snap); }); break;
-    case 1: emu::launch(grid, block, 0, [&] { dsfmt_generate8_kernel<1>(states, refill0, seg, nseg, w0, w1, out, n_out, snap); }); break;
-    case 2: emu::launch(grid, block, 0, [&] { dsfmt_generate8_kernel<2>(states, refill0, seg, nseg, w0, w1, out, n_out, snap); }); break;
-    case 3: emu::launch(grid, block, 0, [&] { dsfmt_generate8_kernel<3>(states, refill0, seg, nseg, w0, w1, out, n_out, snap); }); break;
-    default: emu::launch(grid, block, 0, [&] { dsfmt_generate8_kernel<4>(states, refill0, seg, nseg, w0, w1, out, n_out, snap); }); break;
-  }
-}
-
-template <bool RS>
-static void run_generate_t(int kind, const W128 *states, unsigned long long refill0, unsigned seg, int nseg, unsigned long long w0,
-                           unsigned long long w1, unsigned long long *out, unsigned long long n_out, W128 *snap) {
-  const dim3 grid((nseg + GEN_WARPS - 1) / GEN_WARPS), block(GEN_WARPS * 32);
-  switch (kind) {
-    case 0: emu::launch(grid, block, 0, [&] { dsfmt_generate_kernel<0, RS>(states, refill0, seg, nseg, w0, w1, out, n_out, snap); }); break;
-    case 1: emu::launch(grid, block, 0, [&] { dsfmt_generate_kernel<1, RS>(states, refill0, seg, nseg, w0, w1, out, n_out, snap); }); break;
-    case 2: emu::launch(grid, block, 0, [&] { dsfmt_generate_kernel<2, RS>(states, refill0, seg, nseg, w0, w1, out, n_out, snap); }); break;
-    case 3: emu::launch(grid, block, 0, [&] { dsfmt_generate_kernel<3, RS>(states, refill0, seg, nseg, w0, w1, out, n_out, snap); }); break;
-    default: emu::launch(grid, block, 0, [&] { dsfmt_generate_kernel<4, RS>(states, refill0, seg, nseg, w0, w1, out, n_out, snap); }); break;
-  }
-}
 static void run_generate(int kind, const W128 *states, unsigned long long refill0, unsigned seg, int nseg, unsigned long long w0,
                          unsigned long long w1, unsigned long long *out, unsigned long long n_out, W128 *snap) {
-  if (groups_of_8) run_generate8(kind, states, refill0, seg, nseg, w0, w1, out, n_out, snap);
-  else if (reg_store) run_generate_t<true>(kind, states, refill0, seg, nseg, w0, w1, out, n_out, snap);
-  else run_generate_t<false>(kind, states, refill0, seg, nseg, w0, w1, out, n_out, snap);
-}
-
-template <int THREADS, int GT, int BATCH, typename COL>
-static void run_jump(const uint32_t *K, const uint32_t *polys, int poly_u32, int D, uint32_t *states, int nseg, unsigned gy) {
-  const dim3 grid((nseg + GT - 1) / GT, gy);
-  emu::launch(grid, dim3(THREADS), 0, [&] { dsfmt_jump_kernel<THREADS, GT, BATCH, COL>((const COL *)K, polys, poly_u32, D, states, nseg); });
+  const dim3 grid((nseg + GEN_WARPS - 1) / GEN_WARPS), block(GEN_WARPS * 32);
+  switch (kind) {
+    case 0: emu::launch(grid, block, 0, [&] { dsfmt_generate_kernel<0>(states, refill0, seg, nseg, w0, w1, out, n_out, snap); }); break;
+    case 1: emu::launch(grid, block, 0, [&] { dsfmt_generate_kernel<1>(states, refill0, seg, nseg, w0, w1, out, n_out, snap); }); break;
+    case 2: emu::launch(grid, block, 0, [&] { dsfmt_generate_kernel<2>(states, refill0, seg, nseg, w0, w1, out, n_out, snap); }); break;
+    case 3: emu::launch(grid, block, 0, [&] { dsfmt_generate_kernel<3>(states, refill0, seg, nseg, w0, w1, out, n_out, snap); }); break;
+    default: emu::launch(grid, block, 0, [&] { dsfmt_generate_kernel<4>(states, refill0, seg, nseg, w0, w1, out, n_out, snap); }); break;
+  }
 }
 
 int main() {
@@ -86,10 +58,6 @@ int main() {
   state_t s0;
   chol_dsfmt_seed_state(seed, s0);
 
-  for (int variant = 0; variant < 3; ++variant) {
-  reg_store = variant == 1;
-  groups_of_8 = variant == 2;
-  std::printf("== generation kernel, %s ==\n", groups_of_8 ? "four segments per warp (groups of 8 lanes)" : reg_store ? "stores from registers inside the round" : "read-back stores");
   // ---- 1. one segment from the seed state: the warp-parallel refill against the oracle, every output kind ----
   for (int kind = 0; kind < 5; ++kind) {
     const unsigned refills = 4;
@@ -160,13 +128,8 @@ int main() {
     std::printf("snapshot mode (Krylov rows): %s\n", ok ? "ok" : "MISMATCH");
   }
 
-  }  // generation variants
-  reg_store = false;
-  groups_of_8 = true;  // the jump checks below continue the stream with this variant
-
   // ---- 4. the jump kernel: start states as GF(2) combinations of the Krylov block, with the product's own polynomial rows ----
-  for (int jv = 0; jv < 4; ++jv) {
-    std::printf("== jump kernel variant %d ==\n", jv);
+  {
     int D = 0;
     unsigned gen = 0;
     if (chol_dsfmt_poly_ensure((const uint64_t(*)[2])s0, &D, &gen) != 0) {
@@ -182,7 +145,7 @@ int main() {
       chol_dsfmt_refill_host(cur);
     }
     const int poly_u32 = 2 * ((D + 63) / 64);
-    struct { int level; uint64_t j0; int nseg; unsigned gy; } jc[] = {{4, 3, 11, 3}, {6, 0, 8, 1}, {5, 700, 3, 20}, {4, 100, 101, 7}, {7, 1, 16, 14}};
+    struct { int level; uint64_t j0; int nseg; unsigned gy; } jc[] = {{4, 3, 11, 3}, {6, 0, 8, 1}, {5, 700, 3, 20}, {4, 100, 37, 7}, {7, 1, 16, 14}};
     for (auto &c : jc) {
       std::vector<uint32_t> polys((size_t)c.nseg * poly_u32);
       if (chol_dsfmt_poly_rows(gen, c.level, c.j0, (size_t)c.nseg, polys.data(), (size_t)poly_u32) != 0) {
@@ -190,12 +153,8 @@ int main() {
         return 1;
       }
       std::vector<uint32_t> states((size_t)c.nseg * DS_STATE_U32, c.gy > 1 ? 0u : 0xdeadbeefu);
-      switch (jv) {
-        case 0: run_jump<192, 16, 8, uint4>(K.data(), polys.data(), poly_u32, D, states.data(), c.nseg, c.gy); break;
-        case 1: run_jump<384, 32, 8, uint2>(K.data(), polys.data(), poly_u32, D, states.data(), c.nseg, c.gy); break;
-        case 2: run_jump<384, 48, 8, uint2>(K.data(), polys.data(), poly_u32, D, states.data(), c.nseg, c.gy); break;
-        default: run_jump<384, 64, 4, uint2>(K.data(), polys.data(), poly_u32, D, states.data(), c.nseg, c.gy); break;
-      }
+      const dim3 grid((c.nseg + JUMP_GT - 1) / JUMP_GT, c.gy);
+      emu::launch(grid, dim3(JUMP_THREADS), 0, [&] { dsfmt_jump_kernel((const uint4 *)K.data(), polys.data(), poly_u32, D, states.data(), c.nseg); });
       // direct: iterate the host refill to every segment start
       bool ok = true;
       std::memcpy(cur, s0, sizeof cur);

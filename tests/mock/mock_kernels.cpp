@@ -469,7 +469,6 @@ static uint64_t mock_convert(uint64_t w, int kind) {
   std::memcpy(&o, &r, 8);
   return o;
 }
-void chol_dsfmt_set_variant(int, int) {}
 int chol_dsfmt_jump_launch(const void *K, const void *polys, int poly_u32, int D, void *states, int nseg, void *st) {
   __sync_fetch_and_add(&launches, 1);
   if (nseg <= 0 || D <= 0 || poly_u32 * 32 < D) return 1;

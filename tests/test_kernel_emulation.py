@@ -85,11 +85,11 @@ def test_fp32_gemm_engine_emulated(emu):
 
 def test_device_dsfmt_kernels_emulated(emu):
     """csrc/rng_dsfmt.cu: the warp-parallel refill (64 steps per round through one warp scan), windowed conversion and store in
-    all five output forms (read-back and register-store variants), Krylov snapshots, and the GF(2) jump kernel in its four
-    tile shapes with the product's own polynomial rows - bit for bit against the oracle's sequential generator"""
+    all five output forms, Krylov snapshots, and the GF(2) jump kernel with the product's own polynomial rows - bit for bit
+    against the oracle's sequential generator"""
     out = _passed(emu, "emu_rng.cpp")
-    assert "78 cases, 0 mismatches" in out
-    assert out.count("identical to the oracle") >= 18  # both generation variants x 5 kinds, 4 jump variants x 2 continuations
+    assert "32 cases, 0 mismatches" in out
+    assert out.count("identical to the oracle") >= 7
 
 
 def test_fp64_tensor_core_engine_emulated(emu):
