@@ -162,9 +162,13 @@ def use_all_host_cores():
 
 
 def cpu_spd(n, k=KGEN):
+    """A = B*B^T + n*I with B (n x min(k, n), column-major) = u - 0.5 from the configs' generator, dSFMT-19937 seed SEED
+    (the oracle's restatement of the reference's rng/dsfmt_19937.c; this CPU leg is where bench.py may run oracle/ code)"""
     import numpy as np
-    rng = np.random.default_rng(SEED)
-    B = rng.random((n, min(k, n))) - 0.5
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import harness as H
+    k = min(k, n)
+    B = (H.dsfmt_uniform(SEED, n * k) - 0.5).reshape(k, n).T
     A = B @ B.T + n * np.eye(n)
     return np.asfortranarray(A)
 
@@ -212,7 +216,8 @@ def run_reference(args):
             "config": {"workload": "dpotrf lower N=%d, FP64 DMMA trailing update (BASELINE configs[1]/[4] family at the metric's N); "
                                    "this arm: CPU sample of order %d per step (N=%d would take hours)" % (args.n, n_s, args.n),
                        "N": args.n, "uplo": "L", "sample_N": n_s, "sample_resid": resid, "cpu_gflops_by_sample_N": rates,
-                       "generator": "numpy default_rng(%d).random - 0.5 (not dSFMT)" % SEED,
+                       "generator": "dSFMT-19937 seed %d (CPU, oracle/dsfmt_oracle.c = the reference's rng/dsfmt_19937.c) - 0.5, "
+                                    "A = B*B^T + n*I with B n x %d column-major" % (SEED, KGEN),
                        "note": "CPU reference (lapack/dpotrf.c + blas/*.c, compiled unmodified) timed on a bounded sample per step; "
                                "its rate falls with N, so the GPU/CPU ratio is understated"},
             "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": cores, "kind": kind, "sample": sample},
@@ -299,8 +304,21 @@ def run_ours(args):
 
     # synthetic SPD input, generated in place in the distributed layout (row-major (nloc, N) tensor ==
     # column-major N x nloc with ld = N): A[:, cols] = B * B[cols, :]^T + N * I
-    g = torch.Generator(device=dev).manual_seed(SEED)
-    Bt = torch.rand(KGEN, N, dtype=torch.float64, device=dev, generator=g) - 0.5  # column-major N x KGEN
+    # B (column-major N x KGEN) = u - 0.5 with u from the generator the configs name, dSFMT-19937, produced on the device by the
+    # library's cuRng64GetCloseOpen (bit-identical to the reference's CPU stream; every rank generates the whole of B)
+    Bt = torch.empty(KGEN, N, dtype=torch.float64, device=dev)
+    try:
+        rng = chol.Rng64(SEED)
+        rng.get(Bt.data_ptr(), KGEN * N)
+        torch.cuda.synchronize()
+        rng.close()
+        generator = ("dSFMT-19937 seed %d on the device (cuRng64GetCloseOpen: the reference's rng/dsfmt_19937.c stream) - 0.5, "
+                     "A = B*B^T + N*I with B N x %d column-major" % (SEED, KGEN))
+    except Exception as e:  # noqa: BLE001 - input generation only; the measured path has no fallback
+        g = torch.Generator(device=dev).manual_seed(SEED)
+        Bt = torch.rand(KGEN, N, dtype=torch.float64, device=dev, generator=g)
+        generator = "torch.rand (Philox, seed %d) - 0.5 (device dSFMT failed: %r), A = B*B^T + N*I with B N x %d" % (SEED, e, KGEN)
+    Bt -= 0.5
     A0 = torch.empty(nloc, N, dtype=torch.float64, device=dev)
     for s in range(0, nloc, 4096):
         e = min(nloc, s + 4096)
@@ -519,7 +537,7 @@ def run_ours(args):
             "config": {"workload": "dpotrf lower N=%d, FP64 DMMA trailing update (BASELINE configs[1]/[4] family at the metric's N)" % N,
                        "N": N, "uplo": "L", "nb": nb, "layout": "1-D block-cyclic block columns over %d rank(s)" % P,
                        "timed_api": timed_api, "other_api": other,
-                       "generator": "torch.rand (Philox, seed %d) - 0.5, A = B*B^T + N*I with B N x %d; not the dSFMT stream" % (SEED, KGEN),
+                       "generator": generator,
                        "parallelism": "bc%d" % P, "l2": "inputs (%.1f GB per rank) are larger than L2" % (nloc * N * 8 / 1e9),
                        "restore_in_timed_region": True, "info": info, "probe_resid": probe_resid,
                        "lead_parity_maxrel": parity[0] if parity else None, "lead_parity_bound": parity[1] if parity else None,
