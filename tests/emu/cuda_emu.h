@@ -93,7 +93,7 @@ inline void jitter() {
 }
 }  // namespace emu
 inline void __syncthreads() { emu::current()->bar.wait(); emu::jitter(); }
-inline void __syncwarp(unsigned = 0xffffffffu) { emu::current()->warps[threadIdx.x >> 5].bar.wait(); }
+inline void __syncwarp(unsigned = 0xffffffffu) { emu::current()->warps[threadIdx.x >> 5].bar.wait(); emu::jitter(); }
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 
 // all 32 lanes of the warp must call (full-mask use only, as in the kernels)
@@ -107,6 +107,7 @@ inline T __shfl_sync(unsigned, T v, int src, int width = 32) {  // width: power 
   T r;
   std::memcpy(&r, w.slot[(lane & ~(width - 1)) | (src & (width - 1))], sizeof(T));
   w.bar.wait();
+  emu::jitter();  // lanes leave a shuffle at different times: code that needs a __syncwarp() and lacks it shows
   return r;
 }
 template <typename T>
