@@ -19,6 +19,8 @@
 using namespace chol;
 
 static int failures = 0, cases = 0;
+// fuzz mode (./emu_dmma fuzz SEED COUNT): extra degrees of freedom the fixed sweep does not have
+static bool g_fuzz = false, g_ldc_odd = false, g_beta_zero = false;
 static std::complex<double> cj(std::complex<double> x) { return std::conj(x); }
 static double cj(double x) { return x; }
 
@@ -36,7 +38,7 @@ struct Case {
 };
 
 template <bool CPLX>
-static void run_case(const Case &c, Sched sched) {
+static void run_case(const Case &c, Sched sched) {  // (sched by value: fuzz mode may downgrade it)
   using H = typename std::conditional<CPLX, std::complex<double>, double>::type;
   using Cfg = GemmCfg<CPLX>;
   std::mt19937 g(99u + 3 * c.M + 5 * c.N + 7 * c.K + c.opA + c.opB);
@@ -47,7 +49,7 @@ static void run_case(const Case &c, Sched sched) {
   const bool an = c.opA == 'N', bn = c.opB == 'N';
   const int ar = an ? c.M : c.K, ac = an ? c.K : c.M, br = bn ? c.K : nglob, bc = bn ? nglob : c.K;
   const int pad = c.aligned ? 0 : 1;
-  const int lda = ((ar + 1) / 2) * 2 + pad, ldb = ((br + 1) / 2) * 2 + pad, ldc = ((c.M + 1) / 2) * 2 + 2 * pad + 2;
+  const int lda = ((ar + 1) / 2) * 2 + pad, ldb = ((br + 1) / 2) * 2 + pad, ldc = ((c.M + 1) / 2) * 2 + 2 * pad + 2 + (g_ldc_odd ? 1 : 0);
   std::vector<H> Abuf((size_t)lda * ac + 4), Bbuf((size_t)ldb * bc + 4), C((size_t)ldc * c.N + 2), C0;
   H *A = Abuf.data() + pad, *B = Bbuf.data() + pad;
   for (auto &x : Abuf) x = rnd();
@@ -62,6 +64,7 @@ static void run_case(const Case &c, Sched sched) {
   d.m = c.M; d.n = c.N; d.k = c.K;
   d.alpha[0] = -0.75; d.alpha[1] = CPLX ? 0.25 : 0.0;
   d.beta[0] = 1.25; d.beta[1] = CPLX ? -0.5 : 0.0;
+  if (g_beta_zero) d.beta[0] = d.beta[1] = 0.0;
   d.A = A; d.lda = lda; d.B = B; d.ldb = ldb; d.C = C.data(); d.ldc = ldc; d.D = C.data(); d.ldd = ldc;
   d.cyc_nb = c.cyc_nb; d.cyc_p = c.cyc_p; d.cyc_off = c.cyc_off;
   GemmArgs<CPLX> a;
@@ -69,6 +72,10 @@ static void run_case(const Case &c, Sched sched) {
   bool tma = false;
   if (fill_args<CPLX>(&d, a, tiles, tma) != 0 || tiles == 0) { std::printf("fill_args rejected a case\n"); ++failures; return; }
   a.stage_c = c.stage_c;
+  if (g_fuzz) {  // a drawn schedule the descriptor cannot take falls back the way the launcher does
+    if (sched == STAGGERED_RINGC && !tma) sched = STAGGERED;
+    if ((sched == STAGGERED || sched == STAGGERED_RINGC) && a.K == 0) sched = CLASSIC;
+  }
   const H alpha = [&] { if constexpr (CPLX) return H(d.alpha[0], d.alpha[1]); else return H(d.alpha[0]); }();
   const H beta = [&] { if constexpr (CPLX) return H(d.beta[0], d.beta[1]); else return H(d.beta[0]); }();
 
@@ -166,6 +173,60 @@ static void sweep() {
   run_case<CPLX>({1, 1, 1, 'N', 'N', 0, 0, 0, 0, 0, 0, true, 0, 0, 0, 1}, CLASSIC);
 }
 
+// random descriptors inside the launcher's contract (fill_args): shapes up to a few tiles, every op pair, aligned and
+// unaligned operands, odd ldc (scalar epilogue), beta = 0, triangular operands, triangle-only / Hermitian output, the
+// block-cyclic column map, all four schedules
+template <bool CPLX>
+static void fuzz_one(std::mt19937 &g) {
+  auto ri = [&](int lo, int hi) { return lo + (int)(g() % (unsigned)(hi - lo + 1)); };
+  const int BM = GemmCfg<CPLX>::BM;
+  const char hT = CPLX ? 'C' : 'T';
+  const char ops[3] = {'N', 'T', hT};
+  Case c{};
+  c.M = ri(0, 4) == 0 ? ri(1, 40) : ri(1, 3 * BM + 20);
+  c.N = ri(0, 4) == 0 ? ri(1, 20) : ri(1, 210);
+  c.K = ri(0, 9) == 0 ? 0 : ri(1, 100);
+  c.opA = ops[ri(0, 2)];
+  c.opB = ops[ri(0, 2)];
+  c.aligned = ri(0, 2) != 0;
+  c.stage_c = ri(0, 3) == 0 ? 0 : 1;
+  const int kind = ri(0, 9);
+  if (kind <= 3) {  // the POTRF / SYRK family: NT, triangle-only output
+    c.opA = 'N';
+    c.opB = hT;
+    c.cuplo = "LU"[ri(0, 1)];
+    c.herm = ri(0, 1);
+    if (ri(0, 1)) c.N = c.M;
+    if (ri(0, 3) != 0) {  // mostly the TMA-fed form (tma_eligible): aligned, even m / n, k a multiple of the k-tile
+      c.aligned = true;
+      c.M += c.M & 1;
+      c.N += c.N & 1;
+      c.K = GemmCfg<CPLX>::BK * ri(1, 6);
+    }
+    if (c.cuplo == 'L' && ri(0, 2) == 0) {  // block-cyclic map
+      c.cyc_nb = 64 * ri(1, 2);
+      c.cyc_p = ri(1, 3);
+      c.cyc_off = ri(0, c.cyc_p - 1);
+    }
+  } else if (kind == 4) {  // triangular A (TRMM left): op(A) is M x K, square
+    c.K = c.M;
+    c.triA = "LU"[ri(0, 1)];
+    c.unitA = ri(0, 1);
+  } else if (kind == 5) {  // triangular B (TRMM right): op(B) is K x N, square
+    c.K = c.N;
+    c.triB = "LU"[ri(0, 1)];
+    c.unitB = ri(0, 1);
+  } else if (kind == 6) {  // plain GEMM with a block-cyclic map
+    if (c.opB == 'N') c.opB = hT;
+    c.cyc_nb = 64;
+    c.cyc_p = ri(2, 3);
+    c.cyc_off = ri(0, c.cyc_p - 1);
+  }
+  g_ldc_odd = ri(0, 3) == 0;
+  g_beta_zero = ri(0, 5) == 0;
+  run_case<CPLX>(c, (Sched)ri(0, 3));
+}
+
 int main(int argc, char **argv) {
   std::setvbuf(stdout, nullptr, _IOLBF, 0);
   if (const char *w = getenv("EMU_WATCHDOG")) {  // deadlock report: who waits on which mbarrier, then give up
@@ -179,6 +240,17 @@ int main(int argc, char **argv) {
   if (argc > 1 && std::string(argv[1]) == "staggered-only") {
     run_case<false>({3 * 128, 192, 48, 'N', 'T', 0, 0, 0, 0, 'L', 1, true, 0, 0, 0, 1}, STAGGERED);
     return failures;
+  }
+  if (argc > 3 && std::string(argv[1]) == "fuzz") {
+    g_fuzz = true;
+    std::mt19937 g((unsigned)atoi(argv[2]));
+    for (int i = 0, n = atoi(argv[3]); i < n; ++i) {
+      if (g() & 1u) fuzz_one<false>(g); else fuzz_one<true>(g);
+    }
+    std::printf("%d cases\n", cases);
+    if (failures) { std::printf("EMU FAILED: %d mismatches\n", failures); return 1; }
+    std::printf("EMU PASSED\n");
+    return 0;
   }
   sweep<false>();
   sweep<true>();

@@ -10,6 +10,7 @@
 
 #include <complex>
 #include <random>
+#include <string>
 
 using namespace chol;
 
@@ -134,8 +135,58 @@ static void sweep(bool deep) {
   run_case<T>({5, 3, 0, 0, hT, 0, 0, 0, 0, 0, 0, true}, deep);
 }
 
-int main() {
+// ./emu_ffma fuzz SEED COUNT: random descriptors inside the engine's contract (shapes up to a few tiles, every op pair,
+// aligned / unaligned operands, triangular operands on either side, triangle-only / Hermitian output)
+template <typename T>
+static void fuzz_one(std::mt19937 &g) {
+  constexpr bool CPLX = ScalarOf<T>::cplx;
+  auto ri = [&](int lo, int hi) { return lo + (int)(g() % (unsigned)(hi - lo + 1)); };
+  const int hT = CPLX ? 2 : 1;
+  const int ops[3] = {0, 1, hT};
+  Case c{};
+  c.M = ri(0, 4) == 0 ? ri(1, 30) : ri(1, CPLX ? 170 : 300);
+  c.N = ri(0, 4) == 0 ? ri(1, 30) : ri(1, CPLX ? 170 : 300);
+  c.K = ri(0, 9) == 0 ? 0 : ri(1, 90);
+  c.opA = ops[ri(0, 2)];
+  c.opB = ops[ri(0, 2)];
+  c.aligned = ri(0, 1) != 0;
+  const int kind = ri(0, 7);
+  if (kind <= 2) {  // rank-k update family
+    c.opA = 0;
+    c.opB = hT;
+    c.cuplo = ri(1, 2);
+    c.herm = ri(0, 1);
+    if (ri(0, 1)) c.N = c.M;
+  } else if (kind == 3) {
+    c.K = c.M;
+    c.triA = ri(1, 2);
+    c.unitA = ri(0, 1);
+  } else if (kind == 4) {
+    c.K = c.N;
+    c.triB = ri(1, 2);
+    c.unitB = ri(0, 1);
+  } else if (kind == 5) {  // both masked, triangle-only output (LAUUM forms)
+    c.M = c.N = ri(1, 140);
+    c.K = c.M;
+    c.triA = c.triB = ri(1, 2);
+    c.cuplo = ri(1, 2);
+    c.herm = ri(0, 1);
+  }
+  run_case<T>(c, true);
+}
+
+int main(int argc, char **argv) {
   std::setvbuf(stdout, nullptr, _IOLBF, 0);
+  if (argc > 3 && std::string(argv[1]) == "fuzz") {
+    std::mt19937 g((unsigned)atoi(argv[2]));
+    for (int i = 0, n = atoi(argv[3]); i < n; ++i) {
+      if (g() & 1u) fuzz_one<float>(g); else fuzz_one<float2>(g);
+    }
+    std::printf("fuzz: %d cases, %d mismatches\n", cases, failures);
+    if (failures) { std::printf("EMU FAILED: %d mismatches\n", failures); return 1; }
+    std::printf("EMU PASSED\n");
+    return 0;
+  }
   sweep<float>(true);
   sweep<float2>(true);
   std::printf("deep-k kernels: %d cases so far, %d mismatches\n", cases, failures);

@@ -378,8 +378,34 @@ static void case_scatter_rows(const char *name) {
   check(B == W, what, 0);
 }
 
-int main() {
+// ./emu_panel sizes PREC [STEP]: every block order the one-CTA kernels accept (1 .. 128, z: 64), not just the handful of the
+// default run - potf2 (+ a not-PD column drawn per size), trti2 / lauu2, and trsm_rows in both shapes with a row count drawn per size
+template <typename T, int NMAX, int GW>
+static void every_size(const char *name, double tol, int step) {
+  std::mt19937 g(4242);
+  for (int n = 1; n <= NMAX; n += step) {
+    case_potf2<T, NMAX>(name, n, tol);
+    case_not_pd<T, NMAX>(name, n, (int)(g() % (unsigned)n));
+    case_unfused<T, NMAX>(name, n, tol);
+    case_trsm_rows<T, NMAX, 32, 1>(name, n, 1 + (int)(g() % 9u), 1 + (int)(g() % 4u), tol);
+    case_trsm_rows<T, NMAX, GW, 4>(name, n, 1 + (int)(g() % 70u), 1 + (int)(g() % 3u), tol);
+  }
+}
+
+int main(int argc, char **argv) {
   std::setvbuf(stdout, nullptr, _IOLBF, 0);
+  if (argc > 2 && std::string(argv[1]) == "sizes") {
+    const int step = argc > 3 ? std::max(1, atoi(argv[3])) : 1;
+    switch (argv[2][0]) {
+      case 'd': every_size<double, 128, 8>("d", 1e-12, step); break;
+      case 'z': every_size<double2, 64, 8>("z", 1e-12, step); break;
+      case 's': every_size<float, 128, 8>("s", 2e-4, step); break;
+      default: every_size<float2, 128, 16>("c", 2e-4, step); break;
+    }
+    if (failures) { std::printf("EMU FAILED: %d mismatches\n", failures); return 1; }
+    std::printf("EMU PASSED\n");
+    return 0;
+  }
   case_potf2<double, 128>("d", 128, 1e-12);
   case_potf2<double, 128>("d", 100, 1e-12);
   case_potf2<double, 128>("d", 37, 1e-12);

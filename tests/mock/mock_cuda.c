@@ -27,7 +27,7 @@
 
 #define MAXDEV 16
 struct CUctx_st { int device; };
-static struct CUctx_st ctxs[MAXDEV];
+static struct CUctx_st ctxs[MAXDEV] = {{0}, {1}, {2}, {3}, {4}, {5}, {6}, {7}, {8}, {9}, {10}, {11}, {12}, {13}, {14}, {15}};
 static __thread CUcontext stack[16];
 static __thread int top = 0; /* stack[top-1] is current */
 
@@ -37,11 +37,11 @@ static int ndev(void) {
   return n < 1 ? 1 : (n > MAXDEV ? MAXDEV : n);
 }
 
-CUresult cuInit(unsigned int flags) { (void)flags; for (int i = 0; i < MAXDEV; i++) ctxs[i].device = i; return CUDA_SUCCESS; }
+CUresult cuInit(unsigned int flags) { (void)flags; return CUDA_SUCCESS; } /* callable from every worker thread at once, like the real one */
 CUresult cuGetErrorString(CUresult e, const char **s) { (void)e; *s = "mock CUDA error"; return CUDA_SUCCESS; }
 CUresult cuDeviceGet(CUdevice *d, int ordinal) { if (ordinal < 0 || ordinal >= ndev()) return CUDA_ERROR_INVALID_DEVICE; *d = ordinal; return CUDA_SUCCESS; }
 CUresult cuDeviceGetCount(int *n) { *n = ndev(); return CUDA_SUCCESS; }
-CUresult cuDevicePrimaryCtxRetain(CUcontext *c, CUdevice d) { if (d < 0 || d >= ndev()) return CUDA_ERROR_INVALID_DEVICE; ctxs[d].device = d; *c = &ctxs[d]; return CUDA_SUCCESS; }
+CUresult cuDevicePrimaryCtxRetain(CUcontext *c, CUdevice d) { if (d < 0 || d >= ndev()) return CUDA_ERROR_INVALID_DEVICE; *c = &ctxs[d]; return CUDA_SUCCESS; }
 CUresult cuDevicePrimaryCtxRelease(CUdevice d) { (void)d; return CUDA_SUCCESS; }
 CUresult cuCtxGetCurrent(CUcontext *c) { *c = top ? stack[top - 1] : NULL; return CUDA_SUCCESS; }
 CUresult cuCtxSetCurrent(CUcontext c) { if (top == 0) top = 1; stack[top - 1] = c; return CUDA_SUCCESS; }

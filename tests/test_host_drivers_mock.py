@@ -86,6 +86,8 @@ def mock_runs(tmp_path_factory):
     res["c:cumultigpu_unit:1"] = run_c(os.path.join(cdir, "cumultigpu_unit.c"), 1)
     res["c:cumultigpu_unit:3"] = run_c(os.path.join(cdir, "cumultigpu_unit.c"), 3)
     res["c:dropin_dpotrf"] = run_c(os.path.join(cdir, "dropin_dpotrf.c"), 1, ("300",))
+    res["c:mgpu_potri_chain:1"] = run_c(os.path.join(cdir, "mgpu_potri_chain.c"), 1, ("500",))
+    res["c:mgpu_potri_chain:3"] = run_c(os.path.join(cdir, "mgpu_potri_chain.c"), 3, ("700",))
     return res
 
 
@@ -101,9 +103,11 @@ def test_host_drivers_on_mock_backend(mock_runs, group, min_checks):
     assert n >= min_checks
 
 
-@pytest.mark.parametrize("prog", ["c:cumultigpu_unit:1", "c:cumultigpu_unit:3", "c:dropin_dpotrf"])
+@pytest.mark.parametrize("prog", ["c:cumultigpu_unit:1", "c:cumultigpu_unit:3", "c:dropin_dpotrf", "c:mgpu_potri_chain:1",
+                                  "c:mgpu_potri_chain:3"])
 def test_c_callers_on_mock_backend(mock_runs, prog):
     """tests/c/cumultigpu_unit.c (the reference's cumultigpu.c / cutask.c unit tests plus error latching and
-    submission order, then cuMultiGPUDpotrf on every device) and tests/c/dropin_dpotrf.c, without a GPU"""
+    submission order, then cuMultiGPUDpotrf on every device), tests/c/dropin_dpotrf.c and tests/c/mgpu_potri_chain.c
+    (cuMultiGPUDpotrf -> cuMultiGPUDpotri -> cuMultiGPUDgemm, both triangles, A inv(A) against I), without a GPU"""
     rc, out = mock_runs[prog]
     assert rc == 0 and "PASSED" in out, out[-3000:]
