@@ -102,7 +102,7 @@ static void case_potf2(const char *name, int n, double tol) {
 }
 
 template <typename T, int NMAX>
-static void case_not_pd(const char *name, int n, int bad) {
+static void case_not_pd(const char *name, int n, int bad, double tol = 1e-10) {
   using H = typename Host<T>::type;
   const int lda = n;
   for (int upper = 0; upper < 2; ++upper) {
@@ -121,7 +121,7 @@ static void case_not_pd(const char *name, int n, int bad) {
       for (int i = j; i < n; ++i) e = std::max(e, ab(A1[upper ? j + (size_t)i * lda : i + (size_t)j * lda] - (upper ? cj(L[i + (size_t)j * lda]) : L[i + (size_t)j * lda])));
     char what[160];
     std::snprintf(what, sizeof what, "%s potf2 %s n=%d not PD at column %d: info, finished columns", name, upper ? "upper" : "lower", n, bad);
-    check(i1 == 1000 + bad + 1 && e <= 1e-10, what, e);
+    check(i1 == 1000 + bad + 1 && e <= tol, what, e);
     // a kernel that finds *dinfo != 0 on entry must not touch anything
     std::vector<H> A3 = A0;
     long i3 = 42;
@@ -385,7 +385,7 @@ static void every_size(const char *name, double tol, int step) {
   std::mt19937 g(4242);
   for (int n = 1; n <= NMAX; n += step) {
     case_potf2<T, NMAX>(name, n, tol);
-    case_not_pd<T, NMAX>(name, n, (int)(g() % (unsigned)n));
+    case_not_pd<T, NMAX>(name, n, (int)(g() % (unsigned)n), std::max(tol, 1e-10));
     case_unfused<T, NMAX>(name, n, tol);
     case_trsm_rows<T, NMAX, 32, 1>(name, n, 1 + (int)(g() % 9u), 1 + (int)(g() % 4u), tol);
     case_trsm_rows<T, NMAX, GW, 4>(name, n, 1 + (int)(g() % 70u), 1 + (int)(g() % 3u), tol);
