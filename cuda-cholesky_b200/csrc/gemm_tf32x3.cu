@@ -54,6 +54,19 @@ struct TArgs {
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
+// (tests/emu/tcgen05_emu.h supplies CPU stand-ins with the same names when the kernel's source is run by the
+// emulation harness tests/emu/emu_tf32x3.cpp; under nvcc the code below is what is compiled, unchanged)
+#ifdef CHOL_CPU_EMU
+}  // namespace chol
+#include "tcgen05_emu.h"
+namespace chol {
+#else
+#define T_DYN_SMEM(name) extern __shared__ uint8_t name[]
+#define T_FENCE_MBAR_INIT() asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory")
+#define T_TMEM_ALLOC(slot, cols)                                                                                                    \
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(slot)), "r"(cols) : "memory");       \
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory")
+#define T_TMEM_DEALLOC(base, cols) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory")
 __device__ __forceinline__ uint32_t s_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void t_mbar_init(uint64_t *bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count));
@@ -114,6 +127,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]) :: "memory");
 }
 
+#endif  // CHOL_CPU_EMU
+
 // K-major operand tile, rows of 128 bytes, 128-byte swizzle (what the TMA box writes): 8-row groups
 // are 1024 bytes apart (SBO), the leading offset is unused for swizzled K-major layouts.
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
@@ -158,7 +173,7 @@ __global__ void __launch_bounds__(T_THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                    const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
                    const __grid_constant__ TArgs p) {
-  extern __shared__ uint8_t t_smem_raw[];
+  T_DYN_SMEM(t_smem_raw);
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(t_smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TST * T_STAGE_BYTES);
   uint64_t *full = bars, *empty = bars + TST, *acc_full = bars + 2 * TST, *acc_empty = bars + 2 * TST + 2;
@@ -174,11 +189,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
       t_mbar_init(&acc_full[b], 1);
       t_mbar_init(&acc_empty[b], T_EPI_THREADS);
     }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    T_FENCE_MBAR_INIT();
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    T_TMEM_ALLOC(tmem_slot, 512u);
   }
   tc_fence_before();
   __syncthreads();
@@ -288,7 +302,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    T_TMEM_DEALLOC(tmem_base, 512u);
   }
 }
 
@@ -296,6 +310,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
 // hi[r * kp + c], lo[...] for r < rows, c < kp (zero for c >= k).  trans == 0: source element (r, c) at
 // A[c * lda + r] (the stored operand is rows x k, column-major - the "N" operand of an NT product);
 // trans != 0: at A[r * lda + c].
+#ifndef CHOL_CPU_EMU  // (emulation: tests/emu/tcgen05_emu.h)
 __device__ __forceinline__ void tf32_split(float x, float &hi, float &lo) {
   uint32_t h, l;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
@@ -303,6 +318,7 @@ __device__ __forceinline__ void tf32_split(float x, float &hi, float &lo) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - hi));
   lo = __uint_as_float(l);
 }
+#endif
 __global__ void __launch_bounds__(256) tf32_split_kernel(int trans, int rows, int k, int kp, const float *__restrict__ A, long long lda,
                                                          float *__restrict__ hi, float *__restrict__ lo) {
   __shared__ float tile[32][33];
@@ -367,6 +383,7 @@ __global__ void __launch_bounds__(256) tf32_split_c_kernel(int rows, int k, int 
   }
 }
 
+#ifndef CHOL_CPU_EMU  // the launchers are not part of the CPU emulation (tests/emu restates their argument set-up)
 static int make_map(CUtensorMap *map, const void *base, size_t rows, size_t kp, size_t row_pitch, unsigned box_rows) {
   cuuint64_t gdim[2] = {(cuuint64_t)kp, (cuuint64_t)rows};
   cuuint64_t gstr[1] = {(cuuint64_t)row_pitch * 4};
@@ -378,8 +395,11 @@ static int make_map(CUtensorMap *map, const void *base, size_t rows, size_t kp, 
   return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
 
+#endif  // CHOL_CPU_EMU
+
 }  // namespace chol
 
+#ifndef CHOL_CPU_EMU
 using namespace chol;
 
 extern "C" size_t chol_tf32_kpitch(size_t k) { return (k + TBK - 1) / TBK * TBK; }
@@ -454,3 +474,4 @@ extern "C" int chol_tf32x3_herk_launch(size_t m, size_t n, size_t k, double alph
                                        int cuplo, int herm, void *stream) {
   return tf32x3_launch(2 * m, n, 2 * k, alpha, Ahi, Alo, kp, Bhi, Blo, 2 * kp, kp, beta, C, 2 * ldc, D, 2 * ldd, cuplo, 1, herm, stream);
 }
+#endif  // CHOL_CPU_EMU
