@@ -8,6 +8,9 @@
 
 #include "../../cuda-cholesky_b200/csrc/rng_dsfmt.cu"
 
+#include <random>
+#include <string>
+
 extern "C" {
 #include "../../cuda-cholesky_b200/host/rng_internal.h"
 // oracle/dsfmt_oracle.c
@@ -53,7 +56,53 @@ static void run_generate(int kind, const W128 *states, unsigned long long refill
   }
 }
 
-int main() {
+// ./emu_rng fuzz SEED COUNT: random segmentations (refills per segment, segment count, first refill) and random windows
+// inside them (start word, value count odd / even, 8- or 16-byte aligned pointer, output kind) against the oracle's stream
+static int fuzz(unsigned fseed, int count) {
+  const uint64_t seed = 20121018u;
+  state_t s0;
+  chol_dsfmt_seed_state(seed, s0);
+  std::mt19937 g(fseed);
+  auto ri = [&](unsigned long long lo, unsigned long long hi) { return lo + (unsigned long long)(g() % (unsigned)(hi - lo + 1)); };
+  for (int it = 0; it < count; ++it) {
+    const unsigned seg = (unsigned)ri(1, 5);
+    const int nseg = (int)ri(1, 9);
+    const unsigned long long refill0 = ri(0, 6);
+    std::vector<W128> states((size_t)nseg * DS_STATE_WORDS);
+    state_t cur;
+    std::memcpy(cur, s0, sizeof cur);
+    for (unsigned long long r = 0, sg = 0; sg < (unsigned long long)nseg; ++r) {
+      if (r == refill0 + sg * seg) {
+        std::memcpy(&states[sg * DS_STATE_WORDS], cur, sizeof cur);
+        ++sg;
+      }
+      chol_dsfmt_refill_host(cur);
+    }
+    const unsigned long long lo = refill0 * 191, hi = (refill0 + (unsigned long long)nseg * seg) * 191;  // covered stream words
+    const unsigned long long w0 = ri(lo, hi - 1);
+    unsigned long long words = ri(0, 3) == 0 ? ri(1, 3) : ri(1, hi - w0);
+    if (words > hi - w0) words = hi - w0;
+    const unsigned long long n = 2 * words - (ri(0, 1) ? 1 : 0);  // an odd count drops the last high half
+    const int kind = (int)ri(0, 4), misalign = (int)ri(0, 1);
+    std::vector<unsigned long long> buf(n + 8, 0x3333333333333333ull);
+    unsigned long long *out = buf.data() + 2;
+    while (((uintptr_t)out & 15) != (misalign ? 8u : 0u)) ++out;
+    run_generate(kind, states.data(), refill0, seg, nseg, w0, w0 + words, out, n, nullptr);
+    const auto want = oracle_window(seed, w0, n, kind);
+    const bool ok = std::memcmp(out, want.data(), n * 8) == 0 && out[n] == 0x3333333333333333ull && out[-1] == 0x3333333333333333ull;
+    char what[160];
+    std::snprintf(what, sizeof what, "fuzz: %d segments of %u refills from refill %llu, window at word %llu, %llu values, kind %d, %s pointer", nseg, seg,
+                  refill0, w0, n, kind, misalign ? "8-byte" : "16-byte");
+    expect(ok, what);
+  }
+  std::printf("fuzz: %d cases, %d mismatches\n", cases, failures);
+  if (failures) return 1;
+  std::printf("EMU PASSED\n");
+  return 0;
+}
+
+int main(int argc, char **argv) {
+  if (argc > 3 && std::string(argv[1]) == "fuzz") return fuzz((unsigned)atoi(argv[2]), atoi(argv[3]));
   const uint64_t seed = 20121018u;
   state_t s0;
   chol_dsfmt_seed_state(seed, s0);
