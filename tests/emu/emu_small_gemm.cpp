@@ -7,6 +7,7 @@
 #include "../../cuda-cholesky_b200/csrc/gemm_small.cu"
 
 #include <random>
+#include <string>
 
 using namespace chol;
 
@@ -63,9 +64,20 @@ static void run_case(int M, int N, int K, int opA, int opB, int cuplo, double al
   }
 }
 
-int main() {
+int main(int argc, char **argv) {
   std::setvbuf(stdout, nullptr, _IOLBF, 0);
   int cases = 0;
+  if (argc > 3 && std::string(argv[1]) == "fuzz") {  // ./emu_small_gemm fuzz SEED COUNT: random shapes / ops / triangles / scalars
+    std::mt19937 g((unsigned)atoi(argv[2]));
+    auto ri = [&](int lo, int hi) { return lo + (int)(g() % (unsigned)(hi - lo + 1)); };
+    const double alphas[4] = {-1.0, 0.7, 1.0, 0.0}, betas[4] = {1.0, -0.3, 0.0, 2.0};
+    for (int i = 0, n = atoi(argv[3]); i < n; ++i, ++cases)
+      run_case(ri(1, 130), ri(1, 130), ri(0, 9) == 0 ? 0 : ri(1, 150), ri(0, 1), ri(0, 1), ri(0, 2), alphas[ri(0, 3)], betas[ri(0, 3)], ri(0, 1) != 0);
+    std::printf("fuzz: %d cases, %d mismatches\n", cases, failures);
+    if (failures) { std::printf("EMU FAILED: %d mismatches\n", failures); return 1; }
+    std::printf("EMU PASSED\n");
+    return 0;
+  }
   const int shapes[][3] = {{32, 32, 16}, {37, 50, 23}, {64, 33, 40}, {1, 1, 1}, {96, 96, 128}, {5, 70, 3}};
   for (auto &sh : shapes)
     for (int opA = 0; opA < 2; ++opA)
