@@ -1146,7 +1146,11 @@ static CUresult mgpu_potrf(CUmultiGPULAPACKhandle handle, int prec, int uplo, si
   const int P = m->n;
   potrf_args *args = calloc((size_t)P, sizeof *args);
   potrf_args **ptrs = calloc((size_t)P, sizeof *ptrs);
-  if (args == NULL || ptrs == NULL) return CUDA_ERROR_OUT_OF_MEMORY;
+  if (args == NULL || ptrs == NULL) {
+    free(args);
+    free(ptrs);
+    return CUDA_ERROR_OUT_OF_MEMORY;
+  }
   for (int i = 0; i < P; i++) {
     args[i].R = &m->ranks[i];
     args[i].prec = prec;

@@ -184,7 +184,11 @@ static CUresult mb_run(CUmultiGPU m, mb_args *proto) {
   const int P = cuMultiGPUGetContextCount(m);
   mb_args *args = calloc((size_t)P, sizeof *args);
   mb_args **ptrs = calloc((size_t)P, sizeof *ptrs);
-  if (args == NULL || ptrs == NULL) return CUDA_ERROR_OUT_OF_MEMORY;
+  if (args == NULL || ptrs == NULL) {
+    free(args);
+    free(ptrs);
+    return CUDA_ERROR_OUT_OF_MEMORY;
+  }
   for (int i = 0; i < P; i++) {
     args[i] = *proto;
     args[i].rank = i;

@@ -216,6 +216,15 @@ def child(lib, P, seconds, seed):
         if not np.array_equal(a, b):
             fails.append("%s: other triangle changed" % tag)
 
+    def check2(tag, got, want, p, kdim, slack=1.0):
+        nonlocal cases
+        cases += 1
+        by[tag.split()[0]] = by.get(tag.split()[0], 0) + 1
+        scale = max(1.0, float(np.abs(want).max()))
+        err = float(np.abs(got - want).max())
+        if not err <= 64 * max(kdim, 1) * H.eps(p) * scale * slack:
+            fails.append("%s: err %.3e" % (tag, err))
+
     def dup(M):
         """copy that KEEPS the leading dimension (ndarray.copy() of a padded view is compact)"""
         ldm = M.strides[1] // M.itemsize
@@ -244,9 +253,63 @@ def child(lib, P, seconds, seed):
         nb_eff = nb or (128 if p in "zc" else 256)
         n = min(draw_n(nb_eff), 1800 if p in "ds" else 1200)
         ldx = n + int(rng.choice([0, 0, 1, 5]))
-        routine = str(rng.choice(["potrf", "potrf", "potrf_bad", "trtri", "lauum", "potri", "dist", "trtri_zero"]))
+        routine = str(rng.choice(["potrf", "potrf", "potrf_bad", "trtri", "lauum", "potri", "dist", "trtri_zero", "gemm", "rankk", "trsm", "trmm"]))
         if routine == "dist" and p in "sc":
             p = "d"
+        if routine in ("gemm", "rankk", "trsm", "trmm"):  # the host-pointer BLAS-3 tilers (host/multigpu_blas.c)
+            cplx = PREC[p]["cplx"]
+            hT = "C" if cplx else "T"
+            sd = int(rng.integers(1, 1 << 30))
+            m_, n_, k_ = (int(rng.integers(1, 40)) if rng.integers(0, 4) == 0 else int(rng.integers(1, 700)) for _ in range(3))
+            alpha, beta = ((0.7 - 0.2j, -0.3 + 0.5j) if cplx else (0.7, -0.3))
+            if rng.integers(0, 5) == 0:
+                beta = 0.0
+            tag = "%s %s m=%d n=%d k=%d P=%d" % (routine, p, m_, n_, k_, P)
+            if os.environ.get("MOCK_FUZZ_VERBOSE"):
+                sys.stderr.write(tag + "\n")
+                sys.stderr.flush()
+            try:
+                if routine == "gemm":
+                    tA, tB = (("N", "T", hT)[int(rng.integers(0, 3))] for _ in range(2))
+                    A = H.rand_matrix(p, *((m_, k_) if tA == "N" else (k_, m_)), seed=sd, ld=(m_ if tA == "N" else k_) + int(rng.integers(0, 3)))
+                    B = H.rand_matrix(p, *((k_, n_) if tB == "N" else (n_, k_)), seed=sd + 1)
+                    Cm = H.rand_matrix(p, m_, n_, seed=sd + 2, ld=m_ + int(rng.integers(0, 4)))
+                    want = dup(Cm)
+                    ORA.gemm(p, tA, tB, m_, n_, k_, alpha, A, B, beta, want)
+                    mg.gemm(p, tA, tB, m_, n_, k_, alpha, A.ctypes.data, ldof(A), B.ctypes.data, ldof(B), beta, Cm.ctypes.data, ldof(Cm))
+                    check2(tag + " %s%s" % (tA, tB), Cm, want, p, k_)
+                elif routine == "rankk":
+                    trans = ("N", hT)[int(rng.integers(0, 2))]
+                    A = H.rand_matrix(p, *((n_, k_) if trans == "N" else (k_, n_)), seed=sd)
+                    C0 = H.spd_matrix(p, n_, seed=sd + 1, k=min(n_, 8), ld=n_ + int(rng.integers(0, 3)))
+                    want, got = dup(C0), dup(C0)
+                    a_r, b_r = -0.5, (0.0 if beta == 0.0 else 1.25)  # real scalars (HERK)
+                    ORA.rankk(p, uplo, trans, n_, k_, a_r, A, b_r, want)
+                    mg.rankk(p, uplo, trans, n_, k_, a_r, A.ctypes.data, ldof(A), b_r, got.ctypes.data, ldof(got))
+                    check2(tag + " %s%s" % (uplo, trans), H.tri(got, uplo), H.tri(want, uplo), p, k_)
+                    oth = (np.triu(got, 1), np.triu(C0, 1)) if uplo == "L" else (np.tril(got, -1), np.tril(C0, -1))
+                    if not np.array_equal(*oth):
+                        fails.append(tag + ": other triangle changed")
+                else:
+                    side = "LR"[int(rng.integers(0, 2))]
+                    trans = ("N", "T", hT)[int(rng.integers(0, 3))]
+                    diag = "NU"[int(rng.integers(0, 2))]
+                    na = m_ if side == "L" else n_
+                    T0 = H.spd_matrix(p, na, seed=sd, k=min(na, 16))
+                    ORA.potrf(p, "L", T0)
+                    Tm = dup(T0)
+                    Tm[:, :] = np.tril(T0) + np.tril(T0, -1).conj().T
+                    if diag == "U":
+                        Tm[:, :] = Tm / (np.abs(np.diag(Tm)).max() * 4)
+                    B0 = H.rand_matrix(p, m_, n_, seed=sd + 1, ld=m_ + int(rng.integers(0, 3)))
+                    want, got = dup(B0), dup(B0)
+                    getattr(ORA, routine)(p, side, uplo, trans, diag, m_, n_, alpha, Tm, want)
+                    getattr(mg, routine)(p, side, uplo, trans, diag, m_, n_, alpha, Tm.ctypes.data, ldof(Tm), got.ctypes.data, ldof(got))
+                    check2(tag + " %s%s%s%s" % (side, uplo, trans, diag), got, want, p, na, 4.0 if routine == "trsm" else 1.0)
+            except Exception as e:  # noqa: BLE001
+                fails.append("%s: exception %r" % (tag, e))
+                break
+            continue
         tag = "%s %s %s n=%d nb=%d ld=%d P=%d" % (routine, p, uplo, n, nb, ldx, P)
         if os.environ.get("MOCK_FUZZ_VERBOSE"):
             sys.stderr.write(tag + "\n")
