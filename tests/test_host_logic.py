@@ -188,6 +188,44 @@ def test_block_cyclic_schedule_matches_global_triangle(P):
             assert set(tiles) == want and len(tiles) == len(set(tiles))
 
 
+def _wanted_tiles(cuplo, m, n, nb=0, P=0, off=0):
+    """tiles of the 128 x 64 grid that touch the (block-cyclic) triangle - the rule the kernel's masks assume"""
+    want = set()
+    for bj in range((n + 63) // 64):
+        nloc = bj * 64
+        c0 = (((nloc // nb) * P + off) * nb + nloc % nb) if nb else nloc  # global column of the tile's first column
+        for bi in range((m + 127) // 128):
+            if cuplo == "L" and bi * 128 + 127 < c0:
+                continue
+            if cuplo == "U" and bi * 128 > c0 + 63:
+                continue
+            want.add((bi, bj))
+    return want
+
+
+def test_tile_schedule_random_shapes():
+    """property test of the DMMA engine's host-built tile schedule (csrc/gemm_common.cuh: super-rows of 16 row blocks, prefix
+    table): for random m, n, triangle and block-cyclic map, the decoded tile list is exactly the set of tiles that touch the
+    triangle, each once, and the grid is no smaller than the list"""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=150, deadline=None, derandomize=True)
+    @given(st.sampled_from(["", "L", "U"]), st.integers(1, 9000), st.integers(1, 9000))
+    def plain(cuplo, m, n):
+        grid, tiles = chol.tile_schedule(cuplo, m, n)
+        assert len(tiles) == len(set(tiles)) and set(tiles) == _wanted_tiles(cuplo, m, n) and grid >= len(tiles)
+
+    @settings(max_examples=100, deadline=None, derandomize=True)
+    @given(st.integers(1, 9000), st.integers(1, 4000), st.sampled_from([64, 128, 256, 512, 1024]), st.integers(1, 8), st.data())
+    def cyclic(m, n, nb, P, data):
+        off = data.draw(st.integers(0, P - 1))
+        grid, tiles = chol.tile_schedule("L", m, n, nb, P, off)
+        assert len(tiles) == len(set(tiles)) and set(tiles) == _wanted_tiles("L", m, n, nb, P, off) and grid >= len(tiles)
+
+    plain()
+    cyclic()
+
+
 def test_local_cols_partition():
     for n, nb in ((1000, 256), (4096, 256), (65536, 256), (777, 128)):
         for P in (1, 2, 3, 8):
