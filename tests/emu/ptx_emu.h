@@ -1,14 +1,16 @@
 // ptx_emu.h — CPU stand-ins for the inline-PTX primitives of csrc/ptx_sm100.cuh (included from there
 // when CHOL_CPU_EMU is defined): mbarrier (phase + pending-arrival + transaction-byte accounting,
-// blocking waits), TMA bulk copies (the copy, then complete_tx), cp.async with mbarrier arrival, and the
+// blocking waits), TMA bulk copies (deferred: the data lands when a thread waits on the copy's barrier), cp.async with mbarrier arrival, and the
 // m8n8k4 FP64 MMA as a warp-collective exchange.  TEST INFRASTRUCTURE ONLY.
 //
 // A wait on a phase that can never complete blocks forever here exactly as it would spin forever on the
 // GPU - which is the point: protocol deadlocks show up on the CPU (the harness runs under a timeout).
 #pragma once
 #include <condition_variable>
+#include <functional>
 #include <map>
 #include <mutex>
+#include <vector>
 
 namespace chol {
 
@@ -53,6 +55,36 @@ inline void complete_tx(const void *bar, long long bytes) {
   s.tx -= bytes;
   settle(s);
 }
+// Asynchronous copies that report to a barrier (TMA): the data lands as LATE as the program allows - when a thread
+// actually waits on that barrier (or at once if somebody already does).  A consumer that reads the stage without
+// waiting for its barrier therefore reads stale data here; with an immediate copy that bug would be invisible.
+// EMU_TMA_EAGER=1 restores the immediate copy.
+struct Pending { std::function<void()> copy; long long bytes; };
+inline std::map<const void *, std::vector<Pending>> &pending() { static std::map<const void *, std::vector<Pending>> p; return p; }
+inline std::map<const void *, int> &waiters() { static std::map<const void *, int> w; return w; }
+inline bool eager() { static const bool e = [] { const char *v = std::getenv("EMU_TMA_EAGER"); return v && std::atoi(v); }(); return e; }
+inline void land_locked(const void *bar) {  // mu() held
+  auto it = pending().find(bar);
+  if (it == pending().end()) return;
+  State &s = table()[bar];
+  for (Pending &p : it->second) {
+    p.copy();
+    s.tx -= p.bytes;
+  }
+  pending().erase(it);
+  settle(s);
+}
+inline void async_copy(const void *bar, long long bytes, std::function<void()> copy) {
+  std::lock_guard<std::mutex> l(mu());
+  if (eager() || waiters()[bar] > 0) {
+    copy();
+    State &s = table()[bar];
+    s.tx -= bytes;
+    settle(s);
+  } else {
+    pending()[bar].push_back(Pending{std::move(copy), bytes});
+  }
+}
 }  // namespace emu_mbar
 
 inline void mbar_init(uint64_t *bar, uint32_t count) {
@@ -60,6 +92,8 @@ inline void mbar_init(uint64_t *bar, uint32_t count) {
   emu_mbar::State s;
   s.count = s.pending = count;
   emu_mbar::table()[bar] = s;
+  emu_mbar::pending().erase(bar);  // (a previous block's shared memory lived at the same address)
+  emu_mbar::waiters()[bar] = 0;
 }
 inline void mbar_fence_init() {}
 inline void mbar_arrive(uint64_t *bar) { ::emu::jitter(); emu_mbar::arrive(bar, 1, 0); }
@@ -72,7 +106,10 @@ inline void mbar_wait(uint64_t *bar, uint32_t parity) {
   std::unique_lock<std::mutex> l(emu_mbar::mu());
   emu_mbar::State &s = emu_mbar::table()[bar];
   emu_mbar::waiting()[threadIdx.x & 1023] = emu_mbar::Waiting{bar, parity};
+  emu_mbar::land_locked(bar);  // deferred TMA copies reporting to this barrier land now, not before
+  ++emu_mbar::waiters()[bar];
   emu_mbar::cv().wait(l, [&] { return (s.phase & 1u) != (parity & 1u); });
+  --emu_mbar::waiters()[bar];
   emu_mbar::waiting()[threadIdx.x & 1023] = emu_mbar::Waiting{};
 }
 
@@ -81,8 +118,7 @@ inline void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, u
     std::fprintf(stderr, "emu: cp.async.bulk needs 16-byte aligned size and addresses (%u bytes, dst %p, src %p)\n", bytes, dst_smem, src_gmem);
     std::abort();
   }
-  std::memcpy(dst_smem, src_gmem, bytes);
-  emu_mbar::complete_tx(bar, bytes);
+  emu_mbar::async_copy(bar, bytes, [=] { std::memcpy(dst_smem, src_gmem, bytes); });
 }
 inline void l2_prefetch_bulk(const void *, uint32_t) {}
 

@@ -13,7 +13,8 @@
 //    bits [7,10)), applied by the TMA write and by the MMA read alike: a tile that is not 1024-byte aligned, or a
 //    K advance that leaves the 128-byte row, reads garbage here as on the device;
 //  * K-major SWIZZLE_128B operand: row r of the operand tile lives at start + (r / 8) * SBO + (r % 8) * 128;
-//  * TMA: box elements outside the tensor are filled with zeros, the barrier still gets the whole box's bytes;
+//  * TMA: box elements outside the tensor are filled with zeros, the barrier still gets the whole box's bytes; the box
+//    lands as late as the program allows - when a thread waits on its barrier (ptx_emu.h, emu_mbar::async_copy);
 //  * tcgen05.mma is ASYNCHRONOUS: the emulation queues it and executes the queue at the issuing thread's next
 //    tcgen05.commit (the latest moment the program allows), so an epilogue that reads TMEM, or a producer that refills
 //    a stage, before the commit's barrier has fired sees stale data; TMEM starts out as NaN;
@@ -140,15 +141,17 @@ inline void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint6
   const uint32_t d0 = s_u32(dst);
   if (d0 & 127u) emu_tc::die("TMA destination must be 128-byte aligned");
   ::emu::jitter();
-  for (uint32_t r = 0; r < m.box1; ++r)
-    for (uint32_t c = 0; c < m.box0; ++c) {
-      const long long gr = (long long)c1 + r, gc = (long long)c0 + c;
-      float v = 0.f;  // out-of-bounds box elements are zero-filled
-      if (gr >= 0 && gc >= 0 && (uint64_t)gr < m.dim1 && (uint64_t)gc < m.dim0)
-        v = *reinterpret_cast<const float *>(reinterpret_cast<const unsigned char *>(m.base) + (uint64_t)gr * m.stride1_bytes + (uint64_t)gc * 4u);
-      std::memcpy(emu_tc::smem_ptr(emu_tc::swz128(d0 + r * (m.box0 * 4u) + c * 4u)), &v, 4);
-    }
-  emu_mbar::complete_tx(bar, (long long)m.box0 * m.box1 * 4);
+  const uintptr_t origin = emu_tc::smem_origin();  // (the copy may be executed by another thread of the block: same block, same origin)
+  emu_mbar::async_copy(bar, (long long)m.box0 * m.box1 * 4, [=] {  // lands when somebody waits on `bar` (ptx_emu.h)
+    for (uint32_t r = 0; r < m.box1; ++r)
+      for (uint32_t c = 0; c < m.box0; ++c) {
+        const long long gr = (long long)c1 + r, gc = (long long)c0 + c;
+        float v = 0.f;  // out-of-bounds box elements are zero-filled
+        if (gr >= 0 && gc >= 0 && (uint64_t)gr < m.dim1 && (uint64_t)gc < m.dim0)
+          v = *reinterpret_cast<const float *>(reinterpret_cast<const unsigned char *>(m.base) + (uint64_t)gr * m.stride1_bytes + (uint64_t)gc * 4u);
+        std::memcpy(reinterpret_cast<unsigned char *>(origin + emu_tc::swz128(d0 + r * (m.box0 * 4u) + c * 4u)), &v, 4);
+      }
+  });
 }
 
 inline void tc_fence_before() {}
